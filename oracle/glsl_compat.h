@@ -1,0 +1,351 @@
+// GLSL-in-C++ compatibility layer for the CPU oracle.
+//
+// ORACLE / TEST INFRASTRUCTURE ONLY (see oracle/README.md): nothing under
+// portal_b200/ may include this file.  It lets the reference's GLSL
+// (/root/reference/src/library.glsl, /root/reference/src/frag.glsl and the
+// per-scene snippets stored in scenes/*.ron) be restated as plain C++.
+//
+// GLSL leaves the precision of its built-ins implementation-defined.  The
+// oracle pins ONE conforming numeric profile ("pinned profile")
+// that is reproducible bit-for-bit on any IEEE-754 machine:
+//   * + - * / sqrt are single correctly-rounded IEEE operations, never contracted
+//     (compile with -ffp-contract=off);
+//   * dot(), matN*vecN, cross() and mix() are explicit fused-multiply-add chains
+//     in a fixed order (what every GPU GLSL compiler emits for them);
+//   * inversesqrt(x) = 1/sqrt(x); normalize(v) = v * inversesqrt(dot(v,v));
+//     length(v) = sqrt(dot(v,v));
+//   * min/max/clamp/step/sign/mod/fract follow the GLSL ES 3.00 spec text
+//     (section 8.3) literally, including their behaviour on NaN;
+//   * sin cos tan asin acos atan exp2 log2 pow come from the host libm.
+// PE_REAL selects the arithmetic type: float (the parity reference) or double
+// (used only to flag ill-conditioned pixels).
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#ifndef PE_REAL
+#define PE_REAL float
+#endif
+
+namespace pe_oracle {
+
+typedef PE_REAL real;
+
+static inline real pe_fma(real a, real b, real c) { return std::fma(a, b, c); }
+
+// ------------------------------------------------------------------ scalars
+static inline real radians(real d) { return d * real(0.017453292519943295); }
+static inline real degrees(real r) { return r * real(57.29577951308232); }
+static inline real sin(real x) { return std::sin(x); }
+static inline real cos(real x) { return std::cos(x); }
+static inline real tan(real x) { return std::tan(x); }
+static inline real asin(real x) { return std::asin(x); }
+static inline real acos(real x) { return std::acos(x); }
+static inline real atan(real y, real x) { return std::atan2(y, x); }
+static inline real atan(real x) { return std::atan(x); }
+static inline real pow(real x, real y) { return std::pow(x, y); }
+static inline real exp(real x) { return std::exp(x); }
+static inline real log(real x) { return std::log(x); }
+static inline real exp2(real x) { return std::exp2(x); }
+static inline real log2(real x) { return std::log2(x); }
+static inline real sqrt(real x) { return std::sqrt(x); }
+static inline real inversesqrt(real x) { return real(1) / std::sqrt(x); }
+static inline real abs(real x) { return std::fabs(x); }
+static inline int abs(int x) { return x < 0 ? -x : x; }
+static inline real sign(real x) { return x > real(0) ? real(1) : (x < real(0) ? real(-1) : real(0)); }
+static inline real floor(real x) { return std::floor(x); }
+static inline real ceil(real x) { return std::ceil(x); }
+static inline real fract(real x) { return x - std::floor(x); }
+static inline real mod(real x, real y) { return x - y * std::floor(x / y); }
+static inline real min(real x, real y) { return y < x ? y : x; }
+static inline real max(real x, real y) { return x < y ? y : x; }
+static inline int min(int x, int y) { return y < x ? y : x; }
+static inline int max(int x, int y) { return x < y ? y : x; }
+static inline real clamp(real x, real lo, real hi) { return min(max(x, lo), hi); }
+static inline int clamp(int x, int lo, int hi) { return min(max(x, lo), hi); }
+static inline real mix(real x, real y, real a) { return pe_fma(y, a, x * (real(1) - a)); }
+static inline real step(real edge, real x) { return x < edge ? real(0) : real(1); }
+static inline real smoothstep(real e0, real e1, real x) {
+    real t = clamp((x - e0) / (e1 - e0), real(0), real(1));
+    return t * t * (real(3) - real(2) * t);
+}
+
+// ------------------------------------------------------------------ vectors
+struct vec2;
+struct vec3;
+struct vec4;
+
+#ifndef PE_SWZ_VEC2
+#define PE_SWZ_VEC2
+#endif
+#ifndef PE_SWZ_VEC3
+#define PE_SWZ_VEC3
+#endif
+#ifndef PE_SWZ_VEC4
+#define PE_SWZ_VEC4
+#endif
+
+struct vec2 {
+    union { real x, r, s; };
+    union { real y, g, t; };
+    vec2() : x(0), y(0) {}
+    explicit vec2(real a) : x(a), y(a) {}
+    vec2(real a, real b) : x(a), y(b) {}
+    explicit vec2(const vec3& v);
+    explicit vec2(const vec4& v);
+    real& operator[](int i) { return i == 0 ? x : y; }
+    real operator[](int i) const { return i == 0 ? x : y; }
+    PE_SWZ_VEC2
+};
+
+struct vec3 {
+    union { real x, r, s; };
+    union { real y, g, t; };
+    union { real z, b, p; };
+    vec3() : x(0), y(0), z(0) {}
+    explicit vec3(real a) : x(a), y(a), z(a) {}
+    vec3(real a, real b_, real c) : x(a), y(b_), z(c) {}
+    vec3(const vec2& v, real c) : x(v.x), y(v.y), z(c) {}
+    vec3(real a, const vec2& v) : x(a), y(v.x), z(v.y) {}
+    explicit vec3(const vec4& v);
+    real& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }
+    real operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+    PE_SWZ_VEC3
+};
+
+struct vec4 {
+    union { real x, r, s; };
+    union { real y, g, t; };
+    union { real z, b, p; };
+    union { real w, a, q; };
+    vec4() : x(0), y(0), z(0), w(0) {}
+    explicit vec4(real v) : x(v), y(v), z(v), w(v) {}
+    vec4(real a_, real b_, real c, real d) : x(a_), y(b_), z(c), w(d) {}
+    vec4(const vec3& v, real d) : x(v.x), y(v.y), z(v.z), w(d) {}
+    vec4(real a_, const vec3& v) : x(a_), y(v.x), z(v.y), w(v.z) {}
+    vec4(const vec2& u, const vec2& v) : x(u.x), y(u.y), z(v.x), w(v.y) {}
+    vec4(const vec2& u, real c, real d) : x(u.x), y(u.y), z(c), w(d) {}
+    real& operator[](int i) { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
+    real operator[](int i) const { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
+    PE_SWZ_VEC4
+};
+
+inline vec2::vec2(const vec3& v) : x(v.x), y(v.y) {}
+inline vec2::vec2(const vec4& v) : x(v.x), y(v.y) {}
+inline vec3::vec3(const vec4& v) : x(v.x), y(v.y), z(v.z) {}
+
+
+// vec2
+static inline vec2 operator+(const vec2& a, const vec2& b) { return vec2(a.x + b.x, a.y + b.y); }
+static inline vec2 operator-(const vec2& a, const vec2& b) { return vec2(a.x - b.x, a.y - b.y); }
+static inline vec2 operator*(const vec2& a, const vec2& b) { return vec2(a.x * b.x, a.y * b.y); }
+static inline vec2 operator/(const vec2& a, const vec2& b) { return vec2(a.x / b.x, a.y / b.y); }
+static inline vec2 operator+(const vec2& a, real s) { return vec2(a.x + s, a.y + s); }
+static inline vec2 operator-(const vec2& a, real s) { return vec2(a.x - s, a.y - s); }
+static inline vec2 operator*(const vec2& a, real s) { return vec2(a.x * s, a.y * s); }
+static inline vec2 operator/(const vec2& a, real s) { return vec2(a.x / s, a.y / s); }
+static inline vec2 operator+(real s, const vec2& a) { return vec2(s + a.x, s + a.y); }
+static inline vec2 operator-(real s, const vec2& a) { return vec2(s - a.x, s - a.y); }
+static inline vec2 operator*(real s, const vec2& a) { return vec2(s * a.x, s * a.y); }
+static inline vec2 operator/(real s, const vec2& a) { return vec2(s / a.x, s / a.y); }
+static inline vec2 operator-(const vec2& a) { return vec2(-a.x, -a.y); }
+// vec3
+static inline vec3 operator+(const vec3& a, const vec3& b) { return vec3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline vec3 operator-(const vec3& a, const vec3& b) { return vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline vec3 operator*(const vec3& a, const vec3& b) { return vec3(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline vec3 operator/(const vec3& a, const vec3& b) { return vec3(a.x / b.x, a.y / b.y, a.z / b.z); }
+static inline vec3 operator+(const vec3& a, real s) { return vec3(a.x + s, a.y + s, a.z + s); }
+static inline vec3 operator-(const vec3& a, real s) { return vec3(a.x - s, a.y - s, a.z - s); }
+static inline vec3 operator*(const vec3& a, real s) { return vec3(a.x * s, a.y * s, a.z * s); }
+static inline vec3 operator/(const vec3& a, real s) { return vec3(a.x / s, a.y / s, a.z / s); }
+static inline vec3 operator+(real s, const vec3& a) { return vec3(s + a.x, s + a.y, s + a.z); }
+static inline vec3 operator-(real s, const vec3& a) { return vec3(s - a.x, s - a.y, s - a.z); }
+static inline vec3 operator*(real s, const vec3& a) { return vec3(s * a.x, s * a.y, s * a.z); }
+static inline vec3 operator/(real s, const vec3& a) { return vec3(s / a.x, s / a.y, s / a.z); }
+static inline vec3 operator-(const vec3& a) { return vec3(-a.x, -a.y, -a.z); }
+// vec4
+static inline vec4 operator+(const vec4& a, const vec4& b) { return vec4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+static inline vec4 operator-(const vec4& a, const vec4& b) { return vec4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+static inline vec4 operator*(const vec4& a, const vec4& b) { return vec4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+static inline vec4 operator/(const vec4& a, const vec4& b) { return vec4(a.x / b.x, a.y / b.y, a.z / b.z, a.w / b.w); }
+static inline vec4 operator+(const vec4& a, real s) { return vec4(a.x + s, a.y + s, a.z + s, a.w + s); }
+static inline vec4 operator-(const vec4& a, real s) { return vec4(a.x - s, a.y - s, a.z - s, a.w - s); }
+static inline vec4 operator*(const vec4& a, real s) { return vec4(a.x * s, a.y * s, a.z * s, a.w * s); }
+static inline vec4 operator/(const vec4& a, real s) { return vec4(a.x / s, a.y / s, a.z / s, a.w / s); }
+static inline vec4 operator+(real s, const vec4& a) { return vec4(s + a.x, s + a.y, s + a.z, s + a.w); }
+static inline vec4 operator-(real s, const vec4& a) { return vec4(s - a.x, s - a.y, s - a.z, s - a.w); }
+static inline vec4 operator*(real s, const vec4& a) { return vec4(s * a.x, s * a.y, s * a.z, s * a.w); }
+static inline vec4 operator/(real s, const vec4& a) { return vec4(s / a.x, s / a.y, s / a.z, s / a.w); }
+static inline vec4 operator-(const vec4& a) { return vec4(-a.x, -a.y, -a.z, -a.w); }
+
+#define PE_COMPOUND(V)                                                                      \
+    static inline V& operator+=(V& a, const V& b) { a = a + b; return a; }                  \
+    static inline V& operator-=(V& a, const V& b) { a = a - b; return a; }                  \
+    static inline V& operator*=(V& a, const V& b) { a = a * b; return a; }                  \
+    static inline V& operator/=(V& a, const V& b) { a = a / b; return a; }                  \
+    static inline V& operator+=(V& a, real s) { a = a + s; return a; }                      \
+    static inline V& operator-=(V& a, real s) { a = a - s; return a; }                      \
+    static inline V& operator*=(V& a, real s) { a = a * s; return a; }                      \
+    static inline V& operator/=(V& a, real s) { a = a / s; return a; }
+PE_COMPOUND(vec2)
+PE_COMPOUND(vec3)
+PE_COMPOUND(vec4)
+#undef PE_COMPOUND
+
+static inline bool operator==(const vec2& a, const vec2& b) { return a.x == b.x && a.y == b.y; }
+static inline bool operator==(const vec3& a, const vec3& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+static inline bool operator==(const vec4& a, const vec4& b) { return a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w; }
+static inline bool operator!=(const vec2& a, const vec2& b) { return !(a == b); }
+static inline bool operator!=(const vec3& a, const vec3& b) { return !(a == b); }
+static inline bool operator!=(const vec4& a, const vec4& b) { return !(a == b); }
+
+// geometric built-ins (pinned FMA chains)
+static inline real dot(const vec2& a, const vec2& b) { return pe_fma(a.y, b.y, a.x * b.x); }
+static inline real dot(const vec3& a, const vec3& b) { return pe_fma(a.z, b.z, pe_fma(a.y, b.y, a.x * b.x)); }
+static inline real dot(const vec4& a, const vec4& b) {
+    return pe_fma(a.w, b.w, pe_fma(a.z, b.z, pe_fma(a.y, b.y, a.x * b.x)));
+}
+static inline vec3 cross(const vec3& a, const vec3& b) {
+    return vec3(pe_fma(a.y, b.z, -(a.z * b.y)), pe_fma(a.z, b.x, -(a.x * b.z)), pe_fma(a.x, b.y, -(a.y * b.x)));
+}
+static inline real length(real x) { return abs(x); }
+static inline real length(const vec2& v) { return sqrt(dot(v, v)); }
+static inline real length(const vec3& v) { return sqrt(dot(v, v)); }
+static inline real length(const vec4& v) { return sqrt(dot(v, v)); }
+static inline real distance(const vec2& a, const vec2& b) { return length(a - b); }
+static inline real distance(const vec3& a, const vec3& b) { return length(a - b); }
+static inline real distance(const vec4& a, const vec4& b) { return length(a - b); }
+static inline vec2 normalize(const vec2& v) { return v * inversesqrt(dot(v, v)); }
+static inline vec3 normalize(const vec3& v) { return v * inversesqrt(dot(v, v)); }
+static inline vec4 normalize(const vec4& v) { return v * inversesqrt(dot(v, v)); }
+static inline vec3 reflect(const vec3& i, const vec3& n) { return i - n * (real(2) * dot(n, i)); }
+static inline vec3 refract(const vec3& i, const vec3& n, real eta) {
+    real d = dot(n, i);
+    real k = real(1) - eta * eta * (real(1) - d * d);
+    if (k < real(0)) return vec3(real(0));
+    return i * eta - n * (eta * d + sqrt(k));
+}
+
+// component-wise built-ins
+#define PE_CW1(F)                                                                              \
+    static inline vec2 F(const vec2& v) { return vec2(F(v.x), F(v.y)); }                       \
+    static inline vec3 F(const vec3& v) { return vec3(F(v.x), F(v.y), F(v.z)); }               \
+    static inline vec4 F(const vec4& v) { return vec4(F(v.x), F(v.y), F(v.z), F(v.w)); }
+PE_CW1(sin) PE_CW1(cos) PE_CW1(tan) PE_CW1(asin) PE_CW1(acos) PE_CW1(exp) PE_CW1(log) PE_CW1(exp2) PE_CW1(log2)
+PE_CW1(sqrt) PE_CW1(inversesqrt) PE_CW1(abs) PE_CW1(sign) PE_CW1(floor) PE_CW1(ceil) PE_CW1(fract)
+PE_CW1(radians) PE_CW1(degrees)
+#undef PE_CW1
+#define PE_CW2(F)                                                                                           \
+    static inline vec2 F(const vec2& a, const vec2& b) { return vec2(F(a.x, b.x), F(a.y, b.y)); }           \
+    static inline vec3 F(const vec3& a, const vec3& b) { return vec3(F(a.x, b.x), F(a.y, b.y), F(a.z, b.z)); } \
+    static inline vec4 F(const vec4& a, const vec4& b) { return vec4(F(a.x, b.x), F(a.y, b.y), F(a.z, b.z), F(a.w, b.w)); }
+PE_CW2(mod) PE_CW2(min) PE_CW2(max) PE_CW2(step) PE_CW2(pow) PE_CW2(atan)
+#undef PE_CW2
+#define PE_CW2S(F)                                                                                    \
+    static inline vec2 F(const vec2& a, real b) { return vec2(F(a.x, b), F(a.y, b)); }                \
+    static inline vec3 F(const vec3& a, real b) { return vec3(F(a.x, b), F(a.y, b), F(a.z, b)); }     \
+    static inline vec4 F(const vec4& a, real b) { return vec4(F(a.x, b), F(a.y, b), F(a.z, b), F(a.w, b)); }
+PE_CW2S(mod) PE_CW2S(min) PE_CW2S(max)
+#undef PE_CW2S
+static inline vec2 step(real e, const vec2& v) { return vec2(step(e, v.x), step(e, v.y)); }
+static inline vec3 step(real e, const vec3& v) { return vec3(step(e, v.x), step(e, v.y), step(e, v.z)); }
+static inline vec4 step(real e, const vec4& v) { return vec4(step(e, v.x), step(e, v.y), step(e, v.z), step(e, v.w)); }
+static inline vec2 clamp(const vec2& v, real lo, real hi) { return vec2(clamp(v.x, lo, hi), clamp(v.y, lo, hi)); }
+static inline vec3 clamp(const vec3& v, real lo, real hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
+static inline vec4 clamp(const vec4& v, real lo, real hi) {
+    return vec4(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi), clamp(v.w, lo, hi));
+}
+static inline vec2 clamp(const vec2& v, const vec2& lo, const vec2& hi) { return min(max(v, lo), hi); }
+static inline vec3 clamp(const vec3& v, const vec3& lo, const vec3& hi) { return min(max(v, lo), hi); }
+static inline vec4 clamp(const vec4& v, const vec4& lo, const vec4& hi) { return min(max(v, lo), hi); }
+static inline vec2 mix(const vec2& a, const vec2& b, real t) { return vec2(mix(a.x, b.x, t), mix(a.y, b.y, t)); }
+static inline vec3 mix(const vec3& a, const vec3& b, real t) { return vec3(mix(a.x, b.x, t), mix(a.y, b.y, t), mix(a.z, b.z, t)); }
+static inline vec4 mix(const vec4& a, const vec4& b, real t) {
+    return vec4(mix(a.x, b.x, t), mix(a.y, b.y, t), mix(a.z, b.z, t), mix(a.w, b.w, t));
+}
+static inline vec2 mix(const vec2& a, const vec2& b, const vec2& t) { return vec2(mix(a.x, b.x, t.x), mix(a.y, b.y, t.y)); }
+static inline vec3 mix(const vec3& a, const vec3& b, const vec3& t) {
+    return vec3(mix(a.x, b.x, t.x), mix(a.y, b.y, t.y), mix(a.z, b.z, t.z));
+}
+static inline vec4 mix(const vec4& a, const vec4& b, const vec4& t) {
+    return vec4(mix(a.x, b.x, t.x), mix(a.y, b.y, t.y), mix(a.z, b.z, t.z), mix(a.w, b.w, t.w));
+}
+
+// ----------------------------------------------------------------- matrices
+struct mat4;
+struct mat3 {
+    vec3 c[3];
+    mat3() { c[0] = vec3(1, 0, 0); c[1] = vec3(0, 1, 0); c[2] = vec3(0, 0, 1); }
+    explicit mat3(real d) { c[0] = vec3(d, 0, 0); c[1] = vec3(0, d, 0); c[2] = vec3(0, 0, d); }
+    mat3(const vec3& a, const vec3& b, const vec3& d) { c[0] = a; c[1] = b; c[2] = d; }
+    mat3(real a0, real a1, real a2, real b0, real b1, real b2, real c0, real c1, real c2) {
+        c[0] = vec3(a0, a1, a2); c[1] = vec3(b0, b1, b2); c[2] = vec3(c0, c1, c2);
+    }
+    explicit mat3(const mat4& m);
+    vec3& operator[](int i) { return c[i]; }
+    const vec3& operator[](int i) const { return c[i]; }
+};
+struct mat4 {
+    vec4 c[4];
+    mat4() { c[0] = vec4(1, 0, 0, 0); c[1] = vec4(0, 1, 0, 0); c[2] = vec4(0, 0, 1, 0); c[3] = vec4(0, 0, 0, 1); }
+    explicit mat4(real d) { c[0] = vec4(d, 0, 0, 0); c[1] = vec4(0, d, 0, 0); c[2] = vec4(0, 0, d, 0); c[3] = vec4(0, 0, 0, d); }
+    mat4(const vec4& a, const vec4& b, const vec4& d, const vec4& e) { c[0] = a; c[1] = b; c[2] = d; c[3] = e; }
+    vec4& operator[](int i) { return c[i]; }
+    const vec4& operator[](int i) const { return c[i]; }
+};
+inline mat3::mat3(const mat4& m) { c[0] = vec3(m.c[0]); c[1] = vec3(m.c[1]); c[2] = vec3(m.c[2]); }
+
+static inline vec3 operator*(const mat3& m, const vec3& v) {
+    return vec3(pe_fma(m.c[2].x, v.z, pe_fma(m.c[1].x, v.y, m.c[0].x * v.x)),
+                pe_fma(m.c[2].y, v.z, pe_fma(m.c[1].y, v.y, m.c[0].y * v.x)),
+                pe_fma(m.c[2].z, v.z, pe_fma(m.c[1].z, v.y, m.c[0].z * v.x)));
+}
+static inline vec4 operator*(const mat4& m, const vec4& v) {
+    return vec4(pe_fma(m.c[3].x, v.w, pe_fma(m.c[2].x, v.z, pe_fma(m.c[1].x, v.y, m.c[0].x * v.x))),
+                pe_fma(m.c[3].y, v.w, pe_fma(m.c[2].y, v.z, pe_fma(m.c[1].y, v.y, m.c[0].y * v.x))),
+                pe_fma(m.c[3].z, v.w, pe_fma(m.c[2].z, v.z, pe_fma(m.c[1].z, v.y, m.c[0].z * v.x))),
+                pe_fma(m.c[3].w, v.w, pe_fma(m.c[2].w, v.z, pe_fma(m.c[1].w, v.y, m.c[0].w * v.x))));
+}
+static inline mat4 operator*(const mat4& a, const mat4& b) { return mat4(a * b.c[0], a * b.c[1], a * b.c[2], a * b.c[3]); }
+static inline mat3 operator*(const mat3& a, const mat3& b) { return mat3(a * b.c[0], a * b.c[1], a * b.c[2]); }
+static inline mat3 transpose(const mat3& m) {
+    return mat3(vec3(m.c[0].x, m.c[1].x, m.c[2].x), vec3(m.c[0].y, m.c[1].y, m.c[2].y), vec3(m.c[0].z, m.c[1].z, m.c[2].z));
+}
+static inline mat4 transpose(const mat4& m) {
+    return mat4(vec4(m.c[0].x, m.c[1].x, m.c[2].x, m.c[3].x), vec4(m.c[0].y, m.c[1].y, m.c[2].y, m.c[3].y),
+                vec4(m.c[0].z, m.c[1].z, m.c[2].z, m.c[3].z), vec4(m.c[0].w, m.c[1].w, m.c[2].w, m.c[3].w));
+}
+
+// ----------------------------------------------------------------- textures
+// Pinned sampling rule (macroquad 0.4.14 Texture2D::from_file_with_format defaults,
+// un-vendored: FilterMode::Linear, clamp-to-edge, RGBA8 unorm, row 0 of the file is v = 0):
+// texel centres at (i + 0.5)/size, bilinear weights in `real`, channel value byte/255.
+struct sampler2D {
+    const uint8_t* data;  // RGBA8, row-major, row 0 first
+    int w, h;
+};
+static inline vec4 pe_texel(const sampler2D& s, int ix, int iy) {
+    ix = ix < 0 ? 0 : (ix > s.w - 1 ? s.w - 1 : ix);
+    iy = iy < 0 ? 0 : (iy > s.h - 1 ? s.h - 1 : iy);
+    const uint8_t* p = s.data + 4 * (size_t(iy) * size_t(s.w) + size_t(ix));
+    const real k = real(1) / real(255);
+    return vec4(real(p[0]) * k, real(p[1]) * k, real(p[2]) * k, real(p[3]) * k);
+}
+static inline vec4 texture(const sampler2D& s, const vec2& uv) {
+    if (s.data == nullptr) return vec4(real(0), real(0), real(0), real(1));
+    real x = uv.x * real(s.w) - real(0.5);
+    real y = uv.y * real(s.h) - real(0.5);
+    real x0 = std::floor(x), y0 = std::floor(y);
+    real fx = x - x0, fy = y - y0;
+    // keep the float->int conversion defined for wild coordinates
+    x0 = clamp(x0, real(-2), real(s.w + 1));
+    y0 = clamp(y0, real(-2), real(s.h + 1));
+    int ix = int(x0), iy = int(y0);
+    vec4 c00 = pe_texel(s, ix, iy), c10 = pe_texel(s, ix + 1, iy);
+    vec4 c01 = pe_texel(s, ix, iy + 1), c11 = pe_texel(s, ix + 1, iy + 1);
+    vec4 top = c00 * (real(1) - fx) + c10 * fx;
+    vec4 bot = c01 * (real(1) - fx) + c11 * fx;
+    return top * (real(1) - fy) + bot * fy;
+}
+
+}  // namespace pe_oracle

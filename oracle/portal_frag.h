@@ -1,0 +1,161 @@
+// CPU restatement of the reference's fragment-shader driver (the ray loop).
+//
+// ORACLE / TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+// Follows /root/reference/src/frag.glsl; each function cites its lines.  Included by
+// the generated per-scene translation unit AFTER scene_intersect(), material_process()
+// and scene_intersect_material_process() have been emitted (frag.glsl:19-59 with the
+// generator's sections, /root/reference/src/gui/scene.rs:885-1035, filled in).
+//
+// Variants restated: mono camera, perspective projection, AA loop, darken-by-distance,
+// depth map colouring.  Panini / 360 / 180 / anaglyph / side-by-side and the external-ray
+// probe are SURVEY.md §8(f) "next" rows and are not restated here.
+#pragma once
+
+namespace pe_oracle {
+
+// frag.glsl:74-78
+struct RayTraceResult {
+    vec3 color;
+    real depth;
+    bool has_depth;
+};
+
+// frag.glsl:80-84
+static inline real normalize_depth_value(real depth) {
+    real depth_min = min(_depth_map_min, _depth_map_max);
+    real depth_max = max(_depth_map_min, _depth_map_max);
+    return clamp((depth - depth_min) / max(PE_L(1e-6), depth_max - depth_min), PE_L(0.0), PE_L(1.0));
+}
+
+// frag.glsl:86-99
+static inline vec3 depth_gradient_inferno(real t) {
+    vec3 c0 = sqrvec(vec3(PE_L(0.001462), PE_L(0.000466), PE_L(0.013866)));
+    vec3 c1 = sqrvec(vec3(PE_L(0.258234), PE_L(0.038571), PE_L(0.406485)));
+    vec3 c2 = sqrvec(vec3(PE_L(0.578304), PE_L(0.148039), PE_L(0.404411)));
+    vec3 c3 = sqrvec(vec3(PE_L(0.865006), PE_L(0.316822), PE_L(0.226055)));
+    vec3 c4 = sqrvec(vec3(PE_L(0.987622), PE_L(0.645320), PE_L(0.039886)));
+    vec3 c5 = sqrvec(vec3(PE_L(0.988362), PE_L(0.998364), PE_L(0.644924)));
+
+    if (t < PE_L(0.2)) return mix(c0, c1, t / PE_L(0.2));
+    if (t < PE_L(0.4)) return mix(c1, c2, (t - PE_L(0.2)) / PE_L(0.2));
+    if (t < PE_L(0.6)) return mix(c2, c3, (t - PE_L(0.4)) / PE_L(0.2));
+    if (t < PE_L(0.8)) return mix(c3, c4, (t - PE_L(0.6)) / PE_L(0.2));
+    return mix(c4, c5, (t - PE_L(0.8)) / PE_L(0.2));
+}
+
+// frag.glsl:101-104
+static inline vec3 sample_depth_gradient(real depth) {
+    real t = PE_L(1.0) - normalize_depth_value(depth);
+    return depth_gradient_inferno(t);
+}
+
+// frag.glsl:106-159 (for_prefer_variable = true: the !FOR_VARIABLE! loop header, scene.rs:1076-1077)
+static inline RayTraceResult ray_tracing(Ray r, real camera_scale, int* bounces_out) {
+    // skybox_processing section, scene.rs:1052-1063 (no skybox in the config scenes)
+    vec3 not_found_color = PE_NOT_FOUND_COLOR(r);
+
+    vec3 current_color = vec3(real(1));
+    real all_t = real(0);
+    for (int j = 0; j < _ray_tracing_depth; j++) {
+        if (bounces_out) *bounces_out = j + 1;
+        SceneIntersection i = scene_intersect(r);
+        SceneIntersectionWithMaterial i2 = scene_intersect_material_process(r);
+
+        MaterialProcessing m = material_empty();  // GLSL leaves `m` undefined here (frag.glsl:116)
+        if (nearer(i.hit, i2.scene.hit)) {
+            r.o += r.d * i2.scene.hit.t;
+            all_t += i2.scene.hit.t * r.tmul;
+            if (i2.scene.material == CUSTOM_MATERIAL) {
+                m = i2.material;
+            } else {
+                m = material_process(r, i2.scene);
+            }
+        } else if (i.hit.hit) {
+            r.o += r.d * i.hit.t;
+            all_t += i.hit.t * r.tmul;
+            m = material_process(r, i);
+        }
+
+        if (i.hit.hit || i2.scene.hit.hit) {
+            current_color *= m.mul_to_color;
+            if (m.is_final) {
+                real depth = all_t / max(camera_scale, PE_L(1e-6));
+                if (all_t > _t_start * camera_scale && _darken_by_distance == 1) {
+                    if (all_t > _t_end * camera_scale) all_t = _t_end * camera_scale;
+                    real gray_t = (all_t - _t_start * camera_scale) / (_t_end - _t_start) / camera_scale;
+                    return RayTraceResult{
+                        color(real(0), real(0), real(0)) * sqr(sqr(gray_t)) + current_color * sqr(sqr(PE_L(1.0) - gray_t)), depth,
+                        true};
+                } else {
+                    return RayTraceResult{current_color, depth, true};
+                }
+            } else {
+                r = m.new_ray;
+            }
+        } else {
+            if (r.in_subspace) {
+                return RayTraceResult{color(real(0), real(0), real(0)), PE_L(0.0), false};
+            } else {
+                return RayTraceResult{current_color * not_found_color, PE_L(0.0), false};
+            }
+        }
+    }
+    return RayTraceResult{color(real(0), real(0), real(0)), PE_L(0.0), false};
+}
+
+// frag.glsl:408-464, perspective branch :449-455
+static inline vec3 get_color2(vec2 image_position, const mat4& camera_matrix, bool in_subspace, real camera_scale,
+                              int* bounces_out) {
+    vec4 o = camera_matrix * vec4(real(0), real(0), real(0), real(1));
+    real h = tan(_view_angle / PE_L(2.));
+    vec4 d = normalize(camera_matrix * vec4(image_position.x * h, image_position.y * h, PE_L(1.0), real(0)));
+
+    Ray r = Ray{o, d, PE_L(1.0), in_subspace};
+    RayTraceResult trace = ray_tracing(r, camera_scale, bounces_out);
+    if (_draw_depth_map == 1) {
+        if (trace.has_depth) {
+            return sample_depth_gradient(trace.depth);
+        } else {
+            return vec3(PE_L(0.0));
+        }
+    }
+    return trace.color;
+}
+
+// frag.glsl:466-503, mono path (:474-477, :501); disable_anaglyph = true drops the !ANAGLYPH! lines
+static inline vec3 get_color(vec2 image_position, int* bounces_out) {
+    return get_color2(image_position, _camera, _camera_in_subspace == 1, _camera_scale, bounces_out);
+}
+
+// frag.glsl:506-513
+static inline vec2 quasi_random(int i) {
+    real a1 = PE_L(0.7548776662466927600500267982588025643670318456949186300834636687);
+    real a2 = PE_L(0.5698402909980532659121818632752155853637566123932930564053138358);
+    return vec2(mod(PE_L(0.5) + a1 * real(i), PE_L(1.0)), mod(PE_L(0.5) + a2 * real(i), PE_L(1.0)));
+}
+
+// Vertex shader /root/reference/src/gui/scene.rs:1688-1693 (uv_screen) followed by
+// frag.glsl:515-526, 550-551 (main, _teleport_external_ray == 0).
+// Pixel (px, py) is the fragment whose centre is position.xy = (px + 0.5, py + 0.5);
+// row py = 0 is position.y = 0.5 (framebuffer row convention).
+static inline vec4 shade_pixel(int px, int py, int* bounces_out) {
+    vec2 resolution = vec2(_resolution_x, _resolution_y);
+    vec2 position = vec2(real(px) + PE_L(0.5), real(py) + PE_L(0.5));
+    real coef = min(resolution.x, resolution.y);
+    vec2 uv_screen = (position - resolution / PE_L(2.)) / coef * PE_L(2.);
+
+    vec3 result = vec3(real(0));
+    real pixel_size = PE_L(1.) / min(resolution.x, resolution.y);
+    int worst = 0;
+    for (int a = _aa_start; a < _aa_count + _aa_start; a++) {
+        vec2 offset = quasi_random(a);
+        int b = 0;
+        result += get_color(uv_screen + offset * pixel_size * PE_L(2.), &b);
+        if (b > worst) worst = b;
+    }
+    if (bounces_out) *bounces_out = worst;
+    result = sqrt(result / real(_aa_count));
+    return vec4(result, PE_L(1.));
+}
+
+}  // namespace pe_oracle

@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Regenerate the committed golden fixtures from the reference's scene files.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tools/export_golden.py
+
+Writes, for each BASELINE.json config scene:
+  tests/golden/scenes/<scene>.scene.json    scene IR: objects / materials / snippets (the
+                                            scene's own GLSL, i.e. benchmark *input data*), the
+                                            evaluated uniform table (f64), saved camera
+  tests/golden/scenes/<scene>.textures.npz  decoded RGBA8 texels of the scene's textures
+  tests/golden/frames/<scene>_<W>x<H>_d<D>.npz   oracle (strict f32) framebuffer + sha256
+The front-end used is the ORACLE's (oracle/frontend.py); the product's C++ front-end is
+checked against these files by tests/test_host_frontend.py.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import frontend, runner  # noqa: E402
+
+REF = "/root/reference"
+SCENES = ["basics", "monoportal", "triple_portal", "portal_in_portal", "mobius_monoportal"]
+# (W, H, depth): reduced-size pins; depth as in BASELINE.json configs
+FRAMES = {
+    "basics": (256, 256, 4),
+    "monoportal": (160, 90, 20),
+    "triple_portal": (160, 90, 40),
+    "portal_in_portal": (160, 90, 40),
+    "mobius_monoportal": (160, 90, 64),
+}
+
+
+def main():
+    from PIL import Image
+
+    os.makedirs(os.path.join(ROOT, "tests/golden/scenes"), exist_ok=True)
+    os.makedirs(os.path.join(ROOT, "tests/golden/frames"), exist_ok=True)
+    for name in SCENES:
+        scene = frontend.load_scene(f"{REF}/scenes/{name}.ron")
+        ir = frontend.scene_ir(scene, name)
+        with open(os.path.join(ROOT, f"tests/golden/scenes/{name}.scene.json"), "w") as f:
+            json.dump(ir, f, indent=1)
+        tex = {}
+        for t in ir["textures"]:
+            im = Image.open(os.path.join(REF, t["path"])).convert("RGBA")
+            tex[t["name"]] = np.asarray(im, dtype=np.uint8)
+        tpath = os.path.join(ROOT, f"tests/golden/scenes/{name}.textures.npz")
+        if tex:
+            np.savez_compressed(tpath, **tex)
+        elif os.path.exists(tpath):
+            os.remove(tpath)
+        w, h, d = FRAMES[name]
+        orc = runner.Oracle(ir, "strict", textures=tex)
+        img = orc.render(w, h, d)
+        digest = hashlib.sha256(img.tobytes()).hexdigest()
+        np.savez_compressed(os.path.join(ROOT, f"tests/golden/frames/{name}_{w}x{h}_d{d}.npz"), frame=img,
+                            sha256=np.array(digest))
+        print(f"{name}: {len(ir['objects'])} objects, {len(ir['uniforms'])} uniforms, frame {w}x{h} d{d} sha256 {digest[:16]}")
+
+
+if __name__ == "__main__":
+    main()
