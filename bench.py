@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixels/s of the portal ray loop on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one frame of the headline workload (portal_in_portal, 3840x2160, depth 40, saved
+camera, aa 1): uniform upload + ONE launch of the scene's sm_100a ray-loop kernel (+ for N > 1 the
+NCCL gather of the row strips and the de-interleave kernel on rank 0).  `value` is timed with CUDA
+events on the launching stream with the scene resident on the GPU; `e2e` goes through the
+reference-facing call (render_frame's product: RGBA8 pixels in HOST memory) and includes the
+host->device uniform upload and the device->host readback every step.
+`--impl reference` times the CPU oracle (oracle/, the restatement of the reference's GLSL path --
+the reference has no CPU implementation and cannot be built here) on the host
+cores, on a bounded sample of the same frame.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SCENE_DIR = os.path.join(ROOT, "tests", "golden", "scenes")
+WORKLOADS = {  # BASELINE.json configs
+    "portal_in_portal": (3840, 2160, 40),
+    "triple_portal": (3840, 2160, 40),
+    "monoportal": (1920, 1080, 20),
+    "mobius_monoportal": (7680, 4320, 64),
+    "basics": (256, 256, 4),
+}
+STRIP_ROWS = 16
+METRIC = "Mpixels/s @ 3840x2160 depth-40 portal_in_portal"
+
+
+def load_ir(scene):
+    with open(os.path.join(SCENE_DIR, f"{scene}.scene.json")) as f:
+        return json.load(f)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.proc = None
+        self.path = f"/tmp/_pe_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], None, set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx = float(p[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU oracle legs
+def cpu_oracle_rate(scene, w, h, depth, budget_s=20.0, threads=0):
+    """Mpx/s of the oracle's fast build on a bounded sample: bands of 16 rows spread over the frame."""
+    from oracle import runner
+    tex = runner.load_texture_npz(os.path.join(SCENE_DIR, f"{scene}.textures.npz"))
+    orc = runner.Oracle(load_ir(scene), "fast", textures=tex)
+    cores = threads or (os.cpu_count() or 1)
+    n_bands = 4
+    t0 = time.perf_counter()
+    orc.render(w, h, depth, rows=(h // 2, h // 2 + 16), threads=cores)  # calibrate + warm
+    per_band = max(time.perf_counter() - t0, 1e-4)
+    n_bands = int(max(4, min(h // 16, budget_s / per_band)))
+    starts = [int(i * (h - 16) / max(n_bands - 1, 1)) // 1 for i in range(n_bands)]
+    t0 = time.perf_counter()
+    px = 0
+    for s in starts:
+        orc.render(w, h, depth, rows=(s, s + 16), threads=cores)
+        px += 16 * w
+    dt = time.perf_counter() - t0
+    return px / dt / 1e6, cores, f"{n_bands} bands x 16 rows of the {w}x{h} frame ({px} px, {dt:.1f} s)"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w, h, depth = args.width, args.height, args.depth
+    rates = []
+    for _ in range(args.warmup):
+        cpu_oracle_rate(args.scene, w, h, depth, budget_s=1.0)
+    t0 = time.perf_counter()
+    sample = ""
+    for _ in range(args.steps):
+        r, cores, sample = cpu_oracle_rate(args.scene, w, h, depth, budget_s=max(2.0, 60.0 / max(args.steps, 1)))
+        rates.append(r)
+    dt = time.perf_counter() - t0
+    v = sum(rates) / len(rates)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "Mpixels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(w * h / (v * 1e6) * 1e3, 3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, saved camera, aa 1"},
+        "cpu_baseline": {"value": round(v, 4), "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 4), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": f"CPU oracle (restatement of the reference's GLSL path; the reference itself has no CPU path); wall {dt:.1f} s",
+    }))
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from portal_b200.renderer import SceneRenderer, load_textures
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w, h, depth = args.width, args.height, args.depth
+    ir = load_ir(args.scene)
+    r = SceneRenderer(ir, textures=load_textures(os.path.join(SCENE_DIR, f"{args.scene}.textures.npz")), device=local,
+                      persistent=bool(args.persistent))
+    r.render_depth = depth
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    if world == 1:
+        target = r.full_target(w, h)
+        outs = [torch.empty((h, w, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
+        gathered = None
+    else:
+        target = SceneRenderer.strip_target(w, h, STRIP_ROWS, rank, world)
+        spr = max(SceneRenderer.strip_target(w, h, STRIP_ROWS, k, world).n_strips for k in range(world))
+        outs = [torch.zeros((spr, STRIP_ROWS, w, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
+        gathered = torch.empty((world, spr, STRIP_ROWS, w, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+        frame = torch.empty((h, w, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+
+    def step(i):
+        out = outs[i & 1]
+        r.draw_texture(target, out.data_ptr(), 0, sptr)
+        if world > 1:
+            dist.gather(out, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+            if rank == 0:
+                rc = r._lib.pe_deinterleave_strips(r._ctx, gathered.data_ptr(), frame.data_ptr(), w, h, STRIP_ROWS, world,
+                                                   gathered.shape[1], sptr)
+                assert rc == 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    # ---- timed region: K steps, device time, max over ranks
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = r.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        kev[i][0].record(stream)
+        r.draw_texture(target, outs[i & 1].data_ptr(), 0, sptr)
+        kev[i][1].record(stream)
+        if world > 1:
+            out = outs[i & 1]
+            dist.gather(out, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+            if rank == 0:
+                r._lib.pe_deinterleave_strips(r._ctx, gathered.data_ptr(), frame.data_ptr(), w, h, STRIP_ROWS, world,
+                                              gathered.shape[1], sptr)
+    ev[1].record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = r.launch_count() - l0
+    ms = torch.tensor([ev[0].elapsed_time(ev[1])], dtype=torch.float64, device="cuda")
+    kms = torch.tensor([sum(a.elapsed_time(b) for a, b in kev) / args.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = float(ms.item()), float(kms.item())
+
+    # ---- e2e: the reference-facing call with HOST buffers (RGBA8 readback = get_texture_data)
+    e2e_steps = max(3, min(args.steps, 20))
+    host8 = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
+    cam = r.cam
+    n_px_local = int(C.c_size_t(r._lib.pe_target_pixels(C.byref(target))).value)
+
+    def e2e_step(i):
+        r.set_cam(cam["look_at"], cam["alpha"], cam["beta"], cam["r"])   # per-frame host work: camera -> _camera
+        if world == 1:
+            r.render_host_ptr(w, h, host8.data_ptr(), rgba8=True)
+        else:
+            out = outs[i & 1]
+            r.draw_texture(target, out.data_ptr(), 0, sptr)
+            dist.gather(out, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+            if rank == 0:
+                r._lib.pe_deinterleave_strips(r._ctx, gathered.data_ptr(), frame.data_ptr(), w, h, STRIP_ROWS, world,
+                                              gathered.shape[1], sptr)
+                q = e2e_step.q8
+                r._lib.pe_quantize_rgba8(r._ctx, frame.data_ptr(), q.data_ptr(), w * h, sptr)
+                host8.copy_(q, non_blocking=True)
+            torch.cuda.synchronize()
+    e2e_step.q8 = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda") if (rank == 0 and world > 1) else None
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_rate = w * h * e2e_steps / float(e2e_s.item()) / 1e6
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        value = w * h * args.steps / (total_ms * 1e-3) / 1e6
+        # roofline of the dominant kernel (pe_render_kernel): algorithmic bytes = 16 B/pixel written
+        #  x pixels one launch shades, / its mean launch duration (CUDA events)
+        alg_bytes = 16.0 * n_px_local if world > 1 else 16.0 * w * h
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(f"{args.scene}_{w}x{h}_d{depth}")
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_oracle_rate(args.scene, w, h, depth, budget_s=20.0)
+            cpu = {"value": round(v, 4), "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample}
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, saved camera, aa 1 (BASELINE configs[3])",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} GPUs x cyclic {STRIP_ROWS}-row strips + 1 NCCL gather",
+                       "scheduler": "persistent warps + per-bounce refill" if args.persistent else "one thread per pixel, 8x4 warp tiles",
+                       "l2": "each step writes a 132.7 MB frame (> 126 MB L2) into alternating buffers; inputs are a <8 KB constant block"},
+            "kernel_ms": round(kernel_ms, 4),
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": round(achieved / peaks["hbm_gbs"], 5), "traffic": traffic, "peak_source": peak_src,
+                         "note": "16 B/pixel algorithmic; the loop is fp32-ALU/latency bound, see DESIGN.md §6"},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_rate, 2), "unit": "Mpixels/s", "h2d_bytes_per_step": e2e_h2d_bytes(r),
+                    "d2h_bytes_per_step": w * h * 4, "steps": e2e_steps,
+                    "call": "pe_render_host_rgba8 (RGBA8 into pinned host memory)" if world == 1 else
+                            "pe_render + NCCL gather + pe_deinterleave_strips + pe_quantize_rgba8 + D2H on rank 0"},
+            "gpu_launches": int(launches),
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def e2e_h2d_bytes(r):
+    """Bytes of the constant uniform block uploaded every step (scene matrices + camera + scalars)."""
+    src = r.source()
+    import re
+    m = re.search(r"sizeof\(PeConstBlock\) == (\d+)", src)
+    return int(m.group(1)) if m else 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="portal_in_portal")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--depth", type=int, default=0)
+    ap.add_argument("--persistent", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w, h, d = WORKLOADS[args.scene]
+    args.width, args.height, args.depth = args.width or w, args.height or h, args.depth or d
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

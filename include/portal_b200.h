@@ -1,0 +1,157 @@
+/* portal_b200 -- C ABI of the B200-native renderer for optozorax/portal's per-pixel ray loop.
+ *
+ * This is the drop-in boundary.  In the reference the renderer
+ * (`SceneRenderer`, /root/reference/src/main.rs:732-1976) talks to the GPU through a
+ * macroquad `Material`:
+ *
+ *   load_material(fragment GLSL, MaterialParams{uniforms, textures})   src/gui/scene.rs:1132-1143
+ *   material.set_uniform(name, mat4 | f32 | i32 | (f32,f32))           src/gui/scene.rs:587-656,
+ *                                                                      src/main.rs:1266-1359
+ *   material.set_texture(name, Texture2D)                              src/main.rs:1066-1098
+ *   gl_use_material + draw_rectangle(0,0,w,h) into a render target     src/main.rs:1411-1428
+ *   render_target.texture.get_texture_data() -> RGBA8                  src/main.rs:2939-2943
+ *
+ * The functions below replace exactly those five operations.  The scene is handed over in
+ * the same decomposition the reference's shader generator walks (objects, materials,
+ * intersection materials, library: src/gui/scene.rs:693-1110) with the user's GLSL
+ * snippets as text; this library generates the sm_100a program from them (NVRTC) instead
+ * of a GLSL fragment shader.  Plain pointers and sizes only; one context per host thread
+ * and GPU; all functions return 0 on success, non-zero on failure (see pe_last_error).
+ */
+#ifndef PORTAL_B200_H
+#define PORTAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PE_API __attribute__((visibility("default")))
+#else
+#define PE_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pe_ctx pe_ctx;
+
+/* ---- context ------------------------------------------------------------------------- */
+
+/* device >= 0: CUDA device ordinal.  device < 0: compile-only context (program generation and
+ * NVRTC work without a GPU; pe_render* fail loudly).  Returns NULL on failure. */
+PE_API pe_ctx* pe_create(int device);
+PE_API void pe_destroy(pe_ctx* ctx);
+/* Message of the last failed call on this context (never NULL). With ctx == NULL: why the last
+ * pe_create failed. */
+PE_API const char* pe_last_error(pe_ctx* ctx);
+/* ABI version of this header: major * 100 + minor. */
+PE_API int pe_abi_version(void);
+
+/* ---- scene program  (replaces load_material, src/gui/scene.rs:1112-1176) ----------------- */
+
+enum { PE_SUBSPACE_NORMAL = 0, PE_SUBSPACE_SUBSPACE = 1, PE_SUBSPACE_BOTH = 2 }; /* src/gui/object.rs:39-45 */
+enum { PE_UNIFORM_MAT4 = 0, PE_UNIFORM_FLOAT = 1, PE_UNIFORM_INT = 2 };          /* src/gui/scene.rs:673-677 */
+
+/* Start describing a new scene program; discards the previous description. */
+PE_API int pe_scene_begin(pe_ctx* ctx);
+/* User library code, in scene order (src/gui/scene.rs:1037-1044). */
+PE_API int pe_scene_add_library(pe_ctx* ctx, const char* name, const char* glsl);
+/* Materials in scene order; ids are USER_MATERIAL_OFFSET + k (src/gui/scene.rs:720-780). */
+PE_API int pe_scene_add_material_simple(pe_ctx* ctx, const char* name, const double color[3], double normal_coef, int grid,
+                                 double grid_scale, double grid_coef, int grid2, int grid3);
+PE_API int pe_scene_add_material_reflect(pe_ctx* ctx, const char* name, const double add_to_color[3]);
+PE_API int pe_scene_add_material_refract(pe_ctx* ctx, const char* name, const double add_to_color[3], double refractive_index);
+PE_API int pe_scene_add_material_complex(pe_ctx* ctx, const char* name, const char* glsl);
+/* Objects in scene order (src/gui/scene.rs:847-1009).  matrix_b == NULL: ObjectType::Simple(matrix_a),
+ * otherwise ObjectType::Portal(matrix_a, matrix_b).  Matrix names are the uniform stems
+ * (`<name>_mat`, `<name>_mat_inv`, `<a>_to_<b>_mat_teleport`: src/gui/object.rs:18-30). */
+PE_API int pe_scene_add_object_flat(pe_ctx* ctx, const char* name, int subspace, const char* matrix_a, const char* matrix_b,
+                             const char* is_inside_glsl);
+PE_API int pe_scene_add_object_complex(pe_ctx* ctx, const char* name, int subspace, const char* matrix_a, const char* matrix_b,
+                                const char* intersect_glsl);
+PE_API int pe_scene_add_object_debug_matrix(pe_ctx* ctx, const char* name, const char* matrix);
+/* Intersection materials in scene order (src/gui/scene.rs:1011-1035). */
+PE_API int pe_scene_add_intersection_material(pe_ctx* ctx, const char* name, const char* glsl);
+/* Uniform table (src/gui/scene.rs:424-495): full GLSL names, e.g. "a_mat", "a_mat_inv", "progress_u".
+ * The renderer's `_`-prefixed uniforms (src/gui/scene.rs:497-535) are built in and need no declaration. */
+PE_API int pe_scene_declare_uniform(pe_ctx* ctx, const char* name, int type);
+/* Texture samplers, name without the `_tex` suffix (src/gui/texture.rs:12-16). */
+PE_API int pe_scene_declare_texture(pe_ctx* ctx, const char* name);
+/* Generate + compile the program for sm_100a.  Integer uniforms are specialisation constants:
+ * the program is compiled for their current values and transparently re-specialised (cached)
+ * when pe_render* sees different ones.  On failure pe_last_error holds the compiler log with
+ * each message attributed to the scene element that owns the snippet and its local line
+ * (the role of src/shader_error_parser.rs + src/code_generation.rs:36-43). */
+PE_API int pe_scene_compile(pe_ctx* ctx);
+/* Generated CUDA source / compiled cubin of the current specialisation (valid until the next
+ * compile); for inspection, caching and cuobjdump. */
+PE_API const char* pe_scene_source(pe_ctx* ctx);
+PE_API int pe_scene_cubin(pe_ctx* ctx, const void** data, size_t* size);
+/* Options: "persistent" (0/1, default 0), "specialize_ints" (0/1, default 1), "block_threads",
+ * "min_blocks", "lineinfo" (0/1, default 1).  Set before pe_scene_compile. */
+PE_API int pe_set_option(pe_ctx* ctx, const char* key, int value);
+
+/* ---- uniforms and textures  (replace material.set_uniform / set_texture) ------------------ */
+
+PE_API int pe_set_uniform_mat4(pe_ctx* ctx, const char* name, const float column_major[16]);
+PE_API int pe_set_uniform_f32(pe_ctx* ctx, const char* name, float value);
+PE_API int pe_set_uniform_i32(pe_ctx* ctx, const char* name, int32_t value);
+/* Bulk form of the above for the per-frame upload: n names with one value record each. */
+PE_API int pe_set_uniforms_mat4(pe_ctx* ctx, int n, const char* const* names, const float* column_major_16n);
+/* RGBA8 texels, row 0 first (what Texture2D::from_file_with_format holds, src/main.rs:1075). */
+PE_API int pe_set_texture(pe_ctx* ctx, const char* name, const uint8_t* rgba8, int width, int height);
+
+/* ---- render  (replaces gl_use_material + draw_rectangle + get_texture_data) --------------- */
+
+/* Which rows of the frame this call renders: `n_strips` strips of `strip_rows` rows; local
+ * strip k is global strip strip_first + k * strip_step.  Whole frame on one GPU:
+ * {w, h, h, 0, 1, 1, 1}.  Cyclic sharding over G GPUs, rank r: strip_first = r, strip_step = G. */
+typedef struct pe_target {
+    int32_t width, height;       /* full frame, `_resolution` */
+    int32_t strip_rows;          /* rows per strip */
+    int32_t strip_first;         /* first global strip of this call */
+    int32_t strip_step;          /* distance between consecutive strips of this call */
+    int32_t n_strips;            /* strips rendered by this call */
+    int32_t full_frame_layout;   /* 1: `out` holds the full frame; 0: only this call's rows, compacted */
+} pe_target;
+
+/* Number of pixels a target's compact output holds. */
+PE_API size_t pe_target_pixels(const pe_target* t);
+/* Asynchronous render into DEVICE memory (float RGBA, 16 B/pixel: the value the reference's
+ * shader writes to FragColor, src/frag.glsl:526,551, before the render target quantises it).
+ * `stream` is a cudaStream_t or NULL for the context's own stream.  `out_device` may be a
+ * peer-mapped pointer (see pe_ipc_*). `bounces_device` (int32 per pixel) may be NULL. */
+PE_API int pe_render(pe_ctx* ctx, const pe_target* target, void* out_device, void* bounces_device, void* stream);
+/* Synchronous render into HOST memory, device->host copy included (float RGBA). */
+PE_API int pe_render_host(pe_ctx* ctx, const pe_target* target, float* out_host);
+/* Same, quantised to RGBA8 as the reference's render target + get_texture_data deliver it. */
+PE_API int pe_render_host_rgba8(pe_ctx* ctx, const pe_target* target, uint8_t* out_host);
+PE_API int pe_sync(pe_ctx* ctx);
+/* Number of kernel launches this context has issued (render + helper kernels). */
+PE_API uint64_t pe_launch_count(pe_ctx* ctx);
+
+/* ---- multi-GPU helpers -------------------------------------------------------------------- */
+
+/* De-interleave strips gathered rank-major ([rank][local strip][row][x], every rank padded to
+ * `strips_per_rank` strips) into a row-major frame.  Device pointers; async on `stream`. */
+PE_API int pe_deinterleave_strips(pe_ctx* ctx, const void* gathered_device, void* frame_device, int width, int height,
+                           int strip_rows, int n_ranks, int strips_per_rank, void* stream);
+/* CUDA IPC: let another process's render kernel store its pixels straight into this GPU's
+ * frame over NVLink.  handle_out/handle_in are 64-byte cudaIpcMemHandle_t blobs. */
+PE_API int pe_ipc_export(pe_ctx* ctx, void* device_ptr, uint8_t handle_out[64]);
+PE_API int pe_ipc_open(pe_ctx* ctx, const uint8_t handle_in[64], void** device_ptr_out);
+PE_API int pe_ipc_close(pe_ctx* ctx, void* device_ptr);
+
+/* ---- frame post-processing (the offline `render` caller, src/main.rs:640-722) -------------- */
+
+/* Motion-blur average of n RGBA8 frames in gamma-2 space (average_images). Device pointers. */
+PE_API int pe_average_frames_rgba8(pe_ctx* ctx, const void* const* frames_device, int n_frames, void* out_device,
+                            size_t n_pixels, void* stream);
+/* float RGBA -> RGBA8, the render target's quantisation. Device pointers. */
+PE_API int pe_quantize_rgba8(pe_ctx* ctx, const void* rgba_f32_device, void* rgba8_device, size_t n_pixels, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PORTAL_B200_H */

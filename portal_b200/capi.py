@@ -1,0 +1,95 @@
+"""ctypes binding of the portal_b200 C ABI (include/portal_b200.h).
+
+This is plumbing only: every call goes straight into libportal_b200.so.  There is no Python or
+CPU fallback for rendering -- if the library (or a CUDA device) is missing, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libportal_b200.so")
+
+PE_SUBSPACE = {"Normal": 0, "Subspace": 1, "Both": 2}
+PE_UNIFORM_MAT4, PE_UNIFORM_FLOAT, PE_UNIFORM_INT = 0, 1, 2
+
+
+class PeTarget(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("strip_rows", C.c_int32), ("strip_first", C.c_int32),
+                ("strip_step", C.c_int32), ("n_strips", C.c_int32), ("full_frame_layout", C.c_int32)]
+
+
+class PortalB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libportal_b200.so (built in-tree by `python -m portal_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PortalB200Error(
+            f"{LIB_PATH} is missing: build it with `python -m portal_b200.build` (there is no fallback path)")
+    L = C.CDLL(LIB_PATH)
+    vp, cp, i32 = C.c_void_p, C.c_char_p, C.c_int
+    dbl3 = C.POINTER(C.c_double)
+    sig = {
+        "pe_create": (vp, [i32]),
+        "pe_destroy": (None, [vp]),
+        "pe_last_error": (cp, [vp]),
+        "pe_abi_version": (i32, []),
+        "pe_scene_begin": (i32, [vp]),
+        "pe_scene_add_library": (i32, [vp, cp, cp]),
+        "pe_scene_add_material_simple": (i32, [vp, cp, dbl3, C.c_double, i32, C.c_double, C.c_double, i32, i32]),
+        "pe_scene_add_material_reflect": (i32, [vp, cp, dbl3]),
+        "pe_scene_add_material_refract": (i32, [vp, cp, dbl3, C.c_double]),
+        "pe_scene_add_material_complex": (i32, [vp, cp, cp]),
+        "pe_scene_add_object_flat": (i32, [vp, cp, i32, cp, cp, cp]),
+        "pe_scene_add_object_complex": (i32, [vp, cp, i32, cp, cp, cp]),
+        "pe_scene_add_object_debug_matrix": (i32, [vp, cp, cp]),
+        "pe_scene_add_intersection_material": (i32, [vp, cp, cp]),
+        "pe_scene_declare_uniform": (i32, [vp, cp, i32]),
+        "pe_scene_declare_texture": (i32, [vp, cp]),
+        "pe_scene_compile": (i32, [vp]),
+        "pe_scene_source": (cp, [vp]),
+        "pe_scene_cubin": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+        "pe_set_option": (i32, [vp, cp, i32]),
+        "pe_set_uniform_mat4": (i32, [vp, cp, C.POINTER(C.c_float)]),
+        "pe_set_uniform_f32": (i32, [vp, cp, C.c_float]),
+        "pe_set_uniform_i32": (i32, [vp, cp, C.c_int32]),
+        "pe_set_uniforms_mat4": (i32, [vp, i32, C.POINTER(cp), C.POINTER(C.c_float)]),
+        "pe_set_texture": (i32, [vp, cp, vp, i32, i32]),
+        "pe_target_pixels": (C.c_size_t, [C.POINTER(PeTarget)]),
+        "pe_render": (i32, [vp, C.POINTER(PeTarget), vp, vp, vp]),
+        "pe_render_host": (i32, [vp, C.POINTER(PeTarget), vp]),
+        "pe_render_host_rgba8": (i32, [vp, C.POINTER(PeTarget), vp]),
+        "pe_sync": (i32, [vp]),
+        "pe_launch_count": (C.c_uint64, [vp]),
+        "pe_deinterleave_strips": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        "pe_ipc_export": (i32, [vp, vp, vp]),
+        "pe_ipc_open": (i32, [vp, vp, C.POINTER(vp)]),
+        "pe_ipc_close": (i32, [vp, vp]),
+        "pe_average_frames_rgba8": (i32, [vp, C.POINTER(vp), i32, vp, C.c_size_t, vp]),
+        "pe_quantize_rgba8": (i32, [vp, vp, vp, C.c_size_t, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def exported_symbols():
+    """Names bound above (tests compare them with include/portal_b200.h)."""
+    lib()
+    return sorted(n for n in dir(_lib) if n.startswith("pe_"))
+
+
+def b(s: str) -> bytes:
+    return s.encode("utf-8")

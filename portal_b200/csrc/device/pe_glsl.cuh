@@ -1,0 +1,344 @@
+// portal_b200 device layer 1/3: GLSL value types and built-ins for sm_100a.
+//
+// Compiled at scene-load time by NVRTC (-default-device, --std=c++20, --fmad=false) together with
+// the scene's own GLSL snippets, which the reference stores in its .ron files and feeds to the GL
+// driver (/root/reference/src/gui/scene.rs:1112-1176).  This header is what replaces "the GL
+// driver's GLSL front-end" for those snippets on a B200.
+//
+// Numeric profile: GLSL leaves built-in precision implementation-defined; we pin it
+// so that results are reproducible bit-for-bit against the CPU oracle:
+//   * + - * / sqrt : IEEE round-to-nearest, never contracted (NVRTC --fmad=false, prec-div/sqrt on);
+//   * dot, matN*vecN, cross, mix : explicit FFMA chains in a fixed order (fmaf);
+//   * inversesqrt(x) = 1/sqrt(x), normalize(v) = v * inversesqrt(dot(v,v)), length = sqrt(dot);
+//   * min/max/clamp/step/sign/mod/fract : GLSL ES 3.00 §8.3 text, literally (NaN behaviour included);
+//   * sin cos tan asin acos atan exp2 log2 pow : CUDA libdevice.
+// All matrices a scene uses live in constant memory (one uniform block, <= 6 KB): every lane of a
+// warp reads the same matrix element at the same time, so each element is a constant-bank operand
+// of the FFMA that consumes it -- no load instruction, no shared-memory staging, no bank conflicts.
+#pragma once
+
+namespace pe {
+
+#define PE_FI __forceinline__
+
+// ------------------------------------------------------------------ scalars
+PE_FI float radians(float d) { return d * 0.017453292519943295f; }
+PE_FI float degrees(float r) { return r * 57.29577951308232f; }
+PE_FI float sin(float x) { return ::sinf(x); }
+PE_FI float cos(float x) { return ::cosf(x); }
+PE_FI float tan(float x) { return ::tanf(x); }
+PE_FI float asin(float x) { return ::asinf(x); }
+PE_FI float acos(float x) { return ::acosf(x); }
+PE_FI float atan(float y, float x) { return ::atan2f(y, x); }
+PE_FI float atan(float x) { return ::atanf(x); }
+PE_FI float pow(float x, float y) { return ::powf(x, y); }
+PE_FI float exp(float x) { return ::expf(x); }
+PE_FI float log(float x) { return ::logf(x); }
+PE_FI float exp2(float x) { return ::exp2f(x); }
+PE_FI float log2(float x) { return ::log2f(x); }
+PE_FI float sqrt(float x) { return ::sqrtf(x); }
+PE_FI float inversesqrt(float x) { return 1.0f / ::sqrtf(x); }
+PE_FI float abs(float x) { return ::fabsf(x); }
+PE_FI int abs(int x) { return x < 0 ? -x : x; }
+PE_FI float sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+PE_FI float floor(float x) { return ::floorf(x); }
+PE_FI float ceil(float x) { return ::ceilf(x); }
+PE_FI float fract(float x) { return x - ::floorf(x); }
+PE_FI float mod(float x, float y) { return x - y * ::floorf(x / y); }
+PE_FI float min(float x, float y) { return y < x ? y : x; }
+PE_FI float max(float x, float y) { return x < y ? y : x; }
+PE_FI int min(int x, int y) { return y < x ? y : x; }
+PE_FI int max(int x, int y) { return x < y ? y : x; }
+PE_FI float clamp(float x, float lo, float hi) { return min(max(x, lo), hi); }
+PE_FI int clamp(int x, int lo, int hi) { return min(max(x, lo), hi); }
+PE_FI float mix(float x, float y, float a) { return ::fmaf(y, a, x * (1.0f - a)); }
+PE_FI float step(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
+PE_FI float smoothstep(float e0, float e1, float x) {
+    float t = clamp((x - e0) / (e1 - e0), 0.0f, 1.0f);
+    return t * t * (3.0f - 2.0f * t);
+}
+
+// ------------------------------------------------------------------ vectors
+struct vec2;
+struct vec3;
+struct vec4;
+
+#ifndef PE_SWZ_VEC2
+#define PE_SWZ_VEC2
+#endif
+#ifndef PE_SWZ_VEC3
+#define PE_SWZ_VEC3
+#endif
+#ifndef PE_SWZ_VEC4
+#define PE_SWZ_VEC4
+#endif
+
+// Component aliases (x/r/s ...) are anonymous unions of floats: standard C++, and each vector
+// still scalarises into registers.
+struct vec2 {
+    union { float x, r, s; };
+    union { float y, g, t; };
+    PE_FI vec2() : x(0.0f), y(0.0f) {}
+    PE_FI explicit vec2(float a) : x(a), y(a) {}
+    PE_FI vec2(float a, float b) : x(a), y(b) {}
+    PE_FI explicit vec2(const vec3& v);
+    PE_FI explicit vec2(const vec4& v);
+    PE_FI float& operator[](int i) { return i == 0 ? x : y; }
+    PE_FI float operator[](int i) const { return i == 0 ? x : y; }
+    PE_SWZ_VEC2
+};
+struct vec3 {
+    union { float x, r, s; };
+    union { float y, g, t; };
+    union { float z, b, p; };
+    PE_FI vec3() : x(0.0f), y(0.0f), z(0.0f) {}
+    PE_FI explicit vec3(float a) : x(a), y(a), z(a) {}
+    PE_FI vec3(float a, float b_, float c) : x(a), y(b_), z(c) {}
+    PE_FI vec3(const vec2& v, float c) : x(v.x), y(v.y), z(c) {}
+    PE_FI vec3(float a, const vec2& v) : x(a), y(v.x), z(v.y) {}
+    PE_FI explicit vec3(const vec4& v);
+    PE_FI float& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }
+    PE_FI float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+    PE_SWZ_VEC3
+};
+struct vec4 {
+    union { float x, r, s; };
+    union { float y, g, t; };
+    union { float z, b, p; };
+    union { float w, a, q; };
+    PE_FI vec4() : x(0.0f), y(0.0f), z(0.0f), w(0.0f) {}
+    PE_FI explicit vec4(float v) : x(v), y(v), z(v), w(v) {}
+    PE_FI vec4(float a_, float b_, float c, float d) : x(a_), y(b_), z(c), w(d) {}
+    PE_FI vec4(const vec3& v, float d) : x(v.x), y(v.y), z(v.z), w(d) {}
+    PE_FI vec4(float a_, const vec3& v) : x(a_), y(v.x), z(v.y), w(v.z) {}
+    PE_FI vec4(const vec2& u, const vec2& v) : x(u.x), y(u.y), z(v.x), w(v.y) {}
+    PE_FI vec4(const vec2& u, float c, float d) : x(u.x), y(u.y), z(c), w(d) {}
+    PE_FI float& operator[](int i) { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
+    PE_FI float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
+    PE_SWZ_VEC4
+};
+PE_FI vec2::vec2(const vec3& v) : x(v.x), y(v.y) {}
+PE_FI vec2::vec2(const vec4& v) : x(v.x), y(v.y) {}
+PE_FI vec3::vec3(const vec4& v) : x(v.x), y(v.y), z(v.z) {}
+
+#define PE_V2(EX, EY) vec2(EX, EY)
+#define PE_V3(EX, EY, EZ) vec3(EX, EY, EZ)
+#define PE_V4(EX, EY, EZ, EW) vec4(EX, EY, EZ, EW)
+#define PE_BINOPS(OP)                                                                                              \
+    PE_FI vec2 operator OP(const vec2& a, const vec2& b) { return PE_V2(a.x OP b.x, a.y OP b.y); }                 \
+    PE_FI vec2 operator OP(const vec2& a, float s) { return PE_V2(a.x OP s, a.y OP s); }                           \
+    PE_FI vec2 operator OP(float s, const vec2& a) { return PE_V2(s OP a.x, s OP a.y); }                           \
+    PE_FI vec3 operator OP(const vec3& a, const vec3& b) { return PE_V3(a.x OP b.x, a.y OP b.y, a.z OP b.z); }     \
+    PE_FI vec3 operator OP(const vec3& a, float s) { return PE_V3(a.x OP s, a.y OP s, a.z OP s); }                 \
+    PE_FI vec3 operator OP(float s, const vec3& a) { return PE_V3(s OP a.x, s OP a.y, s OP a.z); }                 \
+    PE_FI vec4 operator OP(const vec4& a, const vec4& b) {                                                         \
+        return PE_V4(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w);                                              \
+    }                                                                                                              \
+    PE_FI vec4 operator OP(const vec4& a, float s) { return PE_V4(a.x OP s, a.y OP s, a.z OP s, a.w OP s); }       \
+    PE_FI vec4 operator OP(float s, const vec4& a) { return PE_V4(s OP a.x, s OP a.y, s OP a.z, s OP a.w); }
+PE_BINOPS(+)
+PE_BINOPS(-)
+PE_BINOPS(*)
+PE_BINOPS(/)
+#undef PE_BINOPS
+PE_FI vec2 operator-(const vec2& a) { return vec2(-a.x, -a.y); }
+PE_FI vec3 operator-(const vec3& a) { return vec3(-a.x, -a.y, -a.z); }
+PE_FI vec4 operator-(const vec4& a) { return vec4(-a.x, -a.y, -a.z, -a.w); }
+
+#define PE_COMPOUND(V)                                                      \
+    PE_FI V& operator+=(V& a, const V& b) { a = a + b; return a; }          \
+    PE_FI V& operator-=(V& a, const V& b) { a = a - b; return a; }          \
+    PE_FI V& operator*=(V& a, const V& b) { a = a * b; return a; }          \
+    PE_FI V& operator/=(V& a, const V& b) { a = a / b; return a; }          \
+    PE_FI V& operator+=(V& a, float s) { a = a + s; return a; }             \
+    PE_FI V& operator-=(V& a, float s) { a = a - s; return a; }             \
+    PE_FI V& operator*=(V& a, float s) { a = a * s; return a; }             \
+    PE_FI V& operator/=(V& a, float s) { a = a / s; return a; }
+PE_COMPOUND(vec2)
+PE_COMPOUND(vec3)
+PE_COMPOUND(vec4)
+#undef PE_COMPOUND
+
+PE_FI bool operator==(const vec2& a, const vec2& b) { return a.x == b.x && a.y == b.y; }
+PE_FI bool operator==(const vec3& a, const vec3& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+PE_FI bool operator==(const vec4& a, const vec4& b) { return a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w; }
+PE_FI bool operator!=(const vec2& a, const vec2& b) { return !(a == b); }
+PE_FI bool operator!=(const vec3& a, const vec3& b) { return !(a == b); }
+PE_FI bool operator!=(const vec4& a, const vec4& b) { return !(a == b); }
+
+// geometric built-ins: FFMA chains, lowest component first
+PE_FI float dot(const vec2& a, const vec2& b) { return ::fmaf(a.y, b.y, a.x * b.x); }
+PE_FI float dot(const vec3& a, const vec3& b) { return ::fmaf(a.z, b.z, ::fmaf(a.y, b.y, a.x * b.x)); }
+PE_FI float dot(const vec4& a, const vec4& b) {
+    return ::fmaf(a.w, b.w, ::fmaf(a.z, b.z, ::fmaf(a.y, b.y, a.x * b.x)));
+}
+PE_FI vec3 cross(const vec3& a, const vec3& b) {
+    return vec3(::fmaf(a.y, b.z, -(a.z * b.y)), ::fmaf(a.z, b.x, -(a.x * b.z)), ::fmaf(a.x, b.y, -(a.y * b.x)));
+}
+PE_FI float length(float x) { return abs(x); }
+PE_FI float length(const vec2& v) { return sqrt(dot(v, v)); }
+PE_FI float length(const vec3& v) { return sqrt(dot(v, v)); }
+PE_FI float length(const vec4& v) { return sqrt(dot(v, v)); }
+PE_FI float distance(const vec2& a, const vec2& b) { return length(a - b); }
+PE_FI float distance(const vec3& a, const vec3& b) { return length(a - b); }
+PE_FI float distance(const vec4& a, const vec4& b) { return length(a - b); }
+PE_FI vec2 normalize(const vec2& v) { return v * inversesqrt(dot(v, v)); }
+PE_FI vec3 normalize(const vec3& v) { return v * inversesqrt(dot(v, v)); }
+PE_FI vec4 normalize(const vec4& v) { return v * inversesqrt(dot(v, v)); }
+PE_FI vec3 reflect(const vec3& i, const vec3& n) { return i - n * (2.0f * dot(n, i)); }
+PE_FI vec3 refract(const vec3& i, const vec3& n, float eta) {
+    float d = dot(n, i);
+    float k = 1.0f - eta * eta * (1.0f - d * d);
+    if (k < 0.0f) return vec3(0.0f);
+    return i * eta - n * (eta * d + sqrt(k));
+}
+
+// component-wise built-ins
+#define PE_CW1(F)                                                                      \
+    PE_FI vec2 F(const vec2& v) { return vec2(F(v.x), F(v.y)); }                       \
+    PE_FI vec3 F(const vec3& v) { return vec3(F(v.x), F(v.y), F(v.z)); }               \
+    PE_FI vec4 F(const vec4& v) { return vec4(F(v.x), F(v.y), F(v.z), F(v.w)); }
+PE_CW1(sin) PE_CW1(cos) PE_CW1(tan) PE_CW1(asin) PE_CW1(acos) PE_CW1(exp) PE_CW1(log) PE_CW1(exp2) PE_CW1(log2)
+PE_CW1(sqrt) PE_CW1(inversesqrt) PE_CW1(abs) PE_CW1(sign) PE_CW1(floor) PE_CW1(ceil) PE_CW1(fract)
+PE_CW1(radians) PE_CW1(degrees)
+#undef PE_CW1
+#define PE_CW2(F)                                                                                               \
+    PE_FI vec2 F(const vec2& a, const vec2& b) { return vec2(F(a.x, b.x), F(a.y, b.y)); }                       \
+    PE_FI vec3 F(const vec3& a, const vec3& b) { return vec3(F(a.x, b.x), F(a.y, b.y), F(a.z, b.z)); }          \
+    PE_FI vec4 F(const vec4& a, const vec4& b) { return vec4(F(a.x, b.x), F(a.y, b.y), F(a.z, b.z), F(a.w, b.w)); }
+PE_CW2(mod) PE_CW2(min) PE_CW2(max) PE_CW2(step) PE_CW2(pow) PE_CW2(atan)
+#undef PE_CW2
+#define PE_CW2S(F)                                                                                    \
+    PE_FI vec2 F(const vec2& a, float b) { return vec2(F(a.x, b), F(a.y, b)); }                       \
+    PE_FI vec3 F(const vec3& a, float b) { return vec3(F(a.x, b), F(a.y, b), F(a.z, b)); }            \
+    PE_FI vec4 F(const vec4& a, float b) { return vec4(F(a.x, b), F(a.y, b), F(a.z, b), F(a.w, b)); }
+PE_CW2S(mod) PE_CW2S(min) PE_CW2S(max)
+#undef PE_CW2S
+PE_FI vec2 step(float e, const vec2& v) { return vec2(step(e, v.x), step(e, v.y)); }
+PE_FI vec3 step(float e, const vec3& v) { return vec3(step(e, v.x), step(e, v.y), step(e, v.z)); }
+PE_FI vec4 step(float e, const vec4& v) { return vec4(step(e, v.x), step(e, v.y), step(e, v.z), step(e, v.w)); }
+PE_FI vec2 clamp(const vec2& v, float lo, float hi) { return vec2(clamp(v.x, lo, hi), clamp(v.y, lo, hi)); }
+PE_FI vec3 clamp(const vec3& v, float lo, float hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
+PE_FI vec4 clamp(const vec4& v, float lo, float hi) {
+    return vec4(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi), clamp(v.w, lo, hi));
+}
+PE_FI vec2 clamp(const vec2& v, const vec2& lo, const vec2& hi) { return min(max(v, lo), hi); }
+PE_FI vec3 clamp(const vec3& v, const vec3& lo, const vec3& hi) { return min(max(v, lo), hi); }
+PE_FI vec4 clamp(const vec4& v, const vec4& lo, const vec4& hi) { return min(max(v, lo), hi); }
+PE_FI vec2 mix(const vec2& a, const vec2& b, float t) { return vec2(mix(a.x, b.x, t), mix(a.y, b.y, t)); }
+PE_FI vec3 mix(const vec3& a, const vec3& b, float t) { return vec3(mix(a.x, b.x, t), mix(a.y, b.y, t), mix(a.z, b.z, t)); }
+PE_FI vec4 mix(const vec4& a, const vec4& b, float t) {
+    return vec4(mix(a.x, b.x, t), mix(a.y, b.y, t), mix(a.z, b.z, t), mix(a.w, b.w, t));
+}
+PE_FI vec2 mix(const vec2& a, const vec2& b, const vec2& t) { return vec2(mix(a.x, b.x, t.x), mix(a.y, b.y, t.y)); }
+PE_FI vec3 mix(const vec3& a, const vec3& b, const vec3& t) {
+    return vec3(mix(a.x, b.x, t.x), mix(a.y, b.y, t.y), mix(a.z, b.z, t.z));
+}
+PE_FI vec4 mix(const vec4& a, const vec4& b, const vec4& t) {
+    return vec4(mix(a.x, b.x, t.x), mix(a.y, b.y, t.y), mix(a.z, b.z, t.z), mix(a.w, b.w, t.w));
+}
+
+// ----------------------------------------------------------------- matrices (column-major)
+struct mat4;
+struct mat3 {
+    vec3 c[3];
+    PE_FI mat3() { c[0] = vec3(1.0f, 0.0f, 0.0f); c[1] = vec3(0.0f, 1.0f, 0.0f); c[2] = vec3(0.0f, 0.0f, 1.0f); }
+    PE_FI explicit mat3(float d) { c[0] = vec3(d, 0.0f, 0.0f); c[1] = vec3(0.0f, d, 0.0f); c[2] = vec3(0.0f, 0.0f, d); }
+    PE_FI mat3(const vec3& a, const vec3& b, const vec3& d) { c[0] = a; c[1] = b; c[2] = d; }
+    PE_FI mat3(float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1, float c2) {
+        c[0] = vec3(a0, a1, a2); c[1] = vec3(b0, b1, b2); c[2] = vec3(c0, c1, c2);
+    }
+    PE_FI explicit mat3(const mat4& m);
+    PE_FI vec3& operator[](int i) { return c[i]; }
+    PE_FI const vec3& operator[](int i) const { return c[i]; }
+};
+struct mat4 {
+    vec4 c[4];
+    PE_FI mat4() {
+        c[0] = vec4(1.0f, 0.0f, 0.0f, 0.0f); c[1] = vec4(0.0f, 1.0f, 0.0f, 0.0f);
+        c[2] = vec4(0.0f, 0.0f, 1.0f, 0.0f); c[3] = vec4(0.0f, 0.0f, 0.0f, 1.0f);
+    }
+    PE_FI explicit mat4(float d) {
+        c[0] = vec4(d, 0.0f, 0.0f, 0.0f); c[1] = vec4(0.0f, d, 0.0f, 0.0f);
+        c[2] = vec4(0.0f, 0.0f, d, 0.0f); c[3] = vec4(0.0f, 0.0f, 0.0f, d);
+    }
+    PE_FI mat4(const vec4& a, const vec4& b, const vec4& d, const vec4& e) { c[0] = a; c[1] = b; c[2] = d; c[3] = e; }
+    PE_FI vec4& operator[](int i) { return c[i]; }
+    PE_FI const vec4& operator[](int i) const { return c[i]; }
+};
+PE_FI mat3::mat3(const mat4& m) { c[0] = vec3(m.c[0]); c[1] = vec3(m.c[1]); c[2] = vec3(m.c[2]); }
+
+// A matrix of the constant uniform block: 16 floats, no constructors (so it can sit in
+// __constant__ memory), implicitly readable as a mat4 where a snippet wants a value.
+struct cmat4 {
+    float e[16];
+    PE_FI operator mat4() const {
+        return mat4(vec4(e[0], e[1], e[2], e[3]), vec4(e[4], e[5], e[6], e[7]), vec4(e[8], e[9], e[10], e[11]),
+                    vec4(e[12], e[13], e[14], e[15]));
+    }
+    PE_FI vec4 operator[](int i) const { return vec4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]); }
+};
+
+PE_FI vec3 operator*(const mat3& m, const vec3& v) {
+    return vec3(::fmaf(m.c[2].x, v.z, ::fmaf(m.c[1].x, v.y, m.c[0].x * v.x)),
+                ::fmaf(m.c[2].y, v.z, ::fmaf(m.c[1].y, v.y, m.c[0].y * v.x)),
+                ::fmaf(m.c[2].z, v.z, ::fmaf(m.c[1].z, v.y, m.c[0].z * v.x)));
+}
+PE_FI vec4 operator*(const mat4& m, const vec4& v) {
+    return vec4(::fmaf(m.c[3].x, v.w, ::fmaf(m.c[2].x, v.z, ::fmaf(m.c[1].x, v.y, m.c[0].x * v.x))),
+                ::fmaf(m.c[3].y, v.w, ::fmaf(m.c[2].y, v.z, ::fmaf(m.c[1].y, v.y, m.c[0].y * v.x))),
+                ::fmaf(m.c[3].z, v.w, ::fmaf(m.c[2].z, v.z, ::fmaf(m.c[1].z, v.y, m.c[0].z * v.x))),
+                ::fmaf(m.c[3].w, v.w, ::fmaf(m.c[2].w, v.z, ::fmaf(m.c[1].w, v.y, m.c[0].w * v.x))));
+}
+// Constant-bank matrix times register vector: every e[k] becomes a c[bank][offset] FFMA operand.
+PE_FI vec4 operator*(const cmat4& m, const vec4& v) {
+    return vec4(::fmaf(m.e[12], v.w, ::fmaf(m.e[8], v.z, ::fmaf(m.e[4], v.y, m.e[0] * v.x))),
+                ::fmaf(m.e[13], v.w, ::fmaf(m.e[9], v.z, ::fmaf(m.e[5], v.y, m.e[1] * v.x))),
+                ::fmaf(m.e[14], v.w, ::fmaf(m.e[10], v.z, ::fmaf(m.e[6], v.y, m.e[2] * v.x))),
+                ::fmaf(m.e[15], v.w, ::fmaf(m.e[11], v.z, ::fmaf(m.e[7], v.y, m.e[3] * v.x))));
+}
+PE_FI mat4 operator*(const mat4& a, const mat4& b) { return mat4(a * b.c[0], a * b.c[1], a * b.c[2], a * b.c[3]); }
+PE_FI mat4 operator*(const cmat4& a, const mat4& b) { return mat4(a) * b; }
+PE_FI mat4 operator*(const mat4& a, const cmat4& b) { return a * mat4(b); }
+PE_FI mat4 operator*(const cmat4& a, const cmat4& b) { return mat4(a) * mat4(b); }
+PE_FI mat3 operator*(const mat3& a, const mat3& b) { return mat3(a * b.c[0], a * b.c[1], a * b.c[2]); }
+PE_FI mat3 transpose(const mat3& m) {
+    return mat3(vec3(m.c[0].x, m.c[1].x, m.c[2].x), vec3(m.c[0].y, m.c[1].y, m.c[2].y), vec3(m.c[0].z, m.c[1].z, m.c[2].z));
+}
+PE_FI mat4 transpose(const mat4& m) {
+    return mat4(vec4(m.c[0].x, m.c[1].x, m.c[2].x, m.c[3].x), vec4(m.c[0].y, m.c[1].y, m.c[2].y, m.c[3].y),
+                vec4(m.c[0].z, m.c[1].z, m.c[2].z, m.c[3].z), vec4(m.c[0].w, m.c[1].w, m.c[2].w, m.c[3].w));
+}
+
+// ----------------------------------------------------------------- textures
+// RGBA8 texels in global memory, fetched through the read-only path; bilinear weights in fp32
+// (the hardware texture unit's 1.8 fixed-point weights would not be reproducible on a CPU).
+// Rule: texel centres at (i+0.5)/size, clamp-to-edge, channel = byte/255, row 0 is v = 0.
+struct sampler2D {
+    const uchar4* data;
+    int w, h;
+};
+PE_FI vec4 pe_texel(const sampler2D& s, int ix, int iy) {
+    ix = ix < 0 ? 0 : (ix > s.w - 1 ? s.w - 1 : ix);
+    iy = iy < 0 ? 0 : (iy > s.h - 1 ? s.h - 1 : iy);
+    uchar4 p = __ldg(s.data + (size_t(iy) * size_t(s.w) + size_t(ix)));
+    const float k = 1.0f / 255.0f;
+    return vec4(float(p.x) * k, float(p.y) * k, float(p.z) * k, float(p.w) * k);
+}
+PE_FI vec4 texture(const sampler2D& s, const vec2& uv) {
+    if (s.data == nullptr) return vec4(0.0f, 0.0f, 0.0f, 1.0f);
+    float x = uv.x * float(s.w) - 0.5f;
+    float y = uv.y * float(s.h) - 0.5f;
+    float x0 = ::floorf(x), y0 = ::floorf(y);
+    float fx = x - x0, fy = y - y0;
+    x0 = clamp(x0, -2.0f, float(s.w + 1));
+    y0 = clamp(y0, -2.0f, float(s.h + 1));
+    int ix = int(x0), iy = int(y0);
+    vec4 c00 = pe_texel(s, ix, iy), c10 = pe_texel(s, ix + 1, iy);
+    vec4 c01 = pe_texel(s, ix, iy + 1), c11 = pe_texel(s, ix + 1, iy + 1);
+    vec4 top = c00 * (1.0f - fx) + c10 * fx;
+    vec4 bot = c01 * (1.0f - fx) + c11 * fx;
+    return top * (1.0f - fy) + bot * fy;
+}
+
+}  // namespace pe

@@ -1,0 +1,299 @@
+// portal_b200 device layer 3/3: the per-pixel portal ray loop as an sm_100a kernel.
+//
+// Replaces the reference's fragment-shader driver: main -> get_color -> get_color2 -> ray_tracing
+// (/root/reference/src/frag.glsl:515-552, :466-503, :408-464, :106-159) plus the vertex stage's
+// uv_screen (/root/reference/src/gui/scene.rs:1688-1693).  The generated part of the program
+// (scene_intersect, material_process, scene_intersect_material_process -- the reference's
+// generator sections, scene.rs:885-1035) is emitted before this file is included.
+//
+// Execution model
+//   * one ray slot per lane; the ray (origin, direction, tmul, subspace flag), the running colour
+//     and the travelled distance are 15 words that stay in registers for the whole life of a ray;
+//   * PE_PERSISTENT = 0: one thread per pixel.  A warp covers an 8x4 pixel tile (coherent primary
+//     rays, and each row of the tile is one full 128-byte line of the float4 framebuffer);
+//   * PE_PERSISTENT = 1: persistent warps.  After every bounce the lanes whose ray ended store
+//     their pixel and take the next untraced pixel of the block's tile queue (ballot + popc
+//     ranks the idle lanes, one atomicAdd per warp per refill), so a warp never idles on a long
+//     portal chain while its other 31 rays are done -- lanes stay converged under divergent depth;
+//   * scene matrices / uniforms: constant bank (see pe_glsl.cuh); renderer uniforms likewise;
+//   * output: linear-light sqrt-encoded RGBA as float4 (16 B per pixel, the path's only HBM
+//     traffic), optionally straight into a peer GPU's frame over NVLink (out may be a P2P pointer).
+#pragma once
+
+namespace pe {
+
+struct RayTraceResult {  // frag.glsl:74-78
+    vec3 color;
+    float depth;
+    bool has_depth;
+};
+
+// frag.glsl:80-104 (depth-map colouring, `_draw_depth_map`)
+PE_FI float normalize_depth_value(float depth) {
+    float depth_min = min(_depth_map_min, _depth_map_max);
+    float depth_max = max(_depth_map_min, _depth_map_max);
+    return clamp((depth - depth_min) / max(1e-6f, depth_max - depth_min), 0.0f, 1.0f);
+}
+inline vec3 depth_gradient_inferno(float t) {
+    vec3 c0 = sqrvec(vec3(0.001462f, 0.000466f, 0.013866f));
+    vec3 c1 = sqrvec(vec3(0.258234f, 0.038571f, 0.406485f));
+    vec3 c2 = sqrvec(vec3(0.578304f, 0.148039f, 0.404411f));
+    vec3 c3 = sqrvec(vec3(0.865006f, 0.316822f, 0.226055f));
+    vec3 c4 = sqrvec(vec3(0.987622f, 0.645320f, 0.039886f));
+    vec3 c5 = sqrvec(vec3(0.988362f, 0.998364f, 0.644924f));
+    if (t < 0.2f) return mix(c0, c1, t / 0.2f);
+    if (t < 0.4f) return mix(c1, c2, (t - 0.2f) / 0.2f);
+    if (t < 0.6f) return mix(c2, c3, (t - 0.4f) / 0.2f);
+    if (t < 0.8f) return mix(c3, c4, (t - 0.6f) / 0.2f);
+    return mix(c4, c5, (t - 0.8f) / 0.2f);
+}
+PE_FI vec3 sample_depth_gradient(float depth) { return depth_gradient_inferno(1.0f - normalize_depth_value(depth)); }
+
+// State of one ray between bounces.
+struct RaySlot {
+    Ray r;
+    vec3 current_color;
+    float all_t;
+    int bounce;
+};
+
+// One iteration of the reference's bounce loop body (frag.glsl:113-156).
+// Returns true when the ray has ended; `res` then holds its RayTraceResult.
+PE_FI bool bounce_once(RaySlot& s, float camera_scale, RayTraceResult& res) {
+    Ray& r = s.r;
+    SceneIntersection i = scene_intersect(r);
+    SceneIntersectionWithMaterial i2 = scene_intersect_material_process(r);
+
+    MaterialProcessing m = material_empty();
+    if (nearer(i.hit, i2.scene.hit)) {
+        r.o += r.d * i2.scene.hit.t;
+        s.all_t += i2.scene.hit.t * r.tmul;
+        if (i2.scene.material == CUSTOM_MATERIAL) {
+            m = i2.material;
+        } else {
+            m = material_process(r, i2.scene);
+        }
+    } else if (i.hit.hit) {
+        r.o += r.d * i.hit.t;
+        s.all_t += i.hit.t * r.tmul;
+        m = material_process(r, i);
+    }
+
+    if (i.hit.hit || i2.scene.hit.hit) {
+        s.current_color *= m.mul_to_color;
+        if (m.is_final) {
+            float all_t = s.all_t;
+            float depth = all_t / max(camera_scale, 1e-6f);
+            if (all_t > _t_start * camera_scale && _darken_by_distance == 1) {
+                if (all_t > _t_end * camera_scale) all_t = _t_end * camera_scale;
+                float gray_t = (all_t - _t_start * camera_scale) / (_t_end - _t_start) / camera_scale;
+                res = RayTraceResult{color(0.0f, 0.0f, 0.0f) * sqr(sqr(gray_t)) + s.current_color * sqr(sqr(1.0f - gray_t)),
+                                     depth, true};
+            } else {
+                res = RayTraceResult{s.current_color, depth, true};
+            }
+            return true;
+        }
+        r = m.new_ray;
+        return false;
+    }
+    if (r.in_subspace) {
+        res = RayTraceResult{color(0.0f, 0.0f, 0.0f), 0.0f, false};
+    } else {
+        res = RayTraceResult{s.current_color * PE_NOT_FOUND_COLOR(r), 0.0f, false};
+    }
+    return true;
+}
+
+// frag.glsl:506-513
+PE_FI vec2 quasi_random(int i) {
+    float a1 = 0.7548776662466927600500267982588025643670318456949186300834636687f;
+    float a2 = 0.5698402909980532659121818632752155853637566123932930564053138358f;
+    return vec2(mod(0.5f + a1 * float(i), 1.0f), mod(0.5f + a2 * float(i), 1.0f));
+}
+
+// Primary ray of AA sample `a` of pixel (px, py): vertex stage + frag.glsl:519-524 + :409, :450-454.
+// `_tan_half_view` = tan(_view_angle / 2) is a uniform expression; the host evaluates it once per
+// frame in fp32 (pe_api.cpp, same libm call as the oracle) instead of once per pixel.
+PE_FI void primary_ray(int px, int py, int a, RaySlot& s) {
+    vec2 resolution = vec2(_resolution_x, _resolution_y);
+    vec2 position = vec2(float(px) + 0.5f, float(py) + 0.5f);
+    float coef = min(resolution.x, resolution.y);
+    vec2 uv_screen = (position - resolution / 2.0f) / coef * 2.0f;
+    float pixel_size = 1.0f / min(resolution.x, resolution.y);
+    vec2 ip = uv_screen + quasi_random(a) * pixel_size * 2.0f;
+
+    vec4 o = _camera * vec4(0.0f, 0.0f, 0.0f, 1.0f);
+    float h = _tan_half_view;
+    vec4 d = normalize(_camera * vec4(ip.x * h, ip.y * h, 1.0f, 0.0f));
+    s.r = Ray{o, d, 1.0f, _camera_in_subspace == 1};
+    s.current_color = vec3(1.0f);
+    s.all_t = 0.0f;
+    s.bounce = 0;
+}
+
+// get_color2's tail (frag.glsl:456-463)
+PE_FI vec3 resolve_sample(const RayTraceResult& t) {
+    if (_draw_depth_map == 1) return t.has_depth ? sample_depth_gradient(t.depth) : vec3(0.0f);
+    return t.color;
+}
+
+}  // namespace pe
+
+// Launch geometry.  A launch renders `n_strips` horizontal strips of `strip_rows` rows each:
+// local strip k is global strip strip_first + k * strip_step (cyclic row-strip sharding across
+// GPUs; a single GPU uses strip_first = 0, strip_step = 1).
+struct PeLaunch {
+    float4* out;          // destination pixels (device or peer-mapped memory)
+    int* bounces;         // optional per-pixel bounce count (same indexing as out), may be null
+    int width, height;    // full frame
+    int strip_rows, strip_first, strip_step, n_strips;
+    int out_full_frame;   // 1: out is the whole frame (index by global row); 0: compact local rows
+    int tiles_x, tiles_y; // 8x4 tiles over the local row space
+    unsigned int* queue;  // PE_PERSISTENT: global tile counter (zeroed by the host before launch)
+};
+
+namespace pe {
+
+PE_FI bool local_to_global_row(const PeLaunch& L, int lrow, int& grow) {
+    int k = lrow / L.strip_rows;
+    if (k >= L.n_strips) return false;
+    grow = (L.strip_first + k * L.strip_step) * L.strip_rows + (lrow - k * L.strip_rows);
+    return grow < L.height;
+}
+
+PE_FI void store_pixel(const PeLaunch& L, int px, int lrow, int grow, vec3 sum, int bounces) {
+    // frag.glsl:526, :551: sqrt(result / aa_count), alpha 1
+    vec3 c = sqrt(sum / float(_aa_count));
+    size_t idx = size_t(L.out_full_frame ? grow : lrow) * size_t(L.width) + size_t(px);
+    L.out[idx] = make_float4(c.x, c.y, c.z, 1.0f);
+    if (L.bounces) L.bounces[idx] = bounces;
+}
+
+}  // namespace pe
+
+#ifndef PE_PERSISTENT
+#define PE_PERSISTENT 0
+#endif
+#ifndef PE_BLOCK_THREADS
+#define PE_BLOCK_THREADS 128
+#endif
+#ifndef PE_MIN_BLOCKS
+#define PE_MIN_BLOCKS 1
+#endif
+
+#if !PE_PERSISTENT
+// ------------------------------------------------------------------------------------------
+// One thread per pixel.  Block = 4 warps = a 16x8 pixel tile (2x2 warp tiles of 8x4).
+extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe_render_kernel(const PeLaunch L) {
+    using namespace pe;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int lrow = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    int grow;
+    if (px >= L.width || !local_to_global_row(L, lrow, grow)) return;
+
+    vec3 sum = vec3(0.0f);
+    int worst = 0;
+    for (int a = _aa_start; a < _aa_count + _aa_start; a++) {  // frag.glsl:522-525
+        RaySlot s;
+        primary_ray(px, grow, a, s);
+        RayTraceResult res = RayTraceResult{color(0.0f, 0.0f, 0.0f), 0.0f, false};  // loop exhausted: frag.glsl:158
+        for (int j = 0; j < _ray_tracing_depth; j++) {                               // frag.glsl:112
+            s.bounce = j + 1;
+            if (bounce_once(s, _camera_scale, res)) break;
+        }
+        sum += resolve_sample(res);
+        worst = pe::max(worst, s.bounce);
+    }
+    store_pixel(L, px, lrow, grow, sum, worst);
+}
+#else
+// ------------------------------------------------------------------------------------------
+// Persistent warps with per-bounce refill.  Work unit = one AA sample of one pixel; the pixel
+// order is 8x4 tiles in row-major tile order, so the 32 rays a warp starts together are
+// neighbours.  Each warp owns its lanes' accumulators: with aa_count > 1 a lane runs all
+// samples of its pixel back to back before it takes a new pixel.
+extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe_render_kernel(const PeLaunch L) {
+    using namespace pe;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned total_tiles = unsigned(L.tiles_x) * unsigned(L.tiles_y);
+    const int depth = _ray_tracing_depth;
+
+    // Per-lane state
+    RaySlot s;
+    RayTraceResult res;
+    vec3 sum = vec3(0.0f);
+    int px = 0, lrow = 0, grow = 0, a = 0, worst = 0;
+    bool alive = false;      // lane holds a ray in flight
+    // Warp-level tile cursor: the warp walks one 8x4 tile (32 pixels) at a time.
+    unsigned tile = 0xffffffffu;  // current tile (warp-uniform)
+    unsigned taken = 32;          // pixels of `tile` already handed to lanes (warp-uniform)
+    bool drained = false;         // queue exhausted (warp-uniform)
+
+    while (true) {
+        // ---- refill: every idle lane takes the next pixel
+        unsigned idle = __ballot_sync(FULL, !alive);
+        while (idle != 0 && !drained) {
+            if (taken >= 32) {
+                unsigned t = 0;
+                if (lane == 0) t = atomicAdd(L.queue, 1u);
+                tile = __shfl_sync(FULL, t, 0);
+                taken = 0;
+                if (tile >= total_tiles) { drained = true; break; }
+            }
+            // hand pixels [taken, taken + n) of the tile to the first n idle lanes
+            unsigned n = unsigned(__popc(idle)); if (n > 32u - taken) n = 32u - taken;
+            unsigned rank = __popc(idle & ((1u << lane) - 1u));
+            bool mine = !alive && rank < n;
+            if (mine) {
+                unsigned p = taken + rank;                       // pixel index inside the 8x4 tile
+                px = int(tile % unsigned(L.tiles_x)) * 8 + int(p & 7u);
+                lrow = int(tile / unsigned(L.tiles_x)) * 4 + int(p >> 3);
+                if (px < L.width && local_to_global_row(L, lrow, grow)) {
+                    a = _aa_start;
+                    sum = vec3(0.0f);
+                    worst = 0;
+                    primary_ray(px, grow, a, s);
+                    alive = true;
+                }
+                // (an out-of-frame pixel of an edge tile is skipped: the lane stays idle)
+            }
+            taken += n;
+            idle = __ballot_sync(FULL, !alive);  // lanes offered an out-of-frame pixel are offered the next one
+        }
+        unsigned active = __ballot_sync(FULL, alive);
+        if (active == 0) {
+            if (drained) break;
+            continue;
+        }
+        // ---- one bounce for every live lane
+        if (alive) {
+            bool done;
+            if (s.bounce >= depth) {           // loop exhausted (frag.glsl:158)
+                res = RayTraceResult{color(0.0f, 0.0f, 0.0f), 0.0f, false};
+                done = true;
+            } else {
+                s.bounce++;
+                done = bounce_once(s, _camera_scale, res);
+                if (!done && s.bounce >= depth) {
+                    res = RayTraceResult{color(0.0f, 0.0f, 0.0f), 0.0f, false};
+                    done = true;
+                }
+            }
+            if (done) {
+                sum += resolve_sample(res);
+                worst = pe::max(worst, s.bounce);
+                a++;
+                if (a < _aa_count + _aa_start) {
+                    primary_ray(px, grow, a, s);   // next AA sample of the same pixel
+                } else {
+                    store_pixel(L, px, lrow, grow, sum, worst);
+                    alive = false;
+                }
+            }
+        }
+    }
+}
+#endif

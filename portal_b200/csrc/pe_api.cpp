@@ -1,0 +1,776 @@
+// portal_b200 C ABI (include/portal_b200.h): context, scene builder, NVRTC specialisation cache,
+// constant-block uploader and launcher of the sm_100a ray-loop kernel.
+//
+// Mirrors, call for call, what the reference's SceneRenderer does with its macroquad Material
+// (/root/reference/src/main.rs:934-1064 new, :1266-1359 set_uniforms, :1411-1428 draw_texture,
+// /root/reference/src/gui/scene.rs:545-658 Scene::set_uniforms, :1112-1176 get_new_material).
+// There is NO CPU rendering path in this library: without a CUDA device pe_render* fail.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/portal_b200.h"
+#include "pe_codegen.h"
+#include "pe_driver.h"
+#include "pe_kernels.h"
+
+using namespace pe_host;
+
+namespace {
+
+struct PeLaunchHost {  // must match `PeLaunch` in device/pe_kernel.cuh
+    void* out;
+    void* bounces;
+    int32_t width, height;
+    int32_t strip_rows, strip_first, strip_step, n_strips;
+    int32_t out_full_frame;
+    int32_t tiles_x, tiles_y;
+    int32_t _pad;
+    void* queue;
+};
+static_assert(sizeof(PeLaunchHost) == 64, "PeLaunch layout");
+
+struct Variant {
+    std::string source;
+    std::vector<char> cubin;
+    CUmodule_t module = nullptr;
+    CUfunction_t kernel = nullptr;
+    CUdeviceptr_t const_ptr = 0;
+    size_t const_size = 0;
+    int regs = 0;
+    int blocks_per_sm = 1;
+};
+
+struct Texture {
+    void* dev = nullptr;
+    int w = 0, h = 0;
+};
+
+std::string g_create_error;
+std::mutex g_create_mutex;
+
+uint64_t fnv1a(const std::string& s, uint64_t h) {
+    for (unsigned char c : s) {
+        h ^= c;
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+std::string lib_dir() {
+    Dl_info info;
+    if (dladdr((void*)&fnv1a, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t s = p.rfind('/');
+        return s == std::string::npos ? "." : p.substr(0, s);
+    }
+    return ".";
+}
+
+std::string cache_dir() {
+    const char* e = std::getenv("PORTAL_B200_CACHE_DIR");
+    std::string d = e && *e ? e : lib_dir() + "/_cache";
+    mkdir(d.c_str(), 0755);
+    return d;
+}
+
+}  // namespace
+
+struct pe_ctx {
+    int device = -1;
+    bool has_gpu = false;
+    int sm_count = 148;
+    std::string err;
+
+    SceneDesc scene;
+    ConstLayout layout;
+    bool layout_valid = false;
+    GenOptions opts;
+    bool lineinfo = true;
+
+    std::vector<uint8_t> cblock;  // host image of the constant block
+    std::map<std::string, std::vector<float>> pending_mat;
+    std::map<std::string, float> pending_f;
+    std::map<std::string, int> pending_i;
+
+    std::map<std::vector<int>, std::unique_ptr<Variant>> variants;  // key: specialised int values
+    Variant* current = nullptr;
+    std::map<std::string, Texture> textures;
+
+    cudaStream_t stream = nullptr;
+    unsigned int* queue_dev = nullptr;
+    void* scratch_dev = nullptr;  // pe_render_host* staging
+    size_t scratch_bytes = 0;
+    void* scratch8_dev = nullptr;
+    size_t scratch8_bytes = 0;
+    uint64_t launches = 0;
+    const DriverApi* drv = nullptr;
+
+    int fail(const std::string& m, int code = 1) {
+        err = m;
+        return code;
+    }
+};
+
+namespace {
+
+bool cuda_ok(pe_ctx* c, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    c->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+
+void set_renderer_defaults(pe_ctx* c);
+
+void ensure_layout(pe_ctx* c) {
+    if (c->layout_valid) return;
+    c->layout = make_layout(c->scene);
+    c->cblock.assign(c->layout.size, 0);
+    c->layout_valid = true;
+    set_renderer_defaults(c);
+    // identity camera
+    float* cam = reinterpret_cast<float*>(c->cblock.data() + c->layout.off_mat) + 16 * c->layout.camera_slot;
+    for (int k = 0; k < 16; k++) cam[k] = (k % 5 == 0) ? 1.0f : 0.0f;
+    // values set before the layout existed
+    for (auto& kv : c->pending_mat) pe_set_uniform_mat4(c, kv.first.c_str(), kv.second.data());
+    for (auto& kv : c->pending_f) pe_set_uniform_f32(c, kv.first.c_str(), kv.second);
+    for (auto& kv : c->pending_i) pe_set_uniform_i32(c, kv.first.c_str(), kv.second);
+    c->pending_mat.clear();
+    c->pending_f.clear();
+    c->pending_i.clear();
+}
+
+float* fslot(pe_ctx* c, int slot) { return reinterpret_cast<float*>(c->cblock.data() + c->layout.off_float) + slot; }
+int* islot(pe_ctx* c, int slot) { return reinterpret_cast<int*>(c->cblock.data() + c->layout.off_int) + slot; }
+
+void set_renderer_defaults(pe_ctx* c) {
+    // SceneRenderer::new (/root/reference/src/main.rs:1021-1047) and RotateAroundCam::new (:94-130)
+    auto F = [&](const char* n, float v) { *fslot(c, c->layout.float_slot[n]) = v; };
+    auto I = [&](const char* n, int v) { *islot(c, c->layout.int_slot[n]) = v; };
+    const float view_angle = float(90.0 / 180.0 * M_PI);
+    F("_camera_scale", 1.0f);
+    F("_view_angle", view_angle);
+    F("_tan_half_view", std::tan(view_angle / 2.0f));
+    F("_t_start", 10.0f);
+    F("_t_end", 210.0f);
+    F("_offset_after_material", 0.005f);
+    F("_depth_map_min", 0.0f);
+    F("_depth_map_max", 10.0f);
+    F("_resolution_x", 1.0f);
+    F("_resolution_y", 1.0f);
+    I("_ray_tracing_depth", 100);
+    I("_aa_start", 0);
+    I("_aa_count", 1);
+    I("_camera_in_subspace", 0);
+    I("_darken_by_distance", 1);
+    I("_angle_color_disable", 0);
+    I("_grid_disable", 0);
+    I("_black_border_disable", 0);
+    I("_draw_depth_map", 0);
+}
+
+std::vector<int> current_ints(pe_ctx* c) {
+    const int n = c->layout.n_int + kNumRendererInts;
+    std::vector<int> v(n);
+    std::memcpy(v.data(), c->cblock.data() + c->layout.off_int, size_t(n) * 4);
+    return v;
+}
+
+std::vector<int> variant_key(pe_ctx* c, const std::vector<int>& ints) {
+    if (!c->opts.specialize_ints) return {};
+    std::vector<int> key = ints;
+    // dynamic renderer ints do not take part in specialisation
+    key[c->layout.int_slot["_ray_tracing_depth"]] = 0;
+    key[c->layout.int_slot["_aa_start"]] = 0;
+    return key;
+}
+
+// NVRTC: source -> sm_100a cubin (disk-cached by content hash).
+bool compile_cubin(pe_ctx* c, const std::string& source, std::vector<char>& cubin) {
+    std::vector<std::string> o = {"--gpu-architecture=sm_100a", "--std=c++20", "-default-device", "--fmad=false",
+                                  "--prec-div=true", "--prec-sqrt=true", "--ftz=false"};
+    if (c->lineinfo) o.push_back("-lineinfo");
+    int major = 0, minor = 0;
+    nvrtcVersion(&major, &minor);
+    std::string tag = "nvrtc" + std::to_string(major) + "." + std::to_string(minor);
+    for (auto& s : o) tag += s;
+    uint64_t h1 = fnv1a(tag, fnv1a(source, 1469598103934665603ull));
+    uint64_t h2 = fnv1a(source, fnv1a(tag, 0x9e3779b97f4a7c15ull));
+    char name[64];
+    std::snprintf(name, sizeof name, "/%016llx%016llx.cubin", (unsigned long long)h1, (unsigned long long)h2);
+    const std::string path = cache_dir() + name;
+    {
+        std::ifstream f(path, std::ios::binary);
+        if (f) {
+            cubin.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+            if (!cubin.empty()) return true;
+        }
+    }
+    nvrtcProgram prog;
+    if (nvrtcCreateProgram(&prog, source.c_str(), "scene_program.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
+        c->err = "nvrtcCreateProgram failed";
+        return false;
+    }
+    std::vector<const char*> opts;
+    for (auto& s : o) opts.push_back(s.c_str());
+    nvrtcResult r = nvrtcCompileProgram(prog, int(opts.size()), opts.data());
+    size_t ls = 0;
+    nvrtcGetProgramLogSize(prog, &ls);
+    std::string log(ls, '\0');
+    if (ls) nvrtcGetProgramLog(prog, &log[0]);
+    if (r != NVRTC_SUCCESS) {
+        // Diagnostics already carry "<scene element>(local line)" thanks to the #line directives
+        // the generator puts around every user snippet.
+        c->err = std::string("scene program failed to compile (") + nvrtcGetErrorString(r) + "):\n" + log;
+        nvrtcDestroyProgram(&prog);
+        return false;
+    }
+    size_t cs = 0;
+    nvrtcGetCUBINSize(prog, &cs);
+    cubin.resize(cs);
+    nvrtcGetCUBIN(prog, cubin.data());
+    nvrtcDestroyProgram(&prog);
+    {
+        std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+        std::ofstream f(tmp, std::ios::binary);
+        if (f) {
+            f.write(cubin.data(), std::streamsize(cubin.size()));
+            f.close();
+            std::rename(tmp.c_str(), path.c_str());
+        }
+    }
+    return true;
+}
+
+// Make the variant for the current integer uniforms current (generate / compile / load as needed).
+bool select_variant(pe_ctx* c) {
+    ensure_layout(c);
+    std::vector<int> ints = current_ints(c);
+    std::vector<int> key = variant_key(c, ints);
+    auto it = c->variants.find(key);
+    if (it == c->variants.end()) {
+        GenResult g = generate_program(c->scene, c->layout, c->opts, ints);
+        if (!g.error.empty()) {
+            c->err = g.error;
+            return false;
+        }
+        auto v = std::make_unique<Variant>();
+        v->source = std::move(g.source);
+        if (!compile_cubin(c, v->source, v->cubin)) return false;
+        it = c->variants.emplace(key, std::move(v)).first;
+    }
+    Variant* v = it->second.get();
+    if (c->has_gpu && !v->module) {
+        const DriverApi* d = c->drv;
+        CUresult_t r = d->cuModuleLoadData(&v->module, v->cubin.data());
+        if (r != 0) { c->err = "cuModuleLoadData: " + driver_error(d, r); return false; }
+        r = d->cuModuleGetFunction(&v->kernel, v->module, "pe_render_kernel");
+        if (r != 0) { c->err = "cuModuleGetFunction(pe_render_kernel): " + driver_error(d, r); return false; }
+        r = d->cuModuleGetGlobal(&v->const_ptr, &v->const_size, v->module, "PE_C");
+        if (r != 0) { c->err = "cuModuleGetGlobal(PE_C): " + driver_error(d, r); return false; }
+        if (v->const_size != c->layout.size) { c->err = "constant block size mismatch between host and device"; return false; }
+        d->cuFuncGetAttribute(&v->regs, 4 /*CU_FUNC_ATTRIBUTE_NUM_REGS*/, v->kernel);
+        int nb = 1;
+        if (d->cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v->kernel, c->opts.block_threads, 0) == 0 && nb > 0)
+            v->blocks_per_sm = nb;
+    }
+    c->current = v;
+    return true;
+}
+
+bool bind_device(pe_ctx* c) {
+    if (!c->has_gpu) {
+        c->err = "this context has no CUDA device (compile-only); portal_b200 has no CPU rendering path";
+        return false;
+    }
+    return cuda_ok(c, cudaSetDevice(c->device), "cudaSetDevice");
+}
+
+bool check_target(pe_ctx* c, const pe_target* t) {
+    if (!t || t->width <= 0 || t->height <= 0 || t->strip_rows <= 0 || t->strip_step <= 0 || t->n_strips <= 0 ||
+        t->strip_first < 0) {
+        c->err = "invalid pe_target";
+        return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pe_abi_version(void) { return 100; }
+
+pe_ctx* pe_create(int device) {
+    std::lock_guard<std::mutex> lk(g_create_mutex);
+    auto c = std::make_unique<pe_ctx>();
+    c->device = device;
+    if (device >= 0) {
+        std::string why;
+        c->drv = driver_api(why);
+        if (!c->drv) {
+            g_create_error = why;
+            return nullptr;
+        }
+        cudaError_t e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = cudaFree(nullptr);  // create the primary context
+        if (e != cudaSuccess) {
+            g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+            return nullptr;
+        }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+            c->sm_count = prop.multiProcessorCount;
+            if (prop.major < 10) {
+                g_create_error = "portal_b200 needs an sm_100a (B200) device; found sm_" + std::to_string(prop.major) +
+                                 std::to_string(prop.minor);
+                return nullptr;
+            }
+        }
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMalloc(&c->queue_dev, 256) != cudaSuccess) {
+            g_create_error = "cannot create stream / queue counter";
+            return nullptr;
+        }
+        c->has_gpu = true;
+    }
+    g_create_error.clear();
+    return c.release();
+}
+
+void pe_destroy(pe_ctx* c) {
+    if (!c) return;
+    if (c->has_gpu) {
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        for (auto& kv : c->variants)
+            if (kv.second->module) c->drv->cuModuleUnload(kv.second->module);
+        for (auto& kv : c->textures)
+            if (kv.second.dev) cudaFree(kv.second.dev);
+        if (c->scratch_dev) cudaFree(c->scratch_dev);
+        if (c->scratch8_dev) cudaFree(c->scratch8_dev);
+        if (c->queue_dev) cudaFree(c->queue_dev);
+        if (c->stream) cudaStreamDestroy(c->stream);
+    }
+    delete c;
+}
+
+const char* pe_last_error(pe_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+// ------------------------------------------------------------------------------ scene builder
+int pe_scene_begin(pe_ctx* c) {
+    if (!c) return 1;
+    if (c->has_gpu) {
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        for (auto& kv : c->variants)
+            if (kv.second->module) c->drv->cuModuleUnload(kv.second->module);
+    }
+    c->variants.clear();
+    c->current = nullptr;
+    c->scene = SceneDesc();
+    c->layout_valid = false;
+    c->cblock.clear();
+    c->pending_mat.clear();
+    c->pending_f.clear();
+    c->pending_i.clear();
+    return 0;
+}
+
+#define PE_NEED(c, p)                                  \
+    if (!(c)) return 1;                                \
+    if (!(p)) return (c)->fail("null argument: " #p);  \
+    if ((c)->layout_valid) return (c)->fail("scene description is frozen (uniforms were already set or compiled); call pe_scene_begin")
+
+int pe_scene_add_library(pe_ctx* c, const char* name, const char* glsl) {
+    PE_NEED(c, name && glsl);
+    c->scene.library.push_back({name, glsl});
+    return 0;
+}
+
+int pe_scene_add_material_simple(pe_ctx* c, const char* name, const double color[3], double normal_coef, int grid,
+                                 double grid_scale, double grid_coef, int grid2, int grid3) {
+    PE_NEED(c, name && color);
+    Material m;
+    m.name = name;
+    m.type = MatType::Simple;
+    for (int k = 0; k < 3; k++) m.color[k] = color[k];
+    m.normal_coef = normal_coef;
+    m.grid = grid != 0;
+    m.grid_scale = grid_scale;
+    m.grid_coef = grid_coef;
+    m.grid2 = grid2 != 0;
+    m.grid3 = grid3 != 0;
+    c->scene.materials.push_back(m);
+    return 0;
+}
+
+int pe_scene_add_material_reflect(pe_ctx* c, const char* name, const double add_to_color[3]) {
+    PE_NEED(c, name && add_to_color);
+    Material m;
+    m.name = name;
+    m.type = MatType::Reflect;
+    for (int k = 0; k < 3; k++) m.color[k] = add_to_color[k];
+    c->scene.materials.push_back(m);
+    return 0;
+}
+
+int pe_scene_add_material_refract(pe_ctx* c, const char* name, const double add_to_color[3], double refractive_index) {
+    PE_NEED(c, name && add_to_color);
+    Material m;
+    m.name = name;
+    m.type = MatType::Refract;
+    for (int k = 0; k < 3; k++) m.color[k] = add_to_color[k];
+    m.refractive_index = refractive_index;
+    c->scene.materials.push_back(m);
+    return 0;
+}
+
+int pe_scene_add_material_complex(pe_ctx* c, const char* name, const char* glsl) {
+    PE_NEED(c, name && glsl);
+    Material m;
+    m.name = name;
+    m.type = MatType::Complex;
+    m.code = glsl;
+    c->scene.materials.push_back(m);
+    return 0;
+}
+
+static int add_object(pe_ctx* c, ObjClass cls, const char* name, int subspace, const char* a, const char* b, const char* code) {
+    Object o;
+    o.name = name;
+    o.cls = cls;
+    o.subspace = subspace;
+    o.matrix_a = a;
+    o.portal = b != nullptr;
+    if (b) o.matrix_b = b;
+    if (code) o.code = code;
+    c->scene.objects.push_back(o);
+    return 0;
+}
+
+int pe_scene_add_object_flat(pe_ctx* c, const char* name, int subspace, const char* matrix_a, const char* matrix_b,
+                             const char* is_inside_glsl) {
+    PE_NEED(c, name && matrix_a && is_inside_glsl);
+    if (subspace < 0 || subspace > 2) return c->fail("subspace must be PE_SUBSPACE_*");
+    return add_object(c, ObjClass::Flat, name, subspace, matrix_a, matrix_b, is_inside_glsl);
+}
+
+int pe_scene_add_object_complex(pe_ctx* c, const char* name, int subspace, const char* matrix_a, const char* matrix_b,
+                                const char* intersect_glsl) {
+    PE_NEED(c, name && matrix_a && intersect_glsl);
+    if (subspace < 0 || subspace > 2) return c->fail("subspace must be PE_SUBSPACE_*");
+    return add_object(c, ObjClass::Complex, name, subspace, matrix_a, matrix_b, intersect_glsl);
+}
+
+int pe_scene_add_object_debug_matrix(pe_ctx* c, const char* name, const char* matrix) {
+    PE_NEED(c, name && matrix);
+    return add_object(c, ObjClass::DebugMatrix, name, PE_SUBSPACE_BOTH, matrix, nullptr, nullptr);
+}
+
+int pe_scene_add_intersection_material(pe_ctx* c, const char* name, const char* glsl) {
+    PE_NEED(c, name && glsl);
+    c->scene.intersection_materials.push_back({name, glsl});
+    return 0;
+}
+
+int pe_scene_declare_uniform(pe_ctx* c, const char* name, int type) {
+    PE_NEED(c, name);
+    if (type < 0 || type > 2) return c->fail("uniform type must be PE_UNIFORM_*");
+    if (name[0] == '_') return c->fail(std::string("`") + name + "`: names starting with `_` are reserved for renderer uniforms");
+    c->scene.uniforms.push_back({name, type});
+    return 0;
+}
+
+int pe_scene_declare_texture(pe_ctx* c, const char* name) {
+    PE_NEED(c, name);
+    c->scene.textures.push_back(name);
+    return 0;
+}
+
+int pe_set_option(pe_ctx* c, const char* key, int value) {
+    if (!c || !key) return 1;
+    std::string k = key;
+    if (k == "persistent") c->opts.persistent = value != 0;
+    else if (k == "specialize_ints") c->opts.specialize_ints = value != 0;
+    else if (k == "block_threads") {
+        if (value < 32 || value > 1024 || value % 32) return c->fail("block_threads must be a multiple of 32 in [32, 1024]");
+        if (!c->opts.persistent && value != 128) { /* the 16x8 tile mapping needs 4 warps */ }
+        c->opts.block_threads = value;
+    } else if (k == "min_blocks") c->opts.min_blocks = value < 1 ? 1 : value;
+    else if (k == "lineinfo") c->lineinfo = value != 0;
+    else return c->fail("unknown option `" + k + "`");
+    // options change the generated program
+    if (c->has_gpu) {
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        for (auto& kv : c->variants)
+            if (kv.second->module) c->drv->cuModuleUnload(kv.second->module);
+    }
+    c->variants.clear();
+    c->current = nullptr;
+    return 0;
+}
+
+int pe_scene_compile(pe_ctx* c) {
+    if (!c) return 1;
+    if (!c->opts.persistent && c->opts.block_threads != 128) return c->fail("block_threads must be 128 unless persistent = 1");
+    return select_variant(c) ? 0 : 1;
+}
+
+const char* pe_scene_source(pe_ctx* c) { return (c && c->current) ? c->current->source.c_str() : ""; }
+
+int pe_scene_cubin(pe_ctx* c, const void** data, size_t* size) {
+    if (!c || !data || !size) return 1;
+    if (!c->current) return c->fail("no compiled program");
+    *data = c->current->cubin.data();
+    *size = c->current->cubin.size();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ uniforms
+int pe_set_uniform_mat4(pe_ctx* c, const char* name, const float m[16]) {
+    if (!c || !name || !m) return 1;
+    if (!c->layout_valid) {
+        c->pending_mat[name] = std::vector<float>(m, m + 16);
+        return 0;
+    }
+    auto it = c->layout.mat_slot.find(name);
+    if (it == c->layout.mat_slot.end()) return c->fail(std::string("unknown mat4 uniform `") + name + "`", 2);
+    std::memcpy(c->cblock.data() + c->layout.off_mat + size_t(it->second) * 64, m, 64);
+    return 0;
+}
+
+int pe_set_uniforms_mat4(pe_ctx* c, int n, const char* const* names, const float* values) {
+    if (!c || n < 0 || (n > 0 && (!names || !values))) return 1;
+    int rc = 0;
+    for (int k = 0; k < n; k++) {
+        int r = pe_set_uniform_mat4(c, names[k], values + 16 * size_t(k));
+        if (r) rc = r;
+    }
+    return rc;
+}
+
+int pe_set_uniform_f32(pe_ctx* c, const char* name, float v) {
+    if (!c || !name) return 1;
+    if (!c->layout_valid) {
+        c->pending_f[name] = v;
+        return 0;
+    }
+    std::string n = name;
+    if (n == "_tan_half_view" || n == "_resolution_x" || n == "_resolution_y")
+        return c->fail("`" + n + "` is derived by the library (from _view_angle / the render target)", 2);
+    auto it = c->layout.float_slot.find(n);
+    if (it == c->layout.float_slot.end()) return c->fail("unknown float uniform `" + n + "`", 2);
+    *fslot(c, it->second) = v;
+    if (n == "_view_angle") {
+        // frag.glsl:450 `tan(_view_angle / 2.)` -- a uniform expression, evaluated once here in fp32
+        *fslot(c, c->layout.float_slot["_tan_half_view"]) = std::tan(v / 2.0f);
+    }
+    return 0;
+}
+
+int pe_set_uniform_i32(pe_ctx* c, const char* name, int32_t v) {
+    if (!c || !name) return 1;
+    if (!c->layout_valid) {
+        c->pending_i[name] = v;
+        return 0;
+    }
+    auto it = c->layout.int_slot.find(name);
+    if (it == c->layout.int_slot.end()) return c->fail(std::string("unknown int uniform `") + name + "`", 2);
+    *islot(c, it->second) = v;
+    return 0;
+}
+
+int pe_set_texture(pe_ctx* c, const char* name, const uint8_t* rgba8, int w, int h) {
+    if (!c || !name || !rgba8 || w <= 0 || h <= 0) return c ? c->fail("pe_set_texture: bad arguments") : 1;
+    ensure_layout(c);
+    auto it = c->layout.tex_slot.find(name);
+    if (it == c->layout.tex_slot.end()) return c->fail(std::string("unknown texture `") + name + "`", 2);
+    if (!bind_device(c)) return 1;
+    Texture& t = c->textures[name];
+    size_t bytes = size_t(w) * size_t(h) * 4;
+    cudaStreamSynchronize(c->stream);
+    if (t.dev) cudaFree(t.dev);
+    t.dev = nullptr;
+    if (!cuda_ok(c, cudaMalloc(&t.dev, bytes), "cudaMalloc(texture)")) return 1;
+    if (!cuda_ok(c, cudaMemcpy(t.dev, rgba8, bytes, cudaMemcpyHostToDevice), "cudaMemcpy(texture)")) return 1;
+    t.w = w;
+    t.h = h;
+    uint8_t* rec = c->cblock.data() + c->layout.off_tex + size_t(it->second) * 16;
+    std::memcpy(rec, &t.dev, 8);
+    std::memcpy(rec + 8, &w, 4);
+    std::memcpy(rec + 12, &h, 4);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ render
+size_t pe_target_pixels(const pe_target* t) {
+    if (!t) return 0;
+    if (t->full_frame_layout) return size_t(t->width) * size_t(t->height);
+    return size_t(t->n_strips) * size_t(t->strip_rows) * size_t(t->width);
+}
+
+int pe_render(pe_ctx* c, const pe_target* t, void* out_device, void* bounces_device, void* stream) {
+    if (!c) return 1;
+    if (!out_device) return c->fail("pe_render: out_device is null");
+    if (!check_target(c, t) || !bind_device(c)) return 1;
+    ensure_layout(c);
+    *fslot(c, c->layout.float_slot["_resolution_x"]) = float(t->width);
+    *fslot(c, c->layout.float_slot["_resolution_y"]) = float(t->height);
+    if (!select_variant(c)) return 1;
+    Variant* v = c->current;
+    const DriverApi* d = c->drv;
+    CUstream_t s = stream ? (CUstream_t)stream : (CUstream_t)c->stream;
+
+    CUresult_t r = d->cuMemcpyHtoDAsync(v->const_ptr, c->cblock.data(), c->cblock.size(), s);
+    if (r != 0) return c->fail("uniform block upload: " + driver_error(d, r));
+
+    PeLaunchHost L;
+    std::memset(&L, 0, sizeof L);
+    L.out = out_device;
+    L.bounces = bounces_device;
+    L.width = t->width;
+    L.height = t->height;
+    L.strip_rows = t->strip_rows;
+    L.strip_first = t->strip_first;
+    L.strip_step = t->strip_step;
+    L.n_strips = t->n_strips;
+    L.out_full_frame = t->full_frame_layout ? 1 : 0;
+    const int local_rows = t->n_strips * t->strip_rows;
+    L.tiles_x = (t->width + 7) / 8;
+    L.tiles_y = (local_rows + 3) / 4;
+    L.queue = c->queue_dev;
+    void* args[] = {&L};
+    unsigned gx, gy;
+    if (c->opts.persistent) {
+        r = d->cuMemsetD32Async((CUdeviceptr_t)c->queue_dev, 0, 1, s);
+        if (r != 0) return c->fail("queue reset: " + driver_error(d, r));
+        gx = unsigned(c->sm_count * v->blocks_per_sm);
+        gy = 1;
+    } else {
+        gx = unsigned((t->width + 15) / 16);
+        gy = unsigned((local_rows + 7) / 8);
+    }
+    r = d->cuLaunchKernel(v->kernel, gx, gy, 1, unsigned(c->opts.block_threads), 1, 1, 0, s, args, nullptr);
+    if (r != 0) return c->fail("cuLaunchKernel(pe_render_kernel): " + driver_error(d, r));
+    c->launches++;
+    return 0;
+}
+
+static bool ensure_scratch(pe_ctx* c, void** p, size_t* have, size_t need) {
+    if (*have >= need) return true;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    if (!cuda_ok(c, cudaMalloc(p, need), "cudaMalloc(staging)")) return false;
+    *have = need;
+    return true;
+}
+
+int pe_render_host(pe_ctx* c, const pe_target* t, float* out_host) {
+    if (!c) return 1;
+    if (!out_host) return c->fail("pe_render_host: out_host is null");
+    if (!check_target(c, t) || !bind_device(c)) return 1;
+    size_t bytes = pe_target_pixels(t) * 16;
+    if (!ensure_scratch(c, &c->scratch_dev, &c->scratch_bytes, bytes)) return 1;
+    if (pe_render(c, t, c->scratch_dev, nullptr, nullptr)) return 1;
+    if (!cuda_ok(c, cudaMemcpyAsync(out_host, c->scratch_dev, bytes, cudaMemcpyDeviceToHost, c->stream), "D2H copy")) return 1;
+    return cuda_ok(c, cudaStreamSynchronize(c->stream), "pe_render_host") ? 0 : 1;
+}
+
+int pe_render_host_rgba8(pe_ctx* c, const pe_target* t, uint8_t* out_host) {
+    if (!c) return 1;
+    if (!out_host) return c->fail("pe_render_host_rgba8: out_host is null");
+    if (!check_target(c, t) || !bind_device(c)) return 1;
+    size_t n = pe_target_pixels(t);
+    if (!ensure_scratch(c, &c->scratch_dev, &c->scratch_bytes, n * 16)) return 1;
+    if (!ensure_scratch(c, &c->scratch8_dev, &c->scratch8_bytes, n * 4)) return 1;
+    if (pe_render(c, t, c->scratch_dev, nullptr, nullptr)) return 1;
+    if (!cuda_ok(c, (cudaError_t)launch_quantize_rgba8(c->scratch_dev, c->scratch8_dev, n, c->sm_count, c->stream), "quantize")) return 1;
+    c->launches++;
+    if (!cuda_ok(c, cudaMemcpyAsync(out_host, c->scratch8_dev, n * 4, cudaMemcpyDeviceToHost, c->stream), "D2H copy")) return 1;
+    return cuda_ok(c, cudaStreamSynchronize(c->stream), "pe_render_host_rgba8") ? 0 : 1;
+}
+
+int pe_sync(pe_ctx* c) {
+    if (!c) return 1;
+    if (!bind_device(c)) return 1;
+    return cuda_ok(c, cudaDeviceSynchronize(), "pe_sync") ? 0 : 1;
+}
+
+uint64_t pe_launch_count(pe_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------ multi-GPU helpers
+int pe_deinterleave_strips(pe_ctx* c, const void* gathered, void* frame, int width, int height, int strip_rows, int n_ranks,
+                           int strips_per_rank, void* stream) {
+    if (!c) return 1;
+    if (!gathered || !frame || width <= 0 || height <= 0 || strip_rows <= 0 || n_ranks <= 0 || strips_per_rank <= 0)
+        return c->fail("pe_deinterleave_strips: bad arguments");
+    if (!bind_device(c)) return 1;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    if (!cuda_ok(c, (cudaError_t)launch_deinterleave(gathered, frame, width, height, strip_rows, n_ranks, strips_per_rank,
+                                                    c->sm_count, s), "deinterleave")) return 1;
+    c->launches++;
+    return 0;
+}
+
+int pe_ipc_export(pe_ctx* c, void* p, uint8_t handle_out[64]) {
+    if (!c || !p || !handle_out) return 1;
+    if (!bind_device(c)) return 1;
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t");
+    if (!cuda_ok(c, cudaIpcGetMemHandle(&h, p), "cudaIpcGetMemHandle")) return 1;
+    std::memcpy(handle_out, &h, 64);
+    return 0;
+}
+
+int pe_ipc_open(pe_ctx* c, const uint8_t handle_in[64], void** out) {
+    if (!c || !handle_in || !out) return 1;
+    if (!bind_device(c)) return 1;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle_in, 64);
+    return cuda_ok(c, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle") ? 0 : 1;
+}
+
+int pe_ipc_close(pe_ctx* c, void* p) {
+    if (!c || !p) return 1;
+    if (!bind_device(c)) return 1;
+    return cuda_ok(c, cudaIpcCloseMemHandle(p), "cudaIpcCloseMemHandle") ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------ post-processing
+int pe_average_frames_rgba8(pe_ctx* c, const void* const* frames, int n_frames, void* out, size_t n_pixels, void* stream) {
+    if (!c) return 1;
+    if (!frames || !out || n_frames < 1) return c->fail("pe_average_frames_rgba8: bad arguments");
+    if (!bind_device(c)) return 1;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    if (!cuda_ok(c, (cudaError_t)launch_average_rgba8(frames, n_frames, out, n_pixels, c->sm_count, s), "average")) return 1;
+    c->launches++;
+    return 0;
+}
+
+int pe_quantize_rgba8(pe_ctx* c, const void* in, void* out, size_t n_pixels, void* stream) {
+    if (!c) return 1;
+    if (!in || !out) return c->fail("pe_quantize_rgba8: bad arguments");
+    if (!bind_device(c)) return 1;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    if (!cuda_ok(c, (cudaError_t)launch_quantize_rgba8(in, out, n_pixels, c->sm_count, s), "quantize")) return 1;
+    c->launches++;
+    return 0;
+}
+
+}  // extern "C"

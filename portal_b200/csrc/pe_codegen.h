@@ -1,0 +1,101 @@
+// Scene description + sm_100a program generator (host side of the C ABI).
+//
+// Plays the role of the reference's shader generator (`Scene::generate_shader_code`,
+// /root/reference/src/gui/scene.rs:693-1110) for a CUDA target: it walks the same scene
+// decomposition in the same order and emits one CUDA translation unit -- device headers
+// (pe_glsl.cuh, pe_library.cuh), the constant uniform block, the scene's GLSL snippets after a
+// lexical GLSL->CUDA rewrite, the per-object intersection sequence, the material chain, and
+// finally the hand-written ray-loop kernel (pe_kernel.cuh).
+#pragma once
+#include <cstdint>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+namespace pe_host {
+
+enum class ObjClass { Flat, Complex, DebugMatrix };
+enum class MatType { Simple, Reflect, Refract, Complex };
+
+struct Material {
+    std::string name;
+    MatType type = MatType::Simple;
+    double color[3] = {0, 0, 0};  // Simple.color / Reflect|Refract.add_to_color
+    double normal_coef = 0, grid_scale = 0, grid_coef = 0, refractive_index = 0;
+    bool grid = false, grid2 = false, grid3 = false;
+    std::string code;  // Complex
+};
+
+struct Object {
+    std::string name;
+    ObjClass cls = ObjClass::Flat;
+    bool portal = false;  // ObjectType::Portal(a, b) vs Simple(a)
+    int subspace = 0;     // PE_SUBSPACE_*
+    std::string matrix_a, matrix_b;
+    std::string code;  // is_inside / intersect snippet
+};
+
+struct NamedCode {
+    std::string name, code;
+};
+
+struct UniformDecl {
+    std::string name;
+    int type = 0;  // PE_UNIFORM_*
+};
+
+struct SceneDesc {
+    std::vector<NamedCode> library;
+    std::vector<Material> materials;
+    std::vector<Object> objects;
+    std::vector<NamedCode> intersection_materials;
+    std::vector<UniformDecl> uniforms;
+    std::vector<std::string> textures;
+};
+
+// Renderer ("_"-prefixed) uniforms, /root/reference/src/gui/scene.rs:497-535 -- the subset the
+// restated variants use.  Order defines the layout of the constant block's tail.
+extern const char* const kRendererFloats[];  // after the scene floats in f[]
+extern const int kNumRendererFloats;
+extern const char* const kRendererInts[];    // after the scene ints in i[]
+extern const int kNumRendererInts;
+
+// Byte layout of the constant block `PE_C` shared by generator and uploader.
+struct ConstLayout {
+    int n_mat = 0, n_float = 0, n_int = 0, n_tex = 0;  // scene-declared counts
+    std::vector<std::string> mats, floats, ints;       // declaration order
+    std::map<std::string, int> mat_slot, float_slot, int_slot, tex_slot;  // names incl. renderer ones
+    size_t off_mat = 0, off_float = 0, off_int = 0, off_tex = 0, size = 0;
+    int camera_slot = 0;  // m[n_mat]
+};
+ConstLayout make_layout(const SceneDesc& scene);
+
+struct GenOptions {
+    bool persistent = false;
+    bool specialize_ints = true;
+    int block_threads = 128;
+    int min_blocks = 1;
+};
+
+struct GenResult {
+    std::string source;
+    std::string error;  // non-empty on failure
+};
+
+// int_values: current value of every slot of i[] (scene ints then renderer ints); used when
+// opts.specialize_ints.
+GenResult generate_program(const SceneDesc& scene, const ConstLayout& layout, const GenOptions& opts,
+                           const std::vector<int>& int_values);
+
+// Lexical GLSL -> CUDA rewrite of one snippet (float-literal suffixes, swizzle accessors,
+// parameter qualifiers, !FOR_NUMBER! marker lines -- scene.rs:1066-1107 with the native defaults).
+// Appends the swizzles it met to `swizzles`.  Throws std::runtime_error on untokenisable input.
+std::string glsl_to_cuda(const std::string& glsl, std::set<std::string>& swizzles);
+
+// Text of the embedded device headers (generated into pe_device_src.inc at build time).
+extern const char* const kSrcGlsl;
+extern const char* const kSrcLibrary;
+extern const char* const kSrcKernel;
+
+}  // namespace pe_host

@@ -1,0 +1,48 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SCENES = ["basics", "monoportal", "triple_portal", "portal_in_portal", "mobius_monoportal"]
+# depth per BASELINE.json config
+DEPTH = {"basics": 4, "monoportal": 20, "triple_portal": 40, "portal_in_portal": 40, "mobius_monoportal": 64}
+# scenes whose per-pixel path uses no libm transcendental at the saved state -> bit-exact parity expected
+BIT_EXACT = ["basics", "monoportal", "triple_portal", "portal_in_portal"]
+REFERENCE = "/root/reference"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_ir(name):
+    with open(os.path.join(GOLDEN, "scenes", f"{name}.scene.json")) as f:
+        return json.load(f)
+
+
+def load_tex(name):
+    p = os.path.join(GOLDEN, "scenes", f"{name}.textures.npz")
+    if not os.path.exists(p):
+        return {}
+    with np.load(p) as z:
+        return {k: np.ascontiguousarray(z[k]) for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def have_reference():
+    return os.path.isdir(REFERENCE)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """Everything (CPU and GPU tests) talks to the in-tree libportal_b200.so."""
+    from portal_b200 import build
+    build.build()
+    return True

