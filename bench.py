@@ -162,8 +162,10 @@ def run_ours(args):
     r = SceneRenderer(ir, textures=load_textures(os.path.join(SCENE_DIR, f"{args.scene}.textures.npz")), device=local,
                       persistent=bool(args.persistent))
     r.render_depth = depth
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-NULL) stream: NULL means "the context's own stream" to the C ABI
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
 
     if world == 1:
         target = r.full_target(w, h)
