@@ -1,0 +1,630 @@
+#include "ph_scene.h"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+#include "../../../include/portal_b200.h"
+
+namespace ph {
+
+// ------------------------------------------------------------------------------ glam arithmetic
+// DMat4 as 16 doubles, column-major: m[4*c + r].
+Mat4 mat_identity() {
+    Mat4 m{};
+    m[0] = m[5] = m[10] = m[15] = 1.0;
+    return m;
+}
+
+static inline void mul_vec(const Mat4& m, const double v[4], double out[4]) {
+    // glam: x_axis*v.x + y_axis*v.y + z_axis*v.z + w_axis*v.w, left to right
+    for (int r = 0; r < 4; r++) {
+        double acc = m[r] * v[0];
+        acc = acc + m[4 + r] * v[1];
+        acc = acc + m[8 + r] * v[2];
+        acc = acc + m[12 + r] * v[3];
+        out[r] = acc;
+    }
+}
+
+Mat4 mat_mul(const Mat4& a, const Mat4& b) {
+    Mat4 o{};
+    for (int c = 0; c < 4; c++) mul_vec(a, &b[4 * c], &o[4 * c]);
+    return o;
+}
+
+// glam 0.13.1 DMat4::inverse: cofactor expansion (GLM formulation) scaled by 1/det; a zero
+// determinant is NOT trapped (glam_assert is a debug feature), so singular input yields Inf/NaN.
+Mat4 mat_inverse(const Mat4& m) {
+    const double m00 = m[0], m01 = m[1], m02 = m[2], m03 = m[3];
+    const double m10 = m[4], m11 = m[5], m12 = m[6], m13 = m[7];
+    const double m20 = m[8], m21 = m[9], m22 = m[10], m23 = m[11];
+    const double m30 = m[12], m31 = m[13], m32 = m[14], m33 = m[15];
+
+    const double coef00 = m22 * m33 - m32 * m23, coef02 = m12 * m33 - m32 * m13, coef03 = m12 * m23 - m22 * m13;
+    const double coef04 = m21 * m33 - m31 * m23, coef06 = m11 * m33 - m31 * m13, coef07 = m11 * m23 - m21 * m13;
+    const double coef08 = m21 * m32 - m31 * m22, coef10 = m11 * m32 - m31 * m12, coef11 = m11 * m22 - m21 * m12;
+    const double coef12 = m20 * m33 - m30 * m23, coef14 = m10 * m33 - m30 * m13, coef15 = m10 * m23 - m20 * m13;
+    const double coef16 = m20 * m32 - m30 * m22, coef18 = m10 * m32 - m30 * m12, coef19 = m10 * m22 - m20 * m12;
+    const double coef20 = m20 * m31 - m30 * m21, coef22 = m10 * m31 - m30 * m11, coef23 = m10 * m21 - m20 * m11;
+
+    const double fac0[4] = {coef00, coef00, coef02, coef03}, fac1[4] = {coef04, coef04, coef06, coef07};
+    const double fac2[4] = {coef08, coef08, coef10, coef11}, fac3[4] = {coef12, coef12, coef14, coef15};
+    const double fac4[4] = {coef16, coef16, coef18, coef19}, fac5[4] = {coef20, coef20, coef22, coef23};
+    const double vec0[4] = {m10, m00, m00, m00}, vec1[4] = {m11, m01, m01, m01};
+    const double vec2[4] = {m12, m02, m02, m02}, vec3[4] = {m13, m03, m03, m03};
+    const double sign_a[4] = {1.0, -1.0, 1.0, -1.0}, sign_b[4] = {-1.0, 1.0, -1.0, 1.0};
+
+    Mat4 inv{};
+    for (int k = 0; k < 4; k++) {
+        inv[k] = (vec1[k] * fac0[k] - vec2[k] * fac1[k] + vec3[k] * fac2[k]) * sign_a[k];
+        inv[4 + k] = (vec0[k] * fac0[k] - vec2[k] * fac3[k] + vec3[k] * fac4[k]) * sign_b[k];
+        inv[8 + k] = (vec0[k] * fac1[k] - vec1[k] * fac3[k] + vec3[k] * fac5[k]) * sign_a[k];
+        inv[12 + k] = (vec0[k] * fac2[k] - vec1[k] * fac4[k] + vec2[k] * fac5[k]) * sign_b[k];
+    }
+    const double d0 = m00 * inv[0], d1 = m01 * inv[4], d2 = m02 * inv[8], d3 = m03 * inv[12];
+    const double det = d0 + d1 + d2 + d3;
+    const double rcp = 1.0 / det;
+    for (double& x : inv) x = x * rcp;
+    return inv;
+}
+
+static void quat_mul(const double a[4], const double b[4], double o[4]) {
+    const double x0 = a[0], y0 = a[1], z0 = a[2], w0 = a[3], x1 = b[0], y1 = b[1], z1 = b[2], w1 = b[3];
+    o[0] = w0 * x1 + x0 * w1 + y0 * z1 - z0 * y1;
+    o[1] = w0 * y1 - x0 * z1 + y0 * w1 + z0 * x1;
+    o[2] = w0 * z1 + x0 * y1 - y0 * x1 + z0 * w1;
+    o[3] = w0 * w1 - x0 * x1 - y0 * y1 - z0 * z1;
+}
+
+// matrix.rs:537-547: DMat4::from_scale_rotation_translation(scale, Rx * Ry * Rz, offset)
+Mat4 mat_srt(const double scale[3], const double rotate[3], const double offset[3]) {
+    const double qx[4] = {std::sin(rotate[0] * 0.5), 0.0, 0.0, std::cos(rotate[0] * 0.5)};
+    const double qy[4] = {0.0, std::sin(rotate[1] * 0.5), 0.0, std::cos(rotate[1] * 0.5)};
+    const double qz[4] = {0.0, 0.0, std::sin(rotate[2] * 0.5), std::cos(rotate[2] * 0.5)};
+    double qxy[4], q[4];
+    quat_mul(qx, qy, qxy);
+    quat_mul(qxy, qz, q);
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double x2 = x + x, y2 = y + y, z2 = z + z;
+    const double xx = x * x2, xy = x * y2, xz = x * z2, yy = y * y2, yz = y * z2, zz = z * z2;
+    const double wx = w * x2, wy = w * y2, wz = w * z2;
+    Mat4 m{};
+    m[0] = (1.0 - (yy + zz)) * scale[0]; m[1] = (xy + wz) * scale[0]; m[2] = (xz - wy) * scale[0]; m[3] = 0.0 * scale[0];
+    m[4] = (xy - wz) * scale[1]; m[5] = (1.0 - (xx + zz)) * scale[1]; m[6] = (yz + wx) * scale[1]; m[7] = 0.0 * scale[1];
+    m[8] = (xz + wy) * scale[2]; m[9] = (yz - wx) * scale[2]; m[10] = (1.0 - (xx + yy)) * scale[2]; m[11] = 0.0 * scale[2];
+    m[12] = offset[0]; m[13] = offset[1]; m[14] = offset[2]; m[15] = 1.0;
+    return m;
+}
+
+static void v3_normalize(double v[3]) {
+    const double l = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const double r = 1.0 / l;
+    v[0] *= r; v[1] *= r; v[2] *= r;
+}
+static void v3_cross(const double a[3], const double b[3], double o[3]) {
+    o[0] = a[1] * b[2] - b[1] * a[2];
+    o[1] = a[2] * b[0] - b[2] * a[0];
+    o[2] = a[0] * b[1] - b[0] * a[1];
+}
+
+// RotateAroundCam::get_pos_vec / get_matrix (main.rs:278-304), teleport_matrix = identity, not free_movement
+Mat4 orbit_camera_matrix(const double look_at[3], double alpha, double beta, double r) {
+    const double pv[3] = {std::sin(beta) * std::cos(alpha) * r, std::cos(beta) * r, std::sin(beta) * std::sin(alpha) * r};
+    const double pos[3] = {pv[0] + look_at[0], pv[1] + look_at[1], pv[2] + look_at[2]};
+    double k[3] = {look_at[0] - pos[0], look_at[1] - pos[1], look_at[2] - pos[2]};
+    v3_normalize(k);
+    const double up[3] = {0.0, 1.0, 0.0};
+    double i[3], j[3];
+    v3_cross(k, up, i);
+    v3_normalize(i);
+    v3_cross(k, i, j);
+    v3_normalize(j);
+    Mat4 m{};
+    m[0] = i[0]; m[1] = i[1]; m[2] = i[2];
+    m[4] = j[0]; m[5] = j[1]; m[6] = j[2];
+    m[8] = k[0]; m[9] = k[1]; m[10] = k[2];
+    m[12] = pos[0]; m[13] = pos[1]; m[14] = pos[2]; m[15] = 1.0;
+    return mat_mul(mat_identity(), m);
+}
+
+// calc_scale (main.rs:1325-1333)
+double camera_scale(const Mat4& m) {
+    double s = 0.0;
+    for (int c = 0; c < 3; c++) s += std::sqrt(m[4 * c] * m[4 * c] + m[4 * c + 1] * m[4 * c + 1] + m[4 * c + 2] * m[4 * c + 2] + m[4 * c + 3] * m[4 * c + 3]);
+    return s / 3.0;
+}
+
+// ------------------------------------------------------------------------------ loading
+namespace {
+
+struct Loader {
+    Scene& sc;
+    explicit Loader(Scene& s) : sc(s) {}
+    bool ok = true;
+    void fail(const std::string& m) {
+        if (ok) sc.error = m;
+        ok = false;
+    }
+
+    // SerStorage<T>(Vec<Named<T>>) -> the inner list
+    const RonValue* storage(const RonValue& root, const char* field, bool required) {
+        const RonValue* v = root.get(field);
+        if (!v) {
+            if (required) fail(std::string("scene has no `") + field + "` section");
+            return nullptr;
+        }
+        if (v->kind == RonValue::List && v->items.size() == 1 && v->items[0]->kind == RonValue::List) return v->items[0].get();
+        if (v->kind == RonValue::List && v->items.empty()) return v;
+        fail(std::string("`") + field + "`: expected ([...])");
+        return nullptr;
+    }
+
+    static const RonValue* unwrap1(const RonValue* v) {  // newtype struct `(x)` -> x
+        while (v && v->kind == RonValue::List && v->items.size() == 1) v = v->items[0].get();
+        return v;
+    }
+
+    int add_uniform(const RonValue& data, const std::string& name) {
+        Uniform u;
+        if (data.kind != RonValue::Tagged) {
+            fail("uniform `" + name + "`: expected an enum variant");
+            return -1;
+        }
+        const RonValue* p = data.at(0);
+        if (data.s == "Bool") { u.kind = Uniform::Bool; u.b = p && p->b; }
+        else if (data.s == "Int") { u.kind = Uniform::Int; const RonValue* v = unwrap1(p); const RonValue* x = v ? v->get("value") : nullptr; u.i = x ? int(x->num()) : 0; }
+        else if (data.s == "Float") { u.kind = Uniform::Float; const RonValue* v = unwrap1(p); const RonValue* x = v ? v->get("value") : nullptr; u.f = x ? x->num() : 0.0; }
+        else if (data.s == "Angle") { u.kind = Uniform::Angle; u.f = p ? p->num() : 0.0; }
+        else if (data.s == "Progress") { u.kind = Uniform::Progress; u.f = p ? p->num() : 0.0; }
+        else if (data.s == "Formula" || data.s == "FormulaInt") {
+            u.kind = data.s == "Formula" ? Uniform::Formula : Uniform::FormulaInt;
+            const RonValue* t = unwrap1(p);
+            u.text = t && t->kind == RonValue::String ? t->s : "";
+        } else u.kind = Uniform::Unsupported;  // TrefoilSpecial: out of scope
+        int id = int(sc.uniforms.size());
+        sc.uniforms.push_back(u);
+        sc.uniform_names.push_back(name);
+        if (!name.empty() && !sc.uniform_by_name.count(name)) sc.uniform_by_name[name] = id;
+        return id;
+    }
+
+    int uniform_ref(const RonValue* ref) {
+        if (!ref || ref->kind == RonValue::Null) return -1;
+        if (ref->is_tag("Named")) {
+            auto it = sc.uniform_by_name.find(ref->at(0) ? ref->at(0)->s : "");
+            return it == sc.uniform_by_name.end() ? -1 : it->second;
+        }
+        if (ref->is_tag("Inline") && ref->at(0)) return add_uniform(*ref->at(0), "");
+        return -1;
+    }
+
+    Param param(const RonValue* p) {
+        Param out;
+        if (!p) return out;
+        if (p->is_tag("Value")) out.value = p->at(0) ? p->at(0)->num() : 0.0;
+        else if (p->is_tag("Uniform")) { out.is_uniform = true; out.uniform = uniform_ref(p->at(0)); }
+        return out;
+    }
+
+    int matrix_ref(const RonValue* ref) {
+        if (!ref || ref->kind == RonValue::Null) return -1;
+        if (ref->is_tag("Named")) {
+            auto it = sc.matrix_by_name.find(ref->at(0) ? ref->at(0)->s : "");
+            return it == sc.matrix_by_name.end() ? -1 : it->second;
+        }
+        if (ref->is_tag("Inline") && ref->at(0)) {
+            int id = int(sc.matrices.size());
+            sc.matrices.emplace_back();
+            sc.matrix_names.emplace_back();
+            Matrix m = matrix_from(*ref->at(0));
+            sc.matrices[id] = m;
+            return id;
+        }
+        return -1;
+    }
+
+    void vec3(const RonValue* v, double out[3]) {
+        for (int k = 0; k < 3; k++) out[k] = (v && v->at(k)) ? v->at(k)->num() : 0.0;
+    }
+    void tvec(const RonValue* v, Param* out, int n) {
+        static const char* names[4] = {"x", "y", "z", "w"};
+        for (int k = 0; k < n; k++) out[k] = param(v ? v->get(names[k]) : nullptr);
+    }
+
+    Matrix matrix_from(const RonValue& m) {
+        Matrix o;
+        if (m.kind != RonValue::Tagged) { fail("matrix: expected an enum variant"); return o; }
+        const std::string& t = m.s;
+        if (t == "Mul") { o.kind = Matrix::Mul; o.a = matrix_ref(m.get("to")); o.b = matrix_ref(m.get("what")); }
+        else if (t == "Teleport") { o.kind = Matrix::Teleport; o.a = matrix_ref(m.get("first_portal")); o.b = matrix_ref(m.get("second_portal")); o.c = matrix_ref(m.get("what")); }
+        else if (t == "Simple") {
+            o.kind = Matrix::Simple;
+            vec3(m.get("offset"), o.offset);
+            vec3(m.get("rotate"), o.rotate);
+            o.scale = m.get("scale") ? m.get("scale")->num() : 1.0;
+            const RonValue* mir = m.get("mirror");
+            for (int k = 0; k < 3; k++) o.mirror[k] = mir && mir->at(k) && mir->at(k)->b;
+        } else if (t == "Parametrized") {
+            o.kind = Matrix::Parametrized;
+            tvec(m.get("offset"), o.p + 0, 3);
+            tvec(m.get("rotate"), o.p + 3, 3);
+            tvec(m.get("mirror"), o.p + 6, 3);
+            o.p[9] = param(m.get("scale"));
+        } else if (t == "Exact") {
+            o.kind = Matrix::Exact;
+            tvec(m.get("i"), o.p + 0, 3); tvec(m.get("j"), o.p + 3, 3); tvec(m.get("k"), o.p + 6, 3); tvec(m.get("pos"), o.p + 9, 3);
+        } else if (t == "ExactFull") {
+            o.kind = Matrix::ExactFull;
+            tvec(m.get("c0"), o.p + 0, 4); tvec(m.get("c1"), o.p + 4, 4); tvec(m.get("c2"), o.p + 8, 4); tvec(m.get("c3"), o.p + 12, 4);
+        } else if (t == "If") { o.kind = Matrix::If; o.p[0] = param(m.get("condition")); o.a = matrix_ref(m.get("then")); o.b = matrix_ref(m.get("otherwise")); }
+        else if (t == "Sqrt") { o.kind = Matrix::Sqrt; o.a = matrix_ref(m.at(0)); }
+        else if (t == "Lerp") { o.kind = Matrix::Lerp; o.p[0] = param(m.get("t")); o.a = matrix_ref(m.get("first")); o.b = matrix_ref(m.get("second")); }
+        else if (t == "Camera") o.kind = Matrix::Camera;
+        else if (t == "Inv") { o.kind = Matrix::Inv; o.a = matrix_ref(m.at(0)); }
+        else fail("unknown matrix kind `" + t + "`");
+        return o;
+    }
+
+    static std::string code_of(const RonValue* v) {
+        v = unwrap1(v);
+        return v && v->kind == RonValue::String ? v->s : "";
+    }
+
+    void load(const RonValue& root) {
+        if (root.kind != RonValue::Struct) { fail("scene file: expected a struct at top level"); return; }
+        if (const RonValue* cam = root.get("cam")) {
+            vec3(cam->get("look_at"), sc.look_at);
+            if (cam->get("alpha")) sc.alpha = cam->get("alpha")->num();
+            if (cam->get("beta")) sc.beta = cam->get("beta")->num();
+            if (cam->get("r")) sc.r = cam->get("r")->num();
+            if (cam->get("offset_after_material")) sc.offset_after_material = cam->get("offset_after_material")->num();
+        }
+        if (const RonValue* t = root.get("use_time")) sc.use_time = t->b;
+        if (const RonValue* s = root.get("skybox")) sc.has_skybox = s->kind != RonValue::Null;
+
+        // uniforms (scene_serialized.rs:1114-1117)
+        if (const RonValue* us = storage(root, "uniforms", true))
+            for (auto& it : us->items) {
+                const RonValue* n = it->get("name");
+                const RonValue* d = it->get("data");
+                if (n && d) add_uniform(*d, n->s);
+            }
+        // matrices, two passes (:1119-1136)
+        const RonValue* ms = storage(root, "matrices", true);
+        if (ms) {
+            for (auto& it : ms->items) {
+                const RonValue* n = it->get("name");
+                std::string name = n ? n->s : "";
+                if (!sc.matrix_by_name.count(name)) sc.matrix_by_name[name] = int(sc.matrices.size());
+                sc.matrices.emplace_back();
+                sc.matrix_names.push_back(name);
+            }
+            for (size_t k = 0; k < ms->items.size(); k++) {
+                const RonValue* d = ms->items[k]->get("data");
+                if (d) {
+                    Matrix m = matrix_from(*d);
+                    sc.matrices[k] = m;
+                }
+            }
+        }
+        // objects (:1138-1177)
+        if (const RonValue* os = storage(root, "objects", true))
+            for (auto& it : os->items) {
+                const RonValue* n = it->get("name");
+                const RonValue* d = it->get("data");
+                if (!n || !d || d->kind != RonValue::Tagged) continue;
+                SceneObject o;
+                o.name = n->s;
+                if (d->s == "DebugMatrix") {
+                    o.cls = SceneObject::DebugMatrix;
+                    o.matrix_a = matrix_ref(d->at(0));
+                    o.subspace = PE_SUBSPACE_BOTH;
+                } else {
+                    o.cls = d->s == "Flat" ? SceneObject::Flat : SceneObject::Complex;
+                    const RonValue* kind = d->get("kind");
+                    if (kind && kind->is_tag("Portal")) {
+                        o.portal = true;
+                        o.matrix_a = matrix_ref(kind->at(0));
+                        o.matrix_b = matrix_ref(kind->at(1));
+                    } else if (kind) {
+                        o.matrix_a = matrix_ref(kind->at(0));
+                    }
+                    o.code = code_of(d->get(o.cls == SceneObject::Flat ? "is_inside" : "intersect"));
+                    const RonValue* sub = d->get("in_subspace");
+                    o.subspace = !sub ? PE_SUBSPACE_NORMAL : sub->is_tag("Subspace") ? PE_SUBSPACE_SUBSPACE : sub->is_tag("Both") ? PE_SUBSPACE_BOTH : PE_SUBSPACE_NORMAL;
+                }
+                sc.objects.push_back(o);
+            }
+        if (const RonValue* ts = storage(root, "textures", true))
+            for (auto& it : ts->items)
+                if (it->get("name")) sc.textures.emplace_back(it->get("name")->s, code_of(it->get("data")));
+        if (const RonValue* mats = storage(root, "materials", true))
+            for (auto& it : mats->items) {
+                const RonValue* n = it->get("name");
+                const RonValue* d = it->get("data");
+                if (!n || !d || d->kind != RonValue::Tagged) continue;
+                SceneMaterial m;
+                m.name = n->s;
+                auto num = [&](const char* f, double dflt) { return d->get(f) ? d->get(f)->num() : dflt; };
+                auto flag = [&](const char* f) { return d->get(f) && d->get(f)->b; };
+                if (d->s == "Simple") {
+                    m.type = SceneMaterial::Simple;
+                    vec3(d->get("color"), m.color);
+                    m.normal_coef = num("normal_coef", 0);
+                    m.grid = flag("grid");
+                    m.grid_scale = num("grid_scale", 0);
+                    m.grid_coef = num("grid_coef", 0);
+                    m.grid2 = flag("grid2");
+                    m.grid3 = flag("grid3");
+                } else if (d->s == "Reflect") {
+                    m.type = SceneMaterial::Reflect;
+                    vec3(d->get("add_to_color"), m.color);
+                } else if (d->s == "Refract") {
+                    m.type = SceneMaterial::Refract;
+                    vec3(d->get("add_to_color"), m.color);
+                    m.refractive_index = num("refractive_index", 1);
+                } else {
+                    m.type = SceneMaterial::Complex;
+                    m.code = code_of(d->get("code"));
+                }
+                sc.materials.push_back(m);
+            }
+        if (const RonValue* ims = storage(root, "intersection_materials", false))
+            for (auto& it : ims->items)
+                if (it->get("name")) sc.intersection_materials.emplace_back(it->get("name")->s, code_of(it->get("data")));
+        if (const RonValue* libs = storage(root, "library", true))
+            for (auto& it : libs->items)
+                if (it->get("name")) sc.library.emplace_back(it->get("name")->s, code_of(it->get("data")));
+    }
+};
+
+// easing.rs:6-44
+double easing_in(double t) { return 1.0 - std::cos(t * M_PI * 0.5); }
+double easing_out(double t) { return 1.0 - easing_in(1.0 - t); }
+double easing_in_out(double t) { return (1.0 - std::cos(t * M_PI)) * 0.5; }
+double easing_in_out_fast(double t) { return easing_in_out(easing_in_out(t)); }
+double easing_plus_minus(double t) {
+    t *= 2.0 * M_PI;
+    const double t2 = 2.0 * t;
+    return std::sin(t) * (3.0 - std::cos(t) - std::cos(t2) - std::cos(t) * std::cos(t2)) / 4.0;
+}
+double easing_elastic_out(double x) {
+    const double c4 = (2.0 * M_PI) / 3.0;
+    if (x == 0.0) return 0.0;
+    if (x == 1.0) return 1.0;
+    return std::pow(2.0, -10.0 * x) * std::sin((x * 10.0 - 0.75) * c4) + 1.0;
+}
+
+}  // namespace
+
+bool Scene::load(const RonValue& root) {
+    Loader l(*this);
+    l.load(root);
+    return l.ok;
+}
+
+std::string Scene::matrix_uniform_stem(int id) const {
+    return matrix_names[id].empty() ? "id" + std::to_string(id) : matrix_names[id];
+}
+
+bool Scene::get_uniform(int id, int& kind, double& value, std::vector<int>& visited) {
+    if (id < 0 || id >= int(uniforms.size())) return false;
+    if (std::find(visited.begin(), visited.end(), id) != visited.end()) return false;  // storage2.rs:158-160
+    Uniform& u = uniforms[id];
+    switch (u.kind) {
+        case Uniform::Bool: kind = 0; value = u.b ? 1.0 : 0.0; return true;
+        case Uniform::Int: kind = 1; value = double(u.i); return true;
+        case Uniform::Float: case Uniform::Angle: case Uniform::Progress: kind = 2; value = u.f; return true;
+        case Uniform::Unsupported: return false;
+        default: break;
+    }
+    if (!u.parsed && !u.parse_failed) {
+        std::string err;
+        u.parsed = formula_parse(u.text, err);
+        u.parse_failed = !u.parsed;
+    }
+    if (!u.parsed) return false;
+    visited.push_back(id);
+    // the reference's `cb` closure, uniform.rs:1014-1124
+    FormulaNamespace ns = [&](const std::string& name, const std::vector<double>& a, double& out) -> bool {
+        auto arg = [&](size_t k) -> double {
+            if (k >= a.size()) throw std::runtime_error(name + ": missing argument");
+            return a[k];
+        };
+        auto truthy = [](double x) { return std::fabs(x - 1.0) < 1e-6; };
+        if (name == "if") out = truthy(arg(0)) ? arg(1) : arg(2);
+        else if (name == "and") out = (truthy(arg(0)) && truthy(arg(1))) ? 1.0 : 0.0;
+        else if (name == "or") out = (truthy(arg(0)) || truthy(arg(1))) ? 1.0 : 0.0;
+        else if (name == "not") out = truthy(arg(0)) ? 0.0 : 1.0;
+        else if (name == "deg2rad") out = arg(0) / 180.0 * M_PI;
+        else if (name == "rad2deg") out = arg(0) * 180.0 / M_PI;
+        else if (name == "switch") {
+            double idx = arg(0);
+            size_t k = (std::isnan(idx) || idx < 0) ? 0 : size_t(idx);
+            out = arg(k);
+        } else if (name == "on") {
+            double v = arg(0), lo = arg(1), hi = arg(2);
+            out = v < lo ? 0.0 : (v > hi ? 1.0 : (v - lo) / (hi - lo));
+        } else if (name == "inv") out = 1.0 - arg(0);
+        else if (name == "sqrt") out = std::sqrt(arg(0));
+        else if (name == "atan2") out = std::atan2(arg(0), arg(1));
+        else if (name == "time") out = time;
+        else if (name == "total_time") out = total_time;
+        else if (name == "easing_linear") out = arg(0);
+        else if (name == "easing_in") out = easing_in(arg(0));
+        else if (name == "easing_out") out = easing_out(arg(0));
+        else if (name == "easing_in_out") out = easing_in_out(arg(0));
+        else if (name == "easing_in_out_fast") out = easing_in_out_fast(arg(0));
+        else if (name == "easing_plus_minus") out = easing_plus_minus(arg(0));
+        else if (name == "easing_elastic_out") out = easing_elastic_out(arg(0));
+        else if (name == "bump") {
+            double x = (arg(0) - arg(1)) / arg(2);
+            out = std::fabs(x) < 1.0 ? 0.5 * (1.0 + std::cos(M_PI * x)) : 0.0;
+        } else if (name == "later_start") {
+            double t = arg(0), tm = 1.0 - arg(1);
+            out = std::fmax(0.0, t / tm - (1.0 - tm) / tm);
+        } else if (name == "early_finish") out = std::fmin(1.0, arg(0) / arg(1));
+        else if (name == "lerp") out = (1.0 - arg(2)) * arg(0) + arg(2) * arg(1);  // emath::lerp
+        else {
+            auto it = uniform_by_name.find(name);
+            if (it == uniform_by_name.end()) return false;
+            int k;
+            double v;
+            if (!get_uniform(it->second, k, v, visited)) return false;
+            out = v;
+        }
+        return true;
+    };
+    double v = 0.0;
+    std::string err;
+    bool ok = formula_eval(u.parsed, ns, v, err);
+    visited.pop_back();
+    if (!ok) return false;
+    if (u.kind == Uniform::Formula) {
+        kind = 2;
+        value = v;
+    } else {  // `as i32`: saturating, NaN -> 0
+        kind = 1;
+        value = std::isnan(v) ? 0.0 : std::trunc(std::fmax(-2147483648.0, std::fmin(2147483647.0, v)));
+    }
+    return true;
+}
+
+bool Scene::get_param(const Param& p, double& out) {
+    if (!p.is_uniform) {
+        out = p.value;
+        return true;
+    }
+    int k;
+    std::vector<int> visited;
+    return get_uniform(p.uniform, k, out, visited);
+}
+
+bool Scene::get_matrix(int id, Mat4& out, std::vector<int>& visited) {
+    if (id < 0 || id >= int(matrices.size())) return false;
+    if (std::find(visited.begin(), visited.end(), id) != visited.end()) return false;
+    visited.push_back(id);
+    const Matrix m = matrices[id];
+    bool ok = true;
+    Mat4 A, B, Cc;
+    switch (m.kind) {
+        case Matrix::Mul:  // what * to (matrix.rs:517-521)
+            ok = get_matrix(m.a, A, visited) && get_matrix(m.b, B, visited);
+            if (ok) out = mat_mul(B, A);
+            break;
+        case Matrix::Teleport:  // second * first^-1 * what (:522-531)
+            ok = get_matrix(m.a, A, visited) && get_matrix(m.b, B, visited) && get_matrix(m.c, Cc, visited);
+            if (ok) out = mat_mul(mat_mul(B, mat_inverse(A)), Cc);
+            break;
+        case Matrix::Simple: {
+            const double s[3] = {m.scale * (m.mirror[0] ? -1.0 : 1.0), m.scale * (m.mirror[1] ? -1.0 : 1.0), m.scale * (m.mirror[2] ? -1.0 : 1.0)};
+            out = mat_srt(s, m.rotate, m.offset);
+            break;
+        }
+        case Matrix::Parametrized: {
+            double v[10];
+            for (int k : {9, 6, 7, 8, 3, 4, 5, 0, 1, 2})  // evaluation order of matrix.rs:555-569
+                if (!get_param(m.p[k], v[k])) { ok = false; break; }
+            if (ok) {
+                const double s[3] = {v[9] * (1.0 - 2.0 * v[6]), v[9] * (1.0 - 2.0 * v[7]), v[9] * (1.0 - 2.0 * v[8])};
+                out = mat_srt(s, v + 3, v + 0);
+            }
+            break;
+        }
+        case Matrix::Exact: {
+            out = Mat4{};
+            for (int c = 0; c < 4 && ok; c++) {
+                for (int r = 0; r < 3 && ok; r++) ok = get_param(m.p[3 * c + r], out[4 * c + r]);
+                out[4 * c + 3] = c == 3 ? 1.0 : 0.0;
+            }
+            break;
+        }
+        case Matrix::ExactFull:
+            for (int k = 0; k < 16 && ok; k++) ok = get_param(m.p[k], out[k]);
+            break;
+        case Matrix::If: {
+            double c;
+            ok = get_param(m.p[0], c);
+            if (ok) ok = c > 0.5 ? get_matrix(m.a, out, visited) : get_matrix(m.b, out, visited);
+            break;
+        }
+        case Matrix::Inv:
+            ok = get_matrix(m.a, A, visited);
+            if (ok) out = mat_inverse(A);
+            break;
+        case Matrix::Camera:
+            out = camera_matrix_for_formulas;
+            break;
+        case Matrix::Sqrt:
+        case Matrix::Lerp:
+            error = "matrix kinds Sqrt / Lerp are not implemented yet (SURVEY.md §8 f1)";
+            ok = false;
+            break;
+    }
+    visited.pop_back();
+    return ok;
+}
+
+bool Scene::uniform_table(std::vector<TableEntry>& out) {
+    out.clear();
+    std::map<std::string, size_t> index;
+    auto put_mat = [&](const std::string& name, const Mat4& m) {
+        auto it = index.find(name);
+        if (it != index.end()) {
+            out[it->second].m = m;
+            return;
+        }
+        index[name] = out.size();
+        TableEntry e;
+        e.name = name;
+        e.type = PE_UNIFORM_MAT4;
+        e.m = m;
+        out.push_back(e);
+    };
+    // passed_matrices: object-referenced, then every named matrix (scene.rs:551-592)
+    std::vector<int> ids;
+    for (const SceneObject& o : objects) {
+        if (o.cls == SceneObject::DebugMatrix) {
+            if (o.matrix_a >= 0) ids.push_back(o.matrix_a);
+        } else if (o.portal) {
+            if (o.matrix_a >= 0 && o.matrix_b >= 0) { ids.push_back(o.matrix_a); ids.push_back(o.matrix_b); }
+        } else if (o.matrix_a >= 0) ids.push_back(o.matrix_a);
+    }
+    for (size_t k = 0; k < matrices.size(); k++)
+        if (!matrix_names[k].empty()) ids.push_back(int(k));
+    for (int id : ids) {
+        Mat4 m;
+        std::vector<int> visited;
+        if (!get_matrix(id, m, visited)) continue;  // "matrix can't be getted": logged and skipped (scene.rs:589-591)
+        const std::string stem = matrix_uniform_stem(id);
+        put_mat(stem + "_mat", m);
+        put_mat(stem + "_mat_inv", mat_inverse(m));
+    }
+    // teleport matrices (scene.rs:594-635)
+    for (const SceneObject& o : objects) {
+        if (o.cls == SceneObject::DebugMatrix || !o.portal || o.matrix_a < 0 || o.matrix_b < 0) continue;
+        Mat4 ma, mb;
+        std::vector<int> v1, v2;
+        if (!get_matrix(o.matrix_a, ma, v1) || !get_matrix(o.matrix_b, mb, v2)) continue;
+        const std::string na = matrix_uniform_stem(o.matrix_a), nb = matrix_uniform_stem(o.matrix_b);
+        put_mat(na + "_to_" + nb + "_mat_teleport", mat_mul(mb, mat_inverse(ma)));
+        if (na != nb) put_mat(nb + "_to_" + na + "_mat_teleport", mat_mul(ma, mat_inverse(mb)));
+    }
+    // scalars (scene.rs:637-656)
+    for (size_t k = 0; k < uniforms.size(); k++) {
+        if (uniform_names[k].empty()) continue;
+        int kind;
+        double v;
+        std::vector<int> visited;
+        if (!get_uniform(int(k), kind, v, visited)) continue;
+        TableEntry e;
+        e.name = uniform_names[k] + "_u";
+        if (kind == 2) { e.type = PE_UNIFORM_FLOAT; e.f = v; }
+        else { e.type = PE_UNIFORM_INT; e.i = int(v); }
+        out.push_back(e);
+    }
+    return true;
+}
+
+}  // namespace ph

@@ -1,0 +1,113 @@
+// Host-side scene model: loader, uniform / matrix evaluation, camera.
+//
+// Mirrors the parts of the reference's Rust host that feed the ray loop every frame
+// (SURVEY.md §8a rows U, M, C):
+//   scene load + name resolution   /root/reference/src/gui/scene_serialized.rs:1102-1477
+//   AnyUniform evaluation          /root/reference/src/gui/uniform.rs:268-296, :1009-1140
+//   Matrix DAG evaluation (f64)    /root/reference/src/gui/matrix.rs:510-631
+//   uniform table + upload order   /root/reference/src/gui/scene.rs:424-658
+//   orbit camera                   /root/reference/src/main.rs:278-304, :1325-1333
+// glam 0.13.1's DMat4 / DQuat arithmetic (un-vendored) is implemented operation by operation
+// in ph_scene.cpp so that singular matrices give the same Inf/NaN patterns.
+#pragma once
+#include <array>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ph_formula.h"
+#include "ph_ron.h"
+
+namespace ph {
+
+using Mat4 = std::array<double, 16>;  // column-major
+
+Mat4 mat_identity();
+Mat4 mat_mul(const Mat4& a, const Mat4& b);
+Mat4 mat_inverse(const Mat4& m);
+Mat4 mat_srt(const double scale[3], const double rotate[3], const double offset[3]);
+Mat4 orbit_camera_matrix(const double look_at[3], double alpha, double beta, double r);
+double camera_scale(const Mat4& m);
+
+struct Uniform {
+    enum Kind { Bool, Int, Float, Angle, Progress, Formula, FormulaInt, Unsupported } kind = Float;
+    bool b = false;
+    int i = 0;
+    double f = 0.0;
+    std::string text;
+    FormulaPtr parsed;  // lazily parsed
+    bool parse_failed = false;
+};
+
+struct Param {  // ParametrizeOrNot (uniform.rs:487-497)
+    bool is_uniform = false;
+    double value = 0.0;
+    int uniform = -1;  // index into Scene::uniforms, -1 = None
+};
+
+struct Matrix {
+    enum Kind { Mul, Teleport, Simple, Parametrized, Exact, ExactFull, If, Sqrt, Lerp, Camera, Inv } kind = Simple;
+    int a = -1, b = -1, c = -1;       // matrix refs (Mul: to, what; Teleport: first, second, what; If: then, otherwise; Inv/Sqrt: a)
+    double offset[3] = {0, 0, 0}, rotate[3] = {0, 0, 0}, scale = 1.0;
+    bool mirror[3] = {false, false, false};
+    Param p[16];                       // Parametrized: offset[0..2] rotate[3..5] mirror[6..8] scale[9]; Exact*: columns; If/Lerp: p[0]
+};
+
+struct SceneObject {
+    std::string name;
+    enum Class { Flat, Complex, DebugMatrix } cls = Flat;
+    bool portal = false;
+    int subspace = 0;
+    int matrix_a = -1, matrix_b = -1;
+    std::string code;
+};
+
+struct SceneMaterial {
+    std::string name;
+    enum Type { Simple, Reflect, Refract, Complex } type = Simple;
+    double color[3] = {0, 0, 0};
+    double normal_coef = 0, grid_scale = 0, grid_coef = 0, refractive_index = 0;
+    bool grid = false, grid2 = false, grid3 = false;
+    std::string code;
+};
+
+struct TableEntry {
+    std::string name;
+    int type = 0;  // PE_UNIFORM_*
+    Mat4 m{};
+    double f = 0.0;
+    int i = 0;
+};
+
+struct Scene {
+    // saved camera (CamSettings, scene.rs) + per-scene `_offset_after_material`
+    double look_at[3] = {0, 0, 0}, alpha = 0, beta = 0, r = 1, offset_after_material = 0.005;
+    bool use_time = false;
+    double time = 0.0, total_time = 0.0;
+    Mat4 camera_matrix_for_formulas = mat_identity();
+
+    std::vector<Uniform> uniforms;
+    std::vector<std::string> uniform_names;  // "" for inline
+    std::map<std::string, int> uniform_by_name;
+    std::vector<Matrix> matrices;
+    std::vector<std::string> matrix_names;   // "" for inline
+    std::map<std::string, int> matrix_by_name;
+    std::vector<SceneObject> objects;
+    std::vector<SceneMaterial> materials;
+    std::vector<std::pair<std::string, std::string>> intersection_materials, library, textures;  // (name, code|path)
+    bool has_skybox = false;
+    std::string error;
+
+    // deserialize_scene_new_format
+    bool load(const RonValue& root);
+    std::string matrix_uniform_stem(int id) const;  // object.rs:188-193: name or "id<N>"
+    // AnyUniform::get -> (kind 0 bool / 1 int / 2 float, value); false = None
+    bool get_uniform(int id, int& kind, double& value, std::vector<int>& visited);
+    bool get_param(const Param& p, double& out);
+    // Matrix::get; false = None
+    bool get_matrix(int id, Mat4& out, std::vector<int>& visited);
+    // Scene::uniforms + Scene::set_uniforms: the evaluated table in upload order
+    bool uniform_table(std::vector<TableEntry>& out);
+};
+
+}  // namespace ph
