@@ -1,0 +1,85 @@
+/* portal_b200 host front-end -- the caller side of the ray-loop boundary, in C.
+ *
+ * north_star keeps the host code in the reference's language (Rust: Scene loader, uniform /
+ * matrix evaluation, orbit camera).  There is no Rust toolchain in this image, so the same host
+ * logic is provided here in C++ behind a C API, mirroring the reference's interfaces:
+ *
+ *   ph_scene_load_ron        ron::from_str + Scene::from_serialized   src/main.rs:2882-2885,
+ *                                                                     src/gui/scene_serialized.rs:1102-1477
+ *   ph_scene_set_time        Scene::update (formula `time`)           src/gui/scene.rs:1353-1428
+ *   ph_scene_uniform_*       Scene::uniforms / set_uniforms           src/gui/scene.rs:424-658
+ *   ph_scene_build_program   Scene::get_new_material                  src/gui/scene.rs:1112-1176
+ *   ph_scene_upload_uniforms Scene::set_uniforms -> material          src/gui/scene.rs:545-658
+ *   ph_orbit_camera_matrix   RotateAroundCam::get_matrix              src/main.rs:278-304
+ *   ph_camera_scale          calc_scale                               src/main.rs:1325-1333
+ *   ph_renderer_*            SceneRenderer::{new, set_uniforms, draw_texture} + render_frame
+ *                                                                     src/main.rs:934-1064, 1266-1359,
+ *                                                                     1411-1428, 2876-2946
+ * A Rust maintainer would NOT need this file: the existing Rust Scene / SceneRenderer would call
+ * include/portal_b200.h directly.  It exists so that the whole path -- .ron in,
+ * pixels out -- runs and is tested here.
+ */
+#ifndef PORTAL_B200_HOST_H
+#define PORTAL_B200_HOST_H
+
+#include "portal_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ph_scene ph_scene;
+
+/* Parse a scene file (RON text). Returns NULL on failure; the message is copied into err. */
+PE_API ph_scene* ph_scene_load_ron(const char* ron_text, size_t len, char* err, size_t err_len);
+PE_API void ph_scene_free(ph_scene* s);
+PE_API const char* ph_scene_last_error(ph_scene* s);
+
+/* Formula variables `time` / `total_time` (0 for a freshly loaded scene). */
+PE_API int ph_scene_set_time(ph_scene* s, double time, double total_time);
+/* Override the value of a named Bool / Int / Float / Angle / Progress uniform (the editor's sliders). */
+PE_API int ph_scene_set_value(ph_scene* s, const char* uniform_name, double value);
+
+/* Evaluate every uniform and matrix (float64) and build the table Scene::set_uniforms uploads.
+ * Returns the number of entries, or -1. */
+PE_API int ph_scene_evaluate(ph_scene* s);
+/* Entry k of the last evaluation: full GLSL name, PE_UNIFORM_* type, and its value(s) in float64:
+ * 16 (column-major) for a mat4, 1 otherwise. */
+PE_API int ph_scene_uniform_get(ph_scene* s, int k, const char** name, int* type, double values[16]);
+
+/* Saved camera (CamSettings): look_at[3], alpha, beta, r, offset_after_material. */
+PE_API int ph_scene_camera(ph_scene* s, double look_at[3], double* alpha, double* beta, double* r,
+                           double* offset_after_material);
+/* Texture k: name and file path as stored in the scene; returns 0 while k is in range. */
+PE_API int ph_scene_texture(ph_scene* s, int k, const char** name, const char** path);
+/* Counts: 0 objects, 1 materials, 2 intersection materials, 3 library entries, 4 textures. */
+PE_API int ph_scene_count(ph_scene* s, int what);
+
+/* Describe the scene program to a renderer context (pe_scene_begin ... pe_scene_declare_*),
+ * i.e. what Scene::get_new_material hands to load_material.  Does not compile. */
+PE_API int ph_scene_build_program(ph_scene* s, pe_ctx* ctx);
+/* Scene::set_uniforms: evaluate and upload every matrix / scalar (float64 -> float32 / int32). */
+PE_API int ph_scene_upload_uniforms(ph_scene* s, pe_ctx* ctx);
+
+/* Orbit camera, float64, column-major out16. */
+PE_API void ph_orbit_camera_matrix(const double look_at[3], double alpha, double beta, double r, double out16[16]);
+PE_API double ph_camera_scale(const double m16[16]);
+
+/* One-call frame: SceneRenderer::new defaults + render_frame.  Uploads scene + renderer uniforms
+ * for the scene's saved camera (or the given orbit angles if use_camera != 0) and renders
+ * width x height at `depth` into host memory: float RGBA (rgba8 == 0) or RGBA8 (rgba8 != 0).
+ * The context must already hold the compiled program (ph_scene_build_program + pe_scene_compile). */
+typedef struct ph_frame_params {
+    int32_t width, height, depth, aa_count, aa_start;
+    int32_t use_camera;      /* 0: scene's saved camera */
+    double look_at[3], alpha, beta, r;
+} ph_frame_params;
+PE_API int ph_render_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, void* out_host, int rgba8);
+/* Same uniform setup, asynchronous render of a row-strip target into device memory. */
+PE_API int ph_render_target(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, const pe_target* target,
+                            void* out_device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PORTAL_B200_HOST_H */

@@ -412,15 +412,20 @@ void pe_oracle_render(const PeOracleFrame* fr, int row0, int row1, float* out, i
     _black_border_disable = fr->black_border_disable; _draw_depth_map = fr->draw_depth_map;
     const int W = fr->width;
     (void)threads;
+    // Work items are 64-pixel runs (not rows) so that a 16-row sample band still feeds every core.
+    const long long total = (long long)(row1 - row0) * (long long)W;
+    const long long CH = 64;
+    const long long chunks = (total + CH - 1) / CH;
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 4)
 #endif
-    for (int y = row0; y < row1; y++) {
-        for (int x = 0; x < W; x++) {
+    for (long long ch = 0; ch < chunks; ch++) {
+        const long long e = (ch + 1) * CH < total ? (ch + 1) * CH : total;
+        for (long long o = ch * CH; o < e; o++) {
+            const int y = row0 + int(o / W), x = int(o % W);
             int b = 0;
             vec4 c = shade_pixel(x, y, &b);
-            size_t o = (size_t(y - row0) * size_t(W) + size_t(x));
             out[4 * o + 0] = float(c.x); out[4 * o + 1] = float(c.y); out[4 * o + 2] = float(c.z); out[4 * o + 3] = float(c.w);
             if (bounces) bounces[o] = b;
         }

@@ -20,6 +20,12 @@ class PeTarget(C.Structure):
                 ("strip_step", C.c_int32), ("n_strips", C.c_int32), ("full_frame_layout", C.c_int32)]
 
 
+class PhFrameParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("depth", C.c_int32), ("aa_count", C.c_int32),
+                ("aa_start", C.c_int32), ("use_camera", C.c_int32), ("look_at", C.c_double * 3), ("alpha", C.c_double),
+                ("beta", C.c_double), ("r", C.c_double)]
+
+
 class PortalB200Error(RuntimeError):
     pass
 
@@ -77,6 +83,25 @@ def lib() -> C.CDLL:
         "pe_average_frames_rgba8": (i32, [vp, C.POINTER(vp), i32, vp, C.c_size_t, vp]),
         "pe_quantize_rgba8": (i32, [vp, vp, vp, C.c_size_t, vp]),
     }
+    f64p = C.POINTER(C.c_double)
+    sig.update({
+        "ph_scene_load_ron": (vp, [cp, C.c_size_t, C.c_char_p, C.c_size_t]),
+        "ph_scene_free": (None, [vp]),
+        "ph_scene_last_error": (cp, [vp]),
+        "ph_scene_set_time": (i32, [vp, C.c_double, C.c_double]),
+        "ph_scene_set_value": (i32, [vp, cp, C.c_double]),
+        "ph_scene_evaluate": (i32, [vp]),
+        "ph_scene_uniform_get": (i32, [vp, i32, C.POINTER(cp), C.POINTER(i32), f64p]),
+        "ph_scene_camera": (i32, [vp, f64p, f64p, f64p, f64p, f64p]),
+        "ph_scene_texture": (i32, [vp, i32, C.POINTER(cp), C.POINTER(cp)]),
+        "ph_scene_count": (i32, [vp, i32]),
+        "ph_scene_build_program": (i32, [vp, vp]),
+        "ph_scene_upload_uniforms": (i32, [vp, vp]),
+        "ph_orbit_camera_matrix": (None, [f64p, C.c_double, C.c_double, C.c_double, f64p]),
+        "ph_camera_scale": (C.c_double, [f64p]),
+        "ph_render_frame": (i32, [vp, vp, C.POINTER(PhFrameParams), vp, i32]),
+        "ph_render_target": (i32, [vp, vp, C.POINTER(PhFrameParams), C.POINTER(PeTarget), vp, vp]),
+    })
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype = res
@@ -88,7 +113,7 @@ def lib() -> C.CDLL:
 def exported_symbols():
     """Names bound above (tests compare them with include/portal_b200.h)."""
     lib()
-    return sorted(n for n in dir(_lib) if n.startswith("pe_"))
+    return sorted(n for n in dir(_lib) if n.startswith(("pe_", "ph_")))
 
 
 def b(s: str) -> bytes:

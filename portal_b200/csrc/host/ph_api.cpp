@@ -1,0 +1,245 @@
+// C API of the host front-end (include/portal_b200_host.h).
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../../include/portal_b200_host.h"
+#include "ph_scene.h"
+
+struct ph_scene {
+    ph::Scene scene;
+    std::vector<ph::TableEntry> table;
+    std::string err;
+};
+
+namespace {
+
+void copy_err(const std::string& m, char* err, size_t n) {
+    if (!err || n == 0) return;
+    std::strncpy(err, m.c_str(), n - 1);
+    err[n - 1] = '\0';
+}
+
+int fail(ph_scene* s, const std::string& m) {
+    if (s) s->err = m;
+    return 1;
+}
+
+// SceneRenderer::set_uniforms (main.rs:1266-1359) for the variants this path implements, with the
+// SceneRenderer::new defaults (main.rs:1021-1047).
+int upload_renderer_uniforms(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p) {
+    double look_at[3] = {s->scene.look_at[0], s->scene.look_at[1], s->scene.look_at[2]};
+    double alpha = s->scene.alpha, beta = s->scene.beta, r = s->scene.r;
+    if (p->use_camera) {
+        for (int k = 0; k < 3; k++) look_at[k] = p->look_at[k];
+        alpha = p->alpha;
+        beta = p->beta;
+        r = p->r;
+    }
+    ph::Mat4 cam = ph::orbit_camera_matrix(look_at, alpha, beta, r);
+    float cam32[16];
+    for (int k = 0; k < 16; k++) cam32[k] = float(cam[k]);
+    int rc = 0;
+    rc |= pe_set_uniform_mat4(ctx, "_camera", cam32);
+    rc |= pe_set_uniform_f32(ctx, "_camera_scale", float(ph::camera_scale(cam)));
+    rc |= pe_set_uniform_f32(ctx, "_view_angle", float(90.0 / 180.0 * M_PI));
+    rc |= pe_set_uniform_f32(ctx, "_offset_after_material", float(s->scene.offset_after_material));
+    rc |= pe_set_uniform_f32(ctx, "_t_start", 10.0f);
+    rc |= pe_set_uniform_f32(ctx, "_t_end", 210.0f);
+    rc |= pe_set_uniform_i32(ctx, "_ray_tracing_depth", p->depth);
+    rc |= pe_set_uniform_i32(ctx, "_aa_count", p->aa_count > 0 ? p->aa_count : 1);
+    rc |= pe_set_uniform_i32(ctx, "_aa_start", p->aa_start);
+    rc |= pe_set_uniform_i32(ctx, "_camera_in_subspace", 0);
+    rc |= pe_set_uniform_i32(ctx, "_darken_by_distance", 1);
+    rc |= pe_set_uniform_i32(ctx, "_angle_color_disable", 0);
+    rc |= pe_set_uniform_i32(ctx, "_grid_disable", 0);
+    rc |= pe_set_uniform_i32(ctx, "_black_border_disable", 0);
+    rc |= pe_set_uniform_i32(ctx, "_draw_depth_map", 0);
+    if (rc) return fail(s, std::string("renderer uniform upload failed: ") + pe_last_error(ctx));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+ph_scene* ph_scene_load_ron(const char* text, size_t len, char* err, size_t err_len) {
+    if (!text) {
+        copy_err("null scene text", err, err_len);
+        return nullptr;
+    }
+    std::string perr;
+    ph::RonPtr root = ph::ron_parse(std::string(text, len), perr);
+    if (!root) {
+        copy_err("RON parse error: " + perr, err, err_len);
+        return nullptr;
+    }
+    auto* s = new ph_scene();
+    if (!s->scene.load(*root)) {
+        copy_err(s->scene.error, err, err_len);
+        delete s;
+        return nullptr;
+    }
+    return s;
+}
+
+void ph_scene_free(ph_scene* s) { delete s; }
+
+const char* ph_scene_last_error(ph_scene* s) { return s ? s->err.c_str() : "null scene"; }
+
+int ph_scene_set_time(ph_scene* s, double time, double total_time) {
+    if (!s) return 1;
+    s->scene.time = time;
+    s->scene.total_time = total_time;
+    return 0;
+}
+
+int ph_scene_set_value(ph_scene* s, const char* name, double value) {
+    if (!s || !name) return 1;
+    auto it = s->scene.uniform_by_name.find(name);
+    if (it == s->scene.uniform_by_name.end()) return fail(s, std::string("no uniform named `") + name + "`");
+    ph::Uniform& u = s->scene.uniforms[it->second];
+    switch (u.kind) {
+        case ph::Uniform::Bool: u.b = value != 0.0; break;
+        case ph::Uniform::Int: u.i = int(value); break;
+        case ph::Uniform::Float: case ph::Uniform::Angle: case ph::Uniform::Progress: u.f = value; break;
+        default: return fail(s, std::string("uniform `") + name + "` is a formula; set its inputs instead");
+    }
+    return 0;
+}
+
+int ph_scene_evaluate(ph_scene* s) {
+    if (!s) return -1;
+    if (!s->scene.uniform_table(s->table)) {
+        s->err = s->scene.error;
+        return -1;
+    }
+    return int(s->table.size());
+}
+
+int ph_scene_uniform_get(ph_scene* s, int k, const char** name, int* type, double values[16]) {
+    if (!s || k < 0 || k >= int(s->table.size())) return 1;
+    const ph::TableEntry& e = s->table[k];
+    if (name) *name = e.name.c_str();
+    if (type) *type = e.type;
+    if (values) {
+        if (e.type == PE_UNIFORM_MAT4) for (int i = 0; i < 16; i++) values[i] = e.m[i];
+        else values[0] = e.type == PE_UNIFORM_FLOAT ? e.f : double(e.i);
+    }
+    return 0;
+}
+
+int ph_scene_camera(ph_scene* s, double look_at[3], double* alpha, double* beta, double* r, double* offset) {
+    if (!s) return 1;
+    if (look_at) for (int k = 0; k < 3; k++) look_at[k] = s->scene.look_at[k];
+    if (alpha) *alpha = s->scene.alpha;
+    if (beta) *beta = s->scene.beta;
+    if (r) *r = s->scene.r;
+    if (offset) *offset = s->scene.offset_after_material;
+    return 0;
+}
+
+int ph_scene_texture(ph_scene* s, int k, const char** name, const char** path) {
+    if (!s || k < 0 || k >= int(s->scene.textures.size())) return 1;
+    if (name) *name = s->scene.textures[k].first.c_str();
+    if (path) *path = s->scene.textures[k].second.c_str();
+    return 0;
+}
+
+int ph_scene_count(ph_scene* s, int what) {
+    if (!s) return -1;
+    switch (what) {
+        case 0: return int(s->scene.objects.size());
+        case 1: return int(s->scene.materials.size());
+        case 2: return int(s->scene.intersection_materials.size());
+        case 3: return int(s->scene.library.size());
+        case 4: return int(s->scene.textures.size());
+    }
+    return -1;
+}
+
+int ph_scene_build_program(ph_scene* s, pe_ctx* ctx) {
+    if (!s || !ctx) return 1;
+    const ph::Scene& sc = s->scene;
+    if (sc.has_skybox) return fail(s, "skybox scenes are not supported yet (SURVEY.md §8 f1)");
+    if (ph_scene_evaluate(s) < 0) return 1;
+    int rc = pe_scene_begin(ctx);
+    for (auto& l : sc.library) rc |= pe_scene_add_library(ctx, l.first.c_str(), l.second.c_str());
+    for (auto& m : sc.materials) {
+        switch (m.type) {
+            case ph::SceneMaterial::Simple:
+                rc |= pe_scene_add_material_simple(ctx, m.name.c_str(), m.color, m.normal_coef, m.grid, m.grid_scale, m.grid_coef, m.grid2, m.grid3);
+                break;
+            case ph::SceneMaterial::Reflect: rc |= pe_scene_add_material_reflect(ctx, m.name.c_str(), m.color); break;
+            case ph::SceneMaterial::Refract: rc |= pe_scene_add_material_refract(ctx, m.name.c_str(), m.color, m.refractive_index); break;
+            case ph::SceneMaterial::Complex: rc |= pe_scene_add_material_complex(ctx, m.name.c_str(), m.code.c_str()); break;
+        }
+    }
+    for (auto& o : sc.objects) {
+        if (o.matrix_a < 0 || (o.portal && o.matrix_b < 0))
+            return fail(s, "object `" + o.name + "` references a missing matrix (the reference's generator returns None)");
+        const std::string a = sc.matrix_uniform_stem(o.matrix_a);
+        const std::string b = o.portal ? sc.matrix_uniform_stem(o.matrix_b) : "";
+        if (o.cls == ph::SceneObject::DebugMatrix) rc |= pe_scene_add_object_debug_matrix(ctx, o.name.c_str(), a.c_str());
+        else if (o.cls == ph::SceneObject::Flat)
+            rc |= pe_scene_add_object_flat(ctx, o.name.c_str(), o.subspace, a.c_str(), o.portal ? b.c_str() : nullptr, o.code.c_str());
+        else
+            rc |= pe_scene_add_object_complex(ctx, o.name.c_str(), o.subspace, a.c_str(), o.portal ? b.c_str() : nullptr, o.code.c_str());
+    }
+    for (auto& im : sc.intersection_materials) rc |= pe_scene_add_intersection_material(ctx, im.first.c_str(), im.second.c_str());
+    for (auto& e : s->table) rc |= pe_scene_declare_uniform(ctx, e.name.c_str(), e.type);
+    for (auto& t : sc.textures) rc |= pe_scene_declare_texture(ctx, t.first.c_str());
+    if (rc) return fail(s, std::string("scene description rejected: ") + pe_last_error(ctx));
+    return 0;
+}
+
+int ph_scene_upload_uniforms(ph_scene* s, pe_ctx* ctx) {
+    if (!s || !ctx) return 1;
+    if (ph_scene_evaluate(s) < 0) return 1;
+    int rc = 0;
+    for (auto& e : s->table) {
+        if (e.type == PE_UNIFORM_MAT4) {
+            float m[16];
+            for (int k = 0; k < 16; k++) m[k] = float(e.m[k]);  // `as_f32()`, scene.rs:587-588
+            rc |= pe_set_uniform_mat4(ctx, e.name.c_str(), m);
+        } else if (e.type == PE_UNIFORM_FLOAT) {
+            rc |= pe_set_uniform_f32(ctx, e.name.c_str(), float(e.f));
+        } else {
+            rc |= pe_set_uniform_i32(ctx, e.name.c_str(), e.i);
+        }
+    }
+    if (rc) return fail(s, std::string("uniform upload failed: ") + pe_last_error(ctx));
+    return 0;
+}
+
+void ph_orbit_camera_matrix(const double look_at[3], double alpha, double beta, double r, double out16[16]) {
+    ph::Mat4 m = ph::orbit_camera_matrix(look_at, alpha, beta, r);
+    for (int k = 0; k < 16; k++) out16[k] = m[k];
+}
+
+double ph_camera_scale(const double m16[16]) {
+    ph::Mat4 m;
+    for (int k = 0; k < 16; k++) m[k] = m16[k];
+    return ph::camera_scale(m);
+}
+
+int ph_render_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, void* out_host, int rgba8) {
+    if (!s || !ctx || !p || !out_host) return 1;
+    if (ph_scene_upload_uniforms(s, ctx)) return 1;
+    if (upload_renderer_uniforms(s, ctx, p)) return 1;
+    pe_target t = {p->width, p->height, p->height, 0, 1, 1, 1};
+    int rc = rgba8 ? pe_render_host_rgba8(ctx, &t, (uint8_t*)out_host) : pe_render_host(ctx, &t, (float*)out_host);
+    if (rc) return fail(s, std::string("render failed: ") + pe_last_error(ctx));
+    return 0;
+}
+
+int ph_render_target(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, const pe_target* target, void* out_device, void* stream) {
+    if (!s || !ctx || !p || !target || !out_device) return 1;
+    if (ph_scene_upload_uniforms(s, ctx)) return 1;
+    if (upload_renderer_uniforms(s, ctx, p)) return 1;
+    if (pe_render(ctx, target, out_device, nullptr, stream)) return fail(s, std::string("render failed: ") + pe_last_error(ctx));
+    return 0;
+}
+
+}  // extern "C"

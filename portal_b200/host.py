@@ -1,0 +1,129 @@
+"""Python handle on the C++ host front-end (include/portal_b200_host.h): scene .ron -> evaluated
+uniform table -> scene program -> frames.  Mirrors the reference's `Scene` + `render_frame` call
+sequence (/root/reference/src/main.rs:2876-2946); all the work happens in libportal_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import PeTarget, PhFrameParams, PortalB200Error, b
+
+
+class HostScene:
+    def __init__(self, ron_text: str):
+        self._lib = capi.lib()
+        raw = ron_text.encode("utf-8")
+        err = C.create_string_buffer(2048)
+        self._s = self._lib.ph_scene_load_ron(raw, len(raw), err, len(err))
+        if not self._s:
+            raise PortalB200Error(err.value.decode(errors="replace"))
+
+    @classmethod
+    def from_file(cls, path: str) -> "HostScene":
+        with open(path, encoding="utf-8") as f:
+            return cls(f.read())
+
+    def close(self):
+        if getattr(self, "_s", None):
+            self._lib.ph_scene_free(self._s)
+            self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PortalB200Error(self._lib.ph_scene_last_error(self._s).decode(errors="replace"))
+
+    def set_time(self, time: float, total_time: float | None = None):
+        self._check(self._lib.ph_scene_set_time(self._s, time, time if total_time is None else total_time))
+
+    def set_value(self, name: str, value: float):
+        self._check(self._lib.ph_scene_set_value(self._s, b(name), float(value)))
+
+    def uniform_table(self) -> dict:
+        """name -> ('mat4', [16 f64]) | ('float', f64) | ('int', int), in upload order."""
+        n = self._lib.ph_scene_evaluate(self._s)
+        if n < 0:
+            raise PortalB200Error(self._lib.ph_scene_last_error(self._s).decode(errors="replace"))
+        out = {}
+        name, typ, vals = C.c_char_p(), C.c_int(), (C.c_double * 16)()
+        for k in range(n):
+            self._check(self._lib.ph_scene_uniform_get(self._s, k, C.byref(name), C.byref(typ), vals))
+            nm = name.value.decode()
+            if typ.value == capi.PE_UNIFORM_MAT4:
+                out[nm] = ("mat4", [vals[i] for i in range(16)])
+            elif typ.value == capi.PE_UNIFORM_FLOAT:
+                out[nm] = ("float", vals[0])
+            else:
+                out[nm] = ("int", int(vals[0]))
+        return out
+
+    def camera(self) -> dict:
+        la, a, be, r, off = (C.c_double * 3)(), C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        self._check(self._lib.ph_scene_camera(self._s, la, C.byref(a), C.byref(be), C.byref(r), C.byref(off)))
+        return {"look_at": list(la), "alpha": a.value, "beta": be.value, "r": r.value, "offset_after_material": off.value}
+
+    def textures(self):
+        out = []
+        name, path = C.c_char_p(), C.c_char_p()
+        k = 0
+        while self._lib.ph_scene_texture(self._s, k, C.byref(name), C.byref(path)) == 0:
+            out.append((name.value.decode(), path.value.decode()))
+            k += 1
+        return out
+
+    def counts(self) -> dict:
+        names = ["objects", "materials", "intersection_materials", "library", "textures"]
+        return {n: self._lib.ph_scene_count(self._s, i) for i, n in enumerate(names)}
+
+
+class HostRenderer:
+    """SceneRenderer::new + render_frame over the C API only (no scene IR involved)."""
+
+    def __init__(self, scene: HostScene, device: int = 0, textures: dict | None = None, persistent: bool = False):
+        self.scene = scene
+        self._lib = capi.lib()
+        self._ctx = self._lib.pe_create(device)
+        if not self._ctx:
+            raise PortalB200Error("pe_create failed: " + self._lib.pe_last_error(None).decode())
+        self._pe(self._lib.pe_set_option(self._ctx, b"persistent", int(persistent)))
+        scene._check(self._lib.ph_scene_build_program(scene._s, self._ctx))
+        scene._check(self._lib.ph_scene_upload_uniforms(scene._s, self._ctx))
+        for name, arr in (textures or {}).items():
+            arr = np.ascontiguousarray(arr, dtype=np.uint8)
+            self._pe(self._lib.pe_set_texture(self._ctx, b(name), arr.ctypes.data, arr.shape[1], arr.shape[0]))
+        self._pe(self._lib.pe_scene_compile(self._ctx))
+
+    def _pe(self, rc):
+        if rc != 0:
+            raise PortalB200Error(self._lib.pe_last_error(self._ctx).decode(errors="replace"))
+
+    def source(self) -> str:
+        return self._lib.pe_scene_source(self._ctx).decode()
+
+    def render_frame(self, width, height, depth, aa_count=1, aa_start=0, camera=None, rgba8=False) -> np.ndarray:
+        p = PhFrameParams(width, height, depth, aa_count, aa_start, 0)
+        if camera is not None:
+            p.use_camera = 1
+            p.look_at = (C.c_double * 3)(*camera["look_at"])
+            p.alpha, p.beta, p.r = camera["alpha"], camera["beta"], camera["r"]
+        out = np.empty((height, width, 4), dtype=np.uint8 if rgba8 else np.float32)
+        self.scene._check(self._lib.ph_render_frame(self.scene._s, self._ctx, C.byref(p), out.ctypes.data, int(rgba8)))
+        return out
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.pe_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

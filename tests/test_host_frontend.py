@@ -1,0 +1,134 @@
+"""The C++ host front-end (RON reader, fasteval-style formulas, glam-style matrix DAG, orbit camera --
+portal_b200/csrc/host, C API include/portal_b200_host.h) against the oracle's independent Python
+restatement (oracle/frontend.py), and -- on the GPU -- the whole path .ron -> pixels."""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import REFERENCE, ROOT, SCENES, load_ir
+from portal_b200 import capi
+from portal_b200.capi import PortalB200Error
+from portal_b200.host import HostRenderer, HostScene
+
+FIXTURE = os.path.join(ROOT, "tests", "fixtures", "two_spheres.ron")
+
+
+def _oracle_ir(path, name, time=0.0):
+    from oracle import frontend
+    return frontend.scene_ir(frontend.load_scene(path), name, time=time)
+
+
+def _assert_same_table(table, ir):
+    assert list(table) == list(ir["uniforms"])           # same names, same upload order
+    for k, (typ, v) in table.items():
+        u = ir["uniforms"][k]
+        assert typ == u["type"], k
+        assert np.array_equal(np.asarray(v, dtype=np.float64), np.asarray(u["value"], dtype=np.float64), equal_nan=True), k
+
+
+def test_fixture_scene_table_matches_oracle_frontend():
+    hs = HostScene.from_file(FIXTURE)
+    ir = _oracle_ir(FIXTURE, "two_spheres")
+    _assert_same_table(hs.uniform_table(), ir)
+    assert hs.camera() == ir["cam"]
+    assert hs.counts() == {"objects": 10, "materials": 7, "intersection_materials": 1, "library": 2, "textures": 0}
+    t = hs.uniform_table()
+    assert t["steps_u"] == ("int", 7) and t["open_u"] == ("int", 1)
+    assert t["lift_u"][1] == 0.5 + 0.25 * 2 + -(math.sin(0.6) * (1 / 4))
+    # If(open) picks portal_a; Inv is the inverse; Teleport = second * first^-1 * what
+    assert t["chosen_mat"] == t["portal_a_mat"] and t["ball_inv_mat"] == t["ball_mat_inv"]
+    assert "portal_a_to_portal_b_mat_teleport" in t and "portal_b_to_portal_a_mat_teleport" in t
+
+
+def test_set_value_and_time_reevaluate():
+    hs = HostScene.from_file(FIXTURE)
+    hs.set_value("open", 0)
+    hs.set_value("p", 0.75)
+    t = hs.uniform_table()
+    assert t["open_u"] == ("int", 0) and t["chosen_mat"] == t["portal_b_mat"]
+    assert t["lift_u"][1] == 0.5 + 0.75 * 2 + -(math.sin(0.6) * (1 / 4))
+    with pytest.raises(PortalB200Error):
+        hs.set_value("lift", 1.0)          # formulas are not settable
+    with pytest.raises(PortalB200Error):
+        hs.set_value("nope", 1.0)
+
+
+def test_bad_scene_files_are_errors():
+    with pytest.raises(PortalB200Error, match="RON parse error"):
+        HostScene("(cam: (")
+    with pytest.raises(PortalB200Error, match="uniforms"):
+        HostScene("(cam: (look_at: (0,0,0), alpha: 0, beta: 1, r: 1, offset_after_material: 0.1))")
+
+
+def test_camera_functions():
+    import ctypes as C
+    lib = capi.lib()
+    ir = load_ir("mobius_monoportal")
+    cam = ir["cam"]
+    out = (C.c_double * 16)()
+    lib.ph_orbit_camera_matrix((C.c_double * 3)(*cam["look_at"]), cam["alpha"], cam["beta"], cam["r"], out)
+    assert list(out) == ir["camera_matrix"]
+    assert lib.ph_camera_scale(out) == ir["camera_scale"]
+
+
+def test_program_from_host_scene_compiles():
+    r = HostRenderer(HostScene.from_file(FIXTURE), device=-1)
+    src = r.source()
+    assert "sphere_hit" in src and "#define steps_u (7)" in src and "float& t" in src
+    assert "intersection material `floating_disk`" in src
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize("scene", SCENES)
+def test_config_scene_tables_match_oracle_and_golden(scene):
+    hs = HostScene.from_file(f"{REFERENCE}/scenes/{scene}.ron")
+    _assert_same_table(hs.uniform_table(), load_ir(scene))          # committed golden (oracle front-end output)
+    if scene in ("triple_portal", "portal_in_portal"):             # use_time scenes: `time` reaches the formulas
+        hs.set_time(0.37)
+        _assert_same_table(hs.uniform_table(), _oracle_ir(f"{REFERENCE}/scenes/{scene}.ron", scene, time=0.37))
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (GPU box)")
+def test_every_reference_scene_loads_and_evaluates():
+    from oracle import frontend
+    n_ok = n_next = 0
+    for path in sorted(glob.glob(f"{REFERENCE}/scenes/*.ron")):
+        name = os.path.basename(path)[:-4]
+        if name == "empty":
+            continue
+        hs = HostScene.from_file(path)
+        try:
+            ir = frontend.scene_ir(frontend.load_scene(path), name)
+        except NotImplementedError:
+            n_next += 1                                            # Sqrt / Lerp matrices: SURVEY §8 f1
+            continue
+        table = hs.uniform_table()
+        common = [k for k in table if k in ir["uniforms"]]
+        assert len(common) >= 0.9 * len(ir["uniforms"]), name
+        for k in common:
+            assert np.array_equal(np.asarray(table[k][1], dtype=np.float64),
+                                  np.asarray(ir["uniforms"][k]["value"], dtype=np.float64), equal_nan=True), (name, k)
+        n_ok += 1
+    assert n_ok >= 60
+
+
+@pytest.mark.gpu
+def test_ron_to_pixels_matches_oracle():
+    from oracle import runner
+    ir = _oracle_ir(FIXTURE, "two_spheres")
+    ref = runner.Oracle(ir, "fast").render(480, 270, 12)
+    for persistent in (False, True):
+        r = HostRenderer(HostScene.from_file(FIXTURE), device=0, persistent=persistent)
+        img = r.render_frame(480, 270, 12)
+        assert np.array_equal(img.view(np.uint32), ref.view(np.uint32))
+        q = r.render_frame(480, 270, 12, rgba8=True)
+        assert np.array_equal(q, np.rint(np.clip(img, 0, 1) * 255).astype(np.uint8))
+    cam = dict(ir["cam"], alpha=ir["cam"]["alpha"] + 1.0)
+    from portal_b200.renderer import camera_scale, orbit_camera_matrix
+    m = orbit_camera_matrix(cam["look_at"], cam["alpha"], cam["beta"], cam["r"])
+    ref2 = runner.Oracle(ir, "fast").render(320, 180, 12, camera=m, camera_scale=camera_scale(m), aa_count=2)
+    img2 = HostRenderer(HostScene.from_file(FIXTURE), device=0).render_frame(320, 180, 12, aa_count=2, camera=cam)
+    assert np.array_equal(img2.view(np.uint32), ref2.view(np.uint32))
