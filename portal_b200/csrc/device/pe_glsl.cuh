@@ -279,6 +279,54 @@ struct cmat4 {
     PE_FI vec4 operator[](int i) const { return vec4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]); }
 };
 
+// A uniform-block matrix whose STRUCTURE is a compile-time constant.  When the uniform table is
+// uploaded the host records, per matrix, which entries are exactly 0.0 and which are exactly 1.0
+// (bit masks Z and O, bit 4*column + row) and selects / JIT-compiles the program variant for that
+// structure (pe_api.cpp, select_variant).  The product then skips the terms a zero contributes and
+// the multiply a one needs: an affine matrix (bottom row 0 0 0 1) costs 12 FFMA per vec4 instead
+// of 16, a pure translation 3.  For finite operands the result is bit-identical to the full FFMA
+// chain (x*1 == x, fma(0, y, acc) == acc up to the sign of a zero result); GLSL does not define
+// Inf/NaN propagation through such terms, and matrices that contain Inf/NaN have no 0/1 entries
+// to skip in the first place.  Same chain order as operator*(cmat4, vec4).
+template <unsigned Z, unsigned O>
+struct smat4 {
+    const cmat4& m;
+    PE_FI operator mat4() const { return mat4(m); }
+    PE_FI vec4 operator[](int i) const { return m[i]; }
+    template <int R>
+    PE_FI float row(const vec4& v) const {
+        float acc = 0.0f;
+        bool have = false;
+        const float comp[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const unsigned bit = 1u << (4 * c + R);
+            if (Z & bit) continue;                       // exact zero: contributes nothing
+            if (O & bit) {                               // exact one: fma(1, v, acc) == acc + v
+                acc = have ? acc + comp[c] : comp[c];
+            } else {
+                acc = have ? ::fmaf(m.e[4 * c + R], comp[c], acc) : m.e[4 * c + R] * comp[c];
+            }
+            have = true;
+        }
+        return acc;
+    }
+};
+template <unsigned Z, unsigned O>
+PE_FI vec4 operator*(const smat4<Z, O>& m, const vec4& v) {
+    return vec4(m.template row<0>(v), m.template row<1>(v), m.template row<2>(v), m.template row<3>(v));
+}
+template <unsigned Z, unsigned O>
+PE_FI mat4 operator*(const smat4<Z, O>& a, const mat4& b) { return mat4(a * b.c[0], a * b.c[1], a * b.c[2], a * b.c[3]); }
+template <unsigned Z, unsigned O>
+PE_FI mat4 operator*(const mat4& a, const smat4<Z, O>& b) { return a * mat4(b); }
+template <unsigned Z, unsigned O>
+PE_FI mat4 operator*(const cmat4& a, const smat4<Z, O>& b) { return mat4(a) * mat4(b); }
+template <unsigned Z, unsigned O>
+PE_FI mat4 operator*(const smat4<Z, O>& a, const cmat4& b) { return a * mat4(b); }
+template <unsigned Z, unsigned O, unsigned Z2, unsigned O2>
+PE_FI mat4 operator*(const smat4<Z, O>& a, const smat4<Z2, O2>& b) { return a * mat4(b); }
+
 PE_FI vec3 operator*(const mat3& m, const vec3& v) {
     return vec3(::fmaf(m.c[2].x, v.z, ::fmaf(m.c[1].x, v.y, m.c[0].x * v.x)),
                 ::fmaf(m.c[2].y, v.z, ::fmaf(m.c[1].y, v.y, m.c[0].y * v.x)),

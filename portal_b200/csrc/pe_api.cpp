@@ -106,7 +106,7 @@ struct pe_ctx {
     std::map<std::string, float> pending_f;
     std::map<std::string, int> pending_i;
 
-    std::map<std::vector<int>, std::unique_ptr<Variant>> variants;  // key: specialised int values
+    std::map<std::vector<int>, std::unique_ptr<Variant>> variants;  // key: specialised ints + matrix structure masks
     Variant* current = nullptr;
     std::map<std::string, Texture> textures;
 
@@ -189,12 +189,32 @@ std::vector<int> current_ints(pe_ctx* c) {
     return v;
 }
 
-std::vector<int> variant_key(pe_ctx* c, const std::vector<int>& ints) {
-    if (!c->opts.specialize_ints) return {};
-    std::vector<int> key = ints;
-    // dynamic renderer ints do not take part in specialisation
-    key[c->layout.int_slot["_ray_tracing_depth"]] = 0;
-    key[c->layout.int_slot["_aa_start"]] = 0;
+// Structure of every scene matrix in the block: which entries are exactly 0 / exactly 1.
+std::vector<std::pair<unsigned, unsigned>> matrix_masks(pe_ctx* c) {
+    std::vector<std::pair<unsigned, unsigned>> out(size_t(c->layout.n_mat));
+    const float* m = reinterpret_cast<const float*>(c->cblock.data() + c->layout.off_mat);
+    for (int k = 0; k < c->layout.n_mat; k++) {
+        unsigned z = 0, o = 0;
+        for (int e = 0; e < 16; e++) {
+            const float v = m[16 * k + e];
+            if (v == 0.0f) z |= 1u << e;
+            else if (v == 1.0f) o |= 1u << e;
+        }
+        out[size_t(k)] = {z, o};
+    }
+    return out;
+}
+
+std::vector<int> variant_key(pe_ctx* c, const std::vector<int>& ints, const std::vector<std::pair<unsigned, unsigned>>& masks) {
+    std::vector<int> key;
+    if (c->opts.specialize_ints) {
+        key = ints;
+        // dynamic renderer ints do not take part in specialisation
+        key[c->layout.int_slot["_ray_tracing_depth"]] = 0;
+        key[c->layout.int_slot["_aa_start"]] = 0;
+    }
+    if (c->opts.specialize_matrices)
+        for (auto& zo : masks) key.push_back(int(zo.first | (zo.second << 16)));
     return key;
 }
 
@@ -259,10 +279,18 @@ bool compile_cubin(pe_ctx* c, const std::string& source, std::vector<char>& cubi
 bool select_variant(pe_ctx* c) {
     ensure_layout(c);
     std::vector<int> ints = current_ints(c);
-    std::vector<int> key = variant_key(c, ints);
+    std::vector<std::pair<unsigned, unsigned>> masks = matrix_masks(c);
+    std::vector<int> key = variant_key(c, ints, masks);
     auto it = c->variants.find(key);
     if (it == c->variants.end()) {
-        GenResult g = generate_program(c->scene, c->layout, c->opts, ints);
+        if (c->variants.size() >= 64) {  // bound the cache: drop everything but the current variant
+            for (auto v = c->variants.begin(); v != c->variants.end();) {
+                if (v->second.get() == c->current) { ++v; continue; }
+                if (v->second->module && c->has_gpu) { cudaDeviceSynchronize(); c->drv->cuModuleUnload(v->second->module); }
+                v = c->variants.erase(v);
+            }
+        }
+        GenResult g = generate_program(c->scene, c->layout, c->opts, ints, masks);
         if (!g.error.empty()) {
             c->err = g.error;
             return false;
@@ -512,6 +540,8 @@ int pe_set_option(pe_ctx* c, const char* key, int value) {
         c->opts.block_threads = value;
     } else if (k == "min_blocks") c->opts.min_blocks = value < 1 ? 1 : value;
     else if (k == "lineinfo") c->lineinfo = value != 0;
+    else if (k == "unroll_loops") c->opts.unroll_loops = value != 0;
+    else if (k == "specialize_matrices") c->opts.specialize_matrices = value != 0;
     else return c->fail("unknown option `" + k + "`");
     // options change the generated program
     if (c->has_gpu) {

@@ -98,7 +98,7 @@ std::string drop_marker_lines(const std::string& code) {
 
 }  // namespace
 
-std::string glsl_to_cuda(const std::string& glsl_in, std::set<std::string>& swizzles) {
+std::string glsl_to_cuda(const std::string& glsl_in, std::set<std::string>& swizzles, bool keep_loops_rolled) {
     const std::string code = drop_marker_lines(glsl_in);
     std::string out;
     out.reserve(code.size() + code.size() / 8);
@@ -167,6 +167,8 @@ std::string glsl_to_cuda(const std::string& glsl_in, std::set<std::string>& swiz
                 continue;
             } else if (cpp_reserved().count(id)) {
                 out += id + "_";
+            } else if (keep_loops_rolled && (id == "for" || id == "while")) {
+                out += "_Pragma(\"unroll 1\") " + id;
             } else {
                 out += id;
                 if (pending_ref) { out += "&"; pending_ref = false; }
@@ -229,13 +231,14 @@ struct Emitter {
     std::ostringstream os;
     std::set<std::string> swz;
     std::string err;
+    bool rolled = false;
 
     void line(const std::string& s) { os << s << "\n"; }
     // A user snippet: `#line` makes NVRTC report "<owner>(local line)" for errors inside it.
     void snippet(const std::string& owner, const std::string& glsl) {
         std::string cu;
         try {
-            cu = glsl_to_cuda(glsl, swz);
+            cu = glsl_to_cuda(glsl, swz, rolled);
         } catch (const std::exception& e) {
             if (err.empty()) err = owner + ": " + e.what();
             return;
@@ -275,9 +278,11 @@ std::string swizzle_macro(const std::set<std::string>& swz, int size) {
 }  // namespace
 
 GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const GenOptions& opts,
-                           const std::vector<int>& int_values) {
+                           const std::vector<int>& int_values,
+                           const std::vector<std::pair<unsigned, unsigned>>& matrix_masks) {
     GenResult R;
     Emitter body;
+    body.rolled = !opts.unroll_loops;
 
     // ---- validate names that become identifiers
     for (const auto& u : scene.uniforms)
@@ -458,7 +463,15 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     hd << "}  // namespace pe\n";
     hd << "extern \"C\" { __constant__ pe::PeConstBlock PE_C; }\n";
     // uniform declarations (scene.rs:661-718) -> names bound to the block / to specialisation constants
-    for (int k = 0; k < L.n_mat; k++) hd << "#define " << L.mats[k] << " (PE_C.m[" << k << "])\n";
+    for (int k = 0; k < L.n_mat; k++) {
+        if (opts.specialize_matrices && size_t(k) < matrix_masks.size() && (matrix_masks[k].first | matrix_masks[k].second)) {
+            char buf[96];
+            std::snprintf(buf, sizeof buf, "(pe::smat4<0x%04xu, 0x%04xu>{PE_C.m[%d]})", matrix_masks[k].first, matrix_masks[k].second, k);
+            hd << "#define " << L.mats[k] << " " << buf << "\n";
+        } else {
+            hd << "#define " << L.mats[k] << " (PE_C.m[" << k << "])\n";
+        }
+    }
     hd << "#define _camera (PE_C.m[" << L.camera_slot << "])\n";
     for (int k = 0; k < L.n_float; k++) hd << "#define " << L.floats[k] << " (PE_C.f[" << k << "])\n";
     for (int k = 0; k < kNumRendererFloats; k++) hd << "#define " << kRendererFloats[k] << " (PE_C.f[" << (L.n_float + k) << "])\n";

@@ -76,6 +76,8 @@ struct GenOptions {
     bool specialize_ints = true;
     int block_threads = 128;
     int min_blocks = 1;
+    bool specialize_matrices = true;  // bake each matrix's exact-0 / exact-1 structure into the program (smat4)
+    bool unroll_loops = true;  // false: `#pragma unroll 1` on every loop of the user snippets (smaller code)
 };
 
 struct GenResult {
@@ -85,13 +87,16 @@ struct GenResult {
 
 // int_values: current value of every slot of i[] (scene ints then renderer ints); used when
 // opts.specialize_ints.
+// matrix_masks: per scene matrix slot (zero mask, one mask), bit 4*column + row; used when
+// opts.specialize_matrices.
 GenResult generate_program(const SceneDesc& scene, const ConstLayout& layout, const GenOptions& opts,
-                           const std::vector<int>& int_values);
+                           const std::vector<int>& int_values,
+                           const std::vector<std::pair<unsigned, unsigned>>& matrix_masks);
 
 // Lexical GLSL -> CUDA rewrite of one snippet (float-literal suffixes, swizzle accessors,
 // parameter qualifiers, !FOR_NUMBER! marker lines -- scene.rs:1066-1107 with the native defaults).
 // Appends the swizzles it met to `swizzles`.  Throws std::runtime_error on untokenisable input.
-std::string glsl_to_cuda(const std::string& glsl, std::set<std::string>& swizzles);
+std::string glsl_to_cuda(const std::string& glsl, std::set<std::string>& swizzles, bool keep_loops_rolled = false);
 
 // Text of the embedded device headers (generated into pe_device_src.inc at build time).
 extern const char* const kSrcGlsl;

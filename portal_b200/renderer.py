@@ -67,7 +67,7 @@ def camera_scale(cam16) -> float:
 
 class SceneRenderer:
     def __init__(self, scene_ir: dict, textures: dict | None = None, device: int = 0, persistent: bool = False,
-                 specialize_ints: bool = True, compile_now: bool = True):
+                 specialize_ints: bool = True, compile_now: bool = True, options: dict | None = None):
         self.ir = scene_ir
         self.device = device
         self._lib = capi.lib()
@@ -94,6 +94,8 @@ class SceneRenderer:
         self.set_cam(cam["look_at"], cam["alpha"], cam["beta"], cam["r"])  # main.rs:1057
         self._check(self._lib.pe_set_option(self._ctx, b"persistent", int(persistent)))
         self._check(self._lib.pe_set_option(self._ctx, b"specialize_ints", int(specialize_ints)))
+        for k, v in (options or {}).items():
+            self._check(self._lib.pe_set_option(self._ctx, b(k), int(v)))
         self._build_scene()
         self.set_scene_uniforms()
         self.set_uniforms()
