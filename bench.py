@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -73,7 +73,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -106,17 +106,20 @@ def cpu_oracle_rate(scene, w, h, depth, budget_s=20.0, threads=0):
     cores = threads or (os.cpu_count() or 1)
     n_bands = 4
     t0 = time.perf_counter()
-    orc.render(w, h, depth, rows=(h // 2, h // 2 + 16), threads=cores)  # calibrate + warm
+    B = min(64, h)
+    orc.render(w, h, depth, rows=(h // 2, min(h, h // 2 + B)), threads=cores)  # warm up the thread pool
+    t0 = time.perf_counter()
+    orc.render(w, h, depth, rows=(h // 2, min(h, h // 2 + B)), threads=cores)  # calibrate
     per_band = max(time.perf_counter() - t0, 1e-4)
-    n_bands = int(max(4, min(h // 16, budget_s / per_band)))
-    starts = [int(i * (h - 16) / max(n_bands - 1, 1)) // 1 for i in range(n_bands)]
+    n_bands = int(max(2, min(h // B, budget_s / per_band)))
+    starts = [int(i * (h - B) / max(n_bands - 1, 1)) for i in range(n_bands)]
     t0 = time.perf_counter()
     px = 0
     for s in starts:
-        orc.render(w, h, depth, rows=(s, s + 16), threads=cores)
-        px += 16 * w
+        orc.render(w, h, depth, rows=(s, s + B), threads=cores)
+        px += B * w
     dt = time.perf_counter() - t0
-    return px / dt / 1e6, cores, f"{n_bands} bands x 16 rows of the {w}x{h} frame ({px} px, {dt:.1f} s)"
+    return px / dt / 1e6, cores, f"{n_bands} bands x {B} rows of the {w}x{h} frame ({px} px, {dt:.1f} s, OpenMP over 64-pixel runs)"
 
 
 def run_reference(args):
@@ -167,26 +170,24 @@ def run_ours(args):
     sptr = stream.cuda_stream
     assert sptr != 0
 
+    from portal_b200.distributed import FrameSharder, STRIP_ROWS as SR
+    mode = args.mode if world > 1 else "gather"
     if world == 1:
         target = r.full_target(w, h)
         outs = [torch.empty((h, w, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
-        gathered = None
+        sharder = None
     else:
-        target = SceneRenderer.strip_target(w, h, STRIP_ROWS, rank, world)
-        spr = max(SceneRenderer.strip_target(w, h, STRIP_ROWS, k, world).n_strips for k in range(world))
-        outs = [torch.zeros((spr, STRIP_ROWS, w, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
-        gathered = torch.empty((world, spr, STRIP_ROWS, w, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
-        frame = torch.empty((h, w, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+        sharder = FrameSharder(r, w, h, rank, world, mode=mode, strip_rows=SR)
+        target = sharder.target
 
     def step(i):
-        out = outs[i & 1]
-        r.draw_texture(target, out.data_ptr(), 0, sptr)
-        if world > 1:
-            dist.gather(out, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
-            if rank == 0:
-                rc = r._lib.pe_deinterleave_strips(r._ctx, gathered.data_ptr(), frame.data_ptr(), w, h, STRIP_ROWS, world,
-                                                   gathered.shape[1], sptr)
-                assert rc == 0
+        if world == 1:
+            r.draw_texture(target, outs[i & 1].data_ptr(), 0, sptr)
+        else:
+            sharder.render(i, sptr)
+            if mode == "p2p":
+                stream.synchronize()          # this rank's pixels are on their way / landed
+                dist.barrier()                # rank 0's frame is complete when everyone is past here
 
     def barrier():
         if world > 1:
@@ -204,22 +205,27 @@ def run_ours(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    t_wall0 = time.perf_counter()
     ev[0].record(stream)
     for i in range(args.steps):
-        kev[i][0].record(stream)
-        r.draw_texture(target, outs[i & 1].data_ptr(), 0, sptr)
-        kev[i][1].record(stream)
-        if world > 1:
-            out = outs[i & 1]
-            dist.gather(out, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
-            if rank == 0:
-                r._lib.pe_deinterleave_strips(r._ctx, gathered.data_ptr(), frame.data_ptr(), w, h, STRIP_ROWS, world,
-                                              gathered.shape[1], sptr)
+        if world == 1:
+            kev[i][0].record(stream)
+            r.draw_texture(target, outs[i & 1].data_ptr(), 0, sptr)
+            kev[i][1].record(stream)
+        else:
+            kev[i][0].record(stream)
+            step(i)
+            kev[i][1].record(stream)
     ev[1].record(stream)
     barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
     launches = r.launch_count() - l0
-    ms = torch.tensor([ev[0].elapsed_time(ev[1])], dtype=torch.float64, device="cuda")
+    dev_ms = ev[0].elapsed_time(ev[1])
+    # p2p mode synchronises on the host every step, so its honest clock is the host's wall clock
+    # between the two device-synchronised barriers; gather mode is timed on the device.
+    step_ms = wall_ms if (world > 1 and mode == "p2p") else dev_ms
+    ms = torch.tensor([step_ms], dtype=torch.float64, device="cuda")
     kms = torch.tensor([sum(a.elapsed_time(b) for a, b in kev) / args.steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -229,25 +235,21 @@ def run_ours(args):
     # ---- e2e: the reference-facing call with HOST buffers (RGBA8 readback = get_texture_data)
     e2e_steps = max(3, min(args.steps, 20))
     host8 = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
+    q8 = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda") if (rank == 0 and world > 1) else None
     cam = r.cam
-    n_px_local = int(C.c_size_t(r._lib.pe_target_pixels(C.byref(target))).value)
+    n_px_local = int(r._lib.pe_target_pixels(C.byref(target))) if world == 1 or mode == "gather" else \
+        sum(1 for y in __import__("portal_b200.distributed", fromlist=["x"]).local_rows(h, rank, world, SR) if y >= 0) * w
 
     def e2e_step(i):
         r.set_cam(cam["look_at"], cam["alpha"], cam["beta"], cam["r"])   # per-frame host work: camera -> _camera
         if world == 1:
             r.render_host_ptr(w, h, host8.data_ptr(), rgba8=True)
         else:
-            out = outs[i & 1]
-            r.draw_texture(target, out.data_ptr(), 0, sptr)
-            dist.gather(out, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+            step(i)
             if rank == 0:
-                r._lib.pe_deinterleave_strips(r._ctx, gathered.data_ptr(), frame.data_ptr(), w, h, STRIP_ROWS, world,
-                                              gathered.shape[1], sptr)
-                q = e2e_step.q8
-                r._lib.pe_quantize_rgba8(r._ctx, frame.data_ptr(), q.data_ptr(), w * h, sptr)
-                host8.copy_(q, non_blocking=True)
+                r._check(r._lib.pe_quantize_rgba8(r._ctx, sharder.frame_ptr, q8.data_ptr(), w * h, sptr))
+                host8.copy_(q8, non_blocking=True)
             torch.cuda.synchronize()
-    e2e_step.q8 = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda") if (rank == 0 and world > 1) else None
     for i in range(2):
         e2e_step(i)
     barrier()
@@ -265,7 +267,7 @@ def run_ours(args):
         value = w * h * args.steps / (total_ms * 1e-3) / 1e6
         # roofline of the dominant kernel (pe_render_kernel): algorithmic bytes = 16 B/pixel written
         #  x pixels one launch shades, / its mean launch duration (CUDA events)
-        alg_bytes = 16.0 * n_px_local if world > 1 else 16.0 * w * h
+        alg_bytes = 16.0 * n_px_local
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -281,7 +283,9 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, saved camera, aa 1 (BASELINE configs[3])",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} GPUs x cyclic {STRIP_ROWS}-row strips + 1 NCCL gather",
+                       "parallelism": "1 GPU" if world == 1 else (
+                           f"{world} GPUs x cyclic {STRIP_ROWS}-row strips + 1 NCCL gather + de-interleave" if mode == "gather" else
+                           f"{world} GPUs x cyclic {STRIP_ROWS}-row strips, kernels store into rank 0's frame over NVLink (CUDA IPC), barrier per frame"),
                        "scheduler": "persistent warps + per-bounce refill" if args.persistent else "one thread per pixel, 8x4 warp tiles",
                        "l2": "each step writes a 132.7 MB frame (> 126 MB L2) into alternating buffers; inputs are a <8 KB constant block"},
             "kernel_ms": round(kernel_ms, 4),
@@ -292,12 +296,15 @@ def run_ours(args):
             "e2e": {"value": round(e2e_rate, 2), "unit": "Mpixels/s", "h2d_bytes_per_step": e2e_h2d_bytes(r),
                     "d2h_bytes_per_step": w * h * 4, "steps": e2e_steps,
                     "call": "pe_render_host_rgba8 (RGBA8 into pinned host memory)" if world == 1 else
-                            "pe_render + NCCL gather + pe_deinterleave_strips + pe_quantize_rgba8 + D2H on rank 0"},
+                            f"pe_render ({mode}) + pe_quantize_rgba8 + D2H on rank 0"},
             "gpu_launches": int(launches),
         }
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
+    if sharder is not None:
+        barrier()
+        sharder.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -313,7 +320,7 @@ def e2e_h2d_bytes(r):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default="portal_in_portal")
@@ -321,6 +328,7 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--persistent", type=int, default=0)
+    ap.add_argument("--mode", default="gather", choices=["gather", "p2p"], help="N > 1: how strips reach rank 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     w, h, d = WORKLOADS[args.scene]

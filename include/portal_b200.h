@@ -139,6 +139,10 @@ PE_API uint64_t pe_launch_count(pe_ctx* ctx);
  * `strips_per_rank` strips) into a row-major frame.  Device pointers; async on `stream`. */
 PE_API int pe_deinterleave_strips(pe_ctx* ctx, const void* gathered_device, void* frame_device, int width, int height,
                            int strip_rows, int n_ranks, int strips_per_rank, void* stream);
+/* Device memory owned by the context (cudaMalloc, so its base address can be exported over IPC). */
+PE_API int pe_device_malloc(pe_ctx* ctx, size_t bytes, void** device_ptr_out);
+PE_API int pe_device_free(pe_ctx* ctx, void* device_ptr);
+PE_API int pe_memcpy_d2h(pe_ctx* ctx, void* host_dst, const void* device_src, size_t bytes, void* stream);
 /* CUDA IPC: let another process's render kernel store its pixels straight into this GPU's
  * frame over NVLink.  handle_out/handle_in are 64-byte cudaIpcMemHandle_t blobs. */
 PE_API int pe_ipc_export(pe_ctx* ctx, void* device_ptr, uint8_t handle_out[64]);

@@ -77,6 +77,9 @@ def lib() -> C.CDLL:
         "pe_sync": (i32, [vp]),
         "pe_launch_count": (C.c_uint64, [vp]),
         "pe_deinterleave_strips": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        "pe_device_malloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),
+        "pe_device_free": (i32, [vp, vp]),
+        "pe_memcpy_d2h": (i32, [vp, vp, vp, C.c_size_t, vp]),
         "pe_ipc_export": (i32, [vp, vp, vp]),
         "pe_ipc_open": (i32, [vp, vp, C.POINTER(vp)]),
         "pe_ipc_close": (i32, [vp, vp]),

@@ -184,12 +184,12 @@ PE_FI void store_pixel(const PeLaunch& L, int px, int lrow, int grow, vec3 sum, 
 
 #if !PE_PERSISTENT
 // ------------------------------------------------------------------------------------------
-// One thread per pixel.  Block = 4 warps = a 16x8 pixel tile (2x2 warp tiles of 8x4).
+// One thread per pixel.  Block = W warps = a 16 x (2W) pixel tile (warp tiles of 8x4, two abreast).
 extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe_render_kernel(const PeLaunch L) {
     using namespace pe;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int lrow = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const int lrow = blockIdx.y * (PE_BLOCK_THREADS / 64 * 4) + (warp >> 1) * 4 + (lane >> 3);
     int grow;
     if (px >= L.width || !local_to_global_row(L, lrow, grow)) return;
 

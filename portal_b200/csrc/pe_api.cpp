@@ -536,7 +536,6 @@ int pe_set_option(pe_ctx* c, const char* key, int value) {
     else if (k == "specialize_ints") c->opts.specialize_ints = value != 0;
     else if (k == "block_threads") {
         if (value < 32 || value > 1024 || value % 32) return c->fail("block_threads must be a multiple of 32 in [32, 1024]");
-        if (!c->opts.persistent && value != 128) { /* the 16x8 tile mapping needs 4 warps */ }
         c->opts.block_threads = value;
     } else if (k == "min_blocks") c->opts.min_blocks = value < 1 ? 1 : value;
     else if (k == "lineinfo") c->lineinfo = value != 0;
@@ -557,7 +556,7 @@ int pe_set_option(pe_ctx* c, const char* key, int value) {
 
 int pe_scene_compile(pe_ctx* c) {
     if (!c) return 1;
-    if (!c->opts.persistent && c->opts.block_threads != 128) return c->fail("block_threads must be 128 unless persistent = 1");
+    if (c->opts.block_threads % 64) return c->fail("block_threads must be a multiple of 64");
     return select_variant(c) ? 0 : 1;
 }
 
@@ -692,8 +691,9 @@ int pe_render(pe_ctx* c, const pe_target* t, void* out_device, void* bounces_dev
         gx = unsigned(c->sm_count * v->blocks_per_sm);
         gy = 1;
     } else {
+        const int rows_per_block = c->opts.block_threads / 64 * 4;
         gx = unsigned((t->width + 15) / 16);
-        gy = unsigned((local_rows + 7) / 8);
+        gy = unsigned((local_rows + rows_per_block - 1) / rows_per_block);
     }
     r = d->cuLaunchKernel(v->kernel, gx, gy, 1, unsigned(c->opts.block_threads), 1, 1, 0, s, args, nullptr);
     if (r != 0) return c->fail("cuLaunchKernel(pe_render_kernel): " + driver_error(d, r));
@@ -756,6 +756,26 @@ int pe_deinterleave_strips(pe_ctx* c, const void* gathered, void* frame, int wid
                                                     c->sm_count, s), "deinterleave")) return 1;
     c->launches++;
     return 0;
+}
+
+int pe_device_malloc(pe_ctx* c, size_t bytes, void** out) {
+    if (!c || !out || bytes == 0) return 1;
+    if (!bind_device(c)) return 1;
+    return cuda_ok(c, cudaMalloc(out, bytes), "cudaMalloc") ? 0 : 1;
+}
+
+int pe_device_free(pe_ctx* c, void* p) {
+    if (!c || !p) return 1;
+    if (!bind_device(c)) return 1;
+    return cuda_ok(c, cudaFree(p), "cudaFree") ? 0 : 1;
+}
+
+int pe_memcpy_d2h(pe_ctx* c, void* dst, const void* src, size_t bytes, void* stream) {
+    if (!c || !dst || !src) return 1;
+    if (!bind_device(c)) return 1;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    if (!cuda_ok(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s), "D2H copy")) return 1;
+    return cuda_ok(c, cudaStreamSynchronize(s), "D2H copy") ? 0 : 1;
 }
 
 int pe_ipc_export(pe_ctx* c, void* p, uint8_t handle_out[64]) {

@@ -75,7 +75,7 @@ struct GenOptions {
     bool persistent = false;
     bool specialize_ints = true;
     int block_threads = 128;
-    int min_blocks = 1;
+    int min_blocks = 5;  // 5 x 128 threads -> <= 96 registers/thread, 20 warps/SM: best of the sweep (profiles/r01b_sweep.txt)
     bool specialize_matrices = true;  // bake each matrix's exact-0 / exact-1 structure into the program (smat4)
     bool unroll_loops = true;  // false: `#pragma unroll 1` on every loop of the user snippets (smaller code)
 };

@@ -1,0 +1,91 @@
+"""N > 1 host logic on CPU: world_size-2/3 gloo processes exchange synthetic strips through the same
+layout + gather code the GPU path uses (portal_b200/distributed.py), and rank 0 checks that the
+assembled frame is in row order.  (Rendering itself exists only on CUDA; on the GPU box
+tests/test_parity_gpu.py::test_row_strips_reassemble_the_frame checks the kernels' side.)"""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from portal_b200 import distributed as D
+
+
+def test_strip_layout_partitions_rows():
+    for h, s, world in [(2160, 16, 8), (4320, 16, 8), (1080, 16, 2), (90, 16, 4), (17, 16, 8), (256, 8, 3)]:
+        seen = []
+        for rank in range(world):
+            rows = D.local_rows(h, rank, world, s)
+            assert len(rows) == D.strips_per_rank(h, world, s) * s
+            seen += [y for y in rows if y >= 0]
+            t = D.make_target(64, h, rank, world, s)
+            assert t.n_strips == len(D.local_strips(h, rank, world, s)) and t.strip_first == rank and t.strip_step == world
+        assert sorted(seen) == list(range(h))
+
+
+def test_deinterleave_index_map():
+    h, w, s, world = 50, 3, 16, 3
+    spr = D.strips_per_rank(h, world, s)
+    g = np.full((world, spr, s, w, 4), -1.0, dtype=np.float32)
+    for rank in range(world):
+        for lr, y in enumerate(D.local_rows(h, rank, world, s)):
+            if y >= 0:
+                g[rank].reshape(-1, w, 4)[lr] = y
+    out = D.deinterleave_numpy(g, h, world, s)
+    assert np.array_equal(out[:, 0, 0], np.arange(h, dtype=np.float32))
+
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, {root!r})
+    from portal_b200 import distributed as D
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo")
+    h, w, s = {h}, {w}, 16
+    spr = D.strips_per_rank(h, world, s)
+    local = torch.full((spr, s, w, 4), -1.0)
+    flat = local.view(-1, w, 4)
+    for lr, y in enumerate(D.local_rows(h, rank, world, s)):
+        if y >= 0:
+            flat[lr] = torch.tensor([float(y), float(rank), 0.0, 1.0])
+    for step in range(3):                         # the bench's per-frame sequence: render -> gather -> assemble
+        gathered = D.gather_to_rank0(local, world, rank)
+        if rank == 0:
+            frame = D.deinterleave_numpy(gathered.numpy(), h, world, s)
+            assert np.array_equal(frame[:, :, 0], np.broadcast_to(np.arange(h, dtype=np.float32)[:, None], (h, w)))
+            owner = (np.arange(h) // s) % world
+            assert np.array_equal(frame[:, 0, 1], owner.astype(np.float32))
+        else:
+            assert gathered is None
+    # max-over-ranks timing reduction used by bench.py
+    t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert t.item() == world
+    dist.barrier()
+    dist.destroy_process_group()
+    print("RANK_OK", rank)
+""")
+
+
+@pytest.mark.parametrize("world,h", [(2, 2160), (3, 100)])
+def test_gloo_gather_of_strips(world, h, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, h=h, w=8))
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for rank, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"RANK_OK {rank}" in o, o[-2000:]
