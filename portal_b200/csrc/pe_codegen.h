@@ -74,8 +74,10 @@ ConstLayout make_layout(const SceneDesc& scene);
 struct GenOptions {
     bool persistent = false;
     bool specialize_ints = true;
-    int block_threads = 128;
-    int min_blocks = 5;  // 5 x 128 threads -> <= 96 registers/thread, 20 warps/SM: best of the sweep (profiles/r01b_sweep.txt)
+    // 4 x 256 threads -> <= 64 registers/thread, 32 warps/SM: best of the sweeps (profiles/r01b_sweep*.txt);
+    // the loop is dependent-issue-latency bound, occupancy buys more than the few spills cost
+    int block_threads = 256;
+    int min_blocks = 4;
     bool specialize_matrices = true;  // bake each matrix's exact-0 / exact-1 structure into the program (smat4)
     bool unroll_loops = true;  // false: `#pragma unroll 1` on every loop of the user snippets (smaller code)
 };
