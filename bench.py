@@ -36,7 +36,11 @@ WORKLOADS = {  # BASELINE.json configs
     "basics": (256, 256, 4),
 }
 STRIP_ROWS = 16
-METRIC = "Mpixels/s @ 3840x2160 depth-40 portal_in_portal"
+METRIC = "Mpixels/s @ 3840x2160 depth-40 portal_in_portal"  # BASELINE.json metric (headline workload)
+
+
+def metric_name(scene, w, h, depth):
+    return f"Mpixels/s @ {w}x{h} depth-{depth} {scene}"
 
 
 def load_ir(scene):
@@ -138,7 +142,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = sum(rates) / len(rates)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "Mpixels/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args.scene, w, h, depth), "value": round(v, 4), "unit": "Mpixels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(w * h / (v * 1e6) * 1e3, 3),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, saved camera, aa 1"},
@@ -281,10 +285,10 @@ def run_ours(args):
             cpu = {"value": round(v, 4), "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample,
                    "single_thread_value": round(v1, 4)}
         line = {
-            "metric": METRIC, "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args.scene, w, h, depth), "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, saved camera, aa 1 (BASELINE configs[3])",
+            "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, saved camera, aa 1" + (" (BASELINE.json headline config)" if (args.scene, w, h, depth) == ("portal_in_portal", 3840, 2160, 40) else ""),
                        "parallelism": "1 GPU" if world == 1 else (
                            f"{world} GPUs x cyclic {STRIP_ROWS}-row strips + 1 NCCL gather + de-interleave" if mode == "gather" else
                            f"{world} GPUs x cyclic {STRIP_ROWS}-row strips, kernels store into rank 0's frame over NVLink (CUDA IPC), barrier per frame"),

@@ -78,6 +78,9 @@ PE_API int pe_scene_add_intersection_material(pe_ctx* ctx, const char* name, con
 PE_API int pe_scene_declare_uniform(pe_ctx* ctx, const char* name, int type);
 /* Texture samplers, name without the `_tex` suffix (src/gui/texture.rs:12-16). */
 PE_API int pe_scene_declare_texture(pe_ctx* ctx, const char* name);
+/* Skybox (src/gui/scene.rs:1052-1063): rays that hit nothing sample this texture by the primary
+ * ray's direction (through `_camera_mul_inv`) instead of the constant grey. */
+PE_API int pe_scene_set_skybox(pe_ctx* ctx, const char* texture_name);
 /* Generate + compile the program for sm_100a.  Integer uniforms are specialisation constants:
  * the program is compiled for their current values and transparently re-specialised (cached)
  * when pe_render* sees different ones.  On failure pe_last_error holds the compiler log with

@@ -62,7 +62,10 @@ def is_swizzle(name: str) -> bool:
     return any(all(c in s for c in name) for s in _SWZ_SETS)
 
 
-def glsl_to_cpp(code: str, float_suffix: str, swizzles: set) -> str:
+_ASSIGN_AHEAD = re.compile(r"\s*(?:=(?!=)|\+=|-=|\*=|/=)")
+
+
+def glsl_to_cpp(code: str, float_suffix: str, swizzles: set, lvalue_swizzles: set | None = None) -> str:
     """Lexical GLSL -> C++ rewrite (see module docstring)."""
     code = filter_marker_lines(code)
     out = []
@@ -92,7 +95,10 @@ def glsl_to_cpp(code: str, float_suffix: str, swizzles: set) -> str:
             else:
                 out.append(body)
         elif kind == "id":
-            if prev_sig == "." and is_swizzle(text):
+            if prev_sig == "." and is_swizzle(text) and _ASSIGN_AHEAD.match(code, pos) and lvalue_swizzles is not None:
+                lvalue_swizzles.add(text)          # `v.xy += ...`: reference bundle instead of a copy
+                out.append(text + "_ref()")
+            elif prev_sig == "." and is_swizzle(text):
                 swizzles.add(text)
                 out.append(text + "()")
             elif prev_sig == ".":
@@ -117,7 +123,7 @@ def glsl_to_cpp(code: str, float_suffix: str, swizzles: set) -> str:
     return "".join(out)
 
 
-def _swizzle_methods(swizzles: set):
+def _swizzle_methods(swizzles: set, lvalue_swizzles: set = frozenset()):
     comp = {}
     for s in _SWZ_SETS:
         for i, c in enumerate(s):
@@ -129,6 +135,16 @@ def _swizzle_methods(swizzles: set):
         ret = f"vec{len(sw)}"
         body = ", ".join(names[i] for i in idx)
         meth = f"{ret} {sw}() const {{ return {ret}({body}); }}"
+        for size in (2, 3, 4):
+            if max(idx) < size:
+                per[size].append(meth)
+    for sw in sorted(lvalue_swizzles):
+        idx = [comp[c] for c in sw]
+        if len(set(idx)) != len(idx):
+            raise ValueError(f"swizzle `{sw}` repeats a component and cannot be assigned to")
+        ret = f"swz{len(sw)}_ref"
+        body = ", ".join(names[i] for i in idx)
+        meth = f"{ret} {sw}_ref() {{ return {ret}{{{body}}}; }}"
         for size in (2, 3, 4):
             if max(idx) < size:
                 per[size].append(meth)
@@ -148,7 +164,7 @@ def _bool(b) -> str:
 
 
 RENDERER_FIELDS = [
-    ("mat4", "_camera"),
+    ("mat4", "_camera"), ("mat4", "_camera_mul_inv"),
     ("real", "_camera_scale"), ("real", "_view_angle"), ("real", "_t_start"), ("real", "_t_end"),
     ("real", "_offset_after_material"), ("real", "_depth_map_min"), ("real", "_depth_map_max"),
     ("real", "_resolution_x"), ("real", "_resolution_y"),
@@ -169,9 +185,10 @@ def uniform_layout(ir: dict):
 def generate_source(ir: dict, real: str = "float") -> str:
     suffix = "f" if real == "float" else ""
     swz: set = set()
+    swz_w: set = set()
 
     def tr(code):
-        return glsl_to_cpp(code, suffix, swz)
+        return glsl_to_cpp(code, suffix, swz, swz_w)
 
     mats, floats, ints = uniform_layout(ir)
     textures = [t["name"] for t in ir["textures"]]
@@ -326,12 +343,14 @@ def generate_source(ir: dict, real: str = "float") -> str:
     if real != "float":
         w("#undef float")
 
-    per = _swizzle_methods(swz)
-    if ir.get("skybox"):
-        raise NotImplementedError("skybox sampling is a SURVEY.md §8(f1) 'next' row")
+    per = _swizzle_methods(swz, swz_w)
     head = []
     h = head.append
     h(f"// GENERATED by oracle/gen_oracle.py for scene `{ir['scene']}` -- ORACLE / TEST INFRASTRUCTURE ONLY.")
+    user_code = "\n".join([l["code"] for l in ir["library"]])
+    for fn in ("transpose", "inverse", "determinant"):
+        if re.search(r"\b(?:mat[234]|float)\s+" + fn + r"\s*\(", user_code):
+            h(f"#define PE_NO_BUILTIN_{fn}  // the scene defines its own {fn}()")
     h(f"#define PE_REAL {real}")
     h("#define PE_L(x) " + ("x##f" if real == "float" else "x"))
     for size in (2, 3, 4):
@@ -355,8 +374,19 @@ def generate_source(ir: dict, real: str = "float") -> str:
     h("}")
     h('#include "portal_library.h"')
     h("namespace pe_oracle {")
-    h("// skybox_processing, scene.rs:1059-1061")
-    h("#define PE_NOT_FOUND_COLOR(r) color(PE_L(0.6), PE_L(0.6), PE_L(0.6))")
+    if ir.get("skybox"):
+        # skybox_processing, scene.rs:1054-1058 (evaluated once, on the primary ray, before the bounce loop)
+        h("#define _skybox_tex (PE_U.tex[%d])" % [t["name"] for t in ir["textures"]].index(ir["skybox"]))
+        h("static inline vec3 pe_skybox_color(const Ray& r) {")
+        h("    vec4 rd2 = _camera_mul_inv * r.d;")
+        h("    real u = atan(rd2.z, rd2.x);")
+        h("    real v = atan(sqrt(rd2.x * rd2.x + rd2.z * rd2.z), rd2.y);")
+        h("    return sqrvec(vec3(texture(_skybox_tex, vec2((u / PI + PE_L(1.)) / PE_L(2.), v / PI))));")
+        h("}")
+        h("#define PE_NOT_FOUND_COLOR(r) pe_skybox_color(r)")
+    else:
+        h("// skybox_processing, scene.rs:1059-1061")
+        h("#define PE_NOT_FOUND_COLOR(r) color(PE_L(0.6), PE_L(0.6), PE_L(0.6))")
     tail = []
     t_ = tail.append
     t_("}  // namespace pe_oracle")
@@ -373,6 +403,7 @@ _ENTRY_POINTS = r"""
 // C entry points; layouts mirrored by oracle/runner.py (ctypes).
 struct PeOracleFrame {
     float camera[16];
+    float camera_mul_inv[16];
     float camera_scale, view_angle, t_start, t_end, offset_after_material, depth_map_min, depth_map_max;
     int ray_tracing_depth, aa_count, aa_start, camera_in_subspace, darken_by_distance, angle_color_disable,
         grid_disable, black_border_disable, draw_depth_map;
@@ -401,6 +432,9 @@ void pe_oracle_render(const PeOracleFrame* fr, int row0, int row1, float* out, i
     for (int c = 0; c < 4; c++)
         _camera.c[c] = vec4(real(fr->camera[4 * c + 0]), real(fr->camera[4 * c + 1]), real(fr->camera[4 * c + 2]),
                                  real(fr->camera[4 * c + 3]));
+    for (int c = 0; c < 4; c++)
+        _camera_mul_inv.c[c] = vec4(real(fr->camera_mul_inv[4 * c + 0]), real(fr->camera_mul_inv[4 * c + 1]),
+                                    real(fr->camera_mul_inv[4 * c + 2]), real(fr->camera_mul_inv[4 * c + 3]));
     _camera_scale = real(fr->camera_scale); _view_angle = real(fr->view_angle);
     _t_start = real(fr->t_start); _t_end = real(fr->t_end);
     _offset_after_material = real(fr->offset_after_material);

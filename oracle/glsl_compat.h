@@ -71,9 +71,47 @@ static inline real smoothstep(real e0, real e1, real x) {
 }
 
 // ------------------------------------------------------------------ vectors
+// Lvalue swizzles (`v.xy += ...`): the rewriter turns a swizzle that is assigned to into an accessor
+// returning one of these reference bundles.
 struct vec2;
 struct vec3;
 struct vec4;
+struct swz2_ref {
+    real &a, &b;
+    inline swz2_ref& operator=(const vec2& v);
+    inline swz2_ref& operator+=(const vec2& v);
+    inline swz2_ref& operator-=(const vec2& v);
+    inline swz2_ref& operator*=(const vec2& v);
+    inline swz2_ref& operator/=(const vec2& v);
+    swz2_ref& operator*=(real s) { a = a * s; b = b * s; return *this; }
+    swz2_ref& operator/=(real s) { a = a / s; b = b / s; return *this; }
+    swz2_ref& operator+=(real s) { a = a + s; b = b + s; return *this; }
+    swz2_ref& operator-=(real s) { a = a - s; b = b - s; return *this; }
+};
+struct swz3_ref {
+    real &a, &b, &c;
+    inline swz3_ref& operator=(const vec3& v);
+    inline swz3_ref& operator+=(const vec3& v);
+    inline swz3_ref& operator-=(const vec3& v);
+    inline swz3_ref& operator*=(const vec3& v);
+    inline swz3_ref& operator/=(const vec3& v);
+    swz3_ref& operator*=(real s) { a = a * s; b = b * s; c = c * s; return *this; }
+    swz3_ref& operator/=(real s) { a = a / s; b = b / s; c = c / s; return *this; }
+    swz3_ref& operator+=(real s) { a = a + s; b = b + s; c = c + s; return *this; }
+    swz3_ref& operator-=(real s) { a = a - s; b = b - s; c = c - s; return *this; }
+};
+struct swz4_ref {
+    real &a, &b, &c, &d;
+    inline swz4_ref& operator=(const vec4& v);
+    inline swz4_ref& operator+=(const vec4& v);
+    inline swz4_ref& operator-=(const vec4& v);
+    inline swz4_ref& operator*=(const vec4& v);
+    inline swz4_ref& operator/=(const vec4& v);
+    swz4_ref& operator*=(real s) { a = a * s; b = b * s; c = c * s; d = d * s; return *this; }
+    swz4_ref& operator/=(real s) { a = a / s; b = b / s; c = c / s; d = d / s; return *this; }
+    swz4_ref& operator+=(real s) { a = a + s; b = b + s; c = c + s; d = d + s; return *this; }
+    swz4_ref& operator-=(real s) { a = a - s; b = b - s; c = c - s; d = d - s; return *this; }
+};
 
 #ifndef PE_SWZ_VEC2
 #define PE_SWZ_VEC2
@@ -130,6 +168,23 @@ struct vec4 {
     PE_SWZ_VEC4
 };
 
+#define PE_SWZ_ASSIGN(R, V, OPEQ, OP, BODY) inline R& R::operator OPEQ(const V& v) { BODY return *this; }
+PE_SWZ_ASSIGN(swz2_ref, vec2, =, =, a = v.x; b = v.y;)
+PE_SWZ_ASSIGN(swz2_ref, vec2, +=, +, a = a + v.x; b = b + v.y;)
+PE_SWZ_ASSIGN(swz2_ref, vec2, -=, -, a = a - v.x; b = b - v.y;)
+PE_SWZ_ASSIGN(swz2_ref, vec2, *=, *, a = a * v.x; b = b * v.y;)
+PE_SWZ_ASSIGN(swz2_ref, vec2, /=, /, a = a / v.x; b = b / v.y;)
+PE_SWZ_ASSIGN(swz3_ref, vec3, =, =, a = v.x; b = v.y; c = v.z;)
+PE_SWZ_ASSIGN(swz3_ref, vec3, +=, +, a = a + v.x; b = b + v.y; c = c + v.z;)
+PE_SWZ_ASSIGN(swz3_ref, vec3, -=, -, a = a - v.x; b = b - v.y; c = c - v.z;)
+PE_SWZ_ASSIGN(swz3_ref, vec3, *=, *, a = a * v.x; b = b * v.y; c = c * v.z;)
+PE_SWZ_ASSIGN(swz3_ref, vec3, /=, /, a = a / v.x; b = b / v.y; c = c / v.z;)
+PE_SWZ_ASSIGN(swz4_ref, vec4, =, =, a = v.x; b = v.y; c = v.z; d = v.w;)
+PE_SWZ_ASSIGN(swz4_ref, vec4, +=, +, a = a + v.x; b = b + v.y; c = c + v.z; d = d + v.w;)
+PE_SWZ_ASSIGN(swz4_ref, vec4, -=, -, a = a - v.x; b = b - v.y; c = c - v.z; d = d - v.w;)
+PE_SWZ_ASSIGN(swz4_ref, vec4, *=, *, a = a * v.x; b = b * v.y; c = c * v.z; d = d * v.w;)
+PE_SWZ_ASSIGN(swz4_ref, vec4, /=, /, a = a / v.x; b = b / v.y; c = c / v.z; d = d / v.w;)
+#undef PE_SWZ_ASSIGN
 inline vec2::vec2(const vec3& v) : x(v.x), y(v.y) {}
 inline vec2::vec2(const vec4& v) : x(v.x), y(v.y) {}
 inline vec3::vec3(const vec4& v) : x(v.x), y(v.y), z(v.z) {}
@@ -295,6 +350,19 @@ struct mat4 {
 };
 inline mat3::mat3(const mat4& m) { c[0] = vec3(m.c[0]); c[1] = vec3(m.c[1]); c[2] = vec3(m.c[2]); }
 
+struct mat2 {
+    vec2 c[2];
+    mat2() { c[0] = vec2(1, 0); c[1] = vec2(0, 1); }
+    explicit mat2(real d) { c[0] = vec2(d, 0); c[1] = vec2(0, d); }
+    mat2(const vec2& a, const vec2& b) { c[0] = a; c[1] = b; }
+    mat2(real a0, real a1, real b0, real b1) { c[0] = vec2(a0, a1); c[1] = vec2(b0, b1); }
+    vec2& operator[](int i) { return c[i]; }
+    const vec2& operator[](int i) const { return c[i]; }
+};
+static inline vec2 operator*(const mat2& m, const vec2& v) {
+    return vec2(pe_fma(m.c[1].x, v.y, m.c[0].x * v.x), pe_fma(m.c[1].y, v.y, m.c[0].y * v.x));
+}
+static inline mat2 operator*(const mat2& a, const mat2& b) { return mat2(a * b.c[0], a * b.c[1]); }
 static inline vec3 operator*(const mat3& m, const vec3& v) {
     return vec3(pe_fma(m.c[2].x, v.z, pe_fma(m.c[1].x, v.y, m.c[0].x * v.x)),
                 pe_fma(m.c[2].y, v.z, pe_fma(m.c[1].y, v.y, m.c[0].y * v.x)),
@@ -308,6 +376,20 @@ static inline vec4 operator*(const mat4& m, const vec4& v) {
 }
 static inline mat4 operator*(const mat4& a, const mat4& b) { return mat4(a * b.c[0], a * b.c[1], a * b.c[2], a * b.c[3]); }
 static inline mat3 operator*(const mat3& a, const mat3& b) { return mat3(a * b.c[0], a * b.c[1], a * b.c[2]); }
+// matrix (op) scalar and matrix +/- matrix, component-wise (GLSL ES 3.00 section 5.9)
+#define PE_MAT_SCALAR_OPS(M, N)                                                                         \
+    static inline M operator*(const M& m, real s) { M o; for (int k = 0; k < N; k++) o.c[k] = m.c[k] * s; return o; }   \
+    static inline M operator*(real s, const M& m) { M o; for (int k = 0; k < N; k++) o.c[k] = s * m.c[k]; return o; }   \
+    static inline M operator/(const M& m, real s) { M o; for (int k = 0; k < N; k++) o.c[k] = m.c[k] / s; return o; }   \
+    static inline M operator+(const M& a, const M& b) { M o; for (int k = 0; k < N; k++) o.c[k] = a.c[k] + b.c[k]; return o; } \
+    static inline M operator-(const M& a, const M& b) { M o; for (int k = 0; k < N; k++) o.c[k] = a.c[k] - b.c[k]; return o; } \
+    static inline M operator-(const M& m) { M o; for (int k = 0; k < N; k++) o.c[k] = -m.c[k]; return o; }
+PE_MAT_SCALAR_OPS(mat2, 2)
+PE_MAT_SCALAR_OPS(mat3, 3)
+PE_MAT_SCALAR_OPS(mat4, 4)
+#undef PE_MAT_SCALAR_OPS
+#ifndef PE_NO_BUILTIN_transpose
+static inline mat2 transpose(const mat2& m) { return mat2(vec2(m.c[0].x, m.c[1].x), vec2(m.c[0].y, m.c[1].y)); }
 static inline mat3 transpose(const mat3& m) {
     return mat3(vec3(m.c[0].x, m.c[1].x, m.c[2].x), vec3(m.c[0].y, m.c[1].y, m.c[2].y), vec3(m.c[0].z, m.c[1].z, m.c[2].z));
 }
@@ -315,6 +397,22 @@ static inline mat4 transpose(const mat4& m) {
     return mat4(vec4(m.c[0].x, m.c[1].x, m.c[2].x, m.c[3].x), vec4(m.c[0].y, m.c[1].y, m.c[2].y, m.c[3].y),
                 vec4(m.c[0].z, m.c[1].z, m.c[2].z, m.c[3].z), vec4(m.c[0].w, m.c[1].w, m.c[2].w, m.c[3].w));
 }
+#endif
+#ifndef PE_NO_BUILTIN_determinant
+static inline real determinant(const mat2& m) { return m.c[0].x * m.c[1].y - m.c[1].x * m.c[0].y; }
+static inline real determinant(const mat3& m) { return dot(m.c[0], cross(m.c[1], m.c[2])); }
+#endif
+#ifndef PE_NO_BUILTIN_inverse
+static inline mat2 inverse(const mat2& m) {
+    real d = m.c[0].x * m.c[1].y - m.c[1].x * m.c[0].y;
+    return mat2(vec2(m.c[1].y, -m.c[0].y) / d, vec2(-m.c[1].x, m.c[0].x) / d);
+}
+static inline mat3 inverse(const mat3& m) {
+    vec3 r0 = cross(m.c[1], m.c[2]), r1 = cross(m.c[2], m.c[0]), r2 = cross(m.c[0], m.c[1]);
+    real d = dot(m.c[0], r0);
+    return mat3(vec3(r0.x, r1.x, r2.x) / d, vec3(r0.y, r1.y, r2.y) / d, vec3(r0.z, r1.z, r2.z) / d);
+}
+#endif
 
 // ----------------------------------------------------------------- textures
 // Pinned sampling rule (macroquad 0.4.14 Texture2D::from_file_with_format defaults,

@@ -19,6 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 class PeOracleFrame(C.Structure):
     _fields_ = [
         ("camera", C.c_float * 16),
+        ("camera_mul_inv", C.c_float * 16),
         ("camera_scale", C.c_float), ("view_angle", C.c_float), ("t_start", C.c_float), ("t_end", C.c_float),
         ("offset_after_material", C.c_float), ("depth_map_min", C.c_float), ("depth_map_max", C.c_float),
         ("ray_tracing_depth", C.c_int), ("aa_count", C.c_int), ("aa_start", C.c_int), ("camera_in_subspace", C.c_int),
@@ -64,6 +65,9 @@ def make_frame(ir: dict, width: int, height: int, depth: int, camera=None, camer
     cam32 = np.asarray(cam, dtype=np.float64).astype(np.float32).reshape(16)
     for k in range(16):
         fr.camera[k] = float(cam32[k])
+    cmi = np.asarray(kw.get("camera_mul_inv", np.eye(4).reshape(16)), dtype=np.float64).astype(np.float32).reshape(16)
+    for k in range(16):
+        fr.camera_mul_inv[k] = float(cmi[k])
     d = ir["renderer"]
     fr.camera_scale = float(np.float32(ir["camera_scale"] if camera_scale is None else camera_scale))
     fr.view_angle = float(np.float32(kw.get("view_angle", d["view_angle"])))

@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
         "pe_scene_add_intersection_material": (i32, [vp, cp, cp]),
         "pe_scene_declare_uniform": (i32, [vp, cp, i32]),
         "pe_scene_declare_texture": (i32, [vp, cp]),
+        "pe_scene_set_skybox": (i32, [vp, cp]),
         "pe_scene_compile": (i32, [vp]),
         "pe_scene_source": (cp, [vp]),
         "pe_scene_cubin": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),

@@ -63,6 +63,45 @@ struct vec2;
 struct vec3;
 struct vec4;
 
+// Lvalue swizzles (`v.xy += ...`): a swizzle that is assigned to is rewritten into an accessor that
+// returns one of these reference bundles (all inlined: the references dissolve into the registers).
+struct swz2_ref {
+    float &a, &b;
+    PE_FI swz2_ref& operator=(const vec2& v);
+    PE_FI swz2_ref& operator+=(const vec2& v);
+    PE_FI swz2_ref& operator-=(const vec2& v);
+    PE_FI swz2_ref& operator*=(const vec2& v);
+    PE_FI swz2_ref& operator/=(const vec2& v);
+    PE_FI swz2_ref& operator*=(float s) { a = a * s; b = b * s; return *this; }
+    PE_FI swz2_ref& operator/=(float s) { a = a / s; b = b / s; return *this; }
+    PE_FI swz2_ref& operator+=(float s) { a = a + s; b = b + s; return *this; }
+    PE_FI swz2_ref& operator-=(float s) { a = a - s; b = b - s; return *this; }
+};
+struct swz3_ref {
+    float &a, &b, &c;
+    PE_FI swz3_ref& operator=(const vec3& v);
+    PE_FI swz3_ref& operator+=(const vec3& v);
+    PE_FI swz3_ref& operator-=(const vec3& v);
+    PE_FI swz3_ref& operator*=(const vec3& v);
+    PE_FI swz3_ref& operator/=(const vec3& v);
+    PE_FI swz3_ref& operator*=(float s) { a = a * s; b = b * s; c = c * s; return *this; }
+    PE_FI swz3_ref& operator/=(float s) { a = a / s; b = b / s; c = c / s; return *this; }
+    PE_FI swz3_ref& operator+=(float s) { a = a + s; b = b + s; c = c + s; return *this; }
+    PE_FI swz3_ref& operator-=(float s) { a = a - s; b = b - s; c = c - s; return *this; }
+};
+struct swz4_ref {
+    float &a, &b, &c, &d;
+    PE_FI swz4_ref& operator=(const vec4& v);
+    PE_FI swz4_ref& operator+=(const vec4& v);
+    PE_FI swz4_ref& operator-=(const vec4& v);
+    PE_FI swz4_ref& operator*=(const vec4& v);
+    PE_FI swz4_ref& operator/=(const vec4& v);
+    PE_FI swz4_ref& operator*=(float s) { a = a * s; b = b * s; c = c * s; d = d * s; return *this; }
+    PE_FI swz4_ref& operator/=(float s) { a = a / s; b = b / s; c = c / s; d = d / s; return *this; }
+    PE_FI swz4_ref& operator+=(float s) { a = a + s; b = b + s; c = c + s; d = d + s; return *this; }
+    PE_FI swz4_ref& operator-=(float s) { a = a - s; b = b - s; c = c - s; d = d - s; return *this; }
+};
+
 #ifndef PE_SWZ_VEC2
 #define PE_SWZ_VEC2
 #endif
@@ -117,6 +156,23 @@ struct vec4 {
     PE_FI float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
     PE_SWZ_VEC4
 };
+#define PE_SWZ_ASSIGN(R, V, OPEQ, BODY) PE_FI R& R::operator OPEQ(const V& v) { BODY return *this; }
+PE_SWZ_ASSIGN(swz2_ref, vec2, =, a = v.x; b = v.y;)
+PE_SWZ_ASSIGN(swz2_ref, vec2, +=, a = a + v.x; b = b + v.y;)
+PE_SWZ_ASSIGN(swz2_ref, vec2, -=, a = a - v.x; b = b - v.y;)
+PE_SWZ_ASSIGN(swz2_ref, vec2, *=, a = a * v.x; b = b * v.y;)
+PE_SWZ_ASSIGN(swz2_ref, vec2, /=, a = a / v.x; b = b / v.y;)
+PE_SWZ_ASSIGN(swz3_ref, vec3, =, a = v.x; b = v.y; c = v.z;)
+PE_SWZ_ASSIGN(swz3_ref, vec3, +=, a = a + v.x; b = b + v.y; c = c + v.z;)
+PE_SWZ_ASSIGN(swz3_ref, vec3, -=, a = a - v.x; b = b - v.y; c = c - v.z;)
+PE_SWZ_ASSIGN(swz3_ref, vec3, *=, a = a * v.x; b = b * v.y; c = c * v.z;)
+PE_SWZ_ASSIGN(swz3_ref, vec3, /=, a = a / v.x; b = b / v.y; c = c / v.z;)
+PE_SWZ_ASSIGN(swz4_ref, vec4, =, a = v.x; b = v.y; c = v.z; d = v.w;)
+PE_SWZ_ASSIGN(swz4_ref, vec4, +=, a = a + v.x; b = b + v.y; c = c + v.z; d = d + v.w;)
+PE_SWZ_ASSIGN(swz4_ref, vec4, -=, a = a - v.x; b = b - v.y; c = c - v.z; d = d - v.w;)
+PE_SWZ_ASSIGN(swz4_ref, vec4, *=, a = a * v.x; b = b * v.y; c = c * v.z; d = d * v.w;)
+PE_SWZ_ASSIGN(swz4_ref, vec4, /=, a = a / v.x; b = b / v.y; c = c / v.z; d = d / v.w;)
+#undef PE_SWZ_ASSIGN
 PE_FI vec2::vec2(const vec3& v) : x(v.x), y(v.y) {}
 PE_FI vec2::vec2(const vec4& v) : x(v.x), y(v.y) {}
 PE_FI vec3::vec3(const vec4& v) : x(v.x), y(v.y), z(v.z) {}
@@ -240,6 +296,19 @@ PE_FI vec4 mix(const vec4& a, const vec4& b, const vec4& t) {
 
 // ----------------------------------------------------------------- matrices (column-major)
 struct mat4;
+struct mat2 {
+    vec2 c[2];
+    PE_FI mat2() { c[0] = vec2(1.0f, 0.0f); c[1] = vec2(0.0f, 1.0f); }
+    PE_FI explicit mat2(float d) { c[0] = vec2(d, 0.0f); c[1] = vec2(0.0f, d); }
+    PE_FI mat2(const vec2& a, const vec2& b) { c[0] = a; c[1] = b; }
+    PE_FI mat2(float a0, float a1, float b0, float b1) { c[0] = vec2(a0, a1); c[1] = vec2(b0, b1); }
+    PE_FI vec2& operator[](int i) { return c[i]; }
+    PE_FI const vec2& operator[](int i) const { return c[i]; }
+};
+PE_FI vec2 operator*(const mat2& m, const vec2& v) {
+    return vec2(::fmaf(m.c[1].x, v.y, m.c[0].x * v.x), ::fmaf(m.c[1].y, v.y, m.c[0].y * v.x));
+}
+PE_FI mat2 operator*(const mat2& a, const mat2& b) { return mat2(a * b.c[0], a * b.c[1]); }
 struct mat3 {
     vec3 c[3];
     PE_FI mat3() { c[0] = vec3(1.0f, 0.0f, 0.0f); c[1] = vec3(0.0f, 1.0f, 0.0f); c[2] = vec3(0.0f, 0.0f, 1.0f); }
@@ -350,6 +419,20 @@ PE_FI mat4 operator*(const cmat4& a, const mat4& b) { return mat4(a) * b; }
 PE_FI mat4 operator*(const mat4& a, const cmat4& b) { return a * mat4(b); }
 PE_FI mat4 operator*(const cmat4& a, const cmat4& b) { return mat4(a) * mat4(b); }
 PE_FI mat3 operator*(const mat3& a, const mat3& b) { return mat3(a * b.c[0], a * b.c[1], a * b.c[2]); }
+// matrix (op) scalar and matrix +/- matrix, component-wise (GLSL ES 3.00 section 5.9)
+#define PE_MAT_SCALAR_OPS(M, N)                                                                         \
+    PE_FI M operator*(const M& m, float s) { M o; for (int k = 0; k < N; k++) o.c[k] = m.c[k] * s; return o; }   \
+    PE_FI M operator*(float s, const M& m) { M o; for (int k = 0; k < N; k++) o.c[k] = s * m.c[k]; return o; }   \
+    PE_FI M operator/(const M& m, float s) { M o; for (int k = 0; k < N; k++) o.c[k] = m.c[k] / s; return o; }   \
+    PE_FI M operator+(const M& a, const M& b) { M o; for (int k = 0; k < N; k++) o.c[k] = a.c[k] + b.c[k]; return o; } \
+    PE_FI M operator-(const M& a, const M& b) { M o; for (int k = 0; k < N; k++) o.c[k] = a.c[k] - b.c[k]; return o; } \
+    PE_FI M operator-(const M& m) { M o; for (int k = 0; k < N; k++) o.c[k] = -m.c[k]; return o; }
+PE_MAT_SCALAR_OPS(mat2, 2)
+PE_MAT_SCALAR_OPS(mat3, 3)
+PE_MAT_SCALAR_OPS(mat4, 4)
+#undef PE_MAT_SCALAR_OPS
+#ifndef PE_NO_BUILTIN_transpose
+PE_FI mat2 transpose(const mat2& m) { return mat2(vec2(m.c[0].x, m.c[1].x), vec2(m.c[0].y, m.c[1].y)); }
 PE_FI mat3 transpose(const mat3& m) {
     return mat3(vec3(m.c[0].x, m.c[1].x, m.c[2].x), vec3(m.c[0].y, m.c[1].y, m.c[2].y), vec3(m.c[0].z, m.c[1].z, m.c[2].z));
 }
@@ -357,6 +440,22 @@ PE_FI mat4 transpose(const mat4& m) {
     return mat4(vec4(m.c[0].x, m.c[1].x, m.c[2].x, m.c[3].x), vec4(m.c[0].y, m.c[1].y, m.c[2].y, m.c[3].y),
                 vec4(m.c[0].z, m.c[1].z, m.c[2].z, m.c[3].z), vec4(m.c[0].w, m.c[1].w, m.c[2].w, m.c[3].w));
 }
+#endif
+#ifndef PE_NO_BUILTIN_determinant
+PE_FI float determinant(const mat2& m) { return m.c[0].x * m.c[1].y - m.c[1].x * m.c[0].y; }
+PE_FI float determinant(const mat3& m) { return dot(m.c[0], cross(m.c[1], m.c[2])); }
+#endif
+#ifndef PE_NO_BUILTIN_inverse
+PE_FI mat2 inverse(const mat2& m) {
+    float d = m.c[0].x * m.c[1].y - m.c[1].x * m.c[0].y;
+    return mat2(vec2(m.c[1].y, -m.c[0].y) / d, vec2(-m.c[1].x, m.c[0].x) / d);
+}
+PE_FI mat3 inverse(const mat3& m) {
+    vec3 r0 = cross(m.c[1], m.c[2]), r1 = cross(m.c[2], m.c[0]), r2 = cross(m.c[0], m.c[1]);
+    float d = dot(m.c[0], r0);
+    return mat3(vec3(r0.x, r1.x, r2.x) / d, vec3(r0.y, r1.y, r2.y) / d, vec3(r0.z, r1.z, r2.z) / d);
+}
+#endif
 
 // ----------------------------------------------------------------- textures
 // RGBA8 texels in global memory, fetched through the read-only path; bilinear weights in fp32

@@ -55,6 +55,9 @@ struct RaySlot {
     vec3 current_color;
     float all_t;
     int bounce;
+#if PE_HAS_SKYBOX
+    vec3 not_found;  // skybox colour of the PRIMARY ray: the reference evaluates it before the loop (scene.rs:1052-1058)
+#endif
 };
 
 // One iteration of the reference's bounce loop body (frag.glsl:113-156).
@@ -100,7 +103,11 @@ PE_FI bool bounce_once(RaySlot& s, float camera_scale, RayTraceResult& res) {
     if (r.in_subspace) {
         res = RayTraceResult{color(0.0f, 0.0f, 0.0f), 0.0f, false};
     } else {
+#if PE_HAS_SKYBOX
+        res = RayTraceResult{s.current_color * s.not_found, 0.0f, false};
+#else
         res = RayTraceResult{s.current_color * PE_NOT_FOUND_COLOR(r), 0.0f, false};
+#endif
     }
     return true;
 }
@@ -130,6 +137,9 @@ PE_FI void primary_ray(int px, int py, int a, RaySlot& s) {
     s.current_color = vec3(1.0f);
     s.all_t = 0.0f;
     s.bounce = 0;
+#if PE_HAS_SKYBOX
+    s.not_found = PE_NOT_FOUND_COLOR(s.r);
+#endif
 }
 
 // get_color2's tail (frag.glsl:456-463)

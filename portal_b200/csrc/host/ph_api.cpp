@@ -162,7 +162,6 @@ int ph_scene_count(ph_scene* s, int what) {
 int ph_scene_build_program(ph_scene* s, pe_ctx* ctx) {
     if (!s || !ctx) return 1;
     const ph::Scene& sc = s->scene;
-    if (sc.has_skybox) return fail(s, "skybox scenes are not supported yet (SURVEY.md §8 f1)");
     if (ph_scene_evaluate(s) < 0) return 1;
     int rc = pe_scene_begin(ctx);
     for (auto& l : sc.library) rc |= pe_scene_add_library(ctx, l.first.c_str(), l.second.c_str());
@@ -190,6 +189,7 @@ int ph_scene_build_program(ph_scene* s, pe_ctx* ctx) {
     for (auto& im : sc.intersection_materials) rc |= pe_scene_add_intersection_material(ctx, im.first.c_str(), im.second.c_str());
     for (auto& e : s->table) rc |= pe_scene_declare_uniform(ctx, e.name.c_str(), e.type);
     for (auto& t : sc.textures) rc |= pe_scene_declare_texture(ctx, t.first.c_str());
+    if (!sc.skybox.empty()) rc |= pe_scene_set_skybox(ctx, sc.skybox.c_str());
     if (rc) return fail(s, std::string("scene description rejected: ") + pe_last_error(ctx));
     return 0;
 }

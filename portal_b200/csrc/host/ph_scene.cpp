@@ -282,7 +282,7 @@ struct Loader {
             if (cam->get("offset_after_material")) sc.offset_after_material = cam->get("offset_after_material")->num();
         }
         if (const RonValue* t = root.get("use_time")) sc.use_time = t->b;
-        if (const RonValue* s = root.get("skybox")) sc.has_skybox = s->kind != RonValue::Null;
+        if (const RonValue* s = root.get("skybox")) sc.skybox = s->kind == RonValue::String ? s->s : "";
 
         // uniforms (scene_serialized.rs:1114-1117)
         if (const RonValue* us = storage(root, "uniforms", true))

@@ -95,7 +95,7 @@ struct Scene {
     std::vector<SceneObject> objects;
     std::vector<SceneMaterial> materials;
     std::vector<std::pair<std::string, std::string>> intersection_materials, library, textures;  // (name, code|path)
-    bool has_skybox = false;
+    std::string skybox;  // texture name, empty = none
     std::string error;
 
     // deserialize_scene_new_format

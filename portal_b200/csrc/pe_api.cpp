@@ -141,9 +141,9 @@ void ensure_layout(pe_ctx* c) {
     c->cblock.assign(c->layout.size, 0);
     c->layout_valid = true;
     set_renderer_defaults(c);
-    // identity camera
+    // identity camera and identity `_camera_mul_inv` (teleport_matrix.inverse(), main.rs:1286-1289)
     float* cam = reinterpret_cast<float*>(c->cblock.data() + c->layout.off_mat) + 16 * c->layout.camera_slot;
-    for (int k = 0; k < 16; k++) cam[k] = (k % 5 == 0) ? 1.0f : 0.0f;
+    for (int k = 0; k < 32; k++) cam[k] = ((k % 16) % 5 == 0) ? 1.0f : 0.0f;
     // values set before the layout existed
     for (auto& kv : c->pending_mat) pe_set_uniform_mat4(c, kv.first.c_str(), kv.second.data());
     for (auto& kv : c->pending_f) pe_set_uniform_f32(c, kv.first.c_str(), kv.second);
@@ -526,6 +526,12 @@ int pe_scene_declare_uniform(pe_ctx* c, const char* name, int type) {
 int pe_scene_declare_texture(pe_ctx* c, const char* name) {
     PE_NEED(c, name);
     c->scene.textures.push_back(name);
+    return 0;
+}
+
+int pe_scene_set_skybox(pe_ctx* c, const char* texture_name) {
+    PE_NEED(c, texture_name);
+    c->scene.skybox = texture_name;
     return 0;
 }
 

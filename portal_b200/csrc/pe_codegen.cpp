@@ -1,6 +1,7 @@
 // sm_100a program generator -- see pe_codegen.h.
 #include "pe_codegen.h"
 
+#include <algorithm>
 #include <cctype>
 #include <cmath>
 #include <cstdio>
@@ -40,11 +41,12 @@ ConstLayout make_layout(const SceneDesc& scene) {
     L.n_tex = int(scene.textures.size());
     L.camera_slot = L.n_mat;
     L.mat_slot["_camera"] = L.camera_slot;
+    L.mat_slot["_camera_mul_inv"] = L.camera_slot + 1;
     for (int k = 0; k < kNumRendererFloats; k++) L.float_slot[kRendererFloats[k]] = L.n_float + k;
     for (int k = 0; k < kNumRendererInts; k++) L.int_slot[kRendererInts[k]] = L.n_int + k;
     for (int k = 0; k < L.n_tex; k++) L.tex_slot[scene.textures[k]] = k;
     L.off_mat = 0;
-    L.off_float = size_t(L.n_mat + 1) * 64;
+    L.off_float = size_t(L.n_mat + 2) * 64;
     L.off_int = L.off_float + size_t(L.n_float + kNumRendererFloats) * 4;
     size_t end_int = L.off_int + size_t(L.n_int + kNumRendererInts) * 4;
     L.off_tex = (end_int + 7) & ~size_t(7);
@@ -98,7 +100,8 @@ std::string drop_marker_lines(const std::string& code) {
 
 }  // namespace
 
-std::string glsl_to_cuda(const std::string& glsl_in, std::set<std::string>& swizzles, bool keep_loops_rolled) {
+std::string glsl_to_cuda(const std::string& glsl_in, std::set<std::string>& swizzles, bool keep_loops_rolled,
+                         std::set<std::string>* lvalue_swizzles) {
     const std::string code = drop_marker_lines(glsl_in);
     std::string out;
     out.reserve(code.size() + code.size() / 8);
@@ -156,7 +159,18 @@ std::string glsl_to_cuda(const std::string& glsl_in, std::set<std::string>& swiz
             std::string id = code.substr(i, j - i);
             i = j;
             if (prev == ".") {
-                if (is_swizzle(id)) { swizzles.insert(id); out += id + "()"; }
+                if (is_swizzle(id)) {
+                    // `v.xy += ...`: a swizzle that is assigned to becomes a reference bundle
+                    size_t k = i;
+                    while (k < n && (code[k] == ' ' || code[k] == '\t' || code[k] == '\r' || code[k] == '\n')) k++;
+                    bool assigned = false;
+                    if (k < n) {
+                        if (code[k] == '=' && !(k + 1 < n && code[k + 1] == '=')) assigned = true;
+                        else if (k + 1 < n && code[k + 1] == '=' && std::strchr("+-*/", code[k])) assigned = true;
+                    }
+                    if (assigned && lvalue_swizzles) { lvalue_swizzles->insert(id); out += id + "_ref()"; }
+                    else { swizzles.insert(id); out += id + "()"; }
+                }
                 else out += id;
             } else if (id == "out" || id == "inout") {
                 pending_ref = true;
@@ -229,7 +243,7 @@ bool valid_ident(const std::string& s) {
 
 struct Emitter {
     std::ostringstream os;
-    std::set<std::string> swz;
+    std::set<std::string> swz, swz_w;
     std::string err;
     bool rolled = false;
 
@@ -238,7 +252,7 @@ struct Emitter {
     void snippet(const std::string& owner, const std::string& glsl) {
         std::string cu;
         try {
-            cu = glsl_to_cuda(glsl, swz, rolled);
+            cu = glsl_to_cuda(glsl, swz, rolled, &swz_w);
         } catch (const std::exception& e) {
             if (err.empty()) err = owner + ": " + e.what();
             return;
@@ -247,6 +261,38 @@ struct Emitter {
         os << "#line 1 \"<generated>\"\n";
     }
 };
+
+int swz_index(char c) {
+    const char* sets[] = {"xyzw", "rgba", "stpq"};
+    for (const char* set : sets) {
+        const char* p = std::strchr(set, c);
+        if (p) return int(p - set);
+    }
+    return 0;
+}
+
+std::string lvalue_swizzle_macro(const std::set<std::string>& swz, int size, std::string& err) {
+    std::string out;
+    for (const std::string& s : swz) {
+        int mx = 0;
+        bool dup = false;
+        for (size_t k = 0; k < s.size(); k++) {
+            mx = std::max(mx, swz_index(s[k]));
+            for (size_t j = 0; j < k; j++)
+                if (swz_index(s[j]) == swz_index(s[k])) dup = true;
+        }
+        if (dup) { err = "swizzle `" + s + "` repeats a component and cannot be assigned to"; continue; }
+        if (mx >= size) continue;
+        std::string ret = "swz" + std::to_string(s.size()) + "_ref";
+        out += " PE_FI " + ret + " " + s + "_ref() { return " + ret + "{";
+        for (size_t k = 0; k < s.size(); k++) {
+            if (k) out += ", ";
+            out += "xyzw"[swz_index(s[k])];
+        }
+        out += "}; }";
+    }
+    return out;
+}
 
 std::string swizzle_macro(const std::set<std::string>& swz, int size) {
     std::string out;
@@ -447,14 +493,40 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     hd << "#define PE_PERSISTENT " << (opts.persistent ? 1 : 0) << "\n";
     hd << "#define PE_BLOCK_THREADS " << opts.block_threads << "\n";
     hd << "#define PE_MIN_BLOCKS " << opts.min_blocks << "\n";
-    hd << "#define PE_SWZ_VEC2" << swizzle_macro(body.swz, 2) << "\n";
-    hd << "#define PE_SWZ_VEC3" << swizzle_macro(body.swz, 3) << "\n";
-    hd << "#define PE_SWZ_VEC4" << swizzle_macro(body.swz, 4) << "\n";
+    std::string swz_err;
+    hd << "#define PE_SWZ_VEC2" << swizzle_macro(body.swz, 2) << lvalue_swizzle_macro(body.swz_w, 2, swz_err) << "\n";
+    hd << "#define PE_SWZ_VEC3" << swizzle_macro(body.swz, 3) << lvalue_swizzle_macro(body.swz_w, 3, swz_err) << "\n";
+    hd << "#define PE_SWZ_VEC4" << swizzle_macro(body.swz, 4) << lvalue_swizzle_macro(body.swz_w, 4, swz_err) << "\n";
+    if (!swz_err.empty()) { R.error = swz_err; return R; }
+    hd << "#define PE_HAS_SKYBOX " << (scene.skybox.empty() ? 0 : 1) << "\n";
+    {   // a scene may define its own transpose / inverse / determinant (GLSL ES 1.00 has none built in)
+        std::string user;
+        for (const auto& lib : scene.library) user += lib.code + "\n";
+        for (const char* fn : {"transpose", "inverse", "determinant"}) {
+            bool defined = false;
+            for (const char* ty : {"mat2", "mat3", "mat4", "float"}) {
+                size_t pos = 0;
+                const std::string needle = std::string(ty);
+                while ((pos = user.find(needle, pos)) != std::string::npos) {
+                    size_t k = pos + needle.size();
+                    size_t k0 = k;
+                    while (k < user.size() && std::isspace((unsigned char)user[k])) k++;
+                    if (k > k0 && user.compare(k, std::strlen(fn), fn) == 0) {
+                        size_t e = k + std::strlen(fn);
+                        while (e < user.size() && std::isspace((unsigned char)user[e])) e++;
+                        if (e < user.size() && user[e] == '(' && (pos == 0 || !is_ident_char(user[pos - 1]))) defined = true;
+                    }
+                    pos = k0;
+                }
+            }
+            if (defined) hd << "#define PE_NO_BUILTIN_" << fn << "\n";
+        }
+    }
     hd << kSrcGlsl << "\n";
     hd << "namespace pe {\n";
     hd << "// Constant uniform block: scene matrices + camera, floats, ints, texture descriptors.\n";
     hd << "struct PeConstBlock {\n";
-    hd << "    cmat4 m[" << (L.n_mat + 1) << "];\n";
+    hd << "    cmat4 m[" << (L.n_mat + 2) << "];\n";
     hd << "    float f[" << (L.n_float + kNumRendererFloats) << "];\n";
     hd << "    int i[" << (L.n_int + kNumRendererInts) << "];\n";
     hd << "    sampler2D tex[" << (L.n_tex > 0 ? L.n_tex : 1) << "];\n";
@@ -473,6 +545,7 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
         }
     }
     hd << "#define _camera (PE_C.m[" << L.camera_slot << "])\n";
+    hd << "#define _camera_mul_inv (PE_C.m[" << (L.camera_slot + 1) << "])\n";
     for (int k = 0; k < L.n_float; k++) hd << "#define " << L.floats[k] << " (PE_C.f[" << k << "])\n";
     for (int k = 0; k < kNumRendererFloats; k++) hd << "#define " << kRendererFloats[k] << " (PE_C.f[" << (L.n_float + k) << "])\n";
     for (int k = 0; k < L.n_int; k++) {
@@ -499,9 +572,23 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
         hd << "#define teleport_" << pos << "_2_M (USER_MATERIAL_OFFSET + " << counter++ << ")\n";
     }
     // skybox_processing (scene.rs:1052-1063): no skybox -> constant colour
-    hd << "#define PE_NOT_FOUND_COLOR(r) color(0.6f, 0.6f, 0.6f)\n";
+    if (!scene.skybox.empty() && !L.tex_slot.count(scene.skybox)) {
+        R.error = "skybox texture `" + scene.skybox + "` was not declared (pe_scene_declare_texture)";
+        return R;
+    }
+    if (scene.skybox.empty()) hd << "#define PE_NOT_FOUND_COLOR(r) color(0.6f, 0.6f, 0.6f)\n";
+    else hd << "#define PE_NOT_FOUND_COLOR(r) pe_skybox_color(r)\n";
     hd << kSrcLibrary << "\n";
     hd << "namespace pe {\n";
+    if (!scene.skybox.empty()) {
+        // skybox_processing, scene.rs:1054-1058
+        hd << "PE_FI vec3 pe_skybox_color(const Ray& r) {\n"
+           << "    vec4 rd2 = _camera_mul_inv * r.d;\n"
+           << "    float u = atan(rd2.z, rd2.x);\n"
+           << "    float v = atan(sqrt(rd2.x * rd2.x + rd2.z * rd2.z), rd2.y);\n"
+           << "    return sqrvec(vec3(texture(" << scene.skybox << "_tex, vec2((u / PI + 1.0f) / 2.0f, v / PI))));\n"
+           << "}\n";
+    }
     hd << "#line 1 \"<generated>\"\n";
 
     R.source = hd.str() + body.os.str() + "}  // namespace pe\n" + kSrcKernel + "\n";

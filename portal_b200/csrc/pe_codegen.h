@@ -52,6 +52,7 @@ struct SceneDesc {
     std::vector<NamedCode> intersection_materials;
     std::vector<UniformDecl> uniforms;
     std::vector<std::string> textures;
+    std::string skybox;  // texture name or empty (scene.rs:1052-1063)
 };
 
 // Renderer ("_"-prefixed) uniforms, /root/reference/src/gui/scene.rs:497-535 -- the subset the
@@ -67,7 +68,7 @@ struct ConstLayout {
     std::vector<std::string> mats, floats, ints;       // declaration order
     std::map<std::string, int> mat_slot, float_slot, int_slot, tex_slot;  // names incl. renderer ones
     size_t off_mat = 0, off_float = 0, off_int = 0, off_tex = 0, size = 0;
-    int camera_slot = 0;  // m[n_mat]
+    int camera_slot = 0;  // m[n_mat]; m[n_mat + 1] = _camera_mul_inv
 };
 ConstLayout make_layout(const SceneDesc& scene);
 
@@ -98,7 +99,8 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& layout, co
 // Lexical GLSL -> CUDA rewrite of one snippet (float-literal suffixes, swizzle accessors,
 // parameter qualifiers, !FOR_NUMBER! marker lines -- scene.rs:1066-1107 with the native defaults).
 // Appends the swizzles it met to `swizzles`.  Throws std::runtime_error on untokenisable input.
-std::string glsl_to_cuda(const std::string& glsl, std::set<std::string>& swizzles, bool keep_loops_rolled = false);
+std::string glsl_to_cuda(const std::string& glsl, std::set<std::string>& swizzles, bool keep_loops_rolled = false,
+                         std::set<std::string>* lvalue_swizzles = nullptr);
 
 // Text of the embedded device headers (generated into pe_device_src.inc at build time).
 extern const char* const kSrcGlsl;

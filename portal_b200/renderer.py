@@ -155,6 +155,8 @@ class SceneRenderer:
             self._check(L.pe_scene_declare_uniform(ctx, b(name), kinds[u["type"]]))
         for t in ir["textures"]:
             self._check(L.pe_scene_declare_texture(ctx, b(t["name"])))
+        if ir.get("skybox"):
+            self._check(L.pe_scene_set_skybox(ctx, b(ir["skybox"])))
 
     def compile(self):
         self._check(self._lib.pe_scene_compile(self._ctx))
