@@ -164,7 +164,10 @@ def _bool(b) -> str:
 
 
 RENDERER_FIELDS = [
-    ("mat4", "_camera"), ("mat4", "_camera_mul_inv"),
+    ("mat4", "_camera"), ("mat4", "_camera_mul_inv"), ("mat4", "_camera_left_eye"), ("mat4", "_camera_right_eye"),
+    ("real", "_left_eye_scale"), ("real", "_right_eye_scale"), ("real", "_panini_param"),
+    ("int", "_left_eye_in_subspace"), ("int", "_right_eye_in_subspace"), ("int", "_use_panini_projection"),
+    ("int", "_use_360_camera"), ("int", "_use_180_camera"), ("int", "_draw_side_by_side"),
     ("real", "_camera_scale"), ("real", "_view_angle"), ("real", "_t_start"), ("real", "_t_end"),
     ("real", "_offset_after_material"), ("real", "_depth_map_min"), ("real", "_depth_map_max"),
     ("real", "_resolution_x"), ("real", "_resolution_y"),
@@ -404,6 +407,9 @@ _ENTRY_POINTS = r"""
 struct PeOracleFrame {
     float camera[16];
     float camera_mul_inv[16];
+    float camera_left_eye[16], camera_right_eye[16];
+    float left_eye_scale, right_eye_scale, panini_param;
+    int left_eye_in_subspace, right_eye_in_subspace, use_panini_projection, use_360_camera, use_180_camera, draw_side_by_side;
     float camera_scale, view_angle, t_start, t_end, offset_after_material, depth_map_min, depth_map_max;
     int ray_tracing_depth, aa_count, aa_start, camera_in_subspace, darken_by_distance, angle_color_disable,
         grid_disable, black_border_disable, draw_depth_map;
@@ -435,6 +441,17 @@ void pe_oracle_render(const PeOracleFrame* fr, int row0, int row1, float* out, i
     for (int c = 0; c < 4; c++)
         _camera_mul_inv.c[c] = vec4(real(fr->camera_mul_inv[4 * c + 0]), real(fr->camera_mul_inv[4 * c + 1]),
                                     real(fr->camera_mul_inv[4 * c + 2]), real(fr->camera_mul_inv[4 * c + 3]));
+    for (int c = 0; c < 4; c++) {
+        _camera_left_eye.c[c] = vec4(real(fr->camera_left_eye[4 * c + 0]), real(fr->camera_left_eye[4 * c + 1]),
+                                     real(fr->camera_left_eye[4 * c + 2]), real(fr->camera_left_eye[4 * c + 3]));
+        _camera_right_eye.c[c] = vec4(real(fr->camera_right_eye[4 * c + 0]), real(fr->camera_right_eye[4 * c + 1]),
+                                      real(fr->camera_right_eye[4 * c + 2]), real(fr->camera_right_eye[4 * c + 3]));
+    }
+    _left_eye_scale = real(fr->left_eye_scale); _right_eye_scale = real(fr->right_eye_scale);
+    _panini_param = real(fr->panini_param);
+    _left_eye_in_subspace = fr->left_eye_in_subspace; _right_eye_in_subspace = fr->right_eye_in_subspace;
+    _use_panini_projection = fr->use_panini_projection; _use_360_camera = fr->use_360_camera;
+    _use_180_camera = fr->use_180_camera; _draw_side_by_side = fr->draw_side_by_side;
     _camera_scale = real(fr->camera_scale); _view_angle = real(fr->view_angle);
     _t_start = real(fr->t_start); _t_end = real(fr->t_end);
     _offset_after_material = real(fr->offset_after_material);

@@ -6,9 +6,10 @@
 // and scene_intersect_material_process() have been emitted (frag.glsl:19-59 with the
 // generator's sections, /root/reference/src/gui/scene.rs:885-1035, filled in).
 //
-// Variants restated: mono camera, perspective projection, AA loop, darken-by-distance,
-// depth map colouring.  Panini / 360 / 180 / anaglyph / side-by-side and the external-ray
-// probe are SURVEY.md §8(f) "next" rows and are not restated here.
+// Variants restated: mono camera and side-by-side stereo; perspective, panini, 360 and VR180
+// projections; AA loop; darken-by-distance; depth-map colouring.  Anaglyph is compiled out of the
+// reference's native build (disable_anaglyph = true, main.rs:938) and the external-ray probe is a
+// SURVEY.md §8(f3) "next" row; neither is restated here.
 #pragma once
 
 namespace pe_oracle {
@@ -103,12 +104,77 @@ static inline RayTraceResult ray_tracing(Ray r, real camera_scale, int* bounces_
     return RayTraceResult{color(real(0), real(0), real(0)), PE_L(0.0), false};
 }
 
-// frag.glsl:408-464, perspective branch :449-455
+// frag.glsl:297-301
+static inline real Pow2(real x) { return x * x; }
+
+// frag.glsl:305-342
+static inline vec3 PaniniProjection(vec2 tc, real fov, real d) {
+    const real Pi = PE_L(3.14159265359);
+    const real Pi05 = Pi * PE_L(0.5);
+    real d2 = d * d;
+    {
+        real fo = Pi05 - fov * PE_L(0.5);
+        real f = cos(fo) / sin(fo);
+        real f2 = f * f;
+        real b = (sqrt(max(PE_L(0.0), Pow2(d + d2) * (f2 + f2 * f2))) - (d * f + f)) / (d2 + d2 * f2 - PE_L(1.0));
+        tc *= b;
+    }
+    real h = tc.x;
+    real v = tc.y;
+    real h2 = h * h;
+    real k = h2 / Pow2(d + PE_L(1.0));
+    real k2 = k * k;
+    real discr = max(PE_L(0.0), k2 * d2 - (k + PE_L(1.0)) * (k * d2 - PE_L(1.0)));
+    real cosPhi = (-k * d + sqrt(discr)) / (k + PE_L(1.0));
+    real S = (d + PE_L(1.0)) / (d + cosPhi);
+    real tanTheta = v / S;
+    real sinPhi = sqrt(max(PE_L(0.0), PE_L(1.0) - Pow2(cosPhi)));
+    if (tc.x < PE_L(0.0)) sinPhi *= PE_L(-1.0);
+    real s = inversesqrt(PE_L(1.0) + Pow2(tanTheta));
+    return vec3(sinPhi, tanTheta, cosPhi) * s;
+}
+
+// frag.glsl:408-464: panini :411-412, 360 :413-437, VR180 :438-448, perspective :449-452
 static inline vec3 get_color2(vec2 image_position, const mat4& camera_matrix, bool in_subspace, real camera_scale,
-                              int* bounces_out) {
+                              vec2 resolution, int* bounces_out) {
+    const real Pi = PE_L(3.14159265359);
+    const real Pi05 = Pi * PE_L(0.5);
     vec4 o = camera_matrix * vec4(real(0), real(0), real(0), real(1));
-    real h = tan(_view_angle / PE_L(2.));
-    vec4 d = normalize(camera_matrix * vec4(image_position.x * h, image_position.y * h, PE_L(1.0), real(0)));
+    vec4 d;
+    if (_use_panini_projection == 1) {
+        d = normalize(camera_matrix * vec4(PaniniProjection(vec2(image_position.x, image_position.y), _view_angle, _panini_param), real(0)));
+    } else if (_use_360_camera == 1) {
+        real coef = min(resolution.x, resolution.y);
+        real ax = resolution.x / coef;
+        real ay = resolution.y / coef;
+        real rx;
+        real ry;
+        if (ax >= PE_L(2.0) * ay) {
+            ry = ay;
+            rx = PE_L(2.0) * ay;
+        } else {
+            rx = ax;
+            ry = ax / PE_L(2.0);
+        }
+        if (abs(image_position.x) > rx || abs(image_position.y) > ry) {
+            return vec3(PE_L(0.0));
+        }
+        real yaw = (image_position.x / rx) * Pi;
+        real pitch = (image_position.y / ry) * Pi05;
+        vec3 dir_local = vec3(sin(yaw) * cos(pitch), sin(pitch), cos(yaw) * cos(pitch));
+        d = normalize(camera_matrix * vec4(dir_local, real(0)));
+    } else if (_use_180_camera == 1) {
+        if (abs(image_position.x) > PE_L(1.0) || abs(image_position.y) > PE_L(1.0)) {
+            return vec3(PE_L(0.0));
+        }
+        real yaw = image_position.x * Pi05;
+        real pitch = image_position.y * Pi05;
+        vec3 dir_local = vec3(sin(yaw) * cos(pitch), sin(pitch), cos(yaw) * cos(pitch));
+        d = normalize(camera_matrix * vec4(dir_local, real(0)));
+    } else {
+        real h = tan(_view_angle / PE_L(2.));
+        d = normalize(camera_matrix * vec4(image_position.x * h, image_position.y * h, PE_L(1.0), real(0)));
+    }
 
     Ray r = Ray{o, d, PE_L(1.0), in_subspace};
     RayTraceResult trace = ray_tracing(r, camera_scale, bounces_out);
@@ -122,9 +188,34 @@ static inline vec3 get_color2(vec2 image_position, const mat4& camera_matrix, bo
     return trace.color;
 }
 
-// frag.glsl:466-503, mono path (:474-477, :501); disable_anaglyph = true drops the !ANAGLYPH! lines
+// frag.glsl:466-503.  The native build sets disable_anaglyph = true (main.rs:938), which drops the
+// !ANAGLYPH! lines (scene.rs:1079): what remains is the mono path and side-by-side stereo (:479-499).
 static inline vec3 get_color(vec2 image_position, int* bounces_out) {
-    return get_color2(image_position, _camera, _camera_in_subspace == 1, _camera_scale, bounces_out);
+    mat4 final_matrix = _camera;
+    bool final_in_subspace = _camera_in_subspace == 1;
+    real final_scale = _camera_scale;
+    vec2 _resolution = vec2(_resolution_x, _resolution_y);
+    vec2 final_resolution = _resolution;
+    if (_draw_side_by_side == 1) {
+        real coef = min(_resolution.x, _resolution.y);
+        vec2 position = image_position / PE_L(2.) * coef + _resolution / PE_L(2.);
+        vec2 resolution = vec2(_resolution.x / PE_L(2.), _resolution.y);
+        real coef2 = min(resolution.x, resolution.y);
+        if (position.x < resolution.x) {
+            image_position = (position - resolution / PE_L(2.)) / coef2 * PE_L(2.);
+            final_matrix = _camera_left_eye;
+            final_in_subspace = _left_eye_in_subspace == 1;
+            final_scale = _left_eye_scale;
+            final_resolution = resolution;
+        } else {
+            image_position = (position - vec2(resolution.x, PE_L(0.)) - resolution / PE_L(2.)) / coef2 * PE_L(2.);
+            final_matrix = _camera_right_eye;
+            final_in_subspace = _right_eye_in_subspace == 1;
+            final_scale = _right_eye_scale;
+            final_resolution = resolution;
+        }
+    }
+    return get_color2(image_position, final_matrix, final_in_subspace, final_scale, final_resolution, bounces_out);
 }
 
 // frag.glsl:506-513

@@ -20,6 +20,10 @@ class PeOracleFrame(C.Structure):
     _fields_ = [
         ("camera", C.c_float * 16),
         ("camera_mul_inv", C.c_float * 16),
+        ("camera_left_eye", C.c_float * 16), ("camera_right_eye", C.c_float * 16),
+        ("left_eye_scale", C.c_float), ("right_eye_scale", C.c_float), ("panini_param", C.c_float),
+        ("left_eye_in_subspace", C.c_int), ("right_eye_in_subspace", C.c_int), ("use_panini_projection", C.c_int),
+        ("use_360_camera", C.c_int), ("use_180_camera", C.c_int), ("draw_side_by_side", C.c_int),
         ("camera_scale", C.c_float), ("view_angle", C.c_float), ("t_start", C.c_float), ("t_end", C.c_float),
         ("offset_after_material", C.c_float), ("depth_map_min", C.c_float), ("depth_map_max", C.c_float),
         ("ray_tracing_depth", C.c_int), ("aa_count", C.c_int), ("aa_start", C.c_int), ("camera_in_subspace", C.c_int),
@@ -68,6 +72,19 @@ def make_frame(ir: dict, width: int, height: int, depth: int, camera=None, camer
     cmi = np.asarray(kw.get("camera_mul_inv", np.eye(4).reshape(16)), dtype=np.float64).astype(np.float32).reshape(16)
     for k in range(16):
         fr.camera_mul_inv[k] = float(cmi[k])
+    for key, dst in (("camera_left_eye", fr.camera_left_eye), ("camera_right_eye", fr.camera_right_eye)):
+        e32 = np.asarray(kw.get(key, cam), dtype=np.float64).astype(np.float32).reshape(16)
+        for k in range(16):
+            dst[k] = float(e32[k])
+    fr.left_eye_scale = float(np.float32(kw.get("left_eye_scale", 1.0)))
+    fr.right_eye_scale = float(np.float32(kw.get("right_eye_scale", 1.0)))
+    fr.panini_param = float(np.float32(kw.get("panini_param", 1.0)))      # RotateAroundCam::new, main.rs:112
+    fr.left_eye_in_subspace = int(kw.get("left_eye_in_subspace", 0))
+    fr.right_eye_in_subspace = int(kw.get("right_eye_in_subspace", 0))
+    fr.use_panini_projection = int(kw.get("use_panini_projection", 0))
+    fr.use_360_camera = int(kw.get("use_360_camera", 0))
+    fr.use_180_camera = int(kw.get("use_180_camera", 0))
+    fr.draw_side_by_side = int(kw.get("draw_side_by_side", 0))
     d = ir["renderer"]
     fr.camera_scale = float(np.float32(ir["camera_scale"] if camera_scale is None else camera_scale))
     fr.view_angle = float(np.float32(kw.get("view_angle", d["view_angle"])))

@@ -54,6 +54,7 @@ struct RaySlot {
     Ray r;
     vec3 current_color;
     float all_t;
+    float scale;  // camera scale of the view this ray belongs to (`_camera_scale` or an eye's)
     int bounce;
 #if PE_HAS_SKYBOX
     vec3 not_found;  // skybox colour of the PRIMARY ray: the reference evaluates it before the loop (scene.rs:1052-1058)
@@ -119,10 +120,71 @@ PE_FI vec2 quasi_random(int i) {
     return vec2(mod(0.5f + a1 * float(i), 1.0f), mod(0.5f + a2 * float(i), 1.0f));
 }
 
-// Primary ray of AA sample `a` of pixel (px, py): vertex stage + frag.glsl:519-524 + :409, :450-454.
-// `_tan_half_view` = tan(_view_angle / 2) is a uniform expression; the host evaluates it once per
-// frame in fp32 (pe_api.cpp, same libm call as the oracle) instead of once per pixel.
-PE_FI void primary_ray(int px, int py, int a, RaySlot& s) {
+// frag.glsl:305-342
+inline vec3 PaniniProjection(vec2 tc, float fov, float d) {
+    const float Pi = 3.14159265359f;
+    const float Pi05 = Pi * 0.5f;
+    float d2 = d * d;
+    {
+        float fo = Pi05 - fov * 0.5f;
+        float f = cos(fo) / sin(fo);
+        float f2 = f * f;
+        float b = (sqrt(max(0.0f, sqr(d + d2) * (f2 + f2 * f2))) - (d * f + f)) / (d2 + d2 * f2 - 1.0f);
+        tc *= b;
+    }
+    float h = tc.x;
+    float v = tc.y;
+    float h2 = h * h;
+    float k = h2 / sqr(d + 1.0f);
+    float k2 = k * k;
+    float discr = max(0.0f, k2 * d2 - (k + 1.0f) * (k * d2 - 1.0f));
+    float cosPhi = (-k * d + sqrt(discr)) / (k + 1.0f);
+    float S = (d + 1.0f) / (d + cosPhi);
+    float tanTheta = v / S;
+    float sinPhi = sqrt(max(0.0f, 1.0f - sqr(cosPhi)));
+    if (tc.x < 0.0f) sinPhi *= -1.0f;
+    float s = inversesqrt(1.0f + sqr(tanTheta));
+    return vec3(sinPhi, tanTheta, cosPhi) * s;
+}
+
+// Ray direction of get_color2 (frag.glsl:408-455) for one view.  Returns false where the reference
+// returns black without tracing (outside the 360 / VR180 image area).
+template <class M>
+PE_FI bool view_ray(const M& camera_matrix, vec2 image_position, vec2 resolution, bool in_subspace, RaySlot& s) {
+    const float Pi = 3.14159265359f;
+    const float Pi05 = Pi * 0.5f;
+    vec4 o = camera_matrix * vec4(0.0f, 0.0f, 0.0f, 1.0f);
+    vec4 d;
+    if (_use_panini_projection == 1) {
+        d = normalize(camera_matrix * vec4(PaniniProjection(image_position, _view_angle, _panini_param), 0.0f));
+    } else if (_use_360_camera == 1) {
+        float coef = min(resolution.x, resolution.y);
+        float ax = resolution.x / coef, ay = resolution.y / coef;
+        float rx, ry;
+        if (ax >= 2.0f * ay) { ry = ay; rx = 2.0f * ay; } else { rx = ax; ry = ax / 2.0f; }
+        if (abs(image_position.x) > rx || abs(image_position.y) > ry) return false;
+        float yaw = (image_position.x / rx) * Pi;
+        float pitch = (image_position.y / ry) * Pi05;
+        d = normalize(camera_matrix * vec4(sin(yaw) * cos(pitch), sin(pitch), cos(yaw) * cos(pitch), 0.0f));
+    } else if (_use_180_camera == 1) {
+        if (abs(image_position.x) > 1.0f || abs(image_position.y) > 1.0f) return false;
+        float yaw = image_position.x * Pi05;
+        float pitch = image_position.y * Pi05;
+        d = normalize(camera_matrix * vec4(sin(yaw) * cos(pitch), sin(pitch), cos(yaw) * cos(pitch), 0.0f));
+    } else {
+        // `_tan_half_view` = tan(_view_angle / 2) is a uniform expression (frag.glsl:450); the host
+        // evaluates it once per frame in fp32 (pe_api.cpp) instead of once per pixel.
+        float h = _tan_half_view;
+        d = normalize(camera_matrix * vec4(image_position.x * h, image_position.y * h, 1.0f, 0.0f));
+    }
+    s.r = Ray{o, d, 1.0f, in_subspace};
+    return true;
+}
+
+// Primary ray of AA sample `a` of pixel (px, py): vertex stage (scene.rs:1688-1693) + frag.glsl:519-524
+// + get_color (:474-501: mono, or side-by-side stereo) + get_color2's ray set-up.
+// Returns false when the sample is black without tracing.
+PE_FI bool primary_ray(int px, int py, int a, RaySlot& s) {
     vec2 resolution = vec2(_resolution_x, _resolution_y);
     vec2 position = vec2(float(px) + 0.5f, float(py) + 0.5f);
     float coef = min(resolution.x, resolution.y);
@@ -130,16 +192,31 @@ PE_FI void primary_ray(int px, int py, int a, RaySlot& s) {
     float pixel_size = 1.0f / min(resolution.x, resolution.y);
     vec2 ip = uv_screen + quasi_random(a) * pixel_size * 2.0f;
 
-    vec4 o = _camera * vec4(0.0f, 0.0f, 0.0f, 1.0f);
-    float h = _tan_half_view;
-    vec4 d = normalize(_camera * vec4(ip.x * h, ip.y * h, 1.0f, 0.0f));
-    s.r = Ray{o, d, 1.0f, _camera_in_subspace == 1};
     s.current_color = vec3(1.0f);
     s.all_t = 0.0f;
     s.bounce = 0;
+    bool ok;
+    if (_draw_side_by_side == 1) {
+        vec2 pos2 = ip / 2.0f * coef + resolution / 2.0f;
+        vec2 half_res = vec2(resolution.x / 2.0f, resolution.y);
+        float coef2 = min(half_res.x, half_res.y);
+        if (pos2.x < half_res.x) {
+            ip = (pos2 - half_res / 2.0f) / coef2 * 2.0f;
+            s.scale = _left_eye_scale;
+            ok = view_ray(_camera_left_eye, ip, half_res, _left_eye_in_subspace == 1, s);
+        } else {
+            ip = (pos2 - vec2(half_res.x, 0.0f) - half_res / 2.0f) / coef2 * 2.0f;
+            s.scale = _right_eye_scale;
+            ok = view_ray(_camera_right_eye, ip, half_res, _right_eye_in_subspace == 1, s);
+        }
+    } else {
+        s.scale = _camera_scale;
+        ok = view_ray(_camera, ip, resolution, _camera_in_subspace == 1, s);
+    }
 #if PE_HAS_SKYBOX
-    s.not_found = PE_NOT_FOUND_COLOR(s.r);
+    if (ok) s.not_found = PE_NOT_FOUND_COLOR(s.r);
 #endif
+    return ok;
 }
 
 // get_color2's tail (frag.glsl:456-463)
@@ -207,13 +284,14 @@ extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe
     int worst = 0;
     for (int a = _aa_start; a < _aa_count + _aa_start; a++) {  // frag.glsl:522-525
         RaySlot s;
-        primary_ray(px, grow, a, s);
         RayTraceResult res = RayTraceResult{color(0.0f, 0.0f, 0.0f), 0.0f, false};  // loop exhausted: frag.glsl:158
-        for (int j = 0; j < _ray_tracing_depth; j++) {                               // frag.glsl:112
-            s.bounce = j + 1;
-            if (bounce_once(s, _camera_scale, res)) break;
-        }
-        sum += resolve_sample(res);
+        if (primary_ray(px, grow, a, s)) {
+            for (int j = 0; j < _ray_tracing_depth; j++) {                           // frag.glsl:112
+                s.bounce = j + 1;
+                if (bounce_once(s, s.scale, res)) break;
+            }
+            sum += resolve_sample(res);
+        }                                                                            // else: get_color2 returned vec3(0)
         worst = pe::max(worst, s.bounce);
     }
     store_pixel(L, px, lrow, grow, sum, worst);
@@ -237,6 +315,7 @@ extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe
     vec3 sum = vec3(0.0f);
     int px = 0, lrow = 0, grow = 0, a = 0, worst = 0;
     bool alive = false;      // lane holds a ray in flight
+    bool skip = false;       // current sample is black without tracing (outside a 360 / VR180 image)
     // Warp-level tile cursor: the warp walks one 8x4 tile (32 pixels) at a time.
     unsigned tile = 0xffffffffu;  // current tile (warp-uniform)
     unsigned taken = 32;          // pixels of `tile` already handed to lanes (warp-uniform)
@@ -265,7 +344,7 @@ extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe
                     a = _aa_start;
                     sum = vec3(0.0f);
                     worst = 0;
-                    primary_ray(px, grow, a, s);
+                    skip = !primary_ray(px, grow, a, s);
                     alive = true;
                 }
                 // (an out-of-frame pixel of an edge tile is skipped: the lane stays idle)
@@ -281,12 +360,15 @@ extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe
         // ---- one bounce for every live lane
         if (alive) {
             bool done;
-            if (s.bounce >= depth) {           // loop exhausted (frag.glsl:158)
+            if (skip) {
+                res = RayTraceResult{vec3(0.0f), 0.0f, false};
+                done = true;
+            } else if (s.bounce >= depth) {    // loop exhausted (frag.glsl:158)
                 res = RayTraceResult{color(0.0f, 0.0f, 0.0f), 0.0f, false};
                 done = true;
             } else {
                 s.bounce++;
-                done = bounce_once(s, _camera_scale, res);
+                done = bounce_once(s, s.scale, res);
                 if (!done && s.bounce >= depth) {
                     res = RayTraceResult{color(0.0f, 0.0f, 0.0f), 0.0f, false};
                     done = true;

@@ -141,9 +141,9 @@ void ensure_layout(pe_ctx* c) {
     c->cblock.assign(c->layout.size, 0);
     c->layout_valid = true;
     set_renderer_defaults(c);
-    // identity camera and identity `_camera_mul_inv` (teleport_matrix.inverse(), main.rs:1286-1289)
+    // identity `_camera`, `_camera_mul_inv` (teleport_matrix.inverse(), main.rs:1286-1289) and eye cameras
     float* cam = reinterpret_cast<float*>(c->cblock.data() + c->layout.off_mat) + 16 * c->layout.camera_slot;
-    for (int k = 0; k < 32; k++) cam[k] = ((k % 16) % 5 == 0) ? 1.0f : 0.0f;
+    for (int k = 0; k < 64; k++) cam[k] = ((k % 16) % 5 == 0) ? 1.0f : 0.0f;
     // values set before the layout existed
     for (auto& kv : c->pending_mat) pe_set_uniform_mat4(c, kv.first.c_str(), kv.second.data());
     for (auto& kv : c->pending_f) pe_set_uniform_f32(c, kv.first.c_str(), kv.second);
@@ -171,6 +171,9 @@ void set_renderer_defaults(pe_ctx* c) {
     F("_depth_map_max", 10.0f);
     F("_resolution_x", 1.0f);
     F("_resolution_y", 1.0f);
+    F("_left_eye_scale", 1.0f);
+    F("_right_eye_scale", 1.0f);
+    F("_panini_param", 1.0f);
     I("_ray_tracing_depth", 100);
     I("_aa_start", 0);
     I("_aa_count", 1);
@@ -180,6 +183,12 @@ void set_renderer_defaults(pe_ctx* c) {
     I("_grid_disable", 0);
     I("_black_border_disable", 0);
     I("_draw_depth_map", 0);
+    I("_left_eye_in_subspace", 0);
+    I("_right_eye_in_subspace", 0);
+    I("_use_panini_projection", 0);
+    I("_use_360_camera", 0);
+    I("_use_180_camera", 0);
+    I("_draw_side_by_side", 0);
 }
 
 std::vector<int> current_ints(pe_ctx* c) {

@@ -15,11 +15,14 @@ namespace pe_host {
 
 const char* const kRendererFloats[] = {"_camera_scale", "_tan_half_view", "_view_angle", "_t_start", "_t_end",
                                        "_offset_after_material", "_depth_map_min", "_depth_map_max",
-                                       "_resolution_x", "_resolution_y"};
+                                       "_resolution_x", "_resolution_y", "_left_eye_scale", "_right_eye_scale",
+                                       "_panini_param"};
 const int kNumRendererFloats = int(sizeof(kRendererFloats) / sizeof(kRendererFloats[0]));
 const char* const kRendererInts[] = {"_ray_tracing_depth", "_aa_start", "_aa_count", "_camera_in_subspace",
                                      "_darken_by_distance", "_angle_color_disable", "_grid_disable",
-                                     "_black_border_disable", "_draw_depth_map"};
+                                     "_black_border_disable", "_draw_depth_map", "_left_eye_in_subspace",
+                                     "_right_eye_in_subspace", "_use_panini_projection", "_use_360_camera",
+                                     "_use_180_camera", "_draw_side_by_side"};
 const int kNumRendererInts = int(sizeof(kRendererInts) / sizeof(kRendererInts[0]));
 // Renderer ints that change per frame / per motion-blur sub-frame stay dynamic.
 static bool renderer_int_is_dynamic(const std::string& n) { return n == "_ray_tracing_depth" || n == "_aa_start"; }
@@ -42,11 +45,13 @@ ConstLayout make_layout(const SceneDesc& scene) {
     L.camera_slot = L.n_mat;
     L.mat_slot["_camera"] = L.camera_slot;
     L.mat_slot["_camera_mul_inv"] = L.camera_slot + 1;
+    L.mat_slot["_camera_left_eye"] = L.camera_slot + 2;
+    L.mat_slot["_camera_right_eye"] = L.camera_slot + 3;
     for (int k = 0; k < kNumRendererFloats; k++) L.float_slot[kRendererFloats[k]] = L.n_float + k;
     for (int k = 0; k < kNumRendererInts; k++) L.int_slot[kRendererInts[k]] = L.n_int + k;
     for (int k = 0; k < L.n_tex; k++) L.tex_slot[scene.textures[k]] = k;
     L.off_mat = 0;
-    L.off_float = size_t(L.n_mat + 2) * 64;
+    L.off_float = size_t(L.n_mat + 4) * 64;
     L.off_int = L.off_float + size_t(L.n_float + kNumRendererFloats) * 4;
     size_t end_int = L.off_int + size_t(L.n_int + kNumRendererInts) * 4;
     L.off_tex = (end_int + 7) & ~size_t(7);
@@ -526,7 +531,7 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     hd << "namespace pe {\n";
     hd << "// Constant uniform block: scene matrices + camera, floats, ints, texture descriptors.\n";
     hd << "struct PeConstBlock {\n";
-    hd << "    cmat4 m[" << (L.n_mat + 2) << "];\n";
+    hd << "    cmat4 m[" << (L.n_mat + 4) << "];\n";
     hd << "    float f[" << (L.n_float + kNumRendererFloats) << "];\n";
     hd << "    int i[" << (L.n_int + kNumRendererInts) << "];\n";
     hd << "    sampler2D tex[" << (L.n_tex > 0 ? L.n_tex : 1) << "];\n";
@@ -546,6 +551,8 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     }
     hd << "#define _camera (PE_C.m[" << L.camera_slot << "])\n";
     hd << "#define _camera_mul_inv (PE_C.m[" << (L.camera_slot + 1) << "])\n";
+    hd << "#define _camera_left_eye (PE_C.m[" << (L.camera_slot + 2) << "])\n";
+    hd << "#define _camera_right_eye (PE_C.m[" << (L.camera_slot + 3) << "])\n";
     for (int k = 0; k < L.n_float; k++) hd << "#define " << L.floats[k] << " (PE_C.f[" << k << "])\n";
     for (int k = 0; k < kNumRendererFloats; k++) hd << "#define " << kRendererFloats[k] << " (PE_C.f[" << (L.n_float + k) << "])\n";
     for (int k = 0; k < L.n_int; k++) {

@@ -68,7 +68,7 @@ struct ConstLayout {
     std::vector<std::string> mats, floats, ints;       // declaration order
     std::map<std::string, int> mat_slot, float_slot, int_slot, tex_slot;  // names incl. renderer ones
     size_t off_mat = 0, off_float = 0, off_int = 0, off_tex = 0, size = 0;
-    int camera_slot = 0;  // m[n_mat]; m[n_mat + 1] = _camera_mul_inv
+    int camera_slot = 0;  // m[n_mat] = _camera, then _camera_mul_inv, _camera_left_eye, _camera_right_eye
 };
 ConstLayout make_layout(const SceneDesc& scene);
 

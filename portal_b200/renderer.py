@@ -90,6 +90,13 @@ class SceneRenderer:
         self.darken_by_distance = True
         self.view_angle = math.pi / 2.0  # RotateAroundCam::new, main.rs:109
         self.camera_in_subspace = False
+        self.use_panini_projection = False   # RotateAroundCam::new, main.rs:111-116
+        self.panini_param = 1.0
+        self.use_360_camera = False
+        self.use_180_camera = False
+        self.draw_side_by_side = False       # SceneRenderer::new, main.rs:1027
+        self.eye_distance = 0.07             # main.rs:1028
+        self.camera_mul_inv = np.eye(4).reshape(16)   # teleport_matrix.inverse(), main.rs:1286-1289
         cam = scene_ir["cam"]
         self.set_cam(cam["look_at"], cam["alpha"], cam["beta"], cam["r"])  # main.rs:1057
         self._check(self._lib.pe_set_option(self._ctx, b"persistent", int(persistent)))
@@ -222,6 +229,33 @@ class SceneRenderer:
         s("_grid_disable", int(self.grid_disable))
         s("_black_border_disable", int(self.black_border_disable))
         s("_darken_by_distance", int(self.darken_by_distance))
+        s("_camera_mul_inv", self.camera_mul_inv)
+        s("_use_panini_projection", int(self.use_panini_projection))
+        s("_panini_param", float(self.panini_param))
+        s("_use_360_camera", int(self.use_360_camera))
+        s("_use_180_camera", int(self.use_180_camera))
+        s("_draw_side_by_side", int(self.draw_side_by_side))
+        left, right = self.eye_matrices()
+        s("_camera_left_eye", left)
+        s("_camera_right_eye", right)
+        s("_left_eye_scale", camera_scale(left))
+        s("_right_eye_scale", camera_scale(right))
+        s("_left_eye_in_subspace", int(self.camera_in_subspace))
+        s("_right_eye_in_subspace", int(self.camera_in_subspace))
+
+    def eye_matrices(self):
+        """Eye cameras of teleport_eye_matrices (main.rs:1121-1139) when no portal lies between the eyes:
+        DMat4::from_translation(C * (+-eye_distance/2, 0, 0, 1) - cam_pos) * C."""
+        c = np.asarray(self.camera_matrix, dtype=np.float64).reshape(4, 4)  # rows = columns of the matrix
+        pos = c[3, :3]
+        out = []
+        for sx in (-0.5, 0.5):
+            v = np.array([sx * self.eye_distance, 0.0, 0.0, 1.0])
+            p = v @ c                       # C * v with column-major storage
+            t = np.eye(4)
+            t[3, :3] = p[:3] - pos
+            out.append((c @ t).reshape(16))  # T * C in column-major rows
+        return out[0], out[1]
 
     def set_texture(self, name: str, rgba8: np.ndarray):
         arr = np.ascontiguousarray(rgba8, dtype=np.uint8)

@@ -121,6 +121,37 @@ def test_antialiasing_and_flags(torch_cuda):
     assert np.abs(r.render_host(200, 120) - ref).max() <= TOL
 
 
+def test_projection_variants_and_side_by_side(torch_cuda):
+    """panini / 360 / VR180 projections (frag.glsl:305-342, 413-448) and side-by-side
+    stereo (:479-499).  sin/cos/tan come from libdevice vs libm -> tolerance, not bit equality."""
+    from portal_b200.renderer import camera_scale
+    scene = "monoportal"
+    orc = _oracle(scene)
+    w, h = 320, 200
+    for kw in ({"use_panini_projection": 1, "panini_param": 0.7}, {"use_360_camera": 1}, {"use_180_camera": 1}):
+        r = _renderer(scene)
+        for k, v in kw.items():
+            setattr(r, k, v if k == "panini_param" else bool(v))
+        ref = orc.render(w, h, DEPTH[scene], **kw)
+        img = r.render_host(w, h)
+        ok = np.abs(img - ref).max(axis=-1) <= TOL
+        assert ok.mean() >= 0.999, (kw, ok.mean())
+        assert not np.array_equal(img, _renderer(scene).render_host(w, h))     # the variant really changes the image
+    r = _renderer(scene)
+    r.draw_side_by_side = True
+    left, right = r.eye_matrices()
+    ref = orc.render(w, h, DEPTH[scene], draw_side_by_side=1, camera_left_eye=left, camera_right_eye=right,
+                     left_eye_scale=camera_scale(left), right_eye_scale=camera_scale(right))
+    img = r.render_host(w, h)
+    assert np.array_equal(_bits(img), _bits(ref))            # no transcendental on this path -> bit-exact
+    assert not np.array_equal(img[:, : w // 2], img[:, w // 2:])
+    rp = _renderer(scene, persistent=True)
+    rp.use_360_camera = True
+    r2 = _renderer(scene)
+    r2.use_360_camera = True
+    assert np.array_equal(_bits(rp.render_host(w, 100)), _bits(r2.render_host(w, 100)))   # black bars: skipped samples
+
+
 def test_uniform_update_and_respecialisation(torch_cuda):
     scene = "portal_in_portal"
     orc = _oracle(scene)
