@@ -190,8 +190,7 @@ def run_ours(args):
         else:
             sharder.render(i, sptr)
             if mode == "p2p":
-                stream.synchronize()          # this rank's pixels are on their way / landed
-                dist.barrier()                # rank 0's frame is complete when everyone is past here
+                sharder.fence()               # stream-ordered 4-byte all-reduce: frame complete on rank 0 after it
 
     def barrier():
         if world > 1:
@@ -226,9 +225,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = r.launch_count() - l0
     dev_ms = ev[0].elapsed_time(ev[1])
-    # p2p mode synchronises on the host every step, so its honest clock is the host's wall clock
-    # between the two device-synchronised barriers; gather mode is timed on the device.
-    step_ms = wall_ms if (world > 1 and mode == "p2p") else dev_ms
+    step_ms = dev_ms      # both modes are stream-ordered end to end: device time between the two events
+    del wall_ms
     ms = torch.tensor([step_ms], dtype=torch.float64, device="cuda")
     kms = torch.tensor([sum(a.elapsed_time(b) for a, b in kev) / args.steps], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -291,7 +289,7 @@ def run_ours(args):
             "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, saved camera, aa 1" + (" (BASELINE.json headline config)" if (args.scene, w, h, depth) == ("portal_in_portal", 3840, 2160, 40) else ""),
                        "parallelism": "1 GPU" if world == 1 else (
                            f"{world} GPUs x cyclic {STRIP_ROWS}-row strips + 1 NCCL gather + de-interleave" if mode == "gather" else
-                           f"{world} GPUs x cyclic {STRIP_ROWS}-row strips, kernels store into rank 0's frame over NVLink (CUDA IPC), barrier per frame"),
+                           f"{world} GPUs x cyclic {STRIP_ROWS}-row strips, kernels store into rank 0's frame over NVLink (CUDA IPC), 4-byte all-reduce as frame fence"),
                        "scheduler": "persistent warps + per-bounce refill" if args.persistent else "one thread per pixel, 8x4 warp tiles, 256-thread blocks, <= 64 regs",
                        "l2": "each step writes a 132.7 MB frame (> 126 MB L2) into alternating buffers; inputs are a <8 KB constant block"},
             "kernel_ms": round(kernel_ms, 4),

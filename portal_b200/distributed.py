@@ -136,6 +136,17 @@ class FrameSharder:
         else:
             r.draw_texture(self.target, self.dst_ptr, 0, stream_ptr)
 
+    def fence(self):
+        """End-of-frame fence for p2p mode, stream-ordered and without a host synchronisation: a 4-byte
+        all-reduce enqueued after the render kernel on every rank.  When it completes on rank 0's
+        stream every rank's kernel -- and with it every remote store into rank 0's frame -- is done."""
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            if not hasattr(self, "_token"):
+                self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
+            dist.all_reduce(self._token)
+
     def close(self):
         lib, ctx = self.r._lib, self.r._ctx
         if self._peer_ptr:

@@ -34,6 +34,8 @@ def main():
         sh = FrameSharder(r, w, h, rank, world, mode=mode)
         for i in range(2):
             sh.render(i, stream.cuda_stream)
+            if mode == "p2p":
+                sh.fence()
             stream.synchronize()
             dist.barrier()
         if rank == 0:
