@@ -132,6 +132,12 @@ PE_API int pe_render(pe_ctx* ctx, const pe_target* target, void* out_device, voi
 PE_API int pe_render_host(pe_ctx* ctx, const pe_target* target, float* out_host);
 /* Same, quantised to RGBA8 as the reference's render target + get_texture_data deliver it. */
 PE_API int pe_render_host_rgba8(pe_ctx* ctx, const pe_target* target, uint8_t* out_host);
+/* Camera-teleportation probe (replaces teleport_external_ray, src/main.rs:1361-1409 +
+ * src/frag.glsl:166-257, 527-547): follow the segment a -> b through the scene's portals (at most
+ * 10, `teleport_light_u` forced on) and return where its end point lands -- directly, instead of
+ * floats encoded into a 2x3 RGBA8 target.  have_result == 0: no portal was crossed (pos = 0). */
+PE_API int pe_probe_ray(pe_ctx* ctx, const float a[3], const float b[3], float pos_out[3], int32_t* have_result,
+                        int32_t* encounter_object, int32_t* change_subspace);
 PE_API int pe_sync(pe_ctx* ctx);
 /* Number of kernel launches this context has issued (render + helper kernels). */
 PE_API uint64_t pe_launch_count(pe_ctx* ctx);

@@ -433,7 +433,7 @@ void pe_oracle_set_texture(int slot, const unsigned char* rgba, int w, int h) {
     pe_oracle::PE_U.tex[slot].w = w;
     pe_oracle::PE_U.tex[slot].h = h;
 }
-void pe_oracle_render(const PeOracleFrame* fr, int row0, int row1, float* out, int* bounces, int threads) {
+static void pe_oracle_load_frame(const PeOracleFrame* fr) {
     using namespace pe_oracle;
     for (int c = 0; c < 4; c++)
         _camera.c[c] = vec4(real(fr->camera[4 * c + 0]), real(fr->camera[4 * c + 1]), real(fr->camera[4 * c + 2]),
@@ -461,6 +461,21 @@ void pe_oracle_render(const PeOracleFrame* fr, int row0, int row1, float* out, i
     _camera_in_subspace = fr->camera_in_subspace; _darken_by_distance = fr->darken_by_distance;
     _angle_color_disable = fr->angle_color_disable; _grid_disable = fr->grid_disable;
     _black_border_disable = fr->black_border_disable; _draw_depth_map = fr->draw_depth_map;
+}
+// main()'s probe branch, frag.glsl:527-529: Ray(a, b - a, 1, _camera_in_subspace == 1); out = pos xyz + 3 flags
+void pe_oracle_probe(const PeOracleFrame* fr, const float* a, const float* b, float* out_pos, int* out_flags) {
+    using namespace pe_oracle;
+    pe_oracle_load_frame(fr);
+    Ray r = Ray{vec4(real(a[0]), real(a[1]), real(a[2]), real(1)),
+                vec4(real(b[0]) - real(a[0]), real(b[1]) - real(a[1]), real(b[2]) - real(a[2]), real(0)), real(1),
+                _camera_in_subspace == 1};
+    ExternalRayTeleportation t = teleport_external_ray(r);
+    out_pos[0] = float(t.pos.x); out_pos[1] = float(t.pos.y); out_pos[2] = float(t.pos.z);
+    out_flags[0] = t.have_result; out_flags[1] = t.encounter_object; out_flags[2] = t.change_subspace;
+}
+void pe_oracle_render(const PeOracleFrame* fr, int row0, int row1, float* out, int* bounces, int threads) {
+    using namespace pe_oracle;
+    pe_oracle_load_frame(fr);
     const int W = fr->width;
     (void)threads;
     // Work items are 64-pixel runs (not rows) so that a 16-row sample band still feeds every core.

@@ -104,6 +104,64 @@ static inline RayTraceResult ray_tracing(Ray r, real camera_scale, int* bounces_
     return RayTraceResult{color(real(0), real(0), real(0)), PE_L(0.0), false};
 }
 
+// frag.glsl:199-203
+struct ExternalRayTeleportation {
+    vec3 pos;
+    bool encounter_object;
+    bool change_subspace;
+    bool have_result;   // not in the GLSL struct: the reference's host infers it from pos != 0 (main.rs:1400-1408)
+};
+
+// frag.glsl:209-257: camera teleportation probe -- follow the segment a->b (r.d = b - a, so t in [0,1]
+// spans the segment) through at most 10 portals and report where its end point lands.
+static inline ExternalRayTeleportation teleport_external_ray(Ray r) {
+    r = normalize_ray(r);
+    bool have_result = false;
+    bool stop_at_object = false;
+    real all_t = real(0);
+    int max_camera_teleports = 10;
+    for (int j = 0; j < max_camera_teleports; j++) {
+        SceneIntersection i = scene_intersect(r);
+        SceneIntersectionWithMaterial i2 = scene_intersect_material_process(r);
+
+        bool continue_intersect = false;
+        MaterialProcessing m = material_empty();
+        if (nearer(i.hit, i2.scene.hit)) {
+            if (i2.scene.hit.t * r.tmul + all_t < PE_L(1.0)) {
+                r.o += r.d * i2.scene.hit.t;
+                all_t += i2.scene.hit.t * r.tmul;
+                if (i2.scene.material == CUSTOM_MATERIAL) {
+                    m = i2.material;
+                } else {
+                    m = material_process(r, i2.scene);
+                }
+                continue_intersect = !m.is_final;
+                stop_at_object = stop_at_object || m.is_final;
+            }
+        } else if (i.hit.hit) {
+            if (i.hit.t * r.tmul + all_t < PE_L(1.0)) {
+                r.o += r.d * i.hit.t;
+                all_t += i.hit.t * r.tmul;
+                m = material_process(r, i);
+                continue_intersect = !m.is_final;
+                stop_at_object = stop_at_object || m.is_final;
+            }
+        }
+        if (continue_intersect) {
+            r = m.new_ray;
+            have_result = true;
+        } else {
+            break;
+        }
+    }
+    if (have_result) {
+        r.o += r.d * (PE_L(1.0) - all_t) / r.tmul;
+        return ExternalRayTeleportation{vec3(r.o), stop_at_object, int(r.in_subspace) != _camera_in_subspace, true};
+    } else {
+        return ExternalRayTeleportation{vec3(real(0)), stop_at_object, int(r.in_subspace) != _camera_in_subspace, false};
+    }
+}
+
 // frag.glsl:297-301
 static inline real Pow2(real x) { return x * x; }
 

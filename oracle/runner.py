@@ -142,3 +142,19 @@ class Oracle:
         bnc = np.empty((r1 - r0, width), dtype=np.int32) if want_bounces else None
         self.lib.pe_oracle_render(C.byref(fr), r0, r1, out.ctypes.data, None if bnc is None else bnc.ctypes.data, threads)
         return (out, bnc) if want_bounces else out
+
+    def probe(self, a, b, **kw):
+        """teleport_external_ray(a, b) -> (pos[3] float32, have_result, encounter_object, change_subspace).
+        Like the reference (main.rs:1367) the probe runs with `teleport_light_u` forced to 1 if the scene has it."""
+        had = "teleport_light_u" in self.ir["uniforms"]
+        if had:
+            self.set_uniforms({"teleport_light_u": 1})
+        fr = make_frame(self.ir, 2, 3, 0, **kw)
+        pa = (C.c_float * 3)(*[float(np.float32(x)) for x in a])
+        pb = (C.c_float * 3)(*[float(np.float32(x)) for x in b])
+        out, flags = (C.c_float * 3)(), (C.c_int * 3)()
+        self.lib.pe_oracle_probe.argtypes = [C.POINTER(PeOracleFrame), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.pe_oracle_probe(C.byref(fr), pa, pb, out, flags)
+        if had:
+            self.set_uniforms()
+        return np.array(list(out), dtype=np.float32), bool(flags[0]), bool(flags[1]), bool(flags[2])

@@ -75,6 +75,8 @@ def lib() -> C.CDLL:
         "pe_render": (i32, [vp, C.POINTER(PeTarget), vp, vp, vp]),
         "pe_render_host": (i32, [vp, C.POINTER(PeTarget), vp]),
         "pe_render_host_rgba8": (i32, [vp, C.POINTER(PeTarget), vp]),
+        "pe_probe_ray": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32),
+                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "pe_sync": (i32, [vp]),
         "pe_launch_count": (C.c_uint64, [vp]),
         "pe_deinterleave_strips": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),

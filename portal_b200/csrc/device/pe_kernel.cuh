@@ -259,6 +259,64 @@ PE_FI void store_pixel(const PeLaunch& L, int px, int lrow, int grow, vec3 sum, 
 
 }  // namespace pe
 
+#ifndef PE_WITH_PROBE
+#define PE_WITH_PROBE 0
+#endif
+#if PE_WITH_PROBE
+// Camera-teleportation probe.  The reference renders a 2x3 RGBA8 target whose pixels
+// carry the bytes of three floats plus two flags (frag.glsl:166-257, :527-547) and decodes them on the
+// host (main.rs:1361-1409); here one thread follows the segment a -> b through at most 10 portals
+// (frag.glsl:209-257) and writes { pos.x, pos.y, pos.z, have_result, encounter_object, change_subspace }.
+struct PeProbe {
+    float ax, ay, az, bx, by, bz;
+    float* out;  // 6 floats
+};
+extern "C" __global__ void pe_probe_kernel(const PeProbe P) {
+    using namespace pe;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Ray r = Ray{vec4(P.ax, P.ay, P.az, 1.0f), vec4(P.bx - P.ax, P.by - P.ay, P.bz - P.az, 0.0f), 1.0f, _camera_in_subspace == 1};
+    r = normalize_ray(r);
+    bool have_result = false, stop_at_object = false;
+    float all_t = 0.0f;
+    for (int j = 0; j < 10; j++) {  // max_camera_teleports, frag.glsl:214
+        SceneIntersection i = scene_intersect(r);
+        SceneIntersectionWithMaterial i2 = scene_intersect_material_process(r);
+        bool continue_intersect = false;
+        MaterialProcessing m = material_empty();
+        if (nearer(i.hit, i2.scene.hit)) {
+            if (i2.scene.hit.t * r.tmul + all_t < 1.0f) {
+                r.o += r.d * i2.scene.hit.t;
+                all_t += i2.scene.hit.t * r.tmul;
+                if (i2.scene.material == CUSTOM_MATERIAL) m = i2.material;
+                else m = material_process(r, i2.scene);
+                continue_intersect = !m.is_final;
+                stop_at_object = stop_at_object || m.is_final;
+            }
+        } else if (i.hit.hit) {
+            if (i.hit.t * r.tmul + all_t < 1.0f) {
+                r.o += r.d * i.hit.t;
+                all_t += i.hit.t * r.tmul;
+                m = material_process(r, i);
+                continue_intersect = !m.is_final;
+                stop_at_object = stop_at_object || m.is_final;
+            }
+        }
+        if (!continue_intersect) break;
+        r = m.new_ray;
+        have_result = true;
+    }
+    vec3 pos = vec3(0.0f);
+    if (have_result) {
+        r.o += r.d * (1.0f - all_t) / r.tmul;
+        pos = vec3(r.o);
+    }
+    P.out[0] = pos.x; P.out[1] = pos.y; P.out[2] = pos.z;
+    P.out[3] = have_result ? 1.0f : 0.0f;
+    P.out[4] = stop_at_object ? 1.0f : 0.0f;
+    P.out[5] = (int(r.in_subspace) != _camera_in_subspace) ? 1.0f : 0.0f;
+}
+#endif
+
 #ifndef PE_PERSISTENT
 #define PE_PERSISTENT 0
 #endif

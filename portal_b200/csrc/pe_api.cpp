@@ -48,6 +48,7 @@ struct Variant {
     std::vector<char> cubin;
     CUmodule_t module = nullptr;
     CUfunction_t kernel = nullptr;
+    CUfunction_t probe = nullptr;
     CUdeviceptr_t const_ptr = 0;
     size_t const_size = 0;
     int regs = 0;
@@ -224,6 +225,7 @@ std::vector<int> variant_key(pe_ctx* c, const std::vector<int>& ints, const std:
     }
     if (c->opts.specialize_matrices)
         for (auto& zo : masks) key.push_back(int(zo.first | (zo.second << 16)));
+    key.push_back(c->opts.with_probe ? 1 : 0);
     return key;
 }
 
@@ -319,6 +321,10 @@ bool select_variant(pe_ctx* c) {
         r = d->cuModuleGetGlobal(&v->const_ptr, &v->const_size, v->module, "PE_C");
         if (r != 0) { c->err = "cuModuleGetGlobal(PE_C): " + driver_error(d, r); return false; }
         if (v->const_size != c->layout.size) { c->err = "constant block size mismatch between host and device"; return false; }
+        if (c->opts.with_probe) {
+            r = d->cuModuleGetFunction(&v->probe, v->module, "pe_probe_kernel");
+            if (r != 0) { c->err = "cuModuleGetFunction(pe_probe_kernel): " + driver_error(d, r); return false; }
+        }
         d->cuFuncGetAttribute(&v->regs, 4 /*CU_FUNC_ATTRIBUTE_NUM_REGS*/, v->kernel);
         int nb = 1;
         if (d->cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v->kernel, c->opts.block_threads, 0) == 0 && nb > 0)
@@ -713,6 +719,51 @@ int pe_render(pe_ctx* c, const pe_target* t, void* out_device, void* bounces_dev
     r = d->cuLaunchKernel(v->kernel, gx, gy, 1, unsigned(c->opts.block_threads), 1, 1, 0, s, args, nullptr);
     if (r != 0) return c->fail("cuLaunchKernel(pe_render_kernel): " + driver_error(d, r));
     c->launches++;
+    return 0;
+}
+
+static bool ensure_scratch(pe_ctx* c, void** p, size_t* have, size_t need);
+
+int pe_probe_ray(pe_ctx* c, const float a[3], const float b[3], float pos_out[3], int32_t* have_result,
+                 int32_t* encounter_object, int32_t* change_subspace) {
+    if (!c) return 1;
+    if (!a || !b || !pos_out) return c->fail("pe_probe_ray: null argument");
+    if (!bind_device(c)) return 1;
+    ensure_layout(c);
+    // main.rs:1367: the probe always runs with `teleport_light_u` = 1 (if the scene has that uniform)
+    auto tl = c->layout.int_slot.find("teleport_light_u");
+    int saved = 0;
+    if (tl != c->layout.int_slot.end()) { saved = *islot(c, tl->second); *islot(c, tl->second) = 1; }
+    const bool had_probe = c->opts.with_probe;
+    c->opts.with_probe = true;
+    bool ok = select_variant(c);
+    struct { float ax, ay, az, bx, by, bz; void* out; } P;
+    float host[6] = {0, 0, 0, 0, 0, 0};
+    if (ok) {
+        if (!ensure_scratch(c, &c->scratch8_dev, &c->scratch8_bytes, 64)) ok = false;
+    }
+    if (ok) {
+        Variant* v = c->current;
+        const DriverApi* d = c->drv;
+        CUstream_t s = (CUstream_t)c->stream;
+        P = {a[0], a[1], a[2], b[0], b[1], b[2], c->scratch8_dev};
+        void* args[] = {&P};
+        CUresult_t r = d->cuMemcpyHtoDAsync(v->const_ptr, c->cblock.data(), c->cblock.size(), s);
+        if (r == 0) r = d->cuLaunchKernel(v->probe, 1, 1, 1, 32, 1, 1, 0, s, args, nullptr);
+        if (r != 0) { c->err = "pe_probe_kernel: " + driver_error(d, r); ok = false; }
+        else {
+            c->launches++;
+            ok = cuda_ok(c, cudaMemcpyAsync(host, c->scratch8_dev, sizeof host, cudaMemcpyDeviceToHost, c->stream), "probe readback") &&
+                 cuda_ok(c, cudaStreamSynchronize(c->stream), "pe_probe_ray");
+        }
+    }
+    c->opts.with_probe = had_probe;
+    if (tl != c->layout.int_slot.end()) *islot(c, tl->second) = saved;
+    if (!ok) return 1;
+    for (int k = 0; k < 3; k++) pos_out[k] = host[k];
+    if (have_result) *have_result = host[3] != 0.0f;
+    if (encounter_object) *encounter_object = host[4] != 0.0f;
+    if (change_subspace) *change_subspace = host[5] != 0.0f;
     return 0;
 }
 

@@ -80,6 +80,7 @@ struct GenOptions {
     int block_threads = 256;
     int min_blocks = 4;
     bool specialize_matrices = true;  // bake each matrix's exact-0 / exact-1 structure into the program (smat4)
+    bool with_probe = false;  // also emit pe_probe_kernel (camera-teleportation probe)
     bool unroll_loops = true;  // false: `#pragma unroll 1` on every loop of the user snippets (smaller code)
 };
 

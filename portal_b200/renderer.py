@@ -301,5 +301,14 @@ class SceneRenderer:
         self.render_host_ptr(width, height, out.ctypes.data, rgba8=True)
         return out
 
+    def probe_ray(self, a, b):
+        """teleport_external_ray (main.rs:1361-1409): -> (pos float32[3], have_result, encounter_object, change_subspace)."""
+        self.set_uniforms()
+        f3 = C.c_float * 3
+        pa, pb, out = f3(*[float(np.float32(x)) for x in a]), f3(*[float(np.float32(x)) for x in b]), f3()
+        hr, eo, cs = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self._lib.pe_probe_ray(self._ctx, pa, pb, out, C.byref(hr), C.byref(eo), C.byref(cs)))
+        return np.array(list(out), dtype=np.float32), bool(hr.value), bool(eo.value), bool(cs.value)
+
     def sync(self):
         self._check(self._lib.pe_sync(self._ctx))

@@ -39,6 +39,21 @@ def _bits(a):
     return np.ascontiguousarray(a).view(np.uint32)
 
 
+def _assert_close_with_edge_protocol(img, ref, scene, w, h, min_ok=0.999, **oracle_kw):
+    """SURVEY.md §8c parity protocol for paths that evaluate libm/libdevice transcendentals: >= min_ok of
+    the pixels within TOL, and every pixel beyond it must be (adjacent to) one the float64 oracle flags as
+    ill-conditioned -- a pixel whose value flips with the last bit of some intermediate (grid / border edges)."""
+    err = np.abs(img - ref).max(axis=-1)
+    bad = err > TOL
+    assert bad.mean() <= 1.0 - min_ok, f"{bad.sum()} of {bad.size} px beyond {TOL}"
+    if bad.any():
+        f64 = _oracle(scene, "f64").render(w, h, DEPTH[scene], **oracle_kw)
+        ill = np.abs(f64 - ref).max(axis=-1) > 1e-5
+        d = ill.copy()
+        d[1:] |= ill[:-1]; d[:-1] |= ill[1:]; d[:, 1:] |= ill[:, :-1]; d[:, :-1] |= ill[:, 1:]
+        assert (bad & ~d).sum() <= max(3, int(0.1 * bad.sum())), "mismatches away from ill-conditioned pixels"
+
+
 @pytest.mark.parametrize("scene", SCENES)
 def test_golden_frame(scene, torch_cuda):
     files = [f for f in os.listdir(os.path.join(GOLDEN, "frames")) if f.startswith(scene + "_")]
@@ -70,15 +85,7 @@ def test_parity_with_oracle(scene, persistent, torch_cuda):
         assert np.array_equal(_bits(img), _bits(ref)), f"max err {err.max()}, mismatching px {(err > 0).sum()}"
         assert np.array_equal(b, ref_b)
     else:
-        bad = err > TOL
-        assert bad.mean() <= 0.001, f"{bad.sum()} px beyond {TOL}"
-        if bad.any():
-            f64 = _oracle(scene, "f64").render(w, h, DEPTH[scene])
-            ill = np.abs(f64 - ref).max(axis=-1) > 1e-5
-            # dilate by one pixel: an edge that flips for one rounding flips for its neighbours' too
-            d = ill.copy()
-            d[1:] |= ill[:-1]; d[:-1] |= ill[1:]; d[:, 1:] |= ill[:, :-1]; d[:, :-1] |= ill[:, 1:]
-            assert (bad & ~d).sum() <= max(3, int(0.1 * bad.sum())), "mismatches away from ill-conditioned pixels"
+        _assert_close_with_edge_protocol(img, ref, scene, w, h)
     assert np.all(img[..., 3] == 1.0)
 
 
@@ -127,16 +134,17 @@ def test_projection_variants_and_side_by_side(torch_cuda):
     from portal_b200.renderer import camera_scale
     scene = "monoportal"
     orc = _oracle(scene)
-    w, h = 320, 200
+    w, h = 640, 400
     for kw in ({"use_panini_projection": 1, "panini_param": 0.7}, {"use_360_camera": 1}, {"use_180_camera": 1}):
         r = _renderer(scene)
         for k, v in kw.items():
             setattr(r, k, v if k == "panini_param" else bool(v))
         ref = orc.render(w, h, DEPTH[scene], **kw)
         img = r.render_host(w, h)
-        ok = np.abs(img - ref).max(axis=-1) <= TOL
-        assert ok.mean() >= 0.999, (kw, ok.mean())
+        # every ray direction goes through sin/cos here, so more pixels sit within an ulp of a grid edge
+        _assert_close_with_edge_protocol(img, ref, scene, w, h, min_ok=0.998, **kw)
         assert not np.array_equal(img, _renderer(scene).render_host(w, h))     # the variant really changes the image
+    w, h = 320, 200
     r = _renderer(scene)
     r.draw_side_by_side = True
     left, right = r.eye_matrices()
@@ -150,6 +158,25 @@ def test_projection_variants_and_side_by_side(torch_cuda):
     r2 = _renderer(scene)
     r2.use_360_camera = True
     assert np.array_equal(_bits(rp.render_host(w, 100)), _bits(r2.render_host(w, 100)))   # black bars: skipped samples
+
+
+def test_external_ray_probe(torch_cuda):
+    """the camera-teleportation probe against the oracle's restatement of frag.glsl:209-257."""
+    for scene, segs in (("portal_in_portal", [([0, 0, -0.5], [0, 0, -1.5]), ([0, 0, 0.5], [0, 0, 0.2]), ([0.1, 0.05, -0.9], [0.12, 0.02, -1.3]),
+                                              ([0.2, 0.1, 0.5], [0.1, 0.0, 1.5]), ([0, 0, -0.5], [0, 0, -5.0])]),
+                        ("monoportal", [([0.0, 0.1, 1.0], [0.0, 0.0, -1.0]), ([1.0, 0.3, 0.2], [-1.0, 0.1, -0.2]), ([3.0, 3.0, 3.0], [3.5, 3.0, 3.0])])):
+        orc = _oracle(scene)
+        r = _renderer(scene)
+        for a, b in segs:
+            pos, hr, eo, cs = r.probe_ray(a, b)
+            rpos, rhr, reo, rcs = orc.probe(a, b)
+            assert (hr, eo, cs) == (rhr, reo, rcs), (scene, a, b)
+            assert np.array_equal(pos.view(np.uint32), rpos.view(np.uint32)), (scene, a, b, pos, rpos)
+    # the probe must not disturb rendering state (teleport_light_u is restored, variants are cached)
+    r = _renderer("portal_in_portal")
+    before = r.render_host(160, 90)
+    r.probe_ray([0, 0, -0.5], [0, 0, -1.5])
+    assert np.array_equal(_bits(r.render_host(160, 90)), _bits(before))
 
 
 def test_uniform_update_and_respecialisation(torch_cuda):
