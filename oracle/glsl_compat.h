@@ -16,7 +16,8 @@
 //     length(v) = sqrt(dot(v,v));
 //   * min/max/clamp/step/sign/mod/fract follow the GLSL ES 3.00 spec text
 //     (section 8.3) literally, including their behaviour on NaN;
-//   * sin cos tan asin acos atan exp2 log2 pow come from the host libm.
+//   * sin cos tan asin acos atan are defined HERE (same sequence of IEEE operations as the kernel);
+//     exp log exp2 log2 pow come from the host libm.
 // PE_REAL selects the arithmetic type: float (the parity reference) or double
 // (used only to flag ill-conditioned pixels).
 #pragma once
@@ -25,6 +26,9 @@
 
 #ifndef PE_REAL
 #define PE_REAL float
+#endif
+#ifndef PE_L
+#define PE_L(x) x##f
 #endif
 
 namespace pe_oracle {
@@ -36,13 +40,83 @@ static inline real pe_fma(real a, real b, real c) { return std::fma(a, b, c); }
 // ------------------------------------------------------------------ scalars
 static inline real radians(real d) { return d * real(0.017453292519943295); }
 static inline real degrees(real r) { return r * real(57.29577951308232); }
-static inline real sin(real x) { return std::sin(x); }
-static inline real cos(real x) { return std::cos(x); }
-static inline real tan(real x) { return std::tan(x); }
-static inline real asin(real x) { return std::asin(x); }
-static inline real acos(real x) { return std::acos(x); }
-static inline real atan(real y, real x) { return std::atan2(y, x); }
-static inline real atan(real x) { return std::atan(x); }
+
+// ---- pinned elementary functions ------------------------------------------
+// GLSL leaves sin/cos/tan/asin/acos/atan to the implementation; libm and libdevice do not agree in
+// the last bit, so both the oracle and the kernel use THESE definitions: Cody-Waite reduction by
+// pi/2 in three parts, Cephes single-precision minimax polynomials, every step a single IEEE
+// operation or an explicit FMA.  Max error vs the exact function: sin/cos 1.5 ulp (|x| < 50),
+// atan 1.4e-7, asin/acos 1.7e-7 (tests/test_oracle.py).
+static inline void pe_sincos_core(real x, real& s, real& c, int& q) {
+    real k = std::rint(x * PE_L(0.636619772367581343));
+    real r = pe_fma(k, PE_L(-1.5707962513), x);
+    r = pe_fma(k, PE_L(-7.5497894159e-08), r);
+    r = pe_fma(k, PE_L(-5.3903029535e-15), r);
+    real z = r * r;
+    real ps = PE_L(-1.9515295891e-4);
+    ps = pe_fma(ps, z, PE_L(8.3321608736e-3));
+    ps = pe_fma(ps, z, PE_L(-1.6666654611e-1));
+    s = pe_fma(ps * z, r, r);
+    real pc = PE_L(2.443315711809948e-5);
+    pc = pe_fma(pc, z, PE_L(-1.388731625493765e-3));
+    pc = pe_fma(pc, z, PE_L(4.166664568298827e-2));
+    c = pe_fma(pc * z, z, pe_fma(z, PE_L(-0.5), PE_L(1.0)));
+    real kq = k - PE_L(4.0) * std::floor(k * PE_L(0.25));
+    q = (kq >= PE_L(0.0) && kq <= PE_L(3.0)) ? int(kq) : 0;
+}
+static inline real sin(real x) {
+    real s, c; int q;
+    pe_sincos_core(x, s, c, q);
+    return q == 0 ? s : (q == 1 ? c : (q == 2 ? -s : -c));
+}
+static inline real cos(real x) {
+    real s, c; int q;
+    pe_sincos_core(x, s, c, q);
+    return q == 0 ? c : (q == 1 ? -s : (q == 2 ? -c : s));
+}
+static inline real tan(real x) {
+    real s, c; int q;
+    pe_sincos_core(x, s, c, q);
+    return (q & 1) ? -c / s : s / c;
+}
+static inline real atan(real x) {
+    real a = std::fabs(x);
+    real y = PE_L(0.0), xr = a;
+    if (a > PE_L(2.414213562373095)) { y = PE_L(1.5707963267948966); xr = PE_L(-1.0) / a; }
+    else if (a > PE_L(0.4142135623730950)) { y = PE_L(0.7853981633974483); xr = (a - PE_L(1.0)) / (a + PE_L(1.0)); }
+    real z = xr * xr;
+    real p = PE_L(8.05374449538e-2);
+    p = pe_fma(p, z, PE_L(-1.38776856032e-1));
+    p = pe_fma(p, z, PE_L(1.99777106478e-1));
+    p = pe_fma(p, z, PE_L(-3.33329491539e-1));
+    real r = y + pe_fma(p * z, xr, xr);
+    return x < PE_L(0.0) ? -r : r;
+}
+static inline real atan(real y, real x) {
+    if (x == PE_L(0.0)) return y > PE_L(0.0) ? PE_L(1.5707963267948966) : (y < PE_L(0.0) ? PE_L(-1.5707963267948966) : PE_L(0.0));
+    real a = atan(y / x);
+    if (x < PE_L(0.0)) a = y < PE_L(0.0) ? a - PE_L(3.14159265358979) : a + PE_L(3.14159265358979);
+    return a;
+}
+static inline real asin(real x) {
+    real a = std::fabs(x);
+    bool flag = a > PE_L(0.5);
+    real z = flag ? PE_L(0.5) * (PE_L(1.0) - a) : a * a;
+    real xr = flag ? std::sqrt(z) : a;
+    real p = PE_L(4.2163199048e-2);
+    p = pe_fma(p, z, PE_L(2.4181311049e-2));
+    p = pe_fma(p, z, PE_L(4.5470025998e-2));
+    p = pe_fma(p, z, PE_L(7.4953002686e-2));
+    p = pe_fma(p, z, PE_L(1.6666752422e-1));
+    real r = pe_fma(p * z, xr, xr);
+    if (flag) r = PE_L(1.5707963267948966) - (r + r);
+    return x < PE_L(0.0) ? -r : r;
+}
+static inline real acos(real x) {
+    if (x < PE_L(-0.5)) return PE_L(3.14159265358979) - PE_L(2.0) * asin(std::sqrt(PE_L(0.5) * (PE_L(1.0) + x)));
+    if (x > PE_L(0.5)) return PE_L(2.0) * asin(std::sqrt(PE_L(0.5) * (PE_L(1.0) - x)));
+    return PE_L(1.5707963267948966) - asin(x);
+}
 static inline real pow(real x, real y) { return std::pow(x, y); }
 static inline real exp(real x) { return std::exp(x); }
 static inline real log(real x) { return std::log(x); }

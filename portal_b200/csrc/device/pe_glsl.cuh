@@ -11,7 +11,8 @@
 //   * dot, matN*vecN, cross, mix : explicit FFMA chains in a fixed order (fmaf);
 //   * inversesqrt(x) = 1/sqrt(x), normalize(v) = v * inversesqrt(dot(v,v)), length = sqrt(dot);
 //   * min/max/clamp/step/sign/mod/fract : GLSL ES 3.00 §8.3 text, literally (NaN behaviour included);
-//   * sin cos tan asin acos atan exp2 log2 pow : CUDA libdevice.
+//   * sin cos tan asin acos atan : defined below, operation for operation as in the oracle (bit-exact);
+//     exp log exp2 log2 pow : CUDA libdevice.
 // All matrices a scene uses live in constant memory (one uniform block, <= 6 KB): every lane of a
 // warp reads the same matrix element at the same time, so each element is a constant-bank operand
 // of the FFMA that consumes it -- no load instruction, no shared-memory staging, no bank conflicts.
@@ -24,13 +25,83 @@ namespace pe {
 // ------------------------------------------------------------------ scalars
 PE_FI float radians(float d) { return d * 0.017453292519943295f; }
 PE_FI float degrees(float r) { return r * 57.29577951308232f; }
-PE_FI float sin(float x) { return ::sinf(x); }
-PE_FI float cos(float x) { return ::cosf(x); }
-PE_FI float tan(float x) { return ::tanf(x); }
-PE_FI float asin(float x) { return ::asinf(x); }
-PE_FI float acos(float x) { return ::acosf(x); }
-PE_FI float atan(float y, float x) { return ::atan2f(y, x); }
-PE_FI float atan(float x) { return ::atanf(x); }
+
+// ---- pinned elementary functions ------------------------------------------
+// GLSL leaves sin/cos/tan/asin/acos/atan to the implementation; libm and libdevice do not agree in
+// the last bit, so both the oracle and the kernel use THESE definitions: Cody-Waite reduction by
+// pi/2 in three parts, Cephes single-precision minimax polynomials, every step a single IEEE
+// operation or an explicit FMA.  Max error vs the exact function: sin/cos 1.5 ulp (|x| < 50),
+// atan 1.4e-7, asin/acos 1.7e-7 (tests/test_oracle.py).
+PE_FI void pe_sincos_core(float x, float& s, float& c, int& q) {
+    float k = ::rintf(x * 0.636619772367581343f);
+    float r = ::fmaf(k, -1.5707962513f, x);
+    r = ::fmaf(k, -7.5497894159e-08f, r);
+    r = ::fmaf(k, -5.3903029535e-15f, r);
+    float z = r * r;
+    float ps = -1.9515295891e-4f;
+    ps = ::fmaf(ps, z, 8.3321608736e-3f);
+    ps = ::fmaf(ps, z, -1.6666654611e-1f);
+    s = ::fmaf(ps * z, r, r);
+    float pc = 2.443315711809948e-5f;
+    pc = ::fmaf(pc, z, -1.388731625493765e-3f);
+    pc = ::fmaf(pc, z, 4.166664568298827e-2f);
+    c = ::fmaf(pc * z, z, ::fmaf(z, -0.5f, 1.0f));
+    float kq = k - 4.0f * ::floorf(k * 0.25f);
+    q = (kq >= 0.0f && kq <= 3.0f) ? int(kq) : 0;
+}
+PE_FI float sin(float x) {
+    float s, c; int q;
+    pe_sincos_core(x, s, c, q);
+    return q == 0 ? s : (q == 1 ? c : (q == 2 ? -s : -c));
+}
+PE_FI float cos(float x) {
+    float s, c; int q;
+    pe_sincos_core(x, s, c, q);
+    return q == 0 ? c : (q == 1 ? -s : (q == 2 ? -c : s));
+}
+PE_FI float tan(float x) {
+    float s, c; int q;
+    pe_sincos_core(x, s, c, q);
+    return (q & 1) ? -c / s : s / c;
+}
+PE_FI float atan(float x) {
+    float a = ::fabsf(x);
+    float y = 0.0f, xr = a;
+    if (a > 2.414213562373095f) { y = 1.5707963267948966f; xr = -1.0f / a; }
+    else if (a > 0.4142135623730950f) { y = 0.7853981633974483f; xr = (a - 1.0f) / (a + 1.0f); }
+    float z = xr * xr;
+    float p = 8.05374449538e-2f;
+    p = ::fmaf(p, z, -1.38776856032e-1f);
+    p = ::fmaf(p, z, 1.99777106478e-1f);
+    p = ::fmaf(p, z, -3.33329491539e-1f);
+    float r = y + ::fmaf(p * z, xr, xr);
+    return x < 0.0f ? -r : r;
+}
+PE_FI float atan(float y, float x) {
+    if (x == 0.0f) return y > 0.0f ? 1.5707963267948966f : (y < 0.0f ? -1.5707963267948966f : 0.0f);
+    float a = atan(y / x);
+    if (x < 0.0f) a = y < 0.0f ? a - 3.14159265358979f : a + 3.14159265358979f;
+    return a;
+}
+PE_FI float asin(float x) {
+    float a = ::fabsf(x);
+    bool flag = a > 0.5f;
+    float z = flag ? 0.5f * (1.0f - a) : a * a;
+    float xr = flag ? ::sqrtf(z) : a;
+    float p = 4.2163199048e-2f;
+    p = ::fmaf(p, z, 2.4181311049e-2f);
+    p = ::fmaf(p, z, 4.5470025998e-2f);
+    p = ::fmaf(p, z, 7.4953002686e-2f);
+    p = ::fmaf(p, z, 1.6666752422e-1f);
+    float r = ::fmaf(p * z, xr, xr);
+    if (flag) r = 1.5707963267948966f - (r + r);
+    return x < 0.0f ? -r : r;
+}
+PE_FI float acos(float x) {
+    if (x < -0.5f) return 3.14159265358979f - 2.0f * asin(::sqrtf(0.5f * (1.0f + x)));
+    if (x > 0.5f) return 2.0f * asin(::sqrtf(0.5f * (1.0f - x)));
+    return 1.5707963267948966f - asin(x);
+}
 PE_FI float pow(float x, float y) { return ::powf(x, y); }
 PE_FI float exp(float x) { return ::expf(x); }
 PE_FI float log(float x) { return ::logf(x); }

@@ -136,6 +136,27 @@ bool cuda_ok(pe_ctx* c, cudaError_t e, const char* what) {
 
 void set_renderer_defaults(pe_ctx* c);
 
+// tan() of the pinned numeric profile (device/pe_glsl.cuh `tan`, same sequence of IEEE operations):
+// used for the one uniform expression hoisted to the host, tan(_view_angle / 2) (frag.glsl:450).
+float pinned_tanf(float x) {
+    float k = std::rint(x * 0.636619772367581343f);
+    float r = std::fmaf(k, -1.5707962513f, x);
+    r = std::fmaf(k, -7.5497894159e-08f, r);
+    r = std::fmaf(k, -5.3903029535e-15f, r);
+    float z = r * r;
+    float ps = -1.9515295891e-4f;
+    ps = std::fmaf(ps, z, 8.3321608736e-3f);
+    ps = std::fmaf(ps, z, -1.6666654611e-1f);
+    float s = std::fmaf(ps * z, r, r);
+    float pc = 2.443315711809948e-5f;
+    pc = std::fmaf(pc, z, -1.388731625493765e-3f);
+    pc = std::fmaf(pc, z, 4.166664568298827e-2f);
+    float c = std::fmaf(pc * z, z, std::fmaf(z, -0.5f, 1.0f));
+    float kq = k - 4.0f * std::floor(k * 0.25f);
+    int q = (kq >= 0.0f && kq <= 3.0f) ? int(kq) : 0;
+    return (q & 1) ? -c / s : s / c;
+}
+
 void ensure_layout(pe_ctx* c) {
     if (c->layout_valid) return;
     c->layout = make_layout(c->scene);
@@ -164,7 +185,7 @@ void set_renderer_defaults(pe_ctx* c) {
     const float view_angle = float(90.0 / 180.0 * M_PI);
     F("_camera_scale", 1.0f);
     F("_view_angle", view_angle);
-    F("_tan_half_view", std::tan(view_angle / 2.0f));
+    F("_tan_half_view", pinned_tanf(view_angle / 2.0f));
     F("_t_start", 10.0f);
     F("_t_end", 210.0f);
     F("_offset_after_material", 0.005f);
@@ -627,8 +648,8 @@ int pe_set_uniform_f32(pe_ctx* c, const char* name, float v) {
     if (it == c->layout.float_slot.end()) return c->fail("unknown float uniform `" + n + "`", 2);
     *fslot(c, it->second) = v;
     if (n == "_view_angle") {
-        // frag.glsl:450 `tan(_view_angle / 2.)` -- a uniform expression, evaluated once here in fp32
-        *fslot(c, c->layout.float_slot["_tan_half_view"]) = std::tan(v / 2.0f);
+        // frag.glsl:450 `tan(_view_angle / 2.)` -- a uniform expression, evaluated once here in fp32 (pinned tan)
+        *fslot(c, c->layout.float_slot["_tan_half_view"]) = pinned_tanf(v / 2.0f);
     }
     return 0;
 }

@@ -13,8 +13,9 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 SCENES = ["basics", "monoportal", "triple_portal", "portal_in_portal", "mobius_monoportal"]
 # depth per BASELINE.json config
 DEPTH = {"basics": 4, "monoportal": 20, "triple_portal": 40, "portal_in_portal": 40, "mobius_monoportal": 64}
-# scenes whose per-pixel path uses no libm transcendental at the saved state -> bit-exact parity expected
-BIT_EXACT = ["basics", "monoportal", "triple_portal", "portal_in_portal"]
+# Oracle and kernel share one pinned numeric profile, transcendentals included: every
+# config scene must agree bit for bit.  (exp/log/pow would be the exception; no config scene calls them.)
+BIT_EXACT = ["basics", "monoportal", "triple_portal", "portal_in_portal", "mobius_monoportal"]
 REFERENCE = "/root/reference"
 
 

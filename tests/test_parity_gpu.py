@@ -2,8 +2,9 @@
 committed golden frames.  Bar (task §3): the path is fp32, the tolerance north_star states is 1e-4 per
 channel on the pre-quantisation value.  Because the oracle and the kernel pin the same numeric profile
 (DESIGN.md §4), scenes whose per-pixel path calls no libm transcendental must agree BIT-EXACTLY;
-`mobius_monoportal` (sin/cos in its Newton solver: CUDA libdevice vs glibc) must have >= 99.9 % of
-pixels within 1e-4 and every mismatch flagged ill-conditioned by the float64 oracle or adjacent to one."""
+(DESIGN.md section 4) -- elementary functions included -- all five config scenes must agree BIT-EXACTLY;
+the 1e-4 / edge-pixel protocol (_assert_close_with_edge_protocol) remains for paths that would call
+libm-only functions (exp/log/pow) and as the fallback criterion SURVEY.md section 8c describes."""
 import os
 
 import numpy as np
@@ -89,6 +90,20 @@ def test_parity_with_oracle(scene, persistent, torch_cuda):
     assert np.all(img[..., 3] == 1.0)
 
 
+def test_orbit_frames_bit_exact(torch_cuda):
+    import math
+    from portal_b200.renderer import camera_scale, orbit_camera_matrix
+    scene = "mobius_monoportal"
+    orc, r = _oracle(scene), _renderer(scene)
+    cam = dict(r.cam)
+    for k in (17, 123, 301):
+        alpha = cam["alpha"] + 2 * math.pi * k / 360
+        r.set_cam(cam["look_at"], alpha, cam["beta"], cam["r"])
+        m = orbit_camera_matrix(cam["look_at"], alpha, cam["beta"], cam["r"])
+        ref = orc.render(256, 144, DEPTH[scene], camera=m, camera_scale=camera_scale(m))
+        assert np.array_equal(_bits(r.render_host(256, 144)), _bits(ref)), k
+
+
 def test_persistent_equals_simple_bitwise(torch_cuda):
     for scene in ("triple_portal", "mobius_monoportal"):
         a = _renderer(scene, persistent=False).render_host(333, 190)   # ragged: not a multiple of the tile
@@ -141,8 +156,7 @@ def test_projection_variants_and_side_by_side(torch_cuda):
             setattr(r, k, v if k == "panini_param" else bool(v))
         ref = orc.render(w, h, DEPTH[scene], **kw)
         img = r.render_host(w, h)
-        # every ray direction goes through sin/cos here, so more pixels sit within an ulp of a grid edge
-        _assert_close_with_edge_protocol(img, ref, scene, w, h, min_ok=0.998, **kw)
+        assert np.array_equal(_bits(img), _bits(ref)), kw       # sin/cos/tan are pinned too -> bit-exact
         assert not np.array_equal(img, _renderer(scene).render_host(w, h))     # the variant really changes the image
     w, h = 320, 200
     r = _renderer(scene)
