@@ -18,6 +18,7 @@ from __future__ import annotations
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import subprocess
 import sys
@@ -145,7 +146,7 @@ def run_reference(args):
         "impl": "reference", "metric": metric_name(args.scene, w, h, depth), "value": round(v, 4), "unit": "Mpixels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(w * h / (v * 1e6) * 1e3, 3),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, saved camera, aa 1"},
+        "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, " + (f"{args.orbit}-frame camera orbit" if args.orbit else "saved camera") + ", aa 1"},
         "cpu_baseline": {"value": round(v, 4), "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 4), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": f"CPU oracle (restatement of the reference's GLSL path; the reference itself has no CPU path); wall {dt:.1f} s",
@@ -184,7 +185,15 @@ def run_ours(args):
         sharder = FrameSharder(r, w, h, rank, world, mode=mode, strip_rows=SR)
         target = sharder.target
 
+    cam0 = dict(r.cam)
+    frame_counter = [0]
+
     def step(i):
+        if args.orbit:
+            # BASELINE config 5: alpha_k = alpha_0 + 2*pi*k/orbit; only `_camera` changes
+            k = frame_counter[0] % args.orbit
+            frame_counter[0] += 1
+            r.set_cam(cam0["look_at"], cam0["alpha"] + 2.0 * math.pi * k / args.orbit, cam0["beta"], cam0["r"])
         if world == 1:
             r.draw_texture(target, outs[i & 1].data_ptr(), 0, sptr)
         else:
@@ -211,14 +220,9 @@ def run_ours(args):
     t_wall0 = time.perf_counter()
     ev[0].record(stream)
     for i in range(args.steps):
-        if world == 1:
-            kev[i][0].record(stream)
-            r.draw_texture(target, outs[i & 1].data_ptr(), 0, sptr)
-            kev[i][1].record(stream)
-        else:
-            kev[i][0].record(stream)
-            step(i)
-            kev[i][1].record(stream)
+        kev[i][0].record(stream)
+        step(i)
+        kev[i][1].record(stream)
     ev[1].record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
@@ -286,7 +290,7 @@ def run_ours(args):
             "metric": metric_name(args.scene, w, h, depth), "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, saved camera, aa 1" + (" (BASELINE.json headline config)" if (args.scene, w, h, depth) == ("portal_in_portal", 3840, 2160, 40) else ""),
+            "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, " + (f"{args.orbit}-frame camera orbit" if args.orbit else "saved camera") + ", aa 1" + (" (BASELINE.json headline config)" if (args.scene, w, h, depth) == ("portal_in_portal", 3840, 2160, 40) else ""),
                        "parallelism": "1 GPU" if world == 1 else (
                            f"{world} GPUs x cyclic {STRIP_ROWS}-row strips + 1 NCCL gather + de-interleave" if mode == "gather" else
                            f"{world} GPUs x cyclic {STRIP_ROWS}-row strips, kernels store into rank 0's frame over NVLink (CUDA IPC), 4-byte all-reduce as frame fence"),
@@ -332,6 +336,7 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--persistent", type=int, default=0)
+    ap.add_argument("--orbit", type=int, default=0, help="camera orbit of this many frames per turn (config 5: 360)")
     ap.add_argument("--mode", default="gather", choices=["gather", "p2p"], help="N > 1: how strips reach rank 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
