@@ -132,6 +132,25 @@ PE_FI SurfaceIntersection plane_intersect(Ray r, const M& plane_inv, vec3 normal
     return result;
 }
 
+// plane_intersect with the uniform half of normalize_normal() done on the host: `unit_normal` is
+// normalize(normal) (library.glsl:57), evaluated once per uniform upload with the same IEEE operations;
+// what is left per ray is the sign flip of library.glsl:58-60.  `flipped` tells the caller which of the
+// two pre-evaluated is_collinear() results applies.
+template <class M>
+PE_FI SurfaceIntersection plane_intersect_pre(Ray r, const M& plane_inv, vec3 unit_normal, bool& flipped) {
+    flipped = dot(unit_normal, vec3(r.d)) > 0.0f;
+    if (flipped) unit_normal *= -1.0f;
+    r = transform(plane_inv, r);
+    float len = length(r.d);
+    r.d = normalize(r.d);
+    SurfaceIntersection result = plane_intersect_normalized(r);
+    if (result.hit) {
+        result.t /= len;
+        result.n = unit_normal;
+    }
+    return result;
+}
+
 PE_FI vec3 color(float r, float g, float b) { return vec3(r * r, g * g, b * b); }  // library.glsl:169-171
 
 PE_FI float color_normal(vec3 normal, vec4 direction) {  // library.glsl:177-181

@@ -213,6 +213,37 @@ void set_renderer_defaults(pe_ctx* c) {
     I("_draw_side_by_side", 0);
 }
 
+// Host evaluation of the per-plane uniform expressions (PlaneRec), in fp32 with exactly the device's
+// operations: get_normal = full FMA chain of M * (0,0,1,0) (library.glsl:104-106), normalize =
+// v * (1 / sqrt(dot)) (pe_glsl.cuh), is_collinear (library.glsl:65-67) for both signs of hit.n.
+void update_derived(pe_ctx* c) {
+    const ConstLayout& L = c->layout;
+    const float* mats = reinterpret_cast<const float*>(c->cblock.data() + L.off_mat);
+    for (size_t q = 0; q < L.planes.size(); q++) {
+        const PlaneRec& p = L.planes[q];
+        float* nf = fslot(c, L.plane_f0 + 3 * int(q));
+        int* bi = islot(c, L.plane_i0 + 2 * int(q));
+        if (p.mat_slot < 0) { nf[0] = nf[1] = nf[2] = 0.0f; bi[0] = bi[1] = 0; continue; }
+        const float* m = mats + 16 * p.mat_slot;
+        float n[3], pass[3], cmp[3], nu[3];
+        for (int i = 0; i < 3; i++) {
+            n[i] = std::fmaf(m[12 + i], 0.0f, std::fmaf(m[8 + i], 1.0f, std::fmaf(m[4 + i], 0.0f, m[i] * 0.0f)));
+            pass[i] = p.pass_sign < 0 ? -n[i] : n[i];
+            cmp[i] = p.cmp_sign < 0 ? -n[i] : n[i];
+        }
+        auto dot3 = [](const float* a, const float* b) { return std::fmaf(a[2], b[2], std::fmaf(a[1], b[1], a[0] * b[0])); };
+        const float inv_len = 1.0f / std::sqrt(dot3(pass, pass));
+        for (int i = 0; i < 3; i++) { nu[i] = pass[i] * inv_len; nf[i] = nu[i]; }
+        const float len_cmp = std::sqrt(dot3(cmp, cmp));
+        for (int sgn = 0; sgn < 2; sgn++) {
+            float a[3];
+            for (int i = 0; i < 3; i++) a[i] = sgn ? nu[i] * -1.0f : nu[i];
+            const float v = std::fabs(dot3(a, cmp) / (std::sqrt(dot3(a, a)) * len_cmp) - 1.0f);
+            bi[sgn] = v < 0.01f ? 1 : 0;
+        }
+    }
+}
+
 std::vector<int> current_ints(pe_ctx* c) {
     const int n = c->layout.n_int + kNumRendererInts;
     std::vector<int> v(n);
@@ -583,6 +614,7 @@ int pe_set_option(pe_ctx* c, const char* key, int value) {
     else if (k == "lineinfo") c->lineinfo = value != 0;
     else if (k == "unroll_loops") c->opts.unroll_loops = value != 0;
     else if (k == "specialize_matrices") c->opts.specialize_matrices = value != 0;
+    else if (k == "hoist_planes") c->opts.hoist_planes = value != 0;
     else return c->fail("unknown option `" + k + "`");
     // options change the generated program
     if (c->has_gpu) {
@@ -703,6 +735,7 @@ int pe_render(pe_ctx* c, const pe_target* t, void* out_device, void* bounces_dev
     *fslot(c, c->layout.float_slot["_resolution_x"]) = float(t->width);
     *fslot(c, c->layout.float_slot["_resolution_y"]) = float(t->height);
     if (!select_variant(c)) return 1;
+    update_derived(c);
     Variant* v = c->current;
     const DriverApi* d = c->drv;
     CUstream_t s = stream ? (CUstream_t)stream : (CUstream_t)c->stream;
@@ -758,6 +791,7 @@ int pe_probe_ray(pe_ctx* c, const float a[3], const float b[3], float pos_out[3]
     const bool had_probe = c->opts.with_probe;
     c->opts.with_probe = true;
     bool ok = select_variant(c);
+    if (ok) update_derived(c);
     struct { float ax, ay, az, bx, by, bz; void* out; } P;
     float host[6] = {0, 0, 0, 0, 0, 0};
     if (ok) {

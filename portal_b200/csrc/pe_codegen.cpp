@@ -50,10 +50,23 @@ ConstLayout make_layout(const SceneDesc& scene) {
     for (int k = 0; k < kNumRendererFloats; k++) L.float_slot[kRendererFloats[k]] = L.n_float + k;
     for (int k = 0; k < kNumRendererInts; k++) L.int_slot[kRendererInts[k]] = L.n_int + k;
     for (int k = 0; k < L.n_tex; k++) L.tex_slot[scene.textures[k]] = k;
+    // planes of Flat objects, in generator order
+    for (const Object& o : scene.objects) {
+        if (o.cls != ObjClass::Flat) continue;
+        auto a = L.mat_slot.find(o.matrix_a + "_mat");
+        auto b = L.mat_slot.find(o.matrix_b + "_mat");
+        if (!o.portal) L.planes.push_back({a == L.mat_slot.end() ? -1 : a->second, +1, -1});
+        else {
+            L.planes.push_back({a == L.mat_slot.end() ? -1 : a->second, -1, -1});
+            L.planes.push_back({b == L.mat_slot.end() ? -1 : b->second, +1, +1});
+        }
+    }
+    L.plane_f0 = L.n_float + kNumRendererFloats;
+    L.plane_i0 = L.n_int + kNumRendererInts;
     L.off_mat = 0;
     L.off_float = size_t(L.n_mat + 4) * 64;
-    L.off_int = L.off_float + size_t(L.n_float + kNumRendererFloats) * 4;
-    size_t end_int = L.off_int + size_t(L.n_int + kNumRendererInts) * 4;
+    L.off_int = L.off_float + size_t(L.plane_f0 + 3 * L.planes.size()) * 4;
+    size_t end_int = L.off_int + size_t(L.plane_i0 + 2 * L.planes.size()) * 4;
     L.off_tex = (end_int + 7) & ~size_t(7);
     L.size = L.off_tex + size_t(L.n_tex > 0 ? L.n_tex : 1) * 16;
     return L;
@@ -379,8 +392,9 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     body.line("PE_FI SceneIntersection scene_intersect(const Ray& r) {");
     body.line("    SceneIntersection i = SceneIntersection{0, intersection_none, false};");
     body.line("    SceneIntersection ihit = i; SurfaceIntersection hit = intersection_none; vec3 normal = vec3(0.0f);");
-    body.line("    float len = 1.0f; Ray transformed_ray = ray_none;");
-    body.line("    (void)ihit; (void)hit; (void)normal; (void)len; (void)transformed_ray;");
+    body.line("    float len = 1.0f; Ray transformed_ray = ray_none; bool flipped = false;");
+    body.line("    (void)ihit; (void)hit; (void)normal; (void)len; (void)transformed_ray; (void)flipped;");
+    int plane_q = 0;
     for (size_t pos = 0; pos < scene.objects.size(); pos++) {
         const Object& o = scene.objects[pos];
         const std::string P = std::to_string(pos);
@@ -397,7 +411,22 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
         const char* guard = o.subspace == PE_SUBSPACE_NORMAL ? "    if (r.in_subspace == false) {"
                           : o.subspace == PE_SUBSPACE_SUBSPACE ? "    if (r.in_subspace == true) {" : "    {";
         body.line(guard);
-        if (o.cls == ObjClass::Flat && !o.portal) {
+        if (o.cls == ObjClass::Flat && opts.hoist_planes) {
+            // Same tests as below with the uniform part of the normal algebra pre-evaluated on the host:
+            // PE_PLANE_N(q) = normalize(+-get_normal(M)), PE_PLANE_BACK(q, flipped) = is_collinear(hit.n, normal).
+            for (int which = 1; which <= (o.portal ? 2 : 1); which++) {
+                const std::string& a = which == 1 ? o.matrix_a : o.matrix_b;
+                const std::string Q = std::to_string(plane_q++);
+                body.line("        hit = plane_intersect_pre(r, " + a + "_mat_inv, PE_PLANE_N(" + Q + "), flipped);");
+                if (!o.portal)
+                    body.line("        if (nearer(i, hit)) { i = process_plane_intersection(i, hit, is_inside_" + P +
+                              "(r.o + r.d * hit.t, hit.u, hit.v, PE_PLANE_BACK(" + Q + ", flipped))); }");
+                else
+                    body.line("        if (nearer(i, hit)) { i = process_portal_intersection(i, hit, is_inside_" + P +
+                              "(r.o + r.d * hit.t, hit.u, hit.v, PE_PLANE_BACK(" + Q + ", flipped), " + b2s(which == 1) +
+                              "), teleport_" + P + "_" + std::to_string(which) + "_M); }");
+            }
+        } else if (o.cls == ObjClass::Flat && !o.portal) {
             const std::string& a = o.matrix_a;
             body.line("        normal = -get_normal(" + a + "_mat);");
             body.line("        hit = plane_intersect(r, " + a + "_mat_inv, get_normal(" + a + "_mat));");
@@ -533,8 +562,8 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     hd << "// Constant uniform block: scene matrices + camera, floats, ints, texture descriptors.\n";
     hd << "struct PeConstBlock {\n";
     hd << "    cmat4 m[" << (L.n_mat + 4) << "];\n";
-    hd << "    float f[" << (L.n_float + kNumRendererFloats) << "];\n";
-    hd << "    int i[" << (L.n_int + kNumRendererInts) << "];\n";
+    hd << "    float f[" << (L.plane_f0 + 3 * L.planes.size()) << "];\n";
+    hd << "    int i[" << (L.plane_i0 + 2 * L.planes.size()) << "];\n";
     hd << "    sampler2D tex[" << (L.n_tex > 0 ? L.n_tex : 1) << "];\n";
     hd << "};\n";
     hd << "static_assert(sizeof(PeConstBlock) == " << L.size << ", \"constant block layout mismatch\");\n";
@@ -586,6 +615,9 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     }
     if (scene.skybox.empty()) hd << "#define PE_NOT_FOUND_COLOR(r) color(0.6f, 0.6f, 0.6f)\n";
     else hd << "#define PE_NOT_FOUND_COLOR(r) pe_skybox_color(r)\n";
+    hd << "#define PE_PLANE_N(q) (pe::vec3(PE_C.f[" << L.plane_f0 << " + 3 * (q)], PE_C.f[" << L.plane_f0
+       << " + 3 * (q) + 1], PE_C.f[" << L.plane_f0 << " + 3 * (q) + 2]))\n";
+    hd << "#define PE_PLANE_BACK(q, flipped) (PE_C.i[" << L.plane_i0 << " + 2 * (q) + ((flipped) ? 1 : 0)] != 0)\n";
     hd << kSrcLibrary << "\n";
     hd << "namespace pe {\n";
     if (!scene.skybox.empty()) {

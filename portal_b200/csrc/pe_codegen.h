@@ -62,12 +62,23 @@ extern const int kNumRendererFloats;
 extern const char* const kRendererInts[];    // after the scene ints in i[]
 extern const int kNumRendererInts;
 
+// A plane test the generator emits for a Flat object (scene.rs:912-948).  Everything about its normal
+// is a uniform expression: the host evaluates it once per upload (pe_api.cpp update_derived) instead of
+// every thread once per bounce.
+struct PlaneRec {
+    int mat_slot = 0;    // slot of `<matrix>_mat`
+    int pass_sign = 1;   // vector handed to plane_intersect: +get_normal(M) (Simple, Portal second) or -get_normal(M) (Portal first)
+    int cmp_sign = 1;    // `normal` that is_collinear compares hit.n with: -n (Simple, Portal first) or +n (Portal second)
+};
+
 // Byte layout of the constant block `PE_C` shared by generator and uploader.
 struct ConstLayout {
     int n_mat = 0, n_float = 0, n_int = 0, n_tex = 0;  // scene-declared counts
     std::vector<std::string> mats, floats, ints;       // declaration order
     std::map<std::string, int> mat_slot, float_slot, int_slot, tex_slot;  // names incl. renderer ones
     size_t off_mat = 0, off_float = 0, off_int = 0, off_tex = 0, size = 0;
+    std::vector<PlaneRec> planes;  // derived uniforms: f[plane_f0 + 3q ..] unit normal, i[plane_i0 + 2q ..] back flags
+    int plane_f0 = 0, plane_i0 = 0;
     int camera_slot = 0;  // m[n_mat] = _camera, then _camera_mul_inv, _camera_left_eye, _camera_right_eye
 };
 ConstLayout make_layout(const SceneDesc& scene);
@@ -80,6 +91,7 @@ struct GenOptions {
     int block_threads = 256;
     int min_blocks = 4;
     bool specialize_matrices = true;  // bake each matrix's exact-0 / exact-1 structure into the program (smat4)
+    bool hoist_planes = true;  // per-plane normal work evaluated on the host (see PlaneRec)
     bool with_probe = false;  // also emit pe_probe_kernel (camera-teleportation probe)
     bool unroll_loops = true;  // false: `#pragma unroll 1` on every loop of the user snippets (smaller code)
 };
