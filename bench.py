@@ -182,7 +182,22 @@ def run_ours(args):
         outs = [torch.empty((h, w, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
         sharder = None
     else:
-        sharder = FrameSharder(r, w, h, rank, world, mode=mode, strip_rows=SR)
+        # default for N > 1: the render kernels store straight into rank 0's frame over NVLink (CUDA IPC).
+        # If the box cannot map peer memory between processes, every rank agrees to use the NCCL gather
+        # instead (both are GPU paths; the mode actually used is reported in `config.parallelism`).
+        sharder, ok = None, 1
+        try:
+            sharder = FrameSharder(r, w, h, rank, world, mode=mode, strip_rows=SR)
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            print(f"[bench] rank {rank}: {mode} set-up failed ({e}); falling back to gather", file=sys.stderr)
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if sharder is not None:
+                sharder.close()
+            mode = "gather"
+            sharder = FrameSharder(r, w, h, rank, world, mode=mode, strip_rows=SR)
         target = sharder.target
 
     cam0 = dict(r.cam)
@@ -337,7 +352,7 @@ def main():
     ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--persistent", type=int, default=0)
     ap.add_argument("--orbit", type=int, default=0, help="camera orbit of this many frames per turn (config 5: 360)")
-    ap.add_argument("--mode", default="gather", choices=["gather", "p2p"], help="N > 1: how strips reach rank 0")
+    ap.add_argument("--mode", default="p2p", choices=["gather", "p2p"], help="N > 1: how strips reach rank 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     w, h, d = WORKLOADS[args.scene]
