@@ -79,6 +79,14 @@ PE_API int ph_render_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, v
 PE_API int ph_render_target(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, const pe_target* target,
                             void* out_device, void* stream);
 
+/* One output frame of the offline `render` loop with motion blur (render_animation,
+ * src/main.rs:1758-1824): sub-frame j of frame `frame_index` (of `frame_count`) is rendered at
+ * t = frame_index/frame_count + j/motion_blur_frames/frame_count * 0.5 (exposure 0.5), formula time =
+ * t * duration_seconds, `_aa_start` = j; the RGBA8 sub-frames are averaged in gamma-2 space
+ * (average_images, src/main.rs:664-722).  Everything stays on the device until the final readback. */
+PE_API int ph_render_motion_blur_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, int frame_index, int frame_count,
+                                       int motion_blur_frames, double duration_seconds, uint8_t* out_host_rgba8);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
         "ph_camera_scale": (C.c_double, [f64p]),
         "ph_render_frame": (i32, [vp, vp, C.POINTER(PhFrameParams), vp, i32]),
         "ph_render_target": (i32, [vp, vp, C.POINTER(PhFrameParams), C.POINTER(PeTarget), vp, vp]),
+        "ph_render_motion_blur_frame": (i32, [vp, vp, C.POINTER(PhFrameParams), i32, i32, i32, C.c_double, vp]),
     })
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -117,6 +117,15 @@ class HostRenderer:
         self.scene._check(self._lib.ph_render_frame(self.scene._s, self._ctx, C.byref(p), out.ctypes.data, int(rgba8)))
         return out
 
+    def render_motion_blur_frame(self, width, height, depth, frame_index, frame_count, motion_blur_frames, duration_seconds,
+                                 aa_count=1) -> np.ndarray:
+        """One frame of the offline `render` loop (main.rs:1758-1824): sub-frames + gamma-2 average, RGBA8."""
+        p = PhFrameParams(width, height, depth, aa_count, 0, 0)
+        out = np.empty((height, width, 4), dtype=np.uint8)
+        self.scene._check(self._lib.ph_render_motion_blur_frame(self.scene._s, self._ctx, C.byref(p), frame_index, frame_count,
+                                                                motion_blur_frames, float(duration_seconds), out.ctypes.data))
+        return out
+
     def close(self):
         if getattr(self, "_ctx", None):
             self._lib.pe_destroy(self._ctx)

@@ -16,16 +16,16 @@ from portal_b200.renderer import SceneRenderer, camera_scale, orbit_camera_matri
 
 
 def _declared():
-    text = open(os.path.join(ROOT, "include", "portal_b200.h")).read()
-    return sorted(set(re.findall(r"PE_API\s+[\w\s\*]+?\b(pe_[a-z0-9_]+)\s*\(", text)))
+    text = open(os.path.join(ROOT, "include", "portal_b200.h")).read() + open(os.path.join(ROOT, "include", "portal_b200_host.h")).read()
+    return sorted(set(re.findall(r"PE_API\s+[\w\s\*]+?\b(p[eh]_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():
     lib = capi.lib()
     declared = _declared()
-    assert len(declared) >= 35
+    assert len(declared) >= 55
     out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
-    exported = set(re.findall(r" T (pe_[a-z0-9_]+)", out))
+    exported = set(re.findall(r" T (p[eh]_[a-z0-9_]+)", out))
     assert set(declared) <= exported, sorted(set(declared) - exported)
     assert exported <= set(declared), f"exported but undeclared: {sorted(exported - set(declared))}"
     for name in declared:
@@ -44,7 +44,7 @@ def test_scene_program_compiles_for_sm_100a(scene, persistent):
     r = SceneRenderer(load_ir(scene), device=-1, persistent=persistent)
     src = r.source()
     assert "pe_render_kernel" in src and "__constant__" in src
-    assert "!FOR_NUMBER!" not in src and "10000" not in src.split("namespace pe {\n#line")[-1][:0] + ""
+    assert "!FOR_NUMBER!" not in src
     cubin = r.cubin()
     assert cubin[:4] == b"\x7fELF" and len(cubin) > 10000
     path = f"/tmp/_pe_test_{scene}_{int(persistent)}.cubin"
@@ -53,7 +53,6 @@ def test_scene_program_compiles_for_sm_100a(scene, persistent):
     assert "pe_render_kernel" in res
     m = re.search(r"REG:(\d+) STACK:(\d+)", res)
     assert m and int(m.group(1)) <= 255
-    assert "sm_100a" in subprocess.run(["cuobjdump", "-elf", path], capture_output=True, text=True).stdout[:4000] or True
     r.close()
 
 

@@ -132,3 +132,23 @@ def test_ron_to_pixels_matches_oracle():
     ref2 = runner.Oracle(ir, "fast").render(320, 180, 12, camera=m, camera_scale=camera_scale(m), aa_count=2)
     img2 = HostRenderer(HostScene.from_file(FIXTURE), device=0).render_frame(320, 180, 12, aa_count=2, camera=cam)
     assert np.array_equal(img2.view(np.uint32), ref2.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_motion_blur_frame_matches_reference_pipeline():
+    """render_animation's inner loop (main.rs:1789-1817): sub-frame times, aa_start = j, RGBA8 readback,
+    average_images -- the oracle side composes it from oracle frames + a numpy restatement of the average."""
+    from oracle import frontend, runner
+    w, h, depth, count, mb, dur, i = 192, 108, 12, 24, 4, 6.0, 5
+    hs = HostScene.from_file(FIXTURE)
+    got = HostRenderer(hs, device=0).render_motion_blur_frame(w, h, depth, i, count, mb, dur)
+    subs = []
+    for j in range(mb):
+        t = (i / count + j / mb / count * 0.5) * dur
+        ir = frontend.scene_ir(frontend.load_scene(FIXTURE), "two_spheres", time=t)
+        f = runner.Oracle(ir, "fast").render(w, h, depth, aa_start=j)
+        subs.append(np.rint(np.clip(f, 0, 1) * 255.0).astype(np.uint8))
+    acc = (np.stack(subs)[..., :3].astype(np.uint32) ** 2).sum(axis=0) // mb
+    want = np.concatenate([(np.sqrt(acc.astype(np.float32)) + np.float32(0.5)).astype(np.uint8), np.full((h, w, 1), 255, np.uint8)], axis=-1)
+    assert np.array_equal(got, want)
+    assert not np.array_equal(subs[0], subs[-1])        # time really moves the scene between sub-frames
