@@ -38,8 +38,27 @@ FRAMES = {
 }
 
 
+# Further reference scenes kept as parity inputs for the GPU tests (beyond the five
+# configs).  Scene IR only (compact JSON); their single texture, where they have one, is the config
+# scenes' scenes/img/monoportal.png, already stored in monoportal.textures.npz.
+EXTRA = ["borromean_rings", "hopf_link", "recursive_space", "mobius", "sphere_intersection", "cone", "recursive_room",
+         "spherical_geometry", "cylinder", "non_linear", "time_portal_spacetime", "matryoshka"]
+
+
+def export_extra():
+    d = os.path.join(ROOT, "tests/golden/scenes_extra")
+    os.makedirs(d, exist_ok=True)
+    for name in EXTRA:
+        ir = frontend.scene_ir(frontend.load_scene(f"{REF}/scenes/{name}.ron"), name)
+        assert all(t["path"] == "scenes/img/monoportal.png" for t in ir["textures"]), name
+        with open(os.path.join(d, f"{name}.scene.json"), "w") as f:
+            json.dump(ir, f, separators=(",", ":"))
+        print(f"extra {name}: {len(ir['objects'])} objects, {len(ir['uniforms'])} uniforms")
+
+
 def main():
     from PIL import Image
+    export_extra()
 
     os.makedirs(os.path.join(ROOT, "tests/golden/scenes"), exist_ok=True)
     os.makedirs(os.path.join(ROOT, "tests/golden/frames"), exist_ok=True)
