@@ -102,13 +102,37 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cores() -> int:
+    """Host threads this process may really use: CPU affinity capped by the cgroup CPU quota (a container
+    can report 128 CPUs and be throttled to a few)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(math.ceil(int(txt[0]) / int(txt[1])))))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, int(math.ceil(q / per))))
+            break
+        except Exception:
+            continue
+    return n
+
+
 # ------------------------------------------------------------------------------ CPU oracle legs
 def cpu_oracle_rate(scene, w, h, depth, budget_s=20.0, threads=0):
     """Mpx/s of the oracle's fast build on a bounded sample: bands of 16 rows spread over the frame."""
     from oracle import runner
     tex = runner.load_texture_npz(os.path.join(SCENE_DIR, f"{scene}.textures.npz"))
     orc = runner.Oracle(load_ir(scene), "fast", textures=tex)
-    cores = threads or (os.cpu_count() or 1)
+    cores = threads or usable_cores()
     n_bands = 4
     t0 = time.perf_counter()
     B = min(64, h)
@@ -133,12 +157,13 @@ def run_reference(args):
         return
     w, h, depth = args.width, args.height, args.depth
     rates = []
-    for _ in range(args.warmup):
-        cpu_oracle_rate(args.scene, w, h, depth, budget_s=1.0)
+    for _ in range(min(args.warmup, 3)):
+        cpu_oracle_rate(args.scene, w, h, depth, budget_s=0.5)
     t0 = time.perf_counter()
     sample = ""
     for _ in range(args.steps):
-        r, cores, sample = cpu_oracle_rate(args.scene, w, h, depth, budget_s=max(2.0, 60.0 / max(args.steps, 1)))
+        # bounded sample per step: the whole arm stays around 1.5 minutes whatever --steps is
+        r, cores, sample = cpu_oracle_rate(args.scene, w, h, depth, budget_s=min(20.0, max(0.25, 90.0 / max(args.steps, 1))))
         rates.append(r)
     dt = time.perf_counter() - t0
     v = sum(rates) / len(rates)
