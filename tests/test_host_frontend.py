@@ -152,3 +152,17 @@ def test_motion_blur_frame_matches_reference_pipeline():
     want = np.concatenate([(np.sqrt(acc.astype(np.float32)) + np.float32(0.5)).astype(np.uint8), np.full((h, w, 1), 255, np.uint8)], axis=-1)
     assert np.array_equal(got, want)
     assert not np.array_equal(subs[0], subs[-1])        # time really moves the scene between sub-frames
+
+
+@pytest.mark.gpu
+def test_render_frame_cli(tmp_path):
+    """The C++ command-line mirror of `portal render-frame` (no Python in the loop)."""
+    import subprocess
+    out = tmp_path / "f.rgba"
+    exe = os.path.join(ROOT, "portal_b200", "portal_b200_render")
+    p = subprocess.run([exe, "render-frame", FIXTURE, "--width", "160", "--height", "90", "--render-depth", "12", "--output", str(out)],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    got = np.frombuffer(out.read_bytes(), dtype=np.uint8).reshape(90, 160, 4)
+    want = HostRenderer(HostScene.from_file(FIXTURE), device=0).render_frame(160, 90, 12, rgba8=True)
+    assert np.array_equal(got, want)
