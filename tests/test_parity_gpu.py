@@ -313,3 +313,31 @@ def test_more_reference_scenes(scene, torch_cuda):
             assert (err <= TOL).mean() >= 0.998, (scene, (err > TOL).sum())
         else:
             assert np.array_equal(_bits(img), _bits(ref)), (scene, persistent, np.abs(img - ref).max())
+
+
+def _empty_ir():
+    base = load_ir("monoportal")
+    ir = dict(base)
+    ir.update(scene="empty", objects=[], materials=[], material_ids={}, intersection_materials=[], library=[], textures=[],
+              uniforms={}, skybox=None)
+    return ir
+
+
+def test_empty_scene_and_degenerate_sizes(torch_cuda):
+    """Edge cases: a scene with no objects (every ray misses -> not_found colour 0.6, frag.glsl:154 +
+    scene.rs:1060), 1x1 and 1xN / Nx1 frames, a frame smaller than one warp tile."""
+    from oracle import runner
+    from portal_b200.renderer import SceneRenderer
+    ir = _empty_ir()
+    orc = runner.Oracle(ir, "fast")
+    for persistent in (False, True):
+        r = SceneRenderer(ir, device=0, persistent=persistent)
+        r.render_depth = 7
+        for w, h in ((1, 1), (1, 37), (53, 1), (5, 3), (64, 36)):
+            img = r.render_host(w, h)
+            assert np.array_equal(_bits(img), _bits(orc.render(w, h, 7))), (w, h)
+            assert np.allclose(img[..., :3], 0.6, atol=1e-6) and np.all(img[..., 3] == 1.0)
+    r = _renderer("triple_portal")
+    o = _oracle("triple_portal")
+    for w, h in ((1, 1), (3, 250), (251, 2)):
+        assert np.array_equal(_bits(r.render_host(w, h)), _bits(o.render(w, h, DEPTH["triple_portal"]))), (w, h)
