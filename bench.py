@@ -59,7 +59,7 @@ def measured_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index):
@@ -75,7 +75,9 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """t0, t1: wall-clock (time.time()) bounds of the timed region; samples outside are used only if
+        the region was too short to contain two samples (nvidia-smi cannot sample faster than ~20 ms)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.05)
@@ -85,21 +87,29 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], None, set()
+        import datetime
+        rows = []
         for line in open(self.path):
             p = [x.strip() for x in line.split(",")]
-            if len(p) < 9:
+            if len(p) < 10:
                 continue
             try:
-                sm.append(float(p[1]))
-                mx = float(p[2])
+                ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(p[2]), float(p[3]), p[6:10]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        window = "timed region"
+        if len(inside) < 2:
+            inside, window = rows, "warm-up + timed region (timed region shorter than the sampling period)"
+        sm = sorted(r[1] for r in inside)
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": inside[0][2] if inside else None,
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def usable_cores() -> int:
@@ -246,18 +256,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                      # nvidia-smi needs ~0.2 s to produce its first sample: start it early
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
     # ---- timed region: K steps, device time, max over ranks
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = r.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
+    t_epoch0 = time.time()
     ev[0].record(stream)
     for i in range(args.steps):
         kev[i][0].record(stream)
@@ -266,7 +277,7 @@ def run_ours(args):
     ev[1].record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_epoch0, time.time()) if rank == 0 else None
     launches = r.launch_count() - l0
     dev_ms = ev[0].elapsed_time(ev[1])
     step_ms = dev_ms      # both modes are stream-ordered end to end: device time between the two events

@@ -204,13 +204,27 @@ class SceneRenderer:
             else:
                 self.set_uniform(name, v)
 
+    def set_uniform_raw_invalidate(self):
+        self._sent_state = None
+
     def set_cam(self, look_at, alpha, beta, r):
         """RotateAroundCam::set_cam (main.rs:320-332) + get_matrix."""
         self.cam = {"look_at": [float(x) for x in look_at], "alpha": float(alpha), "beta": float(beta), "r": float(r)}
         self.camera_matrix = orbit_camera_matrix(look_at, alpha, beta, r)
 
     def set_uniforms(self):
-        """SceneRenderer::set_uniforms (main.rs:1266-1359), the variants this path implements."""
+        """SceneRenderer::set_uniforms (main.rs:1266-1359), the variants this path implements.
+        The reference re-sends all of them every draw; here they are re-sent only when one changed since
+        the last call (the library keeps its own copy of the block), which matters once a frame takes
+        ~0.1 ms per GPU."""
+        state = (tuple(self.camera_matrix), tuple(self.camera_mul_inv), self.camera_in_subspace, self.view_angle, self.render_depth,
+                 self.aa_count, self.aa_start, self.draw_depth_map, self.depth_map_min, self.depth_map_max,
+                 self.offset_after_material, self.gray_t_start, self.gray_t_size, self.angle_color_disable, self.grid_disable,
+                 self.black_border_disable, self.darken_by_distance, self.use_panini_projection, self.panini_param,
+                 self.use_360_camera, self.use_180_camera, self.draw_side_by_side, self.eye_distance)
+        if state == getattr(self, "_sent_state", None):
+            return
+        self._sent_state = state
         s = self.set_uniform
         s("_camera", self.camera_matrix)
         s("_camera_in_subspace", int(self.camera_in_subspace))
