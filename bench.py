@@ -238,7 +238,16 @@ def run_ours(args):
     cam0 = dict(r.cam)
     frame_counter = [0]
 
-    def step(i):
+    def step(i, consumer=None):
+        """One frame.  `consumer` (rank 0) enqueues whatever reads the assembled frame; after it the frame's
+        buffer is released to the other ranks (p2p mode)."""
+        _step_render(i)
+        if consumer is not None:
+            consumer()
+        if sharder is not None:
+            sharder.release(sptr)
+
+    def _step_render(i):
         if args.orbit:
             # BASELINE config 5: alpha_k = alpha_0 + 2*pi*k/orbit (SURVEY.md section 8d); only `_camera` changes
             k = frame_counter[0] % args.orbit
@@ -248,8 +257,6 @@ def run_ours(args):
             r.draw_texture(target, outs[i & 1].data_ptr(), 0, sptr)
         else:
             sharder.render(i, sptr)
-            if mode == "p2p":
-                sharder.fence()               # stream-ordered 4-byte all-reduce: frame complete on rank 0 after it
 
     def barrier():
         if world > 1:
@@ -302,10 +309,11 @@ def run_ours(args):
         if world == 1:
             r.render_host_ptr(w, h, host8.data_ptr(), rgba8=True)
         else:
-            step(i)
-            if rank == 0:
-                r._check(r._lib.pe_quantize_rgba8(r._ctx, sharder.frame_ptr, q8.data_ptr(), w * h, sptr))
-                host8.copy_(q8, non_blocking=True)
+            def consume():
+                if rank == 0:
+                    r._check(r._lib.pe_quantize_rgba8(r._ctx, sharder.frame_ptr, q8.data_ptr(), w * h, sptr))
+                    host8.copy_(q8, non_blocking=True)
+            step(i, consume)
             torch.cuda.synchronize()
     for i in range(2):
         e2e_step(i)
@@ -344,7 +352,7 @@ def run_ours(args):
             "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, " + (f"{args.orbit}-frame camera orbit" if args.orbit else "saved camera") + ", aa 1" + (" (BASELINE.json headline config)" if (args.scene, w, h, depth) == ("portal_in_portal", 3840, 2160, 40) else ""),
                        "parallelism": "1 GPU" if world == 1 else (
                            f"{world} GPUs x cyclic {STRIP_ROWS}-row strips + 1 NCCL gather + de-interleave" if mode == "gather" else
-                           f"{world} GPUs x cyclic {STRIP_ROWS}-row strips, kernels store into rank 0's frame over NVLink (CUDA IPC), 4-byte all-reduce as frame fence"),
+                           f"{world} GPUs x cyclic {STRIP_ROWS}-row strips, kernels store into rank 0's frame over NVLink (CUDA IPC), stream-ordered flag words, no collective"),
                        "scheduler": "persistent warps + per-bounce refill" if args.persistent else "one thread per pixel, 8x4 warp tiles, 256-thread blocks, <= 64 regs",
                        "l2": "each step writes a 132.7 MB frame (> 126 MB L2) into alternating buffers; inputs are a <8 KB constant block"},
             "kernel_ms": round(kernel_ms, 4),

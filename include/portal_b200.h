@@ -153,6 +153,13 @@ PE_API int pe_deinterleave_strips(pe_ctx* ctx, const void* gathered_device, void
 PE_API int pe_device_malloc(pe_ctx* ctx, size_t bytes, void** device_ptr_out);
 PE_API int pe_device_free(pe_ctx* ctx, void* device_ptr);
 PE_API int pe_memcpy_d2h(pe_ctx* ctx, void* host_dst, const void* device_src, size_t bytes, void* stream);
+/* Stream-ordered cross-GPU signalling without a collective: pe_signal_u32 publishes `value` to up to 8
+ * flag words (device pointers, local or peer-mapped) after everything earlier in the stream -- remote
+ * stores of a render kernel included; pe_stream_wait_geq_u32 makes the stream wait until a LOCAL flag
+ * word is >= value (wrap-around safe).  pe_memset_u32 initialises flag words (synchronous). */
+PE_API int pe_signal_u32(pe_ctx* ctx, void* const* device_ptrs, int n, uint32_t value, void* stream);
+PE_API int pe_stream_wait_geq_u32(pe_ctx* ctx, void* local_device_ptr, uint32_t value, void* stream);
+PE_API int pe_memset_u32(pe_ctx* ctx, void* device_ptr, uint32_t value, size_t count, void* stream);
 /* CUDA IPC: let another process's render kernel store its pixels straight into this GPU's
  * frame over NVLink.  handle_out/handle_in are 64-byte cudaIpcMemHandle_t blobs. */
 PE_API int pe_ipc_export(pe_ctx* ctx, void* device_ptr, uint8_t handle_out[64]);

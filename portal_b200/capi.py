@@ -83,6 +83,9 @@ def lib() -> C.CDLL:
         "pe_device_malloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),
         "pe_device_free": (i32, [vp, vp]),
         "pe_memcpy_d2h": (i32, [vp, vp, vp, C.c_size_t, vp]),
+        "pe_signal_u32": (i32, [vp, C.POINTER(vp), i32, C.c_uint32, vp]),
+        "pe_stream_wait_geq_u32": (i32, [vp, vp, C.c_uint32, vp]),
+        "pe_memset_u32": (i32, [vp, vp, C.c_uint32, C.c_size_t, vp]),
         "pe_ipc_export": (i32, [vp, vp, vp]),
         "pe_ipc_open": (i32, [vp, vp, C.POINTER(vp)]),
         "pe_ipc_close": (i32, [vp, vp]),

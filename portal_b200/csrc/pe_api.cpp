@@ -899,6 +899,33 @@ int pe_memcpy_d2h(pe_ctx* c, void* dst, const void* src, size_t bytes, void* str
     return cuda_ok(c, cudaStreamSynchronize(s), "D2H copy") ? 0 : 1;
 }
 
+int pe_signal_u32(pe_ctx* c, void* const* device_ptrs, int n, uint32_t value, void* stream) {
+    if (!c || !device_ptrs) return 1;
+    if (!bind_device(c)) return 1;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    if (!cuda_ok(c, (cudaError_t)launch_signal(device_ptrs, n, value, s), "signal")) return 1;
+    c->launches++;
+    return 0;
+}
+
+int pe_stream_wait_geq_u32(pe_ctx* c, void* local_device_ptr, uint32_t value, void* stream) {
+    if (!c || !local_device_ptr) return 1;
+    if (!bind_device(c)) return 1;
+    CUstream_t s = stream ? (CUstream_t)stream : (CUstream_t)c->stream;
+    CUresult_t r = c->drv->cuStreamWaitValue32(s, (CUdeviceptr_t)local_device_ptr, value, 0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (r != 0) return c->fail("cuStreamWaitValue32: " + driver_error(c->drv, r));
+    return 0;
+}
+
+int pe_memset_u32(pe_ctx* c, void* device_ptr, uint32_t value, size_t count, void* stream) {
+    if (!c || !device_ptr) return 1;
+    if (!bind_device(c)) return 1;
+    CUstream_t s = stream ? (CUstream_t)stream : (CUstream_t)c->stream;
+    CUresult_t r = c->drv->cuMemsetD32Async((CUdeviceptr_t)device_ptr, value, count, s);
+    if (r != 0) return c->fail("cuMemsetD32Async: " + driver_error(c->drv, r));
+    return cuda_ok(c, cudaStreamSynchronize((cudaStream_t)s), "memset") ? 0 : 1;
+}
+
 int pe_ipc_export(pe_ctx* c, void* p, uint8_t handle_out[64]) {
     if (!c || !p || !handle_out) return 1;
     if (!bind_device(c)) return 1;

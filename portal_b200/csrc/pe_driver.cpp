@@ -32,6 +32,7 @@ const DriverApi* driver_api(std::string& why) {
                   bind(h, "cuLaunchKernel", g_api.cuLaunchKernel) &&
                   bind(h, "cuMemcpyHtoDAsync_v2", g_api.cuMemcpyHtoDAsync) &&
                   bind(h, "cuMemsetD32Async", g_api.cuMemsetD32Async) &&
+                  bind(h, "cuStreamWaitValue32_v2", g_api.cuStreamWaitValue32) &&
                   bind(h, "cuGetErrorString", g_api.cuGetErrorString) &&
                   bind(h, "cuFuncGetAttribute", g_api.cuFuncGetAttribute) &&
                   bind(h, "cuOccupancyMaxActiveBlocksPerMultiprocessor", g_api.cuOccupancyMaxActiveBlocksPerMultiprocessor);

@@ -23,6 +23,7 @@ struct DriverApi {
                                  CUstream_t, void**, void**) = nullptr;
     CUresult_t (*cuMemcpyHtoDAsync)(CUdeviceptr_t, const void*, size_t, CUstream_t) = nullptr;
     CUresult_t (*cuMemsetD32Async)(CUdeviceptr_t, unsigned, size_t, CUstream_t) = nullptr;
+    CUresult_t (*cuStreamWaitValue32)(CUstream_t, CUdeviceptr_t, unsigned, unsigned) = nullptr;
     CUresult_t (*cuGetErrorString)(CUresult_t, const char**) = nullptr;
     CUresult_t (*cuFuncGetAttribute)(int*, int, CUfunction_t) = nullptr;
     CUresult_t (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction_t, int, size_t) = nullptr;

@@ -72,6 +72,19 @@ __global__ void __launch_bounds__(256) pe_k_average_rgba8(FramePtrs frames, int 
     }
 }
 
+// Cross-GPU signal: after everything earlier in the stream (the render kernel's remote stores
+// included) one thread publishes `value` to up to 8 flag words, which may live in peer memory.
+struct SignalPtrs {
+    unsigned int* p[8];
+};
+__global__ void pe_k_signal(SignalPtrs ptrs, int n, unsigned int value) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        __threadfence_system();
+        for (int i = 0; i < n; i++) *((volatile unsigned int*)ptrs.p[i]) = value;
+        __threadfence_system();
+    }
+}
+
 int grid_for(size_t n, int sms) {
     size_t blocks = (n + 255) / 256;
     size_t cap = size_t(sms) * 8;  // 8 x 256-thread blocks per SM = full occupancy
@@ -94,6 +107,14 @@ int launch_deinterleave(const void* gathered, void* frame, int width, int height
     size_t n = size_t(width) * size_t(height);
     pe_k_deinterleave<<<grid_for(n, sms), 256, 0, s>>>((const float4*)gathered, (float4*)frame, width, height, strip_rows,
                                                      n_ranks, strips_per_rank);
+    return (int)cudaGetLastError();
+}
+
+int launch_signal(void* const* ptrs, int n, unsigned int value, cudaStream_t s) {
+    if (n < 1 || n > 8) return (int)cudaErrorInvalidValue;
+    SignalPtrs sp;
+    for (int i = 0; i < n; i++) sp.p[i] = (unsigned int*)ptrs[i];
+    pe_k_signal<<<1, 32, 0, s>>>(sp, n, value);
     return (int)cudaGetLastError();
 }
 

@@ -76,7 +76,19 @@ def deinterleave_numpy(gathered: np.ndarray, height: int, world: int, strip_rows
 
 
 class FrameSharder:
-    """Per-rank state of a sharded render (CUDA only)."""
+    """Per-rank state of a sharded render (CUDA only).
+
+    mode "gather": compact strips -> one NCCL gather -> pe_deinterleave_strips on rank 0.
+    mode "p2p":    no collective at all.  Rank 0 owns two frame buffers; every rank maps them (CUDA IPC) and its
+                   render kernel stores straight into frame f's buffer (f & 1).  Completion and buffer
+                   recycling are stream-ordered flag words, each one LOCAL to the rank that waits on it:
+                     arrived[r] on rank 0  <- rank r publishes f after its kernel (pe_signal_u32, peer store)
+                     consumed  on rank r   <- rank 0 publishes f once its consumer of frame f is enqueued
+                   rank 0's stream waits arrived[r] >= f for all r (cuStreamWaitValue32); rank r's stream waits
+                   consumed >= f - 2 before it overwrites a buffer.  Nothing synchronises with the host.
+    """
+
+    ARRIVED, CONSUMED = 0, 32  # word offsets in a rank's 256-byte signal block
 
     def __init__(self, renderer, width: int, height: int, rank: int, world: int, mode: str = "gather", strip_rows: int = STRIP_ROWS):
         import torch
@@ -85,8 +97,10 @@ class FrameSharder:
         self.r, self.w, self.h, self.rank, self.world, self.mode, self.s = renderer, width, height, rank, world, mode, strip_rows
         self.spr = strips_per_rank(height, world, strip_rows)
         lib, ctx = renderer._lib, renderer._ctx
-        self.frame_ptr = None      # rank 0: final frame (device pointer)
-        self._peer_ptr = None
+        self.frame_ptr = None      # rank 0: the most recently completed frame (device pointer)
+        self._opened = []
+        self._owned = []
+        self.frame_no = 0
         if mode == "gather":
             self.target = make_target(width, height, rank, world, strip_rows, full_frame=False)
             self.local = [torch.zeros((self.spr, strip_rows, width, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
@@ -94,64 +108,93 @@ class FrameSharder:
                 self.gathered = torch.empty((world, self.spr, strip_rows, width, 4), dtype=torch.float32, device="cuda")
                 self.frame = torch.empty((height, width, 4), dtype=torch.float32, device="cuda")
                 self.frame_ptr = self.frame.data_ptr()
+            return
+        if world > 8:
+            raise ValueError("p2p mode supports up to 8 ranks (one NVSwitch box)")
+        self.target = make_target(width, height, rank, world, strip_rows, full_frame=True)
+        self.frame_bytes = width * height * 16
+
+        def dmalloc(nbytes):
+            p = C.c_void_p()
+            renderer._check(lib.pe_device_malloc(ctx, nbytes, C.byref(p)))
+            self._owned.append(p.value)
+            return p.value
+
+        def export(ptr):
+            hb = (C.c_uint8 * 64)()
+            renderer._check(lib.pe_ipc_export(ctx, ptr, hb))
+            return list(hb)
+
+        def open_(handle):
+            hb = (C.c_uint8 * 64)(*handle)
+            p = C.c_void_p()
+            renderer._check(lib.pe_ipc_open(ctx, hb, C.byref(p)))
+            self._opened.append(p.value)
+            return p.value
+
+        self.sig = dmalloc(256)
+        renderer._check(lib.pe_memset_u32(ctx, self.sig, 0, 64, None))
+        mine = torch.zeros(128, dtype=torch.uint8)
+        mine[64:] = torch.tensor(export(self.sig), dtype=torch.uint8)
+        if rank == 0:
+            self.frames = dmalloc(2 * self.frame_bytes)
+            mine[:64] = torch.tensor(export(self.frames), dtype=torch.uint8)
+        allh = [torch.zeros(128, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine.cuda())
+        allh = [t.cpu().tolist() for t in allh]
+        if rank == 0:
+            self.peer_sig = [None] + [open_(allh[k][64:]) for k in range(1, world)]
         else:
-            self.target = make_target(width, height, rank, world, strip_rows, full_frame=True)
-            handle = torch.zeros(64, dtype=torch.uint8)
-            if rank == 0:
-                p = C.c_void_p()
-                renderer._check(lib.pe_device_malloc(ctx, width * height * 16, C.byref(p)))
-                self.frame_ptr = p.value
-                hb = (C.c_uint8 * 64)()
-                renderer._check(lib.pe_ipc_export(ctx, p, hb))
-                handle = torch.tensor(list(hb), dtype=torch.uint8)
-            if world > 1:
-                h = handle.cuda()
-                dist.broadcast(h, src=0)
-                handle = h.cpu()
-            if rank == 0:
-                self.dst_ptr = self.frame_ptr
-            else:
-                hb = (C.c_uint8 * 64)(*handle.tolist())
-                p = C.c_void_p()
-                renderer._check(lib.pe_ipc_open(ctx, hb, C.byref(p)))
-                self._peer_ptr = p.value
-                self.dst_ptr = p.value
+            self.frames = open_(allh[0][:64])
+            self.sig0 = open_(allh[0][64:])
+        dist.barrier()
 
     def render(self, i: int, stream_ptr: int):
-        """Render this rank's strips of frame i and assemble on rank 0 (asynchronous on the stream,
-        except for the end-of-frame barrier in p2p mode which the caller issues)."""
+        """Render this rank's strips of the next frame; on rank 0 the stream is, after this call, ordered behind
+        the arrival of every rank's strips (self.frame_ptr = the assembled frame).  Fully asynchronous."""
         import torch.distributed as dist
         r = self.r
+        lib, ctx = r._lib, r._ctx
         if self.mode == "gather":
             out = self.local[i & 1]
             r.draw_texture(self.target, out.data_ptr(), 0, stream_ptr)
             if self.world > 1:
                 dist.gather(out, list(self.gathered.unbind(0)) if self.rank == 0 else None, dst=0)
                 if self.rank == 0:
-                    r._check(r._lib.pe_deinterleave_strips(r._ctx, self.gathered.data_ptr(), self.frame_ptr, self.w, self.h,
-                                                           self.s, self.world, self.spr, stream_ptr))
+                    r._check(lib.pe_deinterleave_strips(ctx, self.gathered.data_ptr(), self.frame_ptr, self.w, self.h,
+                                                        self.s, self.world, self.spr, stream_ptr))
             elif self.rank == 0:
-                r._check(r._lib.pe_deinterleave_strips(r._ctx, out.data_ptr(), self.frame_ptr, self.w, self.h, self.s, 1,
-                                                       self.spr, stream_ptr))
+                r._check(lib.pe_deinterleave_strips(ctx, out.data_ptr(), self.frame_ptr, self.w, self.h, self.s, 1,
+                                                    self.spr, stream_ptr))
+            return
+        self.frame_no += 1
+        f = self.frame_no
+        dst = self.frames + (f & 1) * self.frame_bytes
+        if self.rank != 0 and f > 2:
+            r._check(lib.pe_stream_wait_geq_u32(ctx, self.sig + 4 * self.CONSUMED, f - 2, stream_ptr))
+        r.draw_texture(self.target, dst, 0, stream_ptr)
+        if self.rank != 0:
+            ptrs = (C.c_void_p * 1)(self.sig0 + 4 * (self.ARRIVED + self.rank))
+            r._check(lib.pe_signal_u32(ctx, ptrs, 1, f, stream_ptr))
         else:
-            r.draw_texture(self.target, self.dst_ptr, 0, stream_ptr)
+            for k in range(1, self.world):
+                r._check(lib.pe_stream_wait_geq_u32(ctx, self.sig + 4 * (self.ARRIVED + k), f, stream_ptr))
+            self.frame_ptr = dst
 
-    def fence(self):
-        """End-of-frame fence for p2p mode, stream-ordered and without a host synchronisation: a 4-byte
-        all-reduce enqueued after the render kernel on every rank.  When it completes on rank 0's
-        stream every rank's kernel -- and with it every remote store into rank 0's frame -- is done."""
-        import torch
-        import torch.distributed as dist
-        if self.world > 1:
-            if not hasattr(self, "_token"):
-                self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
-            dist.all_reduce(self._token)
+    def release(self, stream_ptr: int):
+        """Rank 0: everything that reads the current frame has been enqueued on the stream -> let the other
+        ranks reuse its buffer two frames from now.  No-op elsewhere and in gather mode."""
+        if self.mode != "p2p" or self.rank != 0 or self.world == 1:
+            return
+        r = self.r
+        ptrs = (C.c_void_p * (self.world - 1))(*[p + 4 * self.CONSUMED for p in self.peer_sig[1:]])
+        r._check(r._lib.pe_signal_u32(r._ctx, ptrs, self.world - 1, self.frame_no, stream_ptr))
 
     def close(self):
         lib, ctx = self.r._lib, self.r._ctx
-        if self._peer_ptr:
-            lib.pe_ipc_close(ctx, self._peer_ptr)
-            self._peer_ptr = None
-        if self.mode == "p2p" and self.rank == 0 and self.frame_ptr:
-            lib.pe_device_free(ctx, self.frame_ptr)
-            self.frame_ptr = None
+        for p in self._opened:
+            lib.pe_ipc_close(ctx, p)
+        self._opened = []
+        for p in self._owned:
+            lib.pe_device_free(ctx, p)
+        self._owned = []

@@ -32,12 +32,12 @@ def main():
     ok = True
     for mode in ("gather", "p2p"):
         sh = FrameSharder(r, w, h, rank, world, mode=mode)
-        for i in range(2):
+        for i in range(5 if mode == "p2p" else 2):      # p2p: more frames than buffers, exercises the recycling flags
             sh.render(i, stream.cuda_stream)
-            if mode == "p2p":
-                sh.fence()
             stream.synchronize()
             dist.barrier()
+            if i < 4:
+                sh.release(stream.cuda_stream)
         if rank == 0:
             got = np.empty((h, w, 4), dtype=np.float32)
             r._check(r._lib.pe_memcpy_d2h(r._ctx, got.ctypes.data, sh.frame_ptr, got.nbytes, None))
