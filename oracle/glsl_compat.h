@@ -14,6 +14,8 @@
 //     in a fixed order (what every GPU GLSL compiler emits for them);
 //   * inversesqrt(x) = 1/sqrt(x); normalize(v) = v * inversesqrt(dot(v,v));
 //     length(v) = sqrt(dot(v,v));
+//   * vector / scalar = vector * (1/scalar): one IEEE reciprocal, then multiplies -- what GPU GLSL
+//     compilers emit (scalar/scalar and vector/vector stay IEEE divisions);
 //   * min/max/clamp/step/sign/mod/fract follow the GLSL ES 3.00 spec text
 //     (section 8.3) literally, including their behaviour on NaN;
 //   * sin cos tan asin acos atan are defined HERE (same sequence of IEEE operations as the kernel);
@@ -158,7 +160,7 @@ struct swz2_ref {
     inline swz2_ref& operator*=(const vec2& v);
     inline swz2_ref& operator/=(const vec2& v);
     swz2_ref& operator*=(real s) { a = a * s; b = b * s; return *this; }
-    swz2_ref& operator/=(real s) { a = a / s; b = b / s; return *this; }
+    swz2_ref& operator/=(real s) { real r = real(1) / s; a = a * r; b = b * r; return *this; }
     swz2_ref& operator+=(real s) { a = a + s; b = b + s; return *this; }
     swz2_ref& operator-=(real s) { a = a - s; b = b - s; return *this; }
 };
@@ -170,7 +172,7 @@ struct swz3_ref {
     inline swz3_ref& operator*=(const vec3& v);
     inline swz3_ref& operator/=(const vec3& v);
     swz3_ref& operator*=(real s) { a = a * s; b = b * s; c = c * s; return *this; }
-    swz3_ref& operator/=(real s) { a = a / s; b = b / s; c = c / s; return *this; }
+    swz3_ref& operator/=(real s) { real r = real(1) / s; a = a * r; b = b * r; c = c * r; return *this; }
     swz3_ref& operator+=(real s) { a = a + s; b = b + s; c = c + s; return *this; }
     swz3_ref& operator-=(real s) { a = a - s; b = b - s; c = c - s; return *this; }
 };
@@ -182,7 +184,7 @@ struct swz4_ref {
     inline swz4_ref& operator*=(const vec4& v);
     inline swz4_ref& operator/=(const vec4& v);
     swz4_ref& operator*=(real s) { a = a * s; b = b * s; c = c * s; d = d * s; return *this; }
-    swz4_ref& operator/=(real s) { a = a / s; b = b / s; c = c / s; d = d / s; return *this; }
+    swz4_ref& operator/=(real s) { real r = real(1) / s; a = a * r; b = b * r; c = c * r; d = d * r; return *this; }
     swz4_ref& operator+=(real s) { a = a + s; b = b + s; c = c + s; d = d + s; return *this; }
     swz4_ref& operator-=(real s) { a = a - s; b = b - s; c = c - s; d = d - s; return *this; }
 };
@@ -272,7 +274,7 @@ static inline vec2 operator/(const vec2& a, const vec2& b) { return vec2(a.x / b
 static inline vec2 operator+(const vec2& a, real s) { return vec2(a.x + s, a.y + s); }
 static inline vec2 operator-(const vec2& a, real s) { return vec2(a.x - s, a.y - s); }
 static inline vec2 operator*(const vec2& a, real s) { return vec2(a.x * s, a.y * s); }
-static inline vec2 operator/(const vec2& a, real s) { return vec2(a.x / s, a.y / s); }
+static inline vec2 operator/(const vec2& a, real s) { real r = real(1) / s; return vec2(a.x * r, a.y * r); }
 static inline vec2 operator+(real s, const vec2& a) { return vec2(s + a.x, s + a.y); }
 static inline vec2 operator-(real s, const vec2& a) { return vec2(s - a.x, s - a.y); }
 static inline vec2 operator*(real s, const vec2& a) { return vec2(s * a.x, s * a.y); }
@@ -286,7 +288,7 @@ static inline vec3 operator/(const vec3& a, const vec3& b) { return vec3(a.x / b
 static inline vec3 operator+(const vec3& a, real s) { return vec3(a.x + s, a.y + s, a.z + s); }
 static inline vec3 operator-(const vec3& a, real s) { return vec3(a.x - s, a.y - s, a.z - s); }
 static inline vec3 operator*(const vec3& a, real s) { return vec3(a.x * s, a.y * s, a.z * s); }
-static inline vec3 operator/(const vec3& a, real s) { return vec3(a.x / s, a.y / s, a.z / s); }
+static inline vec3 operator/(const vec3& a, real s) { real r = real(1) / s; return vec3(a.x * r, a.y * r, a.z * r); }
 static inline vec3 operator+(real s, const vec3& a) { return vec3(s + a.x, s + a.y, s + a.z); }
 static inline vec3 operator-(real s, const vec3& a) { return vec3(s - a.x, s - a.y, s - a.z); }
 static inline vec3 operator*(real s, const vec3& a) { return vec3(s * a.x, s * a.y, s * a.z); }
@@ -300,7 +302,7 @@ static inline vec4 operator/(const vec4& a, const vec4& b) { return vec4(a.x / b
 static inline vec4 operator+(const vec4& a, real s) { return vec4(a.x + s, a.y + s, a.z + s, a.w + s); }
 static inline vec4 operator-(const vec4& a, real s) { return vec4(a.x - s, a.y - s, a.z - s, a.w - s); }
 static inline vec4 operator*(const vec4& a, real s) { return vec4(a.x * s, a.y * s, a.z * s, a.w * s); }
-static inline vec4 operator/(const vec4& a, real s) { return vec4(a.x / s, a.y / s, a.z / s, a.w / s); }
+static inline vec4 operator/(const vec4& a, real s) { real r = real(1) / s; return vec4(a.x * r, a.y * r, a.z * r, a.w * r); }
 static inline vec4 operator+(real s, const vec4& a) { return vec4(s + a.x, s + a.y, s + a.z, s + a.w); }
 static inline vec4 operator-(real s, const vec4& a) { return vec4(s - a.x, s - a.y, s - a.z, s - a.w); }
 static inline vec4 operator*(real s, const vec4& a) { return vec4(s * a.x, s * a.y, s * a.z, s * a.w); }

@@ -10,6 +10,7 @@
 //   * + - * / sqrt : IEEE round-to-nearest, never contracted (NVRTC --fmad=false, prec-div/sqrt on);
 //   * dot, matN*vecN, cross, mix : explicit FFMA chains in a fixed order (fmaf);
 //   * inversesqrt(x) = 1/sqrt(x), normalize(v) = v * inversesqrt(dot(v,v)), length = sqrt(dot);
+//   * vector / scalar = vector * (1/scalar) (one IEEE reciprocal); scalar/scalar, vector/vector: IEEE divide;
 //   * min/max/clamp/step/sign/mod/fract : GLSL ES 3.00 §8.3 text, literally (NaN behaviour included);
 //   * sin cos tan asin acos atan : defined below, operation for operation as in the oracle (bit-exact);
 //     exp log exp2 log2 pow : CUDA libdevice.
@@ -144,7 +145,7 @@ struct swz2_ref {
     PE_FI swz2_ref& operator*=(const vec2& v);
     PE_FI swz2_ref& operator/=(const vec2& v);
     PE_FI swz2_ref& operator*=(float s) { a = a * s; b = b * s; return *this; }
-    PE_FI swz2_ref& operator/=(float s) { a = a / s; b = b / s; return *this; }
+    PE_FI swz2_ref& operator/=(float s) { float r = 1.0f / s; a = a * r; b = b * r; return *this; }
     PE_FI swz2_ref& operator+=(float s) { a = a + s; b = b + s; return *this; }
     PE_FI swz2_ref& operator-=(float s) { a = a - s; b = b - s; return *this; }
 };
@@ -156,7 +157,7 @@ struct swz3_ref {
     PE_FI swz3_ref& operator*=(const vec3& v);
     PE_FI swz3_ref& operator/=(const vec3& v);
     PE_FI swz3_ref& operator*=(float s) { a = a * s; b = b * s; c = c * s; return *this; }
-    PE_FI swz3_ref& operator/=(float s) { a = a / s; b = b / s; c = c / s; return *this; }
+    PE_FI swz3_ref& operator/=(float s) { float r = 1.0f / s; a = a * r; b = b * r; c = c * r; return *this; }
     PE_FI swz3_ref& operator+=(float s) { a = a + s; b = b + s; c = c + s; return *this; }
     PE_FI swz3_ref& operator-=(float s) { a = a - s; b = b - s; c = c - s; return *this; }
 };
@@ -168,7 +169,7 @@ struct swz4_ref {
     PE_FI swz4_ref& operator*=(const vec4& v);
     PE_FI swz4_ref& operator/=(const vec4& v);
     PE_FI swz4_ref& operator*=(float s) { a = a * s; b = b * s; c = c * s; d = d * s; return *this; }
-    PE_FI swz4_ref& operator/=(float s) { a = a / s; b = b / s; c = c / s; d = d / s; return *this; }
+    PE_FI swz4_ref& operator/=(float s) { float r = 1.0f / s; a = a * r; b = b * r; c = c * r; d = d * r; return *this; }
     PE_FI swz4_ref& operator+=(float s) { a = a + s; b = b + s; c = c + s; d = d + s; return *this; }
     PE_FI swz4_ref& operator-=(float s) { a = a - s; b = b - s; c = c - s; d = d - s; return *this; }
 };
@@ -266,8 +267,18 @@ PE_FI vec3::vec3(const vec4& v) : x(v.x), y(v.y), z(v.z) {}
 PE_BINOPS(+)
 PE_BINOPS(-)
 PE_BINOPS(*)
-PE_BINOPS(/)
 #undef PE_BINOPS
+// Division: vector / vector and scalar / vector divide per component (IEEE); vector / scalar is
+// vector * (1 / scalar) -- one IEEE reciprocal and N multiplies, as the numeric profile pins it.
+PE_FI vec2 operator/(const vec2& a, const vec2& b) { return vec2(a.x / b.x, a.y / b.y); }
+PE_FI vec3 operator/(const vec3& a, const vec3& b) { return vec3(a.x / b.x, a.y / b.y, a.z / b.z); }
+PE_FI vec4 operator/(const vec4& a, const vec4& b) { return vec4(a.x / b.x, a.y / b.y, a.z / b.z, a.w / b.w); }
+PE_FI vec2 operator/(float s, const vec2& a) { return vec2(s / a.x, s / a.y); }
+PE_FI vec3 operator/(float s, const vec3& a) { return vec3(s / a.x, s / a.y, s / a.z); }
+PE_FI vec4 operator/(float s, const vec4& a) { return vec4(s / a.x, s / a.y, s / a.z, s / a.w); }
+PE_FI vec2 operator/(const vec2& a, float s) { float r = 1.0f / s; return vec2(a.x * r, a.y * r); }
+PE_FI vec3 operator/(const vec3& a, float s) { float r = 1.0f / s; return vec3(a.x * r, a.y * r, a.z * r); }
+PE_FI vec4 operator/(const vec4& a, float s) { float r = 1.0f / s; return vec4(a.x * r, a.y * r, a.z * r, a.w * r); }
 PE_FI vec2 operator-(const vec2& a) { return vec2(-a.x, -a.y); }
 PE_FI vec3 operator-(const vec3& a) { return vec3(-a.x, -a.y, -a.z); }
 PE_FI vec4 operator-(const vec4& a) { return vec4(-a.x, -a.y, -a.z, -a.w); }
