@@ -40,6 +40,12 @@ PE_API int ph_scene_set_time(ph_scene* s, double time, double total_time);
 /* Override the value of a named Bool / Int / Float / Angle / Progress uniform (the editor's sliders). */
 PE_API int ph_scene_set_value(ph_scene* s, const char* uniform_name, double value);
 
+/* Scene::init_stage_by_name for an animation stage (`render-frame --stage`, src/main.rs:2900-2906,
+ * src/gui/scene.rs:1180-1200): the stage's `Changed(..)` elements replace the top-level ones, the rest
+ * returns to the dev-stage values.  ph_scene_stage_name enumerates the names (alphabetical). */
+PE_API int ph_scene_init_stage(ph_scene* s, const char* stage_name);
+PE_API int ph_scene_stage_name(ph_scene* s, int k, const char** name);
+
 /* Evaluate every uniform and matrix (float64) and build the table Scene::set_uniforms uploads.
  * Returns the number of entries, or -1. */
 PE_API int ph_scene_evaluate(ph_scene* s);

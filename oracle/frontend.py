@@ -279,6 +279,51 @@ class Scene:
         ]
         self.library = [(it["name"], it["data"][0][0]) for it in ser["library"][0]]
 
+        # animation stages + dev stage (scene_serialized.rs:1286-1371): inline elements are inserted at load time
+        self.stages = {}
+        for item in ser.get("animation_stages", [[]])[0]:
+            d = item["data"]
+            st = {"uniforms": {}, "matrices": {}}
+            for uname, anim in d.get("uniforms", {}).items():
+                if uname in self.uniform_by_name:
+                    st["uniforms"][uname] = self._stage_anim(anim, self._uniform_ref)
+            for mname, anim in d.get("matrices", {}).items():
+                if mname in self.matrix_by_name:
+                    st["matrices"][mname] = self._stage_anim(anim, self._matrix_ref)
+            self.stages[item["name"]] = st
+        dev = ser.get("dev_stage") or {}
+        self.dev_uniforms = {k: v for k, v in dev.get("uniforms", {}).items() if k in self.uniform_by_name}
+        self.dev_matrices = {k: self._matrix_from_ser(v) for k, v in dev.get("matrices", {}).items() if k in self.matrix_by_name}
+
+    @staticmethod
+    def _stage_anim(anim: Tagged, resolve):
+        """StageAnimSer -> ('dev',) | ('set', id or None)."""
+        if anim.tag in ("ProvidedToUser", "FromDev"):
+            return ("dev",)
+        if anim.tag in ("Changed", "ChangedAndToUser"):
+            return ("set", resolve(anim.value[0]))
+        raise ValueError(anim.tag)
+
+    def init_stage(self, name: str):
+        """Scene::init_stage(CurrentStage::Animation) (scene.rs:1180-1200) via StageChanging::init_stage
+        (animation.rs:171-183): `Changed(Some(x))` copies element x over the target, `FromDev` /
+        `ProvidedToUser` restore the dev-stage value.  (Camera selection is the caller's business.)"""
+        st = self.stages[name]
+        for uname, a in st["uniforms"].items():
+            uid = self.uniform_by_name[uname]
+            if a[0] == "set":
+                if a[1] is not None:
+                    self.uniforms[uid] = self.uniforms[a[1]]
+            elif uname in self.dev_uniforms:
+                self.uniforms[uid] = self.dev_uniforms[uname]
+        for mname, a in st["matrices"].items():
+            mid = self.matrix_by_name[mname]
+            if a[0] == "set":
+                if a[1] is not None:
+                    self.matrices[mid] = self.matrices[a[1]]
+            elif mname in self.dev_matrices:
+                self.matrices[mid] = self.dev_matrices[mname]
+
     # ---------------------------------------------------------------- loading
     def _add_uniform(self, data, name=None) -> int:
         uid = len(self.uniforms)
@@ -694,7 +739,9 @@ def _material_ir(name, m: Tagged):
     raise ValueError(m.tag)
 
 
-def scene_ir(scene: Scene, scene_name: str, time: float = 0.0) -> dict:
+def scene_ir(scene: Scene, scene_name: str, time: float = 0.0, stage: str | None = None) -> dict:
+    if stage is not None:
+        scene.init_stage(stage)
     scene.time = time
     scene.total_time = time
     objects = []

@@ -99,6 +99,8 @@ def lib() -> C.CDLL:
         "ph_scene_last_error": (cp, [vp]),
         "ph_scene_set_time": (i32, [vp, C.c_double, C.c_double]),
         "ph_scene_set_value": (i32, [vp, cp, C.c_double]),
+        "ph_scene_init_stage": (i32, [vp, cp]),
+        "ph_scene_stage_name": (i32, [vp, i32, C.POINTER(cp)]),
         "ph_scene_evaluate": (i32, [vp]),
         "ph_scene_uniform_get": (i32, [vp, i32, C.POINTER(cp), C.POINTER(i32), f64p]),
         "ph_scene_camera": (i32, [vp, f64p, f64p, f64p, f64p, f64p]),

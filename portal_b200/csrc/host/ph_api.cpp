@@ -1,6 +1,7 @@
 // C API of the host front-end (include/portal_b200_host.h).
 #include <cmath>
 #include <cstring>
+#include <iterator>
 #include <string>
 #include <vector>
 
@@ -106,6 +107,20 @@ int ph_scene_set_value(ph_scene* s, const char* name, double value) {
         case ph::Uniform::Float: case ph::Uniform::Angle: case ph::Uniform::Progress: u.f = value; break;
         default: return fail(s, std::string("uniform `") + name + "` is a formula; set its inputs instead");
     }
+    return 0;
+}
+
+int ph_scene_init_stage(ph_scene* s, const char* name) {
+    if (!s || !name) return 1;
+    if (!s->scene.init_stage(name)) return fail(s, s->scene.error);
+    return 0;
+}
+
+int ph_scene_stage_name(ph_scene* s, int k, const char** name) {
+    if (!s || k < 0 || k >= int(s->scene.stages.size()) || !name) return 1;
+    auto it = s->scene.stages.begin();
+    std::advance(it, k);
+    *name = it->first.c_str();
     return 0;
 }
 

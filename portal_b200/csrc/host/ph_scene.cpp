@@ -377,6 +377,49 @@ struct Loader {
         if (const RonValue* libs = storage(root, "library", true))
             for (auto& it : libs->items)
                 if (it->get("name")) sc.library.emplace_back(it->get("name")->s, code_of(it->get("data")));
+
+        // animation stages (scene_serialized.rs:1286-1360): inline elements are inserted now
+        auto stage_anim = [&](const RonValue* v, bool is_matrix) {
+            StageAnim a;
+            if (v && v->kind == RonValue::Tagged && (v->s == "Changed" || v->s == "ChangedAndToUser")) {
+                a.from_dev = false;
+                a.element = is_matrix ? matrix_ref(v->at(0)) : uniform_ref(v->at(0));
+            }
+            return a;
+        };
+        if (const RonValue* sts = storage(root, "animation_stages", false))
+            for (auto& it : sts->items) {
+                const RonValue* n = it->get("name");
+                const RonValue* d = it->get("data");
+                if (!n || !d) continue;
+                Stage st;
+                if (const RonValue* us = d->get("uniforms"))
+                    for (auto& kv : us->map) {
+                        auto f = sc.uniform_by_name.find(kv.first->s);
+                        if (f != sc.uniform_by_name.end()) st.uniforms.emplace_back(f->second, stage_anim(kv.second.get(), false));
+                    }
+                if (const RonValue* ms2 = d->get("matrices"))
+                    for (auto& kv : ms2->map) {
+                        auto f = sc.matrix_by_name.find(kv.first->s);
+                        if (f != sc.matrix_by_name.end()) st.matrices.emplace_back(f->second, stage_anim(kv.second.get(), true));
+                    }
+                sc.stages[n->s] = st;
+            }
+        // dev stage (scene_serialized.rs:1362-1374)
+        if (const RonValue* dev = root.get("dev_stage")) {
+            if (const RonValue* us = dev->get("uniforms"))
+                for (auto& kv : us->map) {
+                    auto f = sc.uniform_by_name.find(kv.first->s);
+                    if (f == sc.uniform_by_name.end()) continue;
+                    int tmp = add_uniform(*kv.second, "");        // parse through the common path, then detach
+                    sc.dev_uniforms[f->second] = sc.uniforms[size_t(tmp)];
+                }
+            if (const RonValue* ms3 = dev->get("matrices"))
+                for (auto& kv : ms3->map) {
+                    auto f = sc.matrix_by_name.find(kv.first->s);
+                    if (f != sc.matrix_by_name.end()) sc.dev_matrices[f->second] = matrix_from(*kv.second);
+                }
+        }
     }
 };
 
@@ -403,6 +446,31 @@ bool Scene::load(const RonValue& root) {
     Loader l(*this);
     l.load(root);
     return l.ok;
+}
+
+bool Scene::init_stage(const std::string& name) {
+    auto it = stages.find(name);
+    if (it == stages.end()) {
+        error = "scene has no stage named `" + name + "`";
+        return false;
+    }
+    for (auto& ua : it->second.uniforms) {
+        if (!ua.second.from_dev) {
+            if (ua.second.element >= 0) uniforms[size_t(ua.first)] = uniforms[size_t(ua.second.element)];  // storage.set_id
+        } else {
+            auto d = dev_uniforms.find(ua.first);
+            if (d != dev_uniforms.end()) uniforms[size_t(ua.first)] = d->second;
+        }
+    }
+    for (auto& ma : it->second.matrices) {
+        if (!ma.second.from_dev) {
+            if (ma.second.element >= 0) matrices[size_t(ma.first)] = matrices[size_t(ma.second.element)];
+        } else {
+            auto d = dev_matrices.find(ma.first);
+            if (d != dev_matrices.end()) matrices[size_t(ma.first)] = d->second;
+        }
+    }
+    return true;
 }
 
 std::string Scene::matrix_uniform_stem(int id) const {

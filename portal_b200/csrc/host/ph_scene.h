@@ -79,6 +79,14 @@ struct TableEntry {
     int i = 0;
 };
 
+struct StageAnim {      // StageAnimSer (scene_serialized.rs:508-513) after name resolution
+    bool from_dev = true;   // FromDev / ProvidedToUser: restore the dev-stage value
+    int element = -1;       // Changed / ChangedAndToUser(Some(x)): copy element x over the target; -1 = None
+};
+struct Stage {
+    std::vector<std::pair<int, StageAnim>> uniforms, matrices;  // (target id, what to do)
+};
+
 struct Scene {
     // saved camera (CamSettings, scene.rs) + per-scene `_offset_after_material`
     double look_at[3] = {0, 0, 0}, alpha = 0, beta = 0, r = 1, offset_after_material = 0.005;
@@ -97,6 +105,11 @@ struct Scene {
     std::vector<std::pair<std::string, std::string>> intersection_materials, library, textures;  // (name, code|path)
     std::string skybox;  // texture name, empty = none
     std::string error;
+    std::map<std::string, Stage> stages;                 // animation stages by name
+    std::map<int, Uniform> dev_uniforms;                 // dev stage: target id -> value
+    std::map<int, Matrix> dev_matrices;
+    // Scene::init_stage(CurrentStage::Animation(id)) (scene.rs:1180-1200, animation.rs:171-183)
+    bool init_stage(const std::string& name);
 
     // deserialize_scene_new_format
     bool load(const RonValue& root);

@@ -46,6 +46,16 @@ class HostScene:
     def set_value(self, name: str, value: float):
         self._check(self._lib.ph_scene_set_value(self._s, b(name), float(value)))
 
+    def init_stage(self, name: str):
+        self._check(self._lib.ph_scene_init_stage(self._s, b(name)))
+
+    def stage_names(self):
+        out, nm, k = [], C.c_char_p(), 0
+        while self._lib.ph_scene_stage_name(self._s, k, C.byref(nm)) == 0:
+            out.append(nm.value.decode())
+            k += 1
+        return out
+
     def uniform_table(self) -> dict:
         """name -> ('mat4', [16 f64]) | ('float', f64) | ('int', int), in upload order."""
         n = self._lib.ph_scene_evaluate(self._s)

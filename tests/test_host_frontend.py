@@ -56,6 +56,44 @@ def test_set_value_and_time_reevaluate():
         hs.set_value("nope", 1.0)
 
 
+def test_animation_stages():
+    """Scene::init_stage for animation stages (scene.rs:1180-1200): C++ host vs the oracle front-end."""
+    from oracle import frontend
+    assert HostScene.from_file(FIXTURE).stage_names() == ["closed", "reset"]
+    for stage in ("closed", "reset"):
+        hs = HostScene.from_file(FIXTURE)
+        hs.init_stage(stage)
+        sc = frontend.load_scene(FIXTURE)
+        ir = frontend.scene_ir(sc, "two_spheres", stage=stage)
+        _assert_same_table(hs.uniform_table(), ir)
+    hs = HostScene.from_file(FIXTURE)
+    base = hs.uniform_table()
+    hs.init_stage("closed")
+    t = hs.uniform_table()
+    assert t["open_u"] == ("int", 0) and t["p_u"] == ("float", 0.75) and t["count_u"] == ("int", 5) and t["spin_u"] == ("float", 0.2)
+    assert t["portal_a_mat"] != base["portal_a_mat"] and t["chosen_mat"] == t["portal_b_mat"]     # If(open) now picks portal_b
+    assert t["ball_mat"] != base["ball_mat"]                                                      # FromDev -> dev-stage matrix
+    hs.init_stage("reset")
+    assert hs.uniform_table()["p_u"] == ("float", 0.4)
+    with pytest.raises(PortalB200Error, match="no stage named"):
+        hs.init_stage("nope")
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (GPU box)")
+def test_every_stage_of_the_config_scenes_matches_oracle_frontend():
+    from oracle import frontend
+    n = 0
+    for scene in SCENES:
+        path = f"{REFERENCE}/scenes/{scene}.ron"
+        for stage in HostScene.from_file(path).stage_names():
+            hs = HostScene.from_file(path)
+            hs.init_stage(stage)
+            ir = frontend.scene_ir(frontend.load_scene(path), scene, stage=stage)
+            _assert_same_table(hs.uniform_table(), ir)
+            n += 1
+    assert n == 44
+
+
 def test_bad_scene_files_are_errors():
     with pytest.raises(PortalB200Error, match="RON parse error"):
         HostScene("(cam: (")
@@ -152,6 +190,19 @@ def test_motion_blur_frame_matches_reference_pipeline():
     want = np.concatenate([(np.sqrt(acc.astype(np.float32)) + np.float32(0.5)).astype(np.uint8), np.full((h, w, 1), 255, np.uint8)], axis=-1)
     assert np.array_equal(got, want)
     assert not np.array_equal(subs[0], subs[-1])        # time really moves the scene between sub-frames
+
+
+@pytest.mark.gpu
+def test_stage_to_pixels():
+    from oracle import frontend, runner
+    hs = HostScene.from_file(FIXTURE)
+    hs.init_stage("closed")
+    img = HostRenderer(hs, device=0).render_frame(320, 180, 12)
+    ir = frontend.scene_ir(frontend.load_scene(FIXTURE), "two_spheres", stage="closed")
+    ref = runner.Oracle(ir, "fast").render(320, 180, 12)
+    assert np.array_equal(img.view(np.uint32), ref.view(np.uint32))
+    base = HostRenderer(HostScene.from_file(FIXTURE), device=0).render_frame(320, 180, 12)
+    assert not np.array_equal(img, base)
 
 
 @pytest.mark.gpu
