@@ -2,7 +2,7 @@
 // (/root/reference/src/main.rs:2736-2760 options, :2876-2946 render_frame), C++ host + C ABI only:
 //
 //   portal_b200_render render-frame <scene.ron> [--width W] [--height H] [--render-depth D] [--aa-count N]
-//                      [--time T] [--device K] [--texture name=file.rgba:WxH ...] [--output out.ppm]
+//                      [--time T] [--stage NAME] [--device K] [--texture name=file.rgba:WxH ...] [--output out.ppm]
 //
 // Output: binary PPM (P6) of the RGBA8 frame the reference would hand to export_png (alpha dropped), or
 // raw RGBA8 with a .rgba extension.  PNG encode/decode is out of scope: textures
@@ -35,6 +35,7 @@ int main(int argc, char** argv) {
     int width = 1920, height = 1080, depth = 100, aa = 1, device = 0;  // defaults of RenderFrameCliOptions, main.rs:2744-2754
     double time = 0.0;
     std::vector<std::string> textures;
+    std::string stage;
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -44,6 +45,7 @@ int main(int argc, char** argv) {
         else if (a == "--aa-count") aa = std::atoi(next());
         else if (a == "--time") time = std::atof(next());
         else if (a == "--device") device = std::atoi(next());
+        else if (a == "--stage") stage = next();
         else if (a == "--output") output = next();
         else if (a == "--texture") textures.push_back(next());
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
@@ -56,6 +58,10 @@ int main(int argc, char** argv) {
     if (!scene) { std::fprintf(stderr, "Failed to parse scene `%s`: %s\n", scene_path.c_str(), err); return 1; }
     pe_ctx* ctx = pe_create(device);
     if (!ctx) { std::fprintf(stderr, "pe_create: %s\n", pe_last_error(nullptr)); return 1; }
+    if (!stage.empty() && ph_scene_init_stage(scene, stage.c_str())) {   // main.rs:2900-2906
+        std::fprintf(stderr, "Scene `%s` has no stage named `%s`\n", scene_path.c_str(), stage.c_str());
+        return 1;
+    }
     ph_scene_set_time(scene, time, time);
     if (ph_scene_build_program(scene, ctx) || ph_scene_upload_uniforms(scene, ctx)) {
         std::fprintf(stderr, "%s\n", ph_scene_last_error(scene));
