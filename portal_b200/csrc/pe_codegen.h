@@ -86,10 +86,11 @@ ConstLayout make_layout(const SceneDesc& scene);
 struct GenOptions {
     bool persistent = false;
     bool specialize_ints = true;
-    // 4 x 256 threads -> <= 64 registers/thread, 32 warps/SM: best of the sweeps (profiles/r01b_sweep*.txt);
-    // the loop is dependent-issue-latency bound, occupancy buys more than the few spills cost
-    int block_threads = 256;
-    int min_blocks = 4;
+    // 2 x 512 threads -> <= 64 registers/thread, 32 warps/SM: best of the sweeps (profiles/r01b_sweep*.txt,
+    // r01f_sweep_blocks.txt); the loop is dependent-issue-latency bound, occupancy buys more than the few
+    // spills cost, and 16x32-pixel block tiles beat 16x16 on the plane-heavy scenes
+    int block_threads = 512;
+    int min_blocks = 2;
     bool specialize_matrices = true;  // bake each matrix's exact-0 / exact-1 structure into the program (smat4)
     bool hoist_planes = true;  // per-plane normal work evaluated on the host (see PlaneRec)
     bool with_probe = false;  // also emit pe_probe_kernel (camera-teleportation probe)
