@@ -191,6 +191,96 @@ def srt_matrix(scale3, rotate3, offset3):
     return mat_from_scale_rotation_translation(scale3, q, offset3)
 
 
+def mat_determinant(m):
+    """glam 0.13.1 Matrix4x4::determinant (2x2 sub-determinants of rows 2,3, expansion along column 0)."""
+    (m00, m01, m02, m03), (m10, m11, m12, m13), (m20, m21, m22, m23), (m30, m31, m32, m33) = m
+    a2323 = m22 * m33 - m23 * m32
+    a1323 = m21 * m33 - m23 * m31
+    a1223 = m21 * m32 - m22 * m31
+    a0323 = m20 * m33 - m23 * m30
+    a0223 = m20 * m32 - m22 * m30
+    a0123 = m20 * m31 - m21 * m30
+    return (m00 * (m11 * a2323 - m12 * a1323 + m13 * a1223)
+            - m01 * (m10 * a2323 - m12 * a0323 + m13 * a0223)
+            + m02 * (m10 * a1323 - m11 * a0323 + m13 * a0123)
+            - m03 * (m10 * a1223 - m11 * a0223 + m12 * a0123))
+
+
+def _rcp(x):
+    if x == 0.0:
+        return math.copysign(math.inf, x)
+    return 1.0 / x
+
+
+def _sqrt(x):
+    return math.sqrt(x) if x >= 0.0 else math.nan
+
+
+def _half_over_sqrt(x):
+    r = _sqrt(x)
+    if r == 0.0:
+        return math.copysign(math.inf, r)
+    return 0.5 / r
+
+
+def quat_from_rotation_axes(xa, ya, za):
+    """glam 0.13.1 Quaternion::from_rotation_axes (the branch-on-largest-component form)."""
+    m00, m01, m02 = xa
+    m10, m11, m12 = ya
+    m20, m21, m22 = za
+    if m22 <= 0.0:
+        dif10 = m11 - m00
+        omm22 = 1.0 - m22
+        if dif10 <= 0.0:
+            four_xsq = omm22 - dif10
+            inv4x = _half_over_sqrt(four_xsq)
+            return (four_xsq * inv4x, (m01 + m10) * inv4x, (m02 + m20) * inv4x, (m12 - m21) * inv4x)
+        four_ysq = omm22 + dif10
+        inv4y = _half_over_sqrt(four_ysq)
+        return ((m01 + m10) * inv4y, four_ysq * inv4y, (m12 + m21) * inv4y, (m20 - m02) * inv4y)
+    sum10 = m11 + m00
+    opm22 = 1.0 + m22
+    if sum10 <= 0.0:
+        four_zsq = opm22 - sum10
+        inv4z = _half_over_sqrt(four_zsq)
+        return ((m02 + m20) * inv4z, (m12 + m21) * inv4z, four_zsq * inv4z, (m01 - m10) * inv4z)
+    four_wsq = opm22 + sum10
+    inv4w = _half_over_sqrt(four_wsq)
+    return ((m12 - m21) * inv4w, (m20 - m02) * inv4w, (m01 - m10) * inv4w, four_wsq * inv4w)
+
+
+def mat_to_scale_rotation_translation(m):
+    """glam 0.13.1 DMat4::to_scale_rotation_translation: scale = column lengths (x signed by det),
+    rotation = quaternion of the de-scaled 3x3, translation = w column."""
+    det = mat_determinant(m)
+    sign = math.nan if det != det else math.copysign(1.0, det)
+    length = lambda c: _sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2] + c[3] * c[3])  # noqa: E731
+    scale = [length(m[0]) * sign, length(m[1]), length(m[2])]
+    inv = [_rcp(x) for x in scale]
+    axes = [[m[i][r] * inv[i] for r in range(3)] for i in range(3)]
+    return scale, quat_from_rotation_axes(*axes), [m[3][0], m[3][1], m[3][2]]
+
+
+def vec_lerp(a, b, s):
+    return [x + ((y - x) * s) for x, y in zip(a, b)]
+
+
+def quat_lerp(a, b, s):
+    """glam 0.13.1 Quaternion::lerp: shortest-arc nlerp."""
+    dot = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3]
+    bias = 1.0 if dot >= 0.0 else -1.0
+    q = [x + (((y * bias) - x) * s) for x, y in zip(a, b)]
+    r = _rcp(_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]))
+    return tuple(x * r for x in q)
+
+
+def mat_lerp(first, second, t):
+    """matrix.rs:614-628: component-wise lerp of (scale, rotation, translation)."""
+    fs, fr, ft = mat_to_scale_rotation_translation(first)
+    ss, sr, st = mat_to_scale_rotation_translation(second)
+    return mat_from_scale_rotation_translation(vec_lerp(fs, ss, t), quat_lerp(fr, sr, t), vec_lerp(ft, st, t))
+
+
 def vec3_normalize(v):
     l = math.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
     r = 1.0 / l if l != 0.0 else math.inf
@@ -607,8 +697,18 @@ class Scene:
                 return None if x is None else mat_inverse(x)
             if k == "Camera":
                 return self.camera_matrix
-            if k in ("Sqrt", "Lerp"):
-                raise NotImplementedError(f"matrix kind {k} is a SURVEY.md §8(f1) 'next' row")
+            if k == "Lerp":
+                t = self._param_get(m[1])
+                if t is None:
+                    return None
+                first, second = g(m[2]), g(m[3])
+                if first is None or second is None:
+                    return None
+                return mat_lerp(first, second, t)
+            if k == "Sqrt":
+                # matrix.rs:606-613 + 909-985: a BFGS minimisation (argmin 0.8 + finitediff) of |X*X - M|^2;
+                # its result depends on that library's line search iterate by iterate -- not restated.
+                raise NotImplementedError("matrix kind Sqrt (iterative argmin BFGS solve) is out of scope")
             raise ValueError(k)
         finally:
             visited.pop()

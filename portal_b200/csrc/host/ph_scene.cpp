@@ -78,14 +78,8 @@ static void quat_mul(const double a[4], const double b[4], double o[4]) {
     o[3] = w0 * w1 - x0 * x1 - y0 * y1 - z0 * z1;
 }
 
-// matrix.rs:537-547: DMat4::from_scale_rotation_translation(scale, Rx * Ry * Rz, offset)
-Mat4 mat_srt(const double scale[3], const double rotate[3], const double offset[3]) {
-    const double qx[4] = {std::sin(rotate[0] * 0.5), 0.0, 0.0, std::cos(rotate[0] * 0.5)};
-    const double qy[4] = {0.0, std::sin(rotate[1] * 0.5), 0.0, std::cos(rotate[1] * 0.5)};
-    const double qz[4] = {0.0, 0.0, std::sin(rotate[2] * 0.5), std::cos(rotate[2] * 0.5)};
-    double qxy[4], q[4];
-    quat_mul(qx, qy, qxy);
-    quat_mul(qxy, qz, q);
+// glam 0.13.1 DMat4::from_scale_rotation_translation
+static Mat4 mat_from_srt_quat(const double scale[3], const double q[4], const double offset[3]) {
     const double x = q[0], y = q[1], z = q[2], w = q[3];
     const double x2 = x + x, y2 = y + y, z2 = z + z;
     const double xx = x * x2, xy = x * y2, xz = x * z2, yy = y * y2, yz = y * z2, zz = z * z2;
@@ -96,6 +90,85 @@ Mat4 mat_srt(const double scale[3], const double rotate[3], const double offset[
     m[8] = (xz + wy) * scale[2]; m[9] = (yz - wx) * scale[2]; m[10] = (1.0 - (xx + yy)) * scale[2]; m[11] = 0.0 * scale[2];
     m[12] = offset[0]; m[13] = offset[1]; m[14] = offset[2]; m[15] = 1.0;
     return m;
+}
+
+// matrix.rs:537-547: DMat4::from_scale_rotation_translation(scale, Rx * Ry * Rz, offset)
+Mat4 mat_srt(const double scale[3], const double rotate[3], const double offset[3]) {
+    const double qx[4] = {std::sin(rotate[0] * 0.5), 0.0, 0.0, std::cos(rotate[0] * 0.5)};
+    const double qy[4] = {0.0, std::sin(rotate[1] * 0.5), 0.0, std::cos(rotate[1] * 0.5)};
+    const double qz[4] = {0.0, 0.0, std::sin(rotate[2] * 0.5), std::cos(rotate[2] * 0.5)};
+    double qxy[4], q[4];
+    quat_mul(qx, qy, qxy);
+    quat_mul(qxy, qz, q);
+    return mat_from_srt_quat(scale, q, offset);
+}
+
+// glam 0.13.1 Matrix4x4::determinant
+static double mat_determinant(const Mat4& m) {
+    const double m00 = m[0], m01 = m[1], m02 = m[2], m03 = m[3];
+    const double m10 = m[4], m11 = m[5], m12 = m[6], m13 = m[7];
+    const double m20 = m[8], m21 = m[9], m22 = m[10], m23 = m[11];
+    const double m30 = m[12], m31 = m[13], m32 = m[14], m33 = m[15];
+    const double a2323 = m22 * m33 - m23 * m32, a1323 = m21 * m33 - m23 * m31, a1223 = m21 * m32 - m22 * m31;
+    const double a0323 = m20 * m33 - m23 * m30, a0223 = m20 * m32 - m22 * m30, a0123 = m20 * m31 - m21 * m30;
+    return m00 * (m11 * a2323 - m12 * a1323 + m13 * a1223) - m01 * (m10 * a2323 - m12 * a0323 + m13 * a0223) +
+           m02 * (m10 * a1323 - m11 * a0323 + m13 * a0123) - m03 * (m10 * a1223 - m11 * a0223 + m12 * a0123);
+}
+
+// glam 0.13.1 Quaternion::from_rotation_axes: branch on the largest component
+static void quat_from_rotation_axes(const double xa[3], const double ya[3], const double za[3], double q[4]) {
+    const double m00 = xa[0], m01 = xa[1], m02 = xa[2], m10 = ya[0], m11 = ya[1], m12 = ya[2], m20 = za[0], m21 = za[1], m22 = za[2];
+    if (m22 <= 0.0) {
+        const double dif10 = m11 - m00, omm22 = 1.0 - m22;
+        if (dif10 <= 0.0) {
+            const double four_xsq = omm22 - dif10, inv4x = 0.5 / std::sqrt(four_xsq);
+            q[0] = four_xsq * inv4x; q[1] = (m01 + m10) * inv4x; q[2] = (m02 + m20) * inv4x; q[3] = (m12 - m21) * inv4x;
+        } else {
+            const double four_ysq = omm22 + dif10, inv4y = 0.5 / std::sqrt(four_ysq);
+            q[0] = (m01 + m10) * inv4y; q[1] = four_ysq * inv4y; q[2] = (m12 + m21) * inv4y; q[3] = (m20 - m02) * inv4y;
+        }
+    } else {
+        const double sum10 = m11 + m00, opm22 = 1.0 + m22;
+        if (sum10 <= 0.0) {
+            const double four_zsq = opm22 - sum10, inv4z = 0.5 / std::sqrt(four_zsq);
+            q[0] = (m02 + m20) * inv4z; q[1] = (m12 + m21) * inv4z; q[2] = four_zsq * inv4z; q[3] = (m01 - m10) * inv4z;
+        } else {
+            const double four_wsq = opm22 + sum10, inv4w = 0.5 / std::sqrt(four_wsq);
+            q[0] = (m12 - m21) * inv4w; q[1] = (m20 - m02) * inv4w; q[2] = (m01 - m10) * inv4w; q[3] = four_wsq * inv4w;
+        }
+    }
+}
+
+// glam 0.13.1 DMat4::to_scale_rotation_translation
+static void mat_to_srt(const Mat4& m, double scale[3], double q[4], double t[3]) {
+    const double det = mat_determinant(m);
+    const double sign = std::isnan(det) ? det : std::copysign(1.0, det);
+    auto length = [&](int c) { return std::sqrt(m[4 * c] * m[4 * c] + m[4 * c + 1] * m[4 * c + 1] + m[4 * c + 2] * m[4 * c + 2] + m[4 * c + 3] * m[4 * c + 3]); };
+    scale[0] = length(0) * sign; scale[1] = length(1); scale[2] = length(2);
+    double ax[3][3];
+    for (int c = 0; c < 3; c++) {
+        const double inv = 1.0 / scale[c];
+        for (int r = 0; r < 3; r++) ax[c][r] = m[4 * c + r] * inv;
+    }
+    quat_from_rotation_axes(ax[0], ax[1], ax[2], q);
+    t[0] = m[12]; t[1] = m[13]; t[2] = m[14];
+}
+
+// matrix.rs:614-628: lerp of (scale, rotation [shortest-arc nlerp], translation)
+Mat4 mat_lerp(const Mat4& first, const Mat4& second, double t) {
+    double fs[3], fq[4], ft[3], ss[3], sq[4], st[3], s[3], q[4], o[3];
+    mat_to_srt(first, fs, fq, ft);
+    mat_to_srt(second, ss, sq, st);
+    for (int i = 0; i < 3; i++) {
+        s[i] = fs[i] + ((ss[i] - fs[i]) * t);
+        o[i] = ft[i] + ((st[i] - ft[i]) * t);
+    }
+    const double dot = fq[0] * sq[0] + fq[1] * sq[1] + fq[2] * sq[2] + fq[3] * sq[3];
+    const double bias = dot >= 0.0 ? 1.0 : -1.0;
+    for (int i = 0; i < 4; i++) q[i] = fq[i] + (((sq[i] * bias) - fq[i]) * t);
+    const double r = 1.0 / std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; i++) q[i] = q[i] * r;
+    return mat_from_srt_quat(s, q, o);
 }
 
 static void v3_normalize(double v[3]) {
@@ -625,9 +698,15 @@ bool Scene::get_matrix(int id, Mat4& out, std::vector<int>& visited) {
         case Matrix::Camera:
             out = camera_matrix_for_formulas;
             break;
+        case Matrix::Lerp: {
+            double t;
+            ok = get_param(m.p[0], t) && get_matrix(m.a, A, visited) && get_matrix(m.b, B, visited);
+            if (ok) out = mat_lerp(A, B, t);
+            break;
+        }
         case Matrix::Sqrt:
-        case Matrix::Lerp:
-            error = "matrix kinds Sqrt / Lerp are not implemented yet (SURVEY.md §8 f1)";
+            // matrix.rs:606-613 / 909-985: an iterative argmin-BFGS solve of X*X = M; not restated
+            error = "matrix kind Sqrt (iterative BFGS solve in the reference) is not supported";
             ok = false;
             break;
     }

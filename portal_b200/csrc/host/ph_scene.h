@@ -26,6 +26,7 @@ Mat4 mat_identity();
 Mat4 mat_mul(const Mat4& a, const Mat4& b);
 Mat4 mat_inverse(const Mat4& m);
 Mat4 mat_srt(const double scale[3], const double rotate[3], const double offset[3]);
+Mat4 mat_lerp(const Mat4& first, const Mat4& second, double t);
 Mat4 orbit_camera_matrix(const double look_at[3], double alpha, double beta, double r);
 double camera_scale(const Mat4& m);
 

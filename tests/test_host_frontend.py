@@ -41,6 +41,7 @@ def test_fixture_scene_table_matches_oracle_frontend():
     # If(open) picks portal_a; Inv is the inverse; Teleport = second * first^-1 * what
     assert t["chosen_mat"] == t["portal_a_mat"] and t["ball_inv_mat"] == t["ball_mat_inv"]
     assert "portal_a_to_portal_b_mat_teleport" in t and "portal_b_to_portal_a_mat_teleport" in t
+    assert "between_mat" in t and "between_q_mat" in t             # Lerp matrices
 
 
 def test_set_value_and_time_reevaluate():
@@ -94,6 +95,44 @@ def test_every_stage_of_the_config_scenes_matches_oracle_frontend():
     assert n == 44
 
 
+LERP_SCENES = ("half_spheres", "portal_in_portal_cone", "teleportation_degrees", "portal_in_portal_plus_ultra")
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (GPU box)")
+def test_lerp_matrix_stages_match_oracle_frontend():
+    """Matrix::Lerp (matrix.rs:614-628) only appears in animation stages of four reference scenes;
+    every stage at three times: C++ host == oracle front-end, value for value."""
+    from oracle import frontend
+    n = 0
+    for scene in LERP_SCENES:
+        path = f"{REFERENCE}/scenes/{scene}.ron"
+        sc = frontend.load_scene(path)
+        hs = HostScene.from_file(path)
+        for stage in hs.stage_names():
+            hs.init_stage(stage)
+            for tm in (0.0, 0.3, 1.0):
+                hs.set_time(tm)
+                _assert_same_table(hs.uniform_table(), frontend.scene_ir(sc, scene, time=tm, stage=stage))
+                n += 1
+    assert n == 22 * 3
+
+
+def test_lerp_matrix_properties():
+    """t=0 / t=1 reproduce the endpoints (to ~1 ulp through the quaternion round trip), mirrored input
+    (negative determinant) keeps its handedness, and the nlerp takes the short arc."""
+    from oracle import frontend as F
+    a = F.srt_matrix([2.0, 2.0, 2.0], [0.3, -0.2, 1.0], [1.0, 2.0, 3.0])
+    b = F.srt_matrix([-1.0, 1.0, 1.0], [0.0, 2.5, 0.1], [0.0, 0.0, -1.0])
+    for m, t in ((a, 0.0), (b, 1.0)):
+        got = F.mat_lerp(a, b, t)
+        assert np.allclose(np.asarray(got), np.asarray(m), atol=1e-14)
+    assert F.mat_determinant(b) < 0 and F.mat_to_scale_rotation_translation(b)[0][0] < 0
+    mid = F.mat_lerp(a, a, 0.5)
+    assert np.allclose(np.asarray(mid), np.asarray(a), atol=1e-14)
+    q = F.quat_lerp((0.0, 0.0, 0.0, 1.0), (0.0, 0.0, 0.0, -1.0), 0.5)     # antipodal -> same rotation
+    assert q == (0.0, 0.0, 0.0, 1.0)
+
+
 def test_bad_scene_files_are_errors():
     with pytest.raises(PortalB200Error, match="RON parse error"):
         HostScene("(cam: (")
@@ -141,7 +180,7 @@ def test_every_reference_scene_loads_and_evaluates():
         try:
             ir = frontend.scene_ir(frontend.load_scene(path), name)
         except NotImplementedError:
-            n_next += 1                                            # Sqrt / Lerp matrices: SURVEY §8 f1
+            n_next += 1                                            # Sqrt matrices (argmin BFGS) are not restated
             continue
         table = hs.uniform_table()
         common = [k for k in table if k in ir["uniforms"]]
