@@ -326,6 +326,27 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_rate = w * h * e2e_steps / float(e2e_s.item()) / 1e6
+    e2e_sync_rate = None
+    if world == 1:
+        # the frame-sequence form of the same call (the offline `render` loop reads one frame after another):
+        # pe_submit_host_rgba8 / pe_wait_host, frame i's D2H overlapping frame i+1's kernel; every frame still
+        # uploads its uniforms and lands, complete, in pinned host memory before the clock stops
+        e2e_sync_rate = e2e_rate
+        ring = [host8, torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()]
+        def pipelined(n):
+            prev = None
+            for i in range(n):
+                r.set_cam(cam["look_at"], cam["alpha"], cam["beta"], cam["r"])
+                tk = r.submit_host_rgba8(w, h, ring[i % 2].data_ptr())
+                if prev is not None:
+                    r.wait_host(prev)            # frame i-1 is in host memory: the consumer may read it now
+                prev = tk
+            r.wait_host(prev)
+        pipelined(3)
+        r.sync()
+        t0 = time.perf_counter()
+        pipelined(e2e_steps)
+        e2e_rate = w * h * e2e_steps / (time.perf_counter() - t0) / 1e6
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -362,10 +383,13 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": round(e2e_rate, 2), "unit": "Mpixels/s", "h2d_bytes_per_step": e2e_h2d_bytes(r),
                     "d2h_bytes_per_step": w * h * 4, "steps": e2e_steps,
-                    "call": "pe_render_host_rgba8 (RGBA8 into pinned host memory)" if world == 1 else
+                    "call": "pe_submit_host_rgba8 / pe_wait_host per frame (RGBA8 into pinned host memory, 2 frames in flight)" if world == 1 else
                             f"pe_render ({mode}) + pe_quantize_rgba8 + D2H on rank 0"},
             "gpu_launches": int(launches),
         }
+        if e2e_sync_rate is not None:
+            line["e2e"]["sync_call_value"] = round(e2e_sync_rate, 2)
+            line["e2e"]["sync_call"] = "pe_render_host_rgba8 (one blocking call per frame)"
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

@@ -131,8 +131,25 @@ PE_API size_t pe_target_pixels(const pe_target* t);
 PE_API int pe_render(pe_ctx* ctx, const pe_target* target, void* out_device, void* bounces_device, void* stream);
 /* Synchronous render into HOST memory, device->host copy included (float RGBA). */
 PE_API int pe_render_host(pe_ctx* ctx, const pe_target* target, float* out_host);
-/* Same, quantised to RGBA8 as the reference's render target + get_texture_data deliver it. */
+/* Asynchronous render into DEVICE memory as RGBA8 (4 B/pixel): the kernel itself applies the
+ * render target's float -> unorm8 conversion (src/main.rs:2939-2943 draws into an RGBA8 target),
+ * bit-identical to pe_render followed by pe_quantize_rgba8. */
+PE_API int pe_render_rgba8(pe_ctx* ctx, const pe_target* target, void* out_device_rgba8, void* stream);
+/* Same, quantised to RGBA8 as the reference's render target + get_texture_data deliver it
+ * (src/main.rs:2945-2947). Synchronous. */
 PE_API int pe_render_host_rgba8(pe_ctx* ctx, const pe_target* target, uint8_t* out_host);
+/* Pipelined form of pe_render_host_rgba8 for frame sequences (the offline `render` loop,
+ * src/main.rs:2925-2968, renders and reads back one frame after another): queue render + device->host
+ * copy of one frame and return at once.  Up to PE_PIPELINE_DEPTH frames are in flight; frame i's copy
+ * overlaps frame i+1's kernel.  Uniforms set between submits apply to later frames only.  `out_host`
+ * should be page-locked (pe_host_malloc) or the copy is not asynchronous; it must stay untouched until
+ * pe_wait_host(ticket) returns. */
+#define PE_PIPELINE_DEPTH 2
+PE_API int pe_submit_host_rgba8(pe_ctx* ctx, const pe_target* target, uint8_t* out_host, uint64_t* ticket);
+PE_API int pe_wait_host(pe_ctx* ctx, uint64_t ticket);
+/* Page-locked host memory for the readback calls. */
+PE_API int pe_host_malloc(pe_ctx* ctx, size_t bytes, void** out);
+PE_API int pe_host_free(pe_ctx* ctx, void* p);
 /* Camera-teleportation probe (replaces teleport_external_ray, src/main.rs:1361-1409 +
  * src/frag.glsl:166-257, 527-547): follow the segment a -> b through the scene's portals (at most
  * 10, `teleport_light_u` forced on) and return where its end point lands -- directly, instead of

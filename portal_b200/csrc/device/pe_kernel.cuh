@@ -237,6 +237,7 @@ struct PeLaunch {
     int strip_rows, strip_first, strip_step, n_strips;
     int out_full_frame;   // 1: out is the whole frame (index by global row); 0: compact local rows
     int tiles_x, tiles_y; // 8x4 tiles over the local row space
+    int out_rgba8;        // 1: out is uchar4 pixels, quantised like an RGBA8 render target (main.rs:2939-2943)
     unsigned int* queue;  // PE_PERSISTENT: global tile counter (zeroed by the host before launch)
 };
 
@@ -249,11 +250,23 @@ PE_FI bool local_to_global_row(const PeLaunch& L, int lrow, int& grow) {
     return grow < L.height;
 }
 
+PE_FI unsigned unorm8(float v) {
+    v = ::fminf(::fmaxf(v, 0.0f), 1.0f);
+    return (unsigned)__float2int_rn(v * 255.0f);
+}
+
 PE_FI void store_pixel(const PeLaunch& L, int px, int lrow, int grow, vec3 sum, int bounces) {
     // frag.glsl:526, :551: sqrt(result / aa_count), alpha 1
     vec3 c = sqrt(sum / float(_aa_count));
     size_t idx = size_t(L.out_full_frame ? grow : lrow) * size_t(L.width) + size_t(px);
-    L.out[idx] = make_float4(c.x, c.y, c.z, 1.0f);
+    if (L.out_rgba8) {
+        // GL float -> unorm8: clamp to [0,1] (NaN -> 0), scale by 255, round to nearest even;
+        // the same arithmetic as pe_k_quantize_rgba8 (pe_kernels.cu), so both routes give the same bytes
+        reinterpret_cast<uchar4*>(L.out)[idx] = make_uchar4((unsigned char)unorm8(c.x), (unsigned char)unorm8(c.y),
+                                                            (unsigned char)unorm8(c.z), 255);
+    } else {
+        L.out[idx] = make_float4(c.x, c.y, c.z, 1.0f);
+    }
     if (L.bounces) L.bounces[idx] = bounces;
 }
 

@@ -263,10 +263,9 @@ int ph_render_motion_blur_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params*
     if (frame_count < 1 || motion_blur_frames < 1 || motion_blur_frames > 64 || frame_index < 0)
         return fail(s, "ph_render_motion_blur_frame: bad frame arguments");
     const size_t n = size_t(p->width) * size_t(p->height);
-    void* frame_f32 = nullptr;
     void* out8 = nullptr;
     std::vector<void*> sub(size_t(motion_blur_frames), nullptr);
-    int rc = pe_device_malloc(ctx, n * 16, &frame_f32) | pe_device_malloc(ctx, n * 4, &out8);
+    int rc = pe_device_malloc(ctx, n * 4, &out8);
     for (auto& b : sub) rc |= pe_device_malloc(ctx, n * 4, &b);
     const double saved_time = s->scene.time, saved_total = s->scene.total_time;
     if (!rc) {
@@ -279,7 +278,7 @@ int ph_render_motion_blur_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params*
             q.aa_start = j;                                            // main.rs:1797
             ph_scene_set_time(s, tt * duration_seconds, tt * duration_seconds);   // Scene::update, Dev/Animation stage branch
             rc = ph_scene_upload_uniforms(s, ctx) || upload_renderer_uniforms(s, ctx, &q) ||
-                 pe_render(ctx, &t, frame_f32, nullptr, nullptr) || pe_quantize_rgba8(ctx, frame_f32, sub[size_t(j)], n, nullptr);
+                 pe_render_rgba8(ctx, &t, sub[size_t(j)], nullptr);   // RGBA8 render target, quantised by the kernel
         }
         if (!rc) rc = pe_average_frames_rgba8(ctx, sub.data(), motion_blur_frames, out8, n, nullptr) ||
                       pe_memcpy_d2h(ctx, out_host, out8, n * 4, nullptr);
@@ -289,7 +288,6 @@ int ph_render_motion_blur_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params*
     }
     ph_scene_set_time(s, saved_time, saved_total);
     pe_sync(ctx);
-    if (frame_f32) pe_device_free(ctx, frame_f32);
     if (out8) pe_device_free(ctx, out8);
     for (auto& b : sub) if (b) pe_device_free(ctx, b);
     return rc ? 1 : 0;

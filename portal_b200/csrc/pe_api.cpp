@@ -38,7 +38,7 @@ struct PeLaunchHost {  // must match `PeLaunch` in device/pe_kernel.cuh
     int32_t strip_rows, strip_first, strip_step, n_strips;
     int32_t out_full_frame;
     int32_t tiles_x, tiles_y;
-    int32_t _pad;
+    int32_t out_rgba8;
     void* queue;
 };
 static_assert(sizeof(PeLaunchHost) == 64, "PeLaunch layout");
@@ -116,6 +116,11 @@ struct pe_ctx {
     void* scratch_dev = nullptr;  // pe_render_host* staging
     size_t scratch_bytes = 0;
     void* scratch8_dev = nullptr;
+    // pe_submit_host_rgba8 pipeline
+    struct Slot { void* dev = nullptr; size_t bytes = 0; cudaEvent_t rendered = nullptr, copied = nullptr; uint64_t ticket = 0; };
+    Slot slots[PE_PIPELINE_DEPTH];
+    cudaStream_t copy_stream = nullptr;
+    uint64_t next_ticket = 0;
     size_t scratch8_bytes = 0;
     uint64_t launches = 0;
     const DriverApi* drv = nullptr;
@@ -457,6 +462,12 @@ void pe_destroy(pe_ctx* c) {
             if (kv.second.dev) cudaFree(kv.second.dev);
         if (c->scratch_dev) cudaFree(c->scratch_dev);
         if (c->scratch8_dev) cudaFree(c->scratch8_dev);
+        for (auto& sl : c->slots) {
+            if (sl.dev) cudaFree(sl.dev);
+            if (sl.rendered) cudaEventDestroy(sl.rendered);
+            if (sl.copied) cudaEventDestroy(sl.copied);
+        }
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         if (c->queue_dev) cudaFree(c->queue_dev);
         if (c->stream) cudaStreamDestroy(c->stream);
     }
@@ -727,7 +738,7 @@ size_t pe_target_pixels(const pe_target* t) {
     return size_t(t->n_strips) * size_t(t->strip_rows) * size_t(t->width);
 }
 
-int pe_render(pe_ctx* c, const pe_target* t, void* out_device, void* bounces_device, void* stream) {
+static int render_impl(pe_ctx* c, const pe_target* t, void* out_device, void* bounces_device, void* stream, bool rgba8) {
     if (!c) return 1;
     if (!out_device) return c->fail("pe_render: out_device is null");
     if (!check_target(c, t) || !bind_device(c)) return 1;
@@ -757,6 +768,7 @@ int pe_render(pe_ctx* c, const pe_target* t, void* out_device, void* bounces_dev
     const int local_rows = t->n_strips * t->strip_rows;
     L.tiles_x = (t->width + 7) / 8;
     L.tiles_y = (local_rows + 3) / 4;
+    L.out_rgba8 = rgba8 ? 1 : 0;
     L.queue = c->queue_dev;
     void* args[] = {&L};
     unsigned gx, gy;
@@ -774,6 +786,14 @@ int pe_render(pe_ctx* c, const pe_target* t, void* out_device, void* bounces_dev
     if (r != 0) return c->fail("cuLaunchKernel(pe_render_kernel): " + driver_error(d, r));
     c->launches++;
     return 0;
+}
+
+int pe_render(pe_ctx* c, const pe_target* t, void* out_device, void* bounces_device, void* stream) {
+    return render_impl(c, t, out_device, bounces_device, stream, false);
+}
+
+int pe_render_rgba8(pe_ctx* c, const pe_target* t, void* out_device_rgba8, void* stream) {
+    return render_impl(c, t, out_device_rgba8, nullptr, stream, true);
 }
 
 static bool ensure_scratch(pe_ctx* c, void** p, size_t* have, size_t need);
@@ -848,13 +868,71 @@ int pe_render_host_rgba8(pe_ctx* c, const pe_target* t, uint8_t* out_host) {
     if (!out_host) return c->fail("pe_render_host_rgba8: out_host is null");
     if (!check_target(c, t) || !bind_device(c)) return 1;
     size_t n = pe_target_pixels(t);
-    if (!ensure_scratch(c, &c->scratch_dev, &c->scratch_bytes, n * 16)) return 1;
     if (!ensure_scratch(c, &c->scratch8_dev, &c->scratch8_bytes, n * 4)) return 1;
-    if (pe_render(c, t, c->scratch_dev, nullptr, nullptr)) return 1;
-    if (!cuda_ok(c, (cudaError_t)launch_quantize_rgba8(c->scratch_dev, c->scratch8_dev, n, c->sm_count, c->stream), "quantize")) return 1;
-    c->launches++;
+    if (render_impl(c, t, c->scratch8_dev, nullptr, nullptr, true)) return 1;
     if (!cuda_ok(c, cudaMemcpyAsync(out_host, c->scratch8_dev, n * 4, cudaMemcpyDeviceToHost, c->stream), "D2H copy")) return 1;
     return cuda_ok(c, cudaStreamSynchronize(c->stream), "pe_render_host_rgba8") ? 0 : 1;
+}
+
+// ---- pipelined readback: frame i's D2H copy (copy stream) overlaps frame i+1's kernel (render stream) ----
+static bool ensure_pipeline(pe_ctx* c, size_t bytes) {
+    if (!c->copy_stream) {
+        if (!cuda_ok(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "copy stream")) return false;
+        for (auto& sl : c->slots) {
+            if (!cuda_ok(c, cudaEventCreateWithFlags(&sl.rendered, cudaEventDisableTiming), "event") ||
+                !cuda_ok(c, cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming), "event")) return false;
+        }
+    }
+    for (auto& sl : c->slots)
+        if (!ensure_scratch(c, &sl.dev, &sl.bytes, bytes)) return false;
+    return true;
+}
+
+int pe_submit_host_rgba8(pe_ctx* c, const pe_target* t, uint8_t* out_host, uint64_t* ticket) {
+    if (!c) return 1;
+    if (!out_host || !ticket) return c->fail("pe_submit_host_rgba8: null argument");
+    if (!check_target(c, t) || !bind_device(c)) return 1;
+    const size_t n = pe_target_pixels(t);
+    // growing a slot buffer frees the old one: only legal when nothing is in flight
+    for (auto& sl : c->slots)
+        if (sl.bytes < n * 4 && sl.ticket) {
+            if (!cuda_ok(c, cudaEventSynchronize(sl.copied), "pipeline drain")) return 1;
+        }
+    if (!ensure_pipeline(c, n * 4)) return 1;
+    const uint64_t tk = ++c->next_ticket;
+    auto& sl = c->slots[tk % PE_PIPELINE_DEPTH];
+    // the slot's previous frame (ticket tk - depth) must have left the device before it is overwritten
+    if (sl.ticket && !cuda_ok(c, cudaStreamWaitEvent(c->stream, sl.copied, 0), "pipeline wait")) return 1;
+    if (render_impl(c, t, sl.dev, nullptr, nullptr, true)) return 1;
+    if (!cuda_ok(c, cudaEventRecord(sl.rendered, c->stream), "event record") ||
+        !cuda_ok(c, cudaStreamWaitEvent(c->copy_stream, sl.rendered, 0), "pipeline wait") ||
+        !cuda_ok(c, cudaMemcpyAsync(out_host, sl.dev, n * 4, cudaMemcpyDeviceToHost, c->copy_stream), "D2H copy") ||
+        !cuda_ok(c, cudaEventRecord(sl.copied, c->copy_stream), "event record")) return 1;
+    sl.ticket = tk;
+    *ticket = tk;
+    return 0;
+}
+
+int pe_wait_host(pe_ctx* c, uint64_t ticket) {
+    if (!c) return 1;
+    if (ticket == 0 || ticket > c->next_ticket) return c->fail("pe_wait_host: unknown ticket");
+    if (!bind_device(c)) return 1;
+    auto& sl = c->slots[ticket % PE_PIPELINE_DEPTH];
+    // a newer frame in the same slot was queued behind this one on both streams: waiting for it covers the older ticket
+    if (sl.ticket < ticket) return c->fail("pe_wait_host: ticket was never submitted");
+    return cuda_ok(c, cudaEventSynchronize(sl.copied), "pe_wait_host") ? 0 : 1;
+}
+
+int pe_host_malloc(pe_ctx* c, size_t bytes, void** out) {
+    if (!c || !out || bytes == 0) return 1;
+    if (!bind_device(c)) return 1;
+    return cuda_ok(c, cudaHostAlloc(out, bytes, cudaHostAllocDefault), "cudaHostAlloc") ? 0 : 1;
+}
+
+int pe_host_free(pe_ctx* c, void* p) {
+    if (!c || !p) return 1;
+    if (!bind_device(c)) return 1;
+    return cuda_ok(c, cudaFreeHost(p), "cudaFreeHost") ? 0 : 1;
 }
 
 int pe_sync(pe_ctx* c) {

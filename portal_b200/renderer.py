@@ -310,6 +310,31 @@ class SceneRenderer:
         fn = self._lib.pe_render_host_rgba8 if rgba8 else self._lib.pe_render_host
         self._check(fn(self._ctx, C.byref(t), host_ptr))
 
+    def draw_texture_rgba8(self, target: PeTarget, out_ptr: int, stream: int = 0):
+        """draw_texture into an RGBA8 device buffer: the kernel quantises like the reference's render target."""
+        self.set_uniforms()
+        self._check(self._lib.pe_render_rgba8(self._ctx, C.byref(target), out_ptr, stream or None))
+
+    def submit_host_rgba8(self, width: int, height: int, host_ptr: int) -> int:
+        """Queue one frame (render + D2H into pinned `host_ptr`) and return its ticket; at most
+        PE_PIPELINE_DEPTH frames are in flight, frame i's copy overlaps frame i+1's kernel."""
+        self.set_uniforms()
+        t = self.full_target(width, height)
+        ticket = C.c_uint64()
+        self._check(self._lib.pe_submit_host_rgba8(self._ctx, C.byref(t), host_ptr, C.byref(ticket)))
+        return ticket.value
+
+    def wait_host(self, ticket: int):
+        self._check(self._lib.pe_wait_host(self._ctx, ticket))
+
+    def host_malloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.pe_host_malloc(self._ctx, nbytes, C.byref(p)))
+        return p.value
+
+    def host_free(self, ptr: int):
+        self._check(self._lib.pe_host_free(self._ctx, ptr))
+
     def render_host_rgba8(self, width: int, height: int) -> np.ndarray:
         out = np.empty((height, width, 4), dtype=np.uint8)
         self.render_host_ptr(width, height, out.ctypes.data, rgba8=True)
