@@ -94,7 +94,8 @@ PE_API int pe_scene_cubin(pe_ctx* ctx, const void** data, size_t* size);
 /* Options: "persistent" (0/1, default 0), "specialize_ints" (0/1, default 1), "specialize_matrices"
  * (0/1, default 1: the exact-0 / exact-1 structure of every uploaded matrix is baked in), "block_threads",
  * "min_blocks", "hoist_planes" (0/1, default 1: per-plane normal algebra evaluated once per upload on the
- * host), "lineinfo" (0/1, default 1), "unroll_loops" (0/1, default 1; 0 keeps the loops of
+ * host), "lazy_planes" (0/1, default 1: a plane test stops as soon as its result is certain to be
+ * rejected, same pixels), "lineinfo" (0/1, default 1), "unroll_loops" (0/1, default 1; 0 keeps the loops of
  * user snippets rolled).  Set before pe_scene_compile. */
 PE_API int pe_set_option(pe_ctx* ctx, const char* key, int value);
 

@@ -428,6 +428,11 @@ struct cmat4 {
                     vec4(e[12], e[13], e[14], e[15]));
     }
     PE_FI vec4 operator[](int i) const { return vec4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]); }
+    // one component of operator*(cmat4, vec4), same FFMA chain
+    template <int R>
+    PE_FI float row(const vec4& v) const {
+        return ::fmaf(e[12 + R], v.w, ::fmaf(e[8 + R], v.z, ::fmaf(e[4 + R], v.y, e[R] * v.x)));
+    }
 };
 
 // A uniform-block matrix whose STRUCTURE is a compile-time constant.  When the uniform table is

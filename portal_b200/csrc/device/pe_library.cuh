@@ -151,6 +151,38 @@ PE_FI SurfaceIntersection plane_intersect_pre(Ray r, const M& plane_inv, vec3 un
     return result;
 }
 
+// plane_intersect_pre evaluated lazily, for the one consumer the generated scene_intersect() has:
+//     hit = plane_intersect...;  if (nearer(i, hit)) { ... }           (library.glsl:413-423)
+// Every value that reaches that consumer is computed by the same operations in the same order as
+// plane_intersect_pre; what changes is WHEN, and that work whose result `nearer` is certain to
+// discard is not done:
+//  1. Only row 2 of the transformed origin and direction decides the sign of
+//     t = -o.z / (d.z * inversesqrt(dot(d, d))): the normalising factor is never negative, so a
+//     non-NaN d.z * factor has the sign bit of d.z, and when o.z and d.z have the same sign bit the
+//     quotient is negative, a negative zero, -Inf or NaN -- `t < 0` (no hit) or `t > 0` false
+//     (rejected by nearer) in every case.  Half of all plane tests end here, after 2 dot products.
+//  2. With t known, nearer()'s own test runs before the x / y rows of the origin are transformed
+//     (they only feed u, v).
+// M is a uniform-block matrix (cmat4 / smat4).
+template <class M>
+PE_FI SurfaceIntersection plane_intersect_lazy(const SurfaceIntersection& best, const Ray& r, const M& plane_inv,
+                                               vec3 unit_normal, bool& flipped) {
+    const float oz = plane_inv.template row<2>(r.o);
+    const float dz = plane_inv.template row<2>(r.d);
+    if ((__float_as_int(oz) ^ __float_as_int(dz)) >= 0) return intersection_none;
+    const vec4 d = vec4(plane_inv.template row<0>(r.d), plane_inv.template row<1>(r.d), dz, plane_inv.template row<3>(r.d));
+    const float len = length(d);
+    const vec4 dn = normalize(d);
+    float t = -oz / dn.z;                       // plane_intersect_normalized, library.glsl:139-141
+    if (t < 0.0f) return intersection_none;
+    const float t_world = t / len;              // library.glsl:157
+    if (!((t_world > 0.0f) && (!best.hit || (best.hit && t_world < best.t)))) return intersection_none;
+    const float ox = plane_inv.template row<0>(r.o), oy = plane_inv.template row<1>(r.o);
+    flipped = dot(unit_normal, vec3(r.d)) > 0.0f;
+    if (flipped) unit_normal *= -1.0f;
+    return SurfaceIntersection{true, t_world, ox + dn.x * t, oy + dn.y * t, unit_normal};
+}
+
 PE_FI vec3 color(float r, float g, float b) { return vec3(r * r, g * g, b * b); }  // library.glsl:169-171
 
 PE_FI float color_normal(vec3 normal, vec4 direction) {  // library.glsl:177-181

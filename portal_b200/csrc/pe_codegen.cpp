@@ -417,7 +417,10 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
             for (int which = 1; which <= (o.portal ? 2 : 1); which++) {
                 const std::string& a = which == 1 ? o.matrix_a : o.matrix_b;
                 const std::string Q = std::to_string(plane_q++);
-                body.line("        hit = plane_intersect_pre(r, " + a + "_mat_inv, PE_PLANE_N(" + Q + "), flipped);");
+                if (opts.lazy_planes)
+                    body.line("        hit = plane_intersect_lazy(i.hit, r, " + a + "_mat_inv, PE_PLANE_N(" + Q + "), flipped);");
+                else
+                    body.line("        hit = plane_intersect_pre(r, " + a + "_mat_inv, PE_PLANE_N(" + Q + "), flipped);");
                 if (!o.portal)
                     body.line("        if (nearer(i, hit)) { i = process_plane_intersection(i, hit, is_inside_" + P +
                               "(r.o + r.d * hit.t, hit.u, hit.v, PE_PLANE_BACK(" + Q + ", flipped))); }");

@@ -93,6 +93,7 @@ struct GenOptions {
     int min_blocks = 2;
     bool specialize_matrices = true;  // bake each matrix's exact-0 / exact-1 structure into the program (smat4)
     bool hoist_planes = true;  // per-plane normal work evaluated on the host (see PlaneRec)
+    bool lazy_planes = true;   // with hoist_planes: plane tests stop as soon as nearer() is certain to reject them
     bool with_probe = false;  // also emit pe_probe_kernel (camera-teleportation probe)
     bool unroll_loops = true;  // false: `#pragma unroll 1` on every loop of the user snippets (smaller code)
 };
