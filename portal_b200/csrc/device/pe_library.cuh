@@ -161,7 +161,12 @@ PE_FI SurfaceIntersection plane_intersect_pre(Ray r, const M& plane_inv, vec3 un
 //     non-NaN d.z * factor has the sign bit of d.z, and when o.z and d.z have the same sign bit the
 //     quotient is negative, a negative zero, -Inf or NaN -- `t < 0` (no hit) or `t > 0` false
 //     (rejected by nearer) in every case.  Half of all plane tests end here, after 2 dot products.
-//  2. With t known, nearer()'s own test runs before the x / y rows of the origin are transformed
+//  2. nearer() also needs t < best.t.  In exact arithmetic t = |o.z| / |d.z|; the computed value differs
+//     from that by the roundings of sqrt, 1/sqrt, one product and two quotients -- under 1e-6 relative
+//     while every intermediate is a normal number, which the magnitude guards below ensure.  So when
+//     |o.z| > 1.00001 * best.t * |d.z| the computed t is certain to be >= best.t and the square root and
+//     the three divisions are skipped.  (Outside the guards nothing is assumed: the full path runs.)
+//  3. With t known, nearer()'s own test runs before the x / y rows of the origin are transformed
 //     (they only feed u, v).
 // M is a uniform-block matrix (cmat4 / smat4).
 template <class M>
@@ -171,10 +176,18 @@ PE_FI SurfaceIntersection plane_intersect_lazy(const SurfaceIntersection& best, 
     const float dz = plane_inv.template row<2>(r.d);
     if ((__float_as_int(oz) ^ __float_as_int(dz)) >= 0) return intersection_none;
     const vec4 d = vec4(plane_inv.template row<0>(r.d), plane_inv.template row<1>(r.d), dz, plane_inv.template row<3>(r.d));
-    const float len = length(d);
-    const vec4 dn = normalize(d);
-    float t = -oz / dn.z;                       // plane_intersect_normalized, library.glsl:139-141
-    if (t < 0.0f) return intersection_none;
+    const float q = dot(d, d);
+    if (best.hit) {
+        const float adz = ::fabsf(dz);
+        const bool normal_range = (best.t >= 1e-20f) && (best.t <= 1e20f) && (adz >= 1e-15f) && (adz <= 1e15f) &&
+                                  (q >= 1e-30f) && (q <= 1e30f);
+        if (normal_range && (::fabsf(oz) > best.t * 1.00001f * adz)) return intersection_none;
+    }
+    const float len = sqrt(q);                  // length(d)
+    const vec4 dn = d * inversesqrt(q);         // normalize(d)
+    // plane_intersect_normalized (library.glsl:139-141); its `t < 0` exit cannot fire here: -o.z and dn.z
+    // have the same sign bit (or dn.z is NaN)
+    const float t = -oz / dn.z;
     const float t_world = t / len;              // library.glsl:157
     if (!((t_world > 0.0f) && (!best.hit || (best.hit && t_world < best.t)))) return intersection_none;
     const float ox = plane_inv.template row<0>(r.o), oy = plane_inv.template row<1>(r.o);
