@@ -93,6 +93,39 @@ PE_API int ph_render_target(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, 
 PE_API int ph_render_motion_blur_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, int frame_index, int frame_count,
                                        int motion_blur_frames, double duration_seconds, uint8_t* out_host_rgba8);
 
+/* ---- animations: the animation-facing half of SceneRenderer ------------------------------------------
+ * ph_player mirrors what `render-frame --stage/--animation/--camera/--time` and the offline `render` loop
+ * drive (src/main.rs:2894-2929, 1876-1930, 1757-1830): Scene::init_stage for stages, the dev stage and real
+ * animations (src/gui/scene.rs:1180-1236), Scene::update's time mapping and camera interpolation
+ * (:1353-1496), SceneRenderer::update's camera selection (src/main.rs:1430-1543) and, when a renderer
+ * context is attached, teleport_camera / teleport_matrix (:1217-1264, :1174-1215) on top of pe_probe_ray.
+ * The player keeps a pointer to the scene: free the player first. */
+typedef struct ph_player ph_player;
+PE_API ph_player* ph_player_new(ph_scene* s);
+PE_API void ph_player_free(ph_player* p);
+PE_API const char* ph_player_last_error(ph_player* p);
+/* Route teleport_external_ray through ctx (which must hold the scene's compiled program). Without a
+ * context the camera never teleports: frames whose camera does not cross a portal are unaffected. */
+PE_API int ph_player_attach(ph_player* p, pe_ctx* ctx);
+PE_API int ph_player_init_stage(ph_player* p, const char* stage_name);
+PE_API int ph_player_init_animation(ph_player* p, const char* animation_name);
+PE_API int ph_player_select_camera(ph_player* p, const char* camera_name);
+/* SceneRenderer::update(memory, time): `time_seconds` is wall time; inside a real animation the formula
+ * variable `time` becomes (time % duration) / duration and `total_time` adds the earlier animations. */
+PE_API int ph_player_update(ph_player* p, double time_seconds);
+/* Camera after the last update, float64: `_camera`, `_camera_mul_inv` (column-major), `_camera_in_subspace`,
+ * `_camera_scale`; orbit[6] = look_at xyz, alpha, beta, r; times[2] = formula time, total_time. */
+PE_API int ph_player_camera(ph_player* p, double camera16[16], double camera_mul_inv16[16], int32_t* in_subspace,
+                            double* scale, double orbit[6], double times[2], int64_t* n_probes);
+/* Real animations in file order: count, then name and duration of entry k. */
+PE_API int ph_scene_animation_count(ph_scene* s);
+PE_API int ph_scene_animation(ph_scene* s, int k, const char** name, double* duration);
+PE_API int ph_scene_camera_count(ph_scene* s);
+PE_API int ph_scene_camera_name(ph_scene* s, int k, const char** name);
+/* draw_texture + readback with the player's camera and the scene's current uniforms (width, height, depth,
+ * aa_count, aa_start of `p` are used; its camera fields are ignored). */
+PE_API int ph_player_render_frame(ph_player* pl, pe_ctx* ctx, const ph_frame_params* p, void* out_host, int rgba8);
+
 #ifdef __cplusplus
 }
 #endif

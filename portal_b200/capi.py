@@ -118,6 +118,20 @@ def lib() -> C.CDLL:
         "ph_render_frame": (i32, [vp, vp, C.POINTER(PhFrameParams), vp, i32]),
         "ph_render_target": (i32, [vp, vp, C.POINTER(PhFrameParams), C.POINTER(PeTarget), vp, vp]),
         "ph_render_motion_blur_frame": (i32, [vp, vp, C.POINTER(PhFrameParams), i32, i32, i32, C.c_double, vp]),
+        "ph_player_new": (vp, [vp]),
+        "ph_player_free": (None, [vp]),
+        "ph_player_last_error": (cp, [vp]),
+        "ph_player_attach": (i32, [vp, vp]),
+        "ph_player_init_stage": (i32, [vp, cp]),
+        "ph_player_init_animation": (i32, [vp, cp]),
+        "ph_player_select_camera": (i32, [vp, cp]),
+        "ph_player_update": (i32, [vp, C.c_double]),
+        "ph_player_camera": (i32, [vp, f64p, f64p, C.POINTER(i32), f64p, f64p, f64p, C.POINTER(C.c_int64)]),
+        "ph_scene_animation_count": (i32, [vp]),
+        "ph_scene_animation": (i32, [vp, i32, C.POINTER(cp), f64p]),
+        "ph_scene_camera_count": (i32, [vp]),
+        "ph_scene_camera_name": (i32, [vp, i32, C.POINTER(cp)]),
+        "ph_player_render_frame": (i32, [vp, vp, C.POINTER(PhFrameParams), vp, i32]),
     })
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

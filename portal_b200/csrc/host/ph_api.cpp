@@ -6,12 +6,21 @@
 #include <vector>
 
 #include "../../../include/portal_b200_host.h"
+#include "ph_anim.h"
 #include "ph_scene.h"
 
 struct ph_scene {
     ph::Scene scene;
     std::vector<ph::TableEntry> table;
     std::string err;
+};
+
+struct ph_player {
+    ph_scene* s;
+    ph::Player player;
+    pe_ctx* ctx = nullptr;
+    std::string err;
+    explicit ph_player(ph_scene* sc) : s(sc), player(sc->scene) {}
 };
 
 namespace {
@@ -29,6 +38,9 @@ int fail(ph_scene* s, const std::string& m) {
 
 // SceneRenderer::set_uniforms (main.rs:1266-1359) for the variants this path implements, with the
 // SceneRenderer::new defaults (main.rs:1021-1047).
+int upload_renderer_uniforms_cam(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, const ph::Mat4& cam, const ph::Mat4& teleport,
+                                 bool in_subspace);
+
 int upload_renderer_uniforms(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p) {
     double look_at[3] = {s->scene.look_at[0], s->scene.look_at[1], s->scene.look_at[2]};
     double alpha = s->scene.alpha, beta = s->scene.beta, r = s->scene.r;
@@ -38,11 +50,18 @@ int upload_renderer_uniforms(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p)
         beta = p->beta;
         r = p->r;
     }
-    ph::Mat4 cam = ph::orbit_camera_matrix(look_at, alpha, beta, r);
-    float cam32[16];
+    return upload_renderer_uniforms_cam(s, ctx, p, ph::orbit_camera_matrix(look_at, alpha, beta, r), ph::mat_identity(), false);
+}
+
+int upload_renderer_uniforms_cam(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, const ph::Mat4& cam, const ph::Mat4& teleport,
+                                 bool in_subspace) {
+    float cam32[16], inv32[16];
+    const ph::Mat4 inv = ph::mat_inverse(teleport);      // `_camera_mul_inv` = teleport_matrix.inverse() (main.rs:1284-1287)
     for (int k = 0; k < 16; k++) cam32[k] = float(cam[k]);
+    for (int k = 0; k < 16; k++) inv32[k] = float(inv[k]);
     int rc = 0;
     rc |= pe_set_uniform_mat4(ctx, "_camera", cam32);
+    rc |= pe_set_uniform_mat4(ctx, "_camera_mul_inv", inv32);
     rc |= pe_set_uniform_f32(ctx, "_camera_scale", float(ph::camera_scale(cam)));
     rc |= pe_set_uniform_f32(ctx, "_view_angle", float(90.0 / 180.0 * M_PI));
     rc |= pe_set_uniform_f32(ctx, "_offset_after_material", float(s->scene.offset_after_material));
@@ -51,7 +70,7 @@ int upload_renderer_uniforms(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p)
     rc |= pe_set_uniform_i32(ctx, "_ray_tracing_depth", p->depth);
     rc |= pe_set_uniform_i32(ctx, "_aa_count", p->aa_count > 0 ? p->aa_count : 1);
     rc |= pe_set_uniform_i32(ctx, "_aa_start", p->aa_start);
-    rc |= pe_set_uniform_i32(ctx, "_camera_in_subspace", 0);
+    rc |= pe_set_uniform_i32(ctx, "_camera_in_subspace", in_subspace ? 1 : 0);
     rc |= pe_set_uniform_i32(ctx, "_darken_by_distance", 1);
     rc |= pe_set_uniform_i32(ctx, "_angle_color_disable", 0);
     rc |= pe_set_uniform_i32(ctx, "_grid_disable", 0);
@@ -291,6 +310,116 @@ int ph_render_motion_blur_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params*
     if (out8) pe_device_free(ctx, out8);
     for (auto& b : sub) if (b) pe_device_free(ctx, b);
     return rc ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------ player
+static int pfail(ph_player* p, const std::string& m) {
+    if (p) p->err = m;
+    return 1;
+}
+
+ph_player* ph_player_new(ph_scene* s) { return s ? new ph_player(s) : nullptr; }
+void ph_player_free(ph_player* p) { delete p; }
+const char* ph_player_last_error(ph_player* p) { return p ? p->err.c_str() : "null player"; }
+
+int ph_player_attach(ph_player* p, pe_ctx* ctx) {
+    if (!p) return 1;
+    p->ctx = ctx;
+    if (!ctx) {
+        p->player.probe = nullptr;
+        return 0;
+    }
+    p->player.probe = [p](const double a[3], const double b[3], double pos[3], bool& have, bool& enc, bool& chg) {
+        // teleport_external_ray (main.rs:1361-1409): set_uniforms with the current scene state and camera, then the probe
+        ph_frame_params fp{};
+        fp.width = fp.height = 1;      // `_resolution` is irrelevant to the probe
+        fp.depth = 100;
+        fp.aa_count = 1;
+        const ph::OrbitCam& c = p->player.cam;
+        if (ph_scene_upload_uniforms(p->s, p->ctx) || upload_renderer_uniforms_cam(p->s, p->ctx, &fp, c.get_matrix(), c.teleport_matrix, c.in_subspace)) {
+            p->player.error = p->s->err;
+            return false;
+        }
+        const float fa[3] = {float(a[0]), float(a[1]), float(a[2])}, fb[3] = {float(b[0]), float(b[1]), float(b[2])};  // as_f32()
+        float out[3];
+        int32_t hr = 0, eo = 0, cs = 0;
+        if (pe_probe_ray(p->ctx, fa, fb, out, &hr, &eo, &cs)) {
+            p->player.error = std::string("pe_probe_ray: ") + pe_last_error(p->ctx);
+            return false;
+        }
+        have = !(out[0] == 0.0f && out[1] == 0.0f && out[2] == 0.0f);   // main.rs:1399: Some(..) unless x == y == z == 0
+        for (int k = 0; k < 3; k++) pos[k] = double(out[k]);
+        enc = eo != 0;
+        chg = cs != 0;
+        return true;
+    };
+    return 0;
+}
+
+int ph_player_init_stage(ph_player* p, const char* name) {
+    if (!p || !name) return 1;
+    return p->player.init_stage_by_name(name) ? 0 : pfail(p, p->player.error);
+}
+int ph_player_init_animation(ph_player* p, const char* name) {
+    if (!p || !name) return 1;
+    return p->player.init_animation_by_name(name) ? 0 : pfail(p, p->player.error);
+}
+int ph_player_select_camera(ph_player* p, const char* name) {
+    if (!p || !name) return 1;
+    return p->player.select_camera(name) ? 0 : pfail(p, p->player.error);
+}
+int ph_player_update(ph_player* p, double t) {
+    if (!p) return 1;
+    p->player.error.clear();
+    return p->player.update(t) ? 0 : pfail(p, p->player.error);
+}
+
+int ph_player_camera(ph_player* p, double camera16[16], double inv16[16], int32_t* in_subspace, double* scale, double orbit[6],
+                     double times[2], int64_t* n_probes) {
+    if (!p) return 1;
+    const ph::OrbitCam& c = p->player.cam;
+    const ph::Mat4 m = c.get_matrix();
+    if (camera16) for (int k = 0; k < 16; k++) camera16[k] = m[k];
+    if (inv16) {
+        const ph::Mat4 inv = ph::mat_inverse(c.teleport_matrix);
+        for (int k = 0; k < 16; k++) inv16[k] = inv[k];
+    }
+    if (in_subspace) *in_subspace = c.in_subspace ? 1 : 0;
+    if (scale) *scale = ph::camera_scale(m);
+    if (orbit) {
+        for (int k = 0; k < 3; k++) orbit[k] = c.look_at[k];
+        orbit[3] = c.alpha; orbit[4] = c.beta; orbit[5] = c.r;
+    }
+    if (times) { times[0] = p->s->scene.time; times[1] = p->s->scene.total_time; }
+    if (n_probes) *n_probes = p->player.n_probes;
+    return 0;
+}
+
+int ph_scene_animation_count(ph_scene* s) { return s ? int(s->scene.animations.size()) : -1; }
+int ph_scene_animation(ph_scene* s, int k, const char** name, double* duration) {
+    if (!s || k < 0 || k >= int(s->scene.animations.size())) return 1;
+    if (name) *name = s->scene.animations[size_t(k)].name.c_str();
+    if (duration) *duration = s->scene.animations[size_t(k)].duration;
+    return 0;
+}
+int ph_scene_camera_count(ph_scene* s) { return s ? int(s->scene.camera_by_name.size()) : -1; }
+int ph_scene_camera_name(ph_scene* s, int k, const char** name) {
+    if (!s || k < 0 || k >= int(s->scene.camera_by_name.size()) || !name) return 1;
+    auto it = s->scene.camera_by_name.begin();
+    std::advance(it, k);
+    *name = it->first.c_str();
+    return 0;
+}
+
+int ph_player_render_frame(ph_player* pl, pe_ctx* ctx, const ph_frame_params* p, void* out_host, int rgba8) {
+    if (!pl || !ctx || !p || !out_host) return 1;
+    const ph::OrbitCam& c = pl->player.cam;
+    if (ph_scene_upload_uniforms(pl->s, ctx)) return pfail(pl, pl->s->err);
+    if (upload_renderer_uniforms_cam(pl->s, ctx, p, c.get_matrix(), c.teleport_matrix, c.in_subspace)) return pfail(pl, pl->s->err);
+    pe_target t = {p->width, p->height, p->height, 0, 1, 1, 1};
+    int rc = rgba8 ? pe_render_host_rgba8(ctx, &t, (uint8_t*)out_host) : pe_render_host(ctx, &t, (float*)out_host);
+    if (rc) return pfail(pl, std::string("render failed: ") + pe_last_error(ctx));
+    return 0;
 }
 
 }  // extern "C"

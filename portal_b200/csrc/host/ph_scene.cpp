@@ -202,6 +202,28 @@ Mat4 orbit_camera_matrix(const double look_at[3], double alpha, double beta, dou
     return mat_mul(mat_identity(), m);
 }
 
+Mat4 orbit_camera_matrix(const double look_at[3], double alpha, double beta, double r, const Mat4& teleport, bool free_movement) {
+    const double pv[3] = {std::sin(beta) * std::cos(alpha) * r, std::cos(beta) * r, std::sin(beta) * std::sin(alpha) * r};
+    const double pos[3] = {pv[0] + look_at[0], pv[1] + look_at[1], pv[2] + look_at[2]};
+    double k[3] = {look_at[0] - pos[0], look_at[1] - pos[1], look_at[2] - pos[2]};
+    v3_normalize(k);
+    const double up[3] = {0.0, 1.0, 0.0};
+    double i[3], j[3];
+    v3_cross(k, up, i);
+    v3_normalize(i);
+    v3_cross(k, i, j);
+    v3_normalize(j);
+    const double* last = free_movement ? look_at : pos;
+    Mat4 m{};
+    m[0] = i[0]; m[1] = i[1]; m[2] = i[2];
+    m[4] = j[0]; m[5] = j[1]; m[6] = j[2];
+    m[8] = k[0]; m[9] = k[1]; m[10] = k[2];
+    m[12] = last[0]; m[13] = last[1]; m[14] = last[2]; m[15] = 1.0;
+    return mat_mul(teleport, m);
+}
+
+void mat_mul_vec(const Mat4& m, const double v[4], double out[4]) { mul_vec(m, v, out); }
+
 // calc_scale (main.rs:1325-1333)
 double camera_scale(const Mat4& m) {
     double s = 0.0;
@@ -493,6 +515,139 @@ struct Loader {
                     if (f != sc.matrix_by_name.end()) sc.dev_matrices[f->second] = matrix_from(*kv.second);
                 }
         }
+        load_cameras_and_animations(root);
+    }
+
+    Cam cam_from(const RonValue& d) {  // cam_from_ser (scene_serialized.rs:476-496)
+        Cam c;
+        if (const RonValue* la = d.get("look_at")) {
+            if (la->is_tag("MatrixCenter")) {
+                c.look_at_matrix = true;
+                c.matrix = matrix_ref(la->at(0));
+            } else if (la->is_tag("Coordinate")) {
+                const RonValue* v = unwrap1(la->at(0));
+                if (la->items.size() == 1 && la->items[0]->kind == RonValue::List && la->items[0]->items.size() == 3) v = la->items[0].get();
+                if (v && v->kind == RonValue::List && v->items.size() == 3)
+                    for (int k = 0; k < 3; k++) c.coord[k] = v->items[size_t(k)]->num();
+            }
+        }
+        auto num = [&](const char* f, double dflt) { const RonValue* v = d.get(f); return v && v->is_num() ? v->num() : dflt; };
+        auto flag = [&](const char* f) { const RonValue* v = d.get(f); return v && v->kind == RonValue::Bool && v->b; };
+        c.alpha = num("alpha", 0.0);
+        c.beta = num("beta", 0.0);
+        c.r = num("r", 3.5);
+        c.in_subspace = flag("in_subspace");
+        c.free_movement = flag("free_movement");
+        if (const RonValue* m = d.get("matrix"))
+            if (m->kind == RonValue::List && m->items.size() == 16)
+                for (int k = 0; k < 16; k++) c.teleport[size_t(k)] = m->items[size_t(k)]->num();
+        return c;
+    }
+
+    int cam_ref(const RonValue* ref) {
+        if (!ref || ref->kind == RonValue::Null) return -1;
+        if (ref->is_tag("Named")) {
+            auto it = sc.camera_by_name.find(ref->at(0) ? ref->at(0)->s : "");
+            return it == sc.camera_by_name.end() ? -1 : it->second;
+        }
+        if (ref->is_tag("Inline") && ref->at(0)) {
+            sc.cameras.push_back(cam_from(*ref->at(0)));
+            return int(sc.cameras.size()) - 1;
+        }
+        return -1;
+    }
+
+    StageRef stage_ref(const RonValue* v) {  // scene_serialized.rs:1386-1397
+        StageRef r;
+        if (!v || v->kind != RonValue::Tagged) return r;
+        const std::string n = v->at(0) ? v->at(0)->s : "";
+        if (v->s == "Animation" && sc.stages.count(n)) {
+            r.kind = StageRef::Animation;
+            r.name = n;
+        } else if (v->s == "RealAnimation" && sc.animation_by_name.count(n)) {
+            r.kind = StageRef::Real;
+            r.index = sc.animation_by_name[n];
+        }
+        return r;
+    }
+
+    void load_cameras_and_animations(const RonValue& root) {
+        if (const RonValue* cams = storage(root, "cameras", false))
+            for (auto& it : cams->items) {
+                const RonValue* n = it->get("name");
+                const RonValue* d = it->get("data");
+                if (!n || !d) continue;
+                sc.camera_by_name.emplace(n->s, int(sc.cameras.size()));
+                sc.cameras.push_back(cam_from(*d));
+            }
+        if (const RonValue* sts = storage(root, "animation_stages", false))
+            for (auto& it : sts->items) {
+                const RonValue* n = it->get("name");
+                const RonValue* d = it->get("data");
+                if (!n || !d) continue;
+                sc.stage_cam[n->s] = cam_ref(d->get("set_cam"));   // None and Some(None) both select the original camera
+            }
+        const RonValue* anims = storage(root, "animations", false);
+        if (anims) {
+            for (auto& it : anims->items)
+                if (const RonValue* n = it->get("name")) {
+                    sc.animation_by_name.emplace(n->s, int(sc.animations.size()));
+                    RealAnimation a;
+                    a.name = n->s;
+                    sc.animations.push_back(a);
+                }
+            size_t idx = 0;
+            for (auto& it : anims->items) {
+                if (!it->get("name")) continue;
+                RealAnimation& a = sc.animations[idx++];
+                const RonValue* d = it->get("data");
+                if (!d) continue;
+                if (const RonValue* v = d->get("duration")) a.duration = v->num();
+                a.stage = stage_ref(d->get("animation_stage"));
+                auto parts = [&](const char* field, bool is_matrix, std::vector<std::pair<int, int>>& out) {
+                    const RonValue* m = unwrap1(d->get(field));
+                    if (!m) return;
+                    for (auto& kv : m->map) {
+                        auto& by = is_matrix ? sc.matrix_by_name : sc.uniform_by_name;
+                        auto f = by.find(kv.first->s);
+                        if (f == by.end()) continue;
+                        if (kv.second->is_tag("Changed")) {
+                            const int e = is_matrix ? matrix_ref(kv.second->at(0)) : uniform_ref(kv.second->at(0));
+                            if (e >= 0) out.emplace_back(f->second, e);
+                        }
+                    }
+                };
+                parts("uniforms", false, a.uniforms);
+                parts("matrices", true, a.matrices);
+                auto flag = [&](const char* f) { const RonValue* v = d->get(f); return v && v->kind == RonValue::Bool && v->b; };
+                auto opt_flag = [&](const char* f) { const RonValue* v = d->get(f); return v && v->kind == RonValue::Bool ? (v->b ? 1 : 0) : -1; };
+                auto anim_by = [&](const char* f) {
+                    const RonValue* v = d->get(f);
+                    if (!v || v->kind != RonValue::String) return -1;
+                    auto it2 = sc.animation_by_name.find(v->s);
+                    return it2 == sc.animation_by_name.end() ? -1 : it2->second;
+                };
+                a.use_prev_cam = flag("use_prev_cam");
+                a.use_start_cam_as_end = flag("use_start_cam_as_end");
+                a.cam_start = cam_ref(d->get("cam_start"));
+                a.cam_end = cam_ref(d->get("cam_end"));
+                a.use_any_cam_as_start = opt_flag("use_any_cam_as_start");
+                a.use_any_cam_as_end = opt_flag("use_any_cam_as_end");
+                a.cam_any_start = anim_by("cam_any_start");
+                a.cam_any_end = anim_by("cam_any_end");
+                if (const RonValue* e = d->get("cam_easing"))
+                    if (e->kind == RonValue::Tagged) {
+                        static const char* names[] = {"Linear", "In", "Out", "InOut", "InOutFast", "ElasticOut"};
+                        for (int k = 0; k < 6; k++) if (e->s == names[k]) a.cam_easing = k;
+                    }
+                if (const RonValue* u = d->get("cam_easing_uniform"))
+                    if (u->kind != RonValue::Null) {
+                        const int id = uniform_ref(u);
+                        if (id >= 0) { a.has_easing_uniform = true; a.easing_uniform = id; }   // scene_serialized.rs:1468-1471
+                    }
+            }
+        }
+        sc.current_stage = stage_ref(root.get("current_stage"));
     }
 };
 
@@ -514,6 +669,22 @@ double easing_elastic_out(double x) {
 }
 
 }  // namespace
+
+double ease(int easing, double t) {  // Easing::ease (easing.rs:87-99)
+    switch (easing) {
+        case 1: return easing_in(t);
+        case 2: return easing_out(t);
+        case 3: return easing_in_out(t);
+        case 4: return easing_in_out_fast(t);
+        case 5: return easing_elastic_out(t);
+        default: return t;
+    }
+}
+
+void Scene::init_dev_stage() {
+    for (auto& kv : dev_uniforms) uniforms[size_t(kv.first)] = kv.second;
+    for (auto& kv : dev_matrices) matrices[size_t(kv.first)] = kv.second;
+}
 
 bool Scene::load(const RonValue& root) {
     Loader l(*this);

@@ -28,6 +28,9 @@ Mat4 mat_inverse(const Mat4& m);
 Mat4 mat_srt(const double scale[3], const double rotate[3], const double offset[3]);
 Mat4 mat_lerp(const Mat4& first, const Mat4& second, double t);
 Mat4 orbit_camera_matrix(const double look_at[3], double alpha, double beta, double r);
+// RotateAroundCam::get_matrix with a teleport matrix and the free-movement flag (main.rs:286-304)
+Mat4 orbit_camera_matrix(const double look_at[3], double alpha, double beta, double r, const Mat4& teleport, bool free_movement);
+void mat_mul_vec(const Mat4& m, const double v[4], double out[4]);
 double camera_scale(const Mat4& m);
 
 struct Uniform {
@@ -88,6 +91,40 @@ struct Stage {
     std::vector<std::pair<int, StageAnim>> uniforms, matrices;  // (target id, what to do)
 };
 
+// Cam (camera.rs:62-76)
+struct Cam {
+    bool look_at_matrix = false;  // CamLookAt::MatrixCenter(id) / Coordinate(pos)
+    double coord[3] = {0, 0, 0};
+    int matrix = -1;
+    double alpha = 0, beta = 0, r = 3.5;
+    bool in_subspace = false, free_movement = false;
+    Mat4 teleport = mat_identity();
+};
+
+struct StageRef {  // CurrentStage (scene.rs) after name resolution
+    enum Kind { Dev, Animation, Real } kind = Dev;
+    std::string name;   // Animation: stage name
+    int index = -1;     // Real: index into Scene::animations
+    bool operator==(const StageRef& o) const { return kind == o.kind && name == o.name && index == o.index; }
+    bool operator!=(const StageRef& o) const { return !(*this == o); }
+};
+
+struct RealAnimation {  // animation.rs:1015-1045 after name resolution
+    std::string name;
+    double duration = 0.0;
+    StageRef stage;
+    std::vector<std::pair<int, int>> uniforms, matrices;  // Changed(Some(x)) parts only: (target id, element x)
+    bool use_prev_cam = false, use_start_cam_as_end = false;
+    int cam_start = -1, cam_end = -1;
+    int use_any_cam_as_start = -1, use_any_cam_as_end = -1;  // -1 None, 0 Some(false), 1 Some(true)
+    int cam_any_start = -1, cam_any_end = -1;
+    int cam_easing = 0;              // Easing: 0 Linear 1 In 2 Out 3 InOut 4 InOutFast 5 ElasticOut
+    bool has_easing_uniform = false;
+    int easing_uniform = -1;
+};
+
+double ease(int easing, double t);
+
 struct Scene {
     // saved camera (CamSettings, scene.rs) + per-scene `_offset_after_material`
     double look_at[3] = {0, 0, 0}, alpha = 0, beta = 0, r = 1, offset_after_material = 0.005;
@@ -111,6 +148,14 @@ struct Scene {
     std::map<int, Matrix> dev_matrices;
     // Scene::init_stage(CurrentStage::Animation(id)) (scene.rs:1180-1200, animation.rs:171-183)
     bool init_stage(const std::string& name);
+    // cameras, stage cameras, real animations (scene_serialized.rs:1286-1473)
+    std::vector<Cam> cameras;
+    std::map<std::string, int> camera_by_name;
+    std::map<std::string, int> stage_cam;                // stage name -> camera id (-1 = original camera)
+    std::vector<RealAnimation> animations;               // in file (= visible) order
+    std::map<std::string, int> animation_by_name;
+    StageRef current_stage;
+    void init_dev_stage();                               // DevStageChanging::init_stage (animation.rs:223-227)
 
     // deserialize_scene_new_format
     bool load(const RonValue& root);

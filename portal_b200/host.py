@@ -93,6 +93,76 @@ class HostScene:
         return {n: self._lib.ph_scene_count(self._s, i) for i, n in enumerate(names)}
 
 
+class HostPlayer:
+    """The animation-facing half of SceneRenderer (ph_player_*, include/portal_b200_host.h): stages, real
+    animations, named cameras, time mapping, camera interpolation and -- with a renderer attached -- camera
+    teleportation through portals."""
+
+    def __init__(self, scene: HostScene, renderer: "HostRenderer | None" = None):
+        self.scene = scene
+        self._lib = capi.lib()
+        self._p = self._lib.ph_player_new(scene._s)
+        if renderer is not None:
+            self._check(self._lib.ph_player_attach(self._p, renderer._ctx))
+        self.renderer = renderer
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PortalB200Error(self._lib.ph_player_last_error(self._p).decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self._lib.ph_player_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def animations(self):
+        """[(name, duration seconds)] in file order."""
+        out, nm, d = [], C.c_char_p(), C.c_double()
+        for k in range(self._lib.ph_scene_animation_count(self.scene._s)):
+            self._lib.ph_scene_animation(self.scene._s, k, C.byref(nm), C.byref(d))
+            out.append((nm.value.decode(), d.value))
+        return out
+
+    def camera_names(self):
+        out, nm = [], C.c_char_p()
+        for k in range(self._lib.ph_scene_camera_count(self.scene._s)):
+            self._lib.ph_scene_camera_name(self.scene._s, k, C.byref(nm))
+            out.append(nm.value.decode())
+        return out
+
+    def init_stage(self, name: str):
+        self._check(self._lib.ph_player_init_stage(self._p, b(name)))
+
+    def init_animation(self, name: str):
+        self._check(self._lib.ph_player_init_animation(self._p, b(name)))
+
+    def select_camera(self, name: str):
+        self._check(self._lib.ph_player_select_camera(self._p, b(name)))
+
+    def update(self, time_seconds: float):
+        self._check(self._lib.ph_player_update(self._p, float(time_seconds)))
+
+    def camera_state(self) -> dict:
+        cam, inv, orbit, times = (C.c_double * 16)(), (C.c_double * 16)(), (C.c_double * 6)(), (C.c_double * 2)()
+        sub, scale, n = C.c_int32(), C.c_double(), C.c_int64()
+        self._check(self._lib.ph_player_camera(self._p, cam, inv, C.byref(sub), C.byref(scale), orbit, times, C.byref(n)))
+        return {"camera": list(cam), "camera_mul_inv": list(inv), "in_subspace": bool(sub.value), "scale": scale.value,
+                "look_at": list(orbit[:3]), "alpha": orbit[3], "beta": orbit[4], "r": orbit[5],
+                "time": times[0], "total_time": times[1], "n_probes": n.value}
+
+    def render_frame(self, width, height, depth, aa_count=1, aa_start=0, rgba8=False) -> np.ndarray:
+        p = PhFrameParams(width, height, depth, aa_count, aa_start, 0)
+        out = np.empty((height, width, 4), dtype=np.uint8 if rgba8 else np.float32)
+        self._check(self._lib.ph_player_render_frame(self._p, self.renderer._ctx, C.byref(p), out.ctypes.data, int(rgba8)))
+        return out
+
+
 class HostRenderer:
     """SceneRenderer::new + render_frame over the C API only (no scene IR involved)."""
 

@@ -1,0 +1,216 @@
+"""The animation layer between a scene file and one frame's uniforms: stages with cameras, real
+animations (time mapping, camera interpolation), named cameras and camera teleportation through portals.
+C++ host (`ph_player_*`, portal_b200/csrc/host/ph_anim.cpp) against the oracle's independent restatement
+(oracle/animation.py) -- value for value in float64 -- plus hand-checkable facts about the fixture scene."""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import REFERENCE, ROOT
+from portal_b200.capi import PortalB200Error
+from portal_b200.host import HostPlayer, HostRenderer, HostScene
+
+FIXTURE = os.path.join(ROOT, "tests", "fixtures", "two_spheres.ron")
+ANIMS = [("fly.1", 2.0), ("fly.2", 1.5), ("hold", 1.0), ("through", 4.0)]
+
+
+def _same(a, b):
+    return np.array_equal(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), equal_nan=True)
+
+
+def _assert_same_state(p, hp, s, hs, where):
+    a, b = p.camera_state(), hp.camera_state()
+    for k in a:
+        assert _same(a[k], b[k]), (where, k, a[k], b[k])
+    ta, tb = s.uniform_table(), hs.uniform_table()
+    assert list(ta) == list(tb), where
+    for k in ta:
+        assert _same(ta[k][1], tb[k][1]), (where, k)
+
+
+def _pair(path):
+    from oracle import frontend
+    from oracle.animation import Player
+    s = frontend.load_scene(path)
+    hs = HostScene.from_file(path)
+    return s, Player(s), hs, HostPlayer(hs)
+
+
+def test_fixture_animations_match_oracle_player():
+    _, _, hs0, hp0 = _pair(FIXTURE)
+    assert hp0.animations() == ANIMS
+    assert sorted(hp0.camera_names()) == ["at_ball", "before_gate", "behind_gate", "wide"]
+    for name, _ in ANIMS:
+        s, p, hs, hp = _pair(FIXTURE)
+        p.init_animation(name)
+        hp.init_animation(name)
+        for t in (0.0, 0.3, 1.0, 1.7, 2.6, 0.2):           # not monotonic: the wrap re-arms `override_matrix`
+            p.update(t)
+            hp.update(t)
+            _assert_same_state(p, hp, s, hs, (name, t))
+
+
+def test_time_mapping_and_camera_chain():
+    """Scene::update (scene.rs:1385-1418): inside a real animation formula `time` = (t % duration) / duration and
+    `total_time` adds the durations of the animations before it; cameras: get_start_cam / get_end_cam (:1291-1335)."""
+    s, p, hs, hp = _pair(FIXTURE)
+    hp.init_animation("fly.2")
+    hp.update(0.3)
+    st = hp.camera_state()
+    assert st["time"] == math.fmod(0.3, 1.5) / 1.5 and st["total_time"] == 2.0 + math.fmod(0.3, 1.5)
+    # fly.2 builds on RealAnimation("fly.1") which builds on stage "closed": p from fly.1, spin formula from fly.2
+    t = hs.uniform_table()
+    assert t["p_u"] == ("float", 0.9) and t["open_u"] == ("int", 0) and t["spin_u"] == ("float", 0.2 + st["time"])
+    # use_prev_cam: fly.2 starts where fly.1 ends
+    hp.update(0.0)
+    st = hp.camera_state()
+    assert st["look_at"] == [0.0, 0.5, 0.25] and (st["alpha"], st["beta"], st["r"]) == (2.9, 1.4, 2.2)
+    # cam_easing_uniform is clamped to [0, 1]: near the end of fly.2 the camera IS the end camera ("at_ball")
+    hp.update(1.49)
+    st = hp.camera_state()
+    ball = np.asarray(hs.uniform_table()["ball_mat"][1]).reshape(4, 4)[3, :3]       # column-major: translation
+    assert (st["alpha"], st["beta"], st["r"]) == (-0.4, 1.3, 1.9)
+    assert np.allclose(st["look_at"], ball + 0.001, atol=1e-15)                    # MatrixCenter: centre + 0.001 (camera.rs:117-120)
+    # "hold": use_any_cam_as_start = Some(false) -> fly.1's START camera; use_start_cam_as_end -> stays there
+    _, _, hs2, hp2 = _pair(FIXTURE)
+    hp2.init_animation("hold")
+    for tm in (0.0, 0.6):
+        hp2.update(tm)
+        st = hp2.camera_state()
+        assert st["look_at"] == [0.3, 0.1, -0.2] and (st["alpha"], st["beta"], st["r"]) == (2.1, 1.05, 3.6)
+    assert hp2.camera_state()["total_time"] == 3.5 + 0.6
+    assert hs2.uniform_table()["open_u"] == ("int", 1)                              # Dev stage restored
+
+
+def test_stage_and_named_cameras():
+    s, p, hs, hp = _pair(FIXTURE)
+    hp.update(0.0)                                                                  # plain render-frame: the saved camera
+    st = hp.camera_state()
+    assert st["look_at"] == [0.1, -0.2, 0.0] and (st["alpha"], st["beta"], st["r"]) == (0.83, 1.21, 2.9) and st["time"] == 0.0
+    hp.init_stage("closed")                                                         # set_cam: Some(Some(Named("wide")))
+    hp.update(0.25)
+    st = hp.camera_state()
+    assert (st["alpha"], st["beta"], st["r"]) == (2.1, 1.05, 3.6) and st["time"] == 0.25 and st["total_time"] == 0.25
+    hp.init_stage("reset")                                                          # set_cam: None -> back to the original camera
+    hp.update(0.0)
+    assert hp.camera_state()["alpha"] == 0.83
+    hp.select_camera("at_ball")
+    hp.update(0.0)
+    assert hp.camera_state()["r"] == 1.9
+    for bad in (hp.init_stage, hp.init_animation, hp.select_camera):
+        with pytest.raises(PortalB200Error, match="no (stage|animation|camera) named"):
+            bad("nope")
+    # same walk on the oracle side
+    p.update(0.0)
+    p.init_stage("closed")
+    p.update(0.25)
+    p.init_stage("reset")
+    p.update(0.0)
+    p.select_camera("at_ball")
+    p.update(0.0)
+    _assert_same_state(p, hp, s, hs, "stage walk")
+
+
+def test_camera_teleports_through_the_gate_on_the_oracle():
+    """teleport_camera + teleport_matrix (main.rs:1217-1264, 1174-1215) with the CPU oracle as the external-ray
+    probe: walking through the open gate costs 1 + 3 probes once, and the finite-difference matrix it recovers is
+    portal_b * portal_a^-1 (to the 1e-3 step of the differences)."""
+    from oracle import frontend
+    from oracle.animation import Player
+    from oracle.runner import Oracle
+    orc = Oracle(frontend.scene_ir(frontend.load_scene(FIXTURE), "two_spheres"), variant="strict")
+    s = frontend.load_scene(FIXTURE)
+    p = Player(s, probe=_oracle_probe(orc))
+    p.init_animation("through")
+    crossed_at, cams = None, []
+    for k in range(21):
+        p.update(4.0 * k / 20 * 0.999)
+        cams.append(p.camera_state())
+        if crossed_at is None and p.cam.teleport_matrix != frontend.mat_identity():
+            crossed_at = k
+            a = s.get_matrix(s.matrix_by_name["portal_a"])
+            b = s.get_matrix(s.matrix_by_name["portal_b"])
+            want = np.asarray(frontend.mat_mul(b, frontend.mat_inverse(a)))
+            assert np.allclose(np.asarray(p.cam.teleport_matrix), want, atol=2e-3)
+    assert crossed_at == 13 and p.n_probes == 20 + 3
+    before, after = np.asarray(cams[12]["camera"][12:15]), np.asarray(cams[13]["camera"][12:15])
+    assert np.linalg.norm(after - before) > 2.0                                    # the eye is now at the other portal
+    assert np.allclose(np.asarray(cams[13]["camera_mul_inv"]).reshape(4, 4).T @ np.asarray(p.cam.teleport_matrix).reshape(4, 4).T,
+                       np.eye(4), atol=1e-12)
+
+
+def _oracle_probe(orc):
+    def probe(player, a, b):
+        table = player.scene.uniform_table()
+        orc.set_uniforms({k: v for k, (_, v) in table.items()})
+        cs = player.camera_state()
+        pos, _, enc, chg = orc.probe(a, b, camera=cs["camera"], camera_scale=cs["scale"], camera_mul_inv=cs["camera_mul_inv"],
+                                     camera_in_subspace=int(cs["in_subspace"]))
+        have = not (pos[0] == 0 and pos[1] == 0 and pos[2] == 0)                    # main.rs:1399
+        return ([float(x) for x in pos] if have else None, enc, chg)
+    return probe
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (GPU box)")
+def test_reference_scene_animations_match_oracle_player():
+    """Every reference scene: its first animations at four times, camera + full uniform table, C++ == oracle."""
+    n = 0
+    for path in sorted(glob.glob(f"{REFERENCE}/scenes/*.ron")):
+        if os.path.basename(path) == "empty.ron":
+            continue
+        _, p0, _, hp0 = _pair(path)
+        names = [a["name"] for a in p0.anim.animations]
+        assert [a for a, _ in hp0.animations()] == names
+        for an in names[:3]:
+            s, p, hs, hp = _pair(path)
+            try:
+                p.init_animation(an)
+            except NotImplementedError:                                             # Sqrt matrices (argmin BFGS): not restated
+                continue
+            hp.init_animation(an)
+            dur = p.anim.animations[p.anim.animation_by_name[an]]["duration"]
+            for tt in (0.0, 0.37 * dur, 0.99 * dur, 1.5 * dur):
+                try:
+                    p.update(tt)
+                    s.uniform_table()
+                except NotImplementedError:
+                    break
+                hp.update(tt)
+                _assert_same_state(p, hp, s, hs, (path, an, tt))
+                n += 1
+    assert n >= 250
+
+
+@pytest.mark.gpu
+def test_player_teleports_on_the_gpu_like_the_oracle(torch_cuda):
+    """The same walk through the gate with pe_probe_ray as the probe: every camera matrix, the teleport matrix and
+    the probe count equal the oracle-driven player's bit for bit; the frame after the crossing equals the oracle's."""
+    from oracle import frontend
+    from oracle.animation import Player
+    from oracle.runner import Oracle
+    orc = Oracle(frontend.scene_ir(frontend.load_scene(FIXTURE), "two_spheres"), variant="strict")
+    s = frontend.load_scene(FIXTURE)
+    p = Player(s, probe=_oracle_probe(orc))
+    hs = HostScene.from_file(FIXTURE)
+    hr = HostRenderer(hs)
+    hp = HostPlayer(hs, hr)
+    p.init_animation("through")
+    hp.init_animation("through")
+    for k in range(21):
+        t = 4.0 * k / 20 * 0.999
+        p.update(t)
+        hp.update(t)
+        a, b = p.camera_state(), hp.camera_state()
+        for key in a:
+            assert _same(a[key], b[key]), (k, key)
+        assert b["n_probes"] == p.n_probes
+    assert hp.camera_state()["n_probes"] == 23
+    cs = p.camera_state()
+    orc.set_uniforms({k: v for k, (_, v) in s.uniform_table().items()})
+    want = orc.render(192, 108, 12, camera=cs["camera"], camera_scale=cs["scale"], camera_mul_inv=cs["camera_mul_inv"],
+                      camera_in_subspace=int(cs["in_subspace"]))
+    got = hp.render_frame(192, 108, 12)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
