@@ -125,6 +125,12 @@ PE_API int ph_scene_camera_name(ph_scene* s, int k, const char** name);
 /* draw_texture + readback with the player's camera and the scene's current uniforms (width, height, depth,
  * aa_count, aa_start of `p` are used; its camera fields are ignored). */
 PE_API int ph_player_render_frame(ph_player* pl, pe_ctx* ctx, const ph_frame_params* p, void* out_host, int rgba8);
+/* One output frame of render_animation (src/main.rs:1786-1817) inside the player's current animation: every
+ * sub-frame j calls update(t_j * duration_seconds) -- time mapping, camera interpolation, teleportation --
+ * renders with `_aa_start` = j into an RGBA8 target, and the sub-frames are averaged in gamma-2 space. */
+PE_API int ph_player_render_motion_blur_frame(ph_player* pl, pe_ctx* ctx, const ph_frame_params* p, int frame_index,
+                                              int frame_count, int motion_blur_frames, double duration_seconds,
+                                              uint8_t* out_host_rgba8);
 
 #ifdef __cplusplus
 }

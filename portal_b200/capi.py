@@ -132,6 +132,7 @@ def lib() -> C.CDLL:
         "ph_scene_camera_count": (i32, [vp]),
         "ph_scene_camera_name": (i32, [vp, i32, C.POINTER(cp)]),
         "ph_player_render_frame": (i32, [vp, vp, C.POINTER(PhFrameParams), vp, i32]),
+        "ph_player_render_motion_blur_frame": (i32, [vp, vp, C.POINTER(PhFrameParams), i32, i32, i32, C.c_double, vp]),
     })
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -422,4 +422,41 @@ int ph_player_render_frame(ph_player* pl, pe_ctx* ctx, const ph_frame_params* p,
     return 0;
 }
 
+int ph_player_render_motion_blur_frame(ph_player* pl, pe_ctx* ctx, const ph_frame_params* p, int frame_index, int frame_count,
+                                       int motion_blur_frames, double duration_seconds, uint8_t* out_host) {
+    if (!pl || !ctx || !p || !out_host) return 1;
+    if (frame_count < 1 || motion_blur_frames < 1 || motion_blur_frames > 64 || frame_index < 0)
+        return pfail(pl, "ph_player_render_motion_blur_frame: bad frame arguments");
+    const size_t n = size_t(p->width) * size_t(p->height);
+    void* out8 = nullptr;
+    std::vector<void*> sub(size_t(motion_blur_frames), nullptr);
+    int rc = pe_device_malloc(ctx, n * 4, &out8);
+    for (auto& b : sub) rc |= pe_device_malloc(ctx, n * 4, &b);
+    if (rc) pl->err = std::string("device allocation failed: ") + pe_last_error(ctx);
+    pe_target t = {p->width, p->height, p->height, 0, 1, 1, 1};
+    const double exposure = 0.5;  // main.rs:1787
+    for (int j = 0; j < motion_blur_frames && !rc; j++) {
+        const double tt = double(frame_index) / double(frame_count) + double(j) / double(motion_blur_frames) / double(frame_count) * exposure;
+        ph_frame_params q = *p;
+        q.aa_start = j;  // main.rs:1797
+        if (!pl->player.update(tt * duration_seconds)) { pl->err = pl->player.error; rc = 1; break; }   // self.update(memory, t * duration)
+        const ph::OrbitCam& c = pl->player.cam;
+        if (ph_scene_upload_uniforms(pl->s, ctx) || upload_renderer_uniforms_cam(pl->s, ctx, &q, c.get_matrix(), c.teleport_matrix, c.in_subspace)) {
+            pl->err = pl->s->err;
+            rc = 1;
+        } else if (pe_render_rgba8(ctx, &t, sub[size_t(j)], nullptr)) {
+            pl->err = std::string("render failed: ") + pe_last_error(ctx);
+            rc = 1;
+        }
+    }
+    if (!rc && (pe_average_frames_rgba8(ctx, sub.data(), motion_blur_frames, out8, n, nullptr) || pe_memcpy_d2h(ctx, out_host, out8, n * 4, nullptr))) {
+        pl->err = std::string("motion-blur average failed: ") + pe_last_error(ctx);
+        rc = 1;
+    }
+    pe_sync(ctx);
+    if (out8) pe_device_free(ctx, out8);
+    for (auto& b : sub) if (b) pe_device_free(ctx, b);
+    return rc ? 1 : 0;
+}
+
 }  // extern "C"

@@ -2,7 +2,13 @@
 // (/root/reference/src/main.rs:2736-2760 options, :2876-2946 render_frame), C++ host + C ABI only:
 //
 //   portal_b200_render render-frame <scene.ron> [--width W] [--height H] [--render-depth D] [--aa-count N]
-//                      [--time T] [--stage NAME] [--device K] [--texture name=file.rgba:WxH ...] [--output out.ppm]
+//                      [--time T] [--stage NAME] [--animation NAME] [--camera NAME] [--device K]
+//                      [--texture name=file.rgba:WxH ...] [--output out.ppm]
+//   portal_b200_render render <scene.ron> --animations a,b,... [--fps N] [--motion-blur-frames M] [--width W]
+//                      [--height H] [--render-depth D] [--aa-count N] [--out-dir DIR] [--max-frames K]
+//                      (`portal render`, main.rs:2808-2873 -> render_named_animations :1876-1930 ->
+//                       render_animation :1757-1830; frames are written as DIR/<animation>/frame_<i>.ppm, the
+//                       ffmpeg step is out of scope)
 //
 // Output: binary PPM (P6) of the RGBA8 frame the reference would hand to export_png (alpha dropped), or
 // raw RGBA8 with a .rgba extension.  PNG encode/decode is out of scope: textures
@@ -25,17 +31,34 @@ static std::string slurp(const std::string& path, bool& ok) {
     return ss.str();
 }
 
+static bool write_image(const std::string& output, const std::vector<uint8_t>& px, int width, int height) {
+    std::ofstream out(output, std::ios::binary);
+    if (!out) return false;
+    if (output.size() > 5 && output.substr(output.size() - 5) == ".rgba") {
+        out.write(reinterpret_cast<const char*>(px.data()), std::streamsize(px.size()));
+    } else {
+        out << "P6\n" << width << " " << height << "\n255\n";
+        for (size_t i = 0; i < size_t(width) * size_t(height); i++) out.write(reinterpret_cast<const char*>(&px[4 * i]), 3);
+    }
+    return bool(out);
+}
+
 int main(int argc, char** argv) {
-    if (argc < 3 || std::strcmp(argv[1], "render-frame") != 0) {
-        std::fprintf(stderr, "usage: %s render-frame <scene.ron> [--width W] [--height H] [--render-depth D] [--aa-count N] "
-                             "[--time T] [--device K] [--texture name=file.rgba:WxH] [--output out.ppm]\n", argv[0]);
+    const bool frame_cmd = argc >= 3 && std::strcmp(argv[1], "render-frame") == 0;
+    const bool anim_cmd = argc >= 3 && std::strcmp(argv[1], "render") == 0;
+    if (!frame_cmd && !anim_cmd) {
+        std::fprintf(stderr, "usage: %s render-frame <scene.ron> [--width W] [--height H] [--render-depth D] [--aa-count N] [--time T] "
+                             "[--stage NAME] [--animation NAME] [--camera NAME] [--device K] [--texture name=file.rgba:WxH] [--output out.ppm]\n"
+                             "       %s render <scene.ron> --animations a,b [--fps N] [--motion-blur-frames M] [--width W] [--height H] "
+                             "[--render-depth D] [--aa-count N] [--out-dir DIR] [--max-frames K]\n", argv[0], argv[0]);
         return 2;
     }
-    std::string scene_path = argv[2], output = "frame.ppm";
+    std::string scene_path = argv[2], output = "frame.ppm", out_dir = "video";
     int width = 1920, height = 1080, depth = 100, aa = 1, device = 0;  // defaults of RenderFrameCliOptions, main.rs:2744-2754
+    int fps = 60, motion_blur = 1, max_frames = -1;
     double time = 0.0;
     std::vector<std::string> textures;
-    std::string stage;
+    std::string stage, animation, camera, animations;
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -46,6 +69,13 @@ int main(int argc, char** argv) {
         else if (a == "--time") time = std::atof(next());
         else if (a == "--device") device = std::atoi(next());
         else if (a == "--stage") stage = next();
+        else if (a == "--animation") animation = next();
+        else if (a == "--camera") camera = next();
+        else if (a == "--animations") animations = next();
+        else if (a == "--fps") fps = std::atoi(next());
+        else if (a == "--motion-blur-frames") motion_blur = std::atoi(next());
+        else if (a == "--out-dir") out_dir = next();
+        else if (a == "--max-frames") max_frames = std::atoi(next());
         else if (a == "--output") output = next();
         else if (a == "--texture") textures.push_back(next());
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
@@ -58,11 +88,21 @@ int main(int argc, char** argv) {
     if (!scene) { std::fprintf(stderr, "Failed to parse scene `%s`: %s\n", scene_path.c_str(), err); return 1; }
     pe_ctx* ctx = pe_create(device);
     if (!ctx) { std::fprintf(stderr, "pe_create: %s\n", pe_last_error(nullptr)); return 1; }
-    if (!stage.empty() && ph_scene_init_stage(scene, stage.c_str())) {   // main.rs:2900-2906
-        std::fprintf(stderr, "Scene `%s` has no stage named `%s`\n", scene_path.c_str(), stage.c_str());
-        return 1;
+    ph_player* player = ph_player_new(scene);
+    if (frame_cmd) {  // main.rs:2900-2926
+        if (!stage.empty() && ph_player_init_stage(player, stage.c_str())) {
+            std::fprintf(stderr, "Scene `%s` has no stage named `%s`\n", scene_path.c_str(), stage.c_str());
+            return 1;
+        }
+        if (!animation.empty() && ph_player_init_animation(player, animation.c_str())) {
+            std::fprintf(stderr, "Scene `%s` has no animation named `%s`\n", scene_path.c_str(), animation.c_str());
+            return 1;
+        }
+        if (!camera.empty() && ph_player_select_camera(player, camera.c_str())) {
+            std::fprintf(stderr, "Scene `%s` has no camera named `%s`\n", scene_path.c_str(), camera.c_str());
+            return 1;
+        }
     }
-    ph_scene_set_time(scene, time, time);
     if (ph_scene_build_program(scene, ctx) || ph_scene_upload_uniforms(scene, ctx)) {
         std::fprintf(stderr, "%s\n", ph_scene_last_error(scene));
         return 1;
@@ -77,17 +117,55 @@ int main(int argc, char** argv) {
         if (pe_set_texture(ctx, t.substr(0, eq).c_str(), reinterpret_cast<const uint8_t*>(bytes.data()), tw, th)) { std::fprintf(stderr, "%s\n", pe_last_error(ctx)); return 1; }
     }
     if (pe_scene_compile(ctx)) { std::fprintf(stderr, "%s\n", pe_last_error(ctx)); return 1; }
+    ph_player_attach(player, ctx);  // camera teleportation goes through pe_probe_ray
     std::vector<uint8_t> px(size_t(width) * size_t(height) * 4);
     ph_frame_params p = {width, height, depth, aa, 0, 0, {0, 0, 0}, 0, 0, 0};
-    if (ph_render_frame(scene, ctx, &p, px.data(), 1)) { std::fprintf(stderr, "%s\n", ph_scene_last_error(scene)); return 1; }
-    std::ofstream out(output, std::ios::binary);
-    if (output.size() > 5 && output.substr(output.size() - 5) == ".rgba") {
-        out.write(reinterpret_cast<const char*>(px.data()), std::streamsize(px.size()));
+    if (frame_cmd) {
+        if (ph_player_update(player, time) || ph_player_render_frame(player, ctx, &p, px.data(), 1)) {   // main.rs:2928-2929
+            std::fprintf(stderr, "%s\n", ph_player_last_error(player));
+            return 1;
+        }
+        if (!write_image(output, px, width, height)) { std::fprintf(stderr, "cannot write %s\n", output.c_str()); return 1; }
+        std::printf("Rendered `%s` to `%s`\n", scene_path.c_str(), output.c_str());
     } else {
-        out << "P6\n" << width << " " << height << "\n255\n";
-        for (size_t i = 0; i < size_t(width) * size_t(height); i++) out.write(reinterpret_cast<const char*>(&px[4 * i]), 3);
+        if (animations.empty()) { std::fprintf(stderr, "render: --animations a,b,... is required\n"); return 2; }
+        std::vector<std::string> names;
+        std::stringstream ss(animations);
+        for (std::string item; std::getline(ss, item, ',');) if (!item.empty()) names.push_back(item);
+        for (size_t k = 0; k < names.size(); k++) {  // render_named_animations, main.rs:1888-1927
+            if (ph_player_init_animation(player, names[k].c_str())) {
+                std::fprintf(stderr, "Scene `%s` has no animation named `%s`\n", scene_path.c_str(), names[k].c_str());
+                return 1;
+            }
+            if (ph_player_update(player, 0.0)) { std::fprintf(stderr, "%s\n", ph_player_last_error(player)); return 1; }
+            double duration = 0.0;
+            for (int a = 0; a < ph_scene_animation_count(scene); a++) {
+                const char* nm = nullptr;
+                double d = 0.0;
+                if (ph_scene_animation(scene, a, &nm, &d) == 0 && names[k] == nm) duration = d;
+            }
+            std::printf("Rendering animation %s, %zu/%zu\n", names[k].c_str(), k + 1, names.size());
+            const std::string dir = out_dir + "/" + names[k];
+            std::string cmd = "mkdir -p '" + dir + "'";
+            if (std::system(cmd.c_str()) != 0) { std::fprintf(stderr, "cannot create %s\n", dir.c_str()); return 1; }
+            const float duration32 = float(duration);                                          // render_animation takes f32
+            int count = int(duration32 * float(fps));                                           // main.rs:1785
+            if (count < 1) count = 1;
+            const int todo = max_frames >= 0 && max_frames < count ? max_frames : count;
+            for (int i = 0; i < todo; i++) {
+                if (ph_player_render_motion_blur_frame(player, ctx, &p, i, count, motion_blur, double(duration32), px.data())) {
+                    std::fprintf(stderr, "%s\n", ph_player_last_error(player));
+                    return 1;
+                }
+                const std::string name = dir + "/frame_" + std::to_string(i) + ".ppm";
+                if (!write_image(name, px, width, height)) { std::fprintf(stderr, "cannot write %s\n", name.c_str()); return 1; }
+                std::printf("\r%d/%d done      ", i + 1, count);
+                std::fflush(stdout);
+            }
+            std::printf("\n");
+        }
     }
-    std::printf("Rendered `%s` to `%s`\n", scene_path.c_str(), output.c_str());
+    ph_player_free(player);
     pe_destroy(ctx);
     ph_scene_free(scene);
     return 0;

@@ -163,6 +163,16 @@ class HostPlayer:
         return out
 
 
+    def render_motion_blur_frame(self, width, height, depth, frame_index, frame_count, motion_blur_frames, duration_seconds,
+                                 aa_count=1) -> np.ndarray:
+        """One frame of render_animation (main.rs:1786-1817) inside the current animation, RGBA8."""
+        p = PhFrameParams(width, height, depth, aa_count, 0, 0)
+        out = np.empty((height, width, 4), dtype=np.uint8)
+        self._check(self._lib.ph_player_render_motion_blur_frame(self._p, self.renderer._ctx, C.byref(p), frame_index, frame_count,
+                                                                 motion_blur_frames, float(duration_seconds), out.ctypes.data))
+        return out
+
+
 class HostRenderer:
     """SceneRenderer::new + render_frame over the C API only (no scene IR involved)."""
 

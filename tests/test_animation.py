@@ -214,3 +214,40 @@ def test_player_teleports_on_the_gpu_like_the_oracle(torch_cuda):
                       camera_in_subspace=int(cs["in_subspace"]))
     got = hp.render_frame(192, 108, 12)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_cli_render_frame_animation_and_render_loop(torch_cuda, tmp_path):
+    """`portal_b200_render render-frame --animation/--time` and `render --animations` (C++ only) against the same
+    calls made through the Python bindings."""
+    import subprocess
+    exe = os.path.join(ROOT, "portal_b200", "portal_b200_render")
+    out = tmp_path / "f.rgba"
+    r = subprocess.run([exe, "render-frame", FIXTURE, "--width", "160", "--height", "90", "--render-depth", "12", "--animation", "fly.2",
+                        "--time", "0.6", "--output", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.frombuffer(out.read_bytes(), dtype=np.uint8).reshape(90, 160, 4)
+    hs = HostScene.from_file(FIXTURE)
+    hr = HostRenderer(hs)
+    hp = HostPlayer(hs, hr)
+    hp.init_animation("fly.2")
+    hp.update(0.6)
+    assert np.array_equal(got, hp.render_frame(160, 90, 12, rgba8=True))
+    r = subprocess.run([exe, "render-frame", FIXTURE, "--animation", "nope"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "has no animation named `nope`" in r.stderr
+    # the offline loop: 2 of the 4.0 s * 5 fps = 20 frames of "through", 3 motion-blur sub-frames each
+    r = subprocess.run([exe, "render", FIXTURE, "--animations", "through", "--fps", "5", "--motion-blur-frames", "3", "--width", "96",
+                        "--height", "54", "--render-depth", "8", "--out-dir", str(tmp_path / "video"), "--max-frames", "2"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    hs = HostScene.from_file(FIXTURE)
+    hr = HostRenderer(hs)
+    hp = HostPlayer(hs, hr)
+    hp.init_animation("through")
+    hp.update(0.0)
+    for i in range(2):
+        want = hp.render_motion_blur_frame(96, 54, 8, i, 20, 3, 4.0)
+        raw = (tmp_path / "video" / "through" / f"frame_{i}.ppm").read_bytes()
+        assert raw.startswith(b"P6\n96 54\n255\n")
+        got = np.frombuffer(raw[len(b"P6\n96 54\n255\n"):], dtype=np.uint8).reshape(54, 96, 3)
+        assert np.array_equal(got, want[..., :3])
