@@ -37,6 +37,10 @@ PE_API const char* ph_scene_last_error(ph_scene* s);
 
 /* Formula variables `time` / `total_time` (0 for a freshly loaded scene). */
 PE_API int ph_scene_set_time(ph_scene* s, double time, double total_time);
+/* The camera matrix the `Camera` matrix kind evaluates to (FormulasCache::set_camera_matrix, fed by
+ * send_camera_object_matrix, src/main.rs:1432-1436); identity until set.  ph_render_frame / ph_player_* set it
+ * themselves. */
+PE_API int ph_scene_set_formula_camera(ph_scene* s, const double m16[16]);
 /* Override the value of a named Bool / Int / Float / Angle / Progress uniform (the editor's sliders). */
 PE_API int ph_scene_set_value(ph_scene* s, const char* uniform_name, double value);
 

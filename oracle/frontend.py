@@ -853,9 +853,11 @@ def scene_ir(scene: Scene, scene_name: str, time: float = 0.0, stage: str | None
             objects.append({"name": o["name"], "class": o["class"], "kind": o["kind"],
                             "matrices": [None if x is None else scene.matrix_name(x) for x in o["matrices"]],
                             "in_subspace": o["in_subspace"], "code": o["code"]})
-    table = scene.uniform_table()
     cam = scene.cam
     cm = orbit_camera_matrix([float(x) for x in cam["look_at"]], float(cam["alpha"]), float(cam["beta"]), float(cam["r"]))
+    # send_camera_object_matrix (main.rs:145, 1432-1436, 1530-1534): the `Camera` matrix kind sees the renderer's camera
+    scene.camera_matrix = cm
+    table = scene.uniform_table()
     d = renderer_defaults()
     return {
         "format": "portal-b200 scene IR v1",

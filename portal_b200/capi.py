@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
         "ph_scene_last_error": (cp, [vp]),
         "ph_scene_set_time": (i32, [vp, C.c_double, C.c_double]),
         "ph_scene_set_value": (i32, [vp, cp, C.c_double]),
+        "ph_scene_set_formula_camera": (i32, [vp, f64p]),
         "ph_scene_init_stage": (i32, [vp, cp]),
         "ph_scene_stage_name": (i32, [vp, i32, C.POINTER(cp)]),
         "ph_scene_evaluate": (i32, [vp]),

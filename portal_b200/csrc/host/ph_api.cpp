@@ -41,7 +41,7 @@ int fail(ph_scene* s, const std::string& m) {
 int upload_renderer_uniforms_cam(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, const ph::Mat4& cam, const ph::Mat4& teleport,
                                  bool in_subspace);
 
-int upload_renderer_uniforms(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p) {
+ph::Mat4 frame_camera(ph_scene* s, const ph_frame_params* p) {
     double look_at[3] = {s->scene.look_at[0], s->scene.look_at[1], s->scene.look_at[2]};
     double alpha = s->scene.alpha, beta = s->scene.beta, r = s->scene.r;
     if (p->use_camera) {
@@ -50,7 +50,16 @@ int upload_renderer_uniforms(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p)
         beta = p->beta;
         r = p->r;
     }
-    return upload_renderer_uniforms_cam(s, ctx, p, ph::orbit_camera_matrix(look_at, alpha, beta, r), ph::mat_identity(), false);
+    return ph::orbit_camera_matrix(look_at, alpha, beta, r);
+}
+
+// Scene::set_uniforms + SceneRenderer::set_uniforms for one frame of the scene's own (or the given orbit) camera.  The
+// camera goes to the formulas first: send_camera_object_matrix (main.rs:145, 1432-1436) feeds the `Camera` matrix kind.
+int upload_frame_uniforms(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p) {
+    const ph::Mat4 cam = frame_camera(s, p);
+    s->scene.camera_matrix_for_formulas = cam;
+    if (ph_scene_upload_uniforms(s, ctx)) return 1;
+    return upload_renderer_uniforms_cam(s, ctx, p, cam, ph::mat_identity(), false);
 }
 
 int upload_renderer_uniforms_cam(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, const ph::Mat4& cam, const ph::Mat4& teleport,
@@ -112,6 +121,12 @@ int ph_scene_set_time(ph_scene* s, double time, double total_time) {
     if (!s) return 1;
     s->scene.time = time;
     s->scene.total_time = total_time;
+    return 0;
+}
+
+int ph_scene_set_formula_camera(ph_scene* s, const double m16[16]) {
+    if (!s || !m16) return 1;
+    for (int k = 0; k < 16; k++) s->scene.camera_matrix_for_formulas[size_t(k)] = m16[k];
     return 0;
 }
 
@@ -260,8 +275,7 @@ double ph_camera_scale(const double m16[16]) {
 
 int ph_render_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, void* out_host, int rgba8) {
     if (!s || !ctx || !p || !out_host) return 1;
-    if (ph_scene_upload_uniforms(s, ctx)) return 1;
-    if (upload_renderer_uniforms(s, ctx, p)) return 1;
+    if (upload_frame_uniforms(s, ctx, p)) return 1;
     pe_target t = {p->width, p->height, p->height, 0, 1, 1, 1};
     int rc = rgba8 ? pe_render_host_rgba8(ctx, &t, (uint8_t*)out_host) : pe_render_host(ctx, &t, (float*)out_host);
     if (rc) return fail(s, std::string("render failed: ") + pe_last_error(ctx));
@@ -270,8 +284,7 @@ int ph_render_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, void* ou
 
 int ph_render_target(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, const pe_target* target, void* out_device, void* stream) {
     if (!s || !ctx || !p || !target || !out_device) return 1;
-    if (ph_scene_upload_uniforms(s, ctx)) return 1;
-    if (upload_renderer_uniforms(s, ctx, p)) return 1;
+    if (upload_frame_uniforms(s, ctx, p)) return 1;
     if (pe_render(ctx, target, out_device, nullptr, stream)) return fail(s, std::string("render failed: ") + pe_last_error(ctx));
     return 0;
 }
@@ -296,7 +309,7 @@ int ph_render_motion_blur_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params*
             ph_frame_params q = *p;
             q.aa_start = j;                                            // main.rs:1797
             ph_scene_set_time(s, tt * duration_seconds, tt * duration_seconds);   // Scene::update, Dev/Animation stage branch
-            rc = ph_scene_upload_uniforms(s, ctx) || upload_renderer_uniforms(s, ctx, &q) ||
+            rc = upload_frame_uniforms(s, ctx, &q) ||
                  pe_render_rgba8(ctx, &t, sub[size_t(j)], nullptr);   // RGBA8 render target, quantised by the kernel
         }
         if (!rc) rc = pe_average_frames_rgba8(ctx, sub.data(), motion_blur_frames, out8, n, nullptr) ||

@@ -46,6 +46,15 @@ class HostScene:
     def set_value(self, name: str, value: float):
         self._check(self._lib.ph_scene_set_value(self._s, b(name), float(value)))
 
+    def set_formula_camera(self, m16=None):
+        """What the `Camera` matrix kind evaluates to; default: the scene's saved camera (what render_frame sends)."""
+        if m16 is None:
+            cam = self.camera()
+            m = (C.c_double * 16)()
+            self._lib.ph_orbit_camera_matrix((C.c_double * 3)(*cam["look_at"]), cam["alpha"], cam["beta"], cam["r"], m)
+            m16 = list(m)
+        self._check(self._lib.ph_scene_set_formula_camera(self._s, (C.c_double * 16)(*m16)))
+
     def init_stage(self, name: str):
         self._check(self._lib.ph_scene_init_stage(self._s, b(name)))
 

@@ -108,6 +108,7 @@ def test_lerp_matrix_stages_match_oracle_frontend():
         path = f"{REFERENCE}/scenes/{scene}.ron"
         sc = frontend.load_scene(path)
         hs = HostScene.from_file(path)
+        hs.set_formula_camera()
         for stage in hs.stage_names():
             hs.init_stage(stage)
             for tm in (0.0, 0.3, 1.0):
@@ -177,6 +178,7 @@ def test_every_reference_scene_loads_and_evaluates():
         if name == "empty":
             continue
         hs = HostScene.from_file(path)
+        hs.set_formula_camera()                                    # the `Camera` matrix kind = the renderer's camera
         try:
             ir = frontend.scene_ir(frontend.load_scene(path), name)
         except NotImplementedError:
