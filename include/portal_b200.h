@@ -148,6 +148,15 @@ PE_API int pe_render_host_rgba8(pe_ctx* ctx, const pe_target* target, uint8_t* o
 #define PE_PIPELINE_DEPTH 2
 PE_API int pe_submit_host_rgba8(pe_ctx* ctx, const pe_target* target, uint8_t* out_host, uint64_t* ticket);
 PE_API int pe_wait_host(pe_ctx* ctx, uint64_t ticket);
+/* Multi-GPU host delivery without a device-side gather: `target` selects this rank's row strips, `host_frame`
+ * is the WHOLE width x height RGBA8 frame in host memory shared by all ranks (e.g. POSIX shared memory,
+ * page-locked in each process with pe_host_register).  The strips are rendered as RGBA8 and each one is copied
+ * over this GPU's own PCIe link to its rows of the frame; same ticket / pipeline rules as pe_submit_host_rgba8.
+ * When every rank's ticket has completed the frame is whole. */
+PE_API int pe_submit_host_strips_rgba8(pe_ctx* ctx, const pe_target* target, uint8_t* host_frame, uint64_t* ticket);
+/* Page-lock / unlock caller-owned host memory (cudaHostRegister, portable). */
+PE_API int pe_host_register(pe_ctx* ctx, void* p, size_t bytes);
+PE_API int pe_host_unregister(pe_ctx* ctx, void* p);
 /* Page-locked host memory for the readback calls. */
 PE_API int pe_host_malloc(pe_ctx* ctx, size_t bytes, void** out);
 PE_API int pe_host_free(pe_ctx* ctx, void* p);

@@ -78,6 +78,9 @@ def lib() -> C.CDLL:
         "pe_render_rgba8": (i32, [vp, C.POINTER(PeTarget), vp, vp]),
         "pe_submit_host_rgba8": (i32, [vp, C.POINTER(PeTarget), vp, C.POINTER(C.c_uint64)]),
         "pe_wait_host": (i32, [vp, C.c_uint64]),
+        "pe_submit_host_strips_rgba8": (i32, [vp, C.POINTER(PeTarget), vp, C.POINTER(C.c_uint64)]),
+        "pe_host_register": (i32, [vp, vp, C.c_size_t]),
+        "pe_host_unregister": (i32, [vp, vp]),
         "pe_host_malloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),
         "pe_host_free": (i32, [vp, vp]),
         "pe_probe_ray": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32),

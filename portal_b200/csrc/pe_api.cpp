@@ -889,29 +889,58 @@ static bool ensure_pipeline(pe_ctx* c, size_t bytes) {
     return true;
 }
 
-int pe_submit_host_rgba8(pe_ctx* c, const pe_target* t, uint8_t* out_host, uint64_t* ticket) {
+static int submit_host(pe_ctx* c, const pe_target* t, uint8_t* out_host, uint64_t* ticket, bool strips_into_frame) {
     if (!c) return 1;
     if (!out_host || !ticket) return c->fail("pe_submit_host_rgba8: null argument");
     if (!check_target(c, t) || !bind_device(c)) return 1;
-    const size_t n = pe_target_pixels(t);
-    // growing a slot buffer frees the old one: only legal when nothing is in flight
-    for (auto& sl : c->slots)
-        if (sl.bytes < n * 4 && sl.ticket) {
-            if (!cuda_ok(c, cudaEventSynchronize(sl.copied), "pipeline drain")) return 1;
-        }
+    pe_target local = *t;
+    local.full_frame_layout = 0;  // the device slot always holds the compact rows
+    const size_t n = pe_target_pixels(&local);
     if (!ensure_pipeline(c, n * 4)) return 1;
     const uint64_t tk = ++c->next_ticket;
     auto& sl = c->slots[tk % PE_PIPELINE_DEPTH];
     // the slot's previous frame (ticket tk - depth) must have left the device before it is overwritten
     if (sl.ticket && !cuda_ok(c, cudaStreamWaitEvent(c->stream, sl.copied, 0), "pipeline wait")) return 1;
-    if (render_impl(c, t, sl.dev, nullptr, nullptr, true)) return 1;
+    if (n && render_impl(c, &local, sl.dev, nullptr, nullptr, true)) return 1;
     if (!cuda_ok(c, cudaEventRecord(sl.rendered, c->stream), "event record") ||
-        !cuda_ok(c, cudaStreamWaitEvent(c->copy_stream, sl.rendered, 0), "pipeline wait") ||
-        !cuda_ok(c, cudaMemcpyAsync(out_host, sl.dev, n * 4, cudaMemcpyDeviceToHost, c->copy_stream), "D2H copy") ||
-        !cuda_ok(c, cudaEventRecord(sl.copied, c->copy_stream), "event record")) return 1;
+        !cuda_ok(c, cudaStreamWaitEvent(c->copy_stream, sl.rendered, 0), "pipeline wait")) return 1;
+    if (!strips_into_frame) {
+        if (n && !cuda_ok(c, cudaMemcpyAsync(out_host, sl.dev, n * 4, cudaMemcpyDeviceToHost, c->copy_stream), "D2H copy")) return 1;
+    } else {
+        // strip k of this rank = global strip strip_first + k * strip_step: contiguous rows of the row-major frame
+        const size_t row_bytes = size_t(t->width) * 4;
+        for (int k = 0; k < t->n_strips; k++) {
+            const int row0 = (t->strip_first + k * t->strip_step) * t->strip_rows;
+            if (row0 >= t->height) break;
+            const int rows = row0 + t->strip_rows <= t->height ? t->strip_rows : t->height - row0;
+            if (!cuda_ok(c, cudaMemcpyAsync(out_host + size_t(row0) * row_bytes, (const uint8_t*)sl.dev + size_t(k) * size_t(t->strip_rows) * row_bytes,
+                                            size_t(rows) * row_bytes, cudaMemcpyDeviceToHost, c->copy_stream), "D2H strip copy")) return 1;
+        }
+    }
+    if (!cuda_ok(c, cudaEventRecord(sl.copied, c->copy_stream), "event record")) return 1;
     sl.ticket = tk;
     *ticket = tk;
     return 0;
+}
+
+int pe_submit_host_rgba8(pe_ctx* c, const pe_target* t, uint8_t* out_host, uint64_t* ticket) {
+    return submit_host(c, t, out_host, ticket, false);
+}
+
+int pe_submit_host_strips_rgba8(pe_ctx* c, const pe_target* t, uint8_t* host_frame, uint64_t* ticket) {
+    return submit_host(c, t, host_frame, ticket, true);
+}
+
+int pe_host_register(pe_ctx* c, void* p, size_t bytes) {
+    if (!c || !p || bytes == 0) return 1;
+    if (!bind_device(c)) return 1;
+    return cuda_ok(c, cudaHostRegister(p, bytes, cudaHostRegisterPortable), "cudaHostRegister") ? 0 : 1;
+}
+
+int pe_host_unregister(pe_ctx* c, void* p) {
+    if (!c || !p) return 1;
+    if (!bind_device(c)) return 1;
+    return cuda_ok(c, cudaHostUnregister(p), "cudaHostUnregister") ? 0 : 1;
 }
 
 int pe_wait_host(pe_ctx* c, uint64_t ticket) {

@@ -17,6 +17,7 @@ on CPU); rendering itself only exists on CUDA.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -198,3 +199,103 @@ class FrameSharder:
         for p in self._owned:
             lib.pe_device_free(ctx, p)
         self._owned = []
+
+
+class HostFrameSharder:
+    """Multi-GPU frames delivered to HOST memory with no device-side gather and no collective.
+
+    All ranks map one shared-memory segment: a 4 KiB header of counters and a ring of DEPTH whole RGBA8
+    frames.  Each rank page-locks the mapping, renders its cyclic row strips as RGBA8 and copies every strip
+    over ITS OWN PCIe link straight to its rows of frame f's slot (pe_submit_host_strips_rgba8), so the host
+    sees N links' worth of bandwidth and NVLink carries nothing.  Hand-off is by counters in the header:
+        done[r]   <- rank r, after its copies of frame f completed (pe_wait_host): f + 1
+        consumed  <- rank 0, after the consumer is finished with frame f: f + 1
+    A rank starts frame f only when consumed >= f + 1 - DEPTH (its slot is free again).
+    """
+
+    DEPTH = 3
+    HEADER = 4096
+
+    def __init__(self, renderer, width: int, height: int, rank: int, world: int, strip_rows: int = STRIP_ROWS, name: str | None = None):
+        import mmap
+        import numpy as np
+        self.r, self.w, self.h, self.rank, self.world = renderer, width, height, rank, world
+        self.target = make_target(width, height, rank, world, strip_rows, full_frame=False)
+        self.frame_bytes = width * height * 4
+        size = self.HEADER + self.DEPTH * self.frame_bytes
+        if name is None:
+            import torch.distributed as dist
+            box = [f"portal_b200_{os.getpid()}" if rank == 0 else None]
+            if world > 1:
+                dist.broadcast_object_list(box, src=0)
+            name = box[0]
+        self.path = f"/dev/shm/{name}"
+        if rank == 0:
+            fd = os.open(self.path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+            os.ftruncate(fd, size)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        if rank != 0:
+            fd = os.open(self.path, os.O_RDWR)
+        self._mm = mmap.mmap(fd, size)
+        os.close(fd)
+        self._bytes = np.frombuffer(self._mm, dtype=np.uint8)
+        self._base = self._bytes.ctypes.data
+        self._done = self._bytes[:8 * 64].view(np.uint64)         # done[r] at word r
+        self._consumed = self._bytes[1024:1032].view(np.uint64)
+        renderer._check(renderer._lib.pe_host_register(renderer._ctx, self._base, size))
+        self._tickets = {}
+        self.frame_no = 0
+
+    def slot(self, f: int):
+        """numpy view [h, w, 4] of frame f's slot."""
+        o = self.HEADER + (f % self.DEPTH) * self.frame_bytes
+        return self._bytes[o:o + self.frame_bytes].reshape(self.h, self.w, 4)
+
+    def submit(self) -> int:
+        """Queue this rank's strips of the next frame (uniforms as currently set on the renderer); returns f."""
+        f = self.frame_no
+        self.frame_no += 1
+        need = f + 1 - self.DEPTH
+        while need > 0 and int(self._consumed[0]) < need:
+            pass
+        self.r.set_uniforms()
+        ticket = C.c_uint64()
+        self.r._check(self.r._lib.pe_submit_host_strips_rgba8(self.r._ctx, C.byref(self.target),
+                                                              self._base + self.HEADER + (f % self.DEPTH) * self.frame_bytes, C.byref(ticket)))
+        self._tickets[f] = ticket.value
+        return f
+
+    def complete(self, f: int):
+        """Block until this rank's part of frame f is in host memory, then publish it."""
+        self.r._check(self.r._lib.pe_wait_host(self.r._ctx, self._tickets.pop(f)))
+        self._done[self.rank] = f + 1
+
+    def wait_frame(self, f: int):
+        """Rank 0: block until every rank's part of frame f has landed; returns the frame (view of the slot)."""
+        for rk in range(self.world):
+            while int(self._done[rk]) < f + 1:
+                pass
+        return self.slot(f)
+
+    def release(self, f: int):
+        """Rank 0: the consumer is finished with frame f; its slot may be overwritten."""
+        self._consumed[0] = f + 1
+
+    def close(self):
+        if getattr(self, "_mm", None) is None:
+            return
+        self.r._lib.pe_sync(self.r._ctx)
+        self.r._lib.pe_host_unregister(self.r._ctx, self._base)
+        self._done = self._consumed = self._bytes = None
+        try:
+            self._mm.close()
+        except BufferError:
+            pass
+        self._mm = None
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass

@@ -89,3 +89,84 @@ def test_gloo_gather_of_strips(world, h, tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for rank, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"RANK_OK {rank}" in o, o[-2000:]
+
+
+HOST_WORKER = textwrap.dedent("""
+    import ctypes as C, os, sys
+    import numpy as np
+    import torch.distributed as dist
+    sys.path.insert(0, {root!r})
+    from portal_b200 import distributed as D
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo")
+    h, w, s = {h}, {w}, 16
+
+    class FakeLib:                       # stands in for the C ABI: "renders" strips whose bytes name (frame, row, rank)
+        def __init__(self): self.frame = 0; self.tickets = 0
+        def pe_host_register(self, ctx, p, n): return 0
+        def pe_host_unregister(self, ctx, p): return 0
+        def pe_sync(self, ctx): return 0
+        def pe_wait_host(self, ctx, t): return 0
+        def pe_submit_host_strips_rgba8(self, ctx, target, host_frame, ticket):
+            t = target._obj
+            for k in range(t.n_strips):
+                row0 = (t.strip_first + k * t.strip_step) * t.strip_rows
+                rows = max(0, min(t.strip_rows, t.height - row0))
+                px = np.zeros((rows, t.width, 4), np.uint8)
+                px[..., 0] = self.frame
+                px[..., 1] = (np.arange(row0, row0 + rows) % 251)[:, None]
+                px[..., 2] = rank
+                px[..., 3] = 255
+                C.memmove(host_frame + row0 * t.width * 4, px.ctypes.data, px.nbytes)
+            self.frame += 1; self.tickets += 1
+            ticket._obj.value = self.tickets
+            return 0
+
+    class FakeRenderer:
+        def __init__(self): self._lib = FakeLib(); self._ctx = None
+        def _check(self, rc): assert rc == 0
+        def set_uniforms(self): pass
+
+    hfs = D.HostFrameSharder(FakeRenderer(), w, h, rank, world, s)
+    frames, prev = 8, None                       # more frames than ring slots: exercises the consumed counter
+
+    def finish(f):
+        hfs.complete(f)
+        if rank == 0:
+            fr = hfs.wait_frame(f)
+            assert (fr[..., 0] == f).all() and (fr[..., 3] == 255).all()
+            assert np.array_equal(fr[:, 0, 1], np.arange(h) % 251)
+            assert np.array_equal(fr[:, 0, 2], (np.arange(h) // s) % world)
+            hfs.release(f)
+
+    for f in range(frames):
+        assert hfs.submit() == f
+        if prev is not None:
+            finish(prev)
+        prev = f
+    finish(prev)
+    dist.barrier()
+    hfs.close()
+    assert rank != 0 or not os.path.exists(hfs.path)
+    dist.destroy_process_group()
+    print("RANK_OK", rank)
+""")
+
+
+@pytest.mark.parametrize("world,h", [(2, 360), (3, 100)])
+def test_gloo_host_frame_ring(world, h, tmp_path):
+    """HostFrameSharder's shared-memory ring and counters with a stand-in for the C ABI (the real one needs GPUs:
+    tools/check_multigpu.py)."""
+    script = tmp_path / "worker.py"
+    script.write_text(HOST_WORKER.format(root=ROOT, h=h, w=24))
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for rank, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"RANK_OK {rank}" in o, o[-2000:]

@@ -25,4 +25,4 @@ def test_sharded_frame_equals_single_gpu_frame():
            "--master-port", str(port), os.path.join(ROOT, "tools", "check_multigpu.py"), "portal_in_portal", "1920", "1080", "40"]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
-    assert "gather" in p.stdout and "p2p" in p.stdout and "False" not in p.stdout
+    assert "gather" in p.stdout and "p2p" in p.stdout and "host strips" in p.stdout and "False" not in p.stdout

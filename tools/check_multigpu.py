@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Run under torchrun (one rank per GPU): renders one frame sharded by cyclic row strips in both
-assembly modes (NCCL gather, and kernels storing straight into rank 0's frame over NVLink) and
-checks on rank 0 that the assembled frame is bit-identical to the single-GPU render."""
+device-side assembly modes (NCCL gather, and kernels storing straight into rank 0's frame over NVLink)
+and through the host-delivery path (RGBA8 strips over every rank's PCIe link into one shared host frame),
+and checks on rank 0 that each assembled frame is bit-identical to the single-GPU render."""
 import ctypes as C
 import os
 import sys
@@ -13,7 +14,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from portal_b200.distributed import FrameSharder  # noqa: E402
+from portal_b200.distributed import FrameSharder, HostFrameSharder  # noqa: E402
 from portal_b200.renderer import SceneRenderer, load_scene_ir, load_textures  # noqa: E402
 
 
@@ -46,6 +47,33 @@ def main():
             ok = ok and same
         dist.barrier()
         sh.close()
+    # host delivery: RGBA8 strips over every rank's PCIe link into one shared page-locked frame, 5 frames through a
+    # ring of 3 with a moving camera; rank 0 checks each against its own single-GPU RGBA8 render
+    cam = r.cam
+    hfs = HostFrameSharder(r, w, h, rank, world)
+    frames, prev, same = 5, None, True
+
+    def check(f):
+        hfs.complete(f)
+        if rank == 0:
+            got = hfs.wait_frame(f).copy()
+            hfs.release(f)
+            r.set_cam(cam["look_at"], cam["alpha"] + 0.05 * f, cam["beta"], cam["r"])
+            return np.array_equal(got, r.render_host_rgba8(w, h))
+        return True
+
+    for f in range(frames):
+        r.set_cam(cam["look_at"], cam["alpha"] + 0.05 * f, cam["beta"], cam["r"])
+        hfs.submit()
+        if prev is not None:
+            same = check(prev) and same
+        prev = f
+    same = check(prev) and same
+    dist.barrier()
+    hfs.close()
+    if rank == 0:
+        print(f"multi-GPU host strips: world {world} {scene} {w}x{h} x {frames} frames -> identical to single GPU: {same}", flush=True)
+        ok = ok and same
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
