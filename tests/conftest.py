@@ -47,3 +47,10 @@ def _built_library():
     from portal_b200 import build
     build.build()
     return True
+
+
+@pytest.fixture(scope="session")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch

@@ -17,13 +17,6 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4  # BASELINE.json north_star: "within 1e-4 per channel"
 
 
-@pytest.fixture(scope="module")
-def torch_cuda():
-    import torch
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
-    return torch
-
-
 def _renderer(scene, **kw):
     from portal_b200.renderer import SceneRenderer
     r = SceneRenderer(load_ir(scene), textures=load_tex(scene), device=0, **kw)
