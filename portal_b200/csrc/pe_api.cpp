@@ -907,15 +907,22 @@ static int submit_host(pe_ctx* c, const pe_target* t, uint8_t* out_host, uint64_
     if (!strips_into_frame) {
         if (n && !cuda_ok(c, cudaMemcpyAsync(out_host, sl.dev, n * 4, cudaMemcpyDeviceToHost, c->copy_stream), "D2H copy")) return 1;
     } else {
-        // strip k of this rank = global strip strip_first + k * strip_step: contiguous rows of the row-major frame
-        const size_t row_bytes = size_t(t->width) * 4;
+        // strip k of this rank = global strip strip_first + k * strip_step: contiguous rows of the row-major frame,
+        // world strips apart from strip k + 1 -> ONE pitched copy for the whole strips (+ one for a ragged last strip)
+        const size_t row_bytes = size_t(t->width) * 4, strip_bytes = row_bytes * size_t(t->strip_rows);
+        int full = 0, ragged_rows = 0;
         for (int k = 0; k < t->n_strips; k++) {
             const int row0 = (t->strip_first + k * t->strip_step) * t->strip_rows;
             if (row0 >= t->height) break;
-            const int rows = row0 + t->strip_rows <= t->height ? t->strip_rows : t->height - row0;
-            if (!cuda_ok(c, cudaMemcpyAsync(out_host + size_t(row0) * row_bytes, (const uint8_t*)sl.dev + size_t(k) * size_t(t->strip_rows) * row_bytes,
-                                            size_t(rows) * row_bytes, cudaMemcpyDeviceToHost, c->copy_stream), "D2H strip copy")) return 1;
+            if (row0 + t->strip_rows <= t->height) full++;
+            else ragged_rows = t->height - row0;
         }
+        uint8_t* dst0 = out_host + size_t(t->strip_first) * strip_bytes;
+        if (full && !cuda_ok(c, cudaMemcpy2DAsync(dst0, strip_bytes * size_t(t->strip_step), sl.dev, strip_bytes, strip_bytes, size_t(full),
+                                                  cudaMemcpyDeviceToHost, c->copy_stream), "D2H strip copy")) return 1;
+        if (ragged_rows && !cuda_ok(c, cudaMemcpyAsync(dst0 + size_t(full) * strip_bytes * size_t(t->strip_step),
+                                                       (const uint8_t*)sl.dev + size_t(full) * strip_bytes, size_t(ragged_rows) * row_bytes,
+                                                       cudaMemcpyDeviceToHost, c->copy_stream), "D2H strip copy")) return 1;
     }
     if (!cuda_ok(c, cudaEventRecord(sl.copied, c->copy_stream), "event record")) return 1;
     sl.ticket = tk;

@@ -287,6 +287,21 @@ def test_in_kernel_rgba8_and_pipelined_readback(torch_cuda):
         prev = (tk, i)
     r.wait_host(prev[0])
     assert np.array_equal(views[6 % 2], want[6])
+    # pe_submit_host_strips_rgba8: three "ranks" (one context here) deliver their cyclic strips into one host frame;
+    # 368 rows = 23 strips of 16, so the ranks own 8 / 8 / 7 strips; then a ragged height (last strip 8 rows)
+    for hh in (h, h - 8):
+        r.set_cam(cam["look_at"], cam["alpha"], cam["beta"], cam["r"])
+        whole = r.render_host_rgba8(w, hh)
+        frame = r.host_malloc(w * hh * 4)
+        fv = np.ctypeslib.as_array((C.c_uint8 * (w * hh * 4)).from_address(frame)).reshape(hh, w, 4)
+        fv[:] = 7
+        for rank in range(3):
+            tgt = r.strip_target(w, hh, 16, rank, 3)
+            tk = C.c_uint64()
+            r._check(r._lib.pe_submit_host_strips_rgba8(r._ctx, C.byref(tgt), frame, C.byref(tk)))
+            r.wait_host(tk.value)
+        assert np.array_equal(fv, whole)
+        r.host_free(frame)
     r.wait_host(1)                                   # an old ticket is already complete
     with pytest.raises(Exception, match="unknown ticket"):
         r.wait_host(99)
