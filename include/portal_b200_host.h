@@ -121,6 +121,13 @@ PE_API int ph_player_update(ph_player* p, double time_seconds);
  * `_camera_scale`; orbit[6] = look_at xyz, alpha, beta, r; times[2] = formula time, total_time. */
 PE_API int ph_player_camera(ph_player* p, double camera16[16], double camera_mul_inv16[16], int32_t* in_subspace,
                             double* scale, double orbit[6], double times[2], int64_t* n_probes);
+/* Side-by-side stereo (SceneRenderer::draw_side_by_side, eye_distance 0.07, swap_eyes): with it on, update()
+ * also places the two eye cameras (teleport_eye_matrices, src/main.rs:1121-1172) -- each eye is carried through
+ * a portal that lies between it and the camera -- and the render calls send them with `_draw_side_by_side`.
+ * The caller doubles the frame width, as `render --stereo-image` does (src/main.rs:2809-2816). */
+PE_API int ph_player_set_stereo(ph_player* p, int draw_side_by_side, double eye_distance, int swap_eyes);
+PE_API int ph_player_eyes(ph_player* p, double left16[16], double right16[16], int32_t* left_in_subspace,
+                          int32_t* right_in_subspace);
 /* Real animations in file order: count, then name and duration of entry k. */
 PE_API int ph_scene_animation_count(ph_scene* s);
 PE_API int ph_scene_animation(ph_scene* s, int k, const char** name, double* duration);

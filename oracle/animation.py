@@ -373,6 +373,12 @@ class Player:
         self.cam.prev_cam_pos = self.cam.get_cam_pos()
         self.memory = {"CurrentCam": None, "OriginalCam": self.cam.get_calculated_cam()}
         self.n_probes = 0
+        # stereo (main.rs:1027-1030): eye cameras are placed by teleport_eye_matrices when a stereo mode is on
+        self.draw_side_by_side = False
+        self.eye_distance = 0.07
+        self.swap_eyes = False
+        self.left_eye_matrix, self.right_eye_matrix = F.mat_identity(), F.mat_identity()
+        self.left_eye_in_subspace = self.right_eye_in_subspace = False
 
     # -- render_frame's option handling (main.rs:2900-2926)
     def init_stage(self, name):
@@ -436,6 +442,38 @@ class Player:
         else:
             cam.prev_cam_pos = cam_pos
 
+    def teleport_eye_matrices(self):
+        """main.rs:1121-1172: each eye = the camera shifted along its x axis; if a portal lies between the camera and
+        the eye, the eye's matrix is carried through it like the camera's would be."""
+        cam = self.cam
+        if not (self.draw_side_by_side and cam.allow_teleport):
+            return
+        ed = -self.eye_distance if self.swap_eyes else self.eye_distance
+
+        def one(eye_x):
+            start = cam.get_cam_pos()
+            m = cam.get_matrix()
+            dp = F.mat_mul_vec(m, [eye_x, 0.0, 0.0, 1.0])[:3]
+            tr = F.mat_identity()
+            tr[3] = [dp[0] - start[0], dp[1] - start[1], dp[2] - start[2], 1.0]
+            matrix, sub = F.mat_mul(tr, m), cam.in_subspace
+            if self.probe is None:
+                return matrix, sub
+            teleported, _, change_subspace = self._probe(start, dp)
+            if teleported is not None:
+                for dx in (0.001, 0.0001, 0.00001, 0.000001):
+                    mm = self.teleport_matrix(matrix, start, dp, teleported, dx)
+                    if mm is None:
+                        continue
+                    matrix = mm
+                    if change_subspace:
+                        sub = not cam.in_subspace
+                    break
+            return matrix, sub
+
+        self.left_eye_matrix, self.left_eye_in_subspace = one(-ed)
+        self.right_eye_matrix, self.right_eye_in_subspace = one(ed)
+
     def update(self, time: float):
         mem = self.memory
         self.anim.update(mem, time)
@@ -478,6 +516,7 @@ class Player:
                 cam.do_not_teleport_one_frame = True
         if self.cam.get_matrix() != self.prev_cam.get_matrix():
             self.teleport_camera(self.prev_cam.clone())
+        self.teleport_eye_matrices()
         self.prev_cam = self.cam.clone()
         self.scene.camera_matrix = self.cam.get_matrix()
 
@@ -486,6 +525,10 @@ class Player:
         m = self.cam.get_matrix()
         return {"camera": [x for col in m for x in col],
                 "camera_mul_inv": [x for col in F.mat_inverse(self.cam.teleport_matrix) for x in col],
+                "left_eye": [x for col in self.left_eye_matrix for x in col],
+                "right_eye": [x for col in self.right_eye_matrix for x in col],
+                "left_eye_in_subspace": bool(self.left_eye_in_subspace),
+                "right_eye_in_subspace": bool(self.right_eye_in_subspace),
                 "in_subspace": bool(self.cam.in_subspace), "scale": F.camera_scale(m),
                 "look_at": list(self.cam.look_at), "alpha": self.cam.alpha, "beta": self.cam.beta, "r": self.cam.r,
                 "time": self.scene.time, "total_time": self.scene.total_time}

@@ -301,6 +301,40 @@ bool Player::teleport_camera(const OrbitCam& prev) {  // main.rs:1217-1264
     return true;
 }
 
+bool Player::teleport_eye_matrices() {  // main.rs:1121-1172
+    if (!(draw_side_by_side && cam.allow_teleport)) return true;
+    const double ed = swap_eyes ? -eye_distance : eye_distance;
+    auto one = [&](double eye_x, Mat4& matrix, bool& sub) -> bool {
+        double start[3], p[4];
+        cam.get_cam_pos(start);
+        const Mat4 m = cam.get_matrix();
+        const double ev[4] = {eye_x, 0.0, 0.0, 1.0};
+        mat_mul_vec(m, ev, p);
+        const double dp[3] = {p[0], p[1], p[2]};
+        Mat4 tr = mat_identity();
+        tr[12] = dp[0] - start[0]; tr[13] = dp[1] - start[1]; tr[14] = dp[2] - start[2];
+        matrix = mat_mul(tr, m);
+        sub = cam.in_subspace;
+        if (!probe) return true;
+        double teleported[3];
+        bool have, enc, chg;
+        if (!run_probe(start, dp, teleported, have, enc, chg)) return false;
+        if (have) {
+            for (double dx : {0.001, 0.0001, 0.00001, 0.000001}) {
+                Mat4 mm;
+                bool ok;
+                if (!teleport_matrix(matrix, start, dp, teleported, dx, mm, ok)) return false;
+                if (!ok) continue;
+                matrix = mm;
+                if (chg) sub = !cam.in_subspace;
+                break;
+            }
+        }
+        return true;
+    };
+    return one(-ed, left_eye_matrix, left_eye_in_subspace) && one(ed, right_eye_matrix, right_eye_in_subspace);
+}
+
 bool Player::update(double time) {  // SceneRenderer::update, main.rs:1430-1543
     if (!scene_update(time)) return false;
     sc.camera_matrix_for_formulas = cam.get_matrix();  // send_camera_object_matrix (default true)
@@ -345,6 +379,7 @@ bool Player::update(double time) {  // SceneRenderer::update, main.rs:1430-1543
         const OrbitCam prev = prev_cam;
         if (!teleport_camera(prev)) return false;
     }
+    if (!teleport_eye_matrices()) return false;
     prev_cam = cam;
     sc.camera_matrix_for_formulas = cam.get_matrix();
     return true;

@@ -59,6 +59,12 @@ struct Player {
     bool run_animations = false;
     double prev_t_raw = 0.0;
     OrbitCam cam, prev_cam;
+    // stereo (main.rs:1027-1030, teleport_eye_matrices :1121-1172)
+    bool draw_side_by_side = false, swap_eyes = false;
+    double eye_distance = 0.07;
+    Mat4 left_eye_matrix = mat_identity(), right_eye_matrix = mat_identity();
+    bool left_eye_in_subspace = false, right_eye_in_subspace = false;
+    bool teleport_eye_matrices();
 
     bool init_stage(const StageRef& stage);
     bool init_stage_by_name(const std::string& name);

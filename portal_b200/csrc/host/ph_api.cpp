@@ -408,6 +408,40 @@ int ph_player_camera(ph_player* p, double camera16[16], double inv16[16], int32_
     return 0;
 }
 
+int ph_player_set_stereo(ph_player* p, int draw_side_by_side, double eye_distance, int swap_eyes) {
+    if (!p) return 1;
+    p->player.draw_side_by_side = draw_side_by_side != 0;
+    p->player.eye_distance = eye_distance;
+    p->player.swap_eyes = swap_eyes != 0;
+    return 0;
+}
+
+int ph_player_eyes(ph_player* p, double left16[16], double right16[16], int32_t* left_in_subspace, int32_t* right_in_subspace) {
+    if (!p) return 1;
+    if (left16) for (int k = 0; k < 16; k++) left16[k] = p->player.left_eye_matrix[size_t(k)];
+    if (right16) for (int k = 0; k < 16; k++) right16[k] = p->player.right_eye_matrix[size_t(k)];
+    if (left_in_subspace) *left_in_subspace = p->player.left_eye_in_subspace ? 1 : 0;
+    if (right_in_subspace) *right_in_subspace = p->player.right_eye_in_subspace ? 1 : 0;
+    return 0;
+}
+
+// the stereo part of SceneRenderer::set_uniforms (main.rs:1272-1283, 1306-1307, 1343-1350)
+static int upload_stereo_uniforms(ph_player* pl, pe_ctx* ctx) {
+    const ph::Player& P = pl->player;
+    float l32[16], r32[16];
+    for (int k = 0; k < 16; k++) { l32[k] = float(P.left_eye_matrix[size_t(k)]); r32[k] = float(P.right_eye_matrix[size_t(k)]); }
+    int rc = 0;
+    rc |= pe_set_uniform_mat4(ctx, "_camera_left_eye", l32);
+    rc |= pe_set_uniform_mat4(ctx, "_camera_right_eye", r32);
+    rc |= pe_set_uniform_i32(ctx, "_left_eye_in_subspace", P.left_eye_in_subspace ? 1 : 0);
+    rc |= pe_set_uniform_i32(ctx, "_right_eye_in_subspace", P.right_eye_in_subspace ? 1 : 0);
+    rc |= pe_set_uniform_f32(ctx, "_left_eye_scale", float(ph::camera_scale(P.left_eye_matrix)));
+    rc |= pe_set_uniform_f32(ctx, "_right_eye_scale", float(ph::camera_scale(P.right_eye_matrix)));
+    rc |= pe_set_uniform_i32(ctx, "_draw_side_by_side", P.draw_side_by_side ? 1 : 0);
+    if (rc) return pfail(pl, std::string("stereo uniform upload failed: ") + pe_last_error(ctx));
+    return 0;
+}
+
 int ph_scene_animation_count(ph_scene* s) { return s ? int(s->scene.animations.size()) : -1; }
 int ph_scene_animation(ph_scene* s, int k, const char** name, double* duration) {
     if (!s || k < 0 || k >= int(s->scene.animations.size())) return 1;
@@ -429,6 +463,7 @@ int ph_player_render_frame(ph_player* pl, pe_ctx* ctx, const ph_frame_params* p,
     const ph::OrbitCam& c = pl->player.cam;
     if (ph_scene_upload_uniforms(pl->s, ctx)) return pfail(pl, pl->s->err);
     if (upload_renderer_uniforms_cam(pl->s, ctx, p, c.get_matrix(), c.teleport_matrix, c.in_subspace)) return pfail(pl, pl->s->err);
+    if (upload_stereo_uniforms(pl, ctx)) return 1;
     pe_target t = {p->width, p->height, p->height, 0, 1, 1, 1};
     int rc = rgba8 ? pe_render_host_rgba8(ctx, &t, (uint8_t*)out_host) : pe_render_host(ctx, &t, (float*)out_host);
     if (rc) return pfail(pl, std::string("render failed: ") + pe_last_error(ctx));
@@ -456,6 +491,8 @@ int ph_player_render_motion_blur_frame(ph_player* pl, pe_ctx* ctx, const ph_fram
         const ph::OrbitCam& c = pl->player.cam;
         if (ph_scene_upload_uniforms(pl->s, ctx) || upload_renderer_uniforms_cam(pl->s, ctx, &q, c.get_matrix(), c.teleport_matrix, c.in_subspace)) {
             pl->err = pl->s->err;
+            rc = 1;
+        } else if (upload_stereo_uniforms(pl, ctx)) {
             rc = 1;
         } else if (pe_render_rgba8(ctx, &t, sub[size_t(j)], nullptr)) {
             pl->err = std::string("render failed: ") + pe_last_error(ctx);

@@ -157,11 +157,18 @@ class HostPlayer:
     def update(self, time_seconds: float):
         self._check(self._lib.ph_player_update(self._p, float(time_seconds)))
 
+    def set_stereo(self, draw_side_by_side: bool, eye_distance: float = 0.07, swap_eyes: bool = False):
+        self._check(self._lib.ph_player_set_stereo(self._p, int(draw_side_by_side), float(eye_distance), int(swap_eyes)))
+
     def camera_state(self) -> dict:
         cam, inv, orbit, times = (C.c_double * 16)(), (C.c_double * 16)(), (C.c_double * 6)(), (C.c_double * 2)()
         sub, scale, n = C.c_int32(), C.c_double(), C.c_int64()
         self._check(self._lib.ph_player_camera(self._p, cam, inv, C.byref(sub), C.byref(scale), orbit, times, C.byref(n)))
+        le, re, ls, rs = (C.c_double * 16)(), (C.c_double * 16)(), C.c_int32(), C.c_int32()
+        self._check(self._lib.ph_player_eyes(self._p, le, re, C.byref(ls), C.byref(rs)))
         return {"camera": list(cam), "camera_mul_inv": list(inv), "in_subspace": bool(sub.value), "scale": scale.value,
+                "left_eye": list(le), "right_eye": list(re), "left_eye_in_subspace": bool(ls.value),
+                "right_eye_in_subspace": bool(rs.value),
                 "look_at": list(orbit[:3]), "alpha": orbit[3], "beta": orbit[4], "r": orbit[5],
                 "time": times[0], "total_time": times[1], "n_probes": n.value}
 

@@ -259,11 +259,11 @@ class SceneRenderer:
 
     def eye_matrices(self):
         """Eye cameras of teleport_eye_matrices (main.rs:1121-1139) when no portal lies between the eyes:
-        DMat4::from_translation(C * (+-eye_distance/2, 0, 0, 1) - cam_pos) * C."""
+        DMat4::from_translation(C * (+-eye_distance, 0, 0, 1) - cam_pos) * C."""
         c = np.asarray(self.camera_matrix, dtype=np.float64).reshape(4, 4)  # rows = columns of the matrix
         pos = c[3, :3]
         out = []
-        for sx in (-0.5, 0.5):
+        for sx in (-1.0, 1.0):
             v = np.array([sx * self.eye_distance, 0.0, 0.0, 1.0])
             p = v @ c                       # C * v with column-major storage
             t = np.eye(4)

@@ -42,7 +42,7 @@ def _pair(path):
 def test_fixture_animations_match_oracle_player():
     _, _, hs0, hp0 = _pair(FIXTURE)
     assert hp0.animations() == ANIMS
-    assert sorted(hp0.camera_names()) == ["at_ball", "before_gate", "behind_gate", "wide"]
+    assert sorted(hp0.camera_names()) == ["at_ball", "before_gate", "behind_gate", "beside_gate", "wide"]
     for name, _ in ANIMS:
         s, p, hs, hp = _pair(FIXTURE)
         p.init_animation(name)
@@ -140,6 +140,39 @@ def test_camera_teleports_through_the_gate_on_the_oracle():
     assert np.linalg.norm(after - before) > 2.0                                    # the eye is now at the other portal
     assert np.allclose(np.asarray(cams[13]["camera_mul_inv"]).reshape(4, 4).T @ np.asarray(p.cam.teleport_matrix).reshape(4, 4).T,
                        np.eye(4), atol=1e-12)
+
+
+def test_stereo_eye_is_carried_through_the_gate_on_the_oracle():
+    """teleport_eye_matrices (main.rs:1121-1172): camera "beside_gate" stands 0.1 in front of the gate with its x axis
+    along the gate's normal; with eye_distance 0.25 the left eye lies behind the gate plane and must come out of
+    portal_b, the right eye is a plain translation.  Without a probe both eyes are plain translations (C++ == oracle)."""
+    from oracle import frontend
+    from oracle.animation import Player
+    from oracle.runner import Oracle
+    orc = Oracle(frontend.scene_ir(frontend.load_scene(FIXTURE), "two_spheres"), variant="strict")
+    s = frontend.load_scene(FIXTURE)
+    p = Player(s, probe=_oracle_probe(orc))
+    p.draw_side_by_side, p.eye_distance = True, 0.25
+    p.select_camera("beside_gate")
+    p.update(0.0)
+    cs = p.camera_state()
+    cam, left, right = (np.asarray(cs[k]).reshape(4, 4) for k in ("camera", "left_eye", "right_eye"))
+    assert p.n_probes == 2 + 3
+    assert np.allclose(right[3, :3], cam[3, :3] + 0.25 * cam[0, :3], atol=1e-15) and np.array_equal(right[:3], cam[:3])
+    a, b = s.get_matrix(s.matrix_by_name["portal_a"]), s.get_matrix(s.matrix_by_name["portal_b"])
+    t = np.asarray(frontend.mat_mul(b, frontend.mat_inverse(a)))                    # rows = columns (column-major)
+    plain_left = np.append(cam[3, :3] - 0.25 * cam[0, :3], 1.0)
+    assert np.allclose(left[3, :3], (plain_left @ t)[:3], atol=1e-4)
+    assert np.allclose(left[:3, :3], cam[:3, :3] @ t[:3, :3], atol=2e-3)
+    # no probe attached: both players place the eyes by translation only, identically
+    s2, p2, hs2, hp2 = _pair(FIXTURE)
+    p2.draw_side_by_side, p2.eye_distance = True, 0.25
+    hp2.set_stereo(True, 0.25)
+    for pl in (p2, hp2):
+        pl.select_camera("beside_gate")
+        pl.update(0.0)
+    _assert_same_state(p2, hp2, s2, hs2, "stereo without probe")
+    assert np.allclose(np.asarray(hp2.camera_state()["left_eye"]).reshape(4, 4)[3, :3], plain_left[:3], atol=1e-15)
 
 
 def _oracle_probe(orc):
@@ -251,3 +284,35 @@ def test_cli_render_frame_animation_and_render_loop(torch_cuda, tmp_path):
         assert raw.startswith(b"P6\n96 54\n255\n")
         got = np.frombuffer(raw[len(b"P6\n96 54\n255\n"):], dtype=np.uint8).reshape(54, 96, 3)
         assert np.array_equal(got, want[..., :3])
+
+
+@pytest.mark.gpu
+def test_stereo_frame_through_the_gate_on_the_gpu(torch_cuda):
+    """Eye placement with pe_probe_ray == the oracle-driven player's, bit for bit; the side-by-side frame rendered
+    with those eye cameras equals the oracle's frame."""
+    from oracle import frontend
+    from oracle.animation import Player
+    from oracle.runner import Oracle
+    orc = Oracle(frontend.scene_ir(frontend.load_scene(FIXTURE), "two_spheres"), variant="strict")
+    s = frontend.load_scene(FIXTURE)
+    p = Player(s, probe=_oracle_probe(orc))
+    p.draw_side_by_side, p.eye_distance = True, 0.25
+    hs = HostScene.from_file(FIXTURE)
+    hr = HostRenderer(hs)
+    hp = HostPlayer(hs, hr)
+    hp.set_stereo(True, 0.25)
+    for pl in (p, hp):
+        pl.select_camera("beside_gate")
+        pl.update(0.0)
+    a, b = p.camera_state(), hp.camera_state()
+    for key in a:
+        assert _same(a[key], b[key]), key
+    assert b["n_probes"] == 5
+    orc.set_uniforms({k: v for k, (_, v) in s.uniform_table().items()})
+    want = orc.render(256, 72, 12, camera=a["camera"], camera_scale=a["scale"], camera_mul_inv=a["camera_mul_inv"],
+                      camera_in_subspace=int(a["in_subspace"]), draw_side_by_side=1,
+                      camera_left_eye=a["left_eye"], camera_right_eye=a["right_eye"],
+                      left_eye_in_subspace=int(a["left_eye_in_subspace"]), right_eye_in_subspace=int(a["right_eye_in_subspace"]),
+                      left_eye_scale=frontend.camera_scale(p.left_eye_matrix), right_eye_scale=frontend.camera_scale(p.right_eye_matrix))
+    got = hp.render_frame(256, 72, 12)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
