@@ -5,7 +5,7 @@
 //                      [--time T] [--stage NAME] [--animation NAME] [--camera NAME] [--device K]
 //                      [--texture name=file.rgba:WxH ...] [--output out.ppm]
 //   portal_b200_render render <scene.ron> --animations a,b,... [--fps N] [--motion-blur-frames M] [--width W]
-//                      [--height H] [--render-depth D] [--aa-count N] [--out-dir DIR] [--max-frames K]
+//                      [--height H] [--render-depth D] [--aa-count N] [--stereo-image] [--out-dir DIR] [--max-frames K]
 //                      (`portal render`, main.rs:2808-2873 -> render_named_animations :1876-1930 ->
 //                       render_animation :1757-1830; frames are written as DIR/<animation>/frame_<i>.ppm, the
 //                       ffmpeg step is out of scope)
@@ -50,12 +50,13 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "usage: %s render-frame <scene.ron> [--width W] [--height H] [--render-depth D] [--aa-count N] [--time T] "
                              "[--stage NAME] [--animation NAME] [--camera NAME] [--device K] [--texture name=file.rgba:WxH] [--output out.ppm]\n"
                              "       %s render <scene.ron> --animations a,b [--fps N] [--motion-blur-frames M] [--width W] [--height H] "
-                             "[--render-depth D] [--aa-count N] [--out-dir DIR] [--max-frames K]\n", argv[0], argv[0]);
+                             "[--render-depth D] [--aa-count N] [--stereo-image] [--out-dir DIR] [--max-frames K]\n", argv[0], argv[0]);
         return 2;
     }
     std::string scene_path = argv[2], output = "frame.ppm", out_dir = "video";
     int width = 1920, height = 1080, depth = 100, aa = 1, device = 0;  // defaults of RenderFrameCliOptions, main.rs:2744-2754
     int fps = 60, motion_blur = 1, max_frames = -1;
+    bool stereo = false;
     double time = 0.0;
     std::vector<std::string> textures;
     std::string stage, animation, camera, animations;
@@ -76,6 +77,7 @@ int main(int argc, char** argv) {
         else if (a == "--motion-blur-frames") motion_blur = std::atoi(next());
         else if (a == "--out-dir") out_dir = next();
         else if (a == "--max-frames") max_frames = std::atoi(next());
+        else if (a == "--stereo-image") stereo = true;
         else if (a == "--output") output = next();
         else if (a == "--texture") textures.push_back(next());
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
@@ -118,6 +120,10 @@ int main(int argc, char** argv) {
     }
     if (pe_scene_compile(ctx)) { std::fprintf(stderr, "%s\n", pe_last_error(ctx)); return 1; }
     ph_player_attach(player, ctx);  // camera teleportation goes through pe_probe_ray
+    if (stereo) {                   // `render --stereo-image`: side-by-side eyes, doubled width (main.rs:2809-2816, 2842)
+        width *= 2;
+        ph_player_set_stereo(player, 1, 0.07, 0);
+    }
     std::vector<uint8_t> px(size_t(width) * size_t(height) * 4);
     ph_frame_params p = {width, height, depth, aa, 0, 0, {0, 0, 0}, 0, 0, 0};
     if (frame_cmd) {
