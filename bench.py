@@ -298,7 +298,10 @@ def run_ours(args):
 
     # ---- e2e: the reference-facing call with HOST buffers (RGBA8 readback = get_texture_data)
     e2e_steps = max(3, min(args.steps, 20))
-    host8 = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
+    from portal_b200.distributed import gpu_numa_affinity
+    with gpu_numa_affinity(local):      # pinned pages on the GPU's NUMA node: the D2H copy stays off the socket interconnect
+        host8 = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
+        host8_b = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() if (rank == 0 and world == 1) else None
     q8 = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda") if (rank == 0 and world > 1) else None
     cam = r.cam
     n_px_local = int(r._lib.pe_target_pixels(C.byref(target))) if world == 1 or mode == "gather" else \
@@ -362,7 +365,7 @@ def run_ours(args):
         # pe_submit_host_rgba8 / pe_wait_host, frame i's D2H overlapping frame i+1's kernel; every frame still
         # uploads its uniforms and lands, complete, in pinned host memory before the clock stops
         e2e_sync_rate = e2e_rate
-        ring = [host8, torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()]
+        ring = [host8, host8_b]
         def pipelined(n):
             prev = None
             for i in range(n):

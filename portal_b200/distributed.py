@@ -201,6 +201,38 @@ class FrameSharder:
         self._owned = []
 
 
+class gpu_numa_affinity:
+    """Context manager: run the enclosed block on the CPUs NVML reports as local to CUDA device `device`
+    (nvmlDeviceSetCpuAffinity), then restore the previous affinity.  Host pages allocated / first touched inside
+    the block land on the GPU's NUMA node, so device->host copies do not cross the socket interconnect.
+    Best effort: without NVML (or on any error) it does nothing."""
+
+    def __init__(self, device: int):
+        self.device = device
+        self._old = None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            import torch
+            self._old = os.sched_getaffinity(0)
+            pynvml.nvmlInit()
+            props = torch.cuda.get_device_properties(self.device)
+            bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode()))
+        except Exception:
+            pass
+        return self
+
+    def __exit__(self, *exc):
+        if self._old is not None:
+            try:
+                os.sched_setaffinity(0, self._old)
+            except OSError:
+                pass
+        return False
+
+
 class HostFrameSharder:
     """Multi-GPU frames delivered to HOST memory with no device-side gather and no collective.
 
@@ -244,6 +276,19 @@ class HostFrameSharder:
         self._base = self._bytes.ctypes.data
         self._done = self._bytes[:8 * 64].view(np.uint64)         # done[r] at word r
         self._consumed = self._bytes[1024:1032].view(np.uint64)
+        # first touch: every rank faults in the pages of ITS strips from a CPU next to its GPU, so each strip's pages sit on
+        # the NUMA node of the GPU that will write them; only then is the segment page-locked
+        with gpu_numa_affinity(getattr(renderer, "device", rank)):
+            if rank == 0:
+                self._bytes[:self.HEADER] = 0
+            rows = [y for y in local_rows(height, rank, world, strip_rows) if y >= 0]
+            for d in range(self.DEPTH):
+                fr = self.slot(d)
+                for y0 in rows[::strip_rows]:
+                    fr[y0:y0 + strip_rows] = 0
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
         renderer._check(renderer._lib.pe_host_register(renderer._ctx, self._base, size))
         self._tickets = {}
         self.frame_no = 0
