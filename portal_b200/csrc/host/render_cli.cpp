@@ -4,7 +4,7 @@
 //   portal_b200_render render-frame <scene.ron> [--width W] [--height H] [--render-depth D] [--aa-count N]
 //                      [--time T] [--stage NAME] [--animation NAME] [--camera NAME] [--device K]
 //                      [--texture name=file.rgba:WxH ...] [--output out.ppm]
-//   portal_b200_render render <scene.ron> --animations a,b,... [--fps N] [--motion-blur-frames M] [--width W]
+//   portal_b200_render render <scene.ron> [--animations a,b,... | --starts-with PREFIX] [--fps N] [--motion-blur-frames M] [--width W]
 //                      [--height H] [--render-depth D] [--aa-count N] [--stereo-image] [--out-dir DIR] [--max-frames K]
 //                      (`portal render`, main.rs:2808-2873 -> render_named_animations :1876-1930 ->
 //                       render_animation :1757-1830; frames are written as DIR/<animation>/frame_<i>.ppm, the
@@ -49,7 +49,7 @@ int main(int argc, char** argv) {
     if (!frame_cmd && !anim_cmd) {
         std::fprintf(stderr, "usage: %s render-frame <scene.ron> [--width W] [--height H] [--render-depth D] [--aa-count N] [--time T] "
                              "[--stage NAME] [--animation NAME] [--camera NAME] [--device K] [--texture name=file.rgba:WxH] [--output out.ppm]\n"
-                             "       %s render <scene.ron> --animations a,b [--fps N] [--motion-blur-frames M] [--width W] [--height H] "
+                             "       %s render <scene.ron> [--animations a,b | --starts-with PREFIX] [--fps N] [--motion-blur-frames M] [--width W] [--height H] "
                              "[--render-depth D] [--aa-count N] [--stereo-image] [--out-dir DIR] [--max-frames K]\n", argv[0], argv[0]);
         return 2;
     }
@@ -59,7 +59,7 @@ int main(int argc, char** argv) {
     bool stereo = false;
     double time = 0.0;
     std::vector<std::string> textures;
-    std::string stage, animation, camera, animations;
+    std::string stage, animation, camera, animations, starts_with;
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -73,6 +73,7 @@ int main(int argc, char** argv) {
         else if (a == "--animation") animation = next();
         else if (a == "--camera") camera = next();
         else if (a == "--animations") animations = next();
+        else if (a == "--starts-with") starts_with = next();
         else if (a == "--fps") fps = std::atoi(next());
         else if (a == "--motion-blur-frames") motion_blur = std::atoi(next());
         else if (a == "--out-dir") out_dir = next();
@@ -134,11 +135,20 @@ int main(int argc, char** argv) {
         if (!write_image(output, px, width, height)) { std::fprintf(stderr, "cannot write %s\n", output.c_str()); return 1; }
         std::printf("Rendered `%s` to `%s`\n", scene_path.c_str(), output.c_str());
     } else {
-        if (animations.empty()) { std::fprintf(stderr, "render: --animations a,b,... is required\n"); return 2; }
+        // --animations a,b: render_named_animations (main.rs:1876-1930); otherwise render_all_animations (:1932-1974): every
+        // animation in file order is initialised and updated once, and rendered unless --starts-with filters it out
         std::vector<std::string> names;
-        std::stringstream ss(animations);
-        for (std::string item; std::getline(ss, item, ',');) if (!item.empty()) names.push_back(item);
-        for (size_t k = 0; k < names.size(); k++) {  // render_named_animations, main.rs:1888-1927
+        const bool all = animations.empty();
+        if (all) {
+            for (int a = 0; a < ph_scene_animation_count(scene); a++) {
+                const char* nm = nullptr;
+                if (ph_scene_animation(scene, a, &nm, nullptr) == 0) names.push_back(nm);
+            }
+        } else {
+            std::stringstream ss(animations);
+            for (std::string item; std::getline(ss, item, ',');) if (!item.empty()) names.push_back(item);
+        }
+        for (size_t k = 0; k < names.size(); k++) {
             if (ph_player_init_animation(player, names[k].c_str())) {
                 std::fprintf(stderr, "Scene `%s` has no animation named `%s`\n", scene_path.c_str(), names[k].c_str());
                 return 1;
@@ -150,6 +160,7 @@ int main(int argc, char** argv) {
                 double d = 0.0;
                 if (ph_scene_animation(scene, a, &nm, &d) == 0 && names[k] == nm) duration = d;
             }
+            if (all && !starts_with.empty() && names[k].compare(0, starts_with.size(), starts_with) != 0) continue;
             std::printf("Rendering animation %s, %zu/%zu\n", names[k].c_str(), k + 1, names.size());
             const std::string dir = out_dir + "/" + names[k];
             std::string cmd = "mkdir -p '" + dir + "'";
