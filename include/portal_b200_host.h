@@ -121,6 +121,9 @@ PE_API int ph_player_update(ph_player* p, double time_seconds);
  * `_camera_scale`; orbit[6] = look_at xyz, alpha, beta, r; times[2] = formula time, total_time. */
 PE_API int ph_player_camera(ph_player* p, double camera16[16], double camera_mul_inv16[16], int32_t* in_subspace,
                             double* scale, double orbit[6], double times[2], int64_t* n_probes);
+/* Scene::run_animations (src/gui/scene.rs:1359-1384): update(t) plays ALL real animations back to back -- t is
+ * wrapped to the total duration, the animation it falls into is initialised when it changes. */
+PE_API int ph_player_set_run_animations(ph_player* p, int on);
 /* Side-by-side stereo (SceneRenderer::draw_side_by_side, eye_distance 0.07, swap_eyes): with it on, update()
  * also places the two eye cameras (teleport_eye_matrices, src/main.rs:1121-1172) -- each eye is carried through
  * a portal that lies between it and the camera -- and the render calls send them with `_draw_side_by_side`.

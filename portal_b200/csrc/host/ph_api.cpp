@@ -408,6 +408,12 @@ int ph_player_camera(ph_player* p, double camera16[16], double inv16[16], int32_
     return 0;
 }
 
+int ph_player_set_run_animations(ph_player* p, int on) {
+    if (!p) return 1;
+    p->player.run_animations = on != 0;
+    return 0;
+}
+
 int ph_player_set_stereo(ph_player* p, int draw_side_by_side, double eye_distance, int swap_eyes) {
     if (!p) return 1;
     p->player.draw_side_by_side = draw_side_by_side != 0;

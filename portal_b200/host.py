@@ -157,6 +157,9 @@ class HostPlayer:
     def update(self, time_seconds: float):
         self._check(self._lib.ph_player_update(self._p, float(time_seconds)))
 
+    def set_run_animations(self, on: bool):
+        self._check(self._lib.ph_player_set_run_animations(self._p, int(on)))
+
     def set_stereo(self, draw_side_by_side: bool, eye_distance: float = 0.07, swap_eyes: bool = False):
         self._check(self._lib.ph_player_set_stereo(self._p, int(draw_side_by_side), float(eye_distance), int(swap_eyes)))
 

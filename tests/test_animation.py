@@ -85,6 +85,21 @@ def test_time_mapping_and_camera_chain():
     assert hs2.uniform_table()["open_u"] == ("int", 1)                              # Dev stage restored
 
 
+def test_run_animations_plays_the_whole_sequence():
+    """Scene::run_animations (scene.rs:1359-1384): one clock over all real animations (2.0 + 1.5 + 1.0 + 4.0 s here)."""
+    s, p, hs, hp = _pair(FIXTURE)
+    p.anim.run_animations = True
+    hp.set_run_animations(True)
+    for t, (name, local) in [(0.5, ("fly.1", 0.25)), (2.75, ("fly.2", 0.5)), (3.9, ("hold", 0.4)), (6.5, ("through", 0.5)),
+                              (8.5 + 1.0, ("fly.1", 0.5)), (1.9, ("fly.1", 0.95))]:
+        p.update(t)
+        hp.update(t)
+        _assert_same_state(p, hp, s, hs, t)
+        st = hp.camera_state()
+        assert p.anim.current_stage == ("real", name)
+        assert abs(st["time"] - local) < 1e-12 and abs(st["total_time"] - math.fmod(t, 8.5)) < 1e-12
+
+
 def test_stage_and_named_cameras():
     s, p, hs, hp = _pair(FIXTURE)
     hp.update(0.0)                                                                  # plain render-frame: the saved camera
