@@ -87,9 +87,32 @@ def test_unknown_uniform_and_frozen_scene_are_errors():
 
 
 def test_render_without_gpu_fails_loudly():
+    """There is no CPU rendering path: every entry point that would touch the device says so on a compile-only context."""
+    import ctypes as C
     r = SceneRenderer(load_ir("monoportal"), device=-1)
     with pytest.raises(PortalB200Error, match="no CUDA device"):
         r.render_host(16, 16)
+    lib, ctx, t = r._lib, r._ctx, r.full_target(16, 16)
+    buf = (C.c_uint8 * (16 * 16 * 16))()
+    tk, vp = C.c_uint64(), C.c_void_p()
+    calls = {
+        "pe_render": lambda: lib.pe_render(ctx, C.byref(t), C.addressof(buf), None, None),
+        "pe_render_rgba8": lambda: lib.pe_render_rgba8(ctx, C.byref(t), C.addressof(buf), None),
+        "pe_render_host_rgba8": lambda: lib.pe_render_host_rgba8(ctx, C.byref(t), C.addressof(buf)),
+        "pe_submit_host_rgba8": lambda: lib.pe_submit_host_rgba8(ctx, C.byref(t), C.addressof(buf), C.byref(tk)),
+        "pe_submit_host_strips_rgba8": lambda: lib.pe_submit_host_strips_rgba8(ctx, C.byref(t), C.addressof(buf), C.byref(tk)),
+        "pe_host_malloc": lambda: lib.pe_host_malloc(ctx, 64, C.byref(vp)),
+        "pe_host_register": lambda: lib.pe_host_register(ctx, C.addressof(buf), 4096),
+        "pe_device_malloc": lambda: lib.pe_device_malloc(ctx, 64, C.byref(vp)),
+        "pe_sync": lambda: lib.pe_sync(ctx),
+    }
+    for name, call in calls.items():
+        assert call() != 0, name
+        assert b"no CPU rendering path" in lib.pe_last_error(ctx), name
+    assert lib.pe_wait_host(ctx, 1) != 0 and b"unknown ticket" in lib.pe_last_error(ctx)
+    a = (C.c_float * 3)(0, 0, 0)
+    o, h1, h2, h3 = (C.c_float * 3)(), C.c_int32(), C.c_int32(), C.c_int32()
+    assert lib.pe_probe_ray(ctx, a, a, o, C.byref(h1), C.byref(h2), C.byref(h3)) != 0
 
 
 def test_strip_targets_partition_the_frame():
