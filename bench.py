@@ -278,7 +278,6 @@ def run_ours(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    t_wall0 = time.perf_counter()
     t_epoch0 = time.time()
     ev[0].record(stream)
     for i in range(args.steps):
