@@ -257,10 +257,20 @@ class HostFrameSharder:
         size = self.HEADER + self.DEPTH * self.frame_bytes
         if name is None:
             import torch.distributed as dist
-            box = [f"portal_b200_{os.getpid()}" if rank == 0 else None]
+            box = [None]
+            if rank == 0:
+                # a tmpfs that is too small turns the first touch into SIGBUS: decide up front, for every rank at once
+                try:
+                    st = os.statvfs("/dev/shm")
+                    roomy = st.f_bavail * st.f_frsize >= size + (64 << 20)
+                except OSError:
+                    roomy = False
+                box = [f"portal_b200_{os.getpid()}" if roomy else ""]
             if world > 1:
                 dist.broadcast_object_list(box, src=0)
             name = box[0]
+        if not name:
+            raise RuntimeError(f"HostFrameSharder: /dev/shm cannot hold {size >> 20} MiB of frame ring")
         self.path = f"/dev/shm/{name}"
         if rank == 0:
             fd = os.open(self.path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
