@@ -91,6 +91,11 @@ PE_API int pe_scene_compile(pe_ctx* ctx);
  * compile); for inspection, caching and cuobjdump. */
 PE_API const char* pe_scene_source(pe_ctx* ctx);
 PE_API int pe_scene_cubin(pe_ctx* ctx, const void** data, size_t* size);
+/* Host image of the constant uniform block (`PeConstBlock` of pe_scene_source) exactly as a render of a
+ * width x height frame would upload it now: uploaded uniforms, `_resolution`, and the values the host derives
+ * per upload (tan(view_angle/2), per-plane unit normals).  Valid until the next call on ctx; for inspection and
+ * for running the generated program outside the GPU in tests.  Texture slots hold device pointers. */
+PE_API int pe_scene_uniform_block(pe_ctx* ctx, int width, int height, const void** data, size_t* size);
 /* Options: "persistent" (0/1, default 0), "specialize_ints" (0/1, default 1), "specialize_matrices"
  * (0/1, default 1: the exact-0 / exact-1 structure of every uploaded matrix is baked in), "block_threads",
  * "min_blocks", "hoist_planes" (0/1, default 1: per-plane normal algebra evaluated once per upload on the

@@ -65,6 +65,7 @@ def lib() -> C.CDLL:
         "pe_scene_compile": (i32, [vp]),
         "pe_scene_source": (cp, [vp]),
         "pe_scene_cubin": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+        "pe_scene_uniform_block": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "pe_set_option": (i32, [vp, cp, i32]),
         "pe_set_uniform_mat4": (i32, [vp, cp, C.POINTER(C.c_float)]),
         "pe_set_uniform_f32": (i32, [vp, cp, C.c_float]),

@@ -656,6 +656,19 @@ int pe_scene_cubin(pe_ctx* c, const void** data, size_t* size) {
     return 0;
 }
 
+int pe_scene_uniform_block(pe_ctx* c, int width, int height, const void** data, size_t* size) {
+    if (!c || !data || !size) return 1;
+    if (width <= 0 || height <= 0) return c->fail("pe_scene_uniform_block: bad frame size");
+    ensure_layout(c);
+    *fslot(c, c->layout.float_slot["_resolution_x"]) = float(width);
+    *fslot(c, c->layout.float_slot["_resolution_y"]) = float(height);
+    if (!select_variant(c)) return 1;
+    update_derived(c);
+    *data = c->cblock.data();
+    *size = c->cblock.size();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------ uniforms
 int pe_set_uniform_mat4(pe_ctx* c, const char* name, const float m[16]) {
     if (!c || !name || !m) return 1;

@@ -176,6 +176,14 @@ class SceneRenderer:
         self._check(self._lib.pe_scene_cubin(self._ctx, C.byref(p), C.byref(n)))
         return C.string_at(p, n.value)
 
+    def uniform_block(self, width: int, height: int) -> bytes:
+        """Host image of the constant block a width x height render would upload now (uniforms set on this object
+        are sent first); the program for it is source()."""
+        self.set_uniforms()
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self._lib.pe_scene_uniform_block(self._ctx, width, height, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value)
+
     def launch_count(self) -> int:
         return int(self._lib.pe_launch_count(self._ctx))
 

@@ -1,0 +1,80 @@
+// Runs a generated sm_100a scene program (the text pe_scene_source returns) on the HOST, thread by thread.
+// TEST INFRASTRUCTURE (tests/test_program_on_host.py): the product has no CPU path; this exists so that the
+// generated program + the hand-written device headers can be compared with the oracle without a GPU, and so
+// that generator options (lazy_planes, hoist_planes, specialize_matrices ...) can be proven frame-identical.
+//
+//   g++ -std=c++20 -O1 -ffp-contract=off -DPROGRAM_FILE='"prog.cu"' run_program.cpp -o run
+//   ./run block.bin W H out.f32 [tex0.rgba W0 H0 [tex1.rgba W1 H1 ...]]
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "cuda_on_host.h"
+#include PROGRAM_FILE
+
+static std::vector<unsigned char> slurp(const char* path) {
+    std::vector<unsigned char> b;
+    if (FILE* f = std::fopen(path, "rb")) {
+        std::fseek(f, 0, SEEK_END);
+        long n = std::ftell(f);
+        std::fseek(f, 0, SEEK_SET);
+        b.resize(size_t(n));
+        if (std::fread(b.data(), 1, size_t(n), f) != size_t(n)) b.clear();
+        std::fclose(f);
+    }
+    return b;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 5) return 2;
+    const std::vector<unsigned char> block = slurp(argv[1]);
+    const int w = std::atoi(argv[2]), h = std::atoi(argv[3]);
+    if (block.size() != sizeof(pe::PeConstBlock)) {
+        std::fprintf(stderr, "uniform block is %zu bytes, program expects %zu\n", block.size(), sizeof(pe::PeConstBlock));
+        return 1;
+    }
+    std::memcpy(&PE_C, block.data(), sizeof PE_C);
+    std::vector<std::vector<unsigned char>> textures;
+    const int n_tex = int(sizeof(PE_C.tex) / sizeof(PE_C.tex[0]));
+    for (int k = 0; k < n_tex; k++) {  // device pointers in the block are meaningless here: bind host texels (or nothing)
+        PE_C.tex[k].data = nullptr;
+        PE_C.tex[k].w = PE_C.tex[k].h = 0;
+        const int a = 5 + 3 * k;
+        if (a + 2 < argc) {
+            textures.push_back(slurp(argv[a]));
+            PE_C.tex[k].data = reinterpret_cast<const uchar4*>(textures.back().data());
+            PE_C.tex[k].w = std::atoi(argv[a + 1]);
+            PE_C.tex[k].h = std::atoi(argv[a + 2]);
+        }
+    }
+    std::vector<float4> out(size_t(w) * size_t(h));
+    PeLaunch L{};
+    L.out = out.data();
+    L.bounces = nullptr;
+    L.width = w;
+    L.height = h;
+    L.strip_rows = h;
+    L.strip_first = 0;
+    L.strip_step = 1;
+    L.n_strips = 1;
+    L.out_full_frame = 1;
+    L.tiles_x = (w + 7) / 8;
+    L.tiles_y = (h + 3) / 4;
+    L.out_rgba8 = 0;
+    L.queue = nullptr;
+    const unsigned rows_per_block = PE_BLOCK_THREADS / 64 * 4;
+    blockDim = pe_uint3{unsigned(PE_BLOCK_THREADS), 1, 1};
+    gridDim = pe_uint3{unsigned((w + 15) / 16), unsigned((h + rows_per_block - 1) / rows_per_block), 1};
+    for (unsigned by = 0; by < gridDim.y; by++)
+        for (unsigned bx = 0; bx < gridDim.x; bx++)
+            for (unsigned t = 0; t < blockDim.x; t++) {
+                blockIdx = pe_uint3{bx, by, 0};
+                threadIdx = pe_uint3{t, 0, 0};
+                pe_render_kernel(L);
+            }
+    FILE* f = std::fopen(argv[4], "wb");
+    if (!f) return 1;
+    std::fwrite(out.data(), sizeof(float4), out.size(), f);
+    std::fclose(f);
+    return 0;
+}

@@ -1,0 +1,77 @@
+"""The generated sm_100a scene program -- the exact text pe_scene_source returns, with the hand-written device
+headers in it -- compiled as ordinary C++ and executed thread by thread on the host (tests/host_harness/), fed with
+the uniform-block image the renderer would upload (pe_scene_uniform_block).  It must reproduce the oracle's frame
+bit for bit, and every generator option that claims "same pixels" must keep its promise.  This is a TEST: the
+product has no CPU path (tests/test_capi.py::test_render_without_gpu_fails_loudly)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import DEPTH, ROOT, SCENES, load_ir, load_tex
+from portal_b200.renderer import SceneRenderer
+
+HARNESS = os.path.join(ROOT, "tests", "host_harness")
+W, H = 96, 54
+
+
+def _run_on_host(tmp_path, tag, scene, options=None, uniforms=None, specialize_ints=True):
+    ir = load_ir(scene)
+    r = SceneRenderer(ir, device=-1, options=options or {}, specialize_ints=specialize_ints)
+    r.render_depth = DEPTH[scene]
+    for k, v in (uniforms or {}).items():
+        r.set_uniform(k, v)
+    block, src = r.uniform_block(W, H), r.source()
+    d = tmp_path / tag
+    d.mkdir()
+    (d / "prog.cu").write_text(src)
+    (d / "block.bin").write_bytes(block)
+    cc = subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", f'-DPROGRAM_FILE="{d / "prog.cu"}"', "-I", HARNESS,
+                         os.path.join(HARNESS, "run_program.cpp"), "-o", str(d / "run")], capture_output=True, text=True, timeout=900)
+    assert cc.returncode == 0, cc.stderr[-3000:]
+    args = [str(d / "run"), str(d / "block.bin"), str(W), str(H), str(d / "out.f32")]
+    tex = load_tex(scene) or {}
+    for t in ir["textures"]:                                   # declaration order = slot order in the block
+        arr = np.ascontiguousarray(tex[t["name"]], dtype=np.uint8)
+        path = d / f"{t['name']}.rgba"
+        path.write_bytes(arr.tobytes())
+        args += [str(path), str(arr.shape[1]), str(arr.shape[0])]
+    run = subprocess.run(args, capture_output=True, text=True, timeout=900)
+    assert run.returncode == 0, run.stderr[-2000:]
+    return np.fromfile(d / "out.f32", dtype=np.float32).reshape(H, W, 4), src
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_generated_program_on_host_equals_oracle(scene, tmp_path):
+    from oracle.runner import Oracle
+    got, src = _run_on_host(tmp_path, "default", scene)
+    assert "plane_intersect_lazy(" in src or scene == "mobius_monoportal" or "plane_intersect" in src
+    want = Oracle(load_ir(scene), "strict", textures=load_tex(scene)).render(W, H, DEPTH[scene])
+    assert np.array_equal(_bits(got), _bits(want)), f"{scene}: {(np.abs(got - want) > 0).any(axis=-1).sum()} pixels differ"
+
+
+@pytest.mark.parametrize("scene", ["portal_in_portal", "triple_portal"])
+def test_generator_options_do_not_change_pixels(scene, tmp_path):
+    base, src = _run_on_host(tmp_path, "base", scene)
+    assert "plane_intersect_lazy(" in src
+    for tag, opts, kw in [("nolazy", {"lazy_planes": 0}, {}), ("nohoist", {"hoist_planes": 0}, {}),
+                          ("nomat", {"specialize_matrices": 0}, {}), ("noints", {}, {"specialize_ints": False}),
+                          ("rolled", {"unroll_loops": 0}, {}), ("blk128", {"block_threads": 128, "min_blocks": 4}, {})]:
+        got, s2 = _run_on_host(tmp_path, tag, scene, options=opts, **kw)
+        assert s2 != src or tag == "rolled"          # a scene without loops has nothing to keep rolled
+        assert np.array_equal(_bits(got), _bits(base)), (scene, tag)
+
+
+def test_uniform_change_reaches_the_host_run(tmp_path):
+    """Same harness, different uniforms: the block image really is what drives the frame."""
+    from oracle.runner import Oracle
+    ov = {"teleport_light_u": 0, "show_teleported_u": 3}
+    got, _ = _run_on_host(tmp_path, "ov", "portal_in_portal", uniforms=ov)
+    orc = Oracle(load_ir("portal_in_portal"), "strict", textures=load_tex("portal_in_portal"))
+    orc.set_uniforms(ov)
+    assert np.array_equal(_bits(got), _bits(orc.render(W, H, DEPTH["portal_in_portal"])))
