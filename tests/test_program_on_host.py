@@ -16,10 +16,10 @@ HARNESS = os.path.join(ROOT, "tests", "host_harness")
 W, H = 96, 54
 
 
-def _run_on_host(tmp_path, tag, scene, options=None, uniforms=None, specialize_ints=True):
-    ir = load_ir(scene)
+def _run_on_host(tmp_path, tag, scene, options=None, uniforms=None, specialize_ints=True, ir=None, tex=None, depth=None):
+    ir = load_ir(scene) if ir is None else ir
     r = SceneRenderer(ir, device=-1, options=options or {}, specialize_ints=specialize_ints)
-    r.render_depth = DEPTH[scene]
+    r.render_depth = DEPTH[scene] if depth is None else depth
     for k, v in (uniforms or {}).items():
         r.set_uniform(k, v)
     block, src = r.uniform_block(W, H), r.source()
@@ -31,7 +31,7 @@ def _run_on_host(tmp_path, tag, scene, options=None, uniforms=None, specialize_i
                          os.path.join(HARNESS, "run_program.cpp"), "-o", str(d / "run")], capture_output=True, text=True, timeout=900)
     assert cc.returncode == 0, cc.stderr[-3000:]
     args = [str(d / "run"), str(d / "block.bin"), str(W), str(H), str(d / "out.f32")]
-    tex = load_tex(scene) or {}
+    tex = (load_tex(scene) or {}) if tex is None else tex
     for t in ir["textures"]:                                   # declaration order = slot order in the block
         arr = np.ascontiguousarray(tex[t["name"]], dtype=np.uint8)
         path = d / f"{t['name']}.rgba"
@@ -75,3 +75,19 @@ def test_uniform_change_reaches_the_host_run(tmp_path):
     orc = Oracle(load_ir("portal_in_portal"), "strict", textures=load_tex("portal_in_portal"))
     orc.set_uniforms(ov)
     assert np.array_equal(_bits(got), _bits(orc.render(W, H, DEPTH["portal_in_portal"])))
+
+
+@pytest.mark.parametrize("scene", ["cone", "matryoshka", "recursive_space", "cylinder"])
+def test_more_reference_scenes_on_host(scene, tmp_path):
+    """Reference scenes beyond the five configs (tests/golden/scenes_extra): skybox sampling, Reflect / Refract,
+    subspaces, the `Camera` matrix kind, and (cylinder) libm's exp/log -- on the host both sides call the same
+    libm, so even that one is bit-exact here."""
+    import json
+    from oracle.runner import Oracle
+    with open(os.path.join(ROOT, "tests", "golden", "scenes_extra", f"{scene}.scene.json")) as f:
+        ir = json.load(f)
+    mono = load_tex("monoportal")["monoportal"]
+    tex = {t["name"]: mono for t in ir["textures"]}
+    got, _ = _run_on_host(tmp_path, "x", scene, ir=ir, tex=tex, depth=30)
+    want = Oracle(ir, "strict", textures=tex).render(W, H, 30)
+    assert np.array_equal(_bits(got), _bits(want)), f"{scene}: {(np.abs(got - want) > 0).any(axis=-1).sum()} pixels differ"
