@@ -247,6 +247,20 @@ class HostFrameSharder:
 
     DEPTH = 3
     HEADER = 4096
+    TIMEOUT_S = 120.0        # a rank that died must not leave the others spinning forever
+
+    @staticmethod
+    def _spin_until(cond, what: str):
+        import time
+        n, deadline = 0, None
+        while not cond():
+            n += 1
+            if n % 4096 == 0:
+                now = time.monotonic()
+                if deadline is None:
+                    deadline = now + HostFrameSharder.TIMEOUT_S
+                elif now > deadline:
+                    raise TimeoutError(f"HostFrameSharder: waited {HostFrameSharder.TIMEOUT_S:.0f} s for {what}")
 
     def __init__(self, renderer, width: int, height: int, rank: int, world: int, strip_rows: int = STRIP_ROWS, name: str | None = None):
         import mmap
@@ -313,8 +327,8 @@ class HostFrameSharder:
         f = self.frame_no
         self.frame_no += 1
         need = f + 1 - self.DEPTH
-        while need > 0 and int(self._consumed[0]) < need:
-            pass
+        if need > 0:
+            self._spin_until(lambda: int(self._consumed[0]) >= need, f"the consumer to release frame {need - 1}")
         self.r.set_uniforms()
         ticket = C.c_uint64()
         self.r._check(self.r._lib.pe_submit_host_strips_rgba8(self.r._ctx, C.byref(self.target),
@@ -330,8 +344,7 @@ class HostFrameSharder:
     def wait_frame(self, f: int):
         """Rank 0: block until every rank's part of frame f has landed; returns the frame (view of the slot)."""
         for rk in range(self.world):
-            while int(self._done[rk]) < f + 1:
-                pass
+            self._spin_until(lambda: int(self._done[rk]) >= f + 1, f"rank {rk}'s strips of frame {f}")
         return self.slot(f)
 
     def release(self, f: int):
