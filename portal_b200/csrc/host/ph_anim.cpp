@@ -66,24 +66,24 @@ bool Player::cam_get(int cam_id, CalculatedCam& out) {
     return true;
 }
 
-int Player::get_start_cam(int idx) const {  // scene.rs:1291-1317
-    if (idx < 0 || idx >= int(sc.animations.size())) return -1;
+int Player::get_start_cam(int idx, int depth) const {  // scene.rs:1291-1317
+    if (idx < 0 || idx >= int(sc.animations.size()) || depth > 256) return -1;   // (the reference would overflow its stack on a cycle)
     const RealAnimation& a = sc.animations[size_t(idx)];
-    if (a.use_prev_cam) return idx >= 1 ? get_end_cam(idx - 1) : -1;
+    if (a.use_prev_cam) return idx >= 1 ? get_end_cam(idx - 1, depth + 1) : -1;
     if (a.use_any_cam_as_start >= 0) {
         if (a.cam_any_start < 0) return -1;
-        return a.use_any_cam_as_start ? get_end_cam(a.cam_any_start) : get_start_cam(a.cam_any_start);
+        return a.use_any_cam_as_start ? get_end_cam(a.cam_any_start, depth + 1) : get_start_cam(a.cam_any_start, depth + 1);
     }
     return a.cam_start;
 }
 
-int Player::get_end_cam(int idx) const {  // scene.rs:1319-1335
-    if (idx < 0 || idx >= int(sc.animations.size())) return -1;
+int Player::get_end_cam(int idx, int depth) const {  // scene.rs:1319-1335
+    if (idx < 0 || idx >= int(sc.animations.size()) || depth > 256) return -1;
     const RealAnimation& a = sc.animations[size_t(idx)];
-    if (a.use_start_cam_as_end) return get_start_cam(idx);
+    if (a.use_start_cam_as_end) return get_start_cam(idx, depth + 1);
     if (a.use_any_cam_as_end >= 0) {
         if (a.cam_any_end < 0) return -1;
-        return a.use_any_cam_as_end ? get_end_cam(a.cam_any_end) : get_start_cam(a.cam_any_end);
+        return a.use_any_cam_as_end ? get_end_cam(a.cam_any_end, depth + 1) : get_start_cam(a.cam_any_end, depth + 1);
     }
     return a.cam_end;
 }

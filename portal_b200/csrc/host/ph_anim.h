@@ -73,8 +73,8 @@ struct Player {
     bool update(double time);  // SceneRenderer::update
 
     bool cam_get(int cam_id, CalculatedCam& out);
-    int get_start_cam(int anim) const;
-    int get_end_cam(int anim) const;
+    int get_start_cam(int anim, int depth = 0) const;   // depth: guards against animations whose cameras refer to each other in a cycle
+    int get_end_cam(int anim, int depth = 0) const;
     double total_animation_duration() const;
 
   private:
