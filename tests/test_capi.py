@@ -136,3 +136,29 @@ def test_orbit_camera_matches_oracle_frontend():
     cols = frontend.orbit_camera_matrix(cam["look_at"], cam["alpha"] + 0.3, cam["beta"], cam["r"])
     m2 = orbit_camera_matrix(cam["look_at"], cam["alpha"] + 0.3, cam["beta"], cam["r"])
     assert np.allclose(m2, np.array([x for c in cols for x in c]), rtol=0, atol=1e-15)
+
+
+def _build_c_example(tmp_path):
+    exe = str(tmp_path / "render_frame_c")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    cc = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                         os.path.join(ROOT, "examples", "render_frame.c"), "-L", libdir, "-lportal_b200", f"-Wl,-rpath,{libdir}", "-o", exe],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    return exe
+
+
+def test_headers_are_c11_and_a_plain_c_caller_links(tmp_path):
+    """The boundary is a C ABI: both headers are valid ISO C11, and examples/render_frame.c (no C++, no Python) links
+    against the library, compiles a scene for sm_100a and -- without a GPU -- is refused loudly at the render call."""
+    for h in ("portal_b200.h", "portal_b200_host.h"):
+        src = tmp_path / f"inc_{h}.c"
+        src.write_text(f'#include "{h}"\nint main(void) {{ return 0; }}\n')
+        cc = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                            capture_output=True, text=True)
+        assert cc.returncode == 0, cc.stderr
+    exe = _build_c_example(tmp_path)
+    run = subprocess.run([exe, os.path.join(ROOT, "tests", "fixtures", "two_spheres.ron"), str(tmp_path / "o.ppm"), "64", "36", "8", "-1"],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 3 and "no CPU rendering path" in run.stderr
+    assert "bytes of sm_100a code for 10 objects" in run.stdout
