@@ -16,10 +16,12 @@ HARNESS = os.path.join(ROOT, "tests", "host_harness")
 W, H = 96, 54
 
 
-def _run_on_host(tmp_path, tag, scene, options=None, uniforms=None, specialize_ints=True, ir=None, tex=None, depth=None):
+def _run_on_host(tmp_path, tag, scene, options=None, uniforms=None, specialize_ints=True, ir=None, tex=None, depth=None, attrs=None):
     ir = load_ir(scene) if ir is None else ir
     r = SceneRenderer(ir, device=-1, options=options or {}, specialize_ints=specialize_ints)
     r.render_depth = DEPTH[scene] if depth is None else depth
+    for k, v in (attrs or {}).items():
+        setattr(r, k, v)
     for k, v in (uniforms or {}).items():
         r.set_uniform(k, v)
     block, src = r.uniform_block(W, H), r.source()
@@ -91,3 +93,32 @@ def test_more_reference_scenes_on_host(scene, tmp_path):
     got, _ = _run_on_host(tmp_path, "x", scene, ir=ir, tex=tex, depth=30)
     want = Oracle(ir, "strict", textures=tex).render(W, H, 30)
     assert np.array_equal(_bits(got), _bits(want)), f"{scene}: {(np.abs(got - want) > 0).any(axis=-1).sum()} pixels differ"
+
+
+def test_renderer_flags_on_host(tmp_path):
+    """The renderer-side switches of SceneRenderer::set_uniforms (AA window, colouring flags, depth map, panini /
+    360 / VR180 projections, side-by-side stereo): generated program on the host == oracle, bit for bit."""
+    from oracle.runner import Oracle
+    from portal_b200.renderer import camera_scale
+    scene = "monoportal"
+    orc = Oracle(load_ir(scene), "strict", textures=load_tex(scene))
+    probe = SceneRenderer(load_ir(scene), device=-1)
+    left, right = probe.eye_matrices()
+    cases = [
+        ("aa", dict(aa_count=3, aa_start=2), dict(aa_count=3, aa_start=2)),
+        ("flags", dict(grid_disable=True, angle_color_disable=True, darken_by_distance=False, black_border_disable=True),
+         dict(grid_disable=1, angle_color_disable=1, darken_by_distance=0, black_border_disable=1)),
+        ("depthmap", dict(draw_depth_map=True), dict(draw_depth_map=1)),
+        ("panini", dict(use_panini_projection=True, panini_param=0.7), dict(use_panini_projection=1, panini_param=0.7)),
+        ("cam360", dict(use_360_camera=True), dict(use_360_camera=1)),
+        ("cam180", dict(use_180_camera=True), dict(use_180_camera=1)),
+        ("sbs", dict(draw_side_by_side=True),
+         dict(draw_side_by_side=1, camera_left_eye=left, camera_right_eye=right, left_eye_scale=camera_scale(left),
+              right_eye_scale=camera_scale(right))),
+    ]
+    plain = orc.render(W, H, DEPTH[scene])
+    for tag, attrs, kw in cases:
+        got, _ = _run_on_host(tmp_path, tag, scene, attrs=attrs)
+        want = orc.render(W, H, DEPTH[scene], **kw)
+        assert np.array_equal(_bits(got), _bits(want)), tag
+        assert not np.array_equal(_bits(want), _bits(plain)), tag            # the switch really changes the frame
