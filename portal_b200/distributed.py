@@ -218,8 +218,12 @@ class gpu_numa_affinity:
             self._old = os.sched_getaffinity(0)
             pynvml.nvmlInit()
             props = torch.cuda.get_device_properties(self.device)
-            bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
-            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode()))
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{props.uuid}".encode())
+            except Exception:
+                bus = f"{props.pci_domain_id:08X}:{props.pci_bus_id:02X}:{props.pci_device_id:02X}.0"
+                handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            pynvml.nvmlDeviceSetCpuAffinity(handle)
         except Exception:
             pass
         return self
