@@ -65,10 +65,14 @@ int main(int argc, char** argv) {
     const unsigned rows_per_block = PE_BLOCK_THREADS / 64 * 4;
     blockDim = pe_uint3{unsigned(PE_BLOCK_THREADS), 1, 1};
     gridDim = pe_uint3{unsigned((w + 15) / 16), unsigned((h + rows_per_block - 1) / rows_per_block), 1};
-    for (unsigned by = 0; by < gridDim.y; by++)
-        for (unsigned bx = 0; bx < gridDim.x; bx++)
-            for (unsigned t = 0; t < blockDim.x; t++) {
-                blockIdx = pe_uint3{bx, by, 0};
+    const pe_uint3 bd = blockDim, gd = gridDim;
+#pragma omp parallel for schedule(dynamic, 1)   // (only with -fopenmp: the built-in indices are thread_local)
+    for (int by = 0; by < int(gd.y); by++)
+        for (unsigned bx = 0; bx < gd.x; bx++)
+            for (unsigned t = 0; t < bd.x; t++) {
+                blockDim = bd;
+                gridDim = gd;
+                blockIdx = pe_uint3{bx, unsigned(by), 0};
                 threadIdx = pe_uint3{t, 0, 0};
                 pe_render_kernel(L);
             }
