@@ -18,6 +18,9 @@ Semantics reproduced:
     tan asin acos atan sinh cosh tanh asinh acosh atanh; any other name (with
     or without arguments) goes to the caller's namespace callback -- exactly
     like the reference's `cb` closure (uniform.rs:1014-1124).
+
+parity unpinned: the reference holds no tests, golden vectors or fixtures for this path (oracle/README.md);
+the pins are this repo's committed goldens and its second, independent implementations.
 """
 from __future__ import annotations
 

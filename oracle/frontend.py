@@ -18,6 +18,9 @@ Output: a "scene IR" dict (JSON-serialisable) consumed by the oracle renderer
 build (oracle/build_oracle.py), by tests, and -- as committed golden fixtures
 under tests/golden/scenes/ -- by the product's Python binding on the GPU box.
 Nothing under portal_b200/ imports this module.
+
+parity unpinned: the reference holds no tests, golden vectors or fixtures for this path (oracle/README.md);
+the pins are this repo's committed goldens and its second, independent implementations.
 """
 from __future__ import annotations
 

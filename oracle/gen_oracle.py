@@ -18,6 +18,9 @@ rewriting is lexical (glsl_to_cpp): float literals get the arithmetic type's suf
 -component swizzles become accessor calls, parameter qualifiers become references.
 
 Nothing under portal_b200/ imports this module.
+
+parity unpinned: the reference holds no tests, golden vectors or fixtures for this path (oracle/README.md);
+the pins are this repo's committed goldens and its second, independent implementations.
 """
 from __future__ import annotations
 

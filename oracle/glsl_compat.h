@@ -1,6 +1,7 @@
 // GLSL-in-C++ compatibility layer for the CPU oracle.
 //
 // ORACLE / TEST INFRASTRUCTURE ONLY (see oracle/README.md): nothing under
+// parity unpinned: the reference holds no tests, golden vectors or fixtures for this path (oracle/README.md).
 // portal_b200/ may include this file.  It lets the reference's GLSL
 // (/root/reference/src/library.glsl, /root/reference/src/frag.glsl and the
 // per-scene snippets stored in scenes/*.ron) be restated as plain C++.

@@ -1,6 +1,7 @@
 // CPU restatement of the reference's fragment-shader driver (the ray loop).
 //
 // ORACLE / TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+// parity unpinned: the reference holds no tests, golden vectors or fixtures for this path (oracle/README.md).
 // Follows /root/reference/src/frag.glsl; each function cites its lines.  Included by
 // the generated per-scene translation unit AFTER scene_intersect(), material_process()
 // and scene_intersect_material_process() have been emitted (frag.glsl:19-59 with the

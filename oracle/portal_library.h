@@ -1,6 +1,7 @@
 // CPU restatement of the reference's predefined GLSL library.
 //
 // ORACLE / TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+// parity unpinned: the reference holds no tests, golden vectors or fixtures for this path (oracle/README.md).
 // Every function cites the lines of /root/reference/src/library.glsl it follows.
 // Included by the per-scene translation unit that oracle/gen_oracle.py writes, after
 // glsl_compat.h and after the uniform block (`PE_R` = renderer uniforms) is declared.

@@ -18,6 +18,9 @@ Mapping to Python values:
     Some(x) / None      -> x / None
     [..]                -> list,  {k: v} -> dict
     "..", r#".."#       -> str; numbers -> int | float; true/false -> bool
+
+parity unpinned: the reference holds no tests, golden vectors or fixtures for this path (oracle/README.md);
+the pins are this repo's committed goldens and its second, independent implementations.
 """
 from __future__ import annotations
 

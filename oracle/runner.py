@@ -2,6 +2,9 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this (see oracle/README.md).  Nothing here touches a GPU.
+
+parity unpinned: the reference holds no tests, golden vectors or fixtures for this path (oracle/README.md);
+the pins are this repo's committed goldens and its second, independent implementations.
 """
 from __future__ import annotations
 
