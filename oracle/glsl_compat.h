@@ -20,11 +20,12 @@
 //   * min/max/clamp/step/sign/mod/fract follow the GLSL ES 3.00 spec text
 //     (section 8.3) literally, including their behaviour on NaN;
 //   * sin cos tan asin acos atan are defined HERE (same sequence of IEEE operations as the kernel);
-//     exp log exp2 log2 pow come from the host libm.
+//     exp2 log2 are pinned as well; exp log pow are derived from them (GLSL ES 3.00 section 4.5.1).
 // PE_REAL selects the arithmetic type: float (the parity reference) or double
 // (used only to flag ill-conditioned pixels).
 #pragma once
 #include <cmath>
+#include <limits>
 #include <cstdint>
 
 #ifndef PE_REAL
@@ -120,11 +121,55 @@ static inline real acos(real x) {
     if (x > PE_L(0.5)) return PE_L(2.0) * asin(std::sqrt(PE_L(0.5) * (PE_L(1.0) - x)));
     return PE_L(1.5707963267948966) - asin(x);
 }
-static inline real pow(real x, real y) { return std::pow(x, y); }
-static inline real exp(real x) { return std::exp(x); }
-static inline real log(real x) { return std::log(x); }
-static inline real exp2(real x) { return std::exp2(x); }
-static inline real log2(real x) { return std::log2(x); }
+// exp2 / log2: pinned like the trigonometric functions (same text as pe_glsl.cuh; std::frexp / std::ldexp of 1 are exact,
+// so they equal the device's bit manipulation); exp, log, pow derived from them as GLSL ES 3.00 section 4.5.1 does.
+static inline real pe_pow2i(int k) { return std::ldexp(real(1), k); }
+static inline real exp2(real x) {
+    if (!(x == x)) return x;
+    if (x >= PE_L(128.0)) return std::numeric_limits<real>::infinity();
+    if (x < PE_L(-150.0)) return PE_L(0.0);
+    const real n = std::rint(x);
+    const real f = x - n;
+    real p = PE_L(1.535336188319500e-4);
+    p = pe_fma(p, f, PE_L(1.339887440266574e-3));
+    p = pe_fma(p, f, PE_L(9.618437357674640e-3));
+    p = pe_fma(p, f, PE_L(5.550332471162809e-2));
+    p = pe_fma(p, f, PE_L(2.402264791363012e-1));
+    p = pe_fma(p, f, PE_L(6.931472028550421e-1));
+    p = pe_fma(p, f, PE_L(1.0));
+    const int k = int(n);
+    if (k > 127) return (p * pe_pow2i(k - 64)) * PE_L(18446744073709551616.0);
+    if (k < -126) return (p * pe_pow2i(k + 64)) * PE_L(5.421010862427522170e-20);
+    return p * pe_pow2i(k);
+}
+static inline real log2(real x) {
+    if (!(x == x) || x < PE_L(0.0)) return std::numeric_limits<real>::quiet_NaN();
+    if (x == PE_L(0.0)) return -std::numeric_limits<real>::infinity();
+    if (x == std::numeric_limits<real>::infinity()) return x;
+    int e = 0;
+    real m = std::frexp(x, &e);                                                    // m in [0.5, 1)
+    if (m < PE_L(0.70710678118654752440)) { e -= 1; m = m + m - PE_L(1.0); } else { m = m - PE_L(1.0); }
+    const real z = m * m;
+    real y = PE_L(7.0376836292e-2);
+    y = pe_fma(y, m, PE_L(-1.1514610310e-1));
+    y = pe_fma(y, m, PE_L(1.1676998740e-1));
+    y = pe_fma(y, m, PE_L(-1.2420140846e-1));
+    y = pe_fma(y, m, PE_L(1.4249322787e-1));
+    y = pe_fma(y, m, PE_L(-1.6668057665e-1));
+    y = pe_fma(y, m, PE_L(2.0000714765e-1));
+    y = pe_fma(y, m, PE_L(-2.4999993993e-1));
+    y = pe_fma(y, m, PE_L(3.3333331174e-1));
+    y = y * m * z;
+    y = pe_fma(PE_L(-0.5), z, y);
+    real r = y * PE_L(0.44269504088896340736);
+    r = pe_fma(m, PE_L(0.44269504088896340736), r);
+    r = r + y;
+    r = r + m;
+    return r + real(e);
+}
+static inline real exp(real x) { return exp2(x * PE_L(1.44269504088896340736)); }
+static inline real log(real x) { return log2(x) * PE_L(0.69314718055994530942); }
+static inline real pow(real x, real y) { return exp2(y * log2(x)); }
 static inline real sqrt(real x) { return std::sqrt(x); }
 static inline real inversesqrt(real x) { return real(1) / std::sqrt(x); }
 static inline real abs(real x) { return std::fabs(x); }

@@ -12,8 +12,8 @@
 //   * inversesqrt(x) = 1/sqrt(x), normalize(v) = v * inversesqrt(dot(v,v)), length = sqrt(dot);
 //   * vector / scalar = vector * (1/scalar) (one IEEE reciprocal); scalar/scalar, vector/vector: IEEE divide;
 //   * min/max/clamp/step/sign/mod/fract : GLSL ES 3.00 §8.3 text, literally (NaN behaviour included);
-//   * sin cos tan asin acos atan : defined below, operation for operation as in the oracle (bit-exact);
-//     exp log exp2 log2 pow : CUDA libdevice.
+//   * sin cos tan asin acos atan exp2 log2 : defined below, operation for operation as in the oracle (bit-exact);
+//     exp log pow : derived from exp2 / log2 as GLSL ES 3.00 section 4.5.1 derives their precision.
 // All matrices a scene uses live in constant memory (one uniform block, <= 6 KB): every lane of a
 // warp reads the same matrix element at the same time, so each element is a constant-bank operand
 // of the FFMA that consumes it -- no load instruction, no shared-memory staging, no bank conflicts.
@@ -103,11 +103,60 @@ PE_FI float acos(float x) {
     if (x > 0.5f) return 2.0f * asin(::sqrtf(0.5f * (1.0f - x)));
     return 1.5707963267948966f - asin(x);
 }
-PE_FI float pow(float x, float y) { return ::powf(x, y); }
-PE_FI float exp(float x) { return ::expf(x); }
-PE_FI float log(float x) { return ::logf(x); }
-PE_FI float exp2(float x) { return ::exp2f(x); }
-PE_FI float log2(float x) { return ::log2f(x); }
+// exp2 / log2 are part of the pinned profile too (Cephes single-precision kernels: exp2f's degree-6 minimax on
+// [-0.5, 0.5] and logf's degree-9 on [sqrt(.5), sqrt(2)), every step one IEEE operation or an explicit FMA; scaling by
+// exact powers of two, one rounding even into the denormal range); exp, log and pow are what GLSL ES 3.00 section 4.5.1
+// derives them from: exp(x) = exp2(x * log2 e), log(x) = log2(x) * ln 2, pow(x, y) = exp2(y * log2(x)).
+// Same text, operation for operation, as oracle/glsl_compat.h.
+PE_FI float pe_pow2i(int k) { return __int_as_float((k + 127) << 23); }  // 2^k, -126 <= k <= 127
+PE_FI float exp2(float x) {
+    if (!(x == x)) return x;
+    if (x >= 128.0f) return __int_as_float(0x7f800000);
+    if (x < -150.0f) return 0.0f;
+    const float n = ::rintf(x);
+    const float f = x - n;
+    float p = 1.535336188319500e-4f;
+    p = ::fmaf(p, f, 1.339887440266574e-3f);
+    p = ::fmaf(p, f, 9.618437357674640e-3f);
+    p = ::fmaf(p, f, 5.550332471162809e-2f);
+    p = ::fmaf(p, f, 2.402264791363012e-1f);
+    p = ::fmaf(p, f, 6.931472028550421e-1f);
+    p = ::fmaf(p, f, 1.0f);
+    const int k = int(n);
+    if (k > 127) return (p * pe_pow2i(k - 64)) * 18446744073709551616.0f;
+    if (k < -126) return (p * pe_pow2i(k + 64)) * 5.421010862427522170e-20f;
+    return p * pe_pow2i(k);
+}
+PE_FI float log2(float x) {
+    if (!(x == x) || x < 0.0f) return __int_as_float(0x7fc00000);
+    if (x == 0.0f) return __int_as_float(0xff800000);
+    if (x == __int_as_float(0x7f800000)) return x;
+    int bits = __float_as_int(x), e = 0;
+    if (bits < 0x00800000) { bits = __float_as_int(x * 33554432.0f); e = -25; }   // denormal: scale by 2^25 first
+    e += ((bits >> 23) & 0xff) - 126;
+    float m = __int_as_float((bits & 0x007fffff) | 0x3f000000);                   // frexp: m in [0.5, 1)
+    if (m < 0.70710678118654752440f) { e -= 1; m = m + m - 1.0f; } else { m = m - 1.0f; }
+    const float z = m * m;
+    float y = 7.0376836292e-2f;
+    y = ::fmaf(y, m, -1.1514610310e-1f);
+    y = ::fmaf(y, m, 1.1676998740e-1f);
+    y = ::fmaf(y, m, -1.2420140846e-1f);
+    y = ::fmaf(y, m, 1.4249322787e-1f);
+    y = ::fmaf(y, m, -1.6668057665e-1f);
+    y = ::fmaf(y, m, 2.0000714765e-1f);
+    y = ::fmaf(y, m, -2.4999993993e-1f);
+    y = ::fmaf(y, m, 3.3333331174e-1f);
+    y = y * m * z;
+    y = ::fmaf(-0.5f, z, y);
+    float r = y * 0.44269504088896340736f;
+    r = ::fmaf(m, 0.44269504088896340736f, r);
+    r = r + y;
+    r = r + m;
+    return r + float(e);
+}
+PE_FI float exp(float x) { return exp2(x * 1.44269504088896340736f); }
+PE_FI float log(float x) { return log2(x) * 0.69314718055994530942f; }
+PE_FI float pow(float x, float y) { return exp2(y * log2(x)); }
 PE_FI float sqrt(float x) { return ::sqrtf(x); }
 PE_FI float inversesqrt(float x) { return 1.0f / ::sqrtf(x); }
 PE_FI float abs(float x) { return ::fabsf(x); }
