@@ -169,7 +169,17 @@ static inline real log2(real x) {
 }
 static inline real exp(real x) { return exp2(x * PE_L(1.44269504088896340736)); }
 static inline real log(real x) { return log2(x) * PE_L(0.69314718055994530942); }
-static inline real pow(real x, real y) { return exp2(y * log2(x)); }
+// pow: IEEE 754 / C for pow(x, 0) and for a negative base with an integral exponent, exp2(y * log2 x) otherwise
+// (same text as pe_glsl.cuh).
+static inline real pow(real x, real y) {
+    if (y == PE_L(0.0)) return PE_L(1.0);
+    if (x < PE_L(0.0) && y == std::rint(y)) {
+        const real h = y * PE_L(0.5);
+        const real r = exp2(y * log2(-x));
+        return h != std::rint(h) ? -r : r;
+    }
+    return exp2(y * log2(x));
+}
 static inline real sqrt(real x) { return std::sqrt(x); }
 static inline real inversesqrt(real x) { return real(1) / std::sqrt(x); }
 static inline real abs(real x) { return std::fabs(x); }

@@ -156,7 +156,17 @@ PE_FI float log2(float x) {
 }
 PE_FI float exp(float x) { return exp2(x * 1.44269504088896340736f); }
 PE_FI float log(float x) { return log2(x) * 0.69314718055994530942f; }
-PE_FI float pow(float x, float y) { return exp2(y * log2(x)); }
+// pow follows IEEE 754 / C for the cases scenes rely on -- pow(x, 0) = 1 and a negative base with an integral
+// exponent (scenes write pow(v, 2.0) for a square, GL compilers reduce that to v * v) -- and is exp2(y * log2 x) otherwise.
+PE_FI float pow(float x, float y) {
+    if (y == 0.0f) return 1.0f;
+    if (x < 0.0f && y == ::rintf(y)) {
+        const float h = y * 0.5f;
+        const float r = exp2(y * log2(-x));
+        return h != ::rintf(h) ? -r : r;
+    }
+    return exp2(y * log2(x));
+}
 PE_FI float sqrt(float x) { return ::sqrtf(x); }
 PE_FI float inversesqrt(float x) { return 1.0f / ::sqrtf(x); }
 PE_FI float abs(float x) { return ::fabsf(x); }

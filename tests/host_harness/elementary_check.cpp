@@ -43,6 +43,10 @@ int main(int argc, char** argv) {
         acc(lg, pe::log(ax), pe_oracle::log(ax), std::log(double(ax)));
         const float base = std::fabs(x) * 0.05f + 0.01f;
         acc(pw, pe::pow(base, y), pe_oracle::pow(base, y), std::pow(double(base), double(y)));
+        const float iy = std::rint(y);                                           // negative base, integral exponent; pow(x, 0)
+        acc(pw, pe::pow(-base, iy), pe_oracle::pow(-base, iy), std::pow(double(-base), double(iy)));
+        acc(pw, pe::pow(x, 0.0f), pe_oracle::pow(x, 0.0f), 1.0);
+        if (!same(pe::pow(-base, y), pe_oracle::pow(-base, y))) pw.mism++;       // non-integral exponent: NaN on both sides
         acc(sn, pe::sin(x), pe_oracle::sin(x), std::fabs(x) < 50.0f ? std::sin(double(x)) : NAN);
         acc(cs, pe::cos(x), pe_oracle::cos(x), std::fabs(x) < 50.0f ? std::cos(double(x)) : NAN);
         acc(at, pe::atan(x, y), pe_oracle::atan(x, y), NAN);
