@@ -544,7 +544,11 @@ class Scene:
                     return ("int", 0)
                 return ("int", int(max(-2147483648.0, min(2147483647.0, math.trunc(val)))))
             if t == "TrefoilSpecial":
-                return None  # out of scope
+                # uniform.rs:20 `TrefoilSpecial([(bool, u8, u8); 18])`; packed per element as scene.rs:644-650 uploads it
+                arr = u.value[0]
+                while len(arr) == 1 and isinstance(arr[0], list) and arr[0] and isinstance(arr[0][0], list):
+                    arr = arr[0]
+                return ("trefoil", [int(v) + int(bool(en)) * 10000 + int(col) * 1000 for en, v, col in arr])
             raise ValueError(t)
         finally:
             visited.pop()
@@ -624,7 +628,7 @@ class Scene:
         r = self.get_uniform(uid, visited)
         if r is None:
             return None
-        return float(r[1])
+        return -1.0 if r[0] == "trefoil" else float(r[1])      # uniform.rs:300-311 (`From<AnyUniformResult> for f64`)
 
     def _param_get(self, p):
         if p[0] == "v":
@@ -759,7 +763,10 @@ class Scene:
             r = self.get_uniform(uid)
             if r is None:
                 continue
-            if r[0] == "bool":
+            if r[0] == "trefoil":
+                for i, packed in enumerate(r[1]):                # scene.rs:488-492: `ts_<i>_<name>_u`, one int each
+                    table[f"ts_{i}_{name}_u"] = ("int", packed)
+            elif r[0] == "bool":
                 table[f"{name}_u"] = ("int", int(r[1]))
             elif r[0] == "int":
                 table[f"{name}_u"] = ("int", int(r[1]))

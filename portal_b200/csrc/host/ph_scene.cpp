@@ -277,7 +277,20 @@ struct Loader {
             u.kind = data.s == "Formula" ? Uniform::Formula : Uniform::FormulaInt;
             const RonValue* t = unwrap1(p);
             u.text = t && t->kind == RonValue::String ? t->s : "";
-        } else u.kind = Uniform::Unsupported;  // TrefoilSpecial: out of scope
+        } else if (data.s == "TrefoilSpecial") {
+            u.kind = Uniform::Trefoil;
+            const RonValue* arr = p;
+            while (arr && arr->kind == RonValue::List && arr->items.size() == 1 && arr->items[0]->kind == RonValue::List &&
+                   !arr->items[0]->items.empty() && arr->items[0]->items[0]->kind == RonValue::List)
+                arr = arr->items[0].get();
+            if (arr && arr->kind == RonValue::List)
+                for (size_t k = 0; k < arr->items.size() && k < 18; k++) {
+                    const RonValue& e = *arr->items[k];
+                    if (e.kind != RonValue::List || e.items.size() != 3) continue;
+                    const bool enabled = e.items[0]->kind == RonValue::Bool && e.items[0]->b;
+                    u.trefoil[k] = int(e.items[1]->num()) + (enabled ? 10000 : 0) + int(e.items[2]->num()) * 1000;
+                }
+        } else u.kind = Uniform::Unsupported;
         int id = int(sc.uniforms.size());
         sc.uniforms.push_back(u);
         sc.uniform_names.push_back(name);
@@ -729,6 +742,7 @@ bool Scene::get_uniform(int id, int& kind, double& value, std::vector<int>& visi
         case Uniform::Bool: kind = 0; value = u.b ? 1.0 : 0.0; return true;
         case Uniform::Int: kind = 1; value = double(u.i); return true;
         case Uniform::Float: case Uniform::Angle: case Uniform::Progress: kind = 2; value = u.f; return true;
+        case Uniform::Trefoil: kind = 3; value = -1.0; return true;   // uniform.rs:300-311: -1.0 wherever a number is wanted
         case Uniform::Unsupported: return false;
         default: break;
     }
@@ -937,6 +951,16 @@ bool Scene::uniform_table(std::vector<TableEntry>& out) {
         double v;
         std::vector<int> visited;
         if (!get_uniform(int(k), kind, v, visited)) continue;
+        if (kind == 3) {  // TrefoilSpecial: 18 packed ints `ts_<i>_<name>_u` (scene.rs:488-492, 644-650)
+            for (int i = 0; i < 18; i++) {
+                TableEntry t;
+                t.name = "ts_" + std::to_string(i) + "_" + uniform_names[k] + "_u";
+                t.type = PE_UNIFORM_INT;
+                t.i = uniforms[k].trefoil[i];
+                out.push_back(t);
+            }
+            continue;
+        }
         TableEntry e;
         e.name = uniform_names[k] + "_u";
         if (kind == 2) { e.type = PE_UNIFORM_FLOAT; e.f = v; }

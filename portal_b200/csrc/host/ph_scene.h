@@ -34,7 +34,8 @@ void mat_mul_vec(const Mat4& m, const double v[4], double out[4]);
 double camera_scale(const Mat4& m);
 
 struct Uniform {
-    enum Kind { Bool, Int, Float, Angle, Progress, Formula, FormulaInt, Unsupported } kind = Float;
+    enum Kind { Bool, Int, Float, Angle, Progress, Formula, FormulaInt, Trefoil, Unsupported } kind = Float;
+    int trefoil[18] = {0};  // TrefoilSpecial([(bool, u8, u8); 18]) (uniform.rs:20), packed as scene.rs:644-650 uploads it
     bool b = false;
     int i = 0;
     double f = 0.0;

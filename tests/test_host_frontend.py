@@ -42,6 +42,9 @@ def test_fixture_scene_table_matches_oracle_frontend():
     assert t["chosen_mat"] == t["portal_a_mat"] and t["ball_inv_mat"] == t["ball_mat_inv"]
     assert "portal_a_to_portal_b_mat_teleport" in t and "portal_b_to_portal_a_mat_teleport" in t
     assert "between_mat" in t and "between_q_mat" in t             # Lerp matrices
+    # TrefoilSpecial: 18 packed ints value + 10000 * enabled + 1000 * colour (scene.rs:488-492, 644-650); -1 inside formulas
+    assert "knot_u" not in t and [t[f"ts_{i}_knot_u"][1] for i in (0, 1, 2, 17)] == [0, 10005 + 1000, 10010 + 2000, 10013 + 2000]
+    assert t["knot_as_number_u"] == ("float", -2.0)
 
 
 def test_set_value_and_time_reevaluate():

@@ -79,14 +79,15 @@ def test_uniform_change_reaches_the_host_run(tmp_path):
     assert np.array_equal(_bits(got), _bits(orc.render(W, H, DEPTH["portal_in_portal"])))
 
 
-@pytest.mark.parametrize("scene", ["cone", "matryoshka", "recursive_space", "cylinder"])
+@pytest.mark.parametrize("scene", ["cone", "matryoshka", "recursive_space", "cylinder", "time_portal_spacetime", "trefoil"])
 def test_more_reference_scenes_on_host(scene, tmp_path):
     """Reference scenes beyond the five configs (tests/golden/scenes_extra): skybox sampling, Reflect / Refract,
     subspaces, the `Camera` matrix kind, and (cylinder) libm's exp/log -- on the host both sides call the same
     libm, so even that one is bit-exact here."""
     import json
     from oracle.runner import Oracle
-    with open(os.path.join(ROOT, "tests", "golden", "scenes_extra", f"{scene}.scene.json")) as f:
+    folder = "scenes_host" if scene == "trefoil" else "scenes_extra"     # trefoil: `TrefoilSpecial` packed uniforms
+    with open(os.path.join(ROOT, "tests", "golden", folder, f"{scene}.scene.json")) as f:
         ir = json.load(f)
     mono = load_tex("monoportal")["monoportal"]
     tex = {t["name"]: mono for t in ir["textures"]}

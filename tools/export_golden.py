@@ -45,10 +45,19 @@ EXTRA = ["borromean_rings", "hopf_link", "recursive_space", "mobius", "sphere_in
          "spherical_geometry", "cylinder", "non_linear", "time_portal_spacetime", "matryoshka"]
 
 
+# Scenes checked on the host harness only so far (tests/test_program_on_host.py): same IR format, separate folder so that
+# the GPU parametrisation (scenes_extra) grows only with scenes that have been seen on a GPU.
+HOST_ONLY = ["trefoil"]
+
+
 def export_extra():
-    d = os.path.join(ROOT, "tests/golden/scenes_extra")
+    for folder, names in (("scenes_extra", EXTRA), ("scenes_host", HOST_ONLY)):
+        _export_ir(os.path.join(ROOT, "tests/golden", folder), names)
+
+
+def _export_ir(d, names):
     os.makedirs(d, exist_ok=True)
-    for name in EXTRA:
+    for name in names:
         ir = frontend.scene_ir(frontend.load_scene(f"{REF}/scenes/{name}.ron"), name)
         assert all(t["path"] == "scenes/img/monoportal.png" for t in ir["textures"]), name
         with open(os.path.join(d, f"{name}.scene.json"), "w") as f:
