@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Generate + NVRTC-compile (sm_100a) the program of every scene under a directory of reference `.ron` files and,
 optionally, build the CPU oracle for the same scenes.  No GPU needed.  Prints one line per scene and a summary;
-this is how the "80 of the 82 non-empty reference scenes compile in both generators" figure in DESIGN.md is obtained.
+this is how the "81 of the 82 non-empty reference scenes compile" figure in DESIGN.md is obtained.
 
     python tools/compile_all_scenes.py /root/reference/scenes [--oracle] [--only name,name]
 """
