@@ -216,9 +216,13 @@ def run_ours(args):
 
     from portal_b200.distributed import FrameSharder, STRIP_ROWS as SR
     mode = args.mode if world > 1 else "gather"
+    if world > 1 and mode == "gather":
+        args.format = "f32"                      # the NCCL gather path assembles float frames
     if world == 1:
         target = r.full_target(w, h)
-        outs = [torch.empty((h, w, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
+        # ring of output frames larger than the 126 MB L2: 2 float frames (265 MB at 4K) or 6 RGBA8 frames (199 MB)
+        n_outs = 2 if args.format == "f32" else 6
+        outs = [torch.empty((h, w, 4), dtype=torch.float32 if args.format == "f32" else torch.uint8, device="cuda") for _ in range(n_outs)]
         sharder = None
     else:
         # default for N > 1: the render kernels store straight into rank 0's frame over NVLink (CUDA IPC).
@@ -226,7 +230,7 @@ def run_ours(args):
         # instead (both are GPU paths; the mode actually used is reported in `config.parallelism`).
         sharder, ok = None, 1
         try:
-            sharder = FrameSharder(r, w, h, rank, world, mode=mode, strip_rows=SR)
+            sharder = FrameSharder(r, w, h, rank, world, mode=mode, strip_rows=SR, fmt=args.format)
         except Exception as e:  # noqa: BLE001
             ok = 0
             print(f"[bench] rank {rank}: {mode} set-up failed ({e}); falling back to gather", file=sys.stderr)
@@ -236,6 +240,7 @@ def run_ours(args):
             if sharder is not None:
                 sharder.close()
             mode = "gather"
+            args.format = "f32"                  # the gather path assembles float frames
             sharder = FrameSharder(r, w, h, rank, world, mode=mode, strip_rows=SR)
         target = sharder.target
 
@@ -258,7 +263,10 @@ def run_ours(args):
             frame_counter[0] += 1
             r.set_cam(cam0["look_at"], cam0["alpha"] + 2.0 * math.pi * k / args.orbit, cam0["beta"], cam0["r"])
         if world == 1:
-            r.draw_texture(target, outs[i & 1].data_ptr(), 0, sptr)
+            if args.format == "f32":
+                r.draw_texture(target, outs[i & 1].data_ptr(), 0, sptr)
+            else:
+                r.draw_texture_rgba8(target, outs[i % len(outs)].data_ptr(), sptr)
         else:
             sharder.render(i, sptr)
 
@@ -323,9 +331,12 @@ def run_ours(args):
             r.render_host_ptr(w, h, host8.data_ptr(), rgba8=True)
         else:
             def consume():
-                if rank == 0:
+                if rank == 0 and args.format == "f32":
                     r._check(r._lib.pe_quantize_rgba8(r._ctx, sharder.frame_ptr, q8.data_ptr(), w * h, sptr))
                     host8.copy_(q8, non_blocking=True)
+                elif rank == 0:                  # the assembled frame is RGBA8 already
+                    stream.synchronize()
+                    r._check(r._lib.pe_memcpy_d2h(r._ctx, host8.data_ptr(), sharder.frame_ptr, w * h * 4, sptr))
             step(i, consume)
             torch.cuda.synchronize()
     for i in range(2):
@@ -402,13 +413,14 @@ def run_ours(args):
         value = w * h * args.steps / (total_ms * 1e-3) / 1e6
         # roofline of the dominant kernel (pe_render_kernel): algorithmic bytes = 16 B/pixel written
         #  x pixels one launch shades, / its mean launch duration (CUDA events)
-        alg_bytes = 16.0 * n_px_local
+        bpp = 16.0 if args.format == "f32" else 4.0
+        alg_bytes = bpp * n_px_local
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(f"{args.scene}_{w}x{h}_d{depth}")
+                traffic = json.load(f).get(f"{args.scene}_{w}x{h}_d{depth}") if args.format == "f32" else None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_oracle_rate(args.scene, w, h, depth, budget_s=20.0)
@@ -424,11 +436,15 @@ def run_ours(args):
                            f"{world} GPUs x cyclic {STRIP_ROWS}-row strips + 1 NCCL gather + de-interleave" if mode == "gather" else
                            f"{world} GPUs x cyclic {STRIP_ROWS}-row strips, kernels store into rank 0's frame over NVLink (CUDA IPC), stream-ordered flag words, no collective"),
                        "scheduler": "persistent warps + per-bounce refill" if args.persistent else "one thread per pixel, 8x4 warp tiles, 512-thread blocks, <= 64 regs",
-                       "l2": "each step writes a 132.7 MB frame (> 126 MB L2) into alternating buffers; inputs are a <8 KB constant block"},
+                       "frame_format": "float RGBA (16 B/pixel)" if args.format == "f32" else "RGBA8 quantised by the kernel (4 B/pixel)",
+                       "l2": ("each step writes a 132.7 MB frame (> 126 MB L2) into alternating buffers" if args.format == "f32" else
+                              ("each step writes a 33.2 MB frame into a ring of 6 (199 MB > 126 MB L2)" if world == 1 else
+                               "each step writes a 33.2 MB frame into one of rank 0's two buffers (L2-resident: this format is a bandwidth experiment)")) +
+                             "; inputs are a <8 KB constant block"},
             "kernel_ms": round(kernel_ms, 4),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": round(achieved / peaks["hbm_gbs"], 5), "traffic": traffic, "peak_source": peak_src,
-                         "note": "16 B/pixel algorithmic; the loop is fp32-ALU/latency bound, see DESIGN.md §6"},
+                         "note": f"{int(bpp)} B/pixel algorithmic; the loop is fp32-ALU/latency bound, see DESIGN.md §6"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_rate, 2), "unit": "Mpixels/s", "h2d_bytes_per_step": e2e_h2d_bytes(r),
                     "d2h_bytes_per_step": w * h * 4, "steps": e2e_steps,
@@ -474,6 +490,9 @@ def main():
     ap.add_argument("--orbit", type=int, default=0, help="camera orbit of this many frames per turn (config 5: 360)")
     ap.add_argument("--mode", default="p2p", choices=["gather", "p2p"], help="N > 1: how strips reach rank 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--format", default="f32", choices=["f32", "rgba8"],
+                    help="frame format of the timed steps: f32 = float RGBA, 16 B/pixel (the metric's definition, SURVEY.md 8d); "
+                         "rgba8 = what the reference's RGBA8 render target holds, 4 B/pixel, quantised by the kernel (p2p mode for N > 1)")
     args = ap.parse_args()
     w, h, d = WORKLOADS[args.scene]
     args.width, args.height, args.depth = args.width or w, args.height or h, args.depth or d

@@ -91,10 +91,14 @@ class FrameSharder:
 
     ARRIVED, CONSUMED = 0, 32  # word offsets in a rank's 256-byte signal block
 
-    def __init__(self, renderer, width: int, height: int, rank: int, world: int, mode: str = "gather", strip_rows: int = STRIP_ROWS):
+    def __init__(self, renderer, width: int, height: int, rank: int, world: int, mode: str = "gather", strip_rows: int = STRIP_ROWS,
+                 fmt: str = "f32"):
+        """fmt "rgba8" (p2p mode only): rank 0's frames are RGBA8 -- the kernels quantise as they store (pe_render_rgba8), a
+        quarter of the NVLink traffic of float frames."""
         import torch
         import torch.distributed as dist
-        assert mode in ("gather", "p2p")
+        assert mode in ("gather", "p2p") and fmt in ("f32", "rgba8") and not (fmt == "rgba8" and mode == "gather")
+        self.fmt = fmt
         self.r, self.w, self.h, self.rank, self.world, self.mode, self.s = renderer, width, height, rank, world, mode, strip_rows
         self.spr = strips_per_rank(height, world, strip_rows)
         lib, ctx = renderer._lib, renderer._ctx
@@ -113,7 +117,7 @@ class FrameSharder:
         if world > 8:
             raise ValueError("p2p mode supports up to 8 ranks (one NVSwitch box)")
         self.target = make_target(width, height, rank, world, strip_rows, full_frame=True)
-        self.frame_bytes = width * height * 16
+        self.frame_bytes = width * height * (16 if fmt == "f32" else 4)
 
         def dmalloc(nbytes):
             p = C.c_void_p()
@@ -173,7 +177,10 @@ class FrameSharder:
         dst = self.frames + (f & 1) * self.frame_bytes
         if self.rank != 0 and f > 2:
             r._check(lib.pe_stream_wait_geq_u32(ctx, self.sig + 4 * self.CONSUMED, f - 2, stream_ptr))
-        r.draw_texture(self.target, dst, 0, stream_ptr)
+        if self.fmt == "f32":
+            r.draw_texture(self.target, dst, 0, stream_ptr)
+        else:
+            r.draw_texture_rgba8(self.target, dst, stream_ptr)
         if self.rank != 0:
             ptrs = (C.c_void_p * 1)(self.sig0 + 4 * (self.ARRIVED + self.rank))
             r._check(lib.pe_signal_u32(ctx, ptrs, 1, f, stream_ptr))
