@@ -124,6 +124,11 @@ static inline real acos(real x) {
 // exp2 / log2: pinned like the trigonometric functions (same text as pe_glsl.cuh; std::frexp / std::ldexp of 1 are exact,
 // so they equal the device's bit manipulation); exp, log, pow derived from them as GLSL ES 3.00 section 4.5.1 does.
 static inline real pe_pow2i(int k) { return std::ldexp(real(1), k); }
+static inline real pe_scale2(real p, int k) {
+    if (k > 127) return (p * pe_pow2i(k - 64)) * PE_L(18446744073709551616.0);
+    if (k < -126) return (p * pe_pow2i(k + 64)) * PE_L(5.421010862427522170e-20);
+    return p * pe_pow2i(k);
+}
 static inline real exp2(real x) {
     if (!(x == x)) return x;
     if (x >= PE_L(128.0)) return std::numeric_limits<real>::infinity();
@@ -137,10 +142,7 @@ static inline real exp2(real x) {
     p = pe_fma(p, f, PE_L(2.402264791363012e-1));
     p = pe_fma(p, f, PE_L(6.931472028550421e-1));
     p = pe_fma(p, f, PE_L(1.0));
-    const int k = int(n);
-    if (k > 127) return (p * pe_pow2i(k - 64)) * PE_L(18446744073709551616.0);
-    if (k < -126) return (p * pe_pow2i(k + 64)) * PE_L(5.421010862427522170e-20);
-    return p * pe_pow2i(k);
+    return pe_scale2(p, int(n));
 }
 static inline real log2(real x) {
     if (!(x == x) || x < PE_L(0.0)) return std::numeric_limits<real>::quiet_NaN();
@@ -167,7 +169,22 @@ static inline real log2(real x) {
     r = r + m;
     return r + real(e);
 }
-static inline real exp(real x) { return exp2(x * PE_L(1.44269504088896340736)); }
+static inline real exp(real x) {  // Cephes expf (same text as pe_glsl.cuh)
+    if (!(x == x)) return x;
+    if (x > PE_L(88.72283905206835)) return std::numeric_limits<real>::infinity();
+    if (x < PE_L(-103.972077083991796)) return PE_L(0.0);
+    const real n = std::rint(x * PE_L(1.44269504088896340736));
+    real r = pe_fma(n, PE_L(-0.693359375), x);
+    r = pe_fma(n, PE_L(2.12194440e-4), r);
+    const real z = r * r;
+    real p = PE_L(1.9875691500e-4);
+    p = pe_fma(p, r, PE_L(1.3981999507e-3));
+    p = pe_fma(p, r, PE_L(8.3334519073e-3));
+    p = pe_fma(p, r, PE_L(4.1665795894e-2));
+    p = pe_fma(p, r, PE_L(1.6666665459e-1));
+    p = pe_fma(p, r, PE_L(5.0000001201e-1));
+    return pe_scale2(pe_fma(p, z, r) + PE_L(1.0), int(n));
+}
 static inline real log(real x) { return log2(x) * PE_L(0.69314718055994530942); }
 // pow: IEEE 754 / C for pow(x, 0) and for a negative base with an integral exponent, exp2(y * log2 x) otherwise
 // (same text as pe_glsl.cuh).

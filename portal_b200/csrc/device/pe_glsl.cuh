@@ -109,6 +109,11 @@ PE_FI float acos(float x) {
 // derives them from: exp(x) = exp2(x * log2 e), log(x) = log2(x) * ln 2, pow(x, y) = exp2(y * log2(x)).
 // Same text, operation for operation, as oracle/glsl_compat.h.
 PE_FI float pe_pow2i(int k) { return __int_as_float((k + 127) << 23); }  // 2^k, -126 <= k <= 127
+PE_FI float pe_scale2(float p, int k) {                                  // p * 2^k, -190 <= k <= 191, rounded once
+    if (k > 127) return (p * pe_pow2i(k - 64)) * 18446744073709551616.0f;
+    if (k < -126) return (p * pe_pow2i(k + 64)) * 5.421010862427522170e-20f;
+    return p * pe_pow2i(k);
+}
 PE_FI float exp2(float x) {
     if (!(x == x)) return x;
     if (x >= 128.0f) return __int_as_float(0x7f800000);
@@ -122,10 +127,7 @@ PE_FI float exp2(float x) {
     p = ::fmaf(p, f, 2.402264791363012e-1f);
     p = ::fmaf(p, f, 6.931472028550421e-1f);
     p = ::fmaf(p, f, 1.0f);
-    const int k = int(n);
-    if (k > 127) return (p * pe_pow2i(k - 64)) * 18446744073709551616.0f;
-    if (k < -126) return (p * pe_pow2i(k + 64)) * 5.421010862427522170e-20f;
-    return p * pe_pow2i(k);
+    return pe_scale2(p, int(n));
 }
 PE_FI float log2(float x) {
     if (!(x == x) || x < 0.0f) return __int_as_float(0x7fc00000);
@@ -154,7 +156,23 @@ PE_FI float log2(float x) {
     r = r + m;
     return r + float(e);
 }
-PE_FI float exp(float x) { return exp2(x * 1.44269504088896340736f); }
+// exp: Cephes expf -- n = rint(x log2 e), r = x - n ln 2 in two parts (Cody-Waite), degree-5 kernel for e^r - 1 - r.
+PE_FI float exp(float x) {
+    if (!(x == x)) return x;
+    if (x > 88.72283905206835f) return __int_as_float(0x7f800000);
+    if (x < -103.972077083991796f) return 0.0f;
+    const float n = ::rintf(x * 1.44269504088896340736f);
+    float r = ::fmaf(n, -0.693359375f, x);
+    r = ::fmaf(n, 2.12194440e-4f, r);
+    const float z = r * r;
+    float p = 1.9875691500e-4f;
+    p = ::fmaf(p, r, 1.3981999507e-3f);
+    p = ::fmaf(p, r, 8.3334519073e-3f);
+    p = ::fmaf(p, r, 4.1665795894e-2f);
+    p = ::fmaf(p, r, 1.6666665459e-1f);
+    p = ::fmaf(p, r, 5.0000001201e-1f);
+    return pe_scale2(::fmaf(p, z, r) + 1.0f, int(n));
+}
 PE_FI float log(float x) { return log2(x) * 0.69314718055994530942f; }
 // pow follows IEEE 754 / C for the cases scenes rely on -- pow(x, 0) = 1 and a negative base with an integral
 // exponent (scenes write pow(v, 2.0) for a square, GL compilers reduce that to v * v) -- and is exp2(y * log2 x) otherwise.
