@@ -20,7 +20,7 @@
 //   * min/max/clamp/step/sign/mod/fract follow the GLSL ES 3.00 spec text
 //     (section 8.3) literally, including their behaviour on NaN;
 //   * sin cos tan asin acos atan are defined HERE (same sequence of IEEE operations as the kernel);
-//     exp2 log2 are pinned as well; exp log pow are derived from them (GLSL ES 3.00 section 4.5.1).
+//     exp2 log2 exp are pinned as well; log pow are derived from log2 / exp2 (GLSL ES 3.00 section 4.5.1).
 // PE_REAL selects the arithmetic type: float (the parity reference) or double
 // (used only to flag ill-conditioned pixels).
 #pragma once
@@ -122,7 +122,7 @@ static inline real acos(real x) {
     return PE_L(1.5707963267948966) - asin(x);
 }
 // exp2 / log2: pinned like the trigonometric functions (same text as pe_glsl.cuh; std::frexp / std::ldexp of 1 are exact,
-// so they equal the device's bit manipulation); exp, log, pow derived from them as GLSL ES 3.00 section 4.5.1 does.
+// so they equal the device's bit manipulation); exp is pinned too, log and pow are derived as GLSL ES 3.00 section 4.5.1 does.
 static inline real pe_pow2i(int k) { return std::ldexp(real(1), k); }
 static inline real pe_scale2(real p, int k) {
     if (k > 127) return (p * pe_pow2i(k - 64)) * PE_L(18446744073709551616.0);

@@ -12,8 +12,8 @@
 //   * inversesqrt(x) = 1/sqrt(x), normalize(v) = v * inversesqrt(dot(v,v)), length = sqrt(dot);
 //   * vector / scalar = vector * (1/scalar) (one IEEE reciprocal); scalar/scalar, vector/vector: IEEE divide;
 //   * min/max/clamp/step/sign/mod/fract : GLSL ES 3.00 §8.3 text, literally (NaN behaviour included);
-//   * sin cos tan asin acos atan exp2 log2 : defined below, operation for operation as in the oracle (bit-exact);
-//     exp log pow : derived from exp2 / log2 as GLSL ES 3.00 section 4.5.1 derives their precision.
+//   * sin cos tan asin acos atan exp2 log2 exp : defined below, operation for operation as in the oracle (bit-exact);
+//     log pow : derived from log2 / exp2 as GLSL ES 3.00 section 4.5.1 derives their precision.
 // All matrices a scene uses live in constant memory (one uniform block, <= 6 KB): every lane of a
 // warp reads the same matrix element at the same time, so each element is a constant-bank operand
 // of the FFMA that consumes it -- no load instruction, no shared-memory staging, no bank conflicts.
