@@ -111,6 +111,13 @@ PE_API const char* ph_player_last_error(ph_player* p);
 /* Route teleport_external_ray through ctx (which must hold the scene's compiled program). Without a
  * context the camera never teleports: frames whose camera does not cross a portal are unaffected. */
 PE_API int ph_player_attach(ph_player* p, pe_ctx* ctx);
+/* Or route teleport_external_ray through a caller-supplied function (what the reference's own `teleport_external_ray`
+ * would be if the Rust side kept it): called with the segment a -> b in float64 after the player has evaluated the
+ * scene for the current frame; fills pos[3] and the two flags, returns 0 on success.  `have a result` is derived the
+ * reference's way: pos != (0, 0, 0) (src/main.rs:1399).  Passing NULL detaches. */
+typedef int (*ph_probe_fn)(void* user, const double a[3], const double b[3], double pos[3], int32_t* encounter_object,
+                           int32_t* change_subspace);
+PE_API int ph_player_set_probe(ph_player* p, ph_probe_fn fn, void* user);
 PE_API int ph_player_init_stage(ph_player* p, const char* stage_name);
 PE_API int ph_player_init_animation(ph_player* p, const char* animation_name);
 PE_API int ph_player_select_camera(ph_player* p, const char* camera_name);

@@ -20,6 +20,10 @@ class PeTarget(C.Structure):
                 ("strip_step", C.c_int32), ("n_strips", C.c_int32), ("full_frame_layout", C.c_int32)]
 
 
+PH_PROBE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                          C.POINTER(C.c_int32), C.POINTER(C.c_int32))
+
+
 class PhFrameParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("depth", C.c_int32), ("aa_count", C.c_int32),
                 ("aa_start", C.c_int32), ("use_camera", C.c_int32), ("look_at", C.c_double * 3), ("alpha", C.c_double),
@@ -127,6 +131,7 @@ def lib() -> C.CDLL:
         "ph_player_free": (None, [vp]),
         "ph_player_last_error": (cp, [vp]),
         "ph_player_attach": (i32, [vp, vp]),
+        "ph_player_set_probe": (i32, [vp, vp, vp]),
         "ph_player_init_stage": (i32, [vp, cp]),
         "ph_player_init_animation": (i32, [vp, cp]),
         "ph_player_select_camera": (i32, [vp, cp]),

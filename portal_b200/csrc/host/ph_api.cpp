@@ -369,6 +369,28 @@ int ph_player_attach(ph_player* p, pe_ctx* ctx) {
     return 0;
 }
 
+int ph_player_set_probe(ph_player* p, ph_probe_fn fn, void* user) {
+    if (!p) return 1;
+    p->ctx = nullptr;
+    if (!fn) {
+        p->player.probe = nullptr;
+        return 0;
+    }
+    p->player.probe = [p, fn, user](const double a[3], const double b[3], double pos[3], bool& have, bool& enc, bool& chg) {
+        int32_t eo = 0, cs = 0;
+        pos[0] = pos[1] = pos[2] = 0.0;
+        if (fn(user, a, b, pos, &eo, &cs) != 0) {
+            p->player.error = "the caller's probe function failed";
+            return false;
+        }
+        have = !(pos[0] == 0.0 && pos[1] == 0.0 && pos[2] == 0.0);   // main.rs:1399
+        enc = eo != 0;
+        chg = cs != 0;
+        return true;
+    };
+    return 0;
+}
+
 int ph_player_init_stage(ph_player* p, const char* name) {
     if (!p || !name) return 1;
     return p->player.init_stage_by_name(name) ? 0 : pfail(p, p->player.error);

@@ -157,6 +157,27 @@ class HostPlayer:
     def update(self, time_seconds: float):
         self._check(self._lib.ph_player_update(self._p, float(time_seconds)))
 
+    def set_probe(self, fn):
+        """fn(a[3], b[3]) -> (pos[3] | None, encounter_object, change_subspace): teleport_external_ray supplied by the caller
+        (tests use the CPU oracle's probe here); None detaches."""
+        if fn is None:
+            self._check(self._lib.ph_player_set_probe(self._p, None, None))
+            self._probe_cb = None
+            return
+
+        def tramp(_user, a, b, pos, enc, chg):
+            try:
+                p, e, c = fn([a[0], a[1], a[2]], [b[0], b[1], b[2]])
+                for k in range(3):
+                    pos[k] = 0.0 if p is None else float(p[k])
+                enc[0], chg[0] = int(bool(e)), int(bool(c))
+                return 0
+            except Exception:                       # noqa: BLE001 -- must not propagate through the C frame
+                return 1
+
+        self._probe_cb = capi.PH_PROBE_FN(tramp)         # keep the trampoline alive
+        self._check(self._lib.ph_player_set_probe(self._p, C.cast(self._probe_cb, C.c_void_p), None))
+
     def set_run_animations(self, on: bool):
         self._check(self._lib.ph_player_set_run_animations(self._p, int(on)))
 

@@ -190,6 +190,58 @@ def test_stereo_eye_is_carried_through_the_gate_on_the_oracle():
     assert np.allclose(np.asarray(hp2.camera_state()["left_eye"]).reshape(4, 4)[3, :3], plain_left[:3], atol=1e-15)
 
 
+def _oracle_probe_for_host(orc, hs, hp):
+    """The same CPU probe, attached to the C++ player through ph_player_set_probe."""
+    def probe(a, b):
+        orc.set_uniforms({k: v for k, (_, v) in hs.uniform_table().items()})
+        cs = hp.camera_state()
+        pos, _, enc, chg = orc.probe(a, b, camera=cs["camera"], camera_scale=cs["scale"], camera_mul_inv=cs["camera_mul_inv"],
+                                     camera_in_subspace=int(cs["in_subspace"]))
+        have = not (pos[0] == 0 and pos[1] == 0 and pos[2] == 0)
+        return ([float(x) for x in pos] if have else None, enc, chg)
+    return probe
+
+
+def test_cpp_player_teleports_like_the_oracle_player_on_the_cpu():
+    """teleport_camera / teleport_matrix / teleport_eye_matrices of the C++ player, driven by the CPU oracle's probe through
+    ph_player_set_probe, against the oracle player driven by the same probe: every camera, eye and teleport matrix and the
+    probe count, bit for bit -- the walk through the gate and the stereo pair straddling it, no GPU involved."""
+    from oracle import frontend
+    from oracle.animation import Player
+    from oracle.runner import Oracle
+    orc = Oracle(frontend.scene_ir(frontend.load_scene(FIXTURE), "two_spheres"), variant="strict")
+    s = frontend.load_scene(FIXTURE)
+    p = Player(s, probe=_oracle_probe(orc))
+    hs = HostScene.from_file(FIXTURE)
+    hp = HostPlayer(hs)
+    hp.set_probe(_oracle_probe_for_host(orc, hs, hp))
+    p.init_animation("through")
+    hp.init_animation("through")
+    for k in range(21):
+        t = 4.0 * k / 20 * 0.999
+        p.update(t)
+        hp.update(t)
+        _assert_same_state(p, hp, s, hs, ("through", k))
+        assert hp.camera_state()["n_probes"] == p.n_probes
+    assert p.n_probes == 23 and p.cam.teleport_matrix != frontend.mat_identity()
+    # stereo pair straddling the gate
+    s2 = frontend.load_scene(FIXTURE)
+    p2 = Player(s2, probe=_oracle_probe(orc))
+    p2.draw_side_by_side, p2.eye_distance = True, 0.25
+    hs2 = HostScene.from_file(FIXTURE)
+    hp2 = HostPlayer(hs2)
+    hp2.set_probe(_oracle_probe_for_host(orc, hs2, hp2))
+    hp2.set_stereo(True, 0.25)
+    for pl in (p2, hp2):
+        pl.select_camera("beside_gate")
+        pl.update(0.0)
+    _assert_same_state(p2, hp2, s2, hs2, "stereo")
+    assert hp2.camera_state()["n_probes"] == 5
+    hp2.set_probe(None)                                                              # detached: plain translations again
+    hp2.update(0.0)
+    assert hp2.camera_state()["n_probes"] == 5
+
+
 def _oracle_probe(orc):
     def probe(player, a, b):
         table = player.scene.uniform_table()
