@@ -627,6 +627,7 @@ int pe_set_option(pe_ctx* c, const char* key, int value) {
     else if (k == "specialize_matrices") c->opts.specialize_matrices = value != 0;
     else if (k == "hoist_planes") c->opts.hoist_planes = value != 0;
     else if (k == "lazy_planes") c->opts.lazy_planes = value != 0;
+    else if (k == "with_probe") c->opts.with_probe = value != 0;   // pe_probe_ray turns it on by itself; exposed for inspection
     else return c->fail("unknown option `" + k + "`");
     // options change the generated program
     if (c->has_gpu) {

@@ -7,6 +7,7 @@
 //   ./run block.bin W H out.f32 [tex0.rgba W0 H0 [tex1.rgba W1 H1 ...]]
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "cuda_on_host.h"
@@ -28,6 +29,22 @@ static std::vector<unsigned char> slurp(const char* path) {
 int main(int argc, char** argv) {
     if (argc < 5) return 2;
     const std::vector<unsigned char> block = slurp(argv[1]);
+#if PE_WITH_PROBE
+    if (std::string(argv[2]) == "probe") {   // ./run block.bin probe ax ay az bx by bz: teleport_external_ray on the host
+        if (argc < 9 || block.size() != sizeof(pe::PeConstBlock)) return 2;
+        std::memcpy(&PE_C, block.data(), sizeof PE_C);
+        float out6[6] = {0, 0, 0, 0, 0, 0};
+        PeProbe P{float(std::atof(argv[3])), float(std::atof(argv[4])), float(std::atof(argv[5])), float(std::atof(argv[6])),
+                  float(std::atof(argv[7])), float(std::atof(argv[8])), out6};
+        blockDim = pe_uint3{32, 1, 1};
+        gridDim = pe_uint3{1, 1, 1};
+        blockIdx = pe_uint3{0, 0, 0};
+        threadIdx = pe_uint3{0, 0, 0};
+        pe_probe_kernel(P);
+        std::printf("%a %a %a %a %a %a\n", out6[0], out6[1], out6[2], out6[3], out6[4], out6[5]);
+        return 0;
+    }
+#endif
     const int w = std::atoi(argv[2]), h = std::atoi(argv[3]);
     if (block.size() != sizeof(pe::PeConstBlock)) {
         std::fprintf(stderr, "uniform block is %zu bytes, program expects %zu\n", block.size(), sizeof(pe::PeConstBlock));

@@ -123,3 +123,40 @@ def test_renderer_flags_on_host(tmp_path):
         want = orc.render(W, H, DEPTH[scene], **kw)
         assert np.array_equal(_bits(got), _bits(want)), tag
         assert not np.array_equal(_bits(want), _bits(plain)), tag            # the switch really changes the frame
+
+
+def test_probe_kernel_on_host_equals_oracle_probe(tmp_path):
+    """The camera-teleportation probe (pe_probe_kernel, the hand-written restatement of frag.glsl:166-257) run on the host
+    against the oracle's probe: the same segments tests/test_parity_gpu.py::test_external_ray_probe uses on the GPU."""
+    from oracle.runner import Oracle
+    cases = (("portal_in_portal", [([0, 0, -0.5], [0, 0, -1.5]), ([0, 0, 0.5], [0, 0, 0.2]), ([0.1, 0.05, -0.9], [0.12, 0.02, -1.3]),
+                                   ([0.2, 0.1, 0.5], [0.1, 0.0, 1.5]), ([0, 0, -0.5], [0, 0, -5.0])]),
+             ("monoportal", [([0.0, 0.1, 1.0], [0.0, 0.0, -1.0]), ([1.0, 0.3, 0.2], [-1.0, 0.1, -0.2]), ([3.0, 3.0, 3.0], [3.5, 3.0, 3.0])]))
+    crossed = 0
+    for scene, segs in cases:
+        ir = load_ir(scene)
+        r = SceneRenderer(ir, device=-1, options={"with_probe": 1})
+        r.render_depth = DEPTH[scene]
+        if "teleport_light_u" in ir["uniforms"]:
+            r.set_uniform("teleport_light_u", 1)                  # main.rs:1367: the probe forces it on
+        block, src = r.uniform_block(2, 3), r.source()
+        assert "#define PE_WITH_PROBE 1" in src
+        d = tmp_path / scene
+        d.mkdir()
+        (d / "prog.cu").write_text(src)
+        (d / "block.bin").write_bytes(block)
+        cc = subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", f'-DPROGRAM_FILE="{d / "prog.cu"}"', "-I", HARNESS,
+                             os.path.join(HARNESS, "run_program.cpp"), "-o", str(d / "run")], capture_output=True, text=True, timeout=900)
+        assert cc.returncode == 0, cc.stderr[-3000:]
+        orc = Oracle(ir, "strict", textures=load_tex(scene))
+        for a, b in segs:
+            a32, b32 = np.asarray(a, np.float32), np.asarray(b, np.float32)
+            run = subprocess.run([str(d / "run"), str(d / "block.bin"), "probe"] + [float(x).hex() for x in list(a32) + list(b32)],
+                                 capture_output=True, text=True, timeout=300)
+            assert run.returncode == 0, run.stderr
+            out = np.asarray([float.fromhex(x) for x in run.stdout.split()], dtype=np.float32)
+            rpos, rhr, reo, rcs = orc.probe(a, b)
+            assert np.array_equal(out[:3].view(np.uint32), rpos.view(np.uint32)), (scene, a, b, out, rpos)
+            assert (out[3] != 0, out[4] != 0, out[5] != 0) == (rhr, reo, rcs), (scene, a, b)
+            crossed += int(rhr)
+    assert crossed >= 3
