@@ -101,7 +101,9 @@ PE_API int pe_scene_uniform_block(pe_ctx* ctx, int width, int height, const void
  * "min_blocks", "hoist_planes" (0/1, default 1: per-plane normal algebra evaluated once per upload on the
  * host), "lazy_planes" (0/1, default 1: a plane test stops as soon as its result is certain to be
  * rejected, same pixels), "with_probe" (0/1, default 0: also generate the camera-teleportation probe kernel; pe_probe_ray
- * switches it on by itself), "lineinfo" (0/1, default 1), "unroll_loops" (0/1, default 1; 0 keeps the loops of
+ * switches it on by itself), "adaptive" (0/1, default 1: an int uniform or a matrix structure that differed between
+ * renders more than 4 times stops being a specialisation constant, which bounds recompilation when an animation
+ * drives it), "lineinfo" (0/1, default 1), "unroll_loops" (0/1, default 1; 0 keeps the loops of
  * user snippets rolled).  Set before pe_scene_compile. */
 PE_API int pe_set_option(pe_ctx* ctx, const char* key, int value);
 

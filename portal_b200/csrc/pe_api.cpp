@@ -119,6 +119,12 @@ struct pe_ctx {
     // pe_submit_host_rgba8 pipeline
     struct Slot { void* dev = nullptr; size_t bytes = 0; cudaEvent_t rendered = nullptr, copied = nullptr; uint64_t ticket = 0; };
     Slot slots[PE_PIPELINE_DEPTH];
+    // adaptive de-specialisation: a slot whose value differed between renders more than kMaxRespecialisations times is read
+    // from the constant block from then on (bounds NVRTC compiles when an animation drives an int or a matrix structure)
+    std::vector<int> last_ints, int_changes;
+    std::vector<std::pair<unsigned, unsigned>> last_masks;
+    std::vector<int> mat_changes;
+    bool adapt = true;
     cudaStream_t copy_stream = nullptr;
     uint64_t next_ticket = 0;
     size_t scratch8_bytes = 0;
@@ -283,6 +289,8 @@ std::vector<int> variant_key(pe_ctx* c, const std::vector<int>& ints, const std:
     if (c->opts.specialize_matrices)
         for (auto& zo : masks) key.push_back(int(zo.first | (zo.second << 16)));
     key.push_back(c->opts.with_probe ? 1 : 0);
+    for (char d : c->opts.dynamic_ints) key.push_back(d);
+    for (char d : c->opts.dynamic_mats) key.push_back(d);
     return key;
 }
 
@@ -343,11 +351,31 @@ bool compile_cubin(pe_ctx* c, const std::string& source, std::vector<char>& cubi
     return true;
 }
 
+const int kMaxRespecialisations = 4;
+
 // Make the variant for the current integer uniforms current (generate / compile / load as needed).
 bool select_variant(pe_ctx* c) {
     ensure_layout(c);
     std::vector<int> ints = current_ints(c);
     std::vector<std::pair<unsigned, unsigned>> masks = matrix_masks(c);
+    if (c->adapt) {
+        c->opts.dynamic_ints.resize(ints.size(), 0);
+        c->opts.dynamic_mats.resize(masks.size(), 0);
+        c->int_changes.resize(ints.size(), 0);
+        c->mat_changes.resize(masks.size(), 0);
+        if (c->last_ints.size() == ints.size())
+            for (size_t k = 0; k < ints.size(); k++)
+                if (ints[k] != c->last_ints[k] && ++c->int_changes[k] > kMaxRespecialisations) c->opts.dynamic_ints[k] = 1;
+        if (c->last_masks.size() == masks.size())
+            for (size_t k = 0; k < masks.size(); k++)
+                if (masks[k] != c->last_masks[k] && ++c->mat_changes[k] > kMaxRespecialisations) c->opts.dynamic_mats[k] = 1;
+        c->last_ints = ints;
+        c->last_masks = masks;
+    }
+    for (size_t k = 0; k < ints.size() && k < c->opts.dynamic_ints.size(); k++)
+        if (c->opts.dynamic_ints[k]) ints[k] = 0;                       // not part of the key, not baked in
+    for (size_t k = 0; k < masks.size() && k < c->opts.dynamic_mats.size(); k++)
+        if (c->opts.dynamic_mats[k]) masks[k] = {0u, 0u};               // general matrix: full FFMA chain
     std::vector<int> key = variant_key(c, ints, masks);
     auto it = c->variants.find(key);
     if (it == c->variants.end()) {
@@ -489,6 +517,12 @@ int pe_scene_begin(pe_ctx* c) {
     c->current = nullptr;
     c->scene = SceneDesc();
     c->layout_valid = false;
+    c->last_ints.clear();
+    c->int_changes.clear();
+    c->last_masks.clear();
+    c->mat_changes.clear();
+    c->opts.dynamic_ints.clear();
+    c->opts.dynamic_mats.clear();
     c->cblock.clear();
     c->pending_mat.clear();
     c->pending_f.clear();
@@ -628,6 +662,7 @@ int pe_set_option(pe_ctx* c, const char* key, int value) {
     else if (k == "hoist_planes") c->opts.hoist_planes = value != 0;
     else if (k == "lazy_planes") c->opts.lazy_planes = value != 0;
     else if (k == "with_probe") c->opts.with_probe = value != 0;   // pe_probe_ray turns it on by itself; exposed for inspection
+    else if (k == "adaptive") c->adapt = value != 0;
     else return c->fail("unknown option `" + k + "`");
     // options change the generated program
     if (c->has_gpu) {
@@ -823,9 +858,11 @@ int pe_probe_ray(pe_ctx* c, const float a[3], const float b[3], float pos_out[3]
     auto tl = c->layout.int_slot.find("teleport_light_u");
     int saved = 0;
     if (tl != c->layout.int_slot.end()) { saved = *islot(c, tl->second); *islot(c, tl->second) = 1; }
-    const bool had_probe = c->opts.with_probe;
+    const bool had_probe = c->opts.with_probe, had_adapt = c->adapt;
     c->opts.with_probe = true;
+    c->adapt = false;                 // the probe's own `teleport_light_u` = 1 is not a scene change
     bool ok = select_variant(c);
+    c->adapt = had_adapt;
     if (ok) update_derived(c);
     struct { float ax, ay, az, bx, by, bz; void* out; } P;
     float host[6] = {0, 0, 0, 0, 0, 0};

@@ -588,15 +588,16 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     hd << "#define _camera_right_eye (PE_C.m[" << (L.camera_slot + 3) << "])\n";
     for (int k = 0; k < L.n_float; k++) hd << "#define " << L.floats[k] << " (PE_C.f[" << k << "])\n";
     for (int k = 0; k < kNumRendererFloats; k++) hd << "#define " << kRendererFloats[k] << " (PE_C.f[" << (L.n_float + k) << "])\n";
+    auto int_is_dynamic = [&](int slot) { return size_t(slot) < opts.dynamic_ints.size() && opts.dynamic_ints[size_t(slot)]; };
     for (int k = 0; k < L.n_int; k++) {
-        if (opts.specialize_ints && size_t(k) < int_values.size())
+        if (opts.specialize_ints && !int_is_dynamic(k) && size_t(k) < int_values.size())
             hd << "#define " << L.ints[k] << " (" << int_values[k] << ")\n";
         else
             hd << "#define " << L.ints[k] << " (PE_C.i[" << k << "])\n";
     }
     for (int k = 0; k < kNumRendererInts; k++) {
         const int slot = L.n_int + k;
-        if (opts.specialize_ints && !renderer_int_is_dynamic(kRendererInts[k]) && size_t(slot) < int_values.size())
+        if (opts.specialize_ints && !renderer_int_is_dynamic(kRendererInts[k]) && !int_is_dynamic(slot) && size_t(slot) < int_values.size())
             hd << "#define " << kRendererInts[k] << " (" << int_values[slot] << ")\n";
         else
             hd << "#define " << kRendererInts[k] << " (PE_C.i[" << slot << "])\n";

@@ -96,6 +96,9 @@ struct GenOptions {
     bool lazy_planes = true;   // with hoist_planes: plane tests stop as soon as nearer() is certain to reject them
     bool with_probe = false;  // also emit pe_probe_kernel (camera-teleportation probe)
     bool unroll_loops = true;  // false: `#pragma unroll 1` on every loop of the user snippets (smaller code)
+    // per slot of i[] / per scene matrix: 1 = read it from the constant block even when specialisation is on (slots whose
+    // value kept changing between renders, pe_api.cpp select_variant)
+    std::vector<char> dynamic_ints, dynamic_mats;
 };
 
 struct GenResult {

@@ -162,3 +162,23 @@ def test_headers_are_c11_and_a_plain_c_caller_links(tmp_path):
                          capture_output=True, text=True, timeout=300)
     assert run.returncode == 3 and "no CPU rendering path" in run.stderr
     assert "bytes of sm_100a code for 10 objects" in run.stdout
+
+
+def test_adaptive_despecialisation_bounds_recompiles():
+    """An int uniform that keeps changing between renders (an animation driving it) is a specialisation constant for the
+    first four changes and a constant-block read from then on; "adaptive" 0 keeps the old behaviour; a rebuilt scene starts
+    afresh."""
+    ir = load_ir("portal_in_portal")
+    r = SceneRenderer(ir, device=-1)
+    seen = []
+    for v in range(1, 9):
+        r.set_uniform("show_teleported_u", v)
+        r.uniform_block(64, 36)                       # selects the variant exactly as a render would
+        seen.append(re.search(r"#define show_teleported_u (.*)", r.source()).group(1))
+    assert seen[:4] == ["(1)", "(2)", "(3)", "(4)"] and all(s.startswith("(PE_C.i[") for s in seen[4:])
+    assert "#define teleport_light_u (1)" in r.source()          # the others stay baked in
+    r2 = SceneRenderer(ir, device=-1, options={"adaptive": 0})
+    for v in range(1, 9):
+        r2.set_uniform("show_teleported_u", v)
+        r2.uniform_block(64, 36)
+    assert "#define show_teleported_u (8)" in r2.source()

@@ -69,6 +69,32 @@ def test_generator_options_do_not_change_pixels(scene, tmp_path):
         assert np.array_equal(_bits(got), _bits(base)), (scene, tag)
 
 
+def test_despecialised_uniform_gives_the_same_pixels(tmp_path):
+    """After adaptive de-specialisation (an int that changed between renders more than four times) the program reads the
+    value from the constant block: same frame as the oracle with that value."""
+    from oracle.runner import Oracle
+    scene = "portal_in_portal"
+    ir = load_ir(scene)
+    r = SceneRenderer(ir, device=-1)
+    r.render_depth = DEPTH[scene]
+    for v in (1, 2, 3, 4, 5, 6):
+        r.set_uniform("show_teleported_u", v)
+        block, src = r.uniform_block(W, H), r.source()
+    assert "#define show_teleported_u (PE_C.i[" in src
+    d = tmp_path / "dyn"
+    d.mkdir()
+    (d / "prog.cu").write_text(src)
+    (d / "block.bin").write_bytes(block)
+    cc = subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", f'-DPROGRAM_FILE="{d / "prog.cu"}"', "-I", HARNESS,
+                         os.path.join(HARNESS, "run_program.cpp"), "-o", str(d / "run")], capture_output=True, text=True, timeout=900)
+    assert cc.returncode == 0, cc.stderr[-3000:]
+    assert subprocess.run([str(d / "run"), str(d / "block.bin"), str(W), str(H), str(d / "out.f32")], timeout=900).returncode == 0
+    got = np.fromfile(d / "out.f32", dtype=np.float32).reshape(H, W, 4)
+    orc = Oracle(ir, "strict", textures=load_tex(scene))
+    orc.set_uniforms({"show_teleported_u": 6})
+    assert np.array_equal(_bits(got), _bits(orc.render(W, H, DEPTH[scene])))
+
+
 def test_uniform_change_reaches_the_host_run(tmp_path):
     """Same harness, different uniforms: the block image really is what drives the frame."""
     from oracle.runner import Oracle
