@@ -105,7 +105,8 @@ def test_uniform_change_reaches_the_host_run(tmp_path):
     assert np.array_equal(_bits(got), _bits(orc.render(W, H, DEPTH["portal_in_portal"])))
 
 
-@pytest.mark.parametrize("scene", ["cone", "matryoshka", "recursive_space", "cylinder", "time_portal_spacetime", "trefoil"])
+@pytest.mark.parametrize("scene", ["borromean_rings", "cone", "cylinder", "hopf_link", "matryoshka", "mobius", "non_linear", "recursive_room",
+                                   "recursive_space", "sphere_intersection", "spherical_geometry", "time_portal_spacetime", "trefoil"])
 def test_more_reference_scenes_on_host(scene, tmp_path):
     """Reference scenes beyond the five configs (tests/golden/scenes_extra): skybox sampling, Reflect / Refract,
     subspaces, the `Camera` matrix kind, and (cylinder) libm's exp/log -- on the host both sides call the same
