@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Every reference scene that compiles: generated program run on the host (tests/host_harness) vs the strict oracle at a
+small frame, bit for bit.  A tool (minutes), not a test; needs the reference checkout for the .ron files and textures.
+
+    python tools/all_scenes_host_check.py /root/reference [--size 96x54] [--depth 30] [--only a,b]
+"""
+import argparse
+import glob
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+from oracle import frontend  # noqa: E402
+from oracle.runner import Oracle  # noqa: E402
+from portal_b200.capi import PortalB200Error  # noqa: E402
+from portal_b200.renderer import SceneRenderer  # noqa: E402
+
+HH = os.path.join(ROOT, "tests", "host_harness")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("reference")
+    ap.add_argument("--size", default="96x54")
+    ap.add_argument("--depth", type=int, default=30)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    w, h = (int(x) for x in args.size.split("x"))
+    only = {x for x in args.only.split(",") if x}
+    from PIL import Image
+    same = diff = skipped = 0
+    for path in sorted(glob.glob(os.path.join(args.reference, "scenes", "*.ron"))):
+        name = os.path.basename(path)[:-4]
+        if name == "empty" or (only and name not in only):
+            continue
+        t0 = time.time()
+        try:
+            ir = frontend.scene_ir(frontend.load_scene(path), name)
+            tex = {}
+            for t in ir["textures"]:
+                img = Image.open(os.path.join(args.reference, t["path"])).convert("RGBA")
+                tex[t["name"]] = np.ascontiguousarray(np.asarray(img, dtype=np.uint8))
+            r = SceneRenderer(ir, device=-1)
+            r.render_depth = args.depth
+            d = tempfile.mkdtemp(prefix=f"pe_all_{name}_")
+            open(f"{d}/prog.cu", "w").write(r.source())
+            open(f"{d}/block.bin", "wb").write(r.uniform_block(w, h))
+            subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", f'-DPROGRAM_FILE="{d}/prog.cu"', "-I", HH,
+                            os.path.join(HH, "run_program.cpp"), "-o", f"{d}/run"], check=True, capture_output=True)
+            cmd = [f"{d}/run", f"{d}/block.bin", str(w), str(h), f"{d}/out.f32"]
+            for t in ir["textures"]:
+                tex[t["name"]].tofile(f"{d}/{t['name']}.rgba")
+                cmd += [f"{d}/{t['name']}.rgba", str(tex[t["name"]].shape[1]), str(tex[t["name"]].shape[0])]
+            subprocess.run(cmd, check=True, timeout=1200)
+            got = np.fromfile(f"{d}/out.f32", dtype=np.float32).reshape(h, w, 4)
+            want = Oracle(ir, "strict", textures=tex).render(w, h, args.depth)
+            ok = np.array_equal(got.view(np.uint32), want.view(np.uint32))
+            same += ok
+            diff += not ok
+            status = "bit-identical" if ok else f"DIFFERS in {(np.abs(got - want) > 0).any(axis=-1).sum()} pixels"
+        except (PortalB200Error, NotImplementedError, subprocess.CalledProcessError, KeyError, FileNotFoundError) as e:
+            skipped += 1
+            status = "skipped: " + str(e).strip().splitlines()[0][:120]
+        print(f"{name:40s} {time.time() - t0:6.1f} s  {status}", flush=True)
+    print(f"{same} scenes bit-identical, {diff} differ, {skipped} skipped")
+    return 0 if diff == 0 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
