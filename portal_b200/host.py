@@ -247,6 +247,19 @@ class HostRenderer:
         self.scene._check(self._lib.ph_render_frame(self.scene._s, self._ctx, C.byref(p), out.ctypes.data, int(rgba8)))
         return out
 
+    def render_target(self, target, out_device_ptr: int, depth: int, aa_count=1, aa_start=0, camera=None, stream: int = 0):
+        """ph_render_target: the uniform setup of render_frame, then an asynchronous render of a (row-strip) target into
+        device memory (float RGBA); the multi-GPU building block on the host side."""
+        p = PhFrameParams(target.width, target.height, depth, aa_count, aa_start, 0)
+        if camera is not None:
+            p.use_camera = 1
+            p.look_at = (C.c_double * 3)(*camera["look_at"])
+            p.alpha, p.beta, p.r = camera["alpha"], camera["beta"], camera["r"]
+        self.scene._check(self._lib.ph_render_target(self.scene._s, self._ctx, C.byref(p), C.byref(target), out_device_ptr, stream or None))
+
+    def sync(self):
+        self._pe(self._lib.pe_sync(self._ctx))
+
     def render_motion_blur_frame(self, width, height, depth, frame_index, frame_count, motion_blur_frames, duration_seconds,
                                  aa_count=1) -> np.ndarray:
         """One frame of the offline `render` loop (main.rs:1758-1824): sub-frames + gamma-2 average, RGBA8."""

@@ -25,3 +25,30 @@ def test_full_frame_hash_equals_the_oracles(scene, torch_cuda):
     img = r.render_host(cfg["width"], cfg["height"])
     assert img.dtype == np.float32 and img.shape == (cfg["height"], cfg["width"], 4)
     assert hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() == cfg["sha256_f32_rgba"]
+
+
+def test_host_render_target_strips_reassemble_the_frame(torch_cuda):
+    """ph_render_target (C++ host: uniform setup + asynchronous strip render into device memory): the strips of three
+    "ranks" put back in row order equal ph_render_frame's frame."""
+    torch = torch_cuda
+    from conftest import ROOT
+    from portal_b200.distributed import local_rows
+    from portal_b200.host import HostRenderer, HostScene
+    from portal_b200.renderer import SceneRenderer
+    fixture = os.path.join(ROOT, "tests", "fixtures", "two_spheres.ron")
+    hr = HostRenderer(HostScene.from_file(fixture), device=0)
+    w, h, depth, world = 160, 100, 12, 3
+    whole = hr.render_frame(w, h, depth)
+    got = np.zeros_like(whole)
+    for rank in range(world):
+        t = SceneRenderer.strip_target(w, h, 16, rank, world)
+        rows = local_rows(h, rank, world, 16)
+        buf = torch.zeros((len(rows), w, 4), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()                                  # the fill runs on torch's stream, the render on the context's
+        hr.render_target(t, buf.data_ptr(), depth)
+        hr.sync()
+        part = buf.cpu().numpy()
+        for k, y in enumerate(rows):
+            if y >= 0:
+                got[y] = part[k]
+    assert np.array_equal(got.view(np.uint32), whole.view(np.uint32))
