@@ -182,3 +182,28 @@ def test_adaptive_despecialisation_bounds_recompiles():
         r2.set_uniform("show_teleported_u", v)
         r2.uniform_block(64, 36)
     assert "#define show_teleported_u (8)" in r2.source()
+
+
+def test_bulk_matrix_upload_equals_individual_uploads():
+    """pe_set_uniforms_mat4 (n names, 16n floats) == n x pe_set_uniform_mat4, observed through pe_scene_uniform_block;
+    an unknown name is reported with code 2 and leaves the others applied, like the single call."""
+    ir = load_ir("monoportal")
+    names = [k for k, u in ir["uniforms"].items() if u["type"] == "mat4"][:4]
+    rng = np.random.default_rng(3)
+    vals = rng.standard_normal((len(names), 16)).astype(np.float32)
+    a = SceneRenderer(ir, device=-1)
+    for n, v in zip(names, vals):
+        a._check(a._lib.pe_set_uniform_mat4(a._ctx, n.encode(), v.ctypes.data_as(C.POINTER(C.c_float))))
+    b = SceneRenderer(ir, device=-1)
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    flat = np.ascontiguousarray(vals.reshape(-1))
+    b._check(b._lib.pe_set_uniforms_mat4(b._ctx, len(names), arr, flat.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def block(r):
+        p, n = C.c_void_p(), C.c_size_t()
+        r._check(r._lib.pe_scene_uniform_block(r._ctx, 64, 36, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value)
+    assert block(a) == block(b) and flat.tobytes()[:64] in block(b)
+    arr2 = (C.c_char_p * 2)(names[0].encode(), b"no_such_mat")
+    assert b._lib.pe_set_uniforms_mat4(b._ctx, 2, arr2, flat.ctypes.data_as(C.POINTER(C.c_float))) == 2
+    assert b"no_such_mat" in b._lib.pe_last_error(b._ctx)
