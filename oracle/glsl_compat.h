@@ -595,4 +595,67 @@ static inline vec4 texture(const sampler2D& s, const vec2& uv) {
     return top * (real(1) - fy) + bot * fy;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Built-ins none of the reference's own scenes call (census: SURVEY.md section 8a row a11) but scene authors may:
+// boolean vectors and the relational functions (GLSL ES 3.00 section 8.7; `not()` is a C++ keyword and is not provided),
+// mix() with a boolean selector, trunc / round / roundEven, hyperbolic functions (from the pinned exp), faceforward,
+// matrixCompMult.  Same text as pe_glsl.cuh.
+struct bvec2 {
+    bool x, y;
+    bvec2() : x(false), y(false) {}
+    explicit bvec2(bool a) : x(a), y(a) {}
+    bvec2(bool a, bool b) : x(a), y(b) {}
+};
+struct bvec3 {
+    bool x, y, z;
+    bvec3() : x(false), y(false), z(false) {}
+    explicit bvec3(bool a) : x(a), y(a), z(a) {}
+    bvec3(bool a, bool b, bool c) : x(a), y(b), z(c) {}
+};
+struct bvec4 {
+    bool x, y, z, w;
+    bvec4() : x(false), y(false), z(false), w(false) {}
+    explicit bvec4(bool a) : x(a), y(a), z(a), w(a) {}
+    bvec4(bool a, bool b, bool c, bool d) : x(a), y(b), z(c), w(d) {}
+};
+#define PE_REL(NAME, OP)                                                                                                  \
+    static inline bvec2 NAME(const vec2& a, const vec2& b) { return bvec2(a.x OP b.x, a.y OP b.y); }                              \
+    static inline bvec3 NAME(const vec3& a, const vec3& b) { return bvec3(a.x OP b.x, a.y OP b.y, a.z OP b.z); }                  \
+    static inline bvec4 NAME(const vec4& a, const vec4& b) { return bvec4(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w); }
+PE_REL(lessThan, <) PE_REL(lessThanEqual, <=) PE_REL(greaterThan, >) PE_REL(greaterThanEqual, >=) PE_REL(equal, ==) PE_REL(notEqual, !=)
+#undef PE_REL
+static inline bool any(const bvec2& b) { return b.x || b.y; }
+static inline bool any(const bvec3& b) { return b.x || b.y || b.z; }
+static inline bool any(const bvec4& b) { return b.x || b.y || b.z || b.w; }
+static inline bool all(const bvec2& b) { return b.x && b.y; }
+static inline bool all(const bvec3& b) { return b.x && b.y && b.z; }
+static inline bool all(const bvec4& b) { return b.x && b.y && b.z && b.w; }
+static inline vec2 mix(const vec2& a, const vec2& b, const bvec2& s) { return vec2(s.x ? b.x : a.x, s.y ? b.y : a.y); }
+static inline vec3 mix(const vec3& a, const vec3& b, const bvec3& s) { return vec3(s.x ? b.x : a.x, s.y ? b.y : a.y, s.z ? b.z : a.z); }
+static inline vec4 mix(const vec4& a, const vec4& b, const bvec4& s) {
+    return vec4(s.x ? b.x : a.x, s.y ? b.y : a.y, s.z ? b.z : a.z, s.w ? b.w : a.w);
+}
+static inline real trunc(real x) { return std::trunc(x); }
+static inline real roundEven(real x) { return std::rint(x); }
+static inline real round(real x) { return std::floor(x + PE_L(0.5)); }  // GLSL leaves the direction of ties to the implementation
+static inline real sinh(real x) { const real e = exp(x); return (e - PE_L(1.0) / e) * PE_L(0.5); }
+static inline real cosh(real x) { const real e = exp(x); return (e + PE_L(1.0) / e) * PE_L(0.5); }
+static inline real tanh(real x) {
+    const real e = exp(-PE_L(2.0) * abs(x));
+    const real t = (PE_L(1.0) - e) / (PE_L(1.0) + e);
+    return x < PE_L(0.0) ? -t : t;
+}
+#define PE_CW1X(F)                                                                     \
+    static inline vec2 F(const vec2& v) { return vec2(F(v.x), F(v.y)); }                       \
+    static inline vec3 F(const vec3& v) { return vec3(F(v.x), F(v.y), F(v.z)); }               \
+    static inline vec4 F(const vec4& v) { return vec4(F(v.x), F(v.y), F(v.z), F(v.w)); }
+PE_CW1X(trunc) PE_CW1X(roundEven) PE_CW1X(round) PE_CW1X(sinh) PE_CW1X(cosh) PE_CW1X(tanh)
+#undef PE_CW1X
+static inline vec2 faceforward(const vec2& n, const vec2& i, const vec2& nref) { return dot(nref, i) < PE_L(0.0) ? n : -n; }
+static inline vec3 faceforward(const vec3& n, const vec3& i, const vec3& nref) { return dot(nref, i) < PE_L(0.0) ? n : -n; }
+static inline vec4 faceforward(const vec4& n, const vec4& i, const vec4& nref) { return dot(nref, i) < PE_L(0.0) ? n : -n; }
+static inline mat2 matrixCompMult(const mat2& a, const mat2& b) { return mat2(a.c[0] * b.c[0], a.c[1] * b.c[1]); }
+static inline mat3 matrixCompMult(const mat3& a, const mat3& b) { return mat3(a.c[0] * b.c[0], a.c[1] * b.c[1], a.c[2] * b.c[2]); }
+static inline mat4 matrixCompMult(const mat4& a, const mat4& b) { return mat4(a.c[0] * b.c[0], a.c[1] * b.c[1], a.c[2] * b.c[2], a.c[3] * b.c[3]); }
+
 }  // namespace pe_oracle

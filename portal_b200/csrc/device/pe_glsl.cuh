@@ -652,4 +652,67 @@ PE_FI vec4 texture(const sampler2D& s, const vec2& uv) {
     return top * (1.0f - fy) + bot * fy;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Built-ins none of the reference's own scenes call (census: SURVEY.md section 8a row a11) but scene authors may:
+// boolean vectors and the relational functions (GLSL ES 3.00 section 8.7; `not()` is a C++ keyword and is not provided),
+// mix() with a boolean selector, trunc / round / roundEven, hyperbolic functions (from the pinned exp), faceforward,
+// matrixCompMult.  Same text as the oracle's header.
+struct bvec2 {
+    bool x, y;
+    PE_FI bvec2() : x(false), y(false) {}
+    PE_FI explicit bvec2(bool a) : x(a), y(a) {}
+    PE_FI bvec2(bool a, bool b) : x(a), y(b) {}
+};
+struct bvec3 {
+    bool x, y, z;
+    PE_FI bvec3() : x(false), y(false), z(false) {}
+    PE_FI explicit bvec3(bool a) : x(a), y(a), z(a) {}
+    PE_FI bvec3(bool a, bool b, bool c) : x(a), y(b), z(c) {}
+};
+struct bvec4 {
+    bool x, y, z, w;
+    PE_FI bvec4() : x(false), y(false), z(false), w(false) {}
+    PE_FI explicit bvec4(bool a) : x(a), y(a), z(a), w(a) {}
+    PE_FI bvec4(bool a, bool b, bool c, bool d) : x(a), y(b), z(c), w(d) {}
+};
+#define PE_REL(NAME, OP)                                                                                                  \
+    PE_FI bvec2 NAME(const vec2& a, const vec2& b) { return bvec2(a.x OP b.x, a.y OP b.y); }                              \
+    PE_FI bvec3 NAME(const vec3& a, const vec3& b) { return bvec3(a.x OP b.x, a.y OP b.y, a.z OP b.z); }                  \
+    PE_FI bvec4 NAME(const vec4& a, const vec4& b) { return bvec4(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w); }
+PE_REL(lessThan, <) PE_REL(lessThanEqual, <=) PE_REL(greaterThan, >) PE_REL(greaterThanEqual, >=) PE_REL(equal, ==) PE_REL(notEqual, !=)
+#undef PE_REL
+PE_FI bool any(const bvec2& b) { return b.x || b.y; }
+PE_FI bool any(const bvec3& b) { return b.x || b.y || b.z; }
+PE_FI bool any(const bvec4& b) { return b.x || b.y || b.z || b.w; }
+PE_FI bool all(const bvec2& b) { return b.x && b.y; }
+PE_FI bool all(const bvec3& b) { return b.x && b.y && b.z; }
+PE_FI bool all(const bvec4& b) { return b.x && b.y && b.z && b.w; }
+PE_FI vec2 mix(const vec2& a, const vec2& b, const bvec2& s) { return vec2(s.x ? b.x : a.x, s.y ? b.y : a.y); }
+PE_FI vec3 mix(const vec3& a, const vec3& b, const bvec3& s) { return vec3(s.x ? b.x : a.x, s.y ? b.y : a.y, s.z ? b.z : a.z); }
+PE_FI vec4 mix(const vec4& a, const vec4& b, const bvec4& s) {
+    return vec4(s.x ? b.x : a.x, s.y ? b.y : a.y, s.z ? b.z : a.z, s.w ? b.w : a.w);
+}
+PE_FI float trunc(float x) { return ::truncf(x); }
+PE_FI float roundEven(float x) { return ::rintf(x); }
+PE_FI float round(float x) { return ::floorf(x + 0.5f); }  // GLSL leaves the direction of ties to the implementation
+PE_FI float sinh(float x) { const float e = exp(x); return (e - 1.0f / e) * 0.5f; }
+PE_FI float cosh(float x) { const float e = exp(x); return (e + 1.0f / e) * 0.5f; }
+PE_FI float tanh(float x) {
+    const float e = exp(-2.0f * abs(x));
+    const float t = (1.0f - e) / (1.0f + e);
+    return x < 0.0f ? -t : t;
+}
+#define PE_CW1X(F)                                                                     \
+    PE_FI vec2 F(const vec2& v) { return vec2(F(v.x), F(v.y)); }                       \
+    PE_FI vec3 F(const vec3& v) { return vec3(F(v.x), F(v.y), F(v.z)); }               \
+    PE_FI vec4 F(const vec4& v) { return vec4(F(v.x), F(v.y), F(v.z), F(v.w)); }
+PE_CW1X(trunc) PE_CW1X(roundEven) PE_CW1X(round) PE_CW1X(sinh) PE_CW1X(cosh) PE_CW1X(tanh)
+#undef PE_CW1X
+PE_FI vec2 faceforward(const vec2& n, const vec2& i, const vec2& nref) { return dot(nref, i) < 0.0f ? n : -n; }
+PE_FI vec3 faceforward(const vec3& n, const vec3& i, const vec3& nref) { return dot(nref, i) < 0.0f ? n : -n; }
+PE_FI vec4 faceforward(const vec4& n, const vec4& i, const vec4& nref) { return dot(nref, i) < 0.0f ? n : -n; }
+PE_FI mat2 matrixCompMult(const mat2& a, const mat2& b) { return mat2(a.c[0] * b.c[0], a.c[1] * b.c[1]); }
+PE_FI mat3 matrixCompMult(const mat3& a, const mat3& b) { return mat3(a.c[0] * b.c[0], a.c[1] * b.c[1], a.c[2] * b.c[2]); }
+PE_FI mat4 matrixCompMult(const mat4& a, const mat4& b) { return mat4(a.c[0] * b.c[0], a.c[1] * b.c[1], a.c[2] * b.c[2], a.c[3] * b.c[3]); }
+
 }  // namespace pe

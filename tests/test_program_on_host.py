@@ -187,3 +187,54 @@ def test_probe_kernel_on_host_equals_oracle_probe(tmp_path):
             assert (out[3] != 0, out[4] != 0, out[5] != 0) == (rhr, reo, rcs), (scene, a, b)
             crossed += int(rhr)
     assert crossed >= 3
+
+
+TORTURE = """vec3 c = vec3(.5, 1., 2.e-1);
+vec2 q = (hit.n.xy + vec2(1.)).yx * .5;
+c.xy = q;
+c.zy += vec2(1e-1, -.25) * q.yx;
+c.x++;
+c.x -= 1.0;
+float arr[3];
+arr[0] = c.x; arr[1] = c.y; arr[2] = c.z;
+int k = int(floor(abs(hit.u) * 3.)) % 3;
+float pick = arr[k];
+mat3 m = mat3(vec3(1., 0., 0.), vec3(0., 2., 0.), vec3(0., 0., 3.));
+vec3 w = (matrixCompMult(m, m) * c).zxy;
+w = (k == 1) ? w.yzx : -w;
+bvec3 lt = lessThan(w, vec3(0.25));
+bvec2 b2 = bvec2(w.x > 0., w.y > 0.);
+if (b2.x && !b2.y) { w.xz *= 2.; }
+if (any(lt) && !all(lt)) { w = mix(w, w.zxy, lt); }
+w = faceforward(w, r.d.xyz, hit.n);
+vec4 v4 = vec4(w, 1.).wzyx;
+v4.xw = v4.wx;
+float s = 0.;
+for (int i = 0; i < 4; i++) { if (i == 2) continue; s += float(i) * v4[i]; }
+do { s *= .5; } while (s > 1.);
+s = tanh(s) + 0.1 * trunc(s * 3.) + 0.01 * round(pick * 7.) + 0.001 * roundEven(pick * 5.) + 0.0001 * (cosh(q.x) - sinh(q.y));
+s += pow(abs(q.x) + .1, 1.7) * exp(-q.y) + log(1. + abs(q.x)) + exp2(q.y) * log2(2. + q.x);
+c = clamp(abs(vec3(s, pick, length(v4.xyz) * .1)), 0., 1.);
+c = mix(c, c.zyx, step(.5, fract(hit.v)));
+return material_simple(hit, r, c, 5e-1, false, 4e0, 3e-1);"""
+
+
+def test_synthetic_snippet_surface(tmp_path):
+    """A material snippet that leans on the GLSL surface scene authors can reach -- literal forms, r/lvalue swizzles,
+    arrays, `%`, ternaries, loops with continue / do-while, mat3 products, boolean vectors and relational functions, the
+    less common built-ins and the pinned elementary functions -- through BOTH independent GLSL rewriters (pe_codegen.cpp and
+    oracle/gen_oracle.py): the two programs must compile and agree bit for bit."""
+    from oracle import frontend
+    from oracle.runner import Oracle
+    ir = frontend.scene_ir(frontend.load_scene(os.path.join(ROOT, "tests", "fixtures", "two_spheres.ron")), "two_spheres")
+    n = 0
+    for m in ir["materials"]:
+        if m["type"] == "Complex":
+            m["code"] = TORTURE
+            n += 1
+    assert n == 1
+    got, _ = _run_on_host(tmp_path, "torture", "two_spheres", ir=ir, tex={}, depth=12)
+    want = Oracle(ir, "strict").render(W, H, 12)
+    assert np.array_equal(_bits(got), _bits(want))
+    plain = frontend.scene_ir(frontend.load_scene(os.path.join(ROOT, "tests", "fixtures", "two_spheres.ron")), "two_spheres")
+    assert not np.array_equal(_bits(want), _bits(Oracle(plain, "strict").render(W, H, 12)))       # the snippet is really on the path
