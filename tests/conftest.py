@@ -21,6 +21,11 @@ REFERENCE = "/root/reference"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # On a machine without a GPU the tests JIT many program variants that no GPU run will ever ask for (option sweeps,
+    # synthetic snippets): keep them out of portal_b200/_cache, which build() fills for the config scenes and which travels
+    # to the GPU box with the repository snapshot.
+    if not os.path.exists("/dev/nvidiactl") and "PORTAL_B200_CACHE_DIR" not in os.environ:
+        os.environ["PORTAL_B200_CACHE_DIR"] = os.path.join("/tmp", f"portal_b200_cache_cpu_tests_{os.getuid()}")
 
 
 def load_ir(name):
