@@ -103,7 +103,8 @@ PE_API int pe_scene_uniform_block(pe_ctx* ctx, int width, int height, const void
  * rejected, same pixels), "with_probe" (0/1, default 0: also generate the camera-teleportation probe kernel; pe_probe_ray
  * switches it on by itself), "adaptive" (0/1, default 1: an int uniform or a matrix structure that differed between
  * renders more than 4 times stops being a specialisation constant, which bounds recompilation when an animation
- * drives it), "lineinfo" (0/1, default 1), "unroll_loops" (0/1, default 1; 0 keeps the loops of
+ * drives it), "uniforms_in_smem" (0/1, default 0: every block stages the uniform block in shared memory and reads it
+ * from there instead of the constant bank -- same pixels; an experiment), "lineinfo" (0/1, default 1), "unroll_loops" (0/1, default 1; 0 keeps the loops of
  * user snippets rolled).  Set before pe_scene_compile. */
 PE_API int pe_set_option(pe_ctx* ctx, const char* key, int value);
 

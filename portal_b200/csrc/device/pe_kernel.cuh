@@ -272,6 +272,24 @@ PE_FI void store_pixel(const PeLaunch& L, int px, int lrow, int grow, vec3 sum, 
 
 }  // namespace pe
 
+// Optional: uniforms read from a __shared__ copy of the block (GenOptions::uniforms_in_smem).  Every thread of the block
+// takes part in the copy and in the barrier BEFORE it may leave the kernel.
+#ifndef PE_UNIFORMS_SMEM
+#define PE_UNIFORMS_SMEM 0
+#endif
+#if PE_UNIFORMS_SMEM
+#define PE_STAGE_UNIFORMS()                                                                                   \
+    do {                                                                                                      \
+        const unsigned* pe_src = reinterpret_cast<const unsigned*>(&PE_C_UPLOAD);                             \
+        unsigned* pe_dst = reinterpret_cast<unsigned*>(&PE_C);                                                \
+        for (unsigned pe_i = threadIdx.x; pe_i < unsigned(sizeof(pe::PeConstBlock) / 4); pe_i += blockDim.x)  \
+            pe_dst[pe_i] = pe_src[pe_i];                                                                      \
+        __syncthreads();                                                                                      \
+    } while (0)
+#else
+#define PE_STAGE_UNIFORMS() do { } while (0)
+#endif
+
 #ifndef PE_WITH_PROBE
 #define PE_WITH_PROBE 0
 #endif
@@ -286,6 +304,7 @@ struct PeProbe {
 };
 extern "C" __global__ void pe_probe_kernel(const PeProbe P) {
     using namespace pe;
+    PE_STAGE_UNIFORMS();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Ray r = Ray{vec4(P.ax, P.ay, P.az, 1.0f), vec4(P.bx - P.ax, P.by - P.ay, P.bz - P.az, 0.0f), 1.0f, _camera_in_subspace == 1};
     r = normalize_ray(r);
@@ -345,6 +364,7 @@ extern "C" __global__ void pe_probe_kernel(const PeProbe P) {
 // One thread per pixel.  Block = W warps = a 16 x (2W) pixel tile (warp tiles of 8x4, two abreast).
 extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe_render_kernel(const PeLaunch L) {
     using namespace pe;
+    PE_STAGE_UNIFORMS();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int lrow = blockIdx.y * (PE_BLOCK_THREADS / 64 * 4) + (warp >> 1) * 4 + (lane >> 3);
@@ -375,6 +395,7 @@ extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe
 // samples of its pixel back to back before it takes a new pixel.
 extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe_render_kernel(const PeLaunch L) {
     using namespace pe;
+    PE_STAGE_UNIFORMS();
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned total_tiles = unsigned(L.tiles_x) * unsigned(L.tiles_y);

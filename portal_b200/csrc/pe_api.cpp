@@ -289,6 +289,7 @@ std::vector<int> variant_key(pe_ctx* c, const std::vector<int>& ints, const std:
     if (c->opts.specialize_matrices)
         for (auto& zo : masks) key.push_back(int(zo.first | (zo.second << 16)));
     key.push_back(c->opts.with_probe ? 1 : 0);
+    key.push_back(c->opts.uniforms_in_smem ? 1 : 0);
     for (char d : c->opts.dynamic_ints) key.push_back(d);
     for (char d : c->opts.dynamic_mats) key.push_back(d);
     return key;
@@ -403,8 +404,9 @@ bool select_variant(pe_ctx* c) {
         if (r != 0) { c->err = "cuModuleLoadData: " + driver_error(d, r); return false; }
         r = d->cuModuleGetFunction(&v->kernel, v->module, "pe_render_kernel");
         if (r != 0) { c->err = "cuModuleGetFunction(pe_render_kernel): " + driver_error(d, r); return false; }
-        r = d->cuModuleGetGlobal(&v->const_ptr, &v->const_size, v->module, "PE_C");
-        if (r != 0) { c->err = "cuModuleGetGlobal(PE_C): " + driver_error(d, r); return false; }
+        const char* block_symbol = c->opts.uniforms_in_smem ? "PE_C_UPLOAD" : "PE_C";
+        r = d->cuModuleGetGlobal(&v->const_ptr, &v->const_size, v->module, block_symbol);
+        if (r != 0) { c->err = std::string("cuModuleGetGlobal(") + block_symbol + "): " + driver_error(d, r); return false; }
         if (v->const_size != c->layout.size) { c->err = "constant block size mismatch between host and device"; return false; }
         if (c->opts.with_probe) {
             r = d->cuModuleGetFunction(&v->probe, v->module, "pe_probe_kernel");
@@ -663,6 +665,7 @@ int pe_set_option(pe_ctx* c, const char* key, int value) {
     else if (k == "lazy_planes") c->opts.lazy_planes = value != 0;
     else if (k == "with_probe") c->opts.with_probe = value != 0;   // pe_probe_ray turns it on by itself; exposed for inspection
     else if (k == "adaptive") c->adapt = value != 0;
+    else if (k == "uniforms_in_smem") c->opts.uniforms_in_smem = value != 0;
     else return c->fail("unknown option `" + k + "`");
     // options change the generated program
     if (c->has_gpu) {

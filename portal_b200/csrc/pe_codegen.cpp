@@ -571,7 +571,14 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     hd << "};\n";
     hd << "static_assert(sizeof(PeConstBlock) == " << L.size << ", \"constant block layout mismatch\");\n";
     hd << "}  // namespace pe\n";
-    hd << "extern \"C\" { __constant__ pe::PeConstBlock PE_C; }\n";
+    if (!opts.uniforms_in_smem) {
+        hd << "extern \"C\" { __constant__ pe::PeConstBlock PE_C; }\n";
+    } else {
+        // the host uploads to PE_C_UPLOAD; each block copies it into the shared image PE_C before any thread reads a uniform
+        hd << "#define PE_UNIFORMS_SMEM 1\n";
+        hd << "extern \"C\" { __constant__ pe::PeConstBlock PE_C_UPLOAD; }\n";
+        hd << "__shared__ pe::PeConstBlock PE_C;\n";
+    }
     // uniform declarations (scene.rs:661-718) -> names bound to the block / to specialisation constants
     for (int k = 0; k < L.n_mat; k++) {
         if (opts.specialize_matrices && size_t(k) < matrix_masks.size() && (matrix_masks[k].first | matrix_masks[k].second)) {

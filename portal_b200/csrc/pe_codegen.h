@@ -95,6 +95,10 @@ struct GenOptions {
     bool hoist_planes = true;  // per-plane normal work evaluated on the host (see PlaneRec)
     bool lazy_planes = true;   // with hoist_planes: plane tests stop as soon as nearer() is certain to reject them
     bool with_probe = false;  // also emit pe_probe_kernel (camera-teleportation probe)
+    // Uniform block staged in shared memory: every block copies the constant block to a __shared__ image in its prologue
+    // and the program reads uniforms from there (LDS operands) instead of the constant bank (LDCU / UR operands).  What
+    // north_star sketches; off by default, see DESIGN.md sections 3 and 10.
+    bool uniforms_in_smem = false;
     bool unroll_loops = true;  // false: `#pragma unroll 1` on every loop of the user snippets (smaller code)
     // per slot of i[] / per scene matrix: 1 = read it from the constant block even when specialisation is on (slots whose
     // value kept changing between renders, pe_api.cpp select_variant)

@@ -16,6 +16,8 @@
 #define __host__
 #define __launch_bounds__(...)
 #define __restrict__
+#define __shared__
+static inline void __syncthreads() {}
 
 struct uchar4 { unsigned char x, y, z, w; };
 struct float4 { float x, y, z, w; };

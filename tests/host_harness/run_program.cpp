@@ -33,6 +33,9 @@ int main(int argc, char** argv) {
     if (std::string(argv[2]) == "probe") {   // ./run block.bin probe ax ay az bx by bz: teleport_external_ray on the host
         if (argc < 9 || block.size() != sizeof(pe::PeConstBlock)) return 2;
         std::memcpy(&PE_C, block.data(), sizeof PE_C);
+#if PE_UNIFORMS_SMEM
+        std::memcpy(&PE_C_UPLOAD, block.data(), sizeof PE_C_UPLOAD);
+#endif
         float out6[6] = {0, 0, 0, 0, 0, 0};
         PeProbe P{float(std::atof(argv[3])), float(std::atof(argv[4])), float(std::atof(argv[5])), float(std::atof(argv[6])),
                   float(std::atof(argv[7])), float(std::atof(argv[8])), out6};
@@ -64,6 +67,11 @@ int main(int argc, char** argv) {
             PE_C.tex[k].h = std::atoi(argv[a + 2]);
         }
     }
+#if PE_UNIFORMS_SMEM
+    // the "shared" image is an ordinary global here and the threads run one after another: give the upload symbol the
+    // same bytes, so that each thread's share of the block copy rewrites what is already there
+    std::memcpy(&PE_C_UPLOAD, &PE_C, sizeof PE_C);
+#endif
     std::vector<float4> out(size_t(w) * size_t(h));
     PeLaunch L{};
     L.out = out.data();

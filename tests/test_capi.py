@@ -207,3 +207,23 @@ def test_bulk_matrix_upload_equals_individual_uploads():
     arr2 = (C.c_char_p * 2)(names[0].encode(), b"no_such_mat")
     assert b._lib.pe_set_uniforms_mat4(b._ctx, 2, arr2, flat.ctypes.data_as(C.POINTER(C.c_float))) == 2
     assert b"no_such_mat" in b._lib.pe_last_error(b._ctx)
+
+
+def test_uniform_block_symbol_and_smem_variant():
+    """The host finds the uniform block by symbol name after loading the cubin: the name it looks up must be a constant-space
+    symbol of exactly the block's size in the cubin -- in the default program (`PE_C`) and in the shared-memory-staging
+    variant (`PE_C_UPLOAD`, with `PE_C` a shared image)."""
+    ir = load_ir("portal_in_portal")
+    for opts, symbol in (({}, "PE_C"), ({"uniforms_in_smem": 1}, "PE_C_UPLOAD")):
+        r = SceneRenderer(ir, device=-1, options=opts)
+        size = int(re.search(r"sizeof\(PeConstBlock\) == (\d+)", r.source()).group(1))
+        assert len(r.uniform_block(64, 36)) == size
+        path = f"/tmp/_pe_test_symbol_{symbol}.cubin"
+        open(path, "wb").write(r.cubin())
+        ptx_like = subprocess.run(["cuobjdump", "-elf", path], capture_output=True, text=True).stdout
+        rows = [ln for ln in ptx_like.splitlines() if re.search(rf"\b{symbol}$", ln.strip())]
+        assert rows, symbol
+        assert any(f"0x{size:x}" in ln for ln in rows), (symbol, rows)
+        res = subprocess.run(["cuobjdump", "-res-usage", path], capture_output=True, text=True).stdout
+        shared = int(re.search(r"SHARED:(\d+)", res).group(1))
+        assert (shared >= size) == bool(opts)
