@@ -206,12 +206,17 @@ def _fmod(a, b):
 
 
 def _pow(a, b):
+    """f64::powf (libm pow) without Python's exceptions."""
     try:
         return math.pow(a, b)
-    except (ValueError, OverflowError):
-        if a < 0:
-            return math.nan
-        return math.inf
+    except OverflowError:                       # finite operands, result out of range: +-inf, negative for (-x)^odd
+        odd = math.isfinite(b) and b == math.floor(b) and math.fmod(b, 2.0) != 0.0
+        return -math.inf if (a < 0 and odd) else math.inf
+    except ValueError:
+        if a == 0.0 and b < 0:                  # pow(+-0, negative) = +-inf (pole), Python calls it a domain error
+            odd = math.isfinite(b) and b == math.floor(b) and math.fmod(b, 2.0) != 0.0
+            return math.copysign(math.inf, a) if odd else math.inf
+        return math.nan                         # negative base, non-integral exponent
 
 
 def _div(a, b):
@@ -355,39 +360,66 @@ def _builtin(name, a):
         need(1)
         out = a[0]
         for v in a[1:]:
-            # Rust f64::min/max: NaN-ignoring
+            # f64::min / max semantics: a NaN operand is ignored; among equal values (-0.0 vs 0.0) the earlier argument stays
             if math.isnan(out):
                 out = v
-            elif not math.isnan(v):
-                out = min(out, v) if name == "min" else max(out, v)
+            elif not math.isnan(v) and (v < out if name == "min" else v > out):
+                out = v
         return out
     if name == "log":
         need(1)
         base, x = (10.0, a[0]) if len(a) == 1 else (a[0], a[1])
-        try:
-            return math.log(x) / math.log(base) if base not in (2.0, 10.0) else (
-                math.log2(x) if base == 2.0 else math.log10(x))
-        except ValueError:
-            return math.nan
+
+        def ieee_log(fn, v):                       # Rust f64::ln / log2 / log10: ln(0) = -inf, ln(negative) = NaN
+            if math.isnan(v) or v < 0.0:
+                return math.nan
+            if v == 0.0:
+                return -math.inf
+            return fn(v)
+        if base == 2.0:
+            return ieee_log(math.log2, x)
+        if base == 10.0:
+            return ieee_log(math.log10, x)
+        return _div(ieee_log(math.log, x), ieee_log(math.log, base))
     if name == "round":
         need(1)
         modulus, x = (1.0, a[0]) if len(a) == 1 else (a[0], a[1])
-        q = x / modulus
-        r = math.floor(abs(q) + 0.5) * (1.0 if q >= 0 else -1.0)  # Rust round: half away from zero
+        q = _div(x, modulus)
+        if math.isnan(q) or math.isinf(q):
+            r = q
+        else:
+            fl = float(math.floor(abs(q)))                             # Rust round: half away from zero, sign of q kept;
+            r = math.copysign(fl + 1.0 if abs(q) - fl >= 0.5 else fl, q)  # (not floor(|q| + 0.5): 0.49999999999999994 must give 0)
         return r * modulus
     need(1)
     x = a[0]
+    # Rust's f64 methods are total (IEEE): spell out what Python's math module turns into exceptions
+    if math.isnan(x):
+        return math.nan
+    if math.isinf(x):
+        if name in ("int", "ceil", "floor", "sinh", "asinh"):
+            return x
+        if name in ("abs", "cosh"):
+            return math.inf
+        if name in ("sign", "tanh"):
+            return math.copysign(1.0, x)
+        if name == "atan":
+            return math.copysign(math.pi / 2.0, x)
+        if name == "acosh":
+            return math.inf if x > 0 else math.nan
+        return math.nan                                               # sin cos tan asin acos atanh of +-inf
     try:
-        if name == "int":
-            return float(math.trunc(x))
-        if name == "ceil":
-            return float(math.ceil(x))
-        if name == "floor":
-            return float(math.floor(x))
+        if name in ("int", "ceil", "floor"):
+            r = float({"int": math.trunc, "ceil": math.ceil, "floor": math.floor}[name](x))
+            return math.copysign(0.0, x) if r == 0.0 else r        # IEEE keeps the sign of a zero result (ceil(-0.3) = -0.0)
         if name == "abs":
             return abs(x)
         if name == "sign":
             return math.copysign(1.0, x)  # Rust f64::signum
+        if name == "atanh" and abs(x) == 1.0:
+            return math.copysign(math.inf, x)
         return getattr(math, name)(x)
-    except (ValueError, OverflowError):
+    except OverflowError:                                               # sinh / cosh beyond the f64 range
+        return math.inf if name == "cosh" or x > 0 else -math.inf
+    except ValueError:
         return math.nan

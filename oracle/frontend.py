@@ -295,8 +295,25 @@ def vec3_cross(a, b):
 
 
 # ================================================================== easing.rs:6-44
+def _cos(x):       # f64::cos / sin are total: NaN for +-inf (Python raises)
+    return math.nan if math.isinf(x) or math.isnan(x) else math.cos(x)
+
+
+def _sin(x):
+    return math.nan if math.isinf(x) or math.isnan(x) else math.sin(x)
+
+
+def _pow2(y):      # 2f64.powf(y)
+    if math.isnan(y):
+        return math.nan
+    try:
+        return math.pow(2.0, y)
+    except OverflowError:
+        return math.inf
+
+
 def easing_in(t):
-    return 1.0 - math.cos(t * PI * 0.5)
+    return 1.0 - _cos(t * PI * 0.5)
 
 
 def easing_out(t):
@@ -304,7 +321,7 @@ def easing_out(t):
 
 
 def easing_in_out(t):
-    return (1.0 - math.cos(t * PI)) * 0.5
+    return (1.0 - _cos(t * PI)) * 0.5
 
 
 def easing_in_out_fast(t):
@@ -314,7 +331,7 @@ def easing_in_out_fast(t):
 def easing_plus_minus(t):
     t *= 2.0 * PI
     t2 = 2.0 * t
-    return math.sin(t) * (3.0 - math.cos(t) - math.cos(t2) - math.cos(t) * math.cos(t2)) / 4.0
+    return _sin(t) * (3.0 - _cos(t) - _cos(t2) - _cos(t) * _cos(t2)) / 4.0
 
 
 def easing_elastic_out(x):
@@ -323,7 +340,7 @@ def easing_elastic_out(x):
         return 0.0
     if x == 1.0:
         return 1.0
-    return math.pow(2.0, -10.0 * x) * math.sin((x * 10.0 - 0.75) * c4) + 1.0
+    return _pow2(-10.0 * x) * _sin((x * 10.0 - 0.75) * c4) + 1.0
 
 
 # ==================================================================== scene model

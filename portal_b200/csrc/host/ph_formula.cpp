@@ -334,7 +334,12 @@ struct Evaluator {
         if (f == "min" || f == "max") {
             need(1);
             out = a[0];
-            for (size_t k = 1; k < a.size(); k++) out = f == "min" ? std::fmin(out, a[k]) : std::fmax(out, a[k]);  // Rust f64::min/max
+            // f64::min / max semantics: a NaN operand is ignored; among equal values (-0.0 vs 0.0) the earlier argument stays
+            for (size_t k = 1; k < a.size(); k++) {
+                const double v = a[k];
+                if (std::isnan(out)) out = v;
+                else if (!std::isnan(v) && (f == "min" ? v < out : v > out)) out = v;
+            }
             return true;
         }
         if (f == "log") {
@@ -361,7 +366,7 @@ struct Evaluator {
         else if (f == "ceil") out = std::ceil(x);
         else if (f == "floor") out = std::floor(x);
         else if (f == "abs") out = std::fabs(x);
-        else if (f == "sign") out = std::copysign(1.0, x);  // f64::signum
+        else if (f == "sign") out = std::isnan(x) ? x : std::copysign(1.0, x);  // f64::signum (NaN stays NaN)
         else if (f == "sin") out = std::sin(x);
         else if (f == "cos") out = std::cos(x);
         else if (f == "tan") out = std::tan(x);

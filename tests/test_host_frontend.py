@@ -261,3 +261,68 @@ def test_render_frame_cli(tmp_path):
     got = np.frombuffer(out.read_bytes(), dtype=np.uint8).reshape(90, 160, 4)
     want = HostRenderer(HostScene.from_file(FIXTURE), device=0).render_frame(160, 90, 12, rgba8=True)
     assert np.array_equal(got, want)
+
+
+def _random_formulas(n, seed):
+    """Expressions over the grammar both formula evaluators implement (fasteval 0.2.4 as the reference uses it,
+    uniform.rs:602-635, 1009-1140): numbers in several spellings, + - * / % ^, comparisons, and / or (both spellings), unary
+    minus and !, parentheses, one- and many-argument built-ins, the application's own functions, other uniforms, `time`."""
+    import random
+    rng = random.Random(seed)
+    nums = ["0", "1", "2", "3.5", ".25", "1e-3", "2.5E2", "10", "0.1", "7", "1e10", "0.333"]
+    names = ["time", "p", "spin", "count", "room_size", "pi()", "e()"]
+    f1 = ["sin", "cos", "tan", "abs", "floor", "ceil", "int", "sign", "asin", "acos", "atan", "sinh", "cosh", "tanh", "deg2rad", "rad2deg",
+          "easing_in", "easing_out", "easing_in_out", "easing_in_out_fast", "easing_plus_minus", "easing_elastic_out", "not", "round", "log"]
+    fn = ["min", "max"]
+    ops = ["+", "-", "*", "/", "%", "^", "<", "<=", ">", ">=", "==", "!=", "&&", "||", " and ", " or "]
+
+    def expr(d):
+        k = rng.random()
+        if d <= 0 or k < 0.25:
+            return rng.choice(nums) if rng.random() < 0.6 else rng.choice(names)
+        if k < 0.60:
+            return f"{expr(d - 1)}{rng.choice(ops)}{expr(d - 1)}"
+        if k < 0.70:
+            return f"({expr(d - 1)})"
+        if k < 0.76:
+            return f"-{expr(d - 1)}"
+        if k < 0.79:
+            return f"!{expr(d - 1)}"
+        if k < 0.90:
+            return f"{rng.choice(f1)}({expr(d - 1)})"
+        if k < 0.94:
+            return f"{rng.choice(fn)}({', '.join(expr(d - 1) for _ in range(rng.randint(1, 4)))})"
+        if k < 0.97:
+            return f"if({expr(d - 1)}, {expr(d - 1)}, {expr(d - 1)})"
+        return f"lerp({expr(d - 1)}, {expr(d - 1)}, {expr(d - 1)})" if rng.random() < 0.5 else f"log({expr(d - 1)}, {expr(d - 1)})"
+    return [expr(4) for _ in range(n)]
+
+
+def test_formula_evaluators_agree_on_random_expressions(tmp_path):
+    """Differential fuzz of the two fasteval restatements (C++ ph_formula.cpp vs oracle/formula.py), through both RON readers:
+    1500 random expressions as Formula uniforms of the fixture scene; same set of evaluable uniforms, same float64 bits."""
+    from oracle import frontend
+    exprs = _random_formulas(1500, seed=20260923)
+    text = open(FIXTURE, encoding="utf-8").read()
+    marker = '        (name: "wobble", data: Formula(('
+    assert marker in text
+    extra = "".join(f'        (name: "fz{i}", data: Formula(("{e}"))),\n' for i, e in enumerate(exprs))
+    text = text.replace(marker, extra + marker, 1)
+    path = tmp_path / "fuzz.ron"
+    path.write_text(text, encoding="utf-8")
+    s = frontend.load_scene(str(path))
+    hs = HostScene.from_file(str(path))
+    n_val = n_nan = 0
+    for tm in (0.0, 0.37):
+        s.time = s.total_time = tm
+        hs.set_time(tm)
+        want, got = s.uniform_table(), hs.uniform_table()
+        assert list(want) == list(got)                              # the same expressions are (un)evaluable on both sides
+        for i, e in enumerate(exprs):
+            k = f"fz{i}_u"
+            if k in want:
+                a, b = float(want[k][1]), float(got[k][1])
+                assert np.array_equal(np.float64(a).view(np.uint64), np.float64(b).view(np.uint64)) or (math.isnan(a) and math.isnan(b)), (e, a, b)
+                n_val += 1
+                n_nan += math.isnan(a)
+    assert n_val >= 2000 and n_nan < n_val // 2
