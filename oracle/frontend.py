@@ -123,7 +123,7 @@ def mat_inverse(m):
     d = [m[0][i] * col0[i] for i in range(4)]
     det = d[0] + d[1] + d[2] + d[3]
     if det == 0.0:
-        rcp = math.inf  # f64::recip(0.0) == inf (glam_assert is debug-only)
+        rcp = math.copysign(math.inf, det)  # f64::recip(+-0.0) == +-inf (glam_assert is debug-only)
     else:
         rcp = 1.0 / det
 

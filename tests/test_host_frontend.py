@@ -326,3 +326,84 @@ def test_formula_evaluators_agree_on_random_expressions(tmp_path):
                 n_val += 1
                 n_nan += math.isnan(a)
     assert n_val >= 2000 and n_nan < n_val // 2
+
+
+def _random_matrix_scene(n, seed):
+    """RON text of the fixture scene with n extra named matrices of every kind, built on each other at random."""
+    import random
+    rng = random.Random(seed)
+
+    def num():
+        k = rng.random()
+        if k < 0.12:
+            return rng.choice(["0.0", "1.0", "-1.0", "0.5", "2.0", "-0.0"])
+        if k < 0.17:
+            return rng.choice(["1e-9", "1e9", "3.0e-5"])
+        return repr(round(rng.uniform(-3.0, 3.0), rng.choice([1, 3, 6])))
+
+    names = ["origin", "portal_a", "portal_b", "ball"]
+
+    def ref():
+        return f'Some(Named("{rng.choice(names)}"))'
+
+    def val():
+        return f"Value({num()})" if rng.random() < 0.8 else rng.choice(['Uniform(Some(Named("p")))', 'Uniform(Some(Named("spin")))',
+                                                                       'Uniform(Some(Inline(Formula(("lift * 0.5 - time")))))'])
+
+    def vec3(keys="xyz"):
+        return "(" + ", ".join(f"{c}: {val()}" for c in keys) + ")"
+
+    out = []
+    for i in range(n):
+        kind = rng.choice(["Simple", "Parametrized", "Mul", "Teleport", "Inv", "Lerp", "If", "Exact", "ExactFull"])
+        if kind == "Simple":
+            d = (f"Simple(offset: ({num()}, {num()}, {num()}), scale: {num()}, rotate: ({num()}, {num()}, {num()}), "
+                 f"mirror: ({rng.choice(['true', 'false'])}, {rng.choice(['true', 'false'])}, {rng.choice(['true', 'false'])}))")
+        elif kind == "Parametrized":
+            d = f"Parametrized(offset: {vec3()}, rotate: {vec3()}, mirror: {vec3()}, scale: {val()})"
+        elif kind == "Mul":
+            d = f"Mul(to: {ref()}, what: {ref()})"
+        elif kind == "Teleport":
+            d = f"Teleport(first_portal: {ref()}, second_portal: {ref()}, what: {ref()})"
+        elif kind == "Inv":
+            d = f"Inv({ref()})"
+        elif kind == "Lerp":
+            d = f"Lerp(t: {val()}, first: {ref()}, second: {ref()})"
+        elif kind == "If":
+            d = f"If(condition: {val()}, then: {ref()}, otherwise: {ref()})"
+        elif kind == "Exact":
+            d = f"Exact(i: {vec3()}, j: {vec3()}, k: {vec3()}, pos: {vec3()})"
+        else:
+            d = "ExactFull(" + ", ".join(f"c{c}: {vec3('xyzw')}" for c in range(4)) + ")"
+        out.append(f'        (name: "mz{i}", data: {d}),\n')
+        names.append(f"mz{i}")
+    text = open(FIXTURE, encoding="utf-8").read()
+    marker = '        (name: "ball_inv", data: Inv(Some(Named("ball")))),\n'
+    assert marker in text
+    return text.replace(marker, marker + "".join(out), 1)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_matrix_evaluators_agree_on_random_matrix_dags(seed, tmp_path):
+    """Differential fuzz of the two glam restatements (C++ ph_scene.cpp vs oracle/frontend.py): 300 random matrices of every
+    kind stacked on each other -- scale 0, mirrors, singular inverses, Lerp between mirrored frames, Teleport chains -- must
+    give identical float64 tables (M and M^-1 of every matrix), NaN / Inf patterns included."""
+    from oracle import frontend
+    path = tmp_path / "mat.ron"
+    path.write_text(_random_matrix_scene(300, seed), encoding="utf-8")
+    s = frontend.load_scene(str(path))
+    hs = HostScene.from_file(str(path))
+    for tm in (0.0, 0.6):
+        s.time = s.total_time = tm
+        hs.set_time(tm)
+        want, got = s.uniform_table(), hs.uniform_table()
+        assert list(want) == list(got)
+        n = nonfinite = 0
+        for k in want:
+            a, b = np.asarray(want[k][1], dtype=np.float64), np.asarray(got[k][1], dtype=np.float64)
+            same = (a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))
+            assert same.all(), (k, a, b)
+            if k.startswith("mz"):
+                n += 1
+                nonfinite += int(not np.isfinite(a).all())
+        assert n >= 500 and 0 < nonfinite < n
