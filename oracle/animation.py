@@ -171,28 +171,33 @@ class AnimatedScene:
         return {"look_at": look_at, "alpha": c["alpha"], "beta": c["beta"], "r": c["r"], "in_subspace": c["in_subspace"],
                 "free_movement": c["free_movement"], "matrix": c["matrix"], "override_matrix": True}
 
-    def get_start_cam(self, idx):
-        """scene.rs:1291-1317."""
+    def get_start_cam(self, idx, depth=0):
+        """scene.rs:1291-1317.  (depth: animations whose cameras refer to each other in a cycle would overflow the
+        reference's stack; here, as in the C++ player, the chain gives up after 256 links -> no camera.)"""
+        if depth > 256:
+            return None
         anim = self.animations[idx]
         if anim["use_prev_cam"]:
-            return self.get_end_cam(idx - 1) if idx >= 1 else None
+            return self.get_end_cam(idx - 1, depth + 1) if idx >= 1 else None
         if anim["use_any_cam_as_start"] is not None:
             any_id = anim["cam_any_start"]
             if any_id is None:
                 return None
-            return self.get_end_cam(any_id) if anim["use_any_cam_as_start"] else self.get_start_cam(any_id)
+            return self.get_end_cam(any_id, depth + 1) if anim["use_any_cam_as_start"] else self.get_start_cam(any_id, depth + 1)
         return anim["cam_start"]
 
-    def get_end_cam(self, idx):
+    def get_end_cam(self, idx, depth=0):
         """scene.rs:1319-1335."""
+        if depth > 256:
+            return None
         anim = self.animations[idx]
         if anim["use_start_cam_as_end"]:
-            return self.get_start_cam(idx)
+            return self.get_start_cam(idx, depth + 1)
         if anim["use_any_cam_as_end"] is not None:
             any_id = anim["cam_any_end"]
             if any_id is None:
                 return None
-            return self.get_end_cam(any_id) if anim["use_any_cam_as_end"] else self.get_start_cam(any_id)
+            return self.get_end_cam(any_id, depth + 1) if anim["use_any_cam_as_end"] else self.get_start_cam(any_id, depth + 1)
         return anim["cam_end"]
 
     # ------------------------------------------------------------------ stages

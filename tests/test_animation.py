@@ -383,3 +383,91 @@ def test_stereo_frame_through_the_gate_on_the_gpu(torch_cuda):
                       left_eye_scale=frontend.camera_scale(p.left_eye_matrix), right_eye_scale=frontend.camera_scale(p.right_eye_matrix))
     got = hp.render_frame(256, 72, 12)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def _random_animation_scene(n, seed):
+    """The fixture scene with its animations replaced by n random ones: every stage kind, Changed / CopyPrev parts, camera
+    chains through use_prev_cam / use_start_cam_as_end / use_any_cam_* (cycles included), all easings, easing uniforms."""
+    import random
+    rng = random.Random(seed)
+    cams = ["wide", "at_ball", "before_gate", "behind_gate", "beside_gate"]
+    names = [f"an{i}" for i in range(n)]
+
+    def cam():
+        k = rng.random()
+        if k < 0.25:
+            return "None"
+        if k < 0.7:
+            return f'Some(Named("{rng.choice(cams)}"))'
+        la = (f"Coordinate(({rng.uniform(-1, 1):.3f}, {rng.uniform(-1, 1):.3f}, {rng.uniform(-1, 1):.3f}))" if rng.random() < 0.7
+              else 'MatrixCenter(Some(Named("ball")))')
+        return (f"Some(Inline((look_at: {la}, alpha: {rng.uniform(-3, 3):.4f}, beta: {rng.uniform(0.2, 2.9):.4f}, r: {rng.uniform(0.5, 4):.3f}, "
+                f"in_subspace: {rng.choice(['true', 'false'])}, free_movement: {rng.choice(['true', 'false', 'false'])}, "
+                "matrix: (1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.5, 0.0, -0.25, 1.0))))")
+
+    def opt_flag():
+        return rng.choice(["None", "None", "Some(true)", "Some(false)"])
+
+    def any_name():
+        return "None" if rng.random() < 0.3 else f'Some("{rng.choice(names)}")'
+
+    out = []
+    for i, nm in enumerate(names):
+        stage = rng.choice(["Dev", 'Animation("closed")', 'Animation("reset")'] + ([f'RealAnimation("{rng.choice(names[:i])}")'] if i else []))
+        p = rng.choice(["CopyPrev", f"Changed(Some(Inline(Progress({rng.uniform(0, 1):.3f}))))", 'Changed(Some(Inline(Formula(("0.3 + time * 0.5")))))'])
+        spin = rng.choice(["CopyPrev", f"Changed(Some(Inline(Angle({rng.uniform(-2, 2):.3f}))))", 'Changed(Some(Named("wobble")))'])
+        ball = rng.choice(["CopyPrev", 'Changed(Some(Named("portal_a")))',
+                           'Changed(Some(Inline(Lerp(t: Uniform(Some(Inline(Formula(("time"))))), first: Some(Named("portal_a")), second: Some(Named("portal_b"))))))'])
+        easing = rng.choice(["Linear", "In", "Out", "InOut", "InOutFast", "ElasticOut"])
+        eu = rng.choice(["None", "None", 'Some(Inline(Formula(("easing_in_out(time) * 1.2 - 0.1"))))', 'Some(Named("p"))'])
+        out.append(f"""        (name: "{nm}", data: (
+            duration: {rng.choice(['0.0', '0.5', '1.0', '2.5', '3.0'])},
+            animation_stage: {stage},
+            uniforms: ({{"p": {p}, "spin": {spin}, "open": CopyPrev, "count": CopyPrev}}),
+            matrices: ({{"portal_a": CopyPrev, "ball": {ball}}}),
+            use_prev_cam: {rng.choice(['true', 'false', 'false'])},
+            use_start_cam_as_end: {rng.choice(['true', 'false', 'false'])},
+            cam_start: {cam()},
+            cam_end: {cam()},
+            use_any_cam_as_start: {opt_flag()},
+            use_any_cam_as_end: {opt_flag()},
+            cam_any_start: {any_name()},
+            cam_any_end: {any_name()},
+            cam_easing: {easing},
+            cam_easing_uniform: {eu},
+        )),
+""")
+    text = open(FIXTURE, encoding="utf-8").read()
+    i = text.index("    animations: ([")
+    j = text.index("    current_stage:", i)
+    return text[:i] + "    animations: ([\n" + "".join(out) + "    ]),\n" + text[j:]
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_players_agree_on_random_animations(seed, tmp_path):
+    """Differential fuzz of the two animation layers (C++ ph_anim.cpp vs oracle/animation.py): 60 random animations; each is
+    initialised and stepped through five times (wrap-around included); cameras, times and uniform tables must be identical."""
+    path = tmp_path / "anim.ron"
+    path.write_text(_random_animation_scene(60, seed), encoding="utf-8")
+    s0, p0, hs0, hp0 = _pair(str(path))
+    names = [a for a, _ in hp0.animations()]
+    assert names == [a["name"] for a in p0.anim.animations] and len(names) == 60
+    n = 0
+    for nm in names:
+        s, p, hs, hp = _pair(str(path))
+        p.init_animation(nm)
+        hp.init_animation(nm)
+        for t in (0.0, 0.4, 0.93, 2.7, 0.1):
+            p.update(t)
+            hp.update(t)
+            _assert_same_state(p, hp, s, hs, (seed, nm, t))
+            n += 1
+    assert n == 300
+    # one clock over the whole sequence
+    s, p, hs, hp = _pair(str(path))
+    p.anim.run_animations = True
+    hp.set_run_animations(True)
+    for t in (0.0, 3.3, 17.0, 41.9, 5.5):
+        p.update(t)
+        hp.update(t)
+        _assert_same_state(p, hp, s, hs, (seed, "run", t))
