@@ -132,15 +132,15 @@ def _swizzle_methods(swizzles: set, lvalue_swizzles: set = frozenset()):
         for i, c in enumerate(s):
             comp[c] = i
     names = "xyzw"
-    per = {2: [], 3: [], 4: []}  # receiver size -> methods
+    per = {2: [], 3: [], 4: [], 0: []}  # receiver size -> in-class methods; 0 -> out-of-class definitions (PE_SWZ_DEFS)
     for sw in sorted(swizzles):
         idx = [comp[c] for c in sw]
         ret = f"vec{len(sw)}"
         body = ", ".join(names[i] for i in idx)
-        meth = f"{ret} {sw}() const {{ return {ret}({body}); }}"
         for size in (2, 3, 4):
             if max(idx) < size:
-                per[size].append(meth)
+                per[size].append(f"inline {ret} {sw}() const;")      # defined after vec4 is complete: a vec2 may widen (v.xyxy)
+                per[0].append(f"inline {ret} vec{size}::{sw}() const {{ return {ret}({body}); }}")
     for sw in sorted(lvalue_swizzles):
         idx = [comp[c] for c in sw]
         if len(set(idx)) != len(idx):
@@ -361,6 +361,7 @@ def generate_source(ir: dict, real: str = "float") -> str:
     h("#define PE_L(x) " + ("x##f" if real == "float" else "x"))
     for size in (2, 3, 4):
         h(f"#define PE_SWZ_VEC{size} " + " ".join(per[size]))
+    h("#define PE_SWZ_DEFS " + " ".join(per[0]))
     h('#include "glsl_compat.h"')
     h("#include <cstring>")
     h("#include <cstddef>")

@@ -305,6 +305,11 @@ struct vec4 {
     PE_FI float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
     PE_SWZ_VEC4
 };
+// definitions of the rvalue swizzle accessors declared inside the structs (a narrow vector may widen: v2.xyxy)
+#ifndef PE_SWZ_DEFS
+#define PE_SWZ_DEFS
+#endif
+PE_SWZ_DEFS
 #define PE_SWZ_ASSIGN(R, V, OPEQ, BODY) PE_FI R& R::operator OPEQ(const V& v) { BODY return *this; }
 PE_SWZ_ASSIGN(swz2_ref, vec2, =, a = v.x; b = v.y;)
 PE_SWZ_ASSIGN(swz2_ref, vec2, +=, a = a + v.x; b = b + v.y;)
@@ -711,6 +716,28 @@ PE_CW1X(trunc) PE_CW1X(roundEven) PE_CW1X(round) PE_CW1X(sinh) PE_CW1X(cosh) PE_
 PE_FI vec2 faceforward(const vec2& n, const vec2& i, const vec2& nref) { return dot(nref, i) < 0.0f ? n : -n; }
 PE_FI vec3 faceforward(const vec3& n, const vec3& i, const vec3& nref) { return dot(nref, i) < 0.0f ? n : -n; }
 PE_FI vec4 faceforward(const vec4& n, const vec4& i, const vec4& nref) { return dot(nref, i) < 0.0f ? n : -n; }
+#define PE_REFL(V)                                                                                  \
+    PE_FI V reflect(const V& i, const V& n) { return i - n * (2.0f * dot(n, i)); }                  \
+    PE_FI V refract(const V& i, const V& n, float eta) {                                            \
+        float d = dot(n, i);                                                                        \
+        float k = 1.0f - eta * eta * (1.0f - d * d);                                                \
+        if (k < 0.0f) return V(0.0f);                                                               \
+        return i * eta - n * (eta * d + sqrt(k));                                                   \
+    }
+PE_REFL(vec2) PE_REFL(vec4)
+#undef PE_REFL
+#define PE_SMOOTH(V, BODY_F, BODY_V)                                                                  \
+    PE_FI V smoothstep(float e0, float e1, const V& x) { return BODY_F; }                               \
+    PE_FI V smoothstep(const V& e0, const V& e1, const V& x) { return BODY_V; }
+PE_SMOOTH(vec2, vec2(smoothstep(e0, e1, x.x), smoothstep(e0, e1, x.y)), vec2(smoothstep(e0.x, e1.x, x.x), smoothstep(e0.y, e1.y, x.y)))
+PE_SMOOTH(vec3, vec3(smoothstep(e0, e1, x.x), smoothstep(e0, e1, x.y), smoothstep(e0, e1, x.z)),
+          vec3(smoothstep(e0.x, e1.x, x.x), smoothstep(e0.y, e1.y, x.y), smoothstep(e0.z, e1.z, x.z)))
+PE_SMOOTH(vec4, vec4(smoothstep(e0, e1, x.x), smoothstep(e0, e1, x.y), smoothstep(e0, e1, x.z), smoothstep(e0, e1, x.w)),
+          vec4(smoothstep(e0.x, e1.x, x.x), smoothstep(e0.y, e1.y, x.y), smoothstep(e0.z, e1.z, x.z), smoothstep(e0.w, e1.w, x.w)))
+#undef PE_SMOOTH
+PE_FI vec2 atan(const vec2& v) { return vec2(atan(v.x), atan(v.y)); }
+PE_FI vec3 atan(const vec3& v) { return vec3(atan(v.x), atan(v.y), atan(v.z)); }
+PE_FI vec4 atan(const vec4& v) { return vec4(atan(v.x), atan(v.y), atan(v.z), atan(v.w)); }
 PE_FI mat2 matrixCompMult(const mat2& a, const mat2& b) { return mat2(a.c[0] * b.c[0], a.c[1] * b.c[1]); }
 PE_FI mat3 matrixCompMult(const mat3& a, const mat3& b) { return mat3(a.c[0] * b.c[0], a.c[1] * b.c[1], a.c[2] * b.c[2]); }
 PE_FI mat4 matrixCompMult(const mat4& a, const mat4& b) { return mat4(a.c[0] * b.c[0], a.c[1] * b.c[1], a.c[2] * b.c[2], a.c[3] * b.c[3]); }

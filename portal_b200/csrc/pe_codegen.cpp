@@ -312,6 +312,8 @@ std::string lvalue_swizzle_macro(const std::set<std::string>& swz, int size, std
     return out;
 }
 
+// Rvalue swizzle accessors.  `size` > 0: the in-class DECLARATIONS for a vecN receiver; `size` == 0: the out-of-class
+// DEFINITIONS for every receiver (PE_SWZ_DEFS, expanded after vec4 is complete -- a vec2 may widen: v.xyxy).
 std::string swizzle_macro(const std::set<std::string>& swz, int size) {
     std::string out;
     for (const std::string& s : swz) {
@@ -327,14 +329,20 @@ std::string swizzle_macro(const std::set<std::string>& swz, int size) {
             idx[k] = id;
             if (id > mx) mx = id;
         }
-        if (mx >= size) continue;
-        std::string ret = "vec" + std::to_string(s.size());
-        out += " PE_FI " + ret + " " + s + "() const { return " + ret + "(";
-        for (size_t k = 0; k < s.size(); k++) {
-            if (k) out += ", ";
-            out += "xyzw"[idx[k]];
+        const std::string ret = "vec" + std::to_string(s.size());
+        for (int recv = 2; recv <= 4; recv++) {
+            if (mx >= recv || (size != 0 && size != recv)) continue;
+            if (size != 0) {
+                out += " PE_FI " + ret + " " + s + "() const;";
+            } else {
+                out += " PE_FI " + ret + " vec" + std::to_string(recv) + "::" + s + "() const { return " + ret + "(";
+                for (size_t k = 0; k < s.size(); k++) {
+                    if (k) out += ", ";
+                    out += "xyzw"[idx[k]];
+                }
+                out += "); }";
+            }
         }
-        out += "); }";
     }
     return out;
 }
@@ -535,6 +543,7 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     hd << "#define PE_SWZ_VEC2" << swizzle_macro(body.swz, 2) << lvalue_swizzle_macro(body.swz_w, 2, swz_err) << "\n";
     hd << "#define PE_SWZ_VEC3" << swizzle_macro(body.swz, 3) << lvalue_swizzle_macro(body.swz_w, 3, swz_err) << "\n";
     hd << "#define PE_SWZ_VEC4" << swizzle_macro(body.swz, 4) << lvalue_swizzle_macro(body.swz_w, 4, swz_err) << "\n";
+    hd << "#define PE_SWZ_DEFS" << swizzle_macro(body.swz, 0) << "\n";
     if (!swz_err.empty()) { R.error = swz_err; return R; }
     hd << "#define PE_HAS_SKYBOX " << (scene.skybox.empty() ? 0 : 1) << "\n";
     {   // a scene may define its own transpose / inverse / determinant (GLSL ES 1.00 has none built in)

