@@ -25,7 +25,16 @@ def pytest_configure(config):
     # synthetic snippets): keep them out of portal_b200/_cache, which build() fills for the config scenes and which travels
     # to the GPU box with the repository snapshot.
     if not os.path.exists("/dev/nvidiactl") and "PORTAL_B200_CACHE_DIR" not in os.environ:
-        os.environ["PORTAL_B200_CACHE_DIR"] = os.path.join("/tmp", f"portal_b200_cache_cpu_tests_{os.getuid()}")
+        scratch = os.path.join("/tmp", f"portal_b200_cache_cpu_tests_{os.getuid()}")
+        os.environ["PORTAL_B200_CACHE_DIR"] = scratch
+        # ... seeded with what build() already compiled, so a fresh machine does not JIT those programs twice
+        shipped = os.path.join(ROOT, "portal_b200", "_cache")
+        if os.path.isdir(shipped):
+            import shutil
+            os.makedirs(scratch, exist_ok=True)
+            for f in os.listdir(shipped):
+                if not os.path.exists(os.path.join(scratch, f)):
+                    shutil.copy2(os.path.join(shipped, f), os.path.join(scratch, f))
 
 
 def load_ir(name):
