@@ -435,6 +435,14 @@ bool check_target(pe_ctx* c, const pe_target* t) {
         c->err = "invalid pe_target";
         return false;
     }
+    // keep every index the kernel and the launch geometry compute inside 32 bits: frames up to 65536 x 65536, at most
+    // 2^24 local rows, last global row of the last strip below 2^30
+    const long long last_strip = (long long)t->strip_first + (long long)(t->n_strips - 1) * (long long)t->strip_step;
+    if (t->width > 65536 || t->height > 65536 || (long long)t->n_strips * (long long)t->strip_rows > (1LL << 24) ||
+        (last_strip + 1) * (long long)t->strip_rows > (1LL << 30)) {
+        c->err = "invalid pe_target: frame or strip set too large";
+        return false;
+    }
     return true;
 }
 

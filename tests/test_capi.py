@@ -227,3 +227,34 @@ def test_uniform_block_symbol_and_smem_variant():
         res = subprocess.run(["cuobjdump", "-res-usage", path], capture_output=True, text=True).stdout
         shared = int(re.search(r"SHARED:(\d+)", res).group(1))
         assert (shared >= size) == bool(opts)
+
+
+def test_target_validation():
+    """pe_target fields are validated before anything is launched or allocated: garbage never reaches the device, and every
+    target the repo's own code builds (full frames, cyclic strips of any rank / world, ragged and tiny frames) is accepted
+    (on this compile-only context "accepted" shows as the no-GPU error instead of the invalid-target one)."""
+    import random
+    r = SceneRenderer(load_ir("basics"), device=-1)
+    buf = (C.c_uint8 * 64)()
+
+    def verdict(t):
+        assert r._lib.pe_render_rgba8(r._ctx, C.byref(t), C.addressof(buf), None) != 0
+        return "invalid" if b"invalid pe_target" in r._lib.pe_last_error(r._ctx) else "valid"
+    rng = random.Random(5)
+    vals = [0, 1, -1, 2, 16, 17, 255, 4096, 65536, 65537, 2 ** 31 - 1, -2 ** 31, 7680, 4320]
+    seen = set()
+    for _ in range(5000):
+        t = PeTarget(*[rng.choice(vals) for _ in range(7)])
+        v = verdict(t)
+        seen.add(v)
+        if v == "valid":
+            assert 0 < t.width <= 65536 and 0 < t.height <= 65536 and t.n_strips * t.strip_rows <= 2 ** 24
+    assert seen == {"invalid", "valid"}
+    for w, h in [(1, 1), (1, 37), (37, 1), (5, 3), (256, 256), (3840, 2160), (7680, 4320), (65536, 8)]:
+        assert verdict(SceneRenderer.full_target(w, h)) == "valid"
+        for world in (1, 2, 3, 8):
+            for rank in range(world):
+                t = SceneRenderer.strip_target(w, h, 16, rank, world)
+                assert verdict(t) == ("valid" if t.n_strips > 0 else "invalid"), (w, h, rank, world)
+    assert verdict(PeTarget(2 ** 31 - 1, 2 ** 31 - 1, 1, 0, 1, 1, 1)) == "invalid"
+    assert verdict(PeTarget(64, 64, 65536, 65535, 65536, 65536, 0)) == "invalid"
