@@ -53,7 +53,10 @@ def _tokenize(text):
                     j = k
                     while j < n and text[j].isdigit():
                         j += 1
-            toks.append(("num", float(text[i:j])))
+            try:
+                toks.append(("num", float(text[i:j])))
+            except ValueError:
+                raise FormulaError(f"malformed number {text[i:j]!r} in formula {text!r}") from None
             i = j
         elif c.isalpha() or c == "_":
             j = i
