@@ -407,3 +407,48 @@ def test_matrix_evaluators_agree_on_random_matrix_dags(seed, tmp_path):
                 n += 1
                 nonfinite += int(not np.isfinite(a).all())
         assert n >= 500 and 0 < nonfinite < n
+
+
+def test_garbage_formulas_and_mutated_scene_files_are_handled(tmp_path):
+    """Robustness of the host front-end on hostile input: (1) 2000 random character strings as formulas -- the C++ evaluator and
+    the oracle's accept exactly the same ones, with the same values; (2) 400 random mutations of the fixture scene file --
+    every one is either rejected with a message or loads and evaluates; nothing crashes."""
+    import random
+    from oracle import frontend
+    rng = random.Random(7)
+    alphabet = "0123456789.+-*/%^()<>=!&|, eEpixyzsincotafbrmlgud_[]"
+    exprs = ["".join(rng.choice(alphabet) for _ in range(rng.randint(1, 24))) for _ in range(2000)]
+    text = open(FIXTURE, encoding="utf-8").read()
+    marker = '        (name: "wobble", data: Formula(('
+    path = tmp_path / "garbage.ron"
+    path.write_text(text.replace(marker, "".join(f'        (name: "gz{i}", data: Formula(("{e}"))),\n' for i, e in enumerate(exprs)) + marker, 1),
+                    encoding="utf-8")
+    want = frontend.load_scene(str(path)).uniform_table()
+    got = HostScene.from_file(str(path)).uniform_table()
+    assert list(want) == list(got)
+    evaluable = [k for k in want if k.startswith("gz")]
+    assert 5 < len(evaluable) < 200
+    for k in evaluable:
+        a, b = float(want[k][1]), float(got[k][1])
+        assert np.float64(a).view(np.uint64) == np.float64(b).view(np.uint64) or (math.isnan(a) and math.isnan(b)), (k, a, b)
+    loaded = rejected = 0
+    for _ in range(400):
+        t = list(text)
+        for _ in range(rng.randint(1, 6)):
+            k, pos = rng.random(), rng.randrange(len(t))
+            if k < 0.3:
+                del t[pos:pos + rng.randint(1, 40)]
+            elif k < 0.6:
+                t[pos:pos] = rng.choice(["(", ")", "[", "]", "{", "}", ",", ":", '"', "Some(", "None", "-", "1e999", chr(92), "'", "/*", "//", "nan", "(((("])
+            elif k < 0.8:
+                t[pos] = rng.choice("()[]{},:' 0123456789abcxyz._-" + chr(34) + chr(10))
+            else:
+                t = t[:pos] or ["("]
+        try:
+            hs = HostScene("".join(t))
+            hs.uniform_table()
+            loaded += 1
+        except PortalB200Error as e:
+            assert str(e)
+            rejected += 1
+    assert loaded + rejected == 400 and rejected > 300
