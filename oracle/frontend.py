@@ -29,6 +29,7 @@ from typing import Any
 
 from . import ron
 from .formula import Evaluator, FormulaError
+from .mat_sqrt import mat_sqrt
 from .ron import Tagged
 
 PI = math.pi
@@ -730,9 +731,9 @@ class Scene:
                     return None
                 return mat_lerp(first, second, t)
             if k == "Sqrt":
-                # matrix.rs:606-613 + 909-985: a BFGS minimisation (argmin 0.8 + finitediff) of |X*X - M|^2;
-                # its result depends on that library's line search iterate by iterate -- not restated.
-                raise NotImplementedError("matrix kind Sqrt (iterative argmin BFGS solve) is out of scope")
+                # matrix.rs:606-613: None ("Can't calculate sqrt!") when the minimisation does not reach cost < 1e-4
+                x = g(m[1])
+                return None if x is None else mat_sqrt(x)
             raise ValueError(k)
         finally:
             visited.pop()

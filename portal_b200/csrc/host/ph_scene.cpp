@@ -890,9 +890,8 @@ bool Scene::get_matrix(int id, Mat4& out, std::vector<int>& visited) {
             break;
         }
         case Matrix::Sqrt:
-            // matrix.rs:606-613 / 909-985: an iterative argmin-BFGS solve of X*X = M; not restated
-            error = "matrix kind Sqrt (iterative BFGS solve in the reference) is not supported";
-            ok = false;
+            // matrix.rs:606-613: the matrix is missing when the minimisation does not reach cost < 1e-4
+            ok = get_matrix(m.a, A, visited) && mat_sqrt(A, out);
             break;
     }
     visited.pop_back();

@@ -27,6 +27,8 @@ Mat4 mat_mul(const Mat4& a, const Mat4& b);
 Mat4 mat_inverse(const Mat4& m);
 Mat4 mat_srt(const double scale[3], const double rotate[3], const double offset[3]);
 Mat4 mat_lerp(const Mat4& first, const Mat4& second, double t);
+// matrix kind Sqrt (matrix.rs:909-985): BFGS minimisation of |X*X - m|^2 from X0 = m; false = "Can't calculate sqrt!"
+bool mat_sqrt(const Mat4& m, Mat4& out);
 Mat4 orbit_camera_matrix(const double look_at[3], double alpha, double beta, double r);
 // RotateAroundCam::get_matrix with a teleport matrix and the free-movement flag (main.rs:286-304)
 Mat4 orbit_camera_matrix(const double look_at[3], double alpha, double beta, double r, const Mat4& teleport, bool free_movement);

@@ -266,18 +266,11 @@ def test_reference_scene_animations_match_oracle_player():
         assert [a for a, _ in hp0.animations()] == names
         for an in names[:3]:
             s, p, hs, hp = _pair(path)
-            try:
-                p.init_animation(an)
-            except NotImplementedError:                                             # Sqrt matrices (argmin BFGS): not restated
-                continue
+            p.init_animation(an)
             hp.init_animation(an)
             dur = p.anim.animations[p.anim.animation_by_name[an]]["duration"]
             for tt in (0.0, 0.37 * dur, 0.99 * dur, 1.5 * dur):
-                try:
-                    p.update(tt)
-                    s.uniform_table()
-                except NotImplementedError:
-                    break
+                p.update(tt)
                 hp.update(tt)
                 _assert_same_state(p, hp, s, hs, (path, an, tt))
                 n += 1

@@ -11,9 +11,9 @@ mkdir -p "$OUT"
 python -m portal_b200.build > /dev/null      # makes sure the embedded device sources (pe_device_src.cpp) exist
 FLAGS="-std=c++17 -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -I$ROOT/portal_b200/csrc -I$ROOT/portal_b200/csrc/host -I$ROOT/include"
 H="$ROOT/portal_b200/csrc/host"
-g++ $FLAGS "$ROOT/tests/host_harness/sanitize_frontend.cpp" "$H/ph_ron.cpp" "$H/ph_formula.cpp" "$H/ph_scene.cpp" "$H/ph_anim.cpp" -o "$OUT/frontend"
+g++ $FLAGS "$ROOT/tests/host_harness/sanitize_frontend.cpp" "$H/ph_ron.cpp" "$H/ph_formula.cpp" "$H/ph_scene.cpp" "$H/ph_matsqrt.cpp" "$H/ph_anim.cpp" -o "$OUT/frontend"
 g++ $FLAGS "$ROOT/tests/host_harness/sanitize_rewriter.cpp" "$ROOT/portal_b200/csrc/pe_codegen.cpp" "$ROOT/portal_b200/csrc/pe_device_src.cpp" \
-    "$H/ph_ron.cpp" "$H/ph_formula.cpp" "$H/ph_scene.cpp" -o "$OUT/rewriter"
+    "$H/ph_ron.cpp" "$H/ph_formula.cpp" "$H/ph_scene.cpp" "$H/ph_matsqrt.cpp" -o "$OUT/rewriter"
 "$OUT/frontend" "$@"
 "$OUT/rewriter" "$@"
 echo "sanitizers: no reports"
