@@ -97,7 +97,7 @@ PE_API int pe_scene_cubin(pe_ctx* ctx, const void** data, size_t* size);
  * for running the generated program outside the GPU in tests.  Texture slots hold device pointers. */
 PE_API int pe_scene_uniform_block(pe_ctx* ctx, int width, int height, const void** data, size_t* size);
 /* Options: "persistent" (0/1, default 0), "specialize_ints" (0/1, default 1), "specialize_matrices"
- * (0/1, default 1: the exact-0 / exact-1 structure of every uploaded matrix is baked in), "block_threads",
+ * (0/1, default 1: the exact-0 / exact-1 structure of every uploaded matrix is baked in), "block_threads" (a multiple of 64 in [64, 1024], default 512),
  * "min_blocks", "hoist_planes" (0/1, default 1: per-plane normal algebra evaluated once per upload on the
  * host), "lazy_planes" (0/1, default 1: a plane test stops as soon as its result is certain to be
  * rejected, same pixels), "with_probe" (0/1, default 0: also generate the camera-teleportation probe kernel; pe_probe_ray

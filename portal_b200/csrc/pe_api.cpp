@@ -481,6 +481,7 @@ pe_ctx* pe_create(int device) {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaMalloc(&c->queue_dev, 256) != cudaSuccess) {
             g_create_error = "cannot create stream / queue counter";
+            if (c->stream) cudaStreamDestroy(c->stream);
             return nullptr;
         }
         c->has_gpu = true;
@@ -663,7 +664,8 @@ int pe_set_option(pe_ctx* c, const char* key, int value) {
     if (k == "persistent") c->opts.persistent = value != 0;
     else if (k == "specialize_ints") c->opts.specialize_ints = value != 0;
     else if (k == "block_threads") {
-        if (value < 32 || value > 1024 || value % 32) return c->fail("block_threads must be a multiple of 32 in [32, 1024]");
+        // a block is a column of 16x4-pixel warp pairs (pe_kernel.cuh): whole pairs only
+        if (value < 64 || value > 1024 || value % 64) return c->fail("block_threads must be a multiple of 64 in [64, 1024]");
         c->opts.block_threads = value;
     } else if (k == "min_blocks") c->opts.min_blocks = value < 1 ? 1 : value;
     else if (k == "lineinfo") c->lineinfo = value != 0;

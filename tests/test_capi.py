@@ -258,3 +258,18 @@ def test_target_validation():
                 assert verdict(t) == ("valid" if t.n_strips > 0 else "invalid"), (w, h, rank, world)
     assert verdict(PeTarget(2 ** 31 - 1, 2 ** 31 - 1, 1, 0, 1, 1, 1)) == "invalid"
     assert verdict(PeTarget(64, 64, 65536, 65535, 65536, 65536, 0)) == "invalid"
+
+
+def test_option_validation():
+    """pe_set_option rejects unknown keys and launch geometries the kernel cannot index (a block is a column of 64-thread warp
+    pairs), with a message; accepted values survive a compile."""
+    r = SceneRenderer(load_ir("basics"), device=-1, compile_now=False)
+    for bad in (0, 32, 96, 1088, -64):
+        assert r._lib.pe_set_option(r._ctx, b"block_threads", bad) != 0
+        assert b"block_threads" in r._lib.pe_last_error(r._ctx)
+    assert r._lib.pe_set_option(r._ctx, b"no_such_option", 1) != 0
+    assert b"no_such_option" in r._lib.pe_last_error(r._ctx)
+    for good in (64, 128, 512, 1024):
+        assert r._lib.pe_set_option(r._ctx, b"block_threads", good) == 0
+    assert r._lib.pe_set_option(r._ctx, b"block_threads", 128) == 0 and r._lib.pe_set_option(r._ctx, b"min_blocks", 4) == 0
+    assert r._lib.pe_scene_compile(r._ctx) == 0, r._lib.pe_last_error(r._ctx)
