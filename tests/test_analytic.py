@@ -1,0 +1,133 @@
+"""Analytic pixel checks of the oracle.
+
+The reference has no pixel pins, so the oracle is tied to the reference's shader TEXT here by a second, independent route:
+for tests/fixtures/analytic.ron every pixel of a frame has a closed form that can be written down from frag.glsl /
+library.glsl by hand -- no ray loop, no generated code, float64 numpy -- and the oracle's frame must agree with it to
+rounding (2e-5; the oracle computes in float32) everywhere except within a hair of a decision boundary.  Covered: the
+pixel -> ray map incl. the R2(0) sample offset and the row order (scene.rs:1688-1693, frag.glsl:449-455, 506-526),
+plane_intersect (library.glsl:149-162), the portal jump o' = B A^-1 o with the offset after it (scene.rs:624-627,
+library.glsl:366-379), the distance carried across the jump and the darkening (frag.glsl:119-141), material_simple2's
+angle term and color_grid (library.glsl:177-188, 318-335), the miss colour (scene.rs:1060) and the final sqrt
+(frag.glsl:550).  The GPU tests then hold the kernel to the oracle bit for bit on the same scene."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+SCENE = os.path.join(ROOT, "tests", "fixtures", "analytic.ron")
+W, H, DEPTH = 96, 54, 8
+IDENTITY = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
+
+
+def closed_form(w, h):
+    """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary)."""
+    px, py = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    m = float(min(w, h))
+    # scene.rs:1688-1693 + frag.glsl:515-526 with aa_count = 1, aa_start = 0: uv + R2(0) * pixel_size * 2, R2(0) = (.5, .5)
+    a = ((px + 0.5) - w / 2) / m * 2 + 0.5 * (1 / m) * 2
+    b = ((py + 0.5) - h / 2) / m * 2 + 0.5 * (1 / m) * 2
+    # frag.glsl:449-455 with the identity camera and view angle 90 degrees: d = normalize(a * tan(45), b * tan(45), 1)
+    n = np.sqrt(a * a + b * b + 1)
+    dz = 1 / n
+    out = np.empty((h, w, 3))
+    safe = np.ones((h, w), dtype=bool)
+
+    def near_boundary(x, edge, eps=2e-3):
+        return np.abs(x - edge) < eps
+
+    # gate: plane z = 3, inside the unit circle -> jump by (+100, 0, 0), step 2e-5 along d, carry on to the wall at z = 30
+    gx, gy = 3 * a, 3 * b
+    in_gate = gx * gx + gy * gy < 1
+    safe &= ~near_boundary(gx * gx + gy * gy, 1)
+    t1 = 3 * n
+    t2 = (30 - (3 + 2e-5 * dz)) * n                          # from the stepped origin to z = 30, along the unit direction
+    u, v = gx + a * dz * (2e-5 + t2), gy + b * dz * (2e-5 + t2)   # far wall's local (x, y): the jump moved x by exactly +100
+    all_t = t1 + t2
+    green = np.array([0.2, 0.9, 0.5])
+    c = green * (1 - 0.25) + green * dz[..., None] * 0.25    # color_add_weighted(c, c * |cos|, normal_coef); cos = d.z here
+    fu, fv = np.mod(u * 1.0 * 0.25, 1.0), np.mod(v * 1.0 * 0.25, 1.0)     # color_grid: fract(uv * grid_scale * 0.25)
+    sx, sy = (fu <= 0.5).astype(np.float64), (fv <= 0.5).astype(np.float64)   # step(edge = uv, x = 0.5) = 0.5 < uv ? 0 : 1
+    for f in (fu, fv):
+        safe &= ~(in_gate & (near_boundary(f, 0.5) | near_boundary(f, 0.0) | near_boundary(f, 1.0)))
+    low, high = 0.7 + (1.1 - 0.7) * sx, 1.1 + (0.7 - 1.1) * sx
+    factor = low + (high - low) * sy
+    c = c * (1 - 0.3) + (c * factor[..., None]) * 0.3
+    gray = (np.minimum(all_t, 210.0) - 10.0) / 200.0         # frag.glsl:133-135, camera_scale = 1; all_t > 10 on this path
+    assert (all_t[in_gate] > 10).all()
+    far = c * ((1 - gray) ** 4)[..., None]
+
+    # near wall: plane z = 6, |x| < 4, -2 < y < 3.5 (asymmetric in y: pins the row order), reached only outside the gate
+    nx, ny = 6 * a, 6 * b
+    on_near = (np.abs(nx) < 4) & (ny > -2) & (ny < 3.5) & ~in_gate
+    safe &= ~(~in_gate & (near_boundary(np.abs(nx), 4) | near_boundary(ny, -2) | near_boundary(ny, 3.5)))
+    red = np.array([0.8, 0.4, 0.2])
+    near = red * (1 - 0.5) + red * dz[..., None] * 0.5
+    assert (6 * n[on_near] < 10).all()                       # no darkening on this path
+    miss = np.full(3, 0.6 * 0.6)                             # current_color (1) * color(0.6, 0.6, 0.6), scene.rs:1060
+
+    out[:] = miss
+    out[on_near] = near[on_near]
+    out[in_gate] = far[in_gate]
+    return np.sqrt(out), safe, in_gate, on_near
+
+
+def oracle_frame():
+    from oracle import frontend, runner
+    ir = frontend.scene_ir(frontend.load_scene(SCENE), "analytic")
+    return ir, runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0)
+
+
+def test_oracle_frame_equals_the_closed_form():
+    want, safe, in_gate, on_near = closed_form(W, H)
+    _, got = oracle_frame()
+    assert np.all(got[..., 3] == 1.0)
+    assert in_gate.sum() > 200 and on_near.sum() > 200 and (~in_gate & ~on_near).sum() > 1000 and safe.mean() > 0.9
+    err = np.abs(got[..., :3].astype(np.float64) - want).max(axis=-1)
+    assert err[safe].max() < 2e-5, (err[safe].max(), np.argwhere(safe & (err >= 2e-5))[:5])
+    # the three regions really are different colours, and the few boundary pixels are one of the neighbouring closed forms
+    assert len({tuple(np.round(want[y, x], 3)) for y, x in ((H // 2 - 1, W // 2 - 1), (H // 2 + 12, W // 2 + 14), (2, 2))}) == 3
+    # centre pixel by hand: uv = 0 -> straight down the axis, through the gate, wall at distance 30 - 2e-5, grid cell
+    # factor 0.7: sqrt(green * (0.7 + 0.3 * 0.7) * (1 - (20 - 2e-5) / 200)^4)
+    centre = got[H // 2 - 1, W // 2 - 1, :3]
+    hand = np.sqrt(np.array([0.2, 0.9, 0.5]) * (0.7 + 0.3 * 0.7) * (1 - (20 - 2e-5) / 200) ** 4)
+    assert np.abs(centre - hand).max() < 2e-6
+
+
+def test_oracle_depth_and_switches_on_the_analytic_scene():
+    """Invariants with known answers on the same scene: depth 1 cannot finish the gate path (black behind the gate), depth 2
+    can; without darkening the far wall is the undarkened closed form; without the angle term cos drops out."""
+    from oracle import frontend, runner
+    want, safe, in_gate, on_near = closed_form(W, H)
+    ir = frontend.scene_ir(frontend.load_scene(SCENE), "analytic")
+    orc = runner.Oracle(ir, "strict")
+    d1 = orc.render(W, H, 1, camera=IDENTITY, camera_scale=1.0)
+    assert np.all(d1[in_gate & safe][:, :3] == 0.0)                       # loop exhausted -> black (frag.glsl:158)
+    assert np.abs(d1[on_near & safe][:, :3] - want[on_near & safe]).max() < 2e-5
+    d2 = orc.render(W, H, 2, camera=IDENTITY, camera_scale=1.0)
+    assert np.abs(d2[safe][:, :3] - want[safe]).max() < 2e-5
+    nodark = orc.render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0, darken_by_distance=0)
+    px, py = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    a, b = (px + 1 - W / 2) * 2 / H, (py + 1 - H / 2) * 2 / H
+    n = np.sqrt(a * a + b * b + 1)
+    all_t = 3 * n + (30 - (3 + 2e-5 / n)) * n
+    undo = ((1 - (all_t - 10) / 200) ** 4)[..., None]
+    sel = in_gate & safe
+    assert np.abs(nodark[sel][:, :3].astype(np.float64) ** 2 - (want[sel] ** 2) / undo[sel]).max() < 5e-5
+    flat = orc.render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0, angle_color_disable=1)
+    sel = on_near & safe
+    assert np.abs(flat[sel][:, :3] - np.sqrt(np.array([0.8, 0.4, 0.2]))).max() < 2e-6
+
+
+def test_generated_program_on_host_equals_the_closed_form(tmp_path):
+    """The sm_100a scene program for this scene, run thread by thread on the host (tests/host_harness): bit-identical to the
+    oracle's frame and within rounding of the closed form -- the kernel's code is held to the shader text directly, not only
+    through the oracle."""
+    from test_program_on_host import H as HH, W as HW, _run_on_host
+    assert (HW, HH) == (W, H)
+    ir, ref = oracle_frame()
+    got, _ = _run_on_host(tmp_path, "analytic", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
+    assert np.array_equal(np.ascontiguousarray(got).view(np.uint32), np.ascontiguousarray(ref).view(np.uint32))
+    want, safe, _, _ = closed_form(W, H)
+    assert np.abs(got[..., :3].astype(np.float64) - want)[safe].max() < 2e-5
