@@ -21,8 +21,10 @@ W, H, DEPTH = 96, 54, 8
 IDENTITY = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
 
 
-def closed_form(w, h):
-    """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary)."""
+def closed_form(w, h, s=1.0):
+    """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary, region masks).
+    s: scale of the gate's far side (gate_b) -- the jump then magnifies by s about the gate's centre, the offset step is taken
+    along the UN-normalised direction (length s) and normalize_ray leaves tmul = 1 / s (library.glsl:108-113, 366-371)."""
     px, py = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
     m = float(min(w, h))
     # scene.rs:1688-1693 + frag.glsl:515-526 with aa_count = 1, aa_start = 0: uv + R2(0) * pixel_size * 2, R2(0) = (.5, .5)
@@ -42,9 +44,10 @@ def closed_form(w, h):
     in_gate = gx * gx + gy * gy < 1
     safe &= ~near_boundary(gx * gx + gy * gy, 1)
     t1 = 3 * n
-    t2 = (30 - (3 + 2e-5 * dz)) * n                          # from the stepped origin to z = 30, along the unit direction
-    u, v = gx + a * dz * (2e-5 + t2), gy + b * dz * (2e-5 + t2)   # far wall's local (x, y): the jump moved x by exactly +100
-    all_t = t1 + t2
+    step = s * 2e-5                                          # r.o += r.d * offset with |r.d| = s, before the normalisation
+    t2 = (30 - (3 + step * dz)) * n                          # from the stepped origin to z = 30, along the unit direction
+    u, v = s * gx + a * dz * (step + t2), s * gy + b * dz * (step + t2)   # far wall's local (x, y): the jump moved x by exactly +100
+    all_t = t1 + t2 / s                                      # all_t += t * r.tmul (frag.glsl:119, 125)
     green = np.array([0.2, 0.9, 0.5])
     c = green * (1 - 0.25) + green * dz[..., None] * 0.25    # color_add_weighted(c, c * |cos|, normal_coef); cos = d.z here
     fu, fv = np.mod(u * 1.0 * 0.25, 1.0), np.mod(v * 1.0 * 0.25, 1.0)     # color_grid: fract(uv * grid_scale * 0.25)
@@ -73,9 +76,21 @@ def closed_form(w, h):
     return np.sqrt(out), safe, in_gate, on_near
 
 
-def oracle_frame():
-    from oracle import frontend, runner
-    ir = frontend.scene_ir(frontend.load_scene(SCENE), "analytic")
+def scene_ir(tmp_path=None, s=1.0):
+    from oracle import frontend
+    if s == 1.0:
+        return frontend.scene_ir(frontend.load_scene(SCENE), "analytic")
+    text = open(SCENE, encoding="utf-8").read()
+    old = '(name: "gate_b", data: Simple(offset: (100.0, 0.0, 3.0), scale: 1.0,'
+    assert old in text
+    path = tmp_path / f"analytic_s{s}.ron"
+    path.write_text(text.replace(old, old.replace("scale: 1.0", f"scale: {s!r}")), encoding="utf-8")
+    return frontend.scene_ir(frontend.load_scene(str(path)), f"analytic_s{s}")
+
+
+def oracle_frame(tmp_path=None, s=1.0):
+    from oracle import runner
+    ir = scene_ir(tmp_path, s)
     return ir, runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0)
 
 
@@ -118,6 +133,20 @@ def test_oracle_depth_and_switches_on_the_analytic_scene():
     flat = orc.render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0, angle_color_disable=1)
     sel = on_near & safe
     assert np.abs(flat[sel][:, :3] - np.sqrt(np.array([0.8, 0.4, 0.2]))).max() < 2e-6
+
+
+@pytest.mark.parametrize("s", [2.0, 0.5])
+def test_scaling_gate_carries_tmul_and_the_offset_step(s, tmp_path):
+    """The gate's far side scaled by s: the jump magnifies about the gate centre, the offset step is s * offset, distance
+    beyond the gate counts 1 / s (tmul) in the darkening.  Oracle and host-run kernel program against the closed form."""
+    from test_program_on_host import _run_on_host
+    want, safe, in_gate, _ = closed_form(W, H, s)
+    base, _, _, _ = closed_form(W, H, 1.0)
+    assert np.abs(want - base)[in_gate].max() > 0.01            # the scale really changes what is seen through the gate
+    ir, got = oracle_frame(tmp_path, s)
+    assert np.abs(got[..., :3].astype(np.float64) - want)[safe].max() < 2e-5
+    prog, _ = _run_on_host(tmp_path, f"analytic_s{s}", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
+    assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
 
 
 def test_generated_program_on_host_equals_the_closed_form(tmp_path):

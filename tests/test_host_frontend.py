@@ -408,6 +408,53 @@ def test_matrix_evaluators_agree_on_random_matrix_dags(seed, tmp_path):
         assert n >= 400 and 0 < nonfinite < n
 
 
+def test_matrix_kinds_known_answers(tmp_path):
+    """Conventions of the matrix kinds, by hand (matrix.rs:510-631): rotation order Rx*Ry*Rz in radians, scale before rotation
+    before offset; Mul{to, what} = what * to; Teleport = second * first^-1 * what; Inv; If on > 0.5; Lerp endpoints.  Both
+    front-ends, checked on what they do to a point."""
+    from oracle import frontend
+    hp = "1.5707963267948966"
+    text = open(FIXTURE, encoding="utf-8").read()
+    marker = '        (name: "ball_inv", data: Inv(Some(Named("ball")))),\n'
+
+    def simple(off, scale="1.0", rot="0.0, 0.0, 0.0"):
+        return f"Simple(offset: ({off}), scale: {scale}, rotate: ({rot}), mirror: (false, false, false))"
+    extra = [
+        ("k_srt", simple("1.0, 2.0, 3.0", "2.0", f"0.0, 0.0, {hp}")),
+        ("k_xz", simple("0.0, 0.0, 0.0", "1.0", f"{hp}, 0.0, {hp}")),
+        ("k_t1", simple("1.0, 0.0, 0.0")), ("k_s2", simple("0.0, 0.0, 0.0", "2.0")),
+        ("k_mul", 'Mul(to: Some(Named("k_t1")), what: Some(Named("k_s2")))'),
+        ("k_first", simple("0.0, 0.0, 1.0")), ("k_second", simple("0.0, 5.0, 0.0", "1.0", f"0.0, 0.0, {hp}")), ("k_what", simple("1.0, 0.0, 1.0")),
+        ("k_tp", 'Teleport(first_portal: Some(Named("k_first")), second_portal: Some(Named("k_second")), what: Some(Named("k_what")))'),
+        ("k_inv", 'Inv(Some(Named("k_srt")))'),
+        ("k_if1", 'If(condition: Value(0.51), then: Some(Named("k_t1")), otherwise: Some(Named("k_s2")))'),
+        ("k_if0", 'If(condition: Value(0.5), then: Some(Named("k_t1")), otherwise: Some(Named("k_s2")))'),
+        ("k_l0", 'Lerp(t: Value(0.0), first: Some(Named("k_srt")), second: Some(Named("k_second")))'),
+        ("k_l1", 'Lerp(t: Value(1.0), first: Some(Named("k_srt")), second: Some(Named("k_second")))'),
+        ("k_lh", 'Lerp(t: Value(0.5), first: Some(Named("k_t1")), second: Some(Named("k_what")))'),
+    ]
+    path = tmp_path / "kinds.ron"
+    path.write_text(text.replace(marker, marker + "".join(f'        (name: "{n}", data: {d}),\n' for n, d in extra), 1), encoding="utf-8")
+    for table in (frontend.load_scene(str(path)).uniform_table(), HostScene.from_file(str(path)).uniform_table()):
+        def at(name, p):
+            m = np.asarray(table[f"{name}_mat"][1], dtype=np.float64).reshape(4, 4).T
+            return (m @ np.array([*p, 1.0]))[:3]
+        near = lambda got, want: np.testing.assert_allclose(got, want, atol=1e-12)       # noqa: E731
+        near(at("k_srt", (1, 0, 0)), (1, 4, 3))            # scale 2, quarter turn about z: (1,0,0) -> (0,2,0), + offset
+        near(at("k_srt", (0, 0, 1)), (1, 2, 5))
+        near(at("k_xz", (1, 0, 0)), (0, 0, 1))             # Rx*Ry*Rz: z-turn first (x -> y), then x-turn (y -> z)
+        near(at("k_mul", (0, 0, 0)), (2, 0, 0))            # what * to = S(2) T(1,0,0)
+        near(at("k_tp", (0, 0, 0)), (0, 6, 0))             # (1,0,1) -> first^-1 -> (1,0,0) -> quarter turn (0,1,0) + (0,5,0)
+        near(at("k_inv", (1, 4, 3)), (1, 0, 0))
+        near(at("k_if1", (0, 0, 0)), (1, 0, 0))            # condition > 0.5 -> then
+        near(at("k_if0", (1, 1, 1)), (2, 2, 2))            # 0.5 is not > 0.5 -> otherwise
+        near(at("k_l0", (1, 1, 1)), at("k_srt", (1, 1, 1)))
+        near(at("k_l1", (1, 1, 1)), at("k_second", (1, 1, 1)))
+        near(at("k_lh", (0, 0, 0)), (1, 0, 0.5))           # translations interpolate linearly
+        inv = np.asarray(table["k_srt_mat_inv"][1], dtype=np.float64).reshape(4, 4).T
+        near((inv @ np.array([1, 4, 3, 1.0]))[:3], (1, 0, 0))
+
+
 def test_sqrt_matrices(tmp_path):
     """Matrix kind `Sqrt` (matrix.rs:606-613, 909-985; oracle/mat_sqrt.py, ph_matsqrt.cpp): known answers -- the case the one
     reference scene that uses the kind evaluates (portal_in_portal_plus_ultra.ron:961: b0 = scale 0.81 + offset -0.95 along z ->
