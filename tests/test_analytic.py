@@ -21,15 +21,17 @@ W, H, DEPTH = 96, 54, 8
 IDENTITY = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
 
 
-def closed_form(w, h, s=1.0):
+def closed_form(w, h, s=1.0, sample=0, linear=False):
     """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary, region masks).
     s: scale of the gate's far side (gate_b) -- the jump then magnifies by s about the gate's centre, the offset step is taken
     along the UN-normalised direction (length s) and normalize_ray leaves tmul = 1 / s (library.glsl:108-113, 366-371)."""
     px, py = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
     m = float(min(w, h))
     # scene.rs:1688-1693 + frag.glsl:515-526 with aa_count = 1, aa_start = 0: uv + R2(0) * pixel_size * 2, R2(0) = (.5, .5)
-    a = ((px + 0.5) - w / 2) / m * 2 + 0.5 * (1 / m) * 2
-    b = ((py + 0.5) - h / 2) / m * 2 + 0.5 * (1 / m) * 2
+    # sample i sits at R2(i) = fract(0.5 + (0.7548776662, 0.5698402910) * i) (frag.glsl:506-513)
+    r2x, r2y = np.mod(0.5 + 0.7548776662 * sample, 1.0), np.mod(0.5 + 0.5698402910 * sample, 1.0)
+    a = ((px + 0.5) - w / 2) / m * 2 + r2x * (1 / m) * 2
+    b = ((py + 0.5) - h / 2) / m * 2 + r2y * (1 / m) * 2
     # frag.glsl:449-455 with the identity camera and view angle 90 degrees: d = normalize(a * tan(45), b * tan(45), 1)
     n = np.sqrt(a * a + b * b + 1)
     dz = 1 / n
@@ -73,7 +75,33 @@ def closed_form(w, h, s=1.0):
     out[:] = miss
     out[on_near] = near[on_near]
     out[in_gate] = far[in_gate]
-    return np.sqrt(out), safe, in_gate, on_near
+    return (out if linear else np.sqrt(out)), safe, in_gate, on_near
+
+
+def closed_form2(w, h):
+    """tests/fixtures/analytic2.ron: sphere (centre (0,0,8), radius 2 = unit sphere under a scale-2 matrix), mirror plane
+    z = 12, plain wall z = -4 behind the camera seen only in the mirror."""
+    px, py = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    m = float(min(w, h))
+    a, b = (px + 1 - w / 2) * 2 / m, (py + 1 - h / 2) * 2 / m
+    n = np.sqrt(a * a + b * b + 1)
+    d = np.stack([a / n, b / n, 1 / n], axis=-1)
+    disc = 64 / (n * n) - 60                                  # (d.c)^2 - (|c|^2 - radius^2), c = (0, 0, 8)
+    on_ball = disc > 0
+    safe = np.abs(disc) > 2e-2
+    t = 8 / n - np.sqrt(np.where(on_ball, disc, 0.0))
+    nrm = (d * t[..., None] - np.array([0.0, 0.0, 8.0])) / 2  # unit; adjugate of a uniform scale keeps its direction
+    cos = np.abs((d * nrm).sum(axis=-1))
+    blue = np.array([0.3, 0.6, 0.9])
+    ball = blue * 0.5 + blue * cos[..., None] * 0.5
+    assert (t[on_ball] < 10).all()
+    # mirror at z = 12: reflected direction (a, b, -1) / n, step 2e-5 along it, down to z = -4; the distance keeps adding up
+    all_t = 12 * n + (16 - 2e-5 / n) * n
+    wall = np.array([0.7, 0.7, 0.2])
+    c = wall * 0.5 + wall * (1 / n)[..., None] * 0.5
+    seen = np.array([0.9, 0.95, 1.0]) * c * ((1 - (all_t - 10) / 200) ** 4)[..., None]
+    out = np.where(on_ball[..., None], ball, seen)
+    return np.sqrt(out), safe, on_ball
 
 
 def scene_ir(tmp_path=None, s=1.0):
@@ -147,6 +175,41 @@ def test_scaling_gate_carries_tmul_and_the_offset_step(s, tmp_path):
     assert np.abs(got[..., :3].astype(np.float64) - want)[safe].max() < 2e-5
     prog, _ = _run_on_host(tmp_path, f"analytic_s{s}", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
     assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+
+
+def test_antialiasing_averages_the_r2_samples():
+    """aa_count = 4: the mean of the LINEAR colours at the four R2 sample positions, then the sqrt (frag.glsl:515-526, 550);
+    aa_start = 2, aa_count = 1: the single sample R2(2) (what the motion-blur loop uses, main.rs:1797)."""
+    from oracle import runner
+    orc = runner.Oracle(scene_ir(), "strict")
+    parts = [closed_form(W, H, sample=i, linear=True) for i in range(4)]
+    want = np.sqrt(sum(p[0] for p in parts) / 4)
+    safe = np.logical_and.reduce([p[1] for p in parts])
+    same_region = np.logical_and.reduce([p[2] == parts[0][2] for p in parts]) & np.logical_and.reduce([p[3] == parts[0][3] for p in parts])
+    assert (safe & ~same_region).sum() > 50                      # pixels whose samples straddle two regions are checked too
+    got = orc.render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0, aa_count=4)
+    assert np.abs(got[..., :3].astype(np.float64) - want)[safe].max() < 2e-5
+    w2, safe2, _, _ = closed_form(W, H, sample=2)
+    got2 = orc.render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0, aa_count=1, aa_start=2)
+    assert np.abs(got2[..., :3].astype(np.float64) - w2)[safe2].max() < 2e-5
+    assert np.abs(w2 - closed_form(W, H)[0]).max() > 0.05       # and it is a different frame from sample 0
+
+
+def test_sphere_under_a_scaling_matrix_and_a_mirror(tmp_path):
+    """Complex object path (transform by M^-1, t / len, normal through adjugate(M); scene.rs:962-976) and the Reflect material
+    (my_reflect, the offset along the reflected ray, mul_to_color, distance summed over both legs; library.glsl:70-72, 347-354)
+    against their closed form; oracle and host-run kernel program."""
+    from oracle import frontend, runner
+    from test_program_on_host import _run_on_host
+    ir = frontend.scene_ir(frontend.load_scene(os.path.join(ROOT, "tests", "fixtures", "analytic2.ron")), "analytic2")
+    got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0)
+    want, safe, on_ball = closed_form2(W, H)
+    assert on_ball.sum() > 100 and safe.mean() > 0.95
+    assert np.abs(got[..., :3].astype(np.float64) - want)[safe].max() < 2e-5
+    prog, _ = _run_on_host(tmp_path, "analytic2", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
+    assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+    one = runner.Oracle(ir, "strict").render(W, H, 1, camera=IDENTITY, camera_scale=1.0)       # depth 1: the mirror path cannot finish
+    assert np.all(one[~on_ball & safe][:, :3] == 0.0) and np.abs(one[on_ball & safe][:, :3] - want[on_ball & safe]).max() < 2e-5
 
 
 def test_generated_program_on_host_equals_the_closed_form(tmp_path):
