@@ -21,7 +21,7 @@ W, H, DEPTH = 96, 54, 8
 IDENTITY = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
 
 
-def closed_form(w, h, s=1.0, sample=0, linear=False):
+def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None):
     """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary, region masks).
     s: scale of the gate's far side (gate_b) -- the jump then magnifies by s about the gate's centre, the offset step is taken
     along the UN-normalised direction (length s) and normalize_ray leaves tmul = 1 / s (library.glsl:108-113, 366-371)."""
@@ -32,11 +32,19 @@ def closed_form(w, h, s=1.0, sample=0, linear=False):
     r2x, r2y = np.mod(0.5 + 0.7548776662 * sample, 1.0), np.mod(0.5 + 0.5698402910 * sample, 1.0)
     a = ((px + 0.5) - w / 2) / m * 2 + r2x * (1 / m) * 2
     b = ((py + 0.5) - h / 2) / m * 2 + r2y * (1 / m) * 2
-    # frag.glsl:449-455 with the identity camera and view angle 90 degrees: d = normalize(a * tan(45), b * tan(45), 1)
+    # frag.glsl:449-455 with the identity camera and view angle 90 degrees: d = normalize(a * tan(45), b * tan(45), 1);
+    # another projection hands in its own direction field: everything below only needs a = dx/dz, b = dy/dz, n = 1/dz of
+    # rays going forward, the pixels whose ray goes backwards (they see nothing) and the pixels outside the image (black)
+    backwards = black = edge = np.zeros((h, w), dtype=bool)
+    if projection is not None:
+        dx, dy, dzz, black, edge = projection(a, b)
+        backwards = ~(dzz > 1e-6)
+        dzs = np.where(backwards, 1.0, dzz)
+        a, b = dx / dzs, dy / dzs
     n = np.sqrt(a * a + b * b + 1)
     dz = 1 / n
     out = np.empty((h, w, 3))
-    safe = np.ones((h, w), dtype=bool)
+    safe = ~edge                                               # |position| equal to the image border up to rounding
 
     def near_boundary(x, edge, eps=2e-3):
         return np.abs(x - edge) < eps
@@ -50,18 +58,27 @@ def closed_form(w, h, s=1.0, sample=0, linear=False):
     t2 = (30 - (3 + step * dz)) * n                          # from the stepped origin to z = 30, along the unit direction
     u, v = s * gx + a * dz * (step + t2), s * gy + b * dz * (step + t2)   # far wall's local (x, y): the jump moved x by exactly +100
     all_t = t1 + t2 / s                                      # all_t += t * r.tmul (frag.glsl:119, 125)
-    green = np.array([0.2, 0.9, 0.5])
-    c = green * (1 - 0.25) + green * dz[..., None] * 0.25    # color_add_weighted(c, c * |cos|, normal_coef); cos = d.z here
-    fu, fv = np.mod(u * 1.0 * 0.25, 1.0), np.mod(v * 1.0 * 0.25, 1.0)     # color_grid: fract(uv * grid_scale * 0.25)
-    sx, sy = (fu <= 0.5).astype(np.float64), (fv <= 0.5).astype(np.float64)   # step(edge = uv, x = 0.5) = 0.5 < uv ? 0 : 1
-    for f in (fu, fv):
-        safe &= ~(in_gate & (near_boundary(f, 0.5) | near_boundary(f, 0.0) | near_boundary(f, 1.0)))
-    low, high = 0.7 + (1.1 - 0.7) * sx, 1.1 + (0.7 - 1.1) * sx
-    factor = low + (high - low) * sy
-    c = c * (1 - 0.3) + (c * factor[..., None]) * 0.3
-    gray = (np.minimum(all_t, 210.0) - 10.0) / 200.0         # frag.glsl:133-135, camera_scale = 1; all_t > 10 on this path
-    assert (all_t[in_gate] > 10).all()
-    far = c * ((1 - gray) ** 4)[..., None]
+    def gridded(u, v, all_t, where):
+        """material_simple2 of the far wall (angle term, color_grid) + the darkening, for hits at local (u, v)."""
+        nonlocal safe
+        green = np.array([0.2, 0.9, 0.5])
+        c = green * (1 - 0.25) + green * dz[..., None] * 0.25    # color_add_weighted(c, c * |cos|, normal_coef); cos = d.z here
+        fu, fv = np.mod(u * 1.0 * 0.25, 1.0), np.mod(v * 1.0 * 0.25, 1.0)     # color_grid: fract(uv * grid_scale * 0.25)
+        sx, sy = (fu <= 0.5).astype(np.float64), (fv <= 0.5).astype(np.float64)   # step(edge = uv, x = 0.5) = 0.5 < uv ? 0 : 1
+        for f in (fu, fv):
+            safe &= ~(where & (near_boundary(f, 0.5) | near_boundary(f, 0.0) | near_boundary(f, 1.0)))
+        low, high = 0.7 + (1.1 - 0.7) * sx, 1.1 + (0.7 - 1.1) * sx
+        factor = low + (high - low) * sy
+        c = c * (1 - 0.3) + (c * factor[..., None]) * 0.3
+        gray = (np.minimum(all_t, 210.0) - 10.0) / 200.0         # frag.glsl:133-135, camera_scale = 1; all_t > 10 on these paths
+        assert (all_t[where] > 10).all()
+        return c * ((1 - gray) ** 4)[..., None]
+    far = gridded(u, v, all_t, in_gate)
+    # wide-angle projections also see the far wall directly (x in 60..140 at z = 30), and could graze the gate's far disc
+    direct = ~in_gate & (np.abs(30 * a - 100) < 40) & (np.abs(30 * b) < 40)
+    safe &= ~(~in_gate & (near_boundary(np.abs(30 * a - 100), 40, 0.05) | near_boundary(np.abs(30 * b), 40, 0.05)))
+    safe &= ~((np.abs(3 * a - 100) < 1.5) & (np.abs(3 * b) < 1.5))
+    far_direct = gridded(30 * a - 100, 30 * b, 30 * n, direct)
 
     # near wall: plane z = 6, |x| < 4, -2 < y < 3.5 (asymmetric in y: pins the row order), reached only outside the gate
     nx, ny = 6 * a, 6 * b
@@ -72,9 +89,14 @@ def closed_form(w, h, s=1.0, sample=0, linear=False):
     assert (6 * n[on_near] < 10).all()                       # no darkening on this path
     miss = np.full(3, 0.6 * 0.6)                             # current_color (1) * color(0.6, 0.6, 0.6), scene.rs:1060
 
+    in_gate, on_near, direct = in_gate & ~backwards & ~black, on_near & ~backwards & ~black, direct & ~backwards & ~black
     out[:] = miss
+    out[direct] = far_direct[direct]
     out[on_near] = near[on_near]
     out[in_gate] = far[in_gate]
+    out[black] = 0.0
+    if projection is not None:
+        safe &= ~(np.abs(dzz) < 1e-3)
     return (out if linear else np.sqrt(out)), safe, in_gate, on_near
 
 
@@ -193,6 +215,44 @@ def test_antialiasing_averages_the_r2_samples():
     got2 = orc.render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0, aa_count=1, aa_start=2)
     assert np.abs(got2[..., :3].astype(np.float64) - w2)[safe2].max() < 2e-5
     assert np.abs(w2 - closed_form(W, H)[0]).max() > 0.05       # and it is a different frame from sample 0
+
+
+def test_projections(tmp_path):
+    """Other ray maps of get_color2 (frag.glsl:408-455) on the same scene: a narrower view angle, the 360 and VR180
+    equirectangular cameras with their black bars; oracle and host-run kernel program."""
+    from oracle import runner
+    from test_program_on_host import _run_on_host
+    ir = scene_ir()
+    orc = runner.Oracle(ir, "strict")
+
+    def narrow(x, y):
+        hh = np.tan(np.pi / 6)                                  # view angle 60 degrees
+        nn = np.sqrt((x * hh) ** 2 + (y * hh) ** 2 + 1)
+        return x * hh / nn, y * hh / nn, 1 / nn, np.zeros(x.shape, dtype=bool), np.zeros(x.shape, dtype=bool)
+
+    def vr180(x, y):
+        yaw, pitch = x * np.pi / 2, y * np.pi / 2
+        edge = (np.abs(np.abs(x) - 1) < 1e-6) | (np.abs(np.abs(y) - 1) < 1e-6)
+        return np.sin(yaw) * np.cos(pitch), np.sin(pitch), np.cos(yaw) * np.cos(pitch), (np.abs(x) > 1) | (np.abs(y) > 1), edge
+
+    def full360(x, y):
+        ax, ay = W / min(W, H), H / min(W, H)
+        rx, ry = (2 * ay, ay) if ax >= 2 * ay else (ax, ax / 2)
+        yaw, pitch = x / rx * np.pi, y / ry * np.pi / 2
+        edge = (np.abs(np.abs(x) - rx) < 1e-6) | (np.abs(np.abs(y) - ry) < 1e-6)
+        return np.sin(yaw) * np.cos(pitch), np.sin(pitch), np.cos(yaw) * np.cos(pitch), (np.abs(x) > rx) | (np.abs(y) > ry), edge
+
+    for name, proj, kw, attrs in (("narrow", narrow, {"view_angle": np.pi / 3}, {"view_angle": np.pi / 3}),
+                                  ("vr180", vr180, {"use_180_camera": 1}, {"use_180_camera": 1}),
+                                  ("full360", full360, {"use_360_camera": 1}, {"use_360_camera": 1})):
+        want, safe, in_gate, on_near = closed_form(W, H, projection=proj)
+        got = orc.render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0, **kw)
+        assert in_gate.sum() > 20 and on_near.sum() > 100 and safe.mean() > 0.85, name
+        err = np.abs(got[..., :3].astype(np.float64) - want)
+        assert err[safe].max() < 3e-5, (name, err[safe].max(), np.argwhere(safe & (err.max(axis=-1) >= 3e-5))[:5])
+        prog, _ = _run_on_host(tmp_path, name, None, ir=ir, tex={}, depth=DEPTH, attrs=dict(attrs, camera_matrix=IDENTITY))
+        assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32)), name
+    assert (closed_form(W, H, projection=full360)[0][:2] == 0).all() and (closed_form(W, H, projection=vr180)[0][:, :10] == 0).all()
 
 
 def test_sphere_under_a_scaling_matrix_and_a_mirror(tmp_path):
