@@ -137,7 +137,10 @@ int ph_scene_set_value(ph_scene* s, const char* name, double value) {
     ph::Uniform& u = s->scene.uniforms[it->second];
     switch (u.kind) {
         case ph::Uniform::Bool: u.b = value != 0.0; break;
-        case ph::Uniform::Int: u.i = int(value); break;
+        case ph::Uniform::Int:
+            if (!(value >= -2147483648.0 && value <= 2147483647.0)) return fail(s, std::string("value for int uniform `") + name + "` is out of range");
+            u.i = int(value);
+            break;
         case ph::Uniform::Float: case ph::Uniform::Angle: case ph::Uniform::Progress: u.f = value; break;
         default: return fail(s, std::string("uniform `") + name + "` is a formula; set its inputs instead");
     }
@@ -292,7 +295,8 @@ int ph_render_target(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, const p
 int ph_render_motion_blur_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, int frame_index, int frame_count,
                                 int motion_blur_frames, double duration_seconds, uint8_t* out_host) {
     if (!s || !ctx || !p || !out_host) return 1;
-    if (frame_count < 1 || motion_blur_frames < 1 || motion_blur_frames > 64 || frame_index < 0)
+    if (frame_count < 1 || motion_blur_frames < 1 || motion_blur_frames > 64 || frame_index < 0 || p->width <= 0 || p->height <= 0 ||
+        p->width > 65536 || p->height > 65536)
         return fail(s, "ph_render_motion_blur_frame: bad frame arguments");
     const size_t n = size_t(p->width) * size_t(p->height);
     void* out8 = nullptr;
