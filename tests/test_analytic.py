@@ -21,7 +21,7 @@ W, H, DEPTH = 96, 54, 8
 IDENTITY = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
 
 
-def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None):
+def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None):
     """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary, region masks).
     s: scale of the gate's far side (gate_b) -- the jump then magnifies by s about the gate's centre, the offset step is taken
     along the UN-normalised direction (length s) and normalize_ray leaves tmul = 1 / s (library.glsl:108-113, 366-371)."""
@@ -32,6 +32,17 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None):
     r2x, r2y = np.mod(0.5 + 0.7548776662 * sample, 1.0), np.mod(0.5 + 0.5698402910 * sample, 1.0)
     a = ((px + 0.5) - w / 2) / m * 2 + r2x * (1 / m) * 2
     b = ((py + 0.5) - h / 2) / m * 2 + r2y * (1 / m) * 2
+    ex = 0.0
+    split = np.zeros((h, w), dtype=bool)
+    if stereo is not None:
+        # frag.glsl:476-497: side by side -- each half of the frame is its own image for one eye, here at (-+stereo, 0, 0)
+        posx, posy = a / 2 * m + w / 2, b / 2 * m + h / 2
+        left = posx < w / 2
+        split = np.abs(posx - w / 2) < 1e-6
+        m2 = float(min(w / 2, h))
+        a = np.where(left, posx - w / 4, posx - w / 2 - w / 4) / m2 * 2
+        b = (posy - h / 2) / m2 * 2
+        ex = np.where(left, -stereo, stereo)
     # frag.glsl:449-455 with the identity camera and view angle 90 degrees: d = normalize(a * tan(45), b * tan(45), 1);
     # another projection hands in its own direction field: everything below only needs a = dx/dz, b = dy/dz, n = 1/dz of
     # rays going forward, the pixels whose ray goes backwards (they see nothing) and the pixels outside the image (black)
@@ -44,13 +55,13 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None):
     n = np.sqrt(a * a + b * b + 1)
     dz = 1 / n
     out = np.empty((h, w, 3))
-    safe = ~edge                                               # |position| equal to the image border up to rounding
+    safe = ~edge & ~split                                      # |position| equal to the image border / the eye split up to rounding
 
     def near_boundary(x, edge, eps=2e-3):
         return np.abs(x - edge) < eps
 
     # gate: plane z = 3, inside the unit circle -> jump by (+100, 0, 0), step 2e-5 along d, carry on to the wall at z = 30
-    gx, gy = 3 * a, 3 * b
+    gx, gy = ex + 3 * a, 3 * b
     in_gate = gx * gx + gy * gy < 1
     safe &= ~near_boundary(gx * gx + gy * gy, 1)
     t1 = 3 * n
@@ -75,13 +86,13 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None):
         return c * ((1 - gray) ** 4)[..., None]
     far = gridded(u, v, all_t, in_gate)
     # wide-angle projections also see the far wall directly (x in 60..140 at z = 30), and could graze the gate's far disc
-    direct = ~in_gate & (np.abs(30 * a - 100) < 40) & (np.abs(30 * b) < 40)
-    safe &= ~(~in_gate & (near_boundary(np.abs(30 * a - 100), 40, 0.05) | near_boundary(np.abs(30 * b), 40, 0.05)))
-    safe &= ~((np.abs(3 * a - 100) < 1.5) & (np.abs(3 * b) < 1.5))
-    far_direct = gridded(30 * a - 100, 30 * b, 30 * n, direct)
+    direct = ~in_gate & (np.abs(ex + 30 * a - 100) < 40) & (np.abs(30 * b) < 40)
+    safe &= ~(~in_gate & (near_boundary(np.abs(ex + 30 * a - 100), 40, 0.05) | near_boundary(np.abs(30 * b), 40, 0.05)))
+    safe &= ~((np.abs(ex + 3 * a - 100) < 1.5) & (np.abs(3 * b) < 1.5))
+    far_direct = gridded(ex + 30 * a - 100, 30 * b, 30 * n, direct)
 
     # near wall: plane z = 6, |x| < 4, -2 < y < 3.5 (asymmetric in y: pins the row order), reached only outside the gate
-    nx, ny = 6 * a, 6 * b
+    nx, ny = ex + 6 * a, 6 * b
     on_near = (np.abs(nx) < 4) & (ny > -2) & (ny < 3.5) & ~in_gate
     safe &= ~(~in_gate & (near_boundary(np.abs(nx), 4) | near_boundary(ny, -2) | near_boundary(ny, 3.5)))
     red = np.array([0.8, 0.4, 0.2])
@@ -90,6 +101,21 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None):
     miss = np.full(3, 0.6 * 0.6)                             # current_color (1) * color(0.6, 0.6, 0.6), scene.rs:1060
 
     in_gate, on_near, direct = in_gate & ~backwards & ~black, on_near & ~backwards & ~black, direct & ~backwards & ~black
+    if depth_map is not None:
+        # frag.glsl:80-98, 130, 457-463: depth = all_t / camera_scale of the final hit, coloured by the inferno ramp at
+        # 1 - clamp((depth - min) / (max - min)); rays that end on nothing are black
+        lo, hi = depth_map
+        depth = np.where(in_gate, all_t, np.where(on_near, 6 * n, 30 * n))
+        tt = 1 - np.clip((depth - lo) / max(1e-6, hi - lo), 0, 1)
+        stops = np.array([[0.001462, 0.000466, 0.013866], [0.258234, 0.038571, 0.406485], [0.578304, 0.148039, 0.404411],
+                          [0.865006, 0.316822, 0.226055], [0.987622, 0.645320, 0.039886], [0.988362, 0.998364, 0.644924]]) ** 2
+        seg = np.minimum((tt / 0.2).astype(int), 4)
+        for edge_t in (0.2, 0.4, 0.6, 0.8):
+            safe &= ~near_boundary(tt, edge_t, 1e-4)
+        f = ((tt - 0.2 * seg) / 0.2)[..., None]
+        ramp = stops[seg] * (1 - f) + stops[seg + 1] * f
+        near = far = far_direct = ramp
+        miss = np.zeros(3)
     out[:] = miss
     out[direct] = far_direct[direct]
     out[on_near] = near[on_near]
@@ -242,7 +268,25 @@ def test_projections(tmp_path):
         edge = (np.abs(np.abs(x) - rx) < 1e-6) | (np.abs(np.abs(y) - ry) < 1e-6)
         return np.sin(yaw) * np.cos(pitch), np.sin(pitch), np.cos(yaw) * np.cos(pitch), (np.abs(x) > rx) | (np.abs(y) > ry), edge
 
+    def panini(x, y):
+        fov, dd = np.pi / 2, 0.7                                # PaniniProjection(tc, _view_angle, _panini_param), frag.glsl:304-340
+        d2 = dd * dd
+        fo = np.pi / 2 - fov * 0.5
+        f = np.cos(fo) / np.sin(fo)
+        f2 = f * f
+        bb = (np.sqrt(max(0.0, (dd + d2) ** 2 * (f2 + f2 * f2))) - (dd * f + f)) / (d2 + d2 * f2 - 1.0)
+        hx, v = x * bb, y * bb
+        k = hx * hx / (dd + 1.0) ** 2
+        discr = np.maximum(0.0, k * k * d2 - (k + 1.0) * (k * d2 - 1.0))
+        cos_phi = (-k * dd + np.sqrt(discr)) / (k + 1.0)
+        tan_theta = v / ((dd + 1.0) / (dd + cos_phi))
+        sin_phi = np.sqrt(np.maximum(0.0, 1.0 - cos_phi ** 2)) * np.where(hx < 0, -1.0, 1.0)
+        sc = 1 / np.sqrt(1.0 + tan_theta ** 2)
+        return sin_phi * sc, tan_theta * sc, cos_phi * sc, np.zeros(x.shape, dtype=bool), np.abs(hx) < 1e-9
+
     for name, proj, kw, attrs in (("narrow", narrow, {"view_angle": np.pi / 3}, {"view_angle": np.pi / 3}),
+                                  ("panini", panini, {"use_panini_projection": 1, "panini_param": 0.7},
+                                   {"use_panini_projection": 1, "panini_param": 0.7}),
                                   ("vr180", vr180, {"use_180_camera": 1}, {"use_180_camera": 1}),
                                   ("full360", full360, {"use_360_camera": 1}, {"use_360_camera": 1})):
         want, safe, in_gate, on_near = closed_form(W, H, projection=proj)
@@ -253,6 +297,38 @@ def test_projections(tmp_path):
         prog, _ = _run_on_host(tmp_path, name, None, ir=ir, tex={}, depth=DEPTH, attrs=dict(attrs, camera_matrix=IDENTITY))
         assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32)), name
     assert (closed_form(W, H, projection=full360)[0][:2] == 0).all() and (closed_form(W, H, projection=vr180)[0][:, :10] == 0).all()
+
+
+def test_side_by_side_stereo(tmp_path):
+    """_draw_side_by_side (frag.glsl:476-497): the left half is the left eye's image, the right half the right eye's, each with
+    its own image coordinates; eyes at -+0.4 on the x axis (teleport_eye_matrices with nothing between the eyes)."""
+    from oracle import runner
+    from test_program_on_host import _run_on_host
+    ir, e = scene_ir(), 0.4
+    want, safe, in_gate, on_near = closed_form(W, H, stereo=e)
+    eye = lambda x: [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, x, 0, 0, 1.0]       # noqa: E731
+    got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0, draw_side_by_side=1,
+                                             camera_left_eye=eye(-e), camera_right_eye=eye(e))
+    assert safe.mean() > 0.9 and in_gate[:, :W // 2].sum() > 50 and in_gate[:, W // 2:].sum() > 50
+    assert np.abs(got[..., :3].astype(np.float64) - want)[safe].max() < 2e-5
+    assert np.abs(want[:, :W // 2] - want[:, W // 2:]).max() > 0.05            # the two eyes see the gate in different places
+    prog, _ = _run_on_host(tmp_path, "stereo", None, ir=ir, tex={}, depth=DEPTH,
+                           attrs={"camera_matrix": IDENTITY, "draw_side_by_side": 1, "eye_distance": e})
+    assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+
+
+def test_depth_map_colouring(tmp_path):
+    """_draw_depth_map: the inferno ramp over the depth of the final hit, black where the ray ends on nothing."""
+    from oracle import runner
+    from test_program_on_host import _run_on_host
+    ir = scene_ir()
+    want, safe, in_gate, on_near = closed_form(W, H, depth_map=(2.0, 40.0))
+    got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0, draw_depth_map=1, depth_map_min=2.0, depth_map_max=40.0)
+    assert np.abs(got[..., :3].astype(np.float64) - want)[safe].max() < 2e-5 and safe.mean() > 0.9
+    assert len({tuple(np.round(want[y, x], 2)) for y, x in ((H // 2 - 1, W // 2 - 1), (H // 2 + 12, W // 2 + 14), (2, 2))}) == 3
+    prog, _ = _run_on_host(tmp_path, "depth", None, ir=ir, tex={}, depth=DEPTH,
+                           attrs={"camera_matrix": IDENTITY, "draw_depth_map": 1, "depth_map_min": 2.0, "depth_map_max": 40.0})
+    assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
 
 
 def test_sphere_under_a_scaling_matrix_and_a_mirror(tmp_path):
