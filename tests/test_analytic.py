@@ -299,6 +299,40 @@ def test_projections(tmp_path):
     assert (closed_form(W, H, projection=full360)[0][:2] == 0).all() and (closed_form(W, H, projection=vr180)[0][:, :10] == 0).all()
 
 
+def test_refraction_through_a_pane(tmp_path):
+    """Refract material (my_refract, library.glsl:75-92, 357-364): the pane's hit normal faces the ray, so the text takes its
+    `!from_outside` branch: ri = 1 / 1.5, dir' = dir * ri + n * (ri * c - sqrt(1 - ri^2 (1 - c^2))); the wall behind is shaded
+    with the refracted direction and the distance of both legs."""
+    from oracle import frontend, runner
+    from test_program_on_host import _run_on_host
+    ir = frontend.scene_ir(frontend.load_scene(os.path.join(ROOT, "tests", "fixtures", "analytic3.ron")), "analytic3")
+    px, py = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    a, b = (px + 1 - W / 2) * 2 / H, (py + 1 - H / 2) * 2 / H
+    n = np.sqrt(a * a + b * b + 1)
+    dz = 1 / n
+    through = (np.abs(5 * a) < 3) & (np.abs(5 * b) < 2)
+    safe = ~(np.abs(np.abs(5 * a) - 3) < 2e-3) & ~(np.abs(np.abs(5 * b) - 2) < 2e-3)
+    ri = 1 / 1.5
+    disc = 1 - ri * ri * (1 - dz * dz)                         # c = -dot(normal, dir) = d.z with normal = (0, 0, -1)
+    rz = np.sqrt(disc)                                         # z of the refracted (unit) direction; x, y are d.xy * ri
+    t2 = (5 - 2e-5 * rz) / rz
+    wall = np.array([0.9, 0.5, 0.3])
+
+    def shade(cos, all_t):
+        c = wall * 0.5 + wall * cos[..., None] * 0.5
+        gray = np.where(all_t > 10, (all_t - 10) / 200, 0.0)
+        return c * ((1 - gray) ** 4)[..., None]
+    seen = np.array([0.8, 0.9, 1.0]) * shade(rz, 5 * n + t2)
+    plain = shade(dz, 10 * n)
+    safe &= ~(~through & (np.abs(10 * n - 10) < 1e-4)) & ~(through & (np.abs(5 * n + t2 - 10) < 1e-4))     # all_t > _t_start
+    want = np.sqrt(np.where(through[..., None], seen, plain))
+    got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0)
+    assert through.sum() > 500 and safe.mean() > 0.9
+    assert np.abs(got[..., :3].astype(np.float64) - want)[safe].max() < 2e-5
+    prog, _ = _run_on_host(tmp_path, "analytic3", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
+    assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+
+
 def test_side_by_side_stereo(tmp_path):
     """_draw_side_by_side (frag.glsl:476-497): the left half is the left eye's image, the right half the right eye's, each with
     its own image coordinates; eyes at -+0.4 on the x axis (teleport_eye_matrices with nothing between the eyes)."""
