@@ -21,7 +21,7 @@ W, H, DEPTH = 96, 54, 8
 IDENTITY = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
 
 
-def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None):
+def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid"):
     """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary, region masks).
     s: scale of the gate's far side (gate_b) -- the jump then magnifies by s about the gate's centre, the offset step is taken
     along the UN-normalised direction (length s) and normalize_ray leaves tmul = 1 / s (library.glsl:108-113, 366-371)."""
@@ -74,12 +74,27 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=
         nonlocal safe
         green = np.array([0.2, 0.9, 0.5])
         c = green * (1 - 0.25) + green * dz[..., None] * 0.25    # color_add_weighted(c, c * |cos|, normal_coef); cos = d.z here
-        fu, fv = np.mod(u * 1.0 * 0.25, 1.0), np.mod(v * 1.0 * 0.25, 1.0)     # color_grid: fract(uv * grid_scale * 0.25)
-        sx, sy = (fu <= 0.5).astype(np.float64), (fv <= 0.5).astype(np.float64)   # step(edge = uv, x = 0.5) = 0.5 < uv ? 0 : 1
-        for f in (fu, fv):
-            safe &= ~(where & (near_boundary(f, 0.5) | near_boundary(f, 0.0) | near_boundary(f, 1.0)))
-        low, high = 0.7 + (1.1 - 0.7) * sx, 1.1 + (0.7 - 1.1) * sx
-        factor = low + (high - low) * sy
+        if grid == "grid":
+            fu, fv = np.mod(u * 1.0 * 0.25, 1.0), np.mod(v * 1.0 * 0.25, 1.0)     # color_grid: fract(uv * grid_scale * 0.25)
+            sx, sy = (fu <= 0.5).astype(np.float64), (fv <= 0.5).astype(np.float64)   # step(edge = uv, x = 0.5) = 0.5 < uv ? 0 : 1
+            for f in (fu, fv):
+                safe &= ~(where & (near_boundary(f, 0.5) | near_boundary(f, 0.0) | near_boundary(f, 1.0)))
+            low, high = 0.7 + (1.1 - 0.7) * sx, 1.1 + (0.7 - 1.1) * sx
+            factor = low + (high - low) * sy
+        elif grid == "grid2":                                     # color_grid2 / circle_sdf, library.glsl:199-211
+            sxy = np.array([2.0, np.sqrt(3.0) * 2.0])
+            pos = np.stack([u, v], axis=-1) / sxy
+            d1 = (np.mod(pos, 1.0) - 0.5) * sxy
+            d2 = (np.mod(pos + 0.5, 1.0) - 0.5) * sxy
+            dd = np.sqrt(np.minimum((d1 * d1).sum(axis=-1), (d2 * d2).sum(axis=-1))) - 1.0
+            factor = np.where(dd < -0.2, 1.1, 0.7)
+            safe &= ~(where & near_boundary(dd, -0.2, 5e-3))
+        else:                                                     # color_grid3, library.glsl:268-283
+            qx, qy = np.mod(u * 0.5, 1.0) - 0.5, np.mod(v * 0.5, 1.0) - 0.5
+            dist = np.maximum(np.abs(qx), np.abs(qy)) * 2
+            factor = np.where(dist > 0.985, 0.4, np.where(dist < 0.94, 1.0, np.where(qx > qy, 0.7, 1.2)))
+            safe &= ~(where & (near_boundary(dist, 0.985, 5e-3) | near_boundary(dist, 0.94, 5e-3) |
+                               ((dist >= 0.94) & (dist <= 0.985) & near_boundary(qx - qy, 0.0, 5e-3))))
         c = c * (1 - 0.3) + (c * factor[..., None]) * 0.3
         gray = (np.minimum(all_t, 210.0) - 10.0) / 200.0         # frag.glsl:133-135, camera_scale = 1; all_t > 10 on these paths
         assert (all_t[where] > 10).all()
@@ -152,16 +167,19 @@ def closed_form2(w, h):
     return np.sqrt(out), safe, on_ball
 
 
-def scene_ir(tmp_path=None, s=1.0):
+def scene_ir(tmp_path=None, s=1.0, grid="grid"):
     from oracle import frontend
-    if s == 1.0:
+    if s == 1.0 and grid == "grid":
         return frontend.scene_ir(frontend.load_scene(SCENE), "analytic")
     text = open(SCENE, encoding="utf-8").read()
     old = '(name: "gate_b", data: Simple(offset: (100.0, 0.0, 3.0), scale: 1.0,'
-    assert old in text
-    path = tmp_path / f"analytic_s{s}.ron"
-    path.write_text(text.replace(old, old.replace("scale: 1.0", f"scale: {s!r}")), encoding="utf-8")
-    return frontend.scene_ir(frontend.load_scene(str(path)), f"analytic_s{s}")
+    mat = 'normal_coef: 0.25, grid: true, grid_scale: 1.0, grid_coef: 0.3, grid2: false, grid3: false'
+    assert old in text and mat in text
+    text = text.replace(old, old.replace("scale: 1.0", f"scale: {s!r}"))
+    text = text.replace(mat, mat.replace("grid2: false", "grid2: " + str(grid == "grid2").lower()).replace("grid3: false", "grid3: " + str(grid == "grid3").lower()))
+    path = tmp_path / f"analytic_s{s}_{grid}.ron"
+    path.write_text(text, encoding="utf-8")
+    return frontend.scene_ir(frontend.load_scene(str(path)), f"analytic_s{s}_{grid}")
 
 
 def oracle_frame(tmp_path=None, s=1.0):
@@ -297,6 +315,21 @@ def test_projections(tmp_path):
         prog, _ = _run_on_host(tmp_path, name, None, ir=ir, tex={}, depth=DEPTH, attrs=dict(attrs, camera_matrix=IDENTITY))
         assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32)), name
     assert (closed_form(W, H, projection=full360)[0][:2] == 0).all() and (closed_form(W, H, projection=vr180)[0][:, :10] == 0).all()
+
+
+@pytest.mark.parametrize("grid", ["grid2", "grid3"])
+def test_other_grid_patterns(grid, tmp_path):
+    """material_simple2's grid2 (circle_sdf discs) and grid3 (framed cells) variants on the far wall, at a frame size where
+    the pattern is resolved."""
+    from oracle import runner
+    w, h = 192, 108
+    ir = scene_ir(tmp_path, grid=grid)
+    want, safe, in_gate, _ = closed_form(w, h, grid=grid)
+    got = runner.Oracle(ir, "strict").render(w, h, DEPTH, camera=IDENTITY, camera_scale=1.0)
+    err = np.abs(got[..., :3].astype(np.float64) - want)
+    assert safe.mean() > 0.85 and err[safe].max() < 2e-5, (err[safe].max(), np.argwhere(safe & (err.max(axis=-1) >= 2e-5))[:5])
+    assert np.abs(want - closed_form(w, h)[0])[in_gate].max() > 0.02            # not the default pattern
+    assert len({round(float(x), 3) for x in (want[in_gate][:, 1] / want[in_gate][:, 1].max())}) > 3
 
 
 def test_refraction_through_a_pane(tmp_path):
