@@ -21,7 +21,7 @@ W, H, DEPTH = 96, 54, 8
 IDENTITY = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
 
 
-def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid"):
+def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid", sky=None):
     """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary, region masks).
     s: scale of the gate's far side (gate_b) -- the jump then magnifies by s about the gate's centre, the offset step is taken
     along the UN-normalised direction (length s) and normalize_ray leaves tmul = 1 / s (library.glsl:108-113, 366-371)."""
@@ -47,8 +47,10 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=
     # another projection hands in its own direction field: everything below only needs a = dx/dz, b = dy/dz, n = 1/dz of
     # rays going forward, the pixels whose ray goes backwards (they see nothing) and the pixels outside the image (black)
     backwards = black = edge = np.zeros((h, w), dtype=bool)
+    ray = None
     if projection is not None:
         dx, dy, dzz, black, edge = projection(a, b)
+        ray = (dx, dy, dzz)
         backwards = ~(dzz > 1e-6)
         dzs = np.where(backwards, 1.0, dzz)
         a, b = dx / dzs, dy / dzs
@@ -114,6 +116,23 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=
     near = red * (1 - 0.5) + red * dz[..., None] * 0.5
     assert (6 * n[on_near] < 10).all()                       # no darkening on this path
     miss = np.full(3, 0.6 * 0.6)                             # current_color (1) * color(0.6, 0.6, 0.6), scene.rs:1060
+    if sky is not None:
+        # scene.rs:1052-1058: with a skybox the miss colour is the texture looked up by the direction of the CAMERA ray
+        # (`_camera_mul_inv` = identity here): u = atan(z, x), v = atan(|xz|, y), at ((u / pi + 1) / 2, v / pi), squared
+        rx, ry, rz = ray if ray is not None else (a / n, b / n, 1 / n)
+        su = (np.arctan2(rz, rx) / np.pi + 1) / 2
+        sv = np.arctan2(np.sqrt(rx * rx + rz * rz), ry) / np.pi
+        th, tw = sky.shape[:2]
+        tx, ty = su * tw - 0.5, sv * th - 0.5                  # pinned sampling rule: texel centres at (i + .5) / size, bilinear,
+        x0, y0 = np.floor(tx), np.floor(ty)                    # clamp to edge (oracle/glsl_compat.h `texture`)
+        fx, fy = (tx - x0)[..., None], (ty - y0)[..., None]
+        tex = sky[..., :3].astype(np.float64) / 255
+        ix0, ix1 = np.clip(x0, 0, tw - 1).astype(int), np.clip(x0 + 1, 0, tw - 1).astype(int)
+        iy0, iy1 = np.clip(y0, 0, th - 1).astype(int), np.clip(y0 + 1, 0, th - 1).astype(int)
+        top = tex[iy0, ix0] * (1 - fx) + tex[iy0, ix1] * fx
+        bot = tex[iy1, ix0] * (1 - fx) + tex[iy1, ix1] * fx
+        miss = (top * (1 - fy) + bot * fy) ** 2
+        safe &= ~((rx < 0) & (np.abs(rz) < 2e-2))              # the seam of atan(z, x)
 
     in_gate, on_near, direct = in_gate & ~backwards & ~black, on_near & ~backwards & ~black, direct & ~backwards & ~black
     if depth_map is not None:
@@ -364,6 +383,71 @@ def test_refraction_through_a_pane(tmp_path):
     assert np.abs(got[..., :3].astype(np.float64) - want)[safe].max() < 2e-5
     prog, _ = _run_on_host(tmp_path, "analytic3", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
     assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+
+
+def test_subspace_flag(tmp_path):
+    """TELEPORT_SUBSPACE flips the ray's in_subspace flag (library.glsl:575-589, frag.glsl:33-50); objects are tested only in
+    their own space (scene.rs:906-910); a ray that ends on nothing inside the subspace is black (frag.glsl:150-152)."""
+    from oracle import frontend, runner
+    from test_program_on_host import _run_on_host
+    text = open(SCENE, encoding="utf-8").read().replace("return TELEPORT;", "return TELEPORT_SUBSPACE;")
+    assert text.count("in_subspace: Normal,") == 3
+    head, tail = text.rsplit("in_subspace: Normal,", 1)
+
+    def vr180(x, y):
+        yaw, pitch = x * np.pi / 2, y * np.pi / 2
+        edge = (np.abs(np.abs(x) - 1) < 1e-6) | (np.abs(np.abs(y) - 1) < 1e-6)
+        return np.sin(yaw) * np.cos(pitch), np.sin(pitch), np.cos(yaw) * np.cos(pitch), (np.abs(x) > 1) | (np.abs(y) > 1), edge
+    want, safe, in_gate, on_near = closed_form(W, H, projection=vr180)
+    plain = closed_form(W, H, projection=vr180)[0]
+    direct = safe & ~in_gate & ~on_near & (np.abs(plain - 0.6).max(axis=-1) > 1e-3) & (plain.max(axis=-1) > 0)
+    assert direct.sum() > 20                                    # VR180 is wide enough to see the far wall directly as well
+    for name, scene_text, through_gate, seen_directly in (("far_in_subspace", head + "in_subspace: Subspace," + tail, True, False),
+                                                           ("far_in_normal", text, False, True)):
+        path = tmp_path / f"{name}.ron"
+        path.write_text(scene_text, encoding="utf-8")
+        ir = frontend.scene_ir(frontend.load_scene(str(path)), name)
+        got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0, use_180_camera=1)
+        exp = want.copy()
+        if not through_gate:
+            exp[in_gate] = 0.0                                 # nothing to hit inside the subspace -> black
+        if not seen_directly:
+            exp[direct] = 0.6                                  # the wall lives in the subspace: ordinary rays miss it
+        assert np.abs(got[..., :3].astype(np.float64) - exp)[safe].max() < 3e-5, name
+        prog, _ = _run_on_host(tmp_path, name, None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY, "use_180_camera": 1})
+        assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32)), name
+
+
+def test_skybox_lookup(tmp_path):
+    """A scene with a skybox: rays that end on nothing take the texture's colour at the equirectangular position of the camera
+    ray's direction (scene.rs:1052-1058), sampled by the pinned rule; ordinary camera and the 360 camera (the whole sky)."""
+    from oracle import frontend, runner
+    from test_program_on_host import _run_on_host
+    text = open(SCENE, encoding="utf-8").read()
+    assert "    textures: ([]),\n" in text and "    animation_stages: ([]),\n" in text
+    text = text.replace("    textures: ([]),\n", '    textures: ([(name: "sky", data: ("sky.png"))]),\n')
+    text = text.replace("    animation_stages: ([]),\n", '    animation_stages: ([]),\n    skybox: Some("sky"),\n')
+    path = tmp_path / "analytic_sky.ron"
+    path.write_text(text, encoding="utf-8")
+    ir = frontend.scene_ir(frontend.load_scene(str(path)), "analytic_sky")
+    assert ir["skybox"] == "sky"
+    ys, xs = np.meshgrid(np.arange(8), np.arange(16), indexing="ij")
+    sky = np.stack([40 + 12 * xs, 30 + 25 * ys, 250 - 12 * xs + 3 * ys, np.full_like(xs, 255)], axis=-1).astype(np.uint8)
+
+    def full360(x, y):
+        rx, ry = W / H, W / H / 2
+        yaw, pitch = x / rx * np.pi, y / ry * np.pi / 2
+        edge = (np.abs(np.abs(x) - rx) < 1e-6) | (np.abs(np.abs(y) - ry) < 1e-6)
+        return np.sin(yaw) * np.cos(pitch), np.sin(pitch), np.cos(yaw) * np.cos(pitch), (np.abs(x) > rx) | (np.abs(y) > ry), edge
+    orc = runner.Oracle(ir, "strict", textures={"sky": sky})
+    for name, proj, kw in (("plain", None, {}), ("sky360", full360, {"use_360_camera": 1})):
+        want, safe, in_gate, on_near = closed_form(W, H, projection=proj, sky=sky)
+        got = orc.render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0, **kw)
+        err = np.abs(got[..., :3].astype(np.float64) - want)
+        assert safe.mean() > 0.85 and err[safe].max() < 3e-5, (name, err[safe].max(), np.argwhere(safe & (err.max(axis=-1) >= 3e-5))[:5])
+        assert np.ptp(want[safe & ~in_gate & ~on_near][:, 0]) > 0.2                # the sky really varies over the frame
+        prog, _ = _run_on_host(tmp_path, name, None, ir=ir, tex={"sky": sky}, depth=DEPTH, attrs=dict(kw, camera_matrix=IDENTITY))
+        assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32)), name
 
 
 def test_side_by_side_stereo(tmp_path):
