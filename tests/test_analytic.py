@@ -385,6 +385,39 @@ def test_refraction_through_a_pane(tmp_path):
     assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
 
 
+def test_external_ray_probe(tmp_path):
+    """teleport_external_ray (frag.glsl:205-257), the camera-teleportation probe, on segments with known answers: a step through
+    the gate lands at the jumped end point (plus the offset step); with the far side scaled by 2 the rest of the step is
+    stretched by 2 about the gate; a step that stops short of the gate, or passes beside it, reports no teleport; a step into
+    the near wall reports the object and no position."""
+    from oracle import frontend, runner
+    orc = runner.Oracle(scene_ir(), "strict")
+
+    def probe(o, a, b):
+        pos, have, enc, chg = o.probe(a, b, camera=IDENTITY, camera_scale=1.0)
+        return np.asarray(pos, dtype=np.float64), have, enc, chg
+    pos, have, enc, chg = probe(orc, (0.2, 0.1, 2.0), (0.2, 0.1, 4.0))
+    assert have and not enc and not chg and np.abs(pos - (100.2, 0.1, 4.0 + 2e-5)).max() < 1e-5
+    pos, have, enc, chg = probe(orc, (0.5, -0.3, 2.5), (-0.1, 0.3, 3.5))               # oblique: crosses z = 3 at (0.2, 0, 3)
+    d = np.array([-0.6, 0.6, 1.0]) / np.sqrt(0.36 + 0.36 + 1.0)
+    assert have and np.abs(pos - (np.array([99.9, 0.3, 3.5]) + d * 2e-5)).max() < 1e-5
+    pos, have, enc, chg = probe(orc, (0.2, 0.1, 1.0), (0.2, 0.1, 2.9))                 # stops short of the gate
+    assert not have and not enc and np.all(pos == 0)
+    pos, have, enc, chg = probe(orc, (1.5, 0.0, 2.0), (1.5, 0.0, 4.0))                 # beside the gate, nothing on the way
+    assert not have and not enc
+    pos, have, enc, chg = probe(orc, (1.5, 0.0, 5.0), (1.5, 0.0, 7.0))                 # into the near wall at z = 6
+    assert not have and enc and np.all(pos == 0)
+    big = runner.Oracle(scene_ir(tmp_path, 2.0), "strict")
+    pos, have, enc, chg = probe(big, (0.2, 0.1, 2.0), (0.2, 0.1, 4.0))
+    assert have and np.abs(pos - (100.4, 0.2, 3.0 + 4e-5 + 2.0)).max() < 1e-5         # gate centre + 2 * (offset, remaining step)
+    text = open(SCENE, encoding="utf-8").read().replace("return TELEPORT;", "return TELEPORT_SUBSPACE;")
+    path = tmp_path / "probe_sub.ron"
+    path.write_text(text, encoding="utf-8")
+    o2 = runner.Oracle(frontend.scene_ir(frontend.load_scene(str(path)), "probe_sub"), "strict")
+    pos, have, enc, chg = probe(o2, (0.2, 0.1, 2.0), (0.2, 0.1, 4.0))
+    assert have and chg and np.abs(pos - (100.2, 0.1, 4.0 + 2e-5)).max() < 1e-5
+
+
 def test_subspace_flag(tmp_path):
     """TELEPORT_SUBSPACE flips the ray's in_subspace flag (library.glsl:575-589, frag.glsl:33-50); objects are tested only in
     their own space (scene.rs:906-910); a ray that ends on nothing inside the subspace is black (frag.glsl:150-152)."""
