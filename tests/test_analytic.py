@@ -385,6 +385,23 @@ def test_refraction_through_a_pane(tmp_path):
     assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
 
 
+@pytest.mark.parametrize("name", ["analytic", "analytic2", "analytic3"])
+def test_cpp_front_end_reads_the_analytic_scenes_like_the_oracle(name):
+    """The product's own front-end (C++) on the same files: identical uniform tables, and a program that compiles for sm_100a."""
+    from oracle import frontend
+    from portal_b200.host import HostRenderer, HostScene
+    path = os.path.join(ROOT, "tests", "fixtures", name + ".ron")
+    want = frontend.load_scene(path).uniform_table()
+    hs = HostScene.from_file(path)
+    got = hs.uniform_table()
+    assert list(want) == list(got)
+    for k in want:
+        assert np.array_equal(np.asarray(want[k][1], dtype=np.float64), np.asarray(got[k][1], dtype=np.float64)), k
+    r = HostRenderer(hs, device=-1)
+    assert "pe_render_kernel" in r.source()
+    r.close()
+
+
 def test_external_ray_probe(tmp_path):
     """teleport_external_ray (frag.glsl:205-257), the camera-teleportation probe, on segments with known answers: a step through
     the gate lands at the jumped end point (plus the offset step); with the far side scaled by 2 the rest of the step is
