@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Kernel-time sweep over generator options (run on the GPU box).  Prints one line per combination:
-scene, options, registers, kernel ms (CUDA events, mean of N launches after warm-up), Mpx/s."""
+scene, options, registers, kernel ms (CUDA events, mean of N launches after warm-up), Mpx/s.
+
+    python tools/sweep.py <scene[,scene]> '<json: option -> list of values>' [launches] [WxHxDEPTH]"""
 import itertools
 import json
 import os
@@ -30,10 +32,11 @@ def main():
     scenes = sys.argv[1].split(",") if len(sys.argv) > 1 else ["portal_in_portal"]
     grid = json.loads(sys.argv[2]) if len(sys.argv) > 2 else {"persistent": [0], "min_blocks": [1, 4, 5], "unroll_loops": [1, 0]}
     n = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+    size = tuple(int(x) for x in sys.argv[4].split("x")) if len(sys.argv) > 4 else None
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     for scene in scenes:
-        w, h, d = SCENES[scene]
+        w, h, d = size or SCENES[scene]
         ir = load_scene_ir(os.path.join(ROOT, "tests/golden/scenes", f"{scene}.scene.json"))
         tex = load_textures(os.path.join(ROOT, "tests/golden/scenes", f"{scene}.textures.npz"))
         out = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
