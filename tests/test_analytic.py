@@ -351,6 +351,58 @@ def test_other_grid_patterns(grid, tmp_path):
     assert len({round(float(x), 3) for x in (want[in_gate][:, 1] / want[in_gate][:, 1].max())}) > 3
 
 
+def test_library_triangle_and_cylinder(tmp_path):
+    """The predefined library's triangle() (barycentric u, v feed the grid) and cylinder() (near side, far side where the near
+    one falls off the end, outward normal) against plain analytic geometry."""
+    from oracle import frontend, runner
+    from test_program_on_host import _run_on_host
+    ir = frontend.scene_ir(frontend.load_scene(os.path.join(ROOT, "tests", "fixtures", "analytic4.ron")), "analytic4")
+    px, py = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    a, b = (px + 1 - W / 2) * 2 / H, (py + 1 - H / 2) * 2 / H
+    n = np.sqrt(a * a + b * b + 1)
+    dx, dy, dz = a / n, b / n, 1 / n
+    eps = 2e-3
+    # triangle (-2,-1), (2,-1), (0,2) in the plane z = 6: P = v0 + u (4, 0) + v (2, 3)
+    v = (6 * b + 1) / 3
+    u = (6 * a + 2 - 2 * v) / 4
+    on_tri = (u >= 0) & (v >= 0) & (u + v <= 1)
+    safe = ~((np.abs(u) < eps) | (np.abs(v) < eps) | (np.abs(u + v - 1) < eps))
+    fu, fv = np.mod(u * 8 * 0.25, 1.0), np.mod(v * 8 * 0.25, 1.0)
+    for f in (fu, fv):
+        safe &= ~(on_tri & ((np.abs(f - 0.5) < eps) | (f < eps) | (f > 1 - eps)))
+    sx, sy = (fu <= 0.5).astype(np.float64), (fv <= 0.5).astype(np.float64)
+    low, high = 0.7 + 0.4 * sx, 1.1 - 0.4 * sx
+    factor = low + (high - low) * sy
+    gold = np.array([0.9, 0.8, 0.1])
+    c = gold * 0.5 + gold * dz[..., None] * 0.5
+    tri = c * 0.7 + c * factor[..., None] * 0.3
+    # open cylinder of radius 1 about the line x = 2.5, y = 3, for 6 < z < 12: seen partly from outside (near side) and
+    # partly through its open near end (only the far side lies between the ends)
+    A, Bh, Cc = np.maximum(dx * dx + dy * dy, 1e-300), 2.5 * dx + 3 * dy, 2.5 * 2.5 + 9 - 1.0
+    disc = Bh * Bh - A * Cc
+    root = np.sqrt(np.where(disc > 0, disc, 0.0))
+    t_near, t_far = (Bh - root) / A, (Bh + root) / A
+    between = lambda tt: (tt * dz > 6) & (tt * dz < 12)        # noqa: E731
+    near_ok, far_ok = between(t_near), between(t_far)
+    t = np.where(near_ok, t_near, t_far)
+    on_rod = (disc > 0) & (near_ok | far_ok) & ~on_tri
+    safe &= ~(np.abs(disc) < 5e-3)
+    for tt in (t_near, t_far):
+        safe &= ~((disc > 0) & ((np.abs(tt * dz - 6) < 2e-2) | (np.abs(tt * dz - 12) < 2e-2)))
+    cos = np.abs(dx * (t * dx - 2.5) + dy * (t * dy - 3))
+    blue = np.array([0.4, 0.7, 0.9])
+    gray = np.where(t > 10, (t - 10) / 200, 0.0)
+    safe &= ~(on_rod & (np.abs(t - 10) < 1e-3))
+    rod = blue * cos[..., None] * ((1 - gray) ** 4)[..., None]
+    want = np.sqrt(np.where(on_tri[..., None], tri, np.where(on_rod[..., None], rod, 0.36)))
+    got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0)
+    assert on_tri.sum() > 100 and on_rod.sum() > 80 and ((disc > 0) & ~near_ok & far_ok).sum() > 3 and safe.mean() > 0.85, (on_tri.sum(), on_rod.sum(), ((disc > 0) & ~near_ok & far_ok).sum(), safe.mean())
+    err = np.abs(got[..., :3].astype(np.float64) - want)
+    assert err[safe].max() < 3e-5, (err[safe].max(), np.argwhere(safe & (err.max(axis=-1) >= 3e-5))[:5])
+    prog, _ = _run_on_host(tmp_path, "analytic4", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
+    assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+
+
 def test_refraction_through_a_pane(tmp_path):
     """Refract material (my_refract, library.glsl:75-92, 357-364): the pane's hit normal faces the ray, so the text takes its
     `!from_outside` branch: ri = 1 / 1.5, dir' = dir * ri + n * (ri * c - sqrt(1 - ri^2 (1 - c^2))); the wall behind is shaded
