@@ -15,3 +15,6 @@ timeout 200 python tools/sweep.py basics '{"block_threads":[128,256,512],"min_bl
 echo "== launch list of the bench command"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02a_launches_bench.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 tail -3 gpurun_out/r02a_launches_bench.csv
+# on an 8-GPU call (gpurun --gpus 8), the orbit both ways:
+#   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tools/orbit_frame_parallel.py > gpurun_out/r02a_orbit_frames_n8.json
+#   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --scene mobius_monoportal --orbit 360 --steps 48 --no-cpu-baseline > gpurun_out/r02a_orbit_rows_n8.json
