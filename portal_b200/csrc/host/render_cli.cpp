@@ -65,8 +65,8 @@ int main(int argc, char** argv) {
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
         if (a == "--width") width = std::atoi(next());
         else if (a == "--height") height = std::atoi(next());
-        else if (a == "--render-depth") depth = std::atoi(next());
-        else if (a == "--aa-count") aa = std::atoi(next());
+        else if (a == "--render-depth" || a == "--render_depth") depth = std::atoi(next());
+        else if (a == "--aa-count" || a == "--aa_count") aa = std::atoi(next());
         else if (a == "--time") time = std::atof(next());
         else if (a == "--device") device = std::atoi(next());
         else if (a == "--stage") stage = next();
