@@ -5,7 +5,7 @@
 //                      [--time T] [--stage NAME] [--animation NAME] [--camera NAME] [--device K]
 //                      [--texture name=file.rgba:WxH ...] [--output out.ppm]
 //   portal_b200_render render <scene.ron> [--animations a,b,... | --starts-with PREFIX] [--fps N] [--motion-blur-frames M] [--width W]
-//                      [--height H] [--render-depth D] [--aa-count N] [--stereo-image] [--out-dir DIR] [--max-frames K]
+//                      [--height H] [--render-depth D] [--aa-count N] [--stereo-image] [--no-skip-existing] [--out-dir DIR] [--max-frames K]
 //                      (`portal render`, main.rs:2808-2873 -> render_named_animations :1876-1930 ->
 //                       render_animation :1757-1830; frames are written as DIR/<animation>/frame_<i>.ppm, the
 //                       ffmpeg step is out of scope)
@@ -13,6 +13,10 @@
 // Output: binary PPM (P6) of the RGBA8 frame the reference would hand to export_png (alpha dropped), or
 // raw RGBA8 with a .rgba extension.  PNG encode/decode is out of scope: textures
 // are passed as raw RGBA8 files.
+#include <sys/stat.h>
+#include <sys/types.h>
+
+#include <cerrno>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,24 +47,43 @@ static bool write_image(const std::string& output, const std::vector<uint8_t>& p
     return bool(out);
 }
 
+static bool file_exists(const std::string& path) {
+    struct stat st;
+    return ::stat(path.c_str(), &st) == 0;
+}
+
+// std::fs::create_dir_all (main.rs:1781-1783)
+static bool make_dirs(const std::string& path) {
+    for (size_t i = 1; i <= path.size(); i++) {
+        if (i != path.size() && path[i] != '/') continue;
+        const std::string part = path.substr(0, i);
+        if (::mkdir(part.c_str(), 0755) != 0 && errno != EEXIST) return false;
+    }
+    struct stat st;
+    return ::stat(path.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+
 int main(int argc, char** argv) {
     const bool frame_cmd = argc >= 3 && std::strcmp(argv[1], "render-frame") == 0;
     const bool anim_cmd = argc >= 3 && std::strcmp(argv[1], "render") == 0;
     if (!frame_cmd && !anim_cmd) {
         std::fprintf(stderr, "usage: %s render-frame <scene.ron> [--width W] [--height H] [--render-depth D] [--aa-count N] [--time T] "
                              "[--stage NAME] [--animation NAME] [--camera NAME] [--device K] [--texture name=file.rgba:WxH] [--output out.ppm]\n"
-                             "       %s render <scene.ron> [--animations a,b | --starts-with PREFIX] [--fps N] [--motion-blur-frames M] [--width W] [--height H] "
-                             "[--render-depth D] [--aa-count N] [--stereo-image] [--out-dir DIR] [--max-frames K]\n", argv[0], argv[0]);
+                             "       %s render <scene.ron> [a,b | --animations a,b | --starts-with PREFIX] [--fps N] [--motion-blur-frames M] [--width W] [--height H] "
+                             "[--render-depth D] [--aa-count N] [--stereo-image] [--no-skip-existing] [--out-dir DIR] [--max-frames K]\n", argv[0], argv[0]);
         return 2;
     }
     std::string scene_path = argv[2], output = "frame.ppm", out_dir = "video";
-    int width = 1920, height = 1080, depth = 100, aa = 1, device = 0;  // defaults of RenderFrameCliOptions, main.rs:2744-2754
+    // defaults of RenderFrameCliOptions (main.rs:2744-2754) / RenderCliOptions (main.rs:2764-2803)
+    int width = frame_cmd ? 1920 : 3840, height = frame_cmd ? 1080 : 2160, depth = frame_cmd ? 100 : 150, aa = frame_cmd ? 1 : 4, device = 0;
     int fps = 60, motion_blur = 1, max_frames = -1;
-    bool stereo = false;
+    bool stereo = false, skip_existing = true;
     double time = 0.0;
     std::vector<std::string> textures;
     std::string stage, animation, camera, animations, starts_with;
-    for (int i = 3; i < argc; i++) {
+    int first_option = 3;
+    if (anim_cmd && argc > 3 && std::strncmp(argv[3], "--", 2) != 0) animations = argv[first_option++];   // `render <scene> [animations]`
+    for (int i = first_option; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
         if (a == "--width") width = std::atoi(next());
@@ -73,12 +96,13 @@ int main(int argc, char** argv) {
         else if (a == "--animation") animation = next();
         else if (a == "--camera") camera = next();
         else if (a == "--animations") animations = next();
-        else if (a == "--starts-with") starts_with = next();
+        else if (a == "--starts-with" || a == "--filter-starts-with" || a == "--starts_with" || a == "--filter_starts_with") starts_with = next();
         else if (a == "--fps") fps = std::atoi(next());
-        else if (a == "--motion-blur-frames") motion_blur = std::atoi(next());
+        else if (a == "--motion-blur-frames" || a == "--motion_blur_frames") motion_blur = std::atoi(next());
         else if (a == "--out-dir") out_dir = next();
         else if (a == "--max-frames") max_frames = std::atoi(next());
-        else if (a == "--stereo-image") stereo = true;
+        else if (a == "--stereo-image" || a == "--stereoimage" || a == "--stereo_image") stereo = true;
+        else if (a == "--no-skip-existing" || a == "--no_skip_existing") skip_existing = false;
         else if (a == "--output") output = next();
         else if (a == "--texture") textures.push_back(next());
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
@@ -163,13 +187,13 @@ int main(int argc, char** argv) {
             if (all && !starts_with.empty() && names[k].compare(0, starts_with.size(), starts_with) != 0) continue;
             std::printf("Rendering animation %s, %zu/%zu\n", names[k].c_str(), k + 1, names.size());
             const std::string dir = out_dir + "/" + names[k];
-            std::string cmd = "mkdir -p '" + dir + "'";
-            if (std::system(cmd.c_str()) != 0) { std::fprintf(stderr, "cannot create %s\n", dir.c_str()); return 1; }
+            if (!make_dirs(dir)) { std::fprintf(stderr, "cannot create %s\n", dir.c_str()); return 1; }
             const float duration32 = float(duration);                                          // render_animation takes f32
             int count = int(duration32 * float(fps));                                           // main.rs:1785
             if (count < 1) count = 1;
             const int todo = max_frames >= 0 && max_frames < count ? max_frames : count;
             for (int i = 0; i < todo; i++) {
+                if (skip_existing && file_exists(dir + "/frame_" + std::to_string(i) + ".ppm")) continue;   // resumes like main.rs:1789-1793
                 if (ph_player_render_motion_blur_frame(player, ctx, &p, i, count, motion_blur, double(duration32), px.data())) {
                     std::fprintf(stderr, "%s\n", ph_player_last_error(player));
                     return 1;

@@ -330,7 +330,7 @@ def test_cli_render_frame_animation_and_render_loop(torch_cuda, tmp_path):
     assert r.returncode == 1 and "has no animation named `nope`" in r.stderr
     # the offline loop: 2 of the 4.0 s * 5 fps = 20 frames of "through", 3 motion-blur sub-frames each
     r = subprocess.run([exe, "render", FIXTURE, "--animations", "through", "--fps", "5", "--motion-blur-frames", "3", "--width", "96",
-                        "--height", "54", "--render-depth", "8", "--out-dir", str(tmp_path / "video"), "--max-frames", "2"],
+                        "--height", "54", "--render-depth", "8", "--aa-count", "1", "--out-dir", str(tmp_path / "video"), "--max-frames", "2"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     hs = HostScene.from_file(FIXTURE)
