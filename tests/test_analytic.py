@@ -403,6 +403,67 @@ def test_library_triangle_and_cylinder(tmp_path):
     assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
 
 
+def test_debug_matrix_axes(tmp_path):
+    """DebugMatrix: three capsules (radius 0.03, length 1 in the matrix's frame) along the axes, red / green / blue with the
+    angle term; here scaled by 5 at z = 6.  Closed form: a capsule is a finite cylinder plus two spheres."""
+    from oracle import frontend, runner
+    from test_program_on_host import _run_on_host
+    ir = frontend.scene_ir(frontend.load_scene(os.path.join(ROOT, "tests", "fixtures", "analytic5.ron")), "analytic5")
+    w, h = 192, 108
+    px, py = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    a, b = (px + 1 - w / 2) * 2 / h, (py + 1 - h / 2) * 2 / h
+    n = np.sqrt(a * a + b * b + 1)
+    d = np.stack([a / n, b / n, 1 / n], axis=-1)
+    rad, p0 = 0.03 * 5, np.array([0.0, 0.0, 6.0])
+    best_t = np.full((h, w), np.inf)
+    colour = np.zeros((h, w, 3))
+    safe = np.ones((h, w), dtype=bool)
+    for axis, rgb in ((0, (0.9, 0.2, 0.2)), (1, (0.2, 0.9, 0.2)), (2, (0.2, 0.2, 0.9))):
+        e = np.zeros(3)
+        e[axis] = 1.0
+        p1 = p0 + 5 * e
+        # infinite cylinder about the axis line: |(t d - p0) - ((t d - p0).e) e| = rad
+        de, pe = d @ e, -(p0 @ e)
+        A = 1 - de * de
+        Bh = -(d @ p0) - de * pe                                # half of the linear coefficient of t, negated below
+        Cc = p0 @ p0 - pe * pe - rad * rad
+        disc = Bh * Bh - A * Cc
+        with np.errstate(invalid="ignore", divide="ignore"):
+            tc = (-Bh - np.sqrt(np.where(disc > 0, disc, np.nan))) / A
+        along = tc * de + pe                                    # position along the axis, 0 .. 5 on the body
+        t_body = np.where((disc > 0) & (along > 0) & (along < 5), tc, np.inf)
+        t_axis = t_body
+        for c in (p0, p1):                                      # end spheres
+            bb = d @ c
+            dd = bb * bb - (c @ c - rad * rad)
+            ts = np.where(dd > 0, bb - np.sqrt(np.where(dd > 0, dd, 0.0)), np.inf)
+            t_axis = np.minimum(t_axis, ts)
+            safe &= ~(np.abs(dd) < 2e-4)
+        safe &= ~(np.abs(disc) < 2e-4) & ~((disc > 0) & ((np.abs(along) < 2e-2) | (np.abs(along - 5) < 2e-2)))
+        hit = t_axis < best_t
+        pos = d * np.where(np.isfinite(t_axis), t_axis, 0.0)[..., None]
+        hh = np.clip((pos - p0) @ e, 0, 5)
+        nrm = (pos - p0 - hh[..., None] * e) / rad
+        cos = np.abs((d * nrm).sum(axis=-1))
+        col = np.array(rgb) ** 2                                # color(r, g, b) squares its arguments
+        shade = col * 0.5 + col * cos[..., None] * 0.5
+        colour = np.where(hit[..., None], shade, colour)
+        best_t = np.where(hit, t_axis, best_t)
+    on_axes = np.isfinite(best_t)
+    assert (best_t[on_axes] < 10).all()
+    want = np.sqrt(np.where(on_axes[..., None], colour, 0.36))
+    got = runner.Oracle(ir, "strict").render(w, h, DEPTH, camera=IDENTITY, camera_scale=1.0)
+    err = np.abs(got[..., :3].astype(np.float64) - want)
+    assert on_axes.sum() > 200 and (safe & on_axes).sum() > 100 and safe.mean() > 0.95, (on_axes.sum(), (safe & on_axes).sum(), safe.mean())
+    assert err[safe].max() < 5e-5, (err[safe].max(), np.argwhere(safe & (err.max(axis=-1) >= 5e-5))[:5])
+    reds, greens = want[safe & on_axes][:, 0] > 0.5, want[safe & on_axes][:, 1] > 0.5
+    assert reds.sum() > 50 and greens.sum() > 50
+    from test_program_on_host import W as HW, H as HH
+    small = runner.Oracle(ir, "strict").render(HW, HH, DEPTH, camera=IDENTITY, camera_scale=1.0)
+    prog, _ = _run_on_host(tmp_path, "analytic5", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
+    assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(small).view(np.uint32))
+
+
 def test_refraction_through_a_pane(tmp_path):
     """Refract material (my_refract, library.glsl:75-92, 357-364): the pane's hit normal faces the ray, so the text takes its
     `!from_outside` branch: ri = 1 / 1.5, dir' = dir * ri + n * (ri * c - sqrt(1 - ri^2 (1 - c^2))); the wall behind is shaded
