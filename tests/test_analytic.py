@@ -21,7 +21,7 @@ W, H, DEPTH = 96, 54, 8
 IDENTITY = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
 
 
-def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid", sky=None):
+def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid", sky=None, near_shift=0.0):
     """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary, region masks).
     s: scale of the gate's far side (gate_b) -- the jump then magnifies by s about the gate's centre, the offset step is taken
     along the UN-normalised direction (length s) and normalize_ray leaves tmul = 1 / s (library.glsl:108-113, 366-371)."""
@@ -109,7 +109,7 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=
     far_direct = gridded(ex + 30 * a - 100, 30 * b, 30 * n, direct)
 
     # near wall: plane z = 6, |x| < 4, -2 < y < 3.5 (asymmetric in y: pins the row order), reached only outside the gate
-    nx, ny = ex + 6 * a, 6 * b
+    nx, ny = ex + 6 * a - near_shift, 6 * b                  # the near wall's own x: it may be moved along x
     on_near = (np.abs(nx) < 4) & (ny > -2) & (ny < 3.5) & ~in_gate
     safe &= ~(~in_gate & (near_boundary(np.abs(nx), 4) | near_boundary(ny, -2) | near_boundary(ny, 3.5)))
     red = np.array([0.8, 0.4, 0.2])
@@ -401,6 +401,39 @@ def test_library_triangle_and_cylinder(tmp_path):
     assert err[safe].max() < 3e-5, (err[safe].max(), np.argwhere(safe & (err.max(axis=-1) >= 3e-5))[:5])
     prog, _ = _run_on_host(tmp_path, "analytic4", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
     assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+
+
+def test_time_drives_a_formula_drives_a_matrix_drives_the_pixels(tmp_path):
+    """The whole uniform chain in one frame: `time` -> Formula uniform -> Parametrized matrix -> `near_mat_inv` in the block ->
+    where the near wall is seen.  Both front-ends evaluate it; the frame follows the closed form with the wall moved."""
+    from oracle import frontend, runner
+    from portal_b200.host import HostScene
+    from test_program_on_host import _run_on_host
+    text = open(SCENE, encoding="utf-8").read()
+    old = '(name: "near", data: Simple(offset: (0.0, 0.0, 6.0), scale: 1.0, rotate: (0.0, 0.0, 0.0), mirror: (false, false, false))),'
+    new = ('(name: "near", data: Parametrized(offset: (x: Uniform(Some(Named("shift"))), y: Value(0.0), z: Value(6.0)), '
+           'rotate: (x: Value(0.0), y: Value(0.0), z: Value(0.0)), mirror: (x: Value(0.0), y: Value(0.0), z: Value(0.0)), scale: Value(1.0))),')
+    assert old in text and "    uniforms: ([]),\n" in text
+    text = text.replace(old, new).replace("    uniforms: ([]),\n", '    uniforms: ([(name: "shift", data: Formula(("time * 2 - 1")))]),\n')
+    path = tmp_path / "analytic_time.ron"
+    path.write_text(text, encoding="utf-8")
+    frames = []
+    for tm in (0.0, 0.75, 2.0):
+        shift = tm * 2 - 1
+        ir = frontend.scene_ir(frontend.load_scene(str(path)), f"analytic_time_{tm}", time=tm)
+        hs = HostScene.from_file(str(path))
+        hs.set_time(tm)
+        table = hs.uniform_table()
+        assert table["shift_u"][1] == shift and table["near_mat"][1][12] == shift              # C++ front-end: same chain
+        assert ir["uniforms"]["near_mat"]["value"][12] == shift
+        want, safe, _, on_near = closed_form(W, H, near_shift=shift)
+        got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0)
+        assert on_near.sum() > 300 and np.abs(got[..., :3].astype(np.float64) - want)[safe].max() < 2e-5, tm
+        frames.append(on_near)
+        if tm == 0.75:
+            prog, _ = _run_on_host(tmp_path, "time", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
+            assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+    assert (frames[0] != frames[2]).sum() > 200                    # the wall really moved across the frame
 
 
 def test_debug_matrix_axes(tmp_path):
