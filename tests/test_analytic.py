@@ -436,6 +436,61 @@ def test_time_drives_a_formula_drives_a_matrix_drives_the_pixels(tmp_path):
     assert (frames[0] != frames[2]).sum() > 200                    # the wall really moved across the frame
 
 
+def test_spherical_portal_with_a_larger_far_side(tmp_path):
+    """Complex/Portal object: a unit-sphere gate at (0,0,5) whose far side is a radius-2 sphere at (50,0,5).  The jump
+    B A^-1 doubles everything about the far centre: the ray goes on from 2 (P - c) + c', its offset step and its remaining
+    distance count as in the scaled flat gate, and from inside the far sphere the snippet reports no second hit."""
+    from oracle import frontend, runner
+    from test_program_on_host import _run_on_host
+    ir = frontend.scene_ir(frontend.load_scene(os.path.join(ROOT, "tests", "fixtures", "analytic6.ron")), "analytic6")
+    assert ir["material_ids"]["teleport_0_1_M"] == 12 and ir["material_ids"]["teleport_0_2_M"] == 13    # scene.rs:813-839
+    px, py = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    a, b = (px + 1 - W / 2) * 2 / H, (py + 1 - H / 2) * 2 / H
+    n = np.sqrt(a * a + b * b + 1)
+    dx, dy, dz = a / n, b / n, 1 / n
+    near_b = lambda x, e, eps=2e-3: np.abs(x - e) < eps           # noqa: E731
+    disc = 25 / (n * n) - 24
+    in_orb = disc > 0
+    safe = ~(np.abs(disc) < 2e-2)
+    t1 = 5 / n - np.sqrt(np.where(in_orb, disc, 0.0))
+    pxw, pyw, pzw = dx * t1, dy * t1, dz * t1
+    step = 2 * 2e-5
+    z0 = 5 + 2 * (pzw - 5) + step * dz
+    t2 = (30 - z0) * n
+    u, v = 2 * pxw + dx * (step + t2), 2 * pyw + dy * (step + t2)
+    all_t = t1 + t2 / 2
+
+    def gridded(uu, vv, tt, where):
+        nonlocal safe
+        green = np.array([0.2, 0.9, 0.5])
+        c = green * 0.75 + green * dz[..., None] * 0.25
+        fu, fv = np.mod(uu * 0.25, 1.0), np.mod(vv * 0.25, 1.0)
+        for f in (fu, fv):
+            safe &= ~(where & (near_b(f, 0.5) | near_b(f, 0.0) | near_b(f, 1.0)))
+        sx, sy = (fu <= 0.5).astype(np.float64), (fv <= 0.5).astype(np.float64)
+        low, high = 0.7 + 0.4 * sx, 1.1 - 0.4 * sx
+        factor = low + (high - low) * sy
+        c = c * 0.7 + c * factor[..., None] * 0.3
+        assert (tt[where] > 10).all()
+        return c * ((1 - (np.minimum(tt, 210.0) - 10) / 200) ** 4)[..., None]
+    through = gridded(u, v, all_t, in_orb)
+    on_near = ~in_orb & (np.abs(8 * a) < 4) & (8 * b > -2) & (8 * b < 3.5)
+    safe &= ~(~in_orb & (near_b(np.abs(8 * a), 4) | near_b(8 * b, -2) | near_b(8 * b, 3.5)))
+    red = np.array([0.8, 0.4, 0.2])
+    near = red * 0.5 + red * dz[..., None] * 0.5
+    assert (8 * n[on_near] < 10).all()
+    direct = ~in_orb & ~on_near & (np.abs(30 * a - 50) < 40) & (np.abs(30 * b) < 40)
+    safe &= ~(~in_orb & ~on_near & (near_b(np.abs(30 * a - 50), 40, 0.05) | near_b(np.abs(30 * b), 40, 0.05)))
+    far_direct = gridded(30 * a - 50, 30 * b, 30 * n, direct)
+    want = np.sqrt(np.where(in_orb[..., None], through, np.where(on_near[..., None], near, np.where(direct[..., None], far_direct, 0.36))))
+    got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0)
+    assert in_orb.sum() > 80 and on_near.sum() > 300 and direct.sum() > 300 and safe.mean() > 0.85, (in_orb.sum(), on_near.sum(), direct.sum(), safe.mean())
+    err = np.abs(got[..., :3].astype(np.float64) - want)
+    assert err[safe].max() < 3e-5, (err[safe].max(), np.argwhere(safe & (err.max(axis=-1) >= 3e-5))[:5])
+    prog, _ = _run_on_host(tmp_path, "analytic6", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
+    assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+
+
 def test_debug_matrix_axes(tmp_path):
     """DebugMatrix: three capsules (radius 0.03, length 1 in the matrix's frame) along the axes, red / green / blue with the
     angle term; here scaled by 5 at z = 6.  Closed form: a capsule is a finite cylinder plus two spheres."""
