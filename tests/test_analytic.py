@@ -491,6 +491,44 @@ def test_spherical_portal_with_a_larger_far_side(tmp_path):
     assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
 
 
+def test_intersection_material_between_objects(tmp_path):
+    """An intersection material (its own hit + its own final colour, no angle term) at z = 4, an object in front of part of
+    it (z = 3: the object wins there) and a wall behind it (z = 7: the disc wins): `nearer` decides per pixel."""
+    from oracle import frontend, runner
+    from test_program_on_host import _run_on_host
+    ir = frontend.scene_ir(frontend.load_scene(os.path.join(ROOT, "tests", "fixtures", "analytic7.ron")), "analytic7")
+    px, py = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    a, b = (px + 1 - W / 2) * 2 / H, (py + 1 - H / 2) * 2 / H
+    n = np.sqrt(a * a + b * b + 1)
+    dz = 1 / n
+    eps = 3e-3
+    on_slab = (np.abs(3 * a - 1.5) < 0.5) & (np.abs(3 * b) < 2)
+    safe = ~((np.abs(np.abs(3 * a - 1.5) - 0.5) < eps) | (np.abs(np.abs(3 * b) - 2) < eps))
+    dist = np.hypot(4 * a - 1, 4 * b - 0.5)
+    on_disc = ~on_slab & (dist < 1.5)
+    for edge in (0.5, 1.0, 1.5):
+        safe &= ~(np.abs(dist - edge) < eps)
+    k = np.floor(dist / 0.5) + 1
+    disc = np.stack([(0.2 * k) ** 2, np.full_like(k, 0.25), (1 - 0.25 * k) ** 2], axis=-1)        # color() squares
+    on_wall = ~on_slab & ~on_disc & (np.abs(7 * a) < 9) & (np.abs(7 * b) < 5)
+    safe &= ~(~on_slab & ~on_disc & ((np.abs(np.abs(7 * a) - 9) < eps) | (np.abs(np.abs(7 * b) - 5) < eps)))
+
+    def simple(col, all_t):
+        col = np.array(col)
+        gray = np.where(all_t > 10, (all_t - 10) / 200, 0.0)                                      # frag.glsl:131-141
+        return (col * 0.5 + col * dz[..., None] * 0.5) * ((1 - gray) ** 4)[..., None]
+    safe &= ~(on_wall & (np.abs(7 * n - 10) < 1e-3))
+    want = np.sqrt(np.where(on_slab[..., None], simple((0.8, 0.4, 0.2), 3 * n), np.where(on_disc[..., None], disc,
+                            np.where(on_wall[..., None], simple((0.3, 0.3, 0.8), 7 * n), 0.36))))
+    got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0)
+    assert on_slab.sum() > 100 and on_disc.sum() > 150 and on_wall.sum() > 1000 and (~on_slab & ~on_disc & ~on_wall).sum() > 200
+    assert len(np.unique(k[on_disc & safe])) == 3 and safe.mean() > 0.9
+    err = np.abs(got[..., :3].astype(np.float64) - want)
+    assert err[safe].max() < 2e-5, (err[safe].max(), np.argwhere(safe & (err.max(axis=-1) >= 2e-5))[:5])
+    prog, _ = _run_on_host(tmp_path, "analytic7", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
+    assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+
+
 def test_debug_matrix_axes(tmp_path):
     """DebugMatrix: three capsules (radius 0.03, length 1 in the matrix's frame) along the axes, red / green / blue with the
     angle term; here scaled by 5 at z = 6.  Closed form: a capsule is a finite cylinder plus two spheres."""

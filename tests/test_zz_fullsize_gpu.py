@@ -55,13 +55,13 @@ def test_host_render_target_strips_reassemble_the_frame(torch_cuda):
 
 
 def test_kernel_on_the_analytic_scenes_equals_oracle_and_closed_form(torch_cuda):
-    """tests/fixtures/analytic{,2,3,4,5,6}.ron on the GPU with the identity camera: bit-identical to the oracle's frame,
+    """tests/fixtures/analytic{,2,...,7}.ron on the GPU with the identity camera: bit-identical to the oracle's frame,
     and within rounding of the closed forms written down from the reference's shader text (tests/test_analytic.py)."""
     from conftest import ROOT
     from oracle import frontend, runner
     from portal_b200.renderer import SceneRenderer
     from test_analytic import DEPTH, H, IDENTITY, W, closed_form, closed_form2
-    for name, form in (("analytic", closed_form), ("analytic2", closed_form2), ("analytic3", None), ("analytic4", None), ("analytic5", None), ("analytic6", None)):
+    for name, form in (("analytic", closed_form), ("analytic2", closed_form2), ("analytic3", None), ("analytic4", None), ("analytic5", None), ("analytic6", None), ("analytic7", None)):
         ir = frontend.scene_ir(frontend.load_scene(os.path.join(ROOT, "tests", "fixtures", name + ".ron")), name)
         ref = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0)
         r = SceneRenderer(ir, device=0)
