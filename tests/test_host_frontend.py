@@ -422,6 +422,7 @@ def test_matrix_kinds_known_answers(tmp_path):
     extra = [
         ("k_srt", simple("1.0, 2.0, 3.0", "2.0", f"0.0, 0.0, {hp}")),
         ("k_xz", simple("0.0, 0.0, 0.0", "1.0", f"{hp}, 0.0, {hp}")),
+        ("k_x", simple("0.0, 0.0, 0.0", "1.0", f"{hp}, 0.0, 0.0")), ("k_y", simple("0.0, 0.0, 0.0", "1.0", f"0.0, {hp}, 0.0")),
         ("k_t1", simple("1.0, 0.0, 0.0")), ("k_s2", simple("0.0, 0.0, 0.0", "2.0")),
         ("k_mul", 'Mul(to: Some(Named("k_t1")), what: Some(Named("k_s2")))'),
         ("k_first", simple("0.0, 0.0, 1.0")), ("k_second", simple("0.0, 5.0, 0.0", "1.0", f"0.0, 0.0, {hp}")), ("k_what", simple("1.0, 0.0, 1.0")),
@@ -443,6 +444,8 @@ def test_matrix_kinds_known_answers(tmp_path):
         near(at("k_srt", (1, 0, 0)), (1, 4, 3))            # scale 2, quarter turn about z: (1,0,0) -> (0,2,0), + offset
         near(at("k_srt", (0, 0, 1)), (1, 2, 5))
         near(at("k_xz", (1, 0, 0)), (0, 0, 1))             # Rx*Ry*Rz: z-turn first (x -> y), then x-turn (y -> z)
+        near(at("k_x", (0, 1, 0)), (0, 0, 1))              # right-handed quarter turns: about x, y -> z
+        near(at("k_y", (0, 0, 1)), (1, 0, 0))              # about y, z -> x
         near(at("k_mul", (0, 0, 0)), (2, 0, 0))            # what * to = S(2) T(1,0,0)
         near(at("k_tp", (0, 0, 0)), (0, 6, 0))             # (1,0,1) -> first^-1 -> (1,0,0) -> quarter turn (0,1,0) + (0,5,0)
         near(at("k_inv", (1, 4, 3)), (1, 0, 0))
