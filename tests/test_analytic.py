@@ -21,7 +21,7 @@ W, H, DEPTH = 96, 54, 8
 IDENTITY = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
 
 
-def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid", sky=None, near_shift=0.0):
+def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid", sky=None, near_shift=0.0, far_z=30.0, see_far_directly=True):
     """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary, region masks).
     s: scale of the gate's far side (gate_b) -- the jump then magnifies by s about the gate's centre, the offset step is taken
     along the UN-normalised direction (length s) and normalize_ray leaves tmul = 1 / s (library.glsl:108-113, 366-371)."""
@@ -68,7 +68,7 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=
     safe &= ~near_boundary(gx * gx + gy * gy, 1)
     t1 = 3 * n
     step = s * 2e-5                                          # r.o += r.d * offset with |r.d| = s, before the normalisation
-    t2 = (30 - (3 + step * dz)) * n                          # from the stepped origin to z = 30, along the unit direction
+    t2 = (far_z - (3 + step * dz)) * n                       # from the stepped origin to the far wall, along the unit direction
     u, v = s * gx + a * dz * (step + t2), s * gy + b * dz * (step + t2)   # far wall's local (x, y): the jump moved x by exactly +100
     all_t = t1 + t2 / s                                      # all_t += t * r.tmul (frag.glsl:119, 125)
     def gridded(u, v, all_t, where):
@@ -103,7 +103,7 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=
         return c * ((1 - gray) ** 4)[..., None]
     far = gridded(u, v, all_t, in_gate)
     # wide-angle projections also see the far wall directly (x in 60..140 at z = 30), and could graze the gate's far disc
-    direct = ~in_gate & (np.abs(ex + 30 * a - 100) < 40) & (np.abs(30 * b) < 40)
+    direct = ~in_gate & (np.abs(ex + 30 * a - 100) < 40) & (np.abs(30 * b) < 40) & see_far_directly
     safe &= ~(~in_gate & (near_boundary(np.abs(ex + 30 * a - 100), 40, 0.05) | near_boundary(np.abs(30 * b), 40, 0.05)))
     safe &= ~((np.abs(ex + 3 * a - 100) < 1.5) & (np.abs(3 * b) < 1.5))
     far_direct = gridded(ex + 30 * a - 100, 30 * b, 30 * n, direct)
@@ -400,6 +400,35 @@ def test_library_triangle_and_cylinder(tmp_path):
     err = np.abs(got[..., :3].astype(np.float64) - want)
     assert err[safe].max() < 3e-5, (err[safe].max(), np.argwhere(safe & (err.max(axis=-1) >= 3e-5))[:5])
     prog, _ = _run_on_host(tmp_path, "analytic4", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
+    assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+
+
+def test_gate_that_turns_the_ray(tmp_path):
+    """The gate's far side turned a quarter about y, and the far wall turned the same way 30 further along the new heading:
+    B A^-1 now rotates positions and directions (x <- z, z <- -x), the wall's own frame undoes it, and the picture through
+    the gate is the straight one with the wall at distance 33 -- rotation handedness and order, in pixels."""
+    from oracle import frontend, runner
+    from test_program_on_host import _run_on_host
+    hp = "1.5707963267948966"
+    text = open(SCENE, encoding="utf-8").read()
+    for old, new in (('(name: "gate_b", data: Simple(offset: (100.0, 0.0, 3.0), scale: 1.0, rotate: (0.0, 0.0, 0.0),',
+                      f'(name: "gate_b", data: Simple(offset: (100.0, 0.0, 3.0), scale: 1.0, rotate: (0.0, {hp}, 0.0),'),
+                     ('(name: "far", data: Simple(offset: (100.0, 0.0, 30.0), scale: 1.0, rotate: (0.0, 0.0, 0.0),',
+                      f'(name: "far", data: Simple(offset: (130.0, 0.0, 3.0), scale: 1.0, rotate: (0.0, {hp}, 0.0),')):
+        assert old in text
+        text = text.replace(old, new)
+    path = tmp_path / "analytic_turn.ron"
+    path.write_text(text, encoding="utf-8")
+    ir = frontend.scene_ir(frontend.load_scene(str(path)), "analytic_turn")
+    tp = np.asarray(ir["uniforms"]["gate_a_to_gate_b_mat_teleport"]["value"]).reshape(4, 4).T
+    np.testing.assert_allclose(tp @ [0.5, 0.25, 3.0, 1.0], [100.0, 0.25, 2.5, 1.0], atol=1e-12)      # (x, y, 0) of the gate -> (0, y, -x)
+    np.testing.assert_allclose(tp @ [0.0, 0.0, 1.0, 0.0], [1.0, 0.0, 0.0, 0.0], atol=1e-12)          # heading +z -> +x
+    want, safe, in_gate, _ = closed_form(W, H, far_z=33.0, see_far_directly=False)
+    got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0)
+    err = np.abs(got[..., :3].astype(np.float64) - want)
+    assert err[safe].max() < 3e-5, (err[safe].max(), np.argwhere(safe & (err.max(axis=-1) >= 3e-5))[:5])
+    assert np.abs(want - closed_form(W, H)[0])[in_gate].max() > 0.01
+    prog, _ = _run_on_host(tmp_path, "turn", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
     assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
 
 
