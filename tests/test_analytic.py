@@ -21,7 +21,7 @@ W, H, DEPTH = 96, 54, 8
 IDENTITY = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
 
 
-def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid", sky=None, near_shift=0.0, far_z=30.0, see_far_directly=True):
+def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid", sky=None, near_shift=0.0, far_z=30.0, see_far_directly=True, cs=1.0):
     """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary, region masks).
     s: scale of the gate's far side (gate_b) -- the jump then magnifies by s about the gate's centre, the offset step is taken
     along the UN-normalised direction (length s) and normalize_ray leaves tmul = 1 / s (library.glsl:108-113, 366-371)."""
@@ -98,8 +98,9 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=
             safe &= ~(where & (near_boundary(dist, 0.985, 5e-3) | near_boundary(dist, 0.94, 5e-3) |
                                ((dist >= 0.94) & (dist <= 0.985) & near_boundary(qx - qy, 0.0, 5e-3))))
         c = c * (1 - 0.3) + (c * factor[..., None]) * 0.3
-        gray = (np.minimum(all_t, 210.0) - 10.0) / 200.0         # frag.glsl:133-135, camera_scale = 1; all_t > 10 on these paths
-        assert (all_t[where] > 10).all()
+        # frag.glsl:131-141 with camera_scale cs: darker only beyond _t_start * cs, clamped at _t_end * cs
+        gray = np.where(all_t > 10.0 * cs, (np.minimum(all_t, 210.0 * cs) - 10.0 * cs) / 200.0 / cs, 0.0)
+        safe &= ~(where & (np.abs(all_t - 10.0 * cs) < 1e-3))
         return c * ((1 - gray) ** 4)[..., None]
     far = gridded(u, v, all_t, in_gate)
     # wide-angle projections also see the far wall directly (x in 60..140 at z = 30), and could graze the gate's far disc
@@ -400,6 +401,25 @@ def test_library_triangle_and_cylinder(tmp_path):
     err = np.abs(got[..., :3].astype(np.float64) - want)
     assert err[safe].max() < 3e-5, (err[safe].max(), np.argwhere(safe & (err.max(axis=-1) >= 3e-5))[:5])
     prog, _ = _run_on_host(tmp_path, "analytic4", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
+    assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+
+
+def test_camera_scale_moves_the_darkening(tmp_path):
+    """A camera matrix with columns of length 2.5 sends the same rays but `_camera_scale` = 2.5 (main.rs:1325-1340): darkening
+    starts at 25 instead of 10 and its ramp is 2.5 times as long (frag.glsl:130-141) -- the far wall at 30 is barely darkened."""
+    from oracle import runner
+    from test_program_on_host import _run_on_host
+    ir = scene_ir()
+    cam = [2.5 if (k % 5 == 0 and k < 15) else (1.0 if k == 15 else 0.0) for k in range(16)]
+    want, safe, in_gate, _ = closed_form(W, H, cs=2.5)
+    got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=cam, camera_scale=2.5)
+    assert np.abs(got[..., :3].astype(np.float64) - want)[safe].max() < 2e-5
+    centre = (1 - (30 - 2e-5 - 25) / 200 / 2.5) ** 4
+    assert abs(want[H // 2 - 1, W // 2 - 1, 1] ** 2 / (0.9 * (0.7 + 0.3 * 0.7)) - centre) < 1e-9 and centre > 0.96
+    assert np.abs(want - closed_form(W, H)[0])[in_gate].min() > 0.01
+    from portal_b200.renderer import camera_scale
+    assert camera_scale(cam) == 2.5
+    prog, _ = _run_on_host(tmp_path, "cs", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": cam})
     assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
 
 
