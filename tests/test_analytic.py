@@ -115,7 +115,9 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=
     safe &= ~(~in_gate & (near_boundary(np.abs(nx), 4) | near_boundary(ny, -2) | near_boundary(ny, 3.5)))
     red = np.array([0.8, 0.4, 0.2])
     near = red * (1 - 0.5) + red * dz[..., None] * 0.5
-    assert (6 * n[on_near] < 10).all()                       # no darkening on this path
+    near_t = 6 * n                                           # darkened only if the camera scale pulls _t_start below it
+    near = near * ((1 - np.where(near_t > 10.0 * cs, (np.minimum(near_t, 210.0 * cs) - 10.0 * cs) / 200.0 / cs, 0.0)) ** 4)[..., None]
+    safe &= ~(on_near & (np.abs(near_t - 10.0 * cs) < 1e-3))
     miss = np.full(3, 0.6 * 0.6)                             # current_color (1) * color(0.6, 0.6, 0.6), scene.rs:1060
     if sky is not None:
         # scene.rs:1052-1058: with a skybox the miss colour is the texture looked up by the direction of the CAMERA ray
@@ -419,6 +421,12 @@ def test_camera_scale_moves_the_darkening(tmp_path):
     assert np.abs(want - closed_form(W, H)[0])[in_gate].min() > 0.01
     from portal_b200.renderer import camera_scale
     assert camera_scale(cam) == 2.5
+    # a small camera (scale 0.1): _t_end * 0.1 = 21 < 30 -> the far wall is clamped to fully dark, the near wall (6..) is on the ramp
+    tiny = [0.1 if (k % 5 == 0 and k < 15) else (1.0 if k == 15 else 0.0) for k in range(16)]
+    want2, safe2, in_gate2, on_near2 = closed_form(W, H, cs=0.1)
+    got2 = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=tiny, camera_scale=0.1)
+    assert np.all(want2[in_gate2] == 0.0) and np.abs(got2[..., :3].astype(np.float64) - want2)[safe2].max() < 2e-5
+    assert 0.05 < want2[on_near2 & safe2][:, 0].min() < want2[on_near2 & safe2][:, 0].max() < 0.9
     prog, _ = _run_on_host(tmp_path, "cs", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": cam})
     assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
 
