@@ -21,7 +21,7 @@ W, H, DEPTH = 96, 54, 8
 IDENTITY = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
 
 
-def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid", sky=None, near_shift=0.0, far_z=30.0, see_far_directly=True, cs=1.0):
+def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid", sky=None, near_shift=0.0, far_z=30.0, see_far_directly=True, cs=1.0, near_is_gridded=False):
     """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary, region masks).
     s: scale of the gate's far side (gate_b) -- the jump then magnifies by s about the gate's centre, the offset step is taken
     along the UN-normalised direction (length s) and normalize_ray leaves tmul = 1 / s (library.glsl:108-113, 366-371)."""
@@ -118,6 +118,8 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=
     near_t = 6 * n                                           # darkened only if the camera scale pulls _t_start below it
     near = near * ((1 - np.where(near_t > 10.0 * cs, (np.minimum(near_t, 210.0 * cs) - 10.0 * cs) / 200.0 / cs, 0.0)) ** 4)[..., None]
     safe &= ~(on_near & (np.abs(near_t - 10.0 * cs) < 1e-3))
+    if near_is_gridded:
+        near = gridded(nx, ny, near_t, on_near)
     miss = np.full(3, 0.6 * 0.6)                             # current_color (1) * color(0.6, 0.6, 0.6), scene.rs:1060
     if sky is not None:
         # scene.rs:1052-1058: with a skybox the miss colour is the texture looked up by the direction of the CAMERA ray
@@ -404,6 +406,31 @@ def test_library_triangle_and_cylinder(tmp_path):
     assert err[safe].max() < 3e-5, (err[safe].max(), np.argwhere(safe & (err.max(axis=-1) >= 3e-5))[:5])
     prog, _ = _run_on_host(tmp_path, "analytic4", None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
     assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+
+
+def test_which_side_of_a_plane_is_its_back(tmp_path):
+    """`back` as is_inside_k receives it (scene.rs:912-927): is_collinear(hit.n, -get_normal(M)) -- true when the ray travels
+    along the plane's +z.  A wall that shows one material from the back and another from the front; seen along +z it shows
+    the back one, and with its matrix mirrored in z (get_normal flips) the front one."""
+    from oracle import frontend, runner
+    from test_program_on_host import _run_on_host
+    text = open(SCENE, encoding="utf-8").read()
+    old = "if (abs(x) < 4. && y > -2. && y < 3.5) return plain_M;"
+    assert old in text
+    text = text.replace(old, "if (abs(x) < 4. && y > -2. && y < 3.5) { if (back) return plain_M; return gridded_M; }")
+    mirrored = text.replace('(name: "near", data: Simple(offset: (0.0, 0.0, 6.0), scale: 1.0, rotate: (0.0, 0.0, 0.0), mirror: (false, false, false))),',
+                            '(name: "near", data: Simple(offset: (0.0, 0.0, 6.0), scale: 1.0, rotate: (0.0, 0.0, 0.0), mirror: (false, false, true))),')
+    assert mirrored != text
+    for name, scene_text, gridded_side in (("two_sided", text, False), ("two_sided_mirrored", mirrored, True)):
+        path = tmp_path / f"{name}.ron"
+        path.write_text(scene_text, encoding="utf-8")
+        ir = frontend.scene_ir(frontend.load_scene(str(path)), name)
+        want, safe, _, on_near = closed_form(W, H, near_is_gridded=gridded_side)
+        got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0)
+        assert np.abs(got[..., :3].astype(np.float64) - want)[safe].max() < 2e-5, name
+        prog, _ = _run_on_host(tmp_path, name, None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
+        assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32)), name
+    assert np.abs(closed_form(W, H, near_is_gridded=True)[0] - closed_form(W, H)[0])[on_near].min() > 0.02
 
 
 def test_camera_scale_moves_the_darkening(tmp_path):
