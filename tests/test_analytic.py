@@ -433,6 +433,50 @@ def test_which_side_of_a_plane_is_its_back(tmp_path):
     assert np.abs(closed_form(W, H, near_is_gridded=True)[0] - closed_form(W, H)[0])[on_near].min() > 0.02
 
 
+def test_back_flag_on_both_sides_of_a_portal(tmp_path):
+    """Flat/Portal: side A is tested with normal = -get_normal(A), side B with +get_normal(B) (scene.rs:928-948), so along +z
+    `back` is true at A and false at B.  A gate that teleports only when `back` is false: from the origin (facing A) it is a
+    plain disc; from x = 100 (facing B) it jumps the ray back by B -> A and shows the near wall behind A."""
+    from oracle import frontend, runner
+    from test_program_on_host import _run_on_host
+    text = open(SCENE, encoding="utf-8").read()
+    old = "if (x*x + y*y < 1.) return TELEPORT;"
+    assert old in text
+    path = tmp_path / "analytic_back.ron"
+    path.write_text(text.replace(old, "if (x*x + y*y < 1.) { if (back) return plain_M; return TELEPORT; }"), encoding="utf-8")
+    ir = frontend.scene_ir(frontend.load_scene(str(path)), "analytic_back")
+    orc = runner.Oracle(ir, "strict")
+    px, py = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    a, b = (px + 1 - W / 2) * 2 / H, (py + 1 - H / 2) * 2 / H
+    n = np.sqrt(a * a + b * b + 1)
+    dz = 1 / n
+    red = np.array([0.8, 0.4, 0.2])
+    plain = red * 0.5 + red * dz[..., None] * 0.5
+    disc = 9 * a * a + 9 * b * b < 1
+    edge = np.abs(9 * a * a + 9 * b * b - 1) < 2e-3
+    # facing A: the disc is the plain material at z = 3 (same shade as the near wall: no distance term below 10)
+    base, safe, in_gate, _ = closed_form(W, H)
+    from_a = orc.render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0)
+    want_a = np.where(disc[..., None], np.sqrt(plain), base)
+    assert np.abs(from_a[..., :3].astype(np.float64) - want_a)[safe].max() < 2e-5
+    # facing B from (100, 0, 0): through the disc the ray comes out of A and meets the near wall at z = 6, |x| < 4, -2 < y < 3.5;
+    # around the disc it sees the far wall (centre x = 100) directly
+    cam = list(IDENTITY)
+    cam[12] = 100.0
+    from_b = orc.render(W, H, DEPTH, camera=cam, camera_scale=1.0)
+    behind_a = disc & (np.abs(6 * a) < 4) & (6 * b > -2) & (6 * b < 3.5)
+    assert behind_a.sum() == disc.sum()                          # the whole disc looks onto the near wall
+    sel = disc & ~edge
+    assert sel.sum() > 150 and np.abs(from_b[sel][:, :3].astype(np.float64) - np.sqrt(plain[sel])).max() < 2e-5
+    around = ~disc & ~edge & (np.abs(30 * a) < 39) & (np.abs(30 * b) < 39)
+    green = from_b[around][:, 1] > from_b[around][:, 0]
+    assert around.sum() > 1000 and green.all()                   # the far wall's green, not the near wall's red
+    for name, c in (("from_a", IDENTITY), ("from_b", cam)):
+        prog, _ = _run_on_host(tmp_path, name, None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": c})
+        ref = from_a if name == "from_a" else from_b
+        assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(ref).view(np.uint32)), name
+
+
 def test_camera_scale_moves_the_darkening(tmp_path):
     """A camera matrix with columns of length 2.5 sends the same rays but `_camera_scale` = 2.5 (main.rs:1325-1340): darkening
     starts at 25 instead of 10 and its ramp is 2.5 times as long (frag.glsl:130-141) -- the far wall at 30 is barely darkened."""
