@@ -1,6 +1,7 @@
 """Last file of the suite on purpose.  Full BASELINE.json frame sizes on the GPU against the committed sha256 of the
 strict oracle's frame (tests/golden/fullsize_sha256.json, written by tools/fullsize_host_check.py, which also ran the
-generated program on the host at that size): the whole frame, every bit."""
+generated program on the host at that size): the whole frame, every bit.  Also here: the strips of ph_render_target, and the
+analytic scenes of tests/test_analytic.py on the GPU (oracle bit for bit, closed forms to rounding)."""
 import hashlib
 import json
 import os
