@@ -21,7 +21,7 @@ W, H, DEPTH = 96, 54, 8
 IDENTITY = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
 
 
-def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid", sky=None, near_shift=0.0, far_z=30.0, see_far_directly=True, cs=1.0, near_is_gridded=False):
+def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid", sky=None, near_shift=0.0, far_z=30.0, see_far_directly=True, cs=1.0, near_is_gridded=False, no_near=False):
     """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary, region masks).
     s: scale of the gate's far side (gate_b) -- the jump then magnifies by s about the gate's centre, the offset step is taken
     along the UN-normalised direction (length s) and normalize_ray leaves tmul = 1 / s (library.glsl:108-113, 366-371)."""
@@ -111,7 +111,7 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=
 
     # near wall: plane z = 6, |x| < 4, -2 < y < 3.5 (asymmetric in y: pins the row order), reached only outside the gate
     nx, ny = ex + 6 * a - near_shift, 6 * b                  # the near wall's own x: it may be moved along x
-    on_near = (np.abs(nx) < 4) & (ny > -2) & (ny < 3.5) & ~in_gate
+    on_near = (np.abs(nx) < 4) & (ny > -2) & (ny < 3.5) & ~in_gate & (not no_near)
     safe &= ~(~in_gate & (near_boundary(np.abs(nx), 4) | near_boundary(ny, -2) | near_boundary(ny, 3.5)))
     red = np.array([0.8, 0.4, 0.2])
     near = red * (1 - 0.5) + red * dz[..., None] * 0.5
@@ -431,6 +431,22 @@ def test_which_side_of_a_plane_is_its_back(tmp_path):
         prog, _ = _run_on_host(tmp_path, name, None, ir=ir, tex={}, depth=DEPTH, attrs={"camera_matrix": IDENTITY})
         assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32)), name
     assert np.abs(closed_form(W, H, near_is_gridded=True)[0] - closed_form(W, H)[0])[on_near].min() > 0.02
+
+
+def test_teleport_codes_from_a_plain_object_are_ignored(tmp_path):
+    """process_plane_intersection (library.glsl:560-572): TELEPORT / TELEPORT_SUBSPACE returned by a non-portal object is
+    "wrong code, do nothing" -- the wall is simply not there."""
+    from oracle import frontend, runner
+    text = open(SCENE, encoding="utf-8").read()
+    old = "if (abs(x) < 4. && y > -2. && y < 3.5) return plain_M;"
+    want, safe, _, on_near = closed_form(W, H, no_near=True)
+    assert on_near.sum() == 0 and np.abs(want - closed_form(W, H)[0]).max() > 0.1
+    for code in ("TELEPORT", "TELEPORT_SUBSPACE"):
+        path = tmp_path / f"ignored_{code}.ron"
+        path.write_text(text.replace(old, old.replace("plain_M", code)), encoding="utf-8")
+        ir = frontend.scene_ir(frontend.load_scene(str(path)), f"ignored_{code}")
+        got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0)
+        assert np.abs(got[..., :3].astype(np.float64) - want)[safe].max() < 2e-5, code
 
 
 def test_back_flag_on_both_sides_of_a_portal(tmp_path):
