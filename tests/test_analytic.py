@@ -1,14 +1,20 @@
 """Analytic pixel checks of the oracle.
 
 The reference has no pixel pins, so the oracle is tied to the reference's shader TEXT here by a second, independent route:
-for tests/fixtures/analytic.ron every pixel of a frame has a closed form that can be written down from frag.glsl /
-library.glsl by hand -- no ray loop, no generated code, float64 numpy -- and the oracle's frame must agree with it to
-rounding (2e-5; the oracle computes in float32) everywhere except within a hair of a decision boundary.  Covered: the
-pixel -> ray map incl. the R2(0) sample offset and the row order (scene.rs:1688-1693, frag.glsl:449-455, 506-526),
-plane_intersect (library.glsl:149-162), the portal jump o' = B A^-1 o with the offset after it (scene.rs:624-627,
-library.glsl:366-379), the distance carried across the jump and the darkening (frag.glsl:119-141), material_simple2's
-angle term and color_grid (library.glsl:177-188, 318-335), the miss colour (scene.rs:1060) and the final sqrt
-(frag.glsl:550).  The GPU tests then hold the kernel to the oracle bit for bit on the same scene."""
+for the hand-written scenes tests/fixtures/analytic{,2,...,7}.ron every pixel of a frame has a closed form that can be
+written down from frag.glsl / library.glsl / the generator (scene.rs:720-1063) by hand -- no ray loop, no generated code,
+float64 numpy -- and the oracle's frame must agree with it to rounding (2e-5; the oracle computes in float32) everywhere
+except within a hair of a decision boundary.  The generated sm_100a program, run on the host, must equal the oracle bit
+for bit on the same inputs, and tests/test_zz_fullsize_gpu.py holds the GPU to both.  Covered:
+
+  * pixel -> ray: R2 sample offsets, row order, AA mean of linear colours + sqrt, 60 degree / Panini / 360 / VR180 maps,
+    side-by-side stereo, camera scale (scene.rs:1688-1693, frag.glsl:408-526, 550);
+  * objects: Flat/Simple, Flat/Portal (jump, offset step, tmul under scaling, rotation, both `back` polarities and the way
+    back), Complex/Simple (sphere under a scaling matrix; library triangle() / cylinder()), Complex/Portal (spherical gate),
+    DebugMatrix (axis capsules), an intersection material competing with objects, ignored teleport codes, subspaces;
+  * shading: material_simple2's angle term and the three grid patterns, Reflect, Refract, miss colour and skybox lookup,
+    darkening (start, ramp, clamp, camera scale), depth-map ramp;
+  * uniforms: time -> formula -> matrix -> block -> pixels; the camera-teleportation probe's known answers."""
 import os
 
 import numpy as np
