@@ -471,7 +471,7 @@ extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe
                 worst = pe::max(worst, s.bounce);
                 a++;
                 if (a < _aa_count + _aa_start) {
-                    primary_ray(px, grow, a, s);   // next AA sample of the same pixel
+                    skip = !primary_ray(px, grow, a, s);   // next AA sample of the same pixel (may fall outside a 360 / VR180 image)
                 } else {
                     store_pixel(L, px, lrow, grow, sum, worst);
                     alive = false;

@@ -167,6 +167,33 @@ def test_projection_variants_and_side_by_side(torch_cuda):
     assert np.array_equal(_bits(rp.render_host(w, 100)), _bits(r2.render_host(w, 100)))   # black bars: skipped samples
 
 
+def test_persistent_aa_with_image_area_projections(torch_cuda):
+    """Border pixels of a 360 / VR180 image have AA samples on both sides of the image area (frag.glsl:413-448 returns
+    black for the ones outside): the persistent scheduler must treat EVERY sample like the one-thread-per-pixel kernel
+    does -- also under side-by-side stereo, where each half has its own image area."""
+    from portal_b200.renderer import camera_scale
+    scene = "monoportal"
+    orc = _oracle(scene)
+    w, h = 321, 200          # the 360 image is letter-boxed at this aspect: its borders cross pixel footprints
+    for kw in ({"use_360_camera": 1}, {"use_180_camera": 1}, {"use_360_camera": 1, "draw_side_by_side": 1},
+               {"use_180_camera": 1, "draw_side_by_side": 1}):
+        frames = []
+        for persistent in (False, True):
+            r = _renderer(scene, persistent=persistent)
+            r.aa_count, r.aa_start = 4, 1
+            for k, v in kw.items():
+                setattr(r, k, bool(v))
+            frames.append(r.render_host(w, h))
+            okw = dict(kw)
+            if kw.get("draw_side_by_side"):
+                left, right = r.eye_matrices()
+                okw.update(camera_left_eye=left, camera_right_eye=right, left_eye_scale=camera_scale(left),
+                           right_eye_scale=camera_scale(right))
+        ref = orc.render(w, h, DEPTH[scene], aa_count=4, aa_start=1, **okw)
+        assert np.array_equal(_bits(frames[0]), _bits(ref)), kw
+        assert np.array_equal(_bits(frames[1]), _bits(ref)), ("persistent", kw)
+
+
 def test_external_ray_probe(torch_cuda):
     """the camera-teleportation probe against the oracle's restatement of frag.glsl:209-257."""
     for scene, segs in (("portal_in_portal", [([0, 0, -0.5], [0, 0, -1.5]), ([0, 0, 0.5], [0, 0, 0.2]), ([0.1, 0.05, -0.9], [0.12, 0.02, -1.3]),
