@@ -136,6 +136,10 @@ PE_API int ph_player_set_run_animations(ph_player* p, int on);
  * a portal that lies between it and the camera -- and the render calls send them with `_draw_side_by_side`.
  * The caller doubles the frame width, as `render --stereo-image` does (src/main.rs:2809-2816). */
 PE_API int ph_player_set_stereo(ph_player* p, int draw_side_by_side, double eye_distance, int swap_eyes);
+/* Anaglyph stereo (SceneRenderer::draw_anaglyph / anaglyph_mode "Colorful anaglyph" / anaglyph_p 0.29 / anaglyph_q 0.06,
+ * main.rs:1030-1033, 1308-1315, 1549-1580; shader frag.glsl:343-406, 467-473): every sample is traced through both eye
+ * cameras (the same ones side-by-side uses, teleported through portals alike: main.rs:1122) and combined red / cyan. */
+PE_API int ph_player_set_anaglyph(ph_player* p, int draw_anaglyph, int colorful, double anaglyph_p, double anaglyph_q);
 PE_API int ph_player_eyes(ph_player* p, double left16[16], double right16[16], int32_t* left_in_subspace,
                           int32_t* right_in_subspace);
 /* Real animations in file order: count, then name and duration of entry k. */

@@ -380,6 +380,7 @@ class Player:
         self.n_probes = 0
         # stereo (main.rs:1027-1030): eye cameras are placed by teleport_eye_matrices when a stereo mode is on
         self.draw_side_by_side = False
+        self.draw_anaglyph = False
         self.eye_distance = 0.07
         self.swap_eyes = False
         self.left_eye_matrix, self.right_eye_matrix = F.mat_identity(), F.mat_identity()
@@ -451,7 +452,7 @@ class Player:
         """main.rs:1121-1172: each eye = the camera shifted along its x axis; if a portal lies between the camera and
         the eye, the eye's matrix is carried through it like the camera's would be."""
         cam = self.cam
-        if not (self.draw_side_by_side and cam.allow_teleport):
+        if not ((self.draw_anaglyph or self.draw_side_by_side) and cam.allow_teleport):   # main.rs:1122
             return
         ed = -self.eye_distance if self.swap_eyes else self.eye_distance
 

@@ -177,6 +177,7 @@ RENDERER_FIELDS = [
     ("int", "_ray_tracing_depth"), ("int", "_aa_count"), ("int", "_aa_start"), ("int", "_camera_in_subspace"),
     ("int", "_darken_by_distance"), ("int", "_angle_color_disable"), ("int", "_grid_disable"),
     ("int", "_black_border_disable"), ("int", "_draw_depth_map"),
+    ("int", "_draw_anaglyph"), ("int", "_anaglyph_mode"), ("real", "_anaglyph_p"), ("real", "_anaglyph_q"),
 ]
 
 
@@ -418,6 +419,8 @@ struct PeOracleFrame {
     int ray_tracing_depth, aa_count, aa_start, camera_in_subspace, darken_by_distance, angle_color_disable,
         grid_disable, black_border_disable, draw_depth_map;
     int width, height;
+    int draw_anaglyph, anaglyph_mode;
+    float anaglyph_p, anaglyph_q;
 };
 extern "C" {
 int pe_oracle_counts(int* nm, int* nf, int* ni, int* nt) { *nm = @NM@; *nf = @NF@; *ni = @NI@; *nt = @NT@; return 0; }
@@ -465,6 +468,8 @@ static void pe_oracle_load_frame(const PeOracleFrame* fr) {
     _camera_in_subspace = fr->camera_in_subspace; _darken_by_distance = fr->darken_by_distance;
     _angle_color_disable = fr->angle_color_disable; _grid_disable = fr->grid_disable;
     _black_border_disable = fr->black_border_disable; _draw_depth_map = fr->draw_depth_map;
+    _draw_anaglyph = fr->draw_anaglyph; _anaglyph_mode = fr->anaglyph_mode;
+    _anaglyph_p = real(fr->anaglyph_p); _anaglyph_q = real(fr->anaglyph_q);
 }
 // main()'s probe branch, frag.glsl:527-529: Ray(a, b - a, 1, _camera_in_subspace == 1); out = pos xyz + 3 flags
 void pe_oracle_probe(const PeOracleFrame* fr, const float* a, const float* b, float* out_pos, int* out_flags) {

@@ -247,9 +247,47 @@ static inline vec3 get_color2(vec2 image_position, const mat4& camera_matrix, bo
     return trace.color;
 }
 
-// frag.glsl:466-503.  The native build sets disable_anaglyph = true (main.rs:938), which drops the
-// !ANAGLYPH! lines (scene.rs:1079): what remains is the mono path and side-by-side stereo (:479-499).
+// frag.glsl:343-406
+static inline vec3 anaglyphCombineLinear(vec3 leftLin, vec3 rightLin, int mode) {
+    leftLin = clamp(leftLin, PE_L(0.0), PE_L(1.0));
+    rightLin = clamp(rightLin, PE_L(0.0), PE_L(1.0));
+    if (mode == 0) {
+        const vec3 LUMA = vec3(PE_L(0.299), PE_L(0.587), PE_L(0.114));
+        real P = _anaglyph_p;
+        real Q = _anaglyph_q;
+        real l = dot(leftLin, LUMA);
+        real r = dot(rightLin, LUMA);
+        real denom = max(PE_L(1e-6), PE_L(1.0) - P * Q);
+        real Rout = (l - P * r) / denom;
+        real Cout = (r - Q * l) / denom;
+        return clamp(vec3(Rout, Cout, Cout), PE_L(0.0), PE_L(1.0));
+    } else {
+        real P = _anaglyph_p;
+        real Q = _anaglyph_q;
+        const vec3 LUMA = vec3(PE_L(0.299), PE_L(0.587), PE_L(0.114));
+        real l = dot(leftLin, LUMA);
+        real r = dot(rightLin, LUMA);
+        real denom = max(PE_L(1e-6), PE_L(1.0) - P * Q);
+        real Rout = (l - P * r) / denom;
+        real Cout = (r - Q * l) / denom;
+        real sumGB = rightLin.g + rightLin.b;
+        real k = (sumGB > PE_L(1e-6)) ? (PE_L(2.0) * Cout / sumGB) : PE_L(0.0);
+        vec3 outLin = vec3(Rout, rightLin.g * k, rightLin.b * k);
+        return clamp(outLin, PE_L(0.0), PE_L(1.0));
+    }
+}
+
+// frag.glsl:466-503.  The native build starts with disable_anaglyph = true (main.rs:938), which drops the
+// !ANAGLYPH! lines (scene.rs:1079) until the user enables them (main.rs:1692); with them the shader reads as below.
 static inline vec3 get_color(vec2 image_position, int* bounces_out) {
+    if (_draw_anaglyph == 1) {
+        vec2 full = vec2(_resolution_x, _resolution_y);
+        int bl = 0, br = 0;
+        vec3 left = get_color2(image_position, _camera_left_eye, _left_eye_in_subspace == 1, _left_eye_scale, full, &bl);
+        vec3 right = get_color2(image_position, _camera_right_eye, _right_eye_in_subspace == 1, _right_eye_scale, full, &br);
+        if (bounces_out) *bounces_out = bl > br ? bl : br;
+        return anaglyphCombineLinear(left, right, _anaglyph_mode);
+    }
     mat4 final_matrix = _camera;
     bool final_in_subspace = _camera_in_subspace == 1;
     real final_scale = _camera_scale;

@@ -33,6 +33,7 @@ class PeOracleFrame(C.Structure):
         ("darken_by_distance", C.c_int), ("angle_color_disable", C.c_int), ("grid_disable", C.c_int),
         ("black_border_disable", C.c_int), ("draw_depth_map", C.c_int),
         ("width", C.c_int), ("height", C.c_int),
+        ("draw_anaglyph", C.c_int), ("anaglyph_mode", C.c_int), ("anaglyph_p", C.c_float), ("anaglyph_q", C.c_float),
     ]
 
 
@@ -107,6 +108,10 @@ def make_frame(ir: dict, width: int, height: int, depth: int, camera=None, camer
     fr.draw_depth_map = int(kw.get("draw_depth_map", 0))
     fr.width = int(width)
     fr.height = int(height)
+    fr.draw_anaglyph = int(kw.get("draw_anaglyph", 0))                     # SceneRenderer::new, main.rs:1030-1033
+    fr.anaglyph_mode = int(kw.get("anaglyph_mode", 0))
+    fr.anaglyph_p = float(np.float32(kw.get("anaglyph_p", 0.29)))
+    fr.anaglyph_q = float(np.float32(kw.get("anaglyph_q", 0.06)))
     return fr
 
 

@@ -183,8 +183,9 @@ PE_FI bool view_ray(const M& camera_matrix, vec2 image_position, vec2 resolution
 
 // Primary ray of AA sample `a` of pixel (px, py): vertex stage (scene.rs:1688-1693) + frag.glsl:519-524
 // + get_color (:474-501: mono, or side-by-side stereo) + get_color2's ray set-up.
-// Returns false when the sample is black without tracing.
-PE_FI bool primary_ray(int px, int py, int a, RaySlot& s) {
+// `eye`: 0 = the view get_color picks (mono or the side-by-side half the sample falls in); 1 / 2 = the left / right eye's
+// full-resolution view of anaglyph stereo (frag.glsl:467-473).  Returns false when the sample is black without tracing.
+PE_FI bool primary_ray(int px, int py, int a, int eye, RaySlot& s) {
     vec2 resolution = vec2(_resolution_x, _resolution_y);
     vec2 position = vec2(float(px) + 0.5f, float(py) + 0.5f);
     float coef = min(resolution.x, resolution.y);
@@ -196,7 +197,13 @@ PE_FI bool primary_ray(int px, int py, int a, RaySlot& s) {
     s.all_t = 0.0f;
     s.bounce = 0;
     bool ok;
-    if (_draw_side_by_side == 1) {
+    if (eye == 1) {
+        s.scale = _left_eye_scale;
+        ok = view_ray(_camera_left_eye, ip, resolution, _left_eye_in_subspace == 1, s);
+    } else if (eye == 2) {
+        s.scale = _right_eye_scale;
+        ok = view_ray(_camera_right_eye, ip, resolution, _right_eye_in_subspace == 1, s);
+    } else if (_draw_side_by_side == 1) {
         vec2 pos2 = ip / 2.0f * coef + resolution / 2.0f;
         vec2 half_res = vec2(resolution.x / 2.0f, resolution.y);
         float coef2 = min(half_res.x, half_res.y);
@@ -223,6 +230,25 @@ PE_FI bool primary_ray(int px, int py, int a, RaySlot& s) {
 PE_FI vec3 resolve_sample(const RayTraceResult& t) {
     if (_draw_depth_map == 1) return t.has_depth ? sample_depth_gradient(t.depth) : vec3(0.0f);
     return t.color;
+}
+
+// frag.glsl:343-406: red/cyan anaglyph of the two eyes' LINEAR colours with deghost compensation.
+// mode 0 = grayscale luminance, 1 = half-colour ("Colorful anaglyph", main.rs:1557).
+PE_FI vec3 anaglyphCombineLinear(vec3 leftLin, vec3 rightLin, int mode) {
+    leftLin = clamp(leftLin, 0.0f, 1.0f);
+    rightLin = clamp(rightLin, 0.0f, 1.0f);
+    const vec3 LUMA = vec3(0.299f, 0.587f, 0.114f);
+    float P = _anaglyph_p;
+    float Q = _anaglyph_q;
+    float l = dot(leftLin, LUMA);
+    float r = dot(rightLin, LUMA);
+    float denom = max(1e-6f, 1.0f - P * Q);
+    float Rout = (l - P * r) / denom;
+    float Cout = (r - Q * l) / denom;
+    if (mode == 0) return clamp(vec3(Rout, Cout, Cout), 0.0f, 1.0f);
+    float sumGB = rightLin.g + rightLin.b;
+    float k = (sumGB > 1e-6f) ? (2.0f * Cout / sumGB) : 0.0f;
+    return clamp(vec3(Rout, rightLin.g * k, rightLin.b * k), 0.0f, 1.0f);
 }
 
 }  // namespace pe
@@ -277,7 +303,31 @@ PE_FI void store_pixel(const PeLaunch& L, int px, int lrow, int grow, vec3 sum, 
 #ifndef PE_UNIFORMS_SMEM
 #define PE_UNIFORMS_SMEM 0
 #endif
-#if PE_UNIFORMS_SMEM
+#if PE_UNIFORMS_SMEM == 2
+// One elected thread issues ONE bulk asynchronous copy (TMA, cp.async.bulk) of the whole block from global memory into
+// the shared image and the block waits on the mbarrier the copy completes on: no per-thread copy loop.
+// PE_C_UPLOAD is a __device__ (global) image here: the bulk copy engine reads the global state space.
+#define PE_STAGE_UNIFORMS()                                                                                                     \
+    do {                                                                                                                        \
+        __shared__ __align__(8) unsigned long long pe_bar;                                                                      \
+        const unsigned pe_bar_a = unsigned(__cvta_generic_to_shared(&pe_bar));                                                  \
+        const unsigned pe_dst_a = unsigned(__cvta_generic_to_shared(&PE_C));                                                    \
+        if (threadIdx.x == 0) {                                                                                                 \
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pe_bar_a));                                             \
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");                                                  \
+        }                                                                                                                       \
+        __syncthreads();                                                                                                        \
+        if (threadIdx.x == 0) {                                                                                                 \
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pe_bar_a), "r"(unsigned(sizeof(pe::PeConstBlock))) : "memory"); \
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"             \
+                         ::"r"(pe_dst_a), "l"(reinterpret_cast<const void*>(&PE_C_UPLOAD)), "r"(unsigned(sizeof(pe::PeConstBlock))), "r"(pe_bar_a) : "memory"); \
+        }                                                                                                                       \
+        unsigned pe_done = 0;                                                                                                   \
+        while (!pe_done)                                                                                                        \
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"        \
+                         : "=r"(pe_done) : "r"(pe_bar_a) : "memory");                                                          \
+    } while (0)
+#elif PE_UNIFORMS_SMEM
 #define PE_STAGE_UNIFORMS()                                                                                   \
     do {                                                                                                      \
         const unsigned* pe_src = reinterpret_cast<const unsigned*>(&PE_C_UPLOAD);                             \
@@ -359,31 +409,55 @@ extern "C" __global__ void pe_probe_kernel(const PeProbe P) {
 #define PE_MIN_BLOCKS 1
 #endif
 
+// Warp tile: PE_TILE_W x (32 / PE_TILE_W) pixels, PE_TILE_W in {8, 16, 32}.  8x4 keeps the 32 primary rays of a warp
+// closest together; a wider tile makes the run of pixels a warp stores contiguously longer (8 / 16 / 32 pixels = 128 /
+// 256 / 512 B of a float frame, 32 / 64 / 128 B of an RGBA8 frame) -- what matters when the stores go over NVLink.
+#ifndef PE_TILE_W
+#define PE_TILE_W 8
+#endif
+#define PE_BLOCK_W (PE_TILE_W < 16 ? 16 : PE_TILE_W)                                   /* pixels across a block */
+#define PE_BLOCK_ROWS ((PE_BLOCK_THREADS / 32) / (PE_BLOCK_W / PE_TILE_W) * (32 / PE_TILE_W)) /* rows of a block */
+
 #if !PE_PERSISTENT
+namespace pe {
+// One view of one AA sample: get_color2 (frag.glsl:408-464).
+PE_FI vec3 trace_view(int px, int grow, int a, int eye, int& worst) {
+    RaySlot s;
+    RayTraceResult res = RayTraceResult{color(0.0f, 0.0f, 0.0f), 0.0f, false};      // loop exhausted: frag.glsl:158
+    vec3 c = vec3(0.0f);                                                             // get_color2 returned vec3(0) without tracing
+    if (primary_ray(px, grow, a, eye, s)) {
+        for (int j = 0; j < _ray_tracing_depth; j++) {                               // frag.glsl:112
+            s.bounce = j + 1;
+            if (bounce_once(s, s.scale, res)) break;
+        }
+        c = resolve_sample(res);
+    }
+    worst = pe::max(worst, s.bounce);
+    return c;
+}
+}  // namespace pe
 // ------------------------------------------------------------------------------------------
-// One thread per pixel.  Block = W warps = a 16 x (2W) pixel tile (warp tiles of 8x4, two abreast).
+// One thread per pixel.  Block = W warps = a PE_BLOCK_W x PE_BLOCK_ROWS pixel tile (8x4 warp tiles: two abreast).
 extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe_render_kernel(const PeLaunch L) {
     using namespace pe;
     PE_STAGE_UNIFORMS();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int lrow = blockIdx.y * (PE_BLOCK_THREADS / 64 * 4) + (warp >> 1) * 4 + (lane >> 3);
+    const int warps_x = PE_BLOCK_W / PE_TILE_W;
+    const int px = blockIdx.x * PE_BLOCK_W + (warp % warps_x) * PE_TILE_W + (lane % PE_TILE_W);
+    const int lrow = blockIdx.y * PE_BLOCK_ROWS + (warp / warps_x) * (32 / PE_TILE_W) + (lane / PE_TILE_W);
     int grow;
     if (px >= L.width || !local_to_global_row(L, lrow, grow)) return;
 
     vec3 sum = vec3(0.0f);
     int worst = 0;
     for (int a = _aa_start; a < _aa_count + _aa_start; a++) {  // frag.glsl:522-525
-        RaySlot s;
-        RayTraceResult res = RayTraceResult{color(0.0f, 0.0f, 0.0f), 0.0f, false};  // loop exhausted: frag.glsl:158
-        if (primary_ray(px, grow, a, s)) {
-            for (int j = 0; j < _ray_tracing_depth; j++) {                           // frag.glsl:112
-                s.bounce = j + 1;
-                if (bounce_once(s, s.scale, res)) break;
-            }
-            sum += resolve_sample(res);
-        }                                                                            // else: get_color2 returned vec3(0)
-        worst = pe::max(worst, s.bounce);
+        if (_draw_anaglyph == 1) {                             // frag.glsl:467-473
+            vec3 left = trace_view(px, grow, a, 1, worst);
+            vec3 right = trace_view(px, grow, a, 2, worst);
+            sum += anaglyphCombineLinear(left, right, _anaglyph_mode);
+        } else {
+            sum += trace_view(px, grow, a, 0, worst);
+        }
     }
     store_pixel(L, px, lrow, grow, sum, worst);
 }
@@ -405,6 +479,9 @@ extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe
     RaySlot s;
     RayTraceResult res;
     vec3 sum = vec3(0.0f);
+    vec3 left = vec3(0.0f);  // anaglyph: the left eye's colour of the current sample while the right eye's ray is traced
+    const int first_eye = (_draw_anaglyph == 1) ? 1 : 0;
+    int eye = first_eye;
     int px = 0, lrow = 0, grow = 0, a = 0, worst = 0;
     bool alive = false;      // lane holds a ray in flight
     bool skip = false;       // current sample is black without tracing (outside a 360 / VR180 image)
@@ -436,7 +513,8 @@ extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe
                     a = _aa_start;
                     sum = vec3(0.0f);
                     worst = 0;
-                    skip = !primary_ray(px, grow, a, s);
+                    eye = first_eye;
+                    skip = !primary_ray(px, grow, a, eye, s);
                     alive = true;
                 }
                 // (an out-of-frame pixel of an edge tile is skipped: the lane stays idle)
@@ -467,11 +545,19 @@ extern "C" __global__ void __launch_bounds__(PE_BLOCK_THREADS, PE_MIN_BLOCKS) pe
                 }
             }
             if (done) {
-                sum += resolve_sample(res);
                 worst = pe::max(worst, s.bounce);
+                if (_draw_anaglyph == 1 && eye == 1) {     // frag.glsl:467-473: same sample, now through the right eye
+                    left = resolve_sample(res);
+                    eye = 2;
+                    skip = !primary_ray(px, grow, a, eye, s);
+                    continue;
+                }
+                if (_draw_anaglyph == 1) sum += anaglyphCombineLinear(left, resolve_sample(res), _anaglyph_mode);
+                else sum += resolve_sample(res);
                 a++;
                 if (a < _aa_count + _aa_start) {
-                    skip = !primary_ray(px, grow, a, s);   // next AA sample of the same pixel (may fall outside a 360 / VR180 image)
+                    eye = first_eye;
+                    skip = !primary_ray(px, grow, a, eye, s);   // next AA sample of the same pixel (may fall outside a 360 / VR180 image)
                 } else {
                     store_pixel(L, px, lrow, grow, sum, worst);
                     alive = false;

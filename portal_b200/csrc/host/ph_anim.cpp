@@ -302,7 +302,7 @@ bool Player::teleport_camera(const OrbitCam& prev) {  // main.rs:1217-1264
 }
 
 bool Player::teleport_eye_matrices() {  // main.rs:1121-1172
-    if (!(draw_side_by_side && cam.allow_teleport)) return true;
+    if (!((draw_anaglyph || draw_side_by_side) && cam.allow_teleport)) return true;   // main.rs:1122
     const double ed = swap_eyes ? -eye_distance : eye_distance;
     auto one = [&](double eye_x, Mat4& matrix, bool& sub) -> bool {
         double start[3], p[4];

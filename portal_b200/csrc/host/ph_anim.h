@@ -61,6 +61,8 @@ struct Player {
     OrbitCam cam, prev_cam;
     // stereo (main.rs:1027-1030, teleport_eye_matrices :1121-1172)
     bool draw_side_by_side = false, swap_eyes = false;
+    bool draw_anaglyph = false, anaglyph_mode = false;   // main.rs:1030-1033
+    double anaglyph_p = 0.29, anaglyph_q = 0.06;
     double eye_distance = 0.07;
     Mat4 left_eye_matrix = mat_identity(), right_eye_matrix = mat_identity();
     bool left_eye_in_subspace = false, right_eye_in_subspace = false;

@@ -448,6 +448,15 @@ int ph_player_set_stereo(ph_player* p, int draw_side_by_side, double eye_distanc
     return 0;
 }
 
+int ph_player_set_anaglyph(ph_player* p, int draw_anaglyph, int colorful, double anaglyph_p, double anaglyph_q) {
+    if (!p) return 1;
+    p->player.draw_anaglyph = draw_anaglyph != 0;
+    p->player.anaglyph_mode = colorful != 0;
+    p->player.anaglyph_p = anaglyph_p;
+    p->player.anaglyph_q = anaglyph_q;
+    return 0;
+}
+
 int ph_player_eyes(ph_player* p, double left16[16], double right16[16], int32_t* left_in_subspace, int32_t* right_in_subspace) {
     if (!p) return 1;
     if (left16) for (int k = 0; k < 16; k++) left16[k] = p->player.left_eye_matrix[size_t(k)];
@@ -470,6 +479,10 @@ static int upload_stereo_uniforms(ph_player* pl, pe_ctx* ctx) {
     rc |= pe_set_uniform_f32(ctx, "_left_eye_scale", float(ph::camera_scale(P.left_eye_matrix)));
     rc |= pe_set_uniform_f32(ctx, "_right_eye_scale", float(ph::camera_scale(P.right_eye_matrix)));
     rc |= pe_set_uniform_i32(ctx, "_draw_side_by_side", P.draw_side_by_side ? 1 : 0);
+    rc |= pe_set_uniform_i32(ctx, "_draw_anaglyph", P.draw_anaglyph ? 1 : 0);      // main.rs:1308-1315
+    rc |= pe_set_uniform_f32(ctx, "_anaglyph_p", float(P.anaglyph_p));
+    rc |= pe_set_uniform_f32(ctx, "_anaglyph_q", float(P.anaglyph_q));
+    rc |= pe_set_uniform_i32(ctx, "_anaglyph_mode", P.anaglyph_mode ? 1 : 0);
     if (rc) return pfail(pl, std::string("stereo uniform upload failed: ") + pe_last_error(ctx));
     return 0;
 }

@@ -207,6 +207,8 @@ void set_renderer_defaults(pe_ctx* c) {
     F("_left_eye_scale", 1.0f);
     F("_right_eye_scale", 1.0f);
     F("_panini_param", 1.0f);
+    F("_anaglyph_p", 0.29f);   // SceneRenderer::new, main.rs:1031-1032
+    F("_anaglyph_q", 0.06f);
     I("_ray_tracing_depth", 100);
     I("_aa_start", 0);
     I("_aa_count", 1);
@@ -222,6 +224,8 @@ void set_renderer_defaults(pe_ctx* c) {
     I("_use_360_camera", 0);
     I("_use_180_camera", 0);
     I("_draw_side_by_side", 0);
+    I("_draw_anaglyph", 0);
+    I("_anaglyph_mode", 0);
 }
 
 // Host evaluation of the per-plane uniform expressions (PlaneRec), in fp32 with exactly the device's
@@ -289,7 +293,8 @@ std::vector<int> variant_key(pe_ctx* c, const std::vector<int>& ints, const std:
     if (c->opts.specialize_matrices)
         for (auto& zo : masks) key.push_back(int(zo.first | (zo.second << 16)));
     key.push_back(c->opts.with_probe ? 1 : 0);
-    key.push_back(c->opts.uniforms_in_smem ? 1 : 0);
+    key.push_back(c->opts.uniforms_in_smem);
+    key.push_back(c->opts.tile_w);
     for (char d : c->opts.dynamic_ints) key.push_back(d);
     for (char d : c->opts.dynamic_mats) key.push_back(d);
     return key;
@@ -675,7 +680,13 @@ int pe_set_option(pe_ctx* c, const char* key, int value) {
     else if (k == "lazy_planes") c->opts.lazy_planes = value != 0;
     else if (k == "with_probe") c->opts.with_probe = value != 0;   // pe_probe_ray turns it on by itself; exposed for inspection
     else if (k == "adaptive") c->adapt = value != 0;
-    else if (k == "uniforms_in_smem") c->opts.uniforms_in_smem = value != 0;
+    else if (k == "uniforms_in_smem") {
+        if (value < 0 || value > 2) return c->fail("uniforms_in_smem must be 0 (constant bank), 1 (copy loop) or 2 (TMA bulk copy)");
+        c->opts.uniforms_in_smem = value;
+    } else if (k == "tile_w") {
+        if (value != 8 && value != 16 && value != 32) return c->fail("tile_w must be 8, 16 or 32");
+        c->opts.tile_w = value;
+    }
     else return c->fail("unknown option `" + k + "`");
     // options change the generated program
     if (c->has_gpu) {
@@ -841,8 +852,10 @@ static int render_impl(pe_ctx* c, const pe_target* t, void* out_device, void* bo
         gx = unsigned(c->sm_count * v->blocks_per_sm);
         gy = 1;
     } else {
-        const int rows_per_block = c->opts.block_threads / 64 * 4;
-        gx = unsigned((t->width + 15) / 16);
+        // must match PE_BLOCK_W / PE_BLOCK_ROWS in device/pe_kernel.cuh
+        const int tile_w = c->opts.tile_w, block_w = tile_w < 16 ? 16 : tile_w;
+        const int rows_per_block = (c->opts.block_threads / 32) / (block_w / tile_w) * (32 / tile_w);
+        gx = unsigned((t->width + block_w - 1) / block_w);
         gy = unsigned((local_rows + rows_per_block - 1) / rows_per_block);
     }
     r = d->cuLaunchKernel(v->kernel, gx, gy, 1, unsigned(c->opts.block_threads), 1, 1, 0, s, args, nullptr);

@@ -16,13 +16,13 @@ namespace pe_host {
 const char* const kRendererFloats[] = {"_camera_scale", "_tan_half_view", "_view_angle", "_t_start", "_t_end",
                                        "_offset_after_material", "_depth_map_min", "_depth_map_max",
                                        "_resolution_x", "_resolution_y", "_left_eye_scale", "_right_eye_scale",
-                                       "_panini_param"};
+                                       "_panini_param", "_anaglyph_p", "_anaglyph_q"};
 const int kNumRendererFloats = int(sizeof(kRendererFloats) / sizeof(kRendererFloats[0]));
 const char* const kRendererInts[] = {"_ray_tracing_depth", "_aa_start", "_aa_count", "_camera_in_subspace",
                                      "_darken_by_distance", "_angle_color_disable", "_grid_disable",
                                      "_black_border_disable", "_draw_depth_map", "_left_eye_in_subspace",
                                      "_right_eye_in_subspace", "_use_panini_projection", "_use_360_camera",
-                                     "_use_180_camera", "_draw_side_by_side"};
+                                     "_use_180_camera", "_draw_side_by_side", "_draw_anaglyph", "_anaglyph_mode"};
 const int kNumRendererInts = int(sizeof(kRendererInts) / sizeof(kRendererInts[0]));
 // Renderer ints that change per frame / per motion-blur sub-frame stay dynamic.
 static bool renderer_int_is_dynamic(const std::string& n) { return n == "_ray_tracing_depth" || n == "_aa_start"; }
@@ -69,6 +69,7 @@ ConstLayout make_layout(const SceneDesc& scene) {
     size_t end_int = L.off_int + size_t(L.plane_i0 + 2 * L.planes.size()) * 4;
     L.off_tex = (end_int + 7) & ~size_t(7);
     L.size = L.off_tex + size_t(L.n_tex > 0 ? L.n_tex : 1) * 16;
+    L.size = (L.size + 15) & ~size_t(15);  // whole 16-byte units: the block can be moved by one bulk copy (cp.async.bulk)
     return L;
 }
 
@@ -539,6 +540,7 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     hd << "#define PE_BLOCK_THREADS " << opts.block_threads << "\n";
     hd << "#define PE_MIN_BLOCKS " << opts.min_blocks << "\n";
     hd << "#define PE_WITH_PROBE " << (opts.with_probe ? 1 : 0) << "\n";
+    hd << "#define PE_TILE_W " << opts.tile_w << "\n";
     std::string swz_err;
     hd << "#define PE_SWZ_VEC2" << swizzle_macro(body.swz, 2) << lvalue_swizzle_macro(body.swz_w, 2, swz_err) << "\n";
     hd << "#define PE_SWZ_VEC3" << swizzle_macro(body.swz, 3) << lvalue_swizzle_macro(body.swz_w, 3, swz_err) << "\n";
@@ -572,7 +574,7 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     hd << kSrcGlsl << "\n";
     hd << "namespace pe {\n";
     hd << "// Constant uniform block: scene matrices + camera, floats, ints, texture descriptors.\n";
-    hd << "struct PeConstBlock {\n";
+    hd << "struct __align__(16) PeConstBlock {\n";
     hd << "    cmat4 m[" << (L.n_mat + 4) << "];\n";
     hd << "    float f[" << (L.plane_f0 + 3 * L.planes.size()) << "];\n";
     hd << "    int i[" << (L.plane_i0 + 2 * L.planes.size()) << "];\n";
@@ -584,8 +586,9 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
         hd << "extern \"C\" { __constant__ pe::PeConstBlock PE_C; }\n";
     } else {
         // the host uploads to PE_C_UPLOAD; each block copies it into the shared image PE_C before any thread reads a uniform
-        hd << "#define PE_UNIFORMS_SMEM 1\n";
-        hd << "extern \"C\" { __constant__ pe::PeConstBlock PE_C_UPLOAD; }\n";
+        hd << "#define PE_UNIFORMS_SMEM " << opts.uniforms_in_smem << "\n";
+        // mode 2: the TMA bulk copy reads the global state space, so the uploaded image is a __device__ variable
+        hd << "extern \"C\" { " << (opts.uniforms_in_smem == 2 ? "__device__" : "__constant__") << " pe::PeConstBlock PE_C_UPLOAD; }\n";
         hd << "__shared__ pe::PeConstBlock PE_C;\n";
     }
     // uniform declarations (scene.rs:661-718) -> names bound to the block / to specialisation constants

@@ -98,7 +98,11 @@ struct GenOptions {
     // Uniform block staged in shared memory: every block copies the constant block to a __shared__ image in its prologue
     // and the program reads uniforms from there (LDS operands) instead of the constant bank (LDCU / UR operands).  What
     // north_star sketches; off by default, see DESIGN.md sections 3 and 10.
-    bool uniforms_in_smem = false;
+    // 0 = constant bank; 1 = cooperative copy loop + __syncthreads; 2 = one TMA bulk copy (cp.async.bulk) + mbarrier wait.
+    // Measured in profiles/r02*_sweep_smem.txt.
+    int uniforms_in_smem = 0;
+    // Width of a warp's pixel tile in the one-thread-per-pixel kernel: 8 (8x4), 16 (16x2) or 32 (32x1); see pe_kernel.cuh.
+    int tile_w = 8;
     bool unroll_loops = true;  // false: `#pragma unroll 1` on every loop of the user snippets (smaller code)
     // per slot of i[] / per scene matrix: 1 = read it from the constant block even when specialisation is on (slots whose
     // value kept changing between renders, pe_api.cpp select_variant)

@@ -1,6 +1,6 @@
 // Static (nvcc-compiled, sm_100a) helper kernels of portal_b200: the HBM-bound passes around the
-// ray loop.  All are pure streaming kernels: 16-byte vector accesses, grid sized to the SM count,
-// grid-stride loops.
+// ray loop.  All are pure streaming kernels: 16-byte vector accesses with several independent loads in
+// flight per thread, streaming cache hints (every byte is touched once), grid sized to the SM count.
 //
 //   pe_k_quantize_rgba8     float RGBA -> RGBA8: what the reference's RGBA8 render target does to
 //                           FragColor before get_texture_data() (/root/reference/src/main.rs:2939-2943)
@@ -19,31 +19,67 @@ __device__ __forceinline__ unsigned quant8(float v) {
     v = fminf(fmaxf(v, 0.0f), 1.0f);
     return (unsigned)__float2int_rn(v * 255.0f);
 }
-
-__global__ void __launch_bounds__(256) pe_k_quantize_rgba8(const float4* __restrict__ in, uchar4* __restrict__ out, size_t n) {
-    size_t stride = size_t(gridDim.x) * blockDim.x;
-    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float4 p = in[i];
-        // NaN -> 0 (fmaxf(NaN, 0) == 0), the behaviour of GL's float->unorm conversion on NVIDIA
-        out[i] = make_uchar4((unsigned char)quant8(p.x), (unsigned char)quant8(p.y), (unsigned char)quant8(p.z),
-                             (unsigned char)quant8(p.w));
-    }
+__device__ __forceinline__ unsigned pack8(float4 p) {
+    // NaN -> 0 (fmaxf(NaN, 0) == 0), the behaviour of GL's float->unorm conversion on NVIDIA
+    return quant8(p.x) | (quant8(p.y) << 8) | (quant8(p.z) << 16) | (quant8(p.w) << 24);
 }
 
-// One thread per float4 pixel.  gathered: [rank][strips_per_rank][strip_rows][width]
+// Streaming loads / stores that do not pollute L1 and are evicted first from L2: every byte here is touched once.
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(uint4* p, uint4 v) { __stcs(p, v); }
+
+// float RGBA -> RGBA8.  A thread owns 4 CONSECUTIVE pixels: four 16-byte loads (all issued before the first use, so 64 B
+// per thread are in flight: 2048 threads/SM x 64 B = 128 KB per SM, enough to cover the HBM latency-bandwidth product)
+// and ONE 16-byte store.  A warp's four load instructions together cover 2 KB contiguous; each 32-byte sector is
+// fetched once (the second half of a sector is an L1 hit of the neighbouring load instruction).
+#define PE_Q_UNROLL 2
+__global__ void __launch_bounds__(256) pe_k_quantize_rgba8(const float4* __restrict__ in, uchar4* __restrict__ out, size_t n) {
+    const size_t n4 = n >> 2;                                   // groups of 4 pixels
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; g + (PE_Q_UNROLL - 1) * stride < n4; g += PE_Q_UNROLL * stride) {
+        float4 p[PE_Q_UNROLL][4];
+#pragma unroll
+        for (int u = 0; u < PE_Q_UNROLL; u++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) p[u][k] = ld_stream(in + 4 * (g + u * stride) + k);
+#pragma unroll
+        for (int u = 0; u < PE_Q_UNROLL; u++)
+            st_stream(reinterpret_cast<uint4*>(out) + (g + u * stride),
+                      make_uint4(pack8(p[u][0]), pack8(p[u][1]), pack8(p[u][2]), pack8(p[u][3])));
+    }
+    for (; g < n4; g += stride) {
+        float4 p[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) p[k] = ld_stream(in + 4 * g + k);
+        st_stream(reinterpret_cast<uint4*>(out) + g, make_uint4(pack8(p[0]), pack8(p[1]), pack8(p[2]), pack8(p[3])));
+    }
+    // ragged tail (n not a multiple of 4): at most 3 pixels
+    const size_t i = (n4 << 2) + size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) reinterpret_cast<unsigned*>(out)[i] = pack8(in[i]);
+}
+
+// Rank-major gathered strips -> row-major frame.  Work unit = one 16-byte pixel; the index map is per ROW (a row of the
+// frame is contiguous in both layouts), so the kernel walks rows with blockIdx.y and a thread copies 4 pixels of the
+// row, all four loads in flight before the stores.  gathered: [rank][strips_per_rank][strip_rows][width]
 __global__ void __launch_bounds__(256) pe_k_deinterleave(const float4* __restrict__ gathered, float4* __restrict__ frame,
                                                          int width, int height, int strip_rows, int n_ranks,
                                                          int strips_per_rank) {
-    size_t n = size_t(width) * size_t(height);
-    size_t stride = size_t(gridDim.x) * blockDim.x;
-    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        int y = int(i / size_t(width));
-        int x = int(i - size_t(y) * size_t(width));
-        int gstrip = y / strip_rows;
-        int rank = gstrip % n_ranks;
-        int lstrip = gstrip / n_ranks;
-        size_t src = ((size_t(rank) * strips_per_rank + lstrip) * strip_rows + size_t(y - gstrip * strip_rows)) * size_t(width) + x;
-        frame[i] = gathered[src];
+    for (int y = blockIdx.y; y < height; y += gridDim.y) {
+        const int gstrip = y / strip_rows;
+        const int rank = gstrip % n_ranks;
+        const int lstrip = gstrip / n_ranks;
+        const float4* src = gathered + ((size_t(rank) * strips_per_rank + lstrip) * strip_rows + size_t(y - gstrip * strip_rows)) * size_t(width);
+        float4* dst = frame + size_t(y) * size_t(width);
+        const int step = blockDim.x * gridDim.x;
+        int x = blockIdx.x * blockDim.x + threadIdx.x;
+        for (; x + 3 * step < width; x += 4 * step) {
+            float4 a = ld_stream(src + x), b = ld_stream(src + x + step), c = ld_stream(src + x + 2 * step), d = ld_stream(src + x + 3 * step);
+            st_stream(dst + x, a); st_stream(dst + x + step, b); st_stream(dst + x + 2 * step, c); st_stream(dst + x + 3 * step, d);
+        }
+        for (; x < width; x += step) st_stream(dst + x, ld_stream(src + x));
     }
 }
 
@@ -56,21 +92,62 @@ __device__ __forceinline__ unsigned l_to_s(unsigned l) {
     // L_TO_S[i] = ((i as f32).sqrt() + 0.5) as u8   (main.rs:645-651)
     return (unsigned)(sqrtf((float)l) + 0.5f);
 }
+__device__ __forceinline__ void acc_sq(unsigned w, unsigned& r, unsigned& g, unsigned& b) {
+    const unsigned x = w & 0xffu, y = (w >> 8) & 0xffu, z = (w >> 16) & 0xffu;
+    r += x * x; g += y * y; b += z * z;
+}
 
+// Motion-blur mean in gamma-2 space.  A thread owns 4 consecutive pixels (one 16-byte load per sub-frame, one 16-byte
+// store); the loads of 4 sub-frames are issued together.
 __global__ void __launch_bounds__(256) pe_k_average_rgba8(FramePtrs frames, int n_frames, uchar4* __restrict__ out, size_t n) {
-    size_t stride = size_t(gridDim.x) * blockDim.x;
-    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        unsigned r = 0, g = 0, b = 0;
-        for (int f = 0; f < n_frames; f++) {
-            uchar4 p = frames.p[f][i];
-            r += unsigned(p.x) * unsigned(p.x);
-            g += unsigned(p.y) * unsigned(p.y);
-            b += unsigned(p.z) * unsigned(p.z);
+    const size_t n4 = n >> 2;
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    const unsigned nn = (unsigned)n_frames;
+    for (size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x; g < n4; g += stride) {
+        unsigned r[4] = {0, 0, 0, 0}, gg[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+        int f = 0;
+        for (; f + 4 <= n_frames; f += 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = ld_stream(reinterpret_cast<const uint4*>(frames.p[f + k]) + g);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                acc_sq(v[k].x, r[0], gg[0], b[0]); acc_sq(v[k].y, r[1], gg[1], b[1]);
+                acc_sq(v[k].z, r[2], gg[2], b[2]); acc_sq(v[k].w, r[3], gg[3], b[3]);
+            }
         }
-        unsigned nn = (unsigned)n_frames;
-        out[i] = make_uchar4((unsigned char)l_to_s(r / nn), (unsigned char)l_to_s(g / nn), (unsigned char)l_to_s(b / nn), 255);
+        for (; f < n_frames; f++) {
+            const uint4 v = ld_stream(reinterpret_cast<const uint4*>(frames.p[f]) + g);
+            acc_sq(v.x, r[0], gg[0], b[0]); acc_sq(v.y, r[1], gg[1], b[1]); acc_sq(v.z, r[2], gg[2], b[2]); acc_sq(v.w, r[3], gg[3], b[3]);
+        }
+        unsigned o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = l_to_s(r[k] / nn) | (l_to_s(gg[k] / nn) << 8) | (l_to_s(b[k] / nn) << 16) | 0xff000000u;
+        st_stream(reinterpret_cast<uint4*>(out) + g, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+    const size_t i = (n4 << 2) + size_t(blockIdx.x) * blockDim.x + threadIdx.x;   // ragged tail: at most 3 pixels
+    if (i < n) {
+        unsigned r = 0, g = 0, b = 0;
+        for (int f = 0; f < n_frames; f++) acc_sq(reinterpret_cast<const unsigned*>(frames.p[f])[i], r, g, b);
+        reinterpret_cast<unsigned*>(out)[i] = l_to_s(r / nn) | (l_to_s(g / nn) << 8) | (l_to_s(b / nn) << 16) | 0xff000000u;
     }
 }
+
+// Scalar forms for pixel buffers that are not 16-byte aligned (a caller's sub-rectangle): one pixel per thread.
+__global__ void __launch_bounds__(256) pe_k_quantize_rgba8_px(const float4* __restrict__ in, unsigned* __restrict__ out, size_t n) {
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = pack8(in[i]);
+}
+__global__ void __launch_bounds__(256) pe_k_average_rgba8_px(FramePtrs frames, int n_frames, unsigned* __restrict__ out, size_t n) {
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    const unsigned nn = (unsigned)n_frames;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        unsigned r = 0, g = 0, b = 0;
+        for (int f = 0; f < n_frames; f++) acc_sq(reinterpret_cast<const unsigned*>(frames.p[f])[i], r, g, b);
+        out[i] = l_to_s(r / nn) | (l_to_s(g / nn) << 8) | (l_to_s(b / nn) << 16) | 0xff000000u;
+    }
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // Cross-GPU signal: after everything earlier in the stream (the render kernel's remote stores
 // included) one thread publishes `value` to up to 8 flag words, which may live in peer memory.
@@ -98,15 +175,20 @@ int grid_for(size_t n, int sms) {
 namespace pe_host {
 
 int launch_quantize_rgba8(const void* in, void* out, size_t n, int sms, cudaStream_t s) {
-    pe_k_quantize_rgba8<<<grid_for(n, sms), 256, 0, s>>>((const float4*)in, (uchar4*)out, n);
+    if (aligned16(out)) pe_k_quantize_rgba8<<<grid_for((n + 3) / 4, sms), 256, 0, s>>>((const float4*)in, (uchar4*)out, n);
+    else pe_k_quantize_rgba8_px<<<grid_for(n, sms), 256, 0, s>>>((const float4*)in, (unsigned*)out, n);
     return (int)cudaGetLastError();
 }
 
 int launch_deinterleave(const void* gathered, void* frame, int width, int height, int strip_rows, int n_ranks,
                         int strips_per_rank, int sms, cudaStream_t s) {
-    size_t n = size_t(width) * size_t(height);
-    pe_k_deinterleave<<<grid_for(n, sms), 256, 0, s>>>((const float4*)gathered, (float4*)frame, width, height, strip_rows,
-                                                     n_ranks, strips_per_rank);
+    // rows on blockIdx.y; one block column when a row fits 256 threads x 4 pixels, else enough columns for one pass
+    const unsigned gx = unsigned((width + 1023) / 1024);
+    unsigned gy = unsigned(sms) * 8u / gx;
+    if (gy > unsigned(height)) gy = unsigned(height);
+    if (gy < 1) gy = 1;
+    pe_k_deinterleave<<<dim3(gx, gy), 256, 0, s>>>((const float4*)gathered, (float4*)frame, width, height, strip_rows,
+                                                   n_ranks, strips_per_rank);
     return (int)cudaGetLastError();
 }
 
@@ -122,7 +204,10 @@ int launch_average_rgba8(const void* const* frames, int n_frames, void* out, siz
     if (n_frames < 1 || n_frames > PE_MAX_AVG_FRAMES) return (int)cudaErrorInvalidValue;
     FramePtrs fp;
     for (int i = 0; i < n_frames; i++) fp.p[i] = (const uchar4*)frames[i];
-    pe_k_average_rgba8<<<grid_for(n, sms), 256, 0, s>>>(fp, n_frames, (uchar4*)out, n);
+    bool vec = aligned16(out);
+    for (int i = 0; i < n_frames; i++) vec = vec && aligned16(frames[i]);
+    if (vec) pe_k_average_rgba8<<<grid_for((n + 3) / 4, sms), 256, 0, s>>>(fp, n_frames, (uchar4*)out, n);
+    else pe_k_average_rgba8_px<<<grid_for(n, sms), 256, 0, s>>>(fp, n_frames, (unsigned*)out, n);
     return (int)cudaGetLastError();
 }
 

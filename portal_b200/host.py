@@ -184,6 +184,9 @@ class HostPlayer:
     def set_stereo(self, draw_side_by_side: bool, eye_distance: float = 0.07, swap_eyes: bool = False):
         self._check(self._lib.ph_player_set_stereo(self._p, int(draw_side_by_side), float(eye_distance), int(swap_eyes)))
 
+    def set_anaglyph(self, draw_anaglyph: bool, colorful: bool = False, p: float = 0.29, q: float = 0.06):
+        self._check(self._lib.ph_player_set_anaglyph(self._p, int(draw_anaglyph), int(colorful), float(p), float(q)))
+
     def camera_state(self) -> dict:
         cam, inv, orbit, times = (C.c_double * 16)(), (C.c_double * 16)(), (C.c_double * 6)(), (C.c_double * 2)()
         sub, scale, n = C.c_int32(), C.c_double(), C.c_int64()

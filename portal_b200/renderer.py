@@ -96,6 +96,10 @@ class SceneRenderer:
         self.use_180_camera = False
         self.draw_side_by_side = False       # SceneRenderer::new, main.rs:1027
         self.eye_distance = 0.07             # main.rs:1028
+        self.draw_anaglyph = False           # main.rs:1030-1033 (the UI toggles them: main.rs:1549-1580)
+        self.anaglyph_p = 0.29
+        self.anaglyph_q = 0.06
+        self.anaglyph_mode = False           # False = grayscale, True = "Colorful anaglyph"
         self.camera_mul_inv = np.eye(4).reshape(16)   # teleport_matrix.inverse(), main.rs:1286-1289
         cam = scene_ir["cam"]
         self.set_cam(cam["look_at"], cam["alpha"], cam["beta"], cam["r"])  # main.rs:1057
@@ -229,7 +233,8 @@ class SceneRenderer:
                  self.aa_count, self.aa_start, self.draw_depth_map, self.depth_map_min, self.depth_map_max,
                  self.offset_after_material, self.gray_t_start, self.gray_t_size, self.angle_color_disable, self.grid_disable,
                  self.black_border_disable, self.darken_by_distance, self.use_panini_projection, self.panini_param,
-                 self.use_360_camera, self.use_180_camera, self.draw_side_by_side, self.eye_distance)
+                 self.use_360_camera, self.use_180_camera, self.draw_side_by_side, self.eye_distance,
+                 self.draw_anaglyph, self.anaglyph_p, self.anaglyph_q, self.anaglyph_mode)
         if state == getattr(self, "_sent_state", None):
             return
         self._sent_state = state
@@ -257,6 +262,10 @@ class SceneRenderer:
         s("_use_360_camera", int(self.use_360_camera))
         s("_use_180_camera", int(self.use_180_camera))
         s("_draw_side_by_side", int(self.draw_side_by_side))
+        s("_draw_anaglyph", int(self.draw_anaglyph))            # main.rs:1308-1315
+        s("_anaglyph_p", float(self.anaglyph_p))
+        s("_anaglyph_q", float(self.anaglyph_q))
+        s("_anaglyph_mode", int(self.anaglyph_mode))
         left, right = self.eye_matrices()
         s("_camera_left_eye", left)
         s("_camera_right_eye", right)

@@ -17,6 +17,7 @@
 #define __launch_bounds__(...)
 #define __restrict__
 #define __shared__
+#define __align__(n) alignas(n)
 static inline void __syncthreads() {}
 
 struct uchar4 { unsigned char x, y, z, w; };

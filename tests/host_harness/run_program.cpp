@@ -87,9 +87,9 @@ int main(int argc, char** argv) {
     L.tiles_y = (h + 3) / 4;
     L.out_rgba8 = 0;
     L.queue = nullptr;
-    const unsigned rows_per_block = PE_BLOCK_THREADS / 64 * 4;
+    const unsigned rows_per_block = PE_BLOCK_ROWS;
     blockDim = pe_uint3{unsigned(PE_BLOCK_THREADS), 1, 1};
-    gridDim = pe_uint3{unsigned((w + 15) / 16), unsigned((h + rows_per_block - 1) / rows_per_block), 1};
+    gridDim = pe_uint3{unsigned((w + PE_BLOCK_W - 1) / PE_BLOCK_W), unsigned((h + rows_per_block - 1) / rows_per_block), 1};
     const pe_uint3 bd = blockDim, gd = gridDim;
 #pragma omp parallel for schedule(dynamic, 1)   // (only with -fopenmp: the built-in indices are thread_local)
     for (int by = 0; by < int(gd.y); by++)

@@ -27,7 +27,7 @@ W, H, DEPTH = 96, 54, 8
 IDENTITY = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
 
 
-def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid", sky=None, near_shift=0.0, far_z=30.0, see_far_directly=True, cs=1.0, near_is_gridded=False, no_near=False):
+def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=None, stereo=None, grid="grid", sky=None, near_shift=0.0, far_z=30.0, see_far_directly=True, cs=1.0, near_is_gridded=False, no_near=False, eye=0.0):
     """(frame [h, w, 3] float64, mask of pixels further than a hair from every decision boundary, region masks).
     s: scale of the gate's far side (gate_b) -- the jump then magnifies by s about the gate's centre, the offset step is taken
     along the UN-normalised direction (length s) and normalize_ray leaves tmul = 1 / s (library.glsl:108-113, 366-371)."""
@@ -38,7 +38,7 @@ def closed_form(w, h, s=1.0, sample=0, linear=False, projection=None, depth_map=
     r2x, r2y = np.mod(0.5 + 0.7548776662 * sample, 1.0), np.mod(0.5 + 0.5698402910 * sample, 1.0)
     a = ((px + 0.5) - w / 2) / m * 2 + r2x * (1 / m) * 2
     b = ((py + 0.5) - h / 2) / m * 2 + r2y * (1 / m) * 2
-    ex = 0.0
+    ex = eye                                                 # the camera sits at (eye, 0, 0) (an eye of anaglyph stereo)
     split = np.zeros((h, w), dtype=bool)
     if stereo is not None:
         # frag.glsl:476-497: side by side -- each half of the frame is its own image for one eye, here at (-+stereo, 0, 0)
@@ -905,6 +905,40 @@ def test_side_by_side_stereo(tmp_path):
     prog, _ = _run_on_host(tmp_path, "stereo", None, ir=ir, tex={}, depth=DEPTH,
                            attrs={"camera_matrix": IDENTITY, "draw_side_by_side": 1, "eye_distance": e})
     assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32))
+
+
+def test_anaglyph_stereo(tmp_path):
+    """_draw_anaglyph (frag.glsl:343-406, 467-473): every sample is traced through BOTH eyes at full resolution and the two
+    linear colours are combined into red (left) / cyan (right) with the deghost compensation; both modes, closed form."""
+    from oracle import runner
+    from test_program_on_host import _run_on_host
+    ir, e, P, Q = scene_ir(), 0.4, 0.29, 0.06
+    (left, safe_l, _, _), (right, safe_r, _, _) = closed_form(W, H, linear=True, eye=-e), closed_form(W, H, linear=True, eye=e)
+    safe = safe_l & safe_r
+    luma = np.array([0.299, 0.587, 0.114])
+    lc, rc = np.clip(left, 0, 1), np.clip(right, 0, 1)
+    l, r = lc @ luma, rc @ luma
+    denom = max(1e-6, 1 - P * Q)
+    rout, cout = (l - P * r) / denom, (r - Q * l) / denom
+    eye = lambda x: [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, x, 0, 0, 1.0]       # noqa: E731
+    for mode in (0, 1):
+        if mode == 0:
+            lin = np.stack([rout, cout, cout], axis=-1)
+        else:
+            sum_gb = rc[..., 1] + rc[..., 2]
+            k = np.where(sum_gb > 1e-6, 2 * cout / np.maximum(sum_gb, 1e-30), 0.0)
+            lin = np.stack([rout, rc[..., 1] * k, rc[..., 2] * k], axis=-1)
+        want = np.sqrt(np.clip(lin, 0, 1))
+        got = runner.Oracle(ir, "strict").render(W, H, DEPTH, camera=IDENTITY, camera_scale=1.0, draw_anaglyph=1, anaglyph_mode=mode,
+                                                 camera_left_eye=eye(-e), camera_right_eye=eye(e))
+        # sqrt near 0 amplifies the float32 rounding of a clamped-to-zero channel: compare away from it
+        ok = safe & (lin.min(axis=-1) > 1e-3)
+        assert ok.mean() > 0.8, ok.mean()
+        assert np.abs(got[..., :3].astype(np.float64) - want)[ok].max() < 3e-5, mode
+        assert np.abs(want[..., 0] - want[..., 1])[ok].max() > 0.05             # the channels really carry different eyes
+        prog, _ = _run_on_host(tmp_path, f"anaglyph{mode}", None, ir=ir, tex={}, depth=DEPTH,
+                               attrs={"camera_matrix": IDENTITY, "draw_anaglyph": 1, "anaglyph_mode": bool(mode), "eye_distance": e})
+        assert np.array_equal(np.ascontiguousarray(prog).view(np.uint32), np.ascontiguousarray(got).view(np.uint32)), mode
 
 
 def test_depth_map_colouring(tmp_path):

@@ -194,6 +194,27 @@ def test_persistent_aa_with_image_area_projections(torch_cuda):
         assert np.array_equal(_bits(frames[1]), _bits(ref)), ("persistent", kw)
 
 
+def test_anaglyph_both_schedulers(torch_cuda):
+    """SURVEY.md 8(f4): `_draw_anaglyph` (frag.glsl:343-406, 467-473) -- two full traces per sample, combined red / cyan;
+    grayscale and colourful mode, with AA, one-thread-per-pixel and persistent schedulers, bit-exact against the oracle."""
+    from portal_b200.renderer import camera_scale
+    scene = "monoportal"
+    orc = _oracle(scene)
+    w, h = 320, 180
+    for mode, aa in ((0, 1), (1, 3)):
+        for persistent in (False, True):
+            r = _renderer(scene, persistent=persistent)
+            r.draw_anaglyph, r.anaglyph_mode, r.aa_count = True, bool(mode), aa
+            r.anaglyph_p, r.anaglyph_q = 0.31, 0.07
+            left, right = r.eye_matrices()
+            img = r.render_host(w, h)
+            ref = orc.render(w, h, DEPTH[scene], aa_count=aa, draw_anaglyph=1, anaglyph_mode=mode, anaglyph_p=0.31, anaglyph_q=0.07,
+                             camera_left_eye=left, camera_right_eye=right, left_eye_scale=camera_scale(left),
+                             right_eye_scale=camera_scale(right))
+            assert np.array_equal(_bits(img), _bits(ref)), (mode, aa, persistent)
+            assert np.abs(img[..., 0] - img[..., 1]).max() > 0.05        # red and cyan carry different eyes
+
+
 def test_external_ray_probe(torch_cuda):
     """the camera-teleportation probe against the oracle's restatement of frag.glsl:209-257."""
     for scene, segs in (("portal_in_portal", [([0, 0, -0.5], [0, 0, -1.5]), ([0, 0, 0.5], [0, 0, 0.2]), ([0.1, 0.05, -0.9], [0.12, 0.02, -1.3]),
@@ -355,6 +376,39 @@ def test_rgba8_readback_and_motion_blur_average(torch_cuda):
     assert r._lib.pe_average_frames_rgba8(r._ctx, ptrs, 5, out.data_ptr(), 90 * 160, None) == 0
     r.sync()
     assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_streaming_kernels_ragged_and_unaligned(torch_cuda):
+    """pe_k_quantize_rgba8 / pe_k_average_rgba8 move 4 pixels per thread with 16-byte accesses; pixel counts that are
+    not a multiple of 4, sub-frame counts around the 4-way unroll and buffers that are only pixel-aligned (the scalar
+    kernels) give the same bytes as the numpy restatement, and nothing is written past the end."""
+    torch = torch_cuda
+    import ctypes as C
+    r = _renderer("basics")
+    rng = np.random.default_rng(11)
+    for n, off in ((1, 0), (3, 0), (4, 0), (4099, 0), (4098, 1), (40003, 3)):
+        x = (rng.random((n + off + 8, 4), dtype=np.float32) * 1.4 - 0.2)
+        x[min(2, n - 1) + off, 1] = np.nan
+        src = torch.from_numpy(x).cuda()
+        dst = torch.full((n + off + 8, 4), 7, dtype=torch.uint8, device="cuda")
+        assert r._lib.pe_quantize_rgba8(r._ctx, src.data_ptr() + 16 * off, dst.data_ptr() + 4 * off, n, None) == 0
+        r.sync()
+        want = np.rint(np.fmin(np.fmax(x[off:off + n], np.float32(0)), np.float32(1)) * np.float32(255)).astype(np.uint8)
+        got = dst.cpu().numpy()
+        assert np.array_equal(got[off:off + n], want), (n, off)
+        assert (got[:off] == 7).all() and (got[off + n:] == 7).all(), (n, off)
+        for nf in (1, 3, 4, 6, 9):
+            fr = rng.integers(0, 256, size=(nf, n + off + 8, 4), dtype=np.uint8)
+            dev = [torch.from_numpy(f).cuda() for f in fr]
+            ptrs = (C.c_void_p * nf)(*[d.data_ptr() + 4 * off for d in dev])
+            out = torch.full((n + off + 8, 4), 7, dtype=torch.uint8, device="cuda")
+            assert r._lib.pe_average_frames_rgba8(r._ctx, ptrs, nf, out.data_ptr() + 4 * off, n, None) == 0
+            r.sync()
+            acc = (fr[:, off:off + n, :3].astype(np.uint32) ** 2).sum(axis=0) // nf
+            want = np.concatenate([(np.sqrt(acc.astype(np.float32)) + np.float32(0.5)).astype(np.uint8), np.full((n, 1), 255, np.uint8)], axis=-1)
+            got = out.cpu().numpy()
+            assert np.array_equal(got[off:off + n], want), (n, off, nf)
+            assert (got[:off] == 7).all() and (got[off + n:] == 7).all(), (n, off, nf)
 
 
 def test_full_size_properties(torch_cuda):
