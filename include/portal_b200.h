@@ -103,8 +103,9 @@ PE_API int pe_scene_uniform_block(pe_ctx* ctx, int width, int height, const void
  * rejected, same pixels), "with_probe" (0/1, default 0: also generate the camera-teleportation probe kernel; pe_probe_ray
  * switches it on by itself), "adaptive" (0/1, default 1: an int uniform or a matrix structure that differed between
  * renders more than 4 times stops being a specialisation constant, which bounds recompilation when an animation
- * drives it), "uniforms_in_smem" (0/1, default 0: every block stages the uniform block in shared memory and reads it
- * from there instead of the constant bank -- same pixels; an experiment), "lineinfo" (0/1, default 1), "unroll_loops" (0/1, default 1; 0 keeps the loops of
+ * drives it), "uniforms_in_smem" (0 = constant bank (default), 1 = every block copies the uniform block into
+ * shared memory with a cooperative loop, 2 = with one TMA bulk copy + mbarrier; same pixels, measured in DESIGN.md section 3),
+ * "tile_w" (8 / 16 / 32: a warp covers 8x4, 16x2 or 32x1 pixels -- longer contiguous stores for peer-mapped targets), "lineinfo" (0/1, default 1), "unroll_loops" (0/1, default 1; 0 keeps the loops of
  * user snippets rolled).  Set before pe_scene_compile. */
 PE_API int pe_set_option(pe_ctx* ctx, const char* key, int value);
 
@@ -138,6 +139,8 @@ PE_API size_t pe_target_pixels(const pe_target* t);
  * shader writes to FragColor, src/frag.glsl:526,551, before the render target quantises it).
  * `stream` is a cudaStream_t or NULL for the context's own stream.  `out_device` may be a
  * peer-mapped pointer (see pe_ipc_*). `bounces_device` (int32 per pixel) may be NULL. */
+/* A context has ONE uniform block and ONE tile-queue counter on the device: renders of one context must be issued on one
+ * stream at a time (different contexts are independent).  A target with n_strips == 0 renders nothing and succeeds. */
 PE_API int pe_render(pe_ctx* ctx, const pe_target* target, void* out_device, void* bounces_device, void* stream);
 /* Synchronous render into HOST memory, device->host copy included (float RGBA). */
 PE_API int pe_render_host(pe_ctx* ctx, const pe_target* target, float* out_host);
@@ -201,6 +204,40 @@ PE_API int pe_memset_u32(pe_ctx* ctx, void* device_ptr, uint32_t value, size_t c
 PE_API int pe_ipc_export(pe_ctx* ctx, void* device_ptr, uint8_t handle_out[64]);
 PE_API int pe_ipc_open(pe_ctx* ctx, const uint8_t handle_in[64], void** device_ptr_out);
 PE_API int pe_ipc_close(pe_ctx* ctx, void* device_ptr);
+
+/* ---- sharded frames behind the C ABI --------------------------------------
+ * One process per GPU, all on one box; the ranks rendezvous through the POSIX shared-memory segment /dev/shm/<name>
+ * (no collective library).  Every rank calls pe_sharder_create with the same name / geometry / mode / format and its
+ * own rank; rank 0 creates the segment.  Uniforms are set on the context as usual before each render / submit.
+ *   PE_SHARD_OWNER  each rank keeps the strips it renders in its own HBM (compact rows: pe_sharder_target); nothing moves.
+ *   PE_SHARD_P2P    every rank's render kernel stores its pixels straight into rank 0's whole frame over NVLink (CUDA
+ *                   IPC mapping); frame completion / buffer reuse are stream-ordered flag words.  After
+ *                   pe_sharder_render on rank 0, work enqueued on `stream` sees the assembled frame (*frame_out); once
+ *                   the consumer is enqueued, pe_sharder_release lets the other ranks reuse the buffer 2 frames later.
+ *   PE_SHARD_HOST   RGBA8 strips go over each GPU's own PCIe link into one shared page-locked host frame (ring of
+ *                   PE_HOST_RING_DEPTH): submit -> complete on every rank; wait_frame / release_frame on rank 0. */
+typedef struct pe_sharder pe_sharder;
+enum { PE_SHARD_OWNER = 0, PE_SHARD_P2P = 1, PE_SHARD_HOST = 2 };
+enum { PE_FRAME_F32 = 0, PE_FRAME_RGBA8 = 1 };
+#define PE_HOST_RING_DEPTH 3
+/* Cyclic strip layout: rank r of `world` owns global strips r, r + world, ... */
+PE_API int pe_shard_target(int width, int height, int rank, int world, int strip_rows, int full_frame_layout, pe_target* out);
+/* On failure *out may still hold an object: read pe_sharder_last_error, then pe_sharder_destroy it. */
+PE_API int pe_sharder_create(pe_ctx* ctx, const char* name, int width, int height, int rank, int world, int strip_rows,
+                             int mode, int format, pe_sharder** out);
+PE_API void pe_sharder_destroy(pe_sharder* s);
+PE_API const char* pe_sharder_last_error(pe_sharder* s);
+PE_API int pe_sharder_target(pe_sharder* s, pe_target* out);
+/* OWNER / P2P: enqueue this rank's strips of the next frame on `stream` (asynchronous).  *frame_out: OWNER -- this rank's
+ * compact strips (device); P2P -- on rank 0 the assembled frame (device), NULL elsewhere. */
+PE_API int pe_sharder_render(pe_sharder* s, void* stream, void** frame_out);
+PE_API int pe_sharder_release(pe_sharder* s, void* stream);
+/* HOST: queue this rank's strips of the next frame (returns its number); block until they are in host memory and publish;
+ * rank 0: block until every rank's strips of a frame have landed (*frame = the whole RGBA8 frame); give its slot back. */
+PE_API int pe_sharder_submit(pe_sharder* s, uint64_t* frame_no);
+PE_API int pe_sharder_complete(pe_sharder* s, uint64_t frame_no);
+PE_API int pe_sharder_wait_frame(pe_sharder* s, uint64_t frame_no, const uint8_t** frame);
+PE_API int pe_sharder_release_frame(pe_sharder* s, uint64_t frame_no);
 
 /* ---- frame post-processing (the offline `render` caller, src/main.rs:640-722) -------------- */
 

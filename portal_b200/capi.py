@@ -104,6 +104,17 @@ def lib() -> C.CDLL:
         "pe_ipc_close": (i32, [vp, vp]),
         "pe_average_frames_rgba8": (i32, [vp, C.POINTER(vp), i32, vp, C.c_size_t, vp]),
         "pe_quantize_rgba8": (i32, [vp, vp, vp, C.c_size_t, vp]),
+        "pe_shard_target": (i32, [i32, i32, i32, i32, i32, i32, C.POINTER(PeTarget)]),
+        "pe_sharder_create": (i32, [vp, cp, i32, i32, i32, i32, i32, i32, i32, C.POINTER(vp)]),
+        "pe_sharder_destroy": (None, [vp]),
+        "pe_sharder_last_error": (cp, [vp]),
+        "pe_sharder_target": (i32, [vp, C.POINTER(PeTarget)]),
+        "pe_sharder_render": (i32, [vp, vp, C.POINTER(vp)]),
+        "pe_sharder_release": (i32, [vp, vp]),
+        "pe_sharder_submit": (i32, [vp, C.POINTER(C.c_uint64)]),
+        "pe_sharder_complete": (i32, [vp, C.c_uint64]),
+        "pe_sharder_wait_frame": (i32, [vp, C.c_uint64, C.POINTER(vp)]),
+        "pe_sharder_release_frame": (i32, [vp, C.c_uint64]),
     }
     f64p = C.POINTER(C.c_double)
     sig.update({

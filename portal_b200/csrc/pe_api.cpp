@@ -25,6 +25,7 @@
 #include "../../include/portal_b200.h"
 #include "pe_codegen.h"
 #include "pe_driver.h"
+#include "pe_internal.h"
 #include "pe_kernels.h"
 
 using namespace pe_host;
@@ -301,7 +302,7 @@ std::vector<int> variant_key(pe_ctx* c, const std::vector<int>& ints, const std:
 }
 
 // NVRTC: source -> sm_100a cubin (disk-cached by content hash).
-bool compile_cubin(pe_ctx* c, const std::string& source, std::vector<char>& cubin) {
+bool compile_cubin(pe_ctx* c, const std::string& source, std::vector<char>& cubin, bool force_recompile = false) {
     std::vector<std::string> o = {"--gpu-architecture=sm_100a", "--std=c++20", "-default-device", "--fmad=false",
                                   "--prec-div=true", "--prec-sqrt=true", "--ftz=false"};
     if (c->lineinfo) o.push_back("-lineinfo");
@@ -318,7 +319,19 @@ bool compile_cubin(pe_ctx* c, const std::string& source, std::vector<char>& cubi
         std::ifstream f(path, std::ios::binary);
         if (f) {
             cubin.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
-            if (!cubin.empty()) return true;
+            // a truncated copy (interrupted transfer to the GPU box) must not be trusted: ELF magic + section table inside the file
+            bool ok = cubin.size() > 64 && std::memcmp(cubin.data(), "\x7f" "ELF", 4) == 0;
+            if (ok) {
+                uint64_t shoff = 0;
+                uint16_t shentsize = 0, shnum = 0;
+                std::memcpy(&shoff, cubin.data() + 0x28, 8);
+                std::memcpy(&shentsize, cubin.data() + 0x3a, 2);
+                std::memcpy(&shnum, cubin.data() + 0x3c, 2);
+                ok = shoff + uint64_t(shentsize) * shnum <= cubin.size();
+            }
+            if (ok && !force_recompile) return true;
+            cubin.clear();
+            std::remove(path.c_str());
         }
     }
     nvrtcProgram prog;
@@ -406,6 +419,11 @@ bool select_variant(pe_ctx* c) {
     if (c->has_gpu && !v->module) {
         const DriverApi* d = c->drv;
         CUresult_t r = d->cuModuleLoadData(&v->module, v->cubin.data());
+        if (r != 0) {
+            // a cached cubin the driver rejects (corrupt file, other driver generation): evict it and compile once more
+            if (!compile_cubin(c, v->source, v->cubin, true)) return false;
+            r = d->cuModuleLoadData(&v->module, v->cubin.data());
+        }
         if (r != 0) { c->err = "cuModuleLoadData: " + driver_error(d, r); return false; }
         r = d->cuModuleGetFunction(&v->kernel, v->module, "pe_render_kernel");
         if (r != 0) { c->err = "cuModuleGetFunction(pe_render_kernel): " + driver_error(d, r); return false; }
@@ -435,14 +453,15 @@ bool bind_device(pe_ctx* c) {
 }
 
 bool check_target(pe_ctx* c, const pe_target* t) {
-    if (!t || t->width <= 0 || t->height <= 0 || t->strip_rows <= 0 || t->strip_step <= 0 || t->n_strips <= 0 ||
+    // n_strips == 0 is legal: a rank that owns no strip (fewer strips than ranks); such a render launches nothing
+    if (!t || t->width <= 0 || t->height <= 0 || t->strip_rows <= 0 || t->strip_step <= 0 || t->n_strips < 0 ||
         t->strip_first < 0) {
         c->err = "invalid pe_target";
         return false;
     }
     // keep every index the kernel and the launch geometry compute inside 32 bits: frames up to 65536 x 65536, at most
     // 2^24 local rows, last global row of the last strip below 2^30
-    const long long last_strip = (long long)t->strip_first + (long long)(t->n_strips - 1) * (long long)t->strip_step;
+    const long long last_strip = (long long)t->strip_first + (long long)(t->n_strips > 0 ? t->n_strips - 1 : 0) * (long long)t->strip_step;
     if (t->width > 65536 || t->height > 65536 || (long long)t->n_strips * (long long)t->strip_rows > (1LL << 24) ||
         (last_strip + 1) * (long long)t->strip_rows > (1LL << 30)) {
         c->err = "invalid pe_target: frame or strip set too large";
@@ -453,9 +472,11 @@ bool check_target(pe_ctx* c, const pe_target* t) {
 
 }  // namespace
 
+int pe_internal_device(pe_ctx* c) { return (c && c->has_gpu) ? c->device : -1; }
+
 extern "C" {
 
-int pe_abi_version(void) { return 100; }
+int pe_abi_version(void) { return 101; }
 
 pe_ctx* pe_create(int device) {
     std::lock_guard<std::mutex> lk(g_create_mutex);
@@ -816,6 +837,7 @@ static int render_impl(pe_ctx* c, const pe_target* t, void* out_device, void* bo
     if (!c) return 1;
     if (!out_device) return c->fail("pe_render: out_device is null");
     if (!check_target(c, t) || !bind_device(c)) return 1;
+    if (t->n_strips == 0) return 0;   // nothing of this frame belongs to the caller
     ensure_layout(c);
     *fslot(c, c->layout.float_slot["_resolution_x"]) = float(t->width);
     *fslot(c, c->layout.float_slot["_resolution_y"]) = float(t->height);

@@ -208,6 +208,84 @@ class FrameSharder:
         self._owned = []
 
 
+class NativeSharder:
+    """The sharded-frame protocol of the C ABI (`pe_sharder_*`, include/portal_b200.h): one object per rank, the ranks of
+    a box rendezvous through /dev/shm/<name> -- no collective library.  Modes:
+      "owner"  every rank keeps its strips in its own HBM (render() -> device pointer of this rank's compact rows);
+      "p2p"    render kernels store straight into rank 0's frame over NVLink (render() -> assembled frame on rank 0);
+      "host"   RGBA8 strips over every GPU's own PCIe link into one shared pinned host frame (submit / complete /
+               wait_frame / release_frame).
+    This class only moves arguments across the boundary; uniforms are the renderer's (set_uniforms is called for you)."""
+
+    MODES = {"owner": 0, "p2p": 1, "host": 2}
+    FORMATS = {"f32": 0, "rgba8": 1}
+
+    def __init__(self, renderer, width: int, height: int, rank: int, world: int, mode: str, fmt: str = "f32",
+                 strip_rows: int = STRIP_ROWS, name: str | None = None):
+        self.r, self.w, self.h, self.rank, self.world, self.mode, self.fmt = renderer, width, height, rank, world, mode, fmt
+        self._lib = renderer._lib
+        self._s = C.c_void_p()
+        if name is None:
+            name = shm_name(f"{mode}_{fmt}")
+        rc = self._lib.pe_sharder_create(renderer._ctx, name.encode(), width, height, rank, world, strip_rows, self.MODES[mode],
+                                         self.FORMATS[fmt], C.byref(self._s))
+        if rc:
+            msg = self._lib.pe_sharder_last_error(self._s).decode(errors="replace") if self._s else "pe_sharder_create failed"
+            if self._s:
+                self._lib.pe_sharder_destroy(self._s)
+                self._s = C.c_void_p()
+            raise RuntimeError(msg)
+        self.target = PeTarget()
+        self._check(self._lib.pe_sharder_target(self._s, C.byref(self.target)))
+        self.frame_ptr = None
+
+    def _check(self, rc):
+        if rc:
+            raise RuntimeError(self._lib.pe_sharder_last_error(self._s).decode(errors="replace"))
+
+    def render(self, stream_ptr: int):
+        self.r.set_uniforms()
+        out = C.c_void_p()
+        self._check(self._lib.pe_sharder_render(self._s, stream_ptr or None, C.byref(out)))
+        self.frame_ptr = out.value
+        return out.value
+
+    def release(self, stream_ptr: int):
+        self._check(self._lib.pe_sharder_release(self._s, stream_ptr or None))
+
+    def submit(self) -> int:
+        self.r.set_uniforms()
+        f = C.c_uint64()
+        self._check(self._lib.pe_sharder_submit(self._s, C.byref(f)))
+        return f.value
+
+    def complete(self, f: int):
+        self._check(self._lib.pe_sharder_complete(self._s, f))
+
+    def wait_frame(self, f: int):
+        p = C.c_void_p()
+        self._check(self._lib.pe_sharder_wait_frame(self._s, f, C.byref(p)))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(self.h, self.w, 4))
+
+    def release_frame(self, f: int):
+        self._check(self._lib.pe_sharder_release_frame(self._s, f))
+
+    def close(self):
+        if self._s:
+            self._lib.pe_sharder_destroy(self._s)
+            self._s = C.c_void_p()
+
+
+_shm_counter = [0]
+
+
+def shm_name(tag: str) -> str:
+    """A segment name every rank of one launch derives alike: the launcher's rendezvous port + a per-process counter
+    (ranks create their sharders in the same order)."""
+    _shm_counter[0] += 1
+    return f"portal_b200_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}_{_shm_counter[0]}_{tag}"
+
+
 class gpu_numa_affinity:
     """Context manager: run the enclosed block on the CPUs NVML reports as local to CUDA device `device`
     (nvmlDeviceSetCpuAffinity), then restore the previous affinity.  Host pages allocated / first touched inside

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert exported <= set(declared), f"exported but undeclared: {sorted(exported - set(declared))}"
     for name in declared:
         assert getattr(lib, name)
-    assert lib.pe_abi_version() == 100
+    assert lib.pe_abi_version() == 101      # 1.01: pe_sharder_*, anaglyph uniforms, tile_w
 
 
 def test_library_is_built_for_sm_100a():
@@ -255,7 +255,8 @@ def test_target_validation():
         for world in (1, 2, 3, 8):
             for rank in range(world):
                 t = SceneRenderer.strip_target(w, h, 16, rank, world)
-                assert verdict(t) == ("valid" if t.n_strips > 0 else "invalid"), (w, h, rank, world)
+                assert verdict(t) == "valid", (w, h, rank, world)      # a rank that owns no strip (n_strips == 0) renders nothing
+    assert verdict(PeTarget(64, 64, 16, 0, 1, -1, 0)) == "invalid"
     assert verdict(PeTarget(2 ** 31 - 1, 2 ** 31 - 1, 1, 0, 1, 1, 1)) == "invalid"
     assert verdict(PeTarget(64, 64, 65536, 65535, 65536, 65536, 0)) == "invalid"
 
