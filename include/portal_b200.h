@@ -192,6 +192,10 @@ PE_API int pe_deinterleave_strips(pe_ctx* ctx, const void* gathered_device, void
 PE_API int pe_device_malloc(pe_ctx* ctx, size_t bytes, void** device_ptr_out);
 PE_API int pe_device_free(pe_ctx* ctx, void* device_ptr);
 PE_API int pe_memcpy_d2h(pe_ctx* ctx, void* host_dst, const void* device_src, size_t bytes, void* stream);
+/* Context-owned device scratch, slot 0..127: allocated on first use, grown (never shrunk) when a larger size is asked
+ * for, freed by pe_destroy.  For per-frame intermediates of a frame loop (motion-blur sub-frames): no cudaMalloc /
+ * cudaFree -- each a device-wide synchronisation -- inside the loop. */
+PE_API int pe_scratch_buffer(pe_ctx* ctx, int slot, size_t bytes, void** device_ptr_out);
 /* Stream-ordered cross-GPU signalling without a collective: pe_signal_u32 publishes `value` to up to 8
  * flag words (device pointers, local or peer-mapped) after everything earlier in the stream -- remote
  * stores of a render kernel included; pe_stream_wait_geq_u32 makes the stream wait until a LOCAL flag

@@ -85,6 +85,10 @@ typedef struct ph_frame_params {
     double look_at[3], alpha, beta, r;
 } ph_frame_params;
 PE_API int ph_render_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, void* out_host, int rgba8);
+/* The uniform half of render_frame alone (Scene::set_uniforms + SceneRenderer::set_uniforms for this frame's camera,
+ * src/main.rs:1266-1359, 1411-1420): evaluate the scene in float64, upload table + renderer uniforms into ctx.  What follows
+ * is the caller's choice of delivery: pe_render*, the pipelined pe_submit_host_rgba8, or a pe_sharder_* call. */
+PE_API int ph_frame_uniforms(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p);
 /* Same uniform setup, asynchronous render of a row-strip target into device memory. */
 PE_API int ph_render_target(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, const pe_target* target,
                             void* out_device, void* stream);

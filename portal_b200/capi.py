@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
         "pe_device_malloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),
         "pe_device_free": (i32, [vp, vp]),
         "pe_memcpy_d2h": (i32, [vp, vp, vp, C.c_size_t, vp]),
+        "pe_scratch_buffer": (i32, [vp, i32, C.c_size_t, C.POINTER(vp)]),
         "pe_signal_u32": (i32, [vp, C.POINTER(vp), i32, C.c_uint32, vp]),
         "pe_stream_wait_geq_u32": (i32, [vp, vp, C.c_uint32, vp]),
         "pe_memset_u32": (i32, [vp, vp, C.c_uint32, C.c_size_t, vp]),
@@ -136,6 +137,7 @@ def lib() -> C.CDLL:
         "ph_orbit_camera_matrix": (None, [f64p, C.c_double, C.c_double, C.c_double, f64p]),
         "ph_camera_scale": (C.c_double, [f64p]),
         "ph_render_frame": (i32, [vp, vp, C.POINTER(PhFrameParams), vp, i32]),
+        "ph_frame_uniforms": (i32, [vp, vp, C.POINTER(PhFrameParams)]),
         "ph_render_target": (i32, [vp, vp, C.POINTER(PhFrameParams), C.POINTER(PeTarget), vp, vp]),
         "ph_render_motion_blur_frame": (i32, [vp, vp, C.POINTER(PhFrameParams), i32, i32, i32, C.c_double, vp]),
         "ph_player_new": (vp, [vp]),

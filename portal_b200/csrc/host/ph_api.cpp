@@ -285,6 +285,11 @@ int ph_render_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, void* ou
     return 0;
 }
 
+int ph_frame_uniforms(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p) {
+    if (!s || !ctx || !p) return 1;
+    return upload_frame_uniforms(s, ctx, p);
+}
+
 int ph_render_target(ph_scene* s, pe_ctx* ctx, const ph_frame_params* p, const pe_target* target, void* out_device, void* stream) {
     if (!s || !ctx || !p || !target || !out_device) return 1;
     if (upload_frame_uniforms(s, ctx, p)) return 1;
@@ -299,10 +304,11 @@ int ph_render_motion_blur_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params*
         p->width > 65536 || p->height > 65536)
         return fail(s, "ph_render_motion_blur_frame: bad frame arguments");
     const size_t n = size_t(p->width) * size_t(p->height);
+    // sub-frame and output buffers are the context's scratch slots: allocated once, reused by every frame of the loop
     void* out8 = nullptr;
     std::vector<void*> sub(size_t(motion_blur_frames), nullptr);
-    int rc = pe_device_malloc(ctx, n * 4, &out8);
-    for (auto& b : sub) rc |= pe_device_malloc(ctx, n * 4, &b);
+    int rc = pe_scratch_buffer(ctx, 0, n * 4, &out8);
+    for (size_t j = 0; j < sub.size(); j++) rc |= pe_scratch_buffer(ctx, 1 + int(j), n * 4, &sub[j]);
     const double saved_time = s->scene.time, saved_total = s->scene.total_time;
     if (!rc) {
         pe_target t = {p->width, p->height, p->height, 0, 1, 1, 1};
@@ -323,10 +329,7 @@ int ph_render_motion_blur_frame(ph_scene* s, pe_ctx* ctx, const ph_frame_params*
         s->err = std::string("device allocation failed: ") + pe_last_error(ctx);
     }
     ph_scene_set_time(s, saved_time, saved_total);
-    pe_sync(ctx);
-    if (out8) pe_device_free(ctx, out8);
-    for (auto& b : sub) if (b) pe_device_free(ctx, b);
-    return rc ? 1 : 0;
+    return rc ? 1 : 0;      // pe_memcpy_d2h has synchronised the stream: the frame is in out_host
 }
 
 // ------------------------------------------------------------------------------------ player
@@ -523,8 +526,8 @@ int ph_player_render_motion_blur_frame(ph_player* pl, pe_ctx* ctx, const ph_fram
     const size_t n = size_t(p->width) * size_t(p->height);
     void* out8 = nullptr;
     std::vector<void*> sub(size_t(motion_blur_frames), nullptr);
-    int rc = pe_device_malloc(ctx, n * 4, &out8);
-    for (auto& b : sub) rc |= pe_device_malloc(ctx, n * 4, &b);
+    int rc = pe_scratch_buffer(ctx, 0, n * 4, &out8);
+    for (size_t j = 0; j < sub.size(); j++) rc |= pe_scratch_buffer(ctx, 1 + int(j), n * 4, &sub[j]);
     if (rc) pl->err = std::string("device allocation failed: ") + pe_last_error(ctx);
     pe_target t = {p->width, p->height, p->height, 0, 1, 1, 1};
     const double exposure = 0.5;  // main.rs:1787
@@ -548,9 +551,6 @@ int ph_player_render_motion_blur_frame(ph_player* pl, pe_ctx* ctx, const ph_fram
         pl->err = std::string("motion-blur average failed: ") + pe_last_error(ctx);
         rc = 1;
     }
-    pe_sync(ctx);
-    if (out8) pe_device_free(ctx, out8);
-    for (auto& b : sub) if (b) pe_device_free(ctx, b);
     return rc ? 1 : 0;
 }
 

@@ -131,6 +131,8 @@ struct pe_ctx {
     size_t scratch8_bytes = 0;
     uint64_t launches = 0;
     const DriverApi* drv = nullptr;
+    struct Scratch { void* dev = nullptr; size_t bytes = 0; };
+    std::map<int, Scratch> user_scratch;   // pe_scratch_buffer
 
     int fail(const std::string& m, int code = 1) {
         err = m;
@@ -532,6 +534,8 @@ void pe_destroy(pe_ctx* c) {
             if (sl.rendered) cudaEventDestroy(sl.rendered);
             if (sl.copied) cudaEventDestroy(sl.copied);
         }
+        for (auto& kv : c->user_scratch)
+            if (kv.second.dev) cudaFree(kv.second.dev);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         if (c->queue_dev) cudaFree(c->queue_dev);
         if (c->stream) cudaStreamDestroy(c->stream);
@@ -1103,6 +1107,20 @@ int pe_device_free(pe_ctx* c, void* p) {
     if (!c || !p) return 1;
     if (!bind_device(c)) return 1;
     return cuda_ok(c, cudaFree(p), "cudaFree") ? 0 : 1;
+}
+
+int pe_scratch_buffer(pe_ctx* c, int slot, size_t bytes, void** out) {
+    if (!c || !out || slot < 0 || slot >= 128) return c ? c->fail("pe_scratch_buffer: bad arguments") : 1;
+    if (!bind_device(c)) return 1;
+    auto& s = c->user_scratch[slot];
+    if (s.bytes < bytes) {
+        // growing frees the old block: make sure nothing queued still uses it
+        if (s.dev) { cudaDeviceSynchronize(); cudaFree(s.dev); s.dev = nullptr; s.bytes = 0; }
+        if (!cuda_ok(c, cudaMalloc(&s.dev, bytes), "cudaMalloc(scratch)")) return 1;
+        s.bytes = bytes;
+    }
+    *out = s.dev;
+    return 0;
 }
 
 int pe_memcpy_d2h(pe_ctx* c, void* dst, const void* src, size_t bytes, void* stream) {

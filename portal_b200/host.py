@@ -219,13 +219,17 @@ class HostPlayer:
 class HostRenderer:
     """SceneRenderer::new + render_frame over the C API only (no scene IR involved)."""
 
-    def __init__(self, scene: HostScene, device: int = 0, textures: dict | None = None, persistent: bool = False):
+    def __init__(self, scene: HostScene, device: int = 0, textures: dict | None = None, persistent: bool = False,
+                 options: dict | None = None):
         self.scene = scene
+        self.device = device
         self._lib = capi.lib()
         self._ctx = self._lib.pe_create(device)
         if not self._ctx:
             raise PortalB200Error("pe_create failed: " + self._lib.pe_last_error(None).decode())
         self._pe(self._lib.pe_set_option(self._ctx, b"persistent", int(persistent)))
+        for k, v in (options or {}).items():
+            self._pe(self._lib.pe_set_option(self._ctx, b(k), int(v)))
         scene._check(self._lib.ph_scene_build_program(scene._s, self._ctx))
         scene._check(self._lib.ph_scene_upload_uniforms(scene._s, self._ctx))
         for name, arr in (textures or {}).items():
@@ -262,6 +266,26 @@ class HostRenderer:
 
     def sync(self):
         self._pe(self._lib.pe_sync(self._ctx))
+
+    def frame_uniforms(self, width, height, depth, aa_count=1, aa_start=0, camera=None):
+        """ph_frame_uniforms: the per-frame host work of render_frame (float64 scene evaluation + uniform upload) without
+        a render; follow with pe_render* / pe_submit_host_rgba8 / a sharder call on self._ctx."""
+        p = PhFrameParams(width, height, depth, aa_count, aa_start, 0)
+        if camera is not None:
+            p.use_camera = 1
+            p.look_at = (C.c_double * 3)(*camera["look_at"])
+            p.alpha, p.beta, p.r = camera["alpha"], camera["beta"], camera["r"]
+        self.scene._check(self._lib.ph_frame_uniforms(self.scene._s, self._ctx, C.byref(p)))
+
+    # the renderer-facing names NativeSharder and the bench use on SceneRenderer exist here too
+    def _check(self, rc):
+        self._pe(rc)
+
+    def set_uniforms(self):
+        pass            # uniforms are uploaded by frame_uniforms()
+
+    def launch_count(self) -> int:
+        return int(self._lib.pe_launch_count(self._ctx))
 
     def render_motion_blur_frame(self, width, height, depth, frame_index, frame_count, motion_blur_frames, duration_seconds,
                                  aa_count=1) -> np.ndarray:
