@@ -1,22 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- Mpixels/s of the portal ray loop on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scene S] [--orbit N]
+                    [--mode owner|p2p|gather] [--format f32|rgba8] [--frontend ron|ir]
 
-A "step" is one frame of the headline workload (portal_in_portal, 3840x2160, depth 40, saved
-camera, aa 1): uniform upload + ONE launch of the scene's sm_100a ray-loop kernel (+ for N > 1 the
-NCCL gather of the row strips and the de-interleave kernel on rank 0).  `value` is timed with CUDA
-events on the launching stream with the scene resident on the GPU; `e2e` goes through the
-reference-facing call (render_frame's product: RGBA8 pixels in HOST memory) and includes the
-host->device uniform upload and the device->host readback every step.
-`--impl reference` times the CPU oracle (oracle/, the restatement of the reference's GLSL path --
-the reference has no CPU implementation and cannot be built here) on the host
-cores, on a bounded sample of the same frame.
+A "step" is one frame of the workload (default: the headline config, portal_in_portal.ron 3840x2160 depth 40, saved
+camera, aa 1): uniform-block upload + ONE launch of the scene's sm_100a ray-loop kernel per GPU.
+  value   frames timed with CUDA events on the launching stream, scene resident on the GPU(s), float RGBA frames.
+          N > 1: the frame is sharded by cyclic 16-row strips (`pe_sharder_*`, C ABI); default mode "owner" -- every rank's
+          strips stay in the HBM of the GPU that rendered them (what a consumer then pulls); "p2p" -- every kernel stores
+          into rank 0's frame over NVLink; "gather" -- ONE NCCL gather + de-interleave (what north_star names).  The
+          rank-0-assembled rates are measured too and reported under `assembled`.
+  e2e     the reference-facing call: scene file -> the product's own host front-end (`ph_scene_*`, C++) -> per frame
+          float64 scene evaluation + uniform upload (`ph_frame_uniforms`) -> render -> RGBA8 frame in HOST memory
+          (`pe_submit_host_rgba8` / `pe_wait_host`; N > 1: `pe_sharder_*` host delivery over every GPU's own PCIe link).
+  parity  sha256 of the frames the timed loops produced (value: the last float frame, gathered from the ranks with one
+          NCCL gather when N > 1; e2e: the last RGBA8 host frame) against tests/golden/fullsize_sha256.json -- the CPU
+          oracle's frames at the full BASELINE.json sizes.
+`--impl reference` times the CPU oracle (oracle/, the restatement of the reference's GLSL path -- the reference has no CPU
+implementation and cannot be built here) on the host cores, in a clean subprocess
+(oracle/bench_cpu.py), on a bounded sample of the same frame; `cpu_baseline` of the default arm is the same measurement.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import math
 import os
@@ -29,6 +38,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 SCENE_DIR = os.path.join(ROOT, "tests", "golden", "scenes")
+RON_DIR = os.path.join(ROOT, "tests", "golden", "ron")
 WORKLOADS = {  # BASELINE.json configs
     "portal_in_portal": (3840, 2160, 40),
     "triple_portal": (3840, 2160, 40),
@@ -37,11 +47,16 @@ WORKLOADS = {  # BASELINE.json configs
     "basics": (256, 256, 4),
 }
 STRIP_ROWS = 16
-METRIC = "Mpixels/s @ 3840x2160 depth-40 portal_in_portal"  # BASELINE.json metric (headline workload)
 
 
 def metric_name(scene, w, h, depth):
     return f"Mpixels/s @ {w}x{h} depth-{depth} {scene}"
+
+
+def workload_name(args):
+    """One string for both arms (the driver compares them)."""
+    return (f"{args.scene}.ron {args.width}x{args.height} depth {args.depth}, " +
+            (f"{args.orbit}-frame camera orbit" if args.orbit else "saved camera") + ", aa 1")
 
 
 def load_ir(scene):
@@ -55,6 +70,24 @@ def measured_peaks():
         with open(p) as f:
             return json.load(f), "measured (MEASURED_PEAKS.json)"
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def golden_pins(scene, w, h, depth, orbit=0, k=None):
+    """sha256 pins of the oracle's frame for this workload (tests/golden/fullsize_sha256.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "fullsize_sha256.json")) as f:
+            rec = json.load(f).get(scene)
+    except OSError:
+        return None
+    if not rec:
+        return None
+    if (rec["width"], rec["height"], rec["depth"]) != (w, h, depth):
+        rec = rec.get(f"{w}x{h}")
+        if not rec or rec.get("depth") != depth:
+            return None
+    if orbit:
+        return rec.get(f"orbit_{orbit}", {}).get(str(k))
+    return rec
 
 
 class ClockSampler:
@@ -116,53 +149,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def usable_cores() -> int:
-    """Host threads this process may really use: CPU affinity capped by the cgroup CPU quota (a container
-    can report 128 CPUs and be throttled to a few)."""
-    try:
-        n = len(os.sched_getaffinity(0))
-    except Exception:
-        n = os.cpu_count() or 1
-    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
-        try:
-            txt = open(path).read().split()
-            if path.endswith("cpu.max"):
-                if txt[0] != "max":
-                    n = min(n, max(1, int(math.ceil(int(txt[0]) / int(txt[1])))))
-            else:
-                q = int(txt[0])
-                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
-                if q > 0:
-                    n = min(n, max(1, int(math.ceil(q / per))))
-            break
-        except Exception:
-            continue
-    return n
-
-
 # ------------------------------------------------------------------------------ CPU oracle legs
-def cpu_oracle_rate(scene, w, h, depth, budget_s=20.0, threads=0):
-    """Mpx/s of the oracle's fast build on a bounded sample: bands of 16 rows spread over the frame."""
-    from oracle import runner
-    tex = runner.load_texture_npz(os.path.join(SCENE_DIR, f"{scene}.textures.npz"))
-    orc = runner.Oracle(load_ir(scene), "fast", textures=tex)
-    cores = threads or usable_cores()
-    n_bands = 4
-    t0 = time.perf_counter()
-    B = min(64, h)
-    orc.render(w, h, depth, rows=(h // 2, min(h, h // 2 + B)), threads=cores)  # warm up the thread pool
-    t0 = time.perf_counter()
-    orc.render(w, h, depth, rows=(h // 2, min(h, h // 2 + B)), threads=cores)  # calibrate
-    per_band = max(time.perf_counter() - t0, 1e-4)
-    n_bands = int(max(2, min(h // B, budget_s / per_band)))
-    starts = [int(i * (h - B) / max(n_bands - 1, 1)) for i in range(n_bands)]
-    t0 = time.perf_counter()
-    px = 0
-    for s in starts:
-        orc.render(w, h, depth, rows=(s, s + B), threads=cores)
-        px += B * w
-    dt = time.perf_counter() - t0
-    return px / dt / 1e6, cores, f"{n_bands} bands x {B} rows of the {w}x{h} frame ({px} px, {dt:.1f} s, OpenMP over 64-pixel runs)"
+def cpu_oracle(args, budget_s, steps=1, warmup=1, threads=0):
+    """The oracle's fast build on a bounded sample of the frame, in a CLEAN subprocess (oracle/bench_cpu.py resets the CPU
+    affinity and the OpenMP environment that torchrun narrows).  Returns the parsed JSON line."""
+    env = {k: v for k, v in os.environ.items() if not (k.startswith(("OMP_", "KMP_", "GOMP_", "MKL_")) or k == "PORTAL_B200_BENCH_CPU_REEXEC")}
+    cmd = [sys.executable, "-m", "oracle.bench_cpu", "--scene", args.scene, "--width", str(args.width), "--height", str(args.height),
+           "--depth", str(args.depth), "--budget", str(budget_s), "--steps", str(steps), "--warmup", str(warmup), "--threads", str(threads)]
+    p = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    if p.returncode != 0:
+        raise RuntimeError("oracle.bench_cpu failed: " + (p.stderr or p.stdout)[-2000:])
+    return json.loads(p.stdout.strip().splitlines()[-1])
 
 
 def run_reference(args):
@@ -170,32 +167,31 @@ def run_reference(args):
     if rank != 0:
         return
     w, h, depth = args.width, args.height, args.depth
-    rates = []
-    for _ in range(min(args.warmup, 3)):
-        cpu_oracle_rate(args.scene, w, h, depth, budget_s=0.5)
     t0 = time.perf_counter()
-    sample = ""
-    for _ in range(args.steps):
-        # bounded sample per step: the whole arm stays around 1.5 minutes whatever --steps is
-        r, cores, sample = cpu_oracle_rate(args.scene, w, h, depth, budget_s=min(20.0, max(0.25, 90.0 / max(args.steps, 1))))
-        rates.append(r)
+    res = cpu_oracle(args, budget_s=60.0, steps=args.steps, warmup=min(max(args.warmup, 1), 3))
     dt = time.perf_counter() - t0
-    v = sum(rates) / len(rates)
+    v = res["value"]
     print(json.dumps({
         "impl": "reference", "metric": metric_name(args.scene, w, h, depth), "value": round(v, 4), "unit": "Mpixels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(w * h / (v * 1e6) * 1e3, 3),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, " + (f"{args.orbit}-frame camera orbit" if args.orbit else "saved camera") + ", aa 1"},
-        "cpu_baseline": {"value": round(v, 4), "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args)},
+        "cpu_baseline": {"value": round(v, 4), "unit": "Mpixels/s", "cores": res["threads_used"], "kind": "port", "sample": res["sample"]},
         "e2e": {"value": round(v, 4), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": f"CPU oracle (restatement of the reference's GLSL path; the reference itself has no CPU path); wall {dt:.1f} s",
+        "note": f"CPU oracle (restatement of the reference's GLSL path; the reference itself has no CPU path), clean subprocess; wall {dt:.1f} s",
     }))
 
 
 # ------------------------------------------------------------------------------ our arm
+def sha(buf) -> str:
+    return hashlib.sha256(memoryview(buf).cast("B")).hexdigest()
+
+
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
+    from portal_b200 import distributed as D
     from portal_b200.renderer import SceneRenderer, load_textures
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -205,84 +201,110 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w, h, depth = args.width, args.height, args.depth
-    ir = load_ir(args.scene)
-    r = SceneRenderer(ir, textures=load_textures(os.path.join(SCENE_DIR, f"{args.scene}.textures.npz")), device=local,
-                      persistent=bool(args.persistent))
-    r.render_depth = depth
+    textures = load_textures(os.path.join(SCENE_DIR, f"{args.scene}.textures.npz"))
+    options = {}
+    if args.tile_w:
+        options["tile_w"] = args.tile_w
     stream = torch.cuda.Stream()          # a real (non-NULL) stream: NULL means "the context's own stream" to the C ABI
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
     assert sptr != 0
 
-    from portal_b200.distributed import FrameSharder, STRIP_ROWS as SR
-    mode = args.mode if world > 1 else "gather"
-    if world > 1 and mode == "gather":
-        args.format = "f32"                      # the NCCL gather path assembles float frames
-    if world == 1:
-        target = r.full_target(w, h)
-        # ring of output frames larger than the 126 MB L2: 2 float frames (265 MB at 4K) or 6 RGBA8 frames (199 MB)
-        n_outs = 2 if args.format == "f32" else 6
-        outs = [torch.empty((h, w, 4), dtype=torch.float32 if args.format == "f32" else torch.uint8, device="cuda") for _ in range(n_outs)]
-        sharder = None
+    # ---- the scene: `ron` = the product's own host front-end (RON text -> ph_scene_* -> pe_*), `ir` = the JSON scene IR
+    if args.frontend == "ron":
+        from portal_b200.host import HostRenderer, HostScene
+        hscene = HostScene.from_file(os.path.join(RON_DIR, f"{args.scene}.ron"))
+        r = HostRenderer(hscene, device=local, textures=textures, persistent=bool(args.persistent), options=options)
+        cam0 = hscene.camera()
+
+        def frame_uniforms(k=None):
+            cam = None
+            if k is not None:
+                cam = dict(cam0, alpha=cam0["alpha"] + 2.0 * math.pi * k / args.orbit)
+            r.frame_uniforms(w, h, depth, camera=cam)
     else:
-        # default for N > 1: the render kernels store straight into rank 0's frame over NVLink (CUDA IPC).
-        # If the box cannot map peer memory between processes, every rank agrees to use the NCCL gather
-        # instead (both are GPU paths; the mode actually used is reported in `config.parallelism`).
-        sharder, ok = None, 1
-        try:
-            sharder = FrameSharder(r, w, h, rank, world, mode=mode, strip_rows=SR, fmt=args.format)
-        except Exception as e:  # noqa: BLE001
-            ok = 0
-            print(f"[bench] rank {rank}: {mode} set-up failed ({e}); falling back to gather", file=sys.stderr)
-        flag = torch.tensor([ok], device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            if sharder is not None:
-                sharder.close()
-            mode = "gather"
-            args.format = "f32"                  # the gather path assembles float frames
-            sharder = FrameSharder(r, w, h, rank, world, mode=mode, strip_rows=SR)
-        target = sharder.target
+        r = SceneRenderer(load_ir(args.scene), textures=textures, device=local, persistent=bool(args.persistent), options=options)
+        r.render_depth = depth
+        cam0 = dict(r.cam)
 
-    cam0 = dict(r.cam)
-    frame_counter = [0]
+        def frame_uniforms(k=None):
+            if k is not None:
+                r.set_cam(cam0["look_at"], cam0["alpha"] + 2.0 * math.pi * k / args.orbit, cam0["beta"], cam0["r"])
+            r.set_uniforms()
+    lib, ctx = r._lib, r._ctx
 
-    def step(i, consumer=None):
-        """One frame.  `consumer` (rank 0) enqueues whatever reads the assembled frame; after it the frame's
-        buffer is released to the other ranks (p2p mode)."""
-        _step_render(i)
-        if consumer is not None:
-            consumer()
-        if sharder is not None:
-            sharder.release(sptr)
-
-    def _step_render(i):
-        if args.orbit:
-            # BASELINE config 5: alpha_k = alpha_0 + 2*pi*k/orbit (SURVEY.md section 8d); only `_camera` changes
-            k = frame_counter[0] % args.orbit
-            frame_counter[0] += 1
-            r.set_cam(cam0["look_at"], cam0["alpha"] + 2.0 * math.pi * k / args.orbit, cam0["beta"], cam0["r"])
-        if world == 1:
-            if args.format == "f32":
-                r.draw_texture(target, outs[i & 1].data_ptr(), 0, sptr)
-            else:
-                r.draw_texture_rgba8(target, outs[i % len(outs)].data_ptr(), sptr)
-        else:
-            sharder.render(i, sptr)
+    def check(rc):
+        if rc:
+            raise RuntimeError(lib.pe_last_error(ctx).decode(errors="replace"))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- value leg set-up
+    mode = args.mode if world > 1 else "single"
+    fmt = args.format
+    bpp = 16 if fmt == "f32" else 4
+    tdtype = torch.float32 if fmt == "f32" else torch.uint8
+    frame_counter = [0]
+    sharder = None
+    if world == 1:
+        target = r.full_target(w, h) if hasattr(r, "full_target") else SceneRenderer.full_target(w, h)
+        # ring of output frames larger than the 126 MB L2: >= 2 float frames (265 MB at 4K) / >= 6 RGBA8 frames
+        n_outs = max(2, int(math.ceil(192e6 / (w * h * bpp))) + 1)
+        outs = [torch.empty((h, w, 4), dtype=tdtype, device="cuda") for _ in range(n_outs)]
+        n_px_local = w * h
+    elif mode == "gather":
+        target = D.make_target(w, h, rank, world, STRIP_ROWS, full_frame=False)
+        spr = D.strips_per_rank(h, world, STRIP_ROWS)
+        n_outs = max(2, int(math.ceil(192e6 / max(spr * STRIP_ROWS * w * 16, 1))) + 1)
+        local_bufs = [torch.zeros((spr, STRIP_ROWS, w, 4), dtype=torch.float32, device="cuda") for _ in range(n_outs)]
+        gathered = torch.empty((world, spr, STRIP_ROWS, w, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+        frame_dev = torch.empty((h, w, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+        fmt, bpp = "f32", 16
+        n_px_local = int(lib.pe_target_pixels(C.byref(target)))
+    else:
+        sharder = D.NativeSharder(r, w, h, rank, world, mode, fmt, STRIP_ROWS)
+        target = sharder.target
+        n_px_local = sum(1 for y in D.local_rows(h, rank, world, STRIP_ROWS) if y >= 0) * w
+    last = {"ptr": None}
+
+    def render_once(i):
+        """Enqueue one frame (this rank's part of it) on the stream."""
+        if world == 1:
+            out = outs[i % len(outs)]
+            check(lib.pe_render(ctx, C.byref(target), out.data_ptr(), None, sptr) if fmt == "f32" else
+                  lib.pe_render_rgba8(ctx, C.byref(target), out.data_ptr(), sptr))
+            last["ptr"] = out
+        elif mode == "gather":
+            out = local_bufs[i % len(local_bufs)]
+            check(lib.pe_render(ctx, C.byref(target), out.data_ptr(), None, sptr))
+            dist.gather(out, list(gathered.unbind(0)) if rank == 0 else None, dst=0)       # torch's current stream == `stream`
+            if rank == 0:
+                check(lib.pe_deinterleave_strips(ctx, gathered.data_ptr(), frame_dev.data_ptr(), w, h, STRIP_ROWS, world, spr, sptr))
+            last["ptr"] = out
+        else:
+            last["ptr"] = sharder.render(sptr)
+            sharder.release(sptr)              # p2p, rank 0: the frame's consumer (nothing, here) has been enqueued
+
+    def step(i):
+        if args.orbit:
+            # BASELINE config 5: alpha_k = alpha_0 + 2*pi*k/orbit (SURVEY.md section 8d); only `_camera` changes
+            frame_uniforms(frame_counter[0] % args.orbit)
+            frame_counter[0] += 1
+        render_once(i)
+
+    frame_uniforms(0 if args.orbit else None)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                      # nvidia-smi needs ~0.2 s to produce its first sample: start it early
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
+    frame_counter[0] = 0
     # ---- timed region: K steps, device time, max over ranks
-    l0 = r.launch_count()
+    l0 = int(lib.pe_launch_count(ctx))
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -295,183 +317,255 @@ def run_ours(args):
     ev[1].record(stream)
     barrier()
     t_epoch1 = time.time()
-    launches = r.launch_count() - l0
-    dev_ms = ev[0].elapsed_time(ev[1])
-    step_ms = dev_ms      # both modes are stream-ordered end to end: device time between the two events
-    ms = torch.tensor([step_ms], dtype=torch.float64, device="cuda")
+    launches = torch.tensor([int(lib.pe_launch_count(ctx)) - l0], dtype=torch.int64, device="cuda")
+    ms = torch.tensor([ev[0].elapsed_time(ev[1])], dtype=torch.float64, device="cuda")
     kms = torch.tensor([sum(a.elapsed_time(b) for a, b in kev) / args.steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches, op=dist.ReduceOp.SUM)        # every rank's kernels count
     total_ms, kernel_ms = float(ms.item()), float(kms.item())
+
+    # ---- parity of the value leg: the LAST frame the timed loop produced, hashed against the oracle's pin
+    last_k = (args.steps - 1) % args.orbit if args.orbit else None
+    parity = {}
+
+    def assembled_last_frame():
+        """bytes of the whole last frame on rank 0 (None elsewhere)."""
+        if world == 1:
+            return last["ptr"].cpu().numpy()
+        if mode == "gather":
+            return frame_dev.cpu().numpy() if rank == 0 else None
+        if mode == "p2p":
+            if rank != 0:
+                return None
+            out = np.empty((h, w, 4), dtype=np.float32 if fmt == "f32" else np.uint8)
+            check(lib.pe_memcpy_d2h(ctx, out.ctypes.data, last["ptr"], out.nbytes, sptr))
+            return out
+        # owner: ONE NCCL gather of every rank's strips (exactly the buffers the last timed step wrote) + de-interleave
+        spr_ = D.strips_per_rank(h, world, STRIP_ROWS)
+        mine = torch.zeros((spr_, STRIP_ROWS, w, 4), dtype=tdtype, device="cuda")
+        nb = n_px_local * bpp
+        if nb:
+            # device-to-device: the sharder's buffer (a raw device pointer of the C ABI) seen as a tensor
+            class _DevBuf:
+                __cuda_array_interface__ = {"shape": (nb,), "typestr": "|u1", "data": (int(last["ptr"]), False), "version": 3}
+            mine.view(torch.uint8).reshape(-1)[:nb].copy_(torch.as_tensor(_DevBuf(), device="cuda"))
+        g = torch.empty((world,) + tuple(mine.shape), dtype=tdtype, device="cuda") if rank == 0 else None
+        dist.gather(mine, list(g.unbind(0)) if rank == 0 else None, dst=0)
+        if rank != 0:
+            return None
+        if fmt == "f32":
+            fr = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+            check(lib.pe_deinterleave_strips(ctx, g.data_ptr(), fr.data_ptr(), w, h, STRIP_ROWS, world, spr_, sptr))
+            torch.cuda.synchronize()
+            return fr.cpu().numpy()
+        return D.deinterleave_numpy(g.cpu().numpy(), h, world, STRIP_ROWS)
+
+    frame = assembled_last_frame()
+    if rank == 0:
+        pins = golden_pins(args.scene, w, h, depth, args.orbit, last_k)
+        key = "sha256_f32_rgba" if fmt == "f32" else "sha256_rgba8"
+        got = sha(np.ascontiguousarray(frame))
+        parity["value_frame"] = {"what": f"last timed frame ({'orbit frame %d' % last_k if args.orbit else 'saved camera'}), {fmt}, "
+                                         f"{'as rendered' if world == 1 else 'the ranks strips through one NCCL gather' if mode == 'owner' else 'assembled on rank 0'}",
+                                 "sha256": got, "golden": pins.get(key) if pins else None,
+                                 "match": (got == pins.get(key)) if pins and pins.get(key) else None}
+    del frame
+
     # A timed region of a few tens of ms (many GPUs, short frames) ends before nvidia-smi delivers two samples: keep the
     # GPUs under the identical load, untimed, for ~1.5 s so that the clocks / throttle reasons are observed under it.
-    # The count is derived from the all-reduced time, so every rank runs the same number of steps.
     if total_ms < 100.0:
         extra = max(1, min(50000, int(1500.0 / max(total_ms / args.steps, 1e-3))))
         for i in range(extra):
             step(args.steps + i)
         barrier()
     clocks = sampler.stop(t_epoch0, t_epoch1, time.time()) if rank == 0 else None
+    if sharder is not None:
+        barrier()
+        sharder.close()
+        sharder = None
 
-    # ---- e2e: the reference-facing call with HOST buffers (RGBA8 readback = get_texture_data)
-    e2e_steps = max(3, min(args.steps, 20))
-    from portal_b200.distributed import gpu_numa_affinity
-    with gpu_numa_affinity(local):      # pinned pages on the GPU's NUMA node: the D2H copy stays off the socket interconnect
-        host8 = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
-        host8_b = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() if (rank == 0 and world == 1) else None
-    q8 = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda") if (rank == 0 and world > 1) else None
-    cam = r.cam
-    n_px_local = int(r._lib.pe_target_pixels(C.byref(target))) if world == 1 or mode == "gather" else \
-        sum(1 for y in __import__("portal_b200.distributed", fromlist=["x"]).local_rows(h, rank, world, SR) if y >= 0) * w
+    # ---- N > 1: the same frames ASSEMBLED on rank 0 by the render kernels' own NVLink stores (float and RGBA8 frames)
+    assembled = None
+    if world > 1 and not args.no_assembled:
+        assembled = {}
+        for afmt in ("f32", "rgba8"):
+            sh = D.NativeSharder(r, w, h, rank, world, "p2p", afmt, STRIP_ROWS)
+            n = min(args.steps, 100)
+            for _ in range(3):
+                sh.render(sptr); sh.release(sptr)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(n):
+                sh.render(sptr); sh.release(sptr)
+            e1.record(stream)
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rec = {"value": round(w * h * n / (float(t.item()) * 1e-3) / 1e6, 2), "unit": "Mpixels/s", "steps": n}
+            if rank == 0 and not args.orbit:
+                out = np.empty((h, w, 4), dtype=np.float32 if afmt == "f32" else np.uint8)
+                check(lib.pe_memcpy_d2h(ctx, out.ctypes.data, sh.frame_ptr, out.nbytes, sptr))
+                pins = golden_pins(args.scene, w, h, depth)
+                key = "sha256_f32_rgba" if afmt == "f32" else "sha256_rgba8"
+                rec["frame_matches_golden"] = (sha(out) == pins[key]) if pins and key in pins else None
+            assembled[f"p2p_{afmt}"] = rec
+            barrier()
+            sh.close()
 
-    def e2e_step(i):
-        r.set_cam(cam["look_at"], cam["alpha"], cam["beta"], cam["r"])   # per-frame host work: camera -> _camera
-        if world == 1:
-            r.render_host_ptr(w, h, host8.data_ptr(), rgba8=True)
-        else:
-            def consume():
-                if rank == 0 and args.format == "f32":
-                    r._check(r._lib.pe_quantize_rgba8(r._ctx, sharder.frame_ptr, q8.data_ptr(), w * h, sptr))
-                    host8.copy_(q8, non_blocking=True)
-                elif rank == 0:                  # the assembled frame is RGBA8 already
-                    stream.synchronize()
-                    r._check(r._lib.pe_memcpy_d2h(r._ctx, host8.data_ptr(), sharder.frame_ptr, w * h * 4, sptr))
-            step(i, consume)
-            torch.cuda.synchronize()
-    for i in range(2):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_rate = w * h * e2e_steps / float(e2e_s.item()) / 1e6
+    # ---- e2e: the reference-facing call with HOST buffers (RGBA8 frame = get_texture_data), per-frame host work included
+    e2e_steps = max(3, min(args.steps, 20 if world == 1 else 60))
+    e2e_k = [0]
+
+    def e2e_uniforms():
+        k = None
+        if args.orbit:
+            k = e2e_k[0] % args.orbit
+        e2e_k[0] += 1
+        frame_uniforms(k)                     # ron: float64 scene evaluation + upload; ir: camera -> `_camera` + upload
+        return k
+
     e2e_sync_rate = None
-    if world > 1:
-        # host delivery without a device-side gather: every rank renders its strips as RGBA8 and copies them over its
-        # own PCIe link into one shared, page-locked host frame (HostFrameSharder); rank 0 consumes whole frames
-        from portal_b200.distributed import HostFrameSharder
-        try:
-            hfs = HostFrameSharder(r, w, h, rank, world)     # raises on EVERY rank alike if /dev/shm is too small
-        except RuntimeError as e:
-            hfs = None
-            if rank == 0:
-                print(f"[bench] {e}; e2e stays the blocking rank-0 path", file=sys.stderr)
-    if world > 1 and hfs is not None:
-        e2e_sync_rate = e2e_rate
-        def pipelined_n(n):
-            prev = None
+    e2e_last_k = None
+    if world == 1:
+        with D.gpu_numa_affinity(local):      # pinned pages on the GPU's NUMA node: the D2H copy stays off the socket interconnect
+            ring = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        t8 = SceneRenderer.full_target(w, h)
+
+        def blocking(n):
+            for _ in range(n):
+                e2e_uniforms()
+                check(lib.pe_render_host_rgba8(ctx, C.byref(t8), ring[0].data_ptr()))
+
+        def pipelined(n):
+            prev, k = None, None
             for i in range(n):
-                r.set_cam(cam["look_at"], cam["alpha"], cam["beta"], cam["r"])
-                f = hfs.submit()
+                k = e2e_uniforms()
+                tk = C.c_uint64()
+                check(lib.pe_submit_host_rgba8(ctx, C.byref(t8), ring[i % 2].data_ptr(), C.byref(tk)))
                 if prev is not None:
-                    hfs.complete(prev)
+                    check(lib.pe_wait_host(ctx, prev))     # frame i-1 is in host memory: the consumer may read it now
+                prev = tk.value
+            check(lib.pe_wait_host(ctx, prev))
+            return k, ring[(n - 1) % 2]
+        blocking(2)
+        t0 = time.perf_counter()
+        blocking(e2e_steps)
+        e2e_sync_rate = w * h * e2e_steps / (time.perf_counter() - t0) / 1e6
+        pipelined(3)
+        check(lib.pe_sync(ctx))
+        e2e_k[0] = 0
+        t0 = time.perf_counter()
+        e2e_last_k, host_frame = pipelined(e2e_steps)
+        e2e_rate = w * h * e2e_steps / (time.perf_counter() - t0) / 1e6
+        host_bytes = host_frame.numpy()
+    else:
+        hs = D.NativeSharder(r, w, h, rank, world, "host", "rgba8", STRIP_ROWS)
+
+        def pipelined_n(n):
+            prev, k, fr = None, None, None
+            for _ in range(n):
+                k = e2e_uniforms()
+                f = hs.submit()
+                if prev is not None:
+                    hs.complete(prev)
                     if rank == 0:
-                        hfs.wait_frame(prev)          # the whole frame i-1 is in host memory: the consumer may read it
-                        hfs.release(prev)
+                        hs.wait_frame(prev)          # the whole frame i-1 is in host memory: the consumer may read it
+                        hs.release_frame(prev)
                 prev = f
-            hfs.complete(prev)
+            hs.complete(prev)
             if rank == 0:
-                hfs.wait_frame(prev)
-                hfs.release(prev)
+                fr = hs.wait_frame(prev).copy()
+                hs.release_frame(prev)
+            return k, fr
         pipelined_n(3)
         barrier()
+        e2e_k[0] = 0
         t0 = time.perf_counter()
-        pipelined_n(e2e_steps)
+        e2e_last_k, host_bytes = pipelined_n(e2e_steps)
         barrier()
         e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         e2e_rate = w * h * e2e_steps / float(e2e_s.item()) / 1e6
-        hfs.close()
-    if world == 1:
-        # the frame-sequence form of the same call (the offline `render` loop reads one frame after another):
-        # pe_submit_host_rgba8 / pe_wait_host, frame i's D2H overlapping frame i+1's kernel; every frame still
-        # uploads its uniforms and lands, complete, in pinned host memory before the clock stops
-        e2e_sync_rate = e2e_rate
-        ring = [host8, host8_b]
-        def pipelined(n):
-            prev = None
-            for i in range(n):
-                r.set_cam(cam["look_at"], cam["alpha"], cam["beta"], cam["r"])
-                tk = r.submit_host_rgba8(w, h, ring[i % 2].data_ptr())
-                if prev is not None:
-                    r.wait_host(prev)            # frame i-1 is in host memory: the consumer may read it now
-                prev = tk
-            r.wait_host(prev)
-        pipelined(3)
-        r.sync()
-        t0 = time.perf_counter()
-        pipelined(e2e_steps)
-        e2e_rate = w * h * e2e_steps / (time.perf_counter() - t0) / 1e6
+        barrier()
+        hs.close()
+    if rank == 0:
+        pins = golden_pins(args.scene, w, h, depth, args.orbit, e2e_last_k)
+        got = sha(np.ascontiguousarray(host_bytes))
+        parity["e2e_frame"] = {"what": "last RGBA8 frame delivered to host memory by the e2e loop", "sha256": got,
+                               "golden": pins.get("sha256_rgba8") if pins else None,
+                               "match": (got == pins.get("sha256_rgba8")) if pins and pins.get("sha256_rgba8") else None}
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
         value = w * h * args.steps / (total_ms * 1e-3) / 1e6
         # roofline of the dominant kernel (pe_render_kernel): algorithmic bytes = 16 B/pixel written
-        #  x pixels one launch shades, / its mean launch duration (CUDA events)
-        bpp = 16.0 if args.format == "f32" else 4.0
-        alg_bytes = bpp * n_px_local
+        # (SURVEY.md section 8d) x pixels one launch shades, / its mean launch duration (CUDA events)
+        alg_bytes = float(bpp) * n_px_local
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and world == 1:
             with open(tp) as f:
-                traffic = json.load(f).get(f"{args.scene}_{w}x{h}_d{depth}") if args.format == "f32" else None
+                traffic = json.load(f).get(f"{args.scene}_{w}x{h}_d{depth}") if fmt == "f32" else None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample = cpu_oracle_rate(args.scene, w, h, depth, budget_s=20.0)
-            v1, _, _ = cpu_oracle_rate(args.scene, w, h, depth, budget_s=4.0, threads=1)
-            cpu = {"value": round(v, 4), "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample,
-                   "single_thread_value": round(v1, 4)}
+            res = cpu_oracle(args, budget_s=20.0)
+            res1 = cpu_oracle(args, budget_s=4.0, threads=1)
+            cpu = {"value": round(res["value"], 4), "unit": "Mpixels/s", "cores": res["threads_used"], "kind": "port", "sample": res["sample"],
+                   "single_thread_value": round(res1["value"], 4)}
+        par = {"single": "1 GPU",
+               "owner": f"{world} GPUs x cyclic {STRIP_ROWS}-row strips (pe_sharder_*, C ABI), every rank's strips stay in its own HBM; no collective on the data path",
+               "p2p": f"{world} GPUs x cyclic {STRIP_ROWS}-row strips, kernels store into rank 0's frame over NVLink (CUDA IPC), stream-ordered flag words, no collective",
+               "gather": f"{world} GPUs x cyclic {STRIP_ROWS}-row strips + 1 NCCL gather + de-interleave"}[mode]
+        frame_mb = w * h * bpp / 1e6
         line = {
             "metric": metric_name(args.scene, w, h, depth), "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.scene}.ron {w}x{h} depth {depth}, " + (f"{args.orbit}-frame camera orbit" if args.orbit else "saved camera") + ", aa 1" + (" (BASELINE.json headline config)" if (args.scene, w, h, depth) == ("portal_in_portal", 3840, 2160, 40) else ""),
-                       "parallelism": "1 GPU" if world == 1 else (
-                           f"{world} GPUs x cyclic {STRIP_ROWS}-row strips + 1 NCCL gather + de-interleave" if mode == "gather" else
-                           f"{world} GPUs x cyclic {STRIP_ROWS}-row strips, kernels store into rank 0's frame over NVLink (CUDA IPC), stream-ordered flag words, no collective"),
-                       "scheduler": "persistent warps + per-bounce refill" if args.persistent else "one thread per pixel, 8x4 warp tiles, 512-thread blocks, <= 64 regs",
-                       "frame_format": "float RGBA (16 B/pixel)" if args.format == "f32" else "RGBA8 quantised by the kernel (4 B/pixel)",
-                       "l2": ("each step writes a 132.7 MB frame (> 126 MB L2) into alternating buffers" if args.format == "f32" else
-                              ("each step writes a 33.2 MB frame into a ring of 6 (199 MB > 126 MB L2)" if world == 1 else
-                               "each step writes a 33.2 MB frame into one of rank 0's two buffers (L2-resident: this format is a bandwidth experiment)")) +
-                             "; inputs are a <8 KB constant block"},
+            "config": {"workload": workload_name(args),
+                       "parallelism": par,
+                       "scheduler": "persistent warps + per-bounce refill" if args.persistent else
+                                    f"one thread per pixel, {args.tile_w or 8}x{32 // (args.tile_w or 8)} warp tiles, 512-thread blocks, <= 64 regs",
+                       "frame_format": "float RGBA (16 B/pixel)" if fmt == "f32" else "RGBA8 quantised by the kernel (4 B/pixel)",
+                       "front_end": "scene .ron -> C++ host front-end (ph_scene_*) -> C ABI" if args.frontend == "ron" else "JSON scene IR -> Python SceneRenderer -> C ABI",
+                       "l2": f"each step writes {'a' if world == 1 else 'its part of a'} {frame_mb:.1f} MB frame into a ring of buffers larger than "
+                             f"the 126 MB L2; inputs are a <8 KB constant block"},
             "kernel_ms": round(kernel_ms, 4),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": round(achieved / peaks["hbm_gbs"], 5), "traffic": traffic, "peak_source": peak_src,
-                         "note": f"{int(bpp)} B/pixel algorithmic; the loop is fp32-ALU/latency bound, see DESIGN.md §6"},
+                         "note": f"{int(bpp)} B/pixel algorithmic x {n_px_local} px per launch; the loop is fp32-issue bound (DESIGN.md section 6): "
+                                 f"issue-slot utilisation and instructions per pixel are in profiles/"},
             "clocks": clocks,
-            "e2e": {"value": round(e2e_rate, 2), "unit": "Mpixels/s", "h2d_bytes_per_step": e2e_h2d_bytes(r),
+            "e2e": {"value": round(e2e_rate, 2), "unit": "Mpixels/s", "h2d_bytes_per_step": e2e_h2d_bytes(r) * world,
                     "d2h_bytes_per_step": w * h * 4, "steps": e2e_steps,
-                    "call": "pe_submit_host_rgba8 / pe_wait_host per frame (RGBA8 into pinned host memory, 2 frames in flight)" if world == 1 else
-                            (f"pe_submit_host_strips_rgba8 / pe_wait_host on every rank: RGBA8 strips over {world} PCIe links into one shared pinned host frame, no gather"
-                             if e2e_sync_rate is not None else
-                             f"pe_render ({mode}) into rank 0's float frame + pe_quantize_rgba8 + D2H from rank 0, blocking per frame")},
-            "gpu_launches": int(launches),
+                    "call": ("ph_frame_uniforms + " if args.frontend == "ron" else "set_cam/set_uniforms + ") +
+                            ("pe_submit_host_rgba8 / pe_wait_host per frame (RGBA8 into pinned host memory, 2 frames in flight)" if world == 1 else
+                             f"pe_sharder_submit / complete on every rank, wait_frame / release_frame on rank 0: RGBA8 strips over {world} PCIe links "
+                             f"into one shared pinned host frame, no gather")},
+            "parity": parity,
+            "gpu_launches": int(launches.item()),
         }
         if e2e_sync_rate is not None:
             line["e2e"]["sync_call_value"] = round(e2e_sync_rate, 2)
-            line["e2e"]["sync_call"] = "pe_render_host_rgba8 (one blocking call per frame)" if world == 1 else \
-                f"pe_render ({mode}) into rank 0's float frame + pe_quantize_rgba8 + D2H from rank 0, blocking per frame"
+            line["e2e"]["sync_call"] = "pe_render_host_rgba8 (one blocking call per frame)"
+        if assembled:
+            line["assembled"] = assembled
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    if sharder is not None:
-        barrier()
-        sharder.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    r.close()
 
 
 def e2e_h2d_bytes(r):
     """Bytes of the constant uniform block uploaded every step (scene matrices + camera + scalars)."""
-    src = r.source()
     import re
+    src = r.source()
     m = re.search(r"sizeof\(PeConstBlock\) == (\d+)", src)
     return int(m.group(1)) if m else 0
 
@@ -487,12 +581,18 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--persistent", type=int, default=0)
+    ap.add_argument("--tile-w", type=int, default=0, choices=[0, 8, 16, 32], help="warp tile width (0: the library default, 8)")
     ap.add_argument("--orbit", type=int, default=0, help="camera orbit of this many frames per turn (config 5: 360)")
-    ap.add_argument("--mode", default="p2p", choices=["gather", "p2p"], help="N > 1: how strips reach rank 0")
+    ap.add_argument("--mode", default="owner", choices=["owner", "p2p", "gather"],
+                    help="N > 1, the timed `value` steps: owner = strips stay in the rendering GPU's HBM; p2p = kernels store into rank 0's "
+                         "frame over NVLink; gather = one NCCL gather + de-interleave")
+    ap.add_argument("--frontend", default="ron", choices=["ron", "ir"],
+                    help="ron = the product's C++ host front-end on tests/golden/ron/<scene>.ron; ir = the JSON scene IR (oracle front-end's export)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-assembled", action="store_true", help="N > 1: skip the extra rank-0-assembled measurements")
     ap.add_argument("--format", default="f32", choices=["f32", "rgba8"],
                     help="frame format of the timed steps: f32 = float RGBA, 16 B/pixel (the metric's definition, SURVEY.md 8d); "
-                         "rgba8 = what the reference's RGBA8 render target holds, 4 B/pixel, quantised by the kernel (p2p mode for N > 1)")
+                         "rgba8 = what the reference's RGBA8 render target holds, 4 B/pixel, quantised by the kernel")
     args = ap.parse_args()
     w, h, d = WORKLOADS[args.scene]
     args.width, args.height, args.depth = args.width or w, args.height or h, args.depth or d

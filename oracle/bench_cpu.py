@@ -51,7 +51,9 @@ def main():
     ap.add_argument("--height", type=int, required=True)
     ap.add_argument("--depth", type=int, required=True)
     ap.add_argument("--threads", type=int, default=0)
-    ap.add_argument("--budget", type=float, default=20.0, help="seconds of CPU rendering to spend on the sample")
+    ap.add_argument("--budget", type=float, default=20.0, help="seconds of CPU rendering to spend on the sample (all steps together)")
+    ap.add_argument("--steps", type=int, default=1, help="split the sample into this many timed steps (the reference arm's --steps)")
+    ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--scene-dir", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "scenes"))
     args = ap.parse_args()
     # ---- a clean slate for OpenMP, BEFORE the oracle library (and libgomp) is loaded
@@ -60,9 +62,9 @@ def main():
     except OSError:
         pass
     threads = args.threads or usable_cores()
-    if "OMP_NUM_THREADS_SET_BY_BENCH" not in os.environ:
+    if "PORTAL_B200_BENCH_CPU_REEXEC" not in os.environ:
         env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="spread" if threads > 1 else "false", OMP_PLACES="cores",
-                   OMP_NUM_THREADS_SET_BY_BENCH="1")
+                   PORTAL_B200_BENCH_CPU_REEXEC="1")
         env.pop("KMP_AFFINITY", None)
         os.execve(sys.executable, [sys.executable, "-m", "oracle.bench_cpu", *sys.argv[1:]], env)   # libgomp reads these at load
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -76,21 +78,30 @@ def main():
     used = orc.omp_threads(threads)
     B = min(64, h)
     mid = (h // 2, min(h, h // 2 + B))
-    orc.render(w, h, depth, rows=mid, threads=threads)                       # warm up the thread pool
+    for _ in range(max(1, args.warmup)):
+        orc.render(w, h, depth, rows=mid, threads=threads)                   # warm up the thread pool
     t0 = time.perf_counter()
     orc.render(w, h, depth, rows=mid, threads=threads)                       # calibrate
     per_band = max(time.perf_counter() - t0, 1e-4)
-    n_bands = int(max(2, min(h // B, args.budget / per_band)))
-    starts = [int(i * (h - B) / max(n_bands - 1, 1)) for i in range(n_bands)]
-    t0 = time.perf_counter()
-    px = 0
-    for s in starts:
-        orc.render(w, h, depth, rows=(s, s + B), threads=threads)
-        px += B * w
-    dt = time.perf_counter() - t0
-    print(json.dumps({"value": px / dt / 1e6, "threads_used": used, "threads_requested": threads, "pixels": px, "seconds": dt,
-                      "sample": f"{n_bands} bands x {B} rows spread over the {w}x{h} frame ({px} px, {dt:.1f} s; OpenMP dynamic schedule over "
-                                f"64-pixel runs, {used} threads, OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')})"}))
+    steps = max(1, args.steps)
+    per_step = int(max(1, min(h // B, args.budget / per_band / steps)))      # bands of one step: a bounded sample of the frame
+    rates, px, dt = [], 0, 0.0
+    for k in range(steps):
+        # all steps together sample steps * per_step bands spread uniformly over the frame; step k takes every steps-th of them,
+        # so one step and the whole run both see the frame's cheap and expensive rows in proportion
+        total = steps * per_step
+        starts = [int((k + i * steps + 0.5) / total * (h - B)) for i in range(per_step)]
+        t0 = time.perf_counter()
+        for s in starts:
+            orc.render(w, h, depth, rows=(s, s + B), threads=threads)
+        t = time.perf_counter() - t0
+        rates.append(per_step * B * w / t / 1e6)
+        px += per_step * B * w
+        dt += t
+    print(json.dumps({"value": px / dt / 1e6, "threads_used": used, "threads_requested": threads, "pixels": px, "seconds": dt, "steps": steps,
+                      "step_rates_min_max": [min(rates), max(rates)],
+                      "sample": f"{steps} step(s) x {per_step} bands x {B} rows spread over the {w}x{h} frame ({px} px, {dt:.1f} s; OpenMP dynamic "
+                                f"schedule over 64-pixel runs, {used} threads, OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')})"}))
 
 
 if __name__ == "__main__":

@@ -482,6 +482,20 @@ void pe_oracle_probe(const PeOracleFrame* fr, const float* a, const float* b, fl
     out_pos[0] = float(t.pos.x); out_pos[1] = float(t.pos.y); out_pos[2] = float(t.pos.z);
     out_flags[0] = t.have_result; out_flags[1] = t.encounter_object; out_flags[2] = t.change_subspace;
 }
+// Threads an OpenMP parallel region of this library really gets (what bench.py reports as `cores`).
+int pe_oracle_omp_threads(int threads) {
+    int n = 1;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel
+    {
+#pragma omp single
+        n = omp_get_num_threads();
+    }
+#endif
+    (void)threads;
+    return n;
+}
 void pe_oracle_render(const PeOracleFrame* fr, int row0, int row1, float* out, int* bounces, int threads) {
     using namespace pe_oracle;
     pe_oracle_load_frame(fr);

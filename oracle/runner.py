@@ -151,6 +151,12 @@ class Oracle:
         self.lib.pe_oracle_render(C.byref(fr), r0, r1, out.ctypes.data, None if bnc is None else bnc.ctypes.data, threads)
         return (out, bnc) if want_bounces else out
 
+    def omp_threads(self, threads: int = 0) -> int:
+        """Number of threads an OpenMP region of this build runs with (1 for the strict build)."""
+        self.lib.pe_oracle_omp_threads.argtypes = [C.c_int]
+        self.lib.pe_oracle_omp_threads.restype = C.c_int
+        return int(self.lib.pe_oracle_omp_threads(int(threads)))
+
     def probe(self, a, b, **kw):
         """teleport_external_ray(a, b) -> (pos[3] float32, have_result, encounter_object, change_subspace).
         Like the reference (main.rs:1367) the probe runs with `teleport_light_u` forced to 1 if the scene has it."""

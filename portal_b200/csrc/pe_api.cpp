@@ -20,6 +20,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/portal_b200.h"
@@ -303,13 +304,63 @@ std::vector<int> variant_key(pe_ctx* c, const std::vector<int>& ints, const std:
     return key;
 }
 
+// The JIT compiler is loaded PRIVATELY by path (the toolkit this library was built with, PE_NVRTC_PATH) instead of being a
+// link-time dependency: a process that imported torch first already holds torch's own libnvrtc.so.12 (another release),
+// and a DT_NEEDED entry would silently bind to that one -- the programs build() compiled into the disk cache would then
+// never be used on the GPU box, and the SASS inspected in the build container would not be the SASS that runs.
+struct NvrtcApi {
+    nvrtcResult (*Version)(int*, int*) = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    const char* (*GetErrorString)(nvrtcResult) = nullptr;
+    std::string why;
+    bool ok = false;
+};
+const NvrtcApi& nvrtc_api() {
+    static NvrtcApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = nullptr;
+        const char* env = std::getenv("PORTAL_B200_NVRTC");
+        const char* candidates[] = {env && *env ? env : nullptr,
+#ifdef PE_NVRTC_PATH
+                                    PE_NVRTC_PATH,
+#endif
+                                    "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.12", "libnvrtc.so"};
+        for (const char* cnd : candidates) {
+            if (!cnd) continue;
+            h = dlopen(cnd, RTLD_NOW | RTLD_LOCAL);
+            if (h) break;
+        }
+        if (!h) { api.why = std::string("cannot load NVRTC: ") + dlerror(); return; }
+        auto bind = [&](const char* name, auto& fn) {
+            fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(h, name));
+            if (!fn && api.why.empty()) api.why = std::string("NVRTC: missing symbol ") + name;
+            return fn != nullptr;
+        };
+        api.ok = bind("nvrtcVersion", api.Version) & bind("nvrtcCreateProgram", api.CreateProgram) &
+                 bind("nvrtcCompileProgram", api.CompileProgram) & bind("nvrtcGetProgramLogSize", api.GetProgramLogSize) &
+                 bind("nvrtcGetProgramLog", api.GetProgramLog) & bind("nvrtcGetCUBINSize", api.GetCUBINSize) &
+                 bind("nvrtcGetCUBIN", api.GetCUBIN) & bind("nvrtcDestroyProgram", api.DestroyProgram) &
+                 bind("nvrtcGetErrorString", api.GetErrorString);
+    });
+    return api;
+}
+
 // NVRTC: source -> sm_100a cubin (disk-cached by content hash).
 bool compile_cubin(pe_ctx* c, const std::string& source, std::vector<char>& cubin, bool force_recompile = false) {
     std::vector<std::string> o = {"--gpu-architecture=sm_100a", "--std=c++20", "-default-device", "--fmad=false",
                                   "--prec-div=true", "--prec-sqrt=true", "--ftz=false"};
     if (c->lineinfo) o.push_back("-lineinfo");
+    const NvrtcApi& N = nvrtc_api();
+    if (!N.ok) { c->err = N.why; return false; }
     int major = 0, minor = 0;
-    nvrtcVersion(&major, &minor);
+    N.Version(&major, &minor);
     std::string tag = "nvrtc" + std::to_string(major) + "." + std::to_string(minor);
     for (auto& s : o) tag += s;
     uint64_t h1 = fnv1a(tag, fnv1a(source, 1469598103934665603ull));
@@ -337,29 +388,29 @@ bool compile_cubin(pe_ctx* c, const std::string& source, std::vector<char>& cubi
         }
     }
     nvrtcProgram prog;
-    if (nvrtcCreateProgram(&prog, source.c_str(), "scene_program.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
+    if (N.CreateProgram(&prog, source.c_str(), "scene_program.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
         c->err = "nvrtcCreateProgram failed";
         return false;
     }
     std::vector<const char*> opts;
     for (auto& s : o) opts.push_back(s.c_str());
-    nvrtcResult r = nvrtcCompileProgram(prog, int(opts.size()), opts.data());
+    nvrtcResult r = N.CompileProgram(prog, int(opts.size()), opts.data());
     size_t ls = 0;
-    nvrtcGetProgramLogSize(prog, &ls);
+    N.GetProgramLogSize(prog, &ls);
     std::string log(ls, '\0');
-    if (ls) nvrtcGetProgramLog(prog, &log[0]);
+    if (ls) N.GetProgramLog(prog, &log[0]);
     if (r != NVRTC_SUCCESS) {
         // Diagnostics already carry "<scene element>(local line)" thanks to the #line directives
         // the generator puts around every user snippet.
-        c->err = std::string("scene program failed to compile (") + nvrtcGetErrorString(r) + "):\n" + log;
-        nvrtcDestroyProgram(&prog);
+        c->err = std::string("scene program failed to compile (") + N.GetErrorString(r) + "):\n" + log;
+        N.DestroyProgram(&prog);
         return false;
     }
     size_t cs = 0;
-    nvrtcGetCUBINSize(prog, &cs);
+    N.GetCUBINSize(prog, &cs);
     cubin.resize(cs);
-    nvrtcGetCUBIN(prog, cubin.data());
-    nvrtcDestroyProgram(&prog);
+    N.GetCUBIN(prog, cubin.data());
+    N.DestroyProgram(&prog);
     {
         std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
         std::ofstream f(tmp, std::ios::binary);

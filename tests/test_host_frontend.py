@@ -539,3 +539,18 @@ def test_garbage_formulas_and_mutated_scene_files_are_handled(tmp_path):
             assert str(e)
             rejected += 1
     assert loaded + rejected == 400 and rejected > 300
+
+
+def test_vendored_config_scenes_are_the_references_files(have_reference):
+    """tests/golden/ron/*.ron -- the scene files bench.py and the GPU tests feed to the product's own front-end -- are byte
+    copies of the reference's (checked where the reference checkout exists)."""
+    import glob
+    import pytest
+    if not have_reference:
+        pytest.skip("needs /root/reference")
+    from conftest import REFERENCE, ROOT
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ron", "*.ron")))
+    assert len(files) == 5
+    for f in files:
+        with open(f, "rb") as a, open(os.path.join(REFERENCE, "scenes", os.path.basename(f)), "rb") as b:
+            assert a.read() == b.read(), f

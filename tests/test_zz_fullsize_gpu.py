@@ -17,15 +17,48 @@ with open(os.path.join(GOLDEN, "fullsize_sha256.json")) as f:
     FULL = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
 
 
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
 @pytest.mark.parametrize("scene", sorted(FULL))
 def test_full_frame_hash_equals_the_oracles(scene, torch_cuda):
+    """Every BASELINE config at its full size (config 5: 7680x4320 depth 64), float frame and RGBA8 frame, through the JSON
+    scene IR route."""
     from portal_b200.renderer import SceneRenderer
     cfg = FULL[scene]
     r = SceneRenderer(load_ir(scene), textures=load_tex(scene), device=0)
     r.render_depth = cfg["depth"]
     img = r.render_host(cfg["width"], cfg["height"])
     assert img.dtype == np.float32 and img.shape == (cfg["height"], cfg["width"], 4)
-    assert hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() == cfg["sha256_f32_rgba"]
+    assert _sha(img) == cfg["sha256_f32_rgba"]
+    del img
+    assert _sha(r.render_host_rgba8(cfg["width"], cfg["height"])) == cfg["sha256_rgba8"]
+    r.close()
+
+
+@pytest.mark.parametrize("scene", sorted(FULL))
+def test_full_frame_through_the_products_own_front_end(scene, torch_cuda):
+    """The same frames through `.ron` -> C++ host front-end (ph_scene_*, include/portal_b200_host.h) -> pe_*: the route
+    bench.py's e2e leg measures.  Equal to the oracle's pin, hence bit-identical to the JSON-IR route above."""
+    from conftest import ROOT
+    from portal_b200.host import HostRenderer, HostScene
+    cfg = FULL[scene]
+    w, h, d = cfg["width"], cfg["height"], cfg["depth"]
+    hs = HostScene.from_file(os.path.join(ROOT, "tests", "golden", "ron", f"{scene}.ron"))
+    hr = HostRenderer(hs, device=0, textures=load_tex(scene))
+    assert _sha(hr.render_frame(w, h, d, rgba8=True)) == cfg["sha256_rgba8"]
+    if w * h <= 3840 * 2160:
+        assert _sha(hr.render_frame(w, h, d)) == cfg["sha256_f32_rgba"]
+    for n, frames in ((int(k.split("_")[1]), v) for k, v in cfg.items() if k.startswith("orbit_")):
+        cam = hs.camera()
+        for k, pin in frames.items():
+            if int(k) == 0:
+                continue                                   # frame 0 is the saved camera (checked above)
+            import math
+            c = dict(cam, alpha=cam["alpha"] + 2.0 * math.pi * int(k) / n)
+            assert _sha(hr.render_frame(w, h, d, camera=c, rgba8=True)) == pin["sha256_rgba8"], (scene, k)
+    hr.close()
 
 
 def test_host_render_target_strips_reassemble_the_frame(torch_cuda):
