@@ -326,7 +326,8 @@ def run_ours(args):
         dist.all_reduce(launches, op=dist.ReduceOp.SUM)        # every rank's kernels count
     total_ms, kernel_ms = float(ms.item()), float(kms.item())
 
-    # ---- parity of the value leg: the LAST frame the timed loop produced, hashed against the oracle's pin
+    # ---- parity of the value leg: the LAST frame the timed loop produced, hashed against the oracle's pin.  A camera orbit has
+    # pins for frames 0 and orbit / 2 only: those two are rendered once more, untimed, through the very same step.
     last_k = (args.steps - 1) % args.orbit if args.orbit else None
     parity = {}
 
@@ -362,16 +363,31 @@ def run_ours(args):
             return fr.cpu().numpy()
         return D.deinterleave_numpy(g.cpu().numpy(), h, world, STRIP_ROWS)
 
-    frame = assembled_last_frame()
-    if rank == 0:
-        pins = golden_pins(args.scene, w, h, depth, args.orbit, last_k)
+    def hash_value_frame(k):
+        frame = assembled_last_frame()
+        if rank != 0:
+            return None
+        pins = golden_pins(args.scene, w, h, depth, args.orbit, k)
         key = "sha256_f32_rgba" if fmt == "f32" else "sha256_rgba8"
         got = sha(np.ascontiguousarray(frame))
-        parity["value_frame"] = {"what": f"last timed frame ({'orbit frame %d' % last_k if args.orbit else 'saved camera'}), {fmt}, "
-                                         f"{'as rendered' if world == 1 else 'the ranks strips through one NCCL gather' if mode == 'owner' else 'assembled on rank 0'}",
-                                 "sha256": got, "golden": pins.get(key) if pins else None,
-                                 "match": (got == pins.get(key)) if pins and pins.get(key) else None}
-    del frame
+        how = "as rendered" if world == 1 else ("every rank's strips through one NCCL gather" if mode == "owner" else "assembled on rank 0")
+        return {"what": f"{'orbit frame %d' % k if args.orbit else 'last timed frame, saved camera'}, {fmt}, {how}", "sha256": got,
+                "golden": pins.get(key) if pins else None, "match": (got == pins.get(key)) if pins and pins.get(key) else None}
+
+    if not args.orbit:
+        rec = hash_value_frame(None)
+        if rank == 0:
+            parity["value_frame"] = rec
+    else:
+        recs = []
+        for k in (0, args.orbit // 2):
+            frame_counter[0] = k
+            step(args.steps + k)
+            barrier()
+            recs.append(hash_value_frame(k))
+        if rank == 0:
+            parity["value_frame"] = {"what": "orbit frames rendered once more (untimed) by the timed step", "frames": recs,
+                                     "match": all(r["match"] for r in recs) if all(r["match"] is not None for r in recs) else None}
 
     # A timed region of a few tens of ms (many GPUs, short frames) ends before nvidia-smi delivers two samples: keep the
     # GPUs under the identical load, untimed, for ~1.5 s so that the clocks / throttle reasons are observed under it.
@@ -456,7 +472,7 @@ def run_ours(args):
         e2e_sync_rate = w * h * e2e_steps / (time.perf_counter() - t0) / 1e6
         pipelined(3)
         check(lib.pe_sync(ctx))
-        e2e_k[0] = 0
+        e2e_k[0] = (args.orbit // 2 - (e2e_steps - 1)) if args.orbit else 0      # an orbit's e2e loop ends on pinned frame orbit / 2
         t0 = time.perf_counter()
         e2e_last_k, host_frame = pipelined(e2e_steps)
         e2e_rate = w * h * e2e_steps / (time.perf_counter() - t0) / 1e6
@@ -482,7 +498,7 @@ def run_ours(args):
             return k, fr
         pipelined_n(3)
         barrier()
-        e2e_k[0] = 0
+        e2e_k[0] = (args.orbit // 2 - (e2e_steps - 1)) if args.orbit else 0      # an orbit's e2e loop ends on pinned frame orbit / 2
         t0 = time.perf_counter()
         e2e_last_k, host_bytes = pipelined_n(e2e_steps)
         barrier()

@@ -526,21 +526,33 @@ struct cmat4 {
 // chain (x*1 == x, fma(0, y, acc) == acc up to the sign of a zero result); GLSL does not define
 // Inf/NaN propagation through such terms, and matrices that contain Inf/NaN have no 0/1 entries
 // to skip in the first place.  Same chain order as operator*(cmat4, vec4).
-template <unsigned Z, unsigned O>
+// F = 1: the host has also verified that all 16 entries are FINITE.  An affine (bottom row exactly 0 0 0 1), finite matrix
+// maps a point (w exactly 1) to a point and a direction (w exactly 0) to a direction, and for those the w column needs no
+// arithmetic at all: fma(e, 1, acc) == acc + e exactly, and fma(e, 0, acc) == acc for finite e (up to the sign of a zero
+// result, as above).  point_row / dir_row are those two shortened chains; transform() (pe_library.cuh) uses them for rays
+// whose w components ARE 1 and 0 -- checked at run time where the compiler cannot see it, folded away where it can.
+template <unsigned Z, unsigned O, unsigned F = 0>
 struct smat4 {
     const cmat4& m;
+    static constexpr bool affine = ((Z & 0x0888u) == 0x0888u) && ((O & 0x8000u) != 0u);
+    static constexpr bool canon = affine && (F != 0u);
     PE_FI operator mat4() const { return mat4(m); }
     PE_FI vec4 operator[](int i) const { return m[i]; }
-    template <int R>
-    PE_FI float row(const vec4& v) const {
+    // W = 0: the full chain; W = 1: v.w is exactly 1; W = 2: v.w is exactly 0 (finite matrix)
+    template <int R, int W>
+    PE_FI float row_impl(const vec4& v) const {
         float acc = 0.0f;
         bool have = false;
         const float comp[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const unsigned bit = 1u << (4 * c + R);
+            if (c == 3 && W == 2) continue;              // finite entry times an exact zero
             if (Z & bit) continue;                       // exact zero: contributes nothing
-            if (O & bit) {                               // exact one: fma(1, v, acc) == acc + v
+            if (c == 3 && W == 1) {                      // entry times an exact one: an addition
+                const float e = (O & bit) ? 1.0f : m.e[4 * c + R];
+                acc = have ? acc + e : e;
+            } else if (O & bit) {                        // exact one: fma(1, v, acc) == acc + v
                 acc = have ? acc + comp[c] : comp[c];
             } else {
                 acc = have ? ::fmaf(m.e[4 * c + R], comp[c], acc) : m.e[4 * c + R] * comp[c];
@@ -549,21 +561,34 @@ struct smat4 {
         }
         return acc;
     }
+    template <int R>
+    PE_FI float row(const vec4& v) const { return row_impl<R, 0>(v); }
+    PE_FI vec4 point(const vec4& p) const { return vec4(row_impl<0, 1>(p), row_impl<1, 1>(p), row_impl<2, 1>(p), 1.0f); }
+    PE_FI vec4 dir(const vec4& d) const { return vec4(row_impl<0, 2>(d), row_impl<1, 2>(d), row_impl<2, 2>(d), 0.0f); }
+    // M * (0, 0, 0, 1) for a finite affine matrix: the translation column
+    PE_FI vec4 origin() const {
+        return vec4((Z & 0x1000u) ? 0.0f : ((O & 0x1000u) ? 1.0f : m.e[12]), (Z & 0x2000u) ? 0.0f : ((O & 0x2000u) ? 1.0f : m.e[13]),
+                    (Z & 0x4000u) ? 0.0f : ((O & 0x4000u) ? 1.0f : m.e[14]), 1.0f);
+    }
 };
-template <unsigned Z, unsigned O>
-PE_FI vec4 operator*(const smat4<Z, O>& m, const vec4& v) {
+// compile-time query usable on every matrix type a snippet may hand to the library
+template <class M> struct pe_canon_matrix { static constexpr bool value = false; };
+template <unsigned Z, unsigned O, unsigned F> struct pe_canon_matrix<smat4<Z, O, F>> { static constexpr bool value = smat4<Z, O, F>::canon; };
+
+template <unsigned Z, unsigned O, unsigned F>
+PE_FI vec4 operator*(const smat4<Z, O, F>& m, const vec4& v) {
     return vec4(m.template row<0>(v), m.template row<1>(v), m.template row<2>(v), m.template row<3>(v));
 }
-template <unsigned Z, unsigned O>
-PE_FI mat4 operator*(const smat4<Z, O>& a, const mat4& b) { return mat4(a * b.c[0], a * b.c[1], a * b.c[2], a * b.c[3]); }
-template <unsigned Z, unsigned O>
-PE_FI mat4 operator*(const mat4& a, const smat4<Z, O>& b) { return a * mat4(b); }
-template <unsigned Z, unsigned O>
-PE_FI mat4 operator*(const cmat4& a, const smat4<Z, O>& b) { return mat4(a) * mat4(b); }
-template <unsigned Z, unsigned O>
-PE_FI mat4 operator*(const smat4<Z, O>& a, const cmat4& b) { return a * mat4(b); }
-template <unsigned Z, unsigned O, unsigned Z2, unsigned O2>
-PE_FI mat4 operator*(const smat4<Z, O>& a, const smat4<Z2, O2>& b) { return a * mat4(b); }
+template <unsigned Z, unsigned O, unsigned F>
+PE_FI mat4 operator*(const smat4<Z, O, F>& a, const mat4& b) { return mat4(a * b.c[0], a * b.c[1], a * b.c[2], a * b.c[3]); }
+template <unsigned Z, unsigned O, unsigned F>
+PE_FI mat4 operator*(const mat4& a, const smat4<Z, O, F>& b) { return a * mat4(b); }
+template <unsigned Z, unsigned O, unsigned F>
+PE_FI mat4 operator*(const cmat4& a, const smat4<Z, O, F>& b) { return mat4(a) * mat4(b); }
+template <unsigned Z, unsigned O, unsigned F>
+PE_FI mat4 operator*(const smat4<Z, O, F>& a, const cmat4& b) { return a * mat4(b); }
+template <unsigned Z, unsigned O, unsigned F, unsigned Z2, unsigned O2, unsigned F2>
+PE_FI mat4 operator*(const smat4<Z, O, F>& a, const smat4<Z2, O2, F2>& b) { return a * mat4(b); }
 
 PE_FI vec3 operator*(const mat3& m, const vec3& v) {
     return vec3(::fmaf(m.c[2].x, v.z, ::fmaf(m.c[1].x, v.y, m.c[0].x * v.x)),

@@ -63,7 +63,7 @@ struct RaySlot {
 
 // One iteration of the reference's bounce loop body (frag.glsl:113-156).
 // Returns true when the ray has ended; `res` then holds its RayTraceResult.
-PE_FI bool bounce_once(RaySlot& s, float camera_scale, RayTraceResult& res) {
+PE_FI bool bounce_body(RaySlot& s, float camera_scale, RayTraceResult& res) {
     Ray& r = s.r;
     SceneIntersection i = scene_intersect(r);
     SceneIntersectionWithMaterial i2 = scene_intersect_material_process(r);
@@ -113,6 +113,45 @@ PE_FI bool bounce_once(RaySlot& s, float camera_scale, RayTraceResult& res) {
     return true;
 }
 
+#ifndef PE_CANON_RAYS
+#define PE_CANON_RAYS 1
+#endif
+#if PE_CANON_RAYS
+// The same bounce for a ray that is NOT canonical (origin.w != 1 or direction.w != 0: only a scene whose own GLSL builds such
+// rays, or a non-affine portal matrix, produces one).  Out of line, by value: a cold path that costs the hot one nothing.
+struct BounceOut {
+    RaySlot s;
+    RayTraceResult res;
+    bool done;
+};
+__noinline__ BounceOut bounce_general(RaySlot s, float camera_scale) {
+    BounceOut o;
+    o.res = RayTraceResult{vec3(0.0f), 0.0f, false};
+    o.done = bounce_body(s, camera_scale, o.res);
+    o.s = s;
+    return o;
+}
+#endif
+// Every ray the renderer makes has origin.w == 1 and direction.w == 0 and affine portal matrices keep it so.  Saying so to
+// the compiler -- as constants, behind a run-time check of exactly that -- lets it drop the w column of every transform by a
+// finite affine matrix (pe_library.cuh transform(), smat4::point / dir) and see that a translation leaves a direction
+// untouched, which makes the square roots and reciprocals of a snippet's portal-chain loop loop-invariant.
+PE_FI bool bounce_once(RaySlot& s, float camera_scale, RayTraceResult& res) {
+#if PE_CANON_RAYS
+    if (pe_canonical(s.r)) {
+        s.r.o.w = 1.0f;
+        s.r.d.w = 0.0f;
+        return bounce_body(s, camera_scale, res);
+    }
+    BounceOut o = bounce_general(s, camera_scale);
+    s = o.s;
+    res = o.res;
+    return o.done;
+#else
+    return bounce_body(s, camera_scale, res);
+#endif
+}
+
 // frag.glsl:506-513
 PE_FI vec2 quasi_random(int i) {
     float a1 = 0.7548776662466927600500267982588025643670318456949186300834636687f;
@@ -153,7 +192,9 @@ template <class M>
 PE_FI bool view_ray(const M& camera_matrix, vec2 image_position, vec2 resolution, bool in_subspace, RaySlot& s) {
     const float Pi = 3.14159265359f;
     const float Pi05 = Pi * 0.5f;
-    vec4 o = camera_matrix * vec4(0.0f, 0.0f, 0.0f, 1.0f);
+    vec4 o;
+    if constexpr (pe_canon_matrix<M>::value) o = camera_matrix.origin();      // finite affine camera: its translation column
+    else o = camera_matrix * vec4(0.0f, 0.0f, 0.0f, 1.0f);
     vec4 d;
     if (_use_panini_projection == 1) {
         d = normalize(camera_matrix * vec4(PaniniProjection(image_position, _view_angle, _panini_param), 0.0f));

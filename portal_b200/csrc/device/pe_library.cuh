@@ -74,8 +74,16 @@ PE_FI vec3 my_refract(vec3 dir, vec3 normal, float refractive_index) {  // libra
     return my_reflect(dir, normal);
 }
 
+// A ray whose origin is a point (w exactly 1) and whose direction is a direction (w exactly 0): every ray the renderer itself
+// makes, and what affine matrices keep.  Where the compiler can see the two constants the test folds away.
+PE_FI bool pe_canonical(const Ray& r) { return r.o.w == 1.0f && r.d.w == 0.0f; }
+
 template <class M>
 PE_FI Ray transform(const M& matrix, const Ray& r) {  // library.glsl:95-102
+    if constexpr (pe_canon_matrix<M>::value) {
+        // finite affine matrix x canonical ray: the w column of both products is known (smat4::point / dir, pe_glsl.cuh)
+        if (pe_canonical(r)) return Ray{matrix.point(r.o), matrix.dir(r.d), r.tmul, r.in_subspace};
+    }
     return Ray{matrix * r.o, matrix * r.d, r.tmul, r.in_subspace};
 }
 
@@ -90,7 +98,10 @@ PE_FI vec3 get_normal(const M& matrix) {
 
 PE_FI Ray normalize_ray(Ray r) {  // library.glsl:108-113
     float len = length(r.d);
-    r.d /= len;
+    // `r.d /= len` = r.d * (1 / len) component by component (pe_glsl.cuh); a direction's w stays the exact zero it is
+    // (0 * (1 / len) is a zero for every len but 0 and NaN, and then x, y, z are NaN already)
+    const float inv = 1.0f / len;
+    r.d = vec4(r.d.x * inv, r.d.y * inv, r.d.z * inv, (r.d.w == 0.0f) ? 0.0f : r.d.w * inv);
     r.tmul /= len;
     return r;
 }
@@ -172,10 +183,25 @@ PE_FI SurfaceIntersection plane_intersect_pre(Ray r, const M& plane_inv, vec3 un
 template <class M>
 PE_FI SurfaceIntersection plane_intersect_lazy(const SurfaceIntersection& best, const Ray& r, const M& plane_inv,
                                                vec3 unit_normal, bool& flipped) {
-    const float oz = plane_inv.template row<2>(r.o);
-    const float dz = plane_inv.template row<2>(r.d);
+    // (for a finite affine matrix and a canonical ray the rows are the shortened chains of smat4::point / dir)
+    float oz, dz;
+    bool canonical = false;
+    if constexpr (pe_canon_matrix<M>::value) canonical = pe_canonical(r);
+    if constexpr (pe_canon_matrix<M>::value) {
+        if (canonical) { oz = plane_inv.template row_impl<2, 1>(r.o); dz = plane_inv.template row_impl<2, 2>(r.d); }
+        else { oz = plane_inv.template row<2>(r.o); dz = plane_inv.template row<2>(r.d); }
+    } else {
+        oz = plane_inv.template row<2>(r.o);
+        dz = plane_inv.template row<2>(r.d);
+    }
     if ((__float_as_int(oz) ^ __float_as_int(dz)) >= 0) return intersection_none;
-    const vec4 d = vec4(plane_inv.template row<0>(r.d), plane_inv.template row<1>(r.d), dz, plane_inv.template row<3>(r.d));
+    vec4 d;
+    if constexpr (pe_canon_matrix<M>::value) {
+        if (canonical) d = vec4(plane_inv.template row_impl<0, 2>(r.d), plane_inv.template row_impl<1, 2>(r.d), dz, 0.0f);
+        else d = vec4(plane_inv.template row<0>(r.d), plane_inv.template row<1>(r.d), dz, plane_inv.template row<3>(r.d));
+    } else {
+        d = vec4(plane_inv.template row<0>(r.d), plane_inv.template row<1>(r.d), dz, plane_inv.template row<3>(r.d));
+    }
     const float q = dot(d, d);
     if (best.hit) {
         const float adz = ::fabsf(dz);
@@ -190,7 +216,14 @@ PE_FI SurfaceIntersection plane_intersect_lazy(const SurfaceIntersection& best, 
     const float t = -oz / dn.z;
     const float t_world = t / len;              // library.glsl:157
     if (!((t_world > 0.0f) && (!best.hit || (best.hit && t_world < best.t)))) return intersection_none;
-    const float ox = plane_inv.template row<0>(r.o), oy = plane_inv.template row<1>(r.o);
+    float ox, oy;
+    if constexpr (pe_canon_matrix<M>::value) {
+        if (canonical) { ox = plane_inv.template row_impl<0, 1>(r.o); oy = plane_inv.template row_impl<1, 1>(r.o); }
+        else { ox = plane_inv.template row<0>(r.o); oy = plane_inv.template row<1>(r.o); }
+    } else {
+        ox = plane_inv.template row<0>(r.o);
+        oy = plane_inv.template row<1>(r.o);
+    }
     flipped = dot(unit_normal, vec3(r.d)) > 0.0f;
     if (flipped) unit_normal *= -1.0f;
     return SurfaceIntersection{true, t_world, ox + dn.x * t, oy + dn.y * t, unit_normal};

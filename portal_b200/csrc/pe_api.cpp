@@ -270,19 +270,33 @@ std::vector<int> current_ints(pe_ctx* c) {
     return v;
 }
 
-// Structure of every scene matrix in the block: which entries are exactly 0 / exactly 1.
+// Structure of every scene matrix in the block: which entries are exactly 0 / exactly 1 (bits 0..15 of the two masks) and
+// whether all 16 are finite (bit 16 of the second).  Three more records follow for `_camera`, `_camera_left_eye`,
+// `_camera_right_eye`: of those only "the bottom row is exactly 0 0 0 1" and the finite flag are recorded -- a camera moves
+// every frame, whether it is affine does not change.
 std::vector<std::pair<unsigned, unsigned>> matrix_masks(pe_ctx* c) {
-    std::vector<std::pair<unsigned, unsigned>> out(size_t(c->layout.n_mat));
+    std::vector<std::pair<unsigned, unsigned>> out(size_t(c->layout.n_mat) + 3);
     const float* m = reinterpret_cast<const float*>(c->cblock.data() + c->layout.off_mat);
-    for (int k = 0; k < c->layout.n_mat; k++) {
+    auto masks_of = [&](int slot, bool bottom_row_only) {
         unsigned z = 0, o = 0;
+        bool finite = true;
         for (int e = 0; e < 16; e++) {
-            const float v = m[16 * k + e];
+            const float v = m[16 * slot + e];
+            if (!std::isfinite(v)) finite = false;
             if (v == 0.0f) z |= 1u << e;
             else if (v == 1.0f) o |= 1u << e;
         }
-        out[size_t(k)] = {z, o};
-    }
+        if (bottom_row_only) {
+            const bool affine = (z & 0x0888u) == 0x0888u && (o & 0x8000u);
+            z = affine ? 0x0888u : 0u;
+            o = affine ? 0x8000u : 0u;
+            if (!affine) finite = false;           // nothing to gain: keep one variant for every non-affine camera
+        }
+        return std::pair<unsigned, unsigned>{z, o | (finite ? 1u << 16 : 0u)};
+    };
+    for (int k = 0; k < c->layout.n_mat; k++) out[size_t(k)] = masks_of(k, false);
+    const int cams[3] = {c->layout.camera_slot, c->layout.camera_slot + 2, c->layout.camera_slot + 3};
+    for (int q = 0; q < 3; q++) out[size_t(c->layout.n_mat + q)] = masks_of(cams[q], true);
     return out;
 }
 
@@ -295,10 +309,11 @@ std::vector<int> variant_key(pe_ctx* c, const std::vector<int>& ints, const std:
         key[c->layout.int_slot["_aa_start"]] = 0;
     }
     if (c->opts.specialize_matrices)
-        for (auto& zo : masks) key.push_back(int(zo.first | (zo.second << 16)));
+        for (auto& zo : masks) { key.push_back(int(zo.first)); key.push_back(int(zo.second)); }
     key.push_back(c->opts.with_probe ? 1 : 0);
     key.push_back(c->opts.uniforms_in_smem);
     key.push_back(c->opts.tile_w);
+    key.push_back(c->opts.canon_rays ? 1 : 0);
     for (char d : c->opts.dynamic_ints) key.push_back(d);
     for (char d : c->opts.dynamic_mats) key.push_back(d);
     return key;
@@ -756,6 +771,7 @@ int pe_set_option(pe_ctx* c, const char* key, int value) {
     else if (k == "lazy_planes") c->opts.lazy_planes = value != 0;
     else if (k == "with_probe") c->opts.with_probe = value != 0;   // pe_probe_ray turns it on by itself; exposed for inspection
     else if (k == "adaptive") c->adapt = value != 0;
+    else if (k == "canon_rays") c->opts.canon_rays = value != 0;
     else if (k == "uniforms_in_smem") {
         if (value < 0 || value > 2) return c->fail("uniforms_in_smem must be 0 (constant bank), 1 (copy loop) or 2 (TMA bulk copy)");
         c->opts.uniforms_in_smem = value;

@@ -541,6 +541,7 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     hd << "#define PE_MIN_BLOCKS " << opts.min_blocks << "\n";
     hd << "#define PE_WITH_PROBE " << (opts.with_probe ? 1 : 0) << "\n";
     hd << "#define PE_TILE_W " << opts.tile_w << "\n";
+    hd << "#define PE_CANON_RAYS " << (opts.canon_rays ? 1 : 0) << "\n";
     std::string swz_err;
     hd << "#define PE_SWZ_VEC2" << swizzle_macro(body.swz, 2) << lvalue_swizzle_macro(body.swz_w, 2, swz_err) << "\n";
     hd << "#define PE_SWZ_VEC3" << swizzle_macro(body.swz, 3) << lvalue_swizzle_macro(body.swz_w, 3, swz_err) << "\n";
@@ -594,17 +595,32 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     // uniform declarations (scene.rs:661-718) -> names bound to the block / to specialisation constants
     for (int k = 0; k < L.n_mat; k++) {
         if (opts.specialize_matrices && size_t(k) < matrix_masks.size() && (matrix_masks[k].first | matrix_masks[k].second)) {
-            char buf[96];
-            std::snprintf(buf, sizeof buf, "(pe::smat4<0x%04xu, 0x%04xu>{PE_C.m[%d]})", matrix_masks[k].first, matrix_masks[k].second, k);
+            char buf[128];
+            std::snprintf(buf, sizeof buf, "(pe::smat4<0x%04xu, 0x%04xu, %uu>{PE_C.m[%d]})", matrix_masks[k].first, matrix_masks[k].second & 0xffffu,
+                          opts.canon_rays ? (matrix_masks[k].second >> 16) & 1u : 0u, k);
             hd << "#define " << L.mats[k] << " " << buf << "\n";
         } else {
             hd << "#define " << L.mats[k] << " (PE_C.m[" << k << "])\n";
         }
     }
-    hd << "#define _camera (PE_C.m[" << L.camera_slot << "])\n";
+    {   // cameras: only "bottom row is 0 0 0 1" and "finite" are baked in (masks n_mat, n_mat + 1, n_mat + 2)
+        const char* names[3] = {"_camera", "_camera_left_eye", "_camera_right_eye"};
+        const int slots[3] = {L.camera_slot, L.camera_slot + 2, L.camera_slot + 3};
+        for (int q = 0; q < 3; q++) {
+            const size_t k = size_t(L.n_mat + q);
+            const bool flagged = opts.specialize_matrices && opts.canon_rays && k < matrix_masks.size() &&
+                                 (matrix_masks[k].first | matrix_masks[k].second);
+            if (flagged) {
+                char buf[128];
+                std::snprintf(buf, sizeof buf, "(pe::smat4<0x%04xu, 0x%04xu, %uu>{PE_C.m[%d]})", matrix_masks[k].first,
+                              matrix_masks[k].second & 0xffffu, (matrix_masks[k].second >> 16) & 1u, slots[q]);
+                hd << "#define " << names[q] << " " << buf << "\n";
+            } else {
+                hd << "#define " << names[q] << " (PE_C.m[" << slots[q] << "])\n";
+            }
+        }
+    }
     hd << "#define _camera_mul_inv (PE_C.m[" << (L.camera_slot + 1) << "])\n";
-    hd << "#define _camera_left_eye (PE_C.m[" << (L.camera_slot + 2) << "])\n";
-    hd << "#define _camera_right_eye (PE_C.m[" << (L.camera_slot + 3) << "])\n";
     for (int k = 0; k < L.n_float; k++) hd << "#define " << L.floats[k] << " (PE_C.f[" << k << "])\n";
     for (int k = 0; k < kNumRendererFloats; k++) hd << "#define " << kRendererFloats[k] << " (PE_C.f[" << (L.n_float + k) << "])\n";
     auto int_is_dynamic = [&](int slot) { return size_t(slot) < opts.dynamic_ints.size() && opts.dynamic_ints[size_t(slot)]; };

@@ -103,6 +103,9 @@ struct GenOptions {
     int uniforms_in_smem = 0;
     // Width of a warp's pixel tile in the one-thread-per-pixel kernel: 8 (8x4), 16 (16x2) or 32 (32x1); see pe_kernel.cuh.
     int tile_w = 8;
+    // rays are checked for origin.w == 1 / direction.w == 0 once per bounce and then carry those as constants; matrices get a
+    // "all entries finite" flag next to their 0 / 1 structure (pe_glsl.cuh smat4<Z, O, F>, pe_kernel.cuh bounce_once)
+    bool canon_rays = true;
     bool unroll_loops = true;  // false: `#pragma unroll 1` on every loop of the user snippets (smaller code)
     // per slot of i[] / per scene matrix: 1 = read it from the constant block even when specialisation is on (slots whose
     // value kept changing between renders, pe_api.cpp select_variant)
@@ -116,8 +119,9 @@ struct GenResult {
 
 // int_values: current value of every slot of i[] (scene ints then renderer ints); used when
 // opts.specialize_ints.
-// matrix_masks: per scene matrix slot (zero mask, one mask), bit 4*column + row; used when
-// opts.specialize_matrices.
+// matrix_masks: per scene matrix slot, then `_camera`, `_camera_left_eye`, `_camera_right_eye`: (zero mask, one mask | finite
+// flag << 16), bit 4*column + row; used when opts.specialize_matrices.  The three cameras only ever carry their bottom row
+// and the finite flag (they change every frame; whether they are affine does not).
 GenResult generate_program(const SceneDesc& scene, const ConstLayout& layout, const GenOptions& opts,
                            const std::vector<int>& int_values,
                            const std::vector<std::pair<unsigned, unsigned>>& matrix_masks);

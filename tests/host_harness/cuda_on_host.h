@@ -10,6 +10,7 @@
 #include <cstring>
 
 #define __forceinline__ inline
+#define __noinline__
 #define __constant__
 #define __global__
 #define __device__

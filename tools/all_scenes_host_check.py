@@ -24,21 +24,13 @@ from portal_b200.renderer import SceneRenderer  # noqa: E402
 HH = os.path.join(ROOT, "tests", "host_harness")
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("reference")
-    ap.add_argument("--size", default="96x54")
-    ap.add_argument("--depth", type=int, default=30)
-    ap.add_argument("--only", default="")
-    args = ap.parse_args()
-    w, h = (int(x) for x in args.size.split("x"))
-    only = {x for x in args.only.split(",") if x}
+def one(job):
+    path, reference, w, h, depth = job
     from PIL import Image
-    same = diff = skipped = 0
-    for path in sorted(glob.glob(os.path.join(args.reference, "scenes", "*.ron"))):
-        name = os.path.basename(path)[:-4]
-        if name == "empty" or (only and name not in only):
-            continue
+    name = os.path.basename(path)[:-4]
+    args = argparse.Namespace(reference=reference, depth=depth)
+    ok = None
+    if True:
         t0 = time.time()
         try:
             ir = frontend.scene_ir(frontend.load_scene(path), name)
@@ -60,14 +52,33 @@ def main():
             subprocess.run(cmd, check=True, timeout=1200)
             got = np.fromfile(f"{d}/out.f32", dtype=np.float32).reshape(h, w, 4)
             want = Oracle(ir, "strict", textures=tex).render(w, h, args.depth)
-            ok = np.array_equal(got.view(np.uint32), want.view(np.uint32))
-            same += ok
-            diff += not ok
-            status = "bit-identical" if ok else f"DIFFERS in {(np.abs(got - want) > 0).any(axis=-1).sum()} pixels"
+            ok = bool(np.array_equal(got.view(np.uint32), want.view(np.uint32)))
+            status = "bit-identical" if ok else f"DIFFERS in {(got.view(np.uint32) != want.view(np.uint32)).any(axis=-1).sum()} pixels"
         except (PortalB200Error, NotImplementedError, subprocess.CalledProcessError, KeyError, FileNotFoundError) as e:
-            skipped += 1
             status = "skipped: " + str(e).strip().splitlines()[0][:120]
-        print(f"{name:40s} {time.time() - t0:6.1f} s  {status}", flush=True)
+        return f"{name:40s} {time.time() - t0:6.1f} s  {status}", ok
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("reference")
+    ap.add_argument("--size", default="96x54")
+    ap.add_argument("--depth", type=int, default=30)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--jobs", type=int, default=8)
+    args = ap.parse_args()
+    w, h = (int(x) for x in args.size.split("x"))
+    only = {x for x in args.only.split(",") if x}
+    jobs = [(p, args.reference, w, h, args.depth) for p in sorted(glob.glob(os.path.join(args.reference, "scenes", "*.ron")))
+            if os.path.basename(p) != "empty.ron" and (not only or os.path.basename(p)[:-4] in only)]
+    import concurrent.futures as cf
+    same = diff = skipped = 0
+    with cf.ProcessPoolExecutor(args.jobs) as ex:
+        for line, ok in ex.map(one, jobs):
+            print(line, flush=True)
+            same += ok is True
+            diff += ok is False
+            skipped += ok is None
     print(f"{same} scenes bit-identical, {diff} differ, {skipped} skipped")
     return 0 if diff == 0 else 1
 
