@@ -12,6 +12,8 @@
 struct ph_scene {
     ph::Scene scene;
     std::vector<ph::TableEntry> table;
+    uint64_t table_fingerprint = 0;   // Scene::input_fingerprint() the table was evaluated for
+    bool table_valid = false;
     std::string err;
 };
 
@@ -163,10 +165,15 @@ int ph_scene_stage_name(ph_scene* s, int k, const char** name) {
 
 int ph_scene_evaluate(ph_scene* s) {
     if (!s) return -1;
+    const uint64_t fp = s->scene.input_fingerprint();
+    if (s->table_valid && fp == s->table_fingerprint) return int(s->table.size());   // nothing the table depends on has changed
+    s->table_valid = false;
     if (!s->scene.uniform_table(s->table)) {
         s->err = s->scene.error;
         return -1;
     }
+    s->table_fingerprint = fp;
+    s->table_valid = true;
     return int(s->table.size());
 }
 

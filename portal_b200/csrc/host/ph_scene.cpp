@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <limits>
 #include <stdexcept>
 
@@ -832,7 +833,7 @@ bool Scene::get_matrix(int id, Mat4& out, std::vector<int>& visited) {
     if (id < 0 || id >= int(matrices.size())) return false;
     if (std::find(visited.begin(), visited.end(), id) != visited.end()) return false;
     visited.push_back(id);
-    const Matrix m = matrices[id];
+    const Matrix& m = matrices[id];
     bool ok = true;
     Mat4 A, B, Cc;
     switch (m.kind) {
@@ -896,6 +897,47 @@ bool Scene::get_matrix(int id, Mat4& out, std::vector<int>& visited) {
     }
     visited.pop_back();
     return ok;
+}
+
+uint64_t Scene::input_fingerprint() const {
+    uint64_t h = 0x9e3779b97f4a7c15ull;
+    auto mix_w = [&](uint64_t w) {                    // one 64-bit word per step (splitmix-style finaliser)
+        h ^= w + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+        h *= 0xbf58476d1ce4e5b9ull;
+        h ^= h >> 31;
+    };
+    auto mix = [&](const void* p, size_t n) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        size_t k = 0;
+        for (; k + 8 <= n; k += 8) { uint64_t w; std::memcpy(&w, b + k, 8); mix_w(w); }
+        if (k < n) { uint64_t w = 0; std::memcpy(&w, b + k, n - k); mix_w(w ^ (uint64_t(n - k) << 56)); }
+    };
+    auto mix_d = [&](double v) { uint64_t w; std::memcpy(&w, &v, 8); mix_w(w); };
+    auto mix_i = [&](long long v) { mix_w(uint64_t(v)); };
+    mix_d(time); mix_d(total_time);
+    bool uses_camera = false;
+    mix_i((long long)uniforms.size());
+    for (const Uniform& u : uniforms) {
+        mix_i((long long)u.kind | ((long long)u.b << 8) | ((long long)(unsigned)u.i << 16)); mix_d(u.f);
+        if (!u.text.empty()) mix(u.text.data(), u.text.size());
+        if (u.kind == Uniform::Trefoil) mix(u.trefoil, sizeof u.trefoil);
+    }
+    mix_i((long long)matrices.size());
+    for (const Matrix& m : matrices) {
+        mix_i((long long)m.kind | ((long long)(m.a + 1) << 8) | ((long long)(m.b + 1) << 24) | ((long long)(m.c + 1) << 40));
+        switch (m.kind) {
+            case Matrix::Simple:
+                mix(m.offset, sizeof m.offset); mix(m.rotate, sizeof m.rotate); mix_d(m.scale);
+                mix_i(m.mirror[0] | (m.mirror[1] << 1) | (m.mirror[2] << 2));
+                break;
+            case Matrix::Camera: uses_camera = true; break;
+            case Matrix::Mul: case Matrix::Teleport: case Matrix::Inv: case Matrix::Sqrt: break;
+            default:
+                for (const Param& q : m.p) { mix_i((long long)q.is_uniform | ((long long)(q.uniform + 1) << 8)); mix_d(q.value); }
+        }
+    }
+    if (uses_camera) mix(camera_matrix_for_formulas.data(), sizeof(double) * 16);   // only the `Camera` matrix kind reads it
+    return h;
 }
 
 bool Scene::uniform_table(std::vector<TableEntry>& out) {

@@ -11,6 +11,7 @@
 // in ph_scene.cpp so that singular matrices give the same Inf/NaN patterns.
 #pragma once
 #include <array>
+#include <cstdint>
 #include <map>
 #include <string>
 #include <vector>
@@ -170,6 +171,10 @@ struct Scene {
     bool get_matrix(int id, Mat4& out, std::vector<int>& visited);
     // Scene::uniforms + Scene::set_uniforms: the evaluated table in upload order
     bool uniform_table(std::vector<TableEntry>& out);
+    // Hash of everything uniform_table() reads (time, formula camera, every uniform's and matrix's fields): when it has not
+    // changed since the last evaluation the table has not either -- a frame loop that only moves the camera skips the
+    // float64 evaluation of the whole matrix DAG.
+    uint64_t input_fingerprint() const;
 };
 
 }  // namespace ph

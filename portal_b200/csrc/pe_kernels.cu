@@ -67,19 +67,31 @@ __global__ void __launch_bounds__(256) pe_k_quantize_rgba8(const float4* __restr
 __global__ void __launch_bounds__(256) pe_k_deinterleave(const float4* __restrict__ gathered, float4* __restrict__ frame,
                                                          int width, int height, int strip_rows, int n_ranks,
                                                          int strips_per_rank) {
-    for (int y = blockIdx.y; y < height; y += gridDim.y) {
+    auto row_src = [&](int y) {
         const int gstrip = y / strip_rows;
         const int rank = gstrip % n_ranks;
         const int lstrip = gstrip / n_ranks;
-        const float4* src = gathered + ((size_t(rank) * strips_per_rank + lstrip) * strip_rows + size_t(y - gstrip * strip_rows)) * size_t(width);
-        float4* dst = frame + size_t(y) * size_t(width);
-        const int step = blockDim.x * gridDim.x;
+        return gathered + ((size_t(rank) * strips_per_rank + lstrip) * strip_rows + size_t(y - gstrip * strip_rows)) * size_t(width);
+    };
+    const int step = blockDim.x * gridDim.x;
+    // two rows per pass: eight 16-byte loads in flight per thread before the first store
+    int y = blockIdx.y;
+    for (; y + int(gridDim.y) < height; y += 2 * gridDim.y) {
+        const float4 *s0 = row_src(y), *s1 = row_src(y + gridDim.y);
+        float4 *d0 = frame + size_t(y) * size_t(width), *d1 = frame + size_t(y + gridDim.y) * size_t(width);
         int x = blockIdx.x * blockDim.x + threadIdx.x;
         for (; x + 3 * step < width; x += 4 * step) {
-            float4 a = ld_stream(src + x), b = ld_stream(src + x + step), c = ld_stream(src + x + 2 * step), d = ld_stream(src + x + 3 * step);
-            st_stream(dst + x, a); st_stream(dst + x + step, b); st_stream(dst + x + 2 * step, c); st_stream(dst + x + 3 * step, d);
+            float4 a = ld_stream(s0 + x), b = ld_stream(s0 + x + step), c = ld_stream(s0 + x + 2 * step), d = ld_stream(s0 + x + 3 * step);
+            float4 e = ld_stream(s1 + x), f = ld_stream(s1 + x + step), g = ld_stream(s1 + x + 2 * step), h = ld_stream(s1 + x + 3 * step);
+            st_stream(d0 + x, a); st_stream(d0 + x + step, b); st_stream(d0 + x + 2 * step, c); st_stream(d0 + x + 3 * step, d);
+            st_stream(d1 + x, e); st_stream(d1 + x + step, f); st_stream(d1 + x + 2 * step, g); st_stream(d1 + x + 3 * step, h);
         }
-        for (; x < width; x += step) st_stream(dst + x, ld_stream(src + x));
+        for (; x < width; x += step) { st_stream(d0 + x, ld_stream(s0 + x)); st_stream(d1 + x, ld_stream(s1 + x)); }
+    }
+    for (; y < height; y += gridDim.y) {
+        const float4* src = row_src(y);
+        float4* dst = frame + size_t(y) * size_t(width);
+        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < width; x += step) st_stream(dst + x, ld_stream(src + x));
     }
 }
 
@@ -99,7 +111,12 @@ __device__ __forceinline__ void acc_sq(unsigned w, unsigned& r, unsigned& g, uns
 
 // Motion-blur mean in gamma-2 space.  A thread owns 4 consecutive pixels (one 16-byte load per sub-frame, one 16-byte
 // store); the loads of 4 sub-frames are issued together.
-__global__ void __launch_bounds__(256) pe_k_average_rgba8(FramePtrs frames, int n_frames, uchar4* __restrict__ out, size_t n) {
+// `magic` = ceil(2^32 / n_frames): for sums below 2^23 (64 frames x 255^2 < 2^22) __umulhi(sum, magic) == sum / n_frames
+// exactly (the error term sum * (magic - 2^32 / n) / 2^32 < 2^-9 cannot carry past the next integer: the fractional part of
+// sum / n is at most 1 - 1/64) -- one IMAD.HI instead of a ~20-instruction unsigned division per channel.
+__device__ __forceinline__ unsigned div_n(unsigned sum, unsigned magic, unsigned nn) { return nn == 1u ? sum : __umulhi(sum, magic); }
+
+__global__ void __launch_bounds__(256) pe_k_average_rgba8(FramePtrs frames, int n_frames, unsigned magic, uchar4* __restrict__ out, size_t n) {
     const size_t n4 = n >> 2;
     const size_t stride = size_t(gridDim.x) * blockDim.x;
     const unsigned nn = (unsigned)n_frames;
@@ -122,7 +139,8 @@ __global__ void __launch_bounds__(256) pe_k_average_rgba8(FramePtrs frames, int 
         }
         unsigned o[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) o[k] = l_to_s(r[k] / nn) | (l_to_s(gg[k] / nn) << 8) | (l_to_s(b[k] / nn) << 16) | 0xff000000u;
+        for (int k = 0; k < 4; k++)
+            o[k] = l_to_s(div_n(r[k], magic, nn)) | (l_to_s(div_n(gg[k], magic, nn)) << 8) | (l_to_s(div_n(b[k], magic, nn)) << 16) | 0xff000000u;
         st_stream(reinterpret_cast<uint4*>(out) + g, make_uint4(o[0], o[1], o[2], o[3]));
     }
     const size_t i = (n4 << 2) + size_t(blockIdx.x) * blockDim.x + threadIdx.x;   // ragged tail: at most 3 pixels
@@ -206,7 +224,8 @@ int launch_average_rgba8(const void* const* frames, int n_frames, void* out, siz
     for (int i = 0; i < n_frames; i++) fp.p[i] = (const uchar4*)frames[i];
     bool vec = aligned16(out);
     for (int i = 0; i < n_frames; i++) vec = vec && aligned16(frames[i]);
-    if (vec) pe_k_average_rgba8<<<grid_for((n + 3) / 4, sms), 256, 0, s>>>(fp, n_frames, (uchar4*)out, n);
+    const unsigned magic = n_frames > 1 ? unsigned(((1ull << 32) + unsigned(n_frames) - 1) / unsigned(n_frames)) : 0u;
+    if (vec) pe_k_average_rgba8<<<grid_for((n + 3) / 4, sms), 256, 0, s>>>(fp, n_frames, magic, (uchar4*)out, n);
     else pe_k_average_rgba8_px<<<grid_for(n, sms), 256, 0, s>>>(fp, n_frames, (unsigned*)out, n);
     return (int)cudaGetLastError();
 }
