@@ -19,6 +19,7 @@
 #include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statvfs.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -208,8 +209,12 @@ int pe_sharder_create(pe_ctx* ctx, const char* name, int width, int height, int 
         unlink(s->path.c_str());
         fd = open(s->path.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
         if (fd < 0) return bail("pe_sharder_create: cannot create " + s->path);
-        // posix_fallocate reserves the pages now: a tmpfs that is too small fails HERE, not with SIGBUS at the first touch
-        if (ftruncate(fd, off_t(s->map_bytes)) != 0 || posix_fallocate(fd, 0, off_t(s->map_bytes)) != 0) {
+        // A tmpfs that is too small turns the first touch into SIGBUS: decide up front.  (Not posix_fallocate: it would
+        // allocate every page HERE, on rank 0's NUMA node; the pages of a rank's strips are to be first touched -- and so
+        // placed -- next to the GPU that writes them, below.)
+        struct statvfs vfs;
+        const bool roomy = fstatvfs(fd, &vfs) == 0 && double(vfs.f_bavail) * double(vfs.f_frsize) >= double(s->map_bytes) + double(64u << 20);
+        if (!roomy || ftruncate(fd, off_t(s->map_bytes)) != 0) {
             close(fd);
             unlink(s->path.c_str());
             s->path.clear();
