@@ -140,6 +140,10 @@ PE_API int ph_player_set_run_animations(ph_player* p, int on);
  * a portal that lies between it and the camera -- and the render calls send them with `_draw_side_by_side`.
  * The caller doubles the frame width, as `render --stereo-image` does (src/main.rs:2809-2816). */
 PE_API int ph_player_set_stereo(ph_player* p, int draw_side_by_side, double eye_distance, int swap_eyes);
+/* What SceneRenderer::update_inner_variables (src/main.rs:1696-1755) changed when the current animation was entered
+ * (ph_player_init_animation applies it, as render-frame and the `render` loop do): besides the `subspace_degree` uniform it
+ * hard-codes by animation name, the render depth (100) and frame rate (600) the caller is to use; 0 = no override. */
+PE_API int ph_player_animation_overrides(ph_player* p, int32_t* render_depth, int32_t* fps);
 /* Anaglyph stereo (SceneRenderer::draw_anaglyph / anaglyph_mode "Colorful anaglyph" / anaglyph_p 0.29 / anaglyph_q 0.06,
  * main.rs:1030-1033, 1308-1315, 1549-1580; shader frag.glsl:343-406, 467-473): every sample is traced through both eye
  * cameras (the same ones side-by-side uses, teleported through portals alike: main.rs:1122) and combined red / cyan. */

@@ -392,6 +392,31 @@ class Player:
 
     def init_animation(self, name):
         self.anim.init_animation_by_name(name, self.memory)
+        self.update_inner_variables(name)          # render-frame, main.rs:2906-2917
+
+    _DEGREE_500 = ("v2.face.2", "v2.face.3", "v2.face.4", "v2.face.5", "v2.inside.1", "v2.inside.3", "v2.intro.1", "v2.normal.2",
+                   "v2.normal.3", "v2.rod.2", "v2.rod.3", "v2.spiral.3", "v2.spiral.4", "v2.spiral.5", "v2.spiral.6", "v2.spiral.7",
+                   "v2.spiral.9", "v2.spaaaace.0", "v4.golden.0", "v4.golden.1", "v4.golden.2", "v4.thumbnail.2")
+
+    def update_inner_variables(self, name):
+        """SceneRenderer::update_inner_variables (main.rs:1696-1755): overrides hard-coded by animation name."""
+        from .ron import Tagged
+        self.render_depth_override = self.fps_override = 0
+
+        def set_degree(v):
+            uid = self.scene.uniform_by_name.get("subspace_degree")
+            if uid is None:
+                return False                       # `find_id(..)?` leaves the function
+            self.scene.uniforms[uid] = Tagged("Int", [{"min": None, "max": None, "value": v}])
+            return True
+        if name in self._DEGREE_500 and not set_degree(500):
+            return
+        if name in ("v2.spiral.4", "v2.spiral.5", "v2.spiral.6") and not set_degree(1000):
+            return
+        if name in ("v2.rotated.0", "v2.spiral.0", "v2.screenshot.5", "v2.screenshot.6"):
+            self.render_depth_override = 100
+        if name == "v2.screenshot.3":
+            self.fps_override = 600
 
     def select_camera(self, name):
         if name not in self.anim.camera_by_name:

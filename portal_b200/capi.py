@@ -152,6 +152,7 @@ def lib() -> C.CDLL:
         "ph_player_camera": (i32, [vp, f64p, f64p, C.POINTER(i32), f64p, f64p, f64p, C.POINTER(C.c_int64)]),
         "ph_player_set_stereo": (i32, [vp, i32, C.c_double, i32]),
         "ph_player_set_run_animations": (i32, [vp, i32]),
+        "ph_player_animation_overrides": (i32, [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "ph_player_set_anaglyph": (i32, [vp, i32, i32, C.c_double, C.c_double]),
         "ph_player_eyes": (i32, [vp, f64p, f64p, C.POINTER(i32), C.POINTER(i32)]),
         "ph_scene_animation_count": (i32, [vp]),

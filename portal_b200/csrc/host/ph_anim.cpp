@@ -134,7 +134,39 @@ bool Player::init_animation_by_name(const std::string& name) {
     StageRef r;
     r.kind = StageRef::Real;
     r.index = it->second;
-    return init_stage(r);
+    if (!init_stage(r)) return false;
+    update_inner_variables(name);
+    return true;
+}
+
+void Player::update_inner_variables(const std::string& name) {
+    static const char* const k500[] = {"v2.face.2", "v2.face.3", "v2.face.4", "v2.face.5", "v2.inside.1", "v2.inside.3", "v2.intro.1",
+                                       "v2.normal.2", "v2.normal.3", "v2.rod.2", "v2.rod.3", "v2.spiral.3", "v2.spiral.4", "v2.spiral.5",
+                                       "v2.spiral.6", "v2.spiral.7", "v2.spiral.9", "v2.spaaaace.0", "v4.golden.0", "v4.golden.1",
+                                       "v4.golden.2", "v4.thumbnail.2"};
+    static const char* const k1000[] = {"v2.spiral.4", "v2.spiral.5", "v2.spiral.6"};
+    static const char* const kDepth100[] = {"v2.rotated.0", "v2.spiral.0", "v2.screenshot.5", "v2.screenshot.6"};
+    auto in = [&](const char* const* list, size_t n) {
+        for (size_t k = 0; k < n; k++)
+            if (name == list[k]) return true;
+        return false;
+    };
+    render_depth_override = fps_override = 0;
+    // `find_id("subspace_degree")?`: a scene without that uniform leaves the function at once -- also before the depth / fps
+    // overrides, exactly as the `?` does in the reference
+    auto set_degree = [&](int v) {
+        auto it = sc.uniform_by_name.find("subspace_degree");
+        if (it == sc.uniform_by_name.end()) return false;
+        Uniform u;
+        u.kind = Uniform::Int;
+        u.i = v;
+        sc.uniforms[size_t(it->second)] = u;      // get_original_mut: the stored element itself
+        return true;
+    };
+    if (in(k500, sizeof k500 / sizeof *k500) && !set_degree(500)) return;
+    if (in(k1000, sizeof k1000 / sizeof *k1000) && !set_degree(1000)) return;
+    if (in(kDepth100, sizeof kDepth100 / sizeof *kDepth100)) render_depth_override = 100;
+    if (name == "v2.screenshot.3") fps_override = 600;
 }
 
 bool Player::select_camera(const std::string& name) {

@@ -71,6 +71,11 @@ struct Player {
     bool init_stage(const StageRef& stage);
     bool init_stage_by_name(const std::string& name);
     bool init_animation_by_name(const std::string& name);
+    // SceneRenderer::update_inner_variables (main.rs:1696-1755), which render-frame and the `render` loop call right after
+    // init_animation_by_name: overrides hard-coded by animation name -- the `subspace_degree` uniform (500 / 1000), the render
+    // depth (100) and the frame rate (600).  0 = no override.
+    void update_inner_variables(const std::string& animation_name);
+    int render_depth_override = 0, fps_override = 0;
     bool select_camera(const std::string& name);
     bool update(double time);  // SceneRenderer::update
 

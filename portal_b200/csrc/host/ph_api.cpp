@@ -458,6 +458,13 @@ int ph_player_set_stereo(ph_player* p, int draw_side_by_side, double eye_distanc
     return 0;
 }
 
+int ph_player_animation_overrides(ph_player* p, int32_t* render_depth, int32_t* fps) {
+    if (!p) return 1;
+    if (render_depth) *render_depth = p->player.render_depth_override;
+    if (fps) *fps = p->player.fps_override;
+    return 0;
+}
+
 int ph_player_set_anaglyph(ph_player* p, int draw_anaglyph, int colorful, double anaglyph_p, double anaglyph_q) {
     if (!p) return 1;
     p->player.draw_anaglyph = draw_anaglyph != 0;

@@ -184,6 +184,12 @@ class HostPlayer:
     def set_stereo(self, draw_side_by_side: bool, eye_distance: float = 0.07, swap_eyes: bool = False):
         self._check(self._lib.ph_player_set_stereo(self._p, int(draw_side_by_side), float(eye_distance), int(swap_eyes)))
 
+    def animation_overrides(self) -> dict:
+        """update_inner_variables (main.rs:1696-1755) for the animation entered last: {"render_depth": n | 0, "fps": n | 0}."""
+        d, f = C.c_int32(), C.c_int32()
+        self._check(self._lib.ph_player_animation_overrides(self._p, C.byref(d), C.byref(f)))
+        return {"render_depth": d.value, "fps": f.value}
+
     def set_anaglyph(self, draw_anaglyph: bool, colorful: bool = False, p: float = 0.29, q: float = 0.06):
         self._check(self._lib.ph_player_set_anaglyph(self._p, int(draw_anaglyph), int(colorful), float(p), float(q)))
 

@@ -464,3 +464,36 @@ def test_players_agree_on_random_animations(seed, tmp_path):
         p.update(t)
         hp.update(t)
         _assert_same_state(p, hp, s, hs, (seed, "run", t))
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (GPU box)")
+def test_per_animation_overrides_of_update_inner_variables():
+    """SceneRenderer::update_inner_variables (main.rs:1696-1755), applied right after init_animation_by_name as render-frame
+    does: `subspace_degree` becomes Int(500) / Int(1000) for the listed animation names, render depth 100 / fps 600 for others;
+    a scene WITHOUT `subspace_degree` leaves the function at the `?` -- before the depth override.  C++ player == oracle
+    player, uniform table included."""
+    seen = {"degree500": 0, "degree1000": 0, "depth": 0, "fps": 0, "early_exit": 0}
+    for scene in ("portal_in_portal", "portal_in_portal_cone", "portal_in_portal_plus_ultra", "teleportation_degrees", "recursive_space"):
+        path = f"{REFERENCE}/scenes/{scene}.ron"
+        _, p0, _, _ = _pair(path)
+        for an in [a["name"] for a in p0.anim.animations]:
+            s, p, hs, hp = _pair(path)
+            p.init_animation(an)
+            hp.init_animation(an)
+            ov = hp.animation_overrides()
+            assert ov == {"render_depth": p.render_depth_override, "fps": p.fps_override}, (scene, an)
+            p.update(0.1)
+            hp.update(0.1)
+            _assert_same_state(p, hp, s, hs, (scene, an))
+            table = hs.uniform_table()
+            has_degree = "subspace_degree_u" in table
+            if an in p._DEGREE_500 and has_degree:
+                want = 1000 if an in ("v2.spiral.4", "v2.spiral.5", "v2.spiral.6") else 500
+                assert table["subspace_degree_u"] == ("int", want), (scene, an)
+                seen["degree1000" if want == 1000 else "degree500"] += 1
+            if an in p._DEGREE_500 and not has_degree:
+                assert ov == {"render_depth": 0, "fps": 0}
+                seen["early_exit"] += 1
+            seen["depth"] += ov["render_depth"] == 100
+            seen["fps"] += ov["fps"] == 600
+    assert seen["degree500"] >= 1 and seen["depth"] >= 1 and seen["fps"] >= 1, seen
