@@ -269,6 +269,7 @@ def run_ours(args):
         target = sharder.target
         n_px_local = sum(1 for y in D.local_rows(h, rank, world, STRIP_ROWS) if y >= 0) * w
     last = {"ptr": None}
+    overlapped = world > 1 and mode == "owner" and not args.no_overlap and not args.persistent
 
     def render_once(i):
         """Enqueue one frame (this rank's part of it) on the stream."""
@@ -284,6 +285,8 @@ def run_ours(args):
             if rank == 0:
                 check(lib.pe_deinterleave_strips(ctx, gathered.data_ptr(), frame_dev.data_ptr(), w, h, STRIP_ROWS, world, spr, sptr))
             last["ptr"] = out
+        elif overlapped:
+            sharder.render_overlapped(sptr)    # two frames in flight: the tail of one runs under the head of the next
         else:
             last["ptr"] = sharder.render(sptr)
             sharder.release(sptr)              # p2p, rank 0: the frame's consumer (nothing, here) has been enqueued
@@ -314,6 +317,8 @@ def run_ours(args):
         kev[i][0].record(stream)
         step(i)
         kev[i][1].record(stream)
+    if overlapped:
+        last["ptr"] = sharder.flush(sptr)      # the stream now waits for the frames still in flight: they are inside the timed region
     ev[1].record(stream)
     barrier()
     t_epoch1 = time.time()
@@ -325,6 +330,8 @@ def run_ours(args):
         dist.all_reduce(kms, op=dist.ReduceOp.MAX)
         dist.all_reduce(launches, op=dist.ReduceOp.SUM)        # every rank's kernels count
     total_ms, kernel_ms = float(ms.item()), float(kms.item())
+    if overlapped:
+        kernel_ms = total_ms / args.steps      # launches overlap: per-launch events mean nothing, the frame period does
 
     # ---- parity of the value leg: the LAST frame the timed loop produced, hashed against the oracle's pin.  A camera orbit has
     # pins for frames 0 and orbit / 2 only: those two are rendered once more, untimed, through the very same step.
@@ -383,6 +390,8 @@ def run_ours(args):
         for k in (0, args.orbit // 2):
             frame_counter[0] = k
             step(args.steps + k)
+            if overlapped:
+                last["ptr"] = sharder.flush(sptr)
             barrier()
             recs.append(hash_value_frame(k))
         if rank == 0:
@@ -480,23 +489,33 @@ def run_ours(args):
     else:
         hs = D.NativeSharder(r, w, h, rank, world, "host", "rgba8", STRIP_ROWS)
 
+        LAG = D.NativeSharder.PIPELINE_DEPTH - 1     # a rank keeps this many frames in flight behind the one it submits
+
         def pipelined_n(n):
-            prev, k, fr = None, None, None
-            for _ in range(n):
+            k, fr, done = None, None, 0
+
+            def finish(f, last):
+                hs.complete(f)
+                if rank == 0:
+                    v = hs.wait_frame(f, view=last)          # the whole frame f is in host memory: the consumer may read it
+                    out = v.copy() if last else None
+                    hs.release_frame(f)
+                    return out
+                return None
+            first = None
+            for i in range(n):
                 k = e2e_uniforms()
                 f = hs.submit()
-                if prev is not None:
-                    hs.complete(prev)
-                    if rank == 0:
-                        hs.wait_frame(prev)          # the whole frame i-1 is in host memory: the consumer may read it
-                        hs.release_frame(prev)
-                prev = f
-            hs.complete(prev)
-            if rank == 0:
-                fr = hs.wait_frame(prev).copy()
-                hs.release_frame(prev)
+                if first is None:
+                    first = f
+                if i >= LAG:
+                    finish(first + done, False)
+                    done += 1
+            while done < n:
+                fr = finish(first + done, done == n - 1)
+                done += 1
             return k, fr
-        pipelined_n(3)
+        pipelined_n(2 * LAG + 2)
         barrier()
         e2e_k[0] = (args.orbit // 2 - (e2e_steps - 1)) if args.orbit else 0      # an orbit's e2e loop ends on pinned frame orbit / 2
         t0 = time.perf_counter()
@@ -533,7 +552,8 @@ def run_ours(args):
             cpu = {"value": round(res["value"], 4), "unit": "Mpixels/s", "cores": res["threads_used"], "kind": "port", "sample": res["sample"],
                    "single_thread_value": round(res1["value"], 4)}
         par = {"single": "1 GPU",
-               "owner": f"{world} GPUs x cyclic {STRIP_ROWS}-row strips (pe_sharder_*, C ABI), every rank's strips stay in its own HBM; no collective on the data path",
+               "owner": f"{world} GPUs x cyclic {STRIP_ROWS}-row strips (pe_sharder_*, C ABI), every rank's strips stay in its own HBM; no collective on the data path" +
+                        ("; two frames in flight per GPU (alternating streams and program instances) so that a frame's last wave overlaps the next frame's first" if overlapped else ""),
                "p2p": f"{world} GPUs x cyclic {STRIP_ROWS}-row strips, kernels store into rank 0's frame over NVLink (CUDA IPC), stream-ordered flag words, no collective",
                "gather": f"{world} GPUs x cyclic {STRIP_ROWS}-row strips + 1 NCCL gather + de-interleave"}[mode]
         frame_mb = w * h * bpp / 1e6
@@ -605,6 +625,7 @@ def main():
     ap.add_argument("--frontend", default="ron", choices=["ron", "ir"],
                     help="ron = the product's C++ host front-end on tests/golden/ron/<scene>.ron; ir = the JSON scene IR (oracle front-end's export)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1, owner mode: one frame in flight per GPU instead of two")
     ap.add_argument("--no-assembled", action="store_true", help="N > 1: skip the extra rank-0-assembled measurements")
     ap.add_argument("--format", default="f32", choices=["f32", "rgba8"],
                     help="frame format of the timed steps: f32 = float RGBA, 16 B/pixel (the metric's definition, SURVEY.md 8d); "

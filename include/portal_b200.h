@@ -157,7 +157,7 @@ PE_API int pe_render_host_rgba8(pe_ctx* ctx, const pe_target* target, uint8_t* o
  * overlaps frame i+1's kernel.  Uniforms set between submits apply to later frames only.  `out_host`
  * should be page-locked (pe_host_malloc) or the copy is not asynchronous; it must stay untouched until
  * pe_wait_host(ticket) returns. */
-#define PE_PIPELINE_DEPTH 2
+#define PE_PIPELINE_DEPTH 4
 PE_API int pe_submit_host_rgba8(pe_ctx* ctx, const pe_target* target, uint8_t* out_host, uint64_t* ticket);
 PE_API int pe_wait_host(pe_ctx* ctx, uint64_t ticket);
 /* Multi-GPU host delivery without a device-side gather: `target` selects this rank's row strips, `host_frame`
@@ -223,7 +223,7 @@ PE_API int pe_ipc_close(pe_ctx* ctx, void* device_ptr);
 typedef struct pe_sharder pe_sharder;
 enum { PE_SHARD_OWNER = 0, PE_SHARD_P2P = 1, PE_SHARD_HOST = 2 };
 enum { PE_FRAME_F32 = 0, PE_FRAME_RGBA8 = 1 };
-#define PE_HOST_RING_DEPTH 3
+#define PE_HOST_RING_DEPTH 6
 /* Cyclic strip layout: rank r of `world` owns global strips r, r + world, ... */
 PE_API int pe_shard_target(int width, int height, int rank, int world, int strip_rows, int full_frame_layout, pe_target* out);
 /* On failure *out may still hold an object: read pe_sharder_last_error, then pe_sharder_destroy it. */
@@ -236,6 +236,13 @@ PE_API int pe_sharder_target(pe_sharder* s, pe_target* out);
  * compact strips (device); P2P -- on rank 0 the assembled frame (device), NULL elsewhere. */
 PE_API int pe_sharder_render(pe_sharder* s, void* stream, void** frame_out);
 PE_API int pe_sharder_release(pe_sharder* s, void* stream);
+/* OWNER mode with two frames in flight: consecutive frames alternate between two internal streams and two loaded instances
+ * of the program (each with its own uniform block), so the partly filled last wave of frame f runs under the first waves of
+ * frame f + 1 -- at 8 GPUs a frame is ~7 waves of blocks per GPU and that tail is ~15 % of it.  The frame is enqueued after
+ * everything already on `stream`; `stream` is made to wait for the frame BEFORE it, returned in *prev_frame_out (NULL for the
+ * first): the caller consumes frames one call late.  pe_sharder_flush orders `stream` after the last frame as well. */
+PE_API int pe_sharder_render_overlapped(pe_sharder* s, void* stream, void** prev_frame_out);
+PE_API int pe_sharder_flush(pe_sharder* s, void* stream, void** last_frame_out);
 /* HOST: queue this rank's strips of the next frame (returns its number); block until they are in host memory and publish;
  * rank 0: block until every rank's strips of a frame have landed (*frame = the whole RGBA8 frame); give its slot back. */
 PE_API int pe_sharder_submit(pe_sharder* s, uint64_t* frame_no);

@@ -112,6 +112,8 @@ def lib() -> C.CDLL:
         "pe_sharder_target": (i32, [vp, C.POINTER(PeTarget)]),
         "pe_sharder_render": (i32, [vp, vp, C.POINTER(vp)]),
         "pe_sharder_release": (i32, [vp, vp]),
+        "pe_sharder_render_overlapped": (i32, [vp, vp, C.POINTER(vp)]),
+        "pe_sharder_flush": (i32, [vp, vp, C.POINTER(vp)]),
         "pe_sharder_submit": (i32, [vp, C.POINTER(C.c_uint64)]),
         "pe_sharder_complete": (i32, [vp, C.c_uint64]),
         "pe_sharder_wait_frame": (i32, [vp, C.c_uint64, C.POINTER(vp)]),

@@ -306,12 +306,15 @@ struct PeLaunch {
     int tiles_x, tiles_y; // 8x4 tiles over the local row space
     int out_rgba8;        // 1: out is uchar4 pixels, quantised like an RGBA8 render target (main.rs:2939-2943)
     unsigned int* queue;  // PE_PERSISTENT: global tile counter (zeroed by the host before launch)
+    int strip_shift;      // log2(strip_rows) when it is a power of two (the 16-row strips of a sharded frame), else -1
+    int pad_;
 };
 
 namespace pe {
 
 PE_FI bool local_to_global_row(const PeLaunch& L, int lrow, int& grow) {
-    int k = lrow / L.strip_rows;
+    // one strip (a whole frame on one GPU): no division; power-of-two strips: a shift; anything else: the division
+    int k = L.n_strips == 1 ? (lrow < L.strip_rows ? 0 : 1) : (L.strip_shift >= 0 ? (lrow >> L.strip_shift) : lrow / L.strip_rows);
     if (k >= L.n_strips) return false;
     grow = (L.strip_first + k * L.strip_step) * L.strip_rows + (lrow - k * L.strip_rows);
     return grow < L.height;

@@ -42,8 +42,10 @@ struct PeLaunchHost {  // must match `PeLaunch` in device/pe_kernel.cuh
     int32_t tiles_x, tiles_y;
     int32_t out_rgba8;
     void* queue;
+    int32_t strip_shift;
+    int32_t pad_;
 };
-static_assert(sizeof(PeLaunchHost) == 64, "PeLaunch layout");
+static_assert(sizeof(PeLaunchHost) == 72, "PeLaunch layout");
 
 struct Variant {
     std::string source;
@@ -55,6 +57,11 @@ struct Variant {
     size_t const_size = 0;
     int regs = 0;
     int blocks_per_sm = 1;
+    // A second load of the same cubin: its own copy of the uniform block.  Two frames of one context can then be in flight at
+    // once (on two streams) -- frame f + 1's uniforms are uploaded while frame f's kernel still reads its own.
+    CUmodule_t module2 = nullptr;
+    CUfunction_t kernel2 = nullptr;
+    CUdeviceptr_t const_ptr2 = 0;
 };
 
 struct Texture {
@@ -470,6 +477,7 @@ bool select_variant(pe_ctx* c) {
             for (auto v = c->variants.begin(); v != c->variants.end();) {
                 if (v->second.get() == c->current) { ++v; continue; }
                 if (v->second->module && c->has_gpu) { cudaDeviceSynchronize(); c->drv->cuModuleUnload(v->second->module); }
+                if (v->second->module2 && c->has_gpu) c->drv->cuModuleUnload(v->second->module2);
                 v = c->variants.erase(v);
             }
         }
@@ -541,6 +549,10 @@ bool check_target(pe_ctx* c, const pe_target* t) {
 }  // namespace
 
 int pe_internal_device(pe_ctx* c) { return (c && c->has_gpu) ? c->device : -1; }
+int pe_internal_render_impl(pe_ctx* c, const pe_target* t, void* out_device, void* stream, int rgba8, int instance);
+int pe_internal_render(pe_ctx* c, const pe_target* t, void* out_device, void* stream, int rgba8, int instance) {
+    return pe_internal_render_impl(c, t, out_device, stream, rgba8, instance);
+}
 
 extern "C" {
 
@@ -589,8 +601,10 @@ void pe_destroy(pe_ctx* c) {
     if (c->has_gpu) {
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();
-        for (auto& kv : c->variants)
+        for (auto& kv : c->variants) {
             if (kv.second->module) c->drv->cuModuleUnload(kv.second->module);
+            if (kv.second->module2) c->drv->cuModuleUnload(kv.second->module2);
+        }
         for (auto& kv : c->textures)
             if (kv.second.dev) cudaFree(kv.second.dev);
         if (c->scratch_dev) cudaFree(c->scratch_dev);
@@ -617,8 +631,10 @@ int pe_scene_begin(pe_ctx* c) {
     if (c->has_gpu) {
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();
-        for (auto& kv : c->variants)
+        for (auto& kv : c->variants) {
             if (kv.second->module) c->drv->cuModuleUnload(kv.second->module);
+            if (kv.second->module2) c->drv->cuModuleUnload(kv.second->module2);
+        }
     }
     c->variants.clear();
     c->current = nullptr;
@@ -784,8 +800,10 @@ int pe_set_option(pe_ctx* c, const char* key, int value) {
     if (c->has_gpu) {
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();
-        for (auto& kv : c->variants)
+        for (auto& kv : c->variants) {
             if (kv.second->module) c->drv->cuModuleUnload(kv.second->module);
+            if (kv.second->module2) c->drv->cuModuleUnload(kv.second->module2);
+        }
     }
     c->variants.clear();
     c->current = nullptr;
@@ -904,7 +922,7 @@ size_t pe_target_pixels(const pe_target* t) {
     return size_t(t->n_strips) * size_t(t->strip_rows) * size_t(t->width);
 }
 
-static int render_impl(pe_ctx* c, const pe_target* t, void* out_device, void* bounces_device, void* stream, bool rgba8) {
+static int render_impl(pe_ctx* c, const pe_target* t, void* out_device, void* bounces_device, void* stream, bool rgba8, int instance = 0) {
     if (!c) return 1;
     if (!out_device) return c->fail("pe_render: out_device is null");
     if (!check_target(c, t) || !bind_device(c)) return 1;
@@ -918,7 +936,21 @@ static int render_impl(pe_ctx* c, const pe_target* t, void* out_device, void* bo
     const DriverApi* d = c->drv;
     CUstream_t s = stream ? (CUstream_t)stream : (CUstream_t)c->stream;
 
-    CUresult_t r = d->cuMemcpyHtoDAsync(v->const_ptr, c->cblock.data(), c->cblock.size(), s);
+    CUfunction_t kernel = v->kernel;
+    CUdeviceptr_t const_ptr = v->const_ptr;
+    CUresult_t r = 0;
+    if (instance == 1) {
+        if (!v->module2) {
+            size_t sz = 0;
+            r = d->cuModuleLoadData(&v->module2, v->cubin.data());
+            if (r == 0) r = d->cuModuleGetFunction(&v->kernel2, v->module2, "pe_render_kernel");
+            if (r == 0) r = d->cuModuleGetGlobal(&v->const_ptr2, &sz, v->module2, c->opts.uniforms_in_smem ? "PE_C_UPLOAD" : "PE_C");
+            if (r != 0) return c->fail("second program instance: " + driver_error(d, r));
+        }
+        kernel = v->kernel2;
+        const_ptr = v->const_ptr2;
+    }
+    r = d->cuMemcpyHtoDAsync(const_ptr, c->cblock.data(), c->cblock.size(), s);
     if (r != 0) return c->fail("uniform block upload: " + driver_error(d, r));
 
     PeLaunchHost L;
@@ -937,6 +969,10 @@ static int render_impl(pe_ctx* c, const pe_target* t, void* out_device, void* bo
     L.tiles_y = (local_rows + 3) / 4;
     L.out_rgba8 = rgba8 ? 1 : 0;
     L.queue = c->queue_dev;
+    L.strip_shift = -1;
+    if ((t->strip_rows & (t->strip_rows - 1)) == 0)
+        for (int sh = 0; sh < 31; sh++)
+            if ((1 << sh) == t->strip_rows) L.strip_shift = sh;
     void* args[] = {&L};
     unsigned gx, gy;
     if (c->opts.persistent) {
@@ -951,11 +987,17 @@ static int render_impl(pe_ctx* c, const pe_target* t, void* out_device, void* bo
         gx = unsigned((t->width + block_w - 1) / block_w);
         gy = unsigned((local_rows + rows_per_block - 1) / rows_per_block);
     }
-    r = d->cuLaunchKernel(v->kernel, gx, gy, 1, unsigned(c->opts.block_threads), 1, 1, 0, s, args, nullptr);
+    r = d->cuLaunchKernel(kernel, gx, gy, 1, unsigned(c->opts.block_threads), 1, 1, 0, s, args, nullptr);
     if (r != 0) return c->fail("cuLaunchKernel(pe_render_kernel): " + driver_error(d, r));
     c->launches++;
     return 0;
 }
+
+}  // extern "C"
+int pe_internal_render_impl(pe_ctx* c, const pe_target* t, void* out_device, void* stream, int rgba8, int instance) {
+    return render_impl(c, t, out_device, nullptr, stream, rgba8 != 0, instance);
+}
+extern "C" {
 
 int pe_render(pe_ctx* c, const pe_target* t, void* out_device, void* bounces_device, void* stream) {
     return render_impl(c, t, out_device, bounces_device, stream, false);

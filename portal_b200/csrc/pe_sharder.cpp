@@ -23,6 +23,7 @@
 #include <time.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cctype>
 #include <cstdio>
@@ -109,7 +110,7 @@ struct pe_sharder {
     uint8_t* map = nullptr;
     bool registered = false;
     // device modes
-    void* local[2] = {nullptr, nullptr};   // OWNER: this rank's compact strips
+    std::vector<void*> local;              // OWNER: this rank's compact strips, a ring of buffers larger than the L2
     void* frames = nullptr;                // P2P: rank 0's two frames (own allocation on rank 0, IPC mapping elsewhere)
     void* sig = nullptr;                   // P2P: this rank's signal block
     void* sig0 = nullptr;                  // P2P, rank != 0: rank 0's signal block
@@ -117,6 +118,13 @@ struct pe_sharder {
     std::vector<void*> opened, owned;
     uint32_t frame_no = 0;
     void* current = nullptr;
+    // OWNER, overlapped rendering: consecutive frames alternate between two internal streams and two program instances, so
+    // the tail of frame f (its last, partly filled wave of blocks) runs under the head of frame f + 1
+    cudaStream_t lane[2] = {nullptr, nullptr};
+    cudaEvent_t lane_done[2] = {nullptr, nullptr}, submitted = nullptr;
+    void* lane_frame[2] = {nullptr, nullptr};
+    bool lane_busy[2] = {false, false};
+    int ring = 2;
     // host mode
     uint64_t host_frame_no = 0;
     std::map<uint64_t, uint64_t> tickets;
@@ -166,6 +174,9 @@ const char* pe_sharder_last_error(pe_sharder* s) { return s ? s->err.c_str() : "
 void pe_sharder_destroy(pe_sharder* s) {
     if (!s) return;
     if (s->ctx) pe_sync(s->ctx);
+    for (auto& l : s->lane) if (l) cudaStreamDestroy(l);
+    for (auto& e : s->lane_done) if (e) cudaEventDestroy(e);
+    if (s->submitted) cudaEventDestroy(s->submitted);
     if (s->registered) pe_host_unregister(s->ctx, s->map);
     for (void* p : s->opened) pe_ipc_close(s->ctx, p);
     for (void* p : s->owned) pe_device_free(s->ctx, p);
@@ -256,8 +267,12 @@ int pe_sharder_create(pe_ctx* ctx, const char* name, int width, int height, int 
         return true;
     };
     if (mode == PE_SHARD_OWNER) {
+        // enough buffers that a long run of frames writes through the 126 MB L2 instead of rewriting two resident buffers
+        const size_t lb = s->local_bytes ? s->local_bytes : 16;
+        s->ring = int(std::min<size_t>(32, std::max<size_t>(2, (size_t(192) << 20) / lb + 1)));
+        s->local.assign(size_t(s->ring), nullptr);
         for (auto& b : s->local)
-            if (!dmalloc(s->local_bytes ? s->local_bytes : 16, &b)) return bail(std::string("device allocation: ") + pe_last_error(ctx));
+            if (!dmalloc(lb, &b)) return bail(std::string("device allocation: ") + pe_last_error(ctx));
         if (!barrier(s, 0)) return bail("pe_sharder_create: a rank failed or timed out during set-up");
     } else if (mode == PE_SHARD_P2P) {
         if (!dmalloc(256, &s->sig) || pe_memset_u32(ctx, s->sig, 0, 64, nullptr) || pe_ipc_export(ctx, s->sig, s->hdr->sig_handle[rank]))
@@ -315,7 +330,7 @@ int pe_sharder_render(pe_sharder* s, void* stream, void** frame_out) {
     pe_ctx* c = s->ctx;
     const uint32_t f = ++s->frame_no;
     if (s->mode == PE_SHARD_OWNER) {
-        void* dst = s->local[f & 1];
+        void* dst = s->local[f % uint32_t(s->ring)];
         if (s->target.n_strips > 0) {
             const int rc = s->format == PE_FRAME_F32 ? pe_render(c, &s->target, dst, nullptr, stream) : pe_render_rgba8(c, &s->target, dst, stream);
             if (rc) return s->fail_ctx("render");
@@ -341,6 +356,50 @@ int pe_sharder_render(pe_sharder* s, void* stream, void** frame_out) {
         s->current = dst;
         if (frame_out) *frame_out = dst;
     }
+    return 0;
+}
+
+// OWNER mode, two frames in flight.  Frame f is enqueued on internal lane f & 1 (ordered after everything already on
+// `stream`); `stream` itself is made to wait for the frame BEFORE it, whose buffer is returned: after the call, work on
+// `stream` may read *prev_frame_out (NULL for the first frame).  pe_sharder_flush orders `stream` after the last frame too.
+int pe_sharder_render_overlapped(pe_sharder* s, void* stream, void** prev_frame_out) {
+    if (!s) return 1;
+    if (prev_frame_out) *prev_frame_out = nullptr;
+    if (s->mode != PE_SHARD_OWNER) return s->fail("pe_sharder_render_overlapped: owner mode only");
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    if (!s->lane[0]) {
+        for (int q = 0; q < 2; q++)
+            if (cudaStreamCreateWithFlags(&s->lane[q], cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s->lane_done[q], cudaEventDisableTiming) != cudaSuccess)
+                return s->fail("pe_sharder_render_overlapped: cannot create streams");
+        if (cudaEventCreateWithFlags(&s->submitted, cudaEventDisableTiming) != cudaSuccess) return s->fail("pe_sharder_render_overlapped: event");
+    }
+    const uint32_t f = ++s->frame_no;
+    const int q = int(f & 1u);
+    void* dst = s->local[f % uint32_t(s->ring)];
+    // the lane starts after what the caller has enqueued so far (e.g. its reader of the buffer this frame overwrites)
+    if (cudaEventRecord(s->submitted, user) != cudaSuccess || cudaStreamWaitEvent(s->lane[q], s->submitted, 0) != cudaSuccess)
+        return s->fail("pe_sharder_render_overlapped: stream ordering failed");
+    if (s->target.n_strips > 0 && pe_internal_render(s->ctx, &s->target, dst, s->lane[q], s->format == PE_FRAME_RGBA8, q))
+        return s->fail_ctx("render");
+    if (cudaEventRecord(s->lane_done[q], s->lane[q]) != cudaSuccess) return s->fail("pe_sharder_render_overlapped: event record failed");
+    s->lane_frame[q] = dst;
+    s->lane_busy[q] = true;
+    const int p = q ^ 1;
+    if (s->lane_busy[p]) {
+        if (cudaStreamWaitEvent(user, s->lane_done[p], 0) != cudaSuccess) return s->fail("pe_sharder_render_overlapped: stream wait failed");
+        if (prev_frame_out) *prev_frame_out = s->lane_frame[p];
+    }
+    s->current = dst;
+    return 0;
+}
+
+int pe_sharder_flush(pe_sharder* s, void* stream, void** last_frame_out) {
+    if (!s) return 1;
+    if (last_frame_out) *last_frame_out = s->current;
+    for (int q = 0; q < 2; q++)
+        if (s->lane_busy[q] && cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), s->lane_done[q], 0) != cudaSuccess)
+            return s->fail("pe_sharder_flush: stream wait failed");
     return 0;
 }
 

@@ -253,6 +253,20 @@ class NativeSharder:
     def release(self, stream_ptr: int):
         self._check(self._lib.pe_sharder_release(self._s, stream_ptr or None))
 
+    def render_overlapped(self, stream_ptr: int):
+        """Owner mode, two frames in flight (pe_sharder_render_overlapped): returns the PREVIOUS frame's buffer, complete in
+        `stream` order (None for the first frame)."""
+        self.r.set_uniforms()
+        out = C.c_void_p()
+        self._check(self._lib.pe_sharder_render_overlapped(self._s, stream_ptr or None, C.byref(out)))
+        return out.value
+
+    def flush(self, stream_ptr: int):
+        out = C.c_void_p()
+        self._check(self._lib.pe_sharder_flush(self._s, stream_ptr or None, C.byref(out)))
+        self.frame_ptr = out.value
+        return out.value
+
     def submit(self) -> int:
         self.r.set_uniforms()
         f = C.c_uint64()
@@ -262,10 +276,20 @@ class NativeSharder:
     def complete(self, f: int):
         self._check(self._lib.pe_sharder_complete(self._s, f))
 
-    def wait_frame(self, f: int):
+    RING_DEPTH = 6          # PE_HOST_RING_DEPTH: frames a rank may run ahead of the consumer
+    PIPELINE_DEPTH = 4      # PE_PIPELINE_DEPTH: frames of one rank in flight between kernel and host memory
+
+    def wait_frame(self, f: int, view: bool = True):
+        """Rank 0: block until every rank's strips of frame f are in host memory; returns the frame (numpy view of the slot;
+        None with view=False, for a consumer that reads the slot by other means)."""
         p = C.c_void_p()
         self._check(self._lib.pe_sharder_wait_frame(self._s, f, C.byref(p)))
-        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(self.h, self.w, 4))
+        if not view:
+            return None
+        views = self.__dict__.setdefault("_views", {})
+        if p.value not in views:
+            views[p.value] = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(self.h, self.w, 4))
+        return views[p.value]
 
     def release_frame(self, f: int):
         self._check(self._lib.pe_sharder_release_frame(self._s, f))

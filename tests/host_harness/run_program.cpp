@@ -87,6 +87,7 @@ int main(int argc, char** argv) {
     L.tiles_y = (h + 3) / 4;
     L.out_rgba8 = 0;
     L.queue = nullptr;
+    L.strip_shift = -1;
     const unsigned rows_per_block = PE_BLOCK_ROWS;
     blockDim = pe_uint3{unsigned(PE_BLOCK_THREADS), 1, 1};
     gridDim = pe_uint3{unsigned((w + PE_BLOCK_W - 1) / PE_BLOCK_W), unsigned((h + rows_per_block - 1) / rows_per_block), 1};

@@ -44,7 +44,7 @@ def test_c_abi_sharder_protocol_on_one_gpu(world, size):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     out = p.stdout + p.stderr
     assert p.returncode == 0, out[-3000:]
-    for what in ("owner f32", "owner rgba8", "p2p f32", "p2p rgba8", "host rgba8"):
+    for what in ("owner f32", "owner rgba8", "owner overlapped f32", "p2p f32", "p2p rgba8", "host rgba8"):
         assert f"sharder {what}" in out, out[-3000:]
     assert "False" not in p.stdout
 

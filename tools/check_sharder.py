@@ -52,7 +52,7 @@ def main():
     # ---- owner: strips stay in each rank's HBM; the checker pulls them and assembles
     for fmt, dtype in (("f32", np.float32), ("rgba8", np.uint8)):
         sh = NativeSharder(r, w, h, rank, world, "owner", fmt)
-        for f in range(3):                         # ring of two buffers: the third frame reuses the first
+        for f in range(3):
             set_frame(f)
             ptr = sh.render(sp)
         rows = local_rows(h, rank, world)
@@ -73,6 +73,40 @@ def main():
         dist.barrier()
         sh.close()
 
+    # ---- owner, two frames in flight: every call returns the PREVIOUS frame; 6 frames with a moving camera
+    sh = NativeSharder(r, w, h, rank, world, "owner", "f32")
+    rows = local_rows(h, rank, world)
+    same = True
+
+    def check_owner_frame(ptr, f):
+        strips = d2h(ptr, (len(rows), w, 4), np.float32) if sh.target.n_strips > 0 else np.zeros((len(rows), w, 4), np.float32)
+        gathered = [None] * world
+        dist.gather_object((rows, strips), gathered if rank == 0 else None, dst=0)
+        if rank != 0:
+            return True
+        frame = np.zeros((h, w, 4), np.float32)
+        for rws, st in gathered:
+            for k, y in enumerate(rws):
+                if y >= 0:
+                    frame[y] = st[k]
+        torch.cuda.synchronize()          # the frame still in flight reads a uniform block the reference render below would overwrite
+        set_frame(f)
+        return bool(np.array_equal(frame.view(np.uint32), r.render_host(w, h).view(np.uint32)))
+
+    for f in range(6):
+        set_frame(f)
+        prev = sh.render_overlapped(sp)
+        if f == 0:
+            assert prev is None
+        else:
+            same = check_owner_frame(prev, f - 1) and same
+    same = check_owner_frame(sh.flush(sp), 5) and same
+    if rank == 0:
+        print(f"sharder owner overlapped f32: world {world} {scene} {w}x{h} x 6 frames -> bit-identical to single GPU: {same}", flush=True)
+        ok = ok and same
+    dist.barrier()
+    sh.close()
+
     # ---- p2p: kernels store into rank 0's frame; 5 frames through 2 buffers exercise the recycling flags
     for fmt, dtype in (("f32", np.float32), ("rgba8", np.uint8)):
         sh = NativeSharder(r, w, h, rank, world, "p2p", fmt)
@@ -92,9 +126,9 @@ def main():
             ok = ok and same
         sh.close()
 
-    # ---- host: RGBA8 strips over every rank's PCIe link into one shared pinned frame; 7 frames through a ring of 3
+    # ---- host: RGBA8 strips over every rank's PCIe link into one shared pinned frame; 15 frames through a ring of 6 (4 device slots)
     sh = NativeSharder(r, w, h, rank, world, "host", "rgba8")
-    frames, prev, same = 7, None, True
+    frames, prev, same = 15, None, True
 
     def finish(f):
         sh.complete(f)
