@@ -497,3 +497,46 @@ def test_per_animation_overrides_of_update_inner_variables():
             seen["depth"] += ov["render_depth"] == 100
             seen["fps"] += ov["fps"] == 600
     assert seen["degree500"] >= 1 and seen["depth"] >= 1 and seen["fps"] >= 1, seen
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene", ["portal_in_portal", "triple_portal", "basics"])
+def test_animated_states_of_config_scenes_bit_exact_on_the_gpu(scene, torch_cuda):
+    """The config scenes are measured at their saved state, where many matrices are pure translations and some are singular
+    (`c0`: scale 0, inverse all NaN).  Animations drive exactly those: `violet_progress` opens the third portal, matrices
+    stop being translations, structure masks and the finite flags of the specialised program change from frame to frame.
+    Every animation of the scene, three times each, through the product's own player (C++ host + GPU) against the oracle
+    driven by the oracle's player: camera, uniform tables and every pixel, bit for bit."""
+    from conftest import GOLDEN, load_tex
+    from oracle import frontend
+    from oracle.animation import Player
+    from oracle.runner import Oracle
+    path = os.path.join(ROOT, "tests", "golden", "ron", f"{scene}.ron")
+    depth = {"portal_in_portal": 40, "triple_portal": 40, "basics": 4}[scene]
+    tex = load_tex(scene)
+    s0 = frontend.load_scene(path)
+    names = [a["name"] for a in Player(s0).anim.animations]
+    assert len(names) >= 2
+    orc = Oracle(frontend.scene_ir(s0, scene), variant="fast", textures=tex)
+    hs = HostScene.from_file(path)
+    hr = HostRenderer(hs, textures=tex)
+    hp = HostPlayer(hs, hr)
+    s = frontend.load_scene(path)
+    p = Player(s)
+    n = 0
+    for an in names[:6]:
+        p.init_animation(an)
+        hp.init_animation(an)
+        dur = p.anim.animations[p.anim.animation_by_name[an]]["duration"]
+        for frac in (0.13, 0.5, 0.97):
+            p.update(frac * dur)
+            hp.update(frac * dur)
+            _assert_same_state(p, hp, s, hs, (an, frac))
+            cs = p.camera_state()
+            orc.set_uniforms({k: v for k, (_, v) in s.uniform_table().items()})
+            want = orc.render(160, 90, depth, camera=cs["camera"], camera_scale=cs["scale"], camera_mul_inv=cs["camera_mul_inv"],
+                              camera_in_subspace=int(cs["in_subspace"]))
+            got = hp.render_frame(160, 90, depth)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (scene, an, frac, int((got.view(np.uint32) != want.view(np.uint32)).any(axis=-1).sum()))
+            n += 1
+    assert n >= 6
