@@ -161,6 +161,11 @@ class FrameSharder:
         r = self.r
         lib, ctx = r._lib, r._ctx
         if self.mode == "gather":
+            import torch
+            # dist.gather orders itself against torch's CURRENT stream: the render must be on that stream
+            if torch.cuda.current_stream().cuda_stream != stream_ptr:
+                raise RuntimeError("FrameSharder(mode='gather'): make `stream_ptr` torch's current stream (torch.cuda.set_stream) -- "
+                                   "the NCCL gather is enqueued on the current stream and must follow the render")
             out = self.local[i & 1]
             r.draw_texture(self.target, out.data_ptr(), 0, stream_ptr)
             if self.world > 1:
