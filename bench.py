@@ -243,13 +243,15 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- value leg set-up
-    mode = args.mode if world > 1 else "single"
+    mode = args.mode if (world > 1 or not args.no_overlap) else "single"
+    if world == 1 and mode != "single":
+        mode = "owner"                     # one GPU: the same sharder, one rank (so that every N runs the same code)
     fmt = args.format
     bpp = 16 if fmt == "f32" else 4
     tdtype = torch.float32 if fmt == "f32" else torch.uint8
     frame_counter = [0]
     sharder = None
-    if world == 1:
+    if mode == "single":
         target = r.full_target(w, h) if hasattr(r, "full_target") else SceneRenderer.full_target(w, h)
         # ring of output frames larger than the 126 MB L2: >= 2 float frames (265 MB at 4K) / >= 6 RGBA8 frames
         n_outs = max(2, int(math.ceil(192e6 / (w * h * bpp))) + 1)
@@ -269,11 +271,11 @@ def run_ours(args):
         target = sharder.target
         n_px_local = sum(1 for y in D.local_rows(h, rank, world, STRIP_ROWS) if y >= 0) * w
     last = {"ptr": None}
-    overlapped = world > 1 and mode == "owner" and not args.no_overlap and not args.persistent
+    overlapped = mode == "owner" and not args.no_overlap and not args.persistent
 
     def render_once(i):
         """Enqueue one frame (this rank's part of it) on the stream."""
-        if world == 1:
+        if mode == "single":
             out = outs[i % len(outs)]
             check(lib.pe_render(ctx, C.byref(target), out.data_ptr(), None, sptr) if fmt == "f32" else
                   lib.pe_render_rgba8(ctx, C.byref(target), out.data_ptr(), sptr))
@@ -340,8 +342,12 @@ def run_ours(args):
 
     def assembled_last_frame():
         """bytes of the whole last frame on rank 0 (None elsewhere)."""
-        if world == 1:
+        if mode == "single":
             return last["ptr"].cpu().numpy()
+        if world == 1:                     # the sharder's buffer of the one rank IS the frame
+            out = np.empty((h, w, 4), dtype=np.float32 if fmt == "f32" else np.uint8)
+            check(lib.pe_memcpy_d2h(ctx, out.ctypes.data, last["ptr"], out.nbytes, sptr))
+            return out
         if mode == "gather":
             return frame_dev.cpu().numpy() if rank == 0 else None
         if mode == "p2p":
@@ -552,7 +558,7 @@ def run_ours(args):
             cpu = {"value": round(res["value"], 4), "unit": "Mpixels/s", "cores": res["threads_used"], "kind": "port", "sample": res["sample"],
                    "single_thread_value": round(res1["value"], 4)}
         par = {"single": "1 GPU",
-               "owner": f"{world} GPUs x cyclic {STRIP_ROWS}-row strips (pe_sharder_*, C ABI), every rank's strips stay in its own HBM; no collective on the data path" +
+               "owner": f"{world} GPU{'s' if world > 1 else ''} x cyclic {STRIP_ROWS}-row strips (pe_sharder_*, C ABI), every rank's strips stay in its own HBM; no collective on the data path" +
                         ("; two frames in flight per GPU (alternating streams and program instances) so that a frame's last wave overlaps the next frame's first" if overlapped else ""),
                "p2p": f"{world} GPUs x cyclic {STRIP_ROWS}-row strips, kernels store into rank 0's frame over NVLink (CUDA IPC), stream-ordered flag words, no collective",
                "gather": f"{world} GPUs x cyclic {STRIP_ROWS}-row strips + 1 NCCL gather + de-interleave"}[mode]

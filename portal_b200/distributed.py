@@ -312,7 +312,8 @@ def shm_name(tag: str) -> str:
     """A segment name every rank of one launch derives alike: the launcher's rendezvous port + a per-process counter
     (ranks create their sharders in the same order)."""
     _shm_counter[0] += 1
-    return f"portal_b200_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}_{_shm_counter[0]}_{tag}"
+    solo = f"_pid{os.getpid()}" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else ""     # a lone process needs no agreement
+    return f"portal_b200_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}_{_shm_counter[0]}_{tag}{solo}"
 
 
 class gpu_numa_affinity:
