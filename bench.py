@@ -301,6 +301,15 @@ def run_ours(args):
         render_once(i)
 
     frame_uniforms(0 if args.orbit else None)
+    # ---- per-scene autotuning (pe_autotune): block size 512 / 1024 x canonical rays on / off, same pixels, timed on this
+    # rank's own part of the frame; untimed set-up, like the scene compilation itself
+    tuned = None
+    if not args.no_autotune and not args.persistent:
+        tt = D.make_target(w, h, rank, world, STRIP_ROWS, full_frame=False) if mode != "single" else target
+        if tt.n_strips > 0:
+            buf = C.create_string_buffer(2048)
+            check(lib.pe_autotune(ctx, C.byref(tt), 5, buf, len(buf)))
+            tuned = buf.value.decode().strip().splitlines()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                      # nvidia-smi needs ~0.2 s to produce its first sample: start it early
@@ -570,7 +579,9 @@ def run_ours(args):
             "config": {"workload": workload_name(args),
                        "parallelism": par,
                        "scheduler": "persistent warps + per-bounce refill" if args.persistent else
-                                    f"one thread per pixel, {args.tile_w or 8}x{32 // (args.tile_w or 8)} warp tiles, 512-thread blocks, <= 64 regs",
+                                    f"one thread per pixel, {args.tile_w or 8}x{32 // (args.tile_w or 8)} warp tiles, <= 64 regs; " +
+                                    (f"pe_autotune on rank 0: {tuned[-1]}" if tuned else "512-thread blocks, canonical rays (no autotune)"),
+                       "autotune": tuned,
                        "frame_format": "float RGBA (16 B/pixel)" if fmt == "f32" else "RGBA8 quantised by the kernel (4 B/pixel)",
                        "front_end": "scene .ron -> C++ host front-end (ph_scene_*) -> C ABI" if args.frontend == "ron" else "JSON scene IR -> Python SceneRenderer -> C ABI",
                        "l2": f"each step writes {'a' if world == 1 else 'its part of a'} {frame_mb:.1f} MB frame into a ring of buffers larger than "
@@ -631,6 +642,7 @@ def main():
     ap.add_argument("--frontend", default="ron", choices=["ron", "ir"],
                     help="ron = the product's C++ host front-end on tests/golden/ron/<scene>.ron; ir = the JSON scene IR (oracle front-end's export)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-autotune", action="store_true", help="keep the library defaults (512-thread blocks, canonical rays) instead of pe_autotune")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1, owner mode: one frame in flight per GPU instead of two")
     ap.add_argument("--no-assembled", action="store_true", help="N > 1: skip the extra rank-0-assembled measurements")
     ap.add_argument("--format", default="f32", choices=["f32", "rgba8"],

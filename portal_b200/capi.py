@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
         "pe_host_free": (i32, [vp, vp]),
         "pe_probe_ray": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32),
                                C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+        "pe_autotune": (i32, [vp, C.POINTER(PeTarget), i32, cp, C.c_size_t]),
         "pe_sync": (i32, [vp]),
         "pe_launch_count": (C.c_uint64, [vp]),
         "pe_deinterleave_strips": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),

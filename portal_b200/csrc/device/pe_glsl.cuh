@@ -47,18 +47,21 @@ PE_FI void pe_sincos_core(float x, float& s, float& c, int& q) {
     pc = ::fmaf(pc, z, -1.388731625493765e-3f);
     pc = ::fmaf(pc, z, 4.166664568298827e-2f);
     c = ::fmaf(pc * z, z, ::fmaf(z, -0.5f, 1.0f));
-    float kq = k - 4.0f * ::floorf(k * 0.25f);
-    q = (kq >= 0.0f && kq <= 3.0f) ? int(kq) : 0;
+    // q = k mod 4.  The profile's definition is kq = k - 4 floor(k / 4), q = (0 <= kq <= 3) ? int(kq) : 0 (oracle/glsl_compat.h);
+    // for |k| < 2^30 that is the two low bits of the integer k, beyond it every float is a multiple of 4 (q = 0), NaN gives 0:
+    // the same q with one conversion and one AND instead of a multiply, a floor, an FMA, two compares and a conversion.
+    q = (::fabsf(k) < 1073741824.0f) ? (__float2int_rz(k) & 3) : 0;
 }
+// quadrant q: sin = s, c, -s, -c and cos = c, -s, -c, s -- pick by the low bit, flip the sign bit by the other
 PE_FI float sin(float x) {
     float s, c; int q;
     pe_sincos_core(x, s, c, q);
-    return q == 0 ? s : (q == 1 ? c : (q == 2 ? -s : -c));
+    return __int_as_float(__float_as_int((q & 1) ? c : s) ^ ((q & 2) << 30));
 }
 PE_FI float cos(float x) {
     float s, c; int q;
     pe_sincos_core(x, s, c, q);
-    return q == 0 ? c : (q == 1 ? -s : (q == 2 ? -c : s));
+    return __int_as_float(__float_as_int((q & 1) ? s : c) ^ (((q + 1) & 2) << 30));
 }
 PE_FI float tan(float x) {
     float s, c; int q;

@@ -321,6 +321,9 @@ std::vector<int> variant_key(pe_ctx* c, const std::vector<int>& ints, const std:
     key.push_back(c->opts.uniforms_in_smem);
     key.push_back(c->opts.tile_w);
     key.push_back(c->opts.canon_rays ? 1 : 0);
+    key.push_back(c->opts.block_threads);
+    key.push_back(c->opts.min_blocks);
+    key.push_back(c->opts.persistent ? 1 : 0);
     for (char d : c->opts.dynamic_ints) key.push_back(d);
     for (char d : c->opts.dynamic_mats) key.push_back(d);
     return key;
@@ -1229,6 +1232,62 @@ int pe_scratch_buffer(pe_ctx* c, int slot, size_t bytes, void** out) {
         s.bytes = bytes;
     }
     *out = s.dev;
+    return 0;
+}
+
+// Launch / specialisation alternatives that keep the pixels, tried on the scene and target at hand.  Which is fastest depends on
+// the scene's own code: the Moebius portal's Newton solver wants 1024-thread blocks (-11 %) and loses 3 % to the canonical-ray
+// split, the plane-heavy scenes want 512-thread blocks and gain 6-14 % from it (profiles/r02f_sweep_*.txt).
+int pe_autotune(pe_ctx* c, const pe_target* t, int reps, char* report, size_t report_len) {
+    if (!c) return 1;
+    if (report && report_len) report[0] = 0;
+    if (!check_target(c, t) || !bind_device(c)) return 1;
+    if (c->opts.persistent) return 0;                       // the persistent scheduler has its own geometry: nothing to try
+    if (reps < 1) reps = 3;
+    struct Cand { int block_threads, min_blocks; bool canon; };
+    const Cand cands[] = {{512, 2, true}, {512, 2, false}, {1024, 1, true}, {1024, 1, false}};
+    const GenOptions saved = c->opts;
+    void* scratch = nullptr;
+    const size_t bytes = (pe_target_pixels(t) ? pe_target_pixels(t) : 1) * 16;
+    if (pe_scratch_buffer(c, 127, bytes, &scratch)) return 1;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (!cuda_ok(c, cudaEventCreate(&e0), "event") || !cuda_ok(c, cudaEventCreate(&e1), "event")) return 1;
+    int best = -1;
+    float best_ms = 0.0f;
+    std::string rep;
+    int rc = 0;
+    for (int k = 0; k < int(sizeof cands / sizeof *cands) && !rc; k++) {
+        c->opts.block_threads = cands[k].block_threads;
+        c->opts.min_blocks = cands[k].min_blocks;
+        c->opts.canon_rays = cands[k].canon;
+        c->current = nullptr;
+        if (render_impl(c, t, scratch, nullptr, nullptr, false)) { rc = 1; break; }            // compile / load + warm-up
+        cudaEventRecord(e0, c->stream);
+        for (int i = 0; i < reps && !rc; i++) rc = render_impl(c, t, scratch, nullptr, nullptr, false);
+        cudaEventRecord(e1, c->stream);
+        if (rc || !cuda_ok(c, cudaEventSynchronize(e1), "autotune")) { rc = 1; break; }
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ms /= float(reps);
+        char line[160];
+        std::snprintf(line, sizeof line, "block_threads %d min_blocks %d canon_rays %d: %.4f ms\n", cands[k].block_threads, cands[k].min_blocks,
+                      cands[k].canon ? 1 : 0, ms);
+        rep += line;
+        if (best < 0 || ms < best_ms * 0.99f) { best = k; best_ms = ms; }          // a later candidate must win by more than the noise
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->opts = saved;
+    c->current = nullptr;
+    if (rc) return 1;
+    c->opts.block_threads = cands[best].block_threads;
+    c->opts.min_blocks = cands[best].min_blocks;
+    c->opts.canon_rays = cands[best].canon;
+    char line[160];
+    std::snprintf(line, sizeof line, "chosen: block_threads %d min_blocks %d canon_rays %d\n", cands[best].block_threads, cands[best].min_blocks,
+                  cands[best].canon ? 1 : 0);
+    rep += line;
+    if (report && report_len) std::snprintf(report, report_len, "%s", rep.c_str());
     return 0;
 }
 

@@ -33,6 +33,13 @@ static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); retur
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
 static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
+// truncating, saturating like cvt.rzi.s32.f32 (NaN -> 0)
+static inline int __float2int_rz(float v) {
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return 2147483647;
+    if (v <= -2147483648.0f) return -2147483647 - 1;
+    return int(v);
+}
 // round to nearest even, saturating like cvt.rni.s32.f32 (NaN -> 0)
 static inline int __float2int_rn(float v) {
     if (v != v) return 0;

@@ -106,6 +106,10 @@ def main():
             return pre + "rest of the bounce"
         if "bounce_once(" in chain or "bounce_body(" in chain:
             return "rest of the bounce (advance, darken, loop control)"
+        # code of a function the compiler did not inline has no chain up to the kernel: name it by the scene element / header it is in
+        owner = st[-1][0] if st else "?"
+        if owner not in ("<generated>", "?"):
+            return f"out-of-line function in {owner}" if owner != "scene_program.cu" else "out-of-line device-header function (called from a snippet)"
         return "kernel prologue / index arithmetic"
 
     by_sec, by_line, ops = collections.Counter(), collections.Counter(), collections.defaultdict(collections.Counter)
