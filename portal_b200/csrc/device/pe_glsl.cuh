@@ -578,8 +578,20 @@ struct smat4 {
 template <class M> struct pe_canon_matrix { static constexpr bool value = false; };
 template <unsigned Z, unsigned O, unsigned F> struct pe_canon_matrix<smat4<Z, O, F>> { static constexpr bool value = smat4<Z, O, F>::canon; };
 
+#ifndef PE_W_AWARE
+#define PE_W_AWARE 1
+#endif
 template <unsigned Z, unsigned O, unsigned F>
 PE_FI vec4 operator*(const smat4<Z, O, F>& m, const vec4& v) {
+#if PE_W_AWARE
+    // finite affine matrix: a direction (w exactly 0) or a point (w exactly 1) needs no arithmetic on the w column.  A snippet's
+    // `M * vec4(n, 0.)` and everything derived from it through further affine matrices has a w the compiler KNOWS: the tests
+    // fold away, and under a translation such a vector is visibly unchanged (loop-invariant normals in a portal-chain loop).
+    if constexpr (smat4<Z, O, F>::canon) {
+        if (v.w == 0.0f) return m.dir(v);
+        if (v.w == 1.0f) return m.point(v);
+    }
+#endif
     return vec4(m.template row<0>(v), m.template row<1>(v), m.template row<2>(v), m.template row<3>(v));
 }
 template <unsigned Z, unsigned O, unsigned F>

@@ -321,6 +321,7 @@ std::vector<int> variant_key(pe_ctx* c, const std::vector<int>& ints, const std:
     key.push_back(c->opts.uniforms_in_smem);
     key.push_back(c->opts.tile_w);
     key.push_back(c->opts.canon_rays ? 1 : 0);
+    key.push_back(c->opts.w_aware ? 1 : 0);
     key.push_back(c->opts.block_threads);
     key.push_back(c->opts.min_blocks);
     key.push_back(c->opts.persistent ? 1 : 0);
@@ -791,6 +792,7 @@ int pe_set_option(pe_ctx* c, const char* key, int value) {
     else if (k == "with_probe") c->opts.with_probe = value != 0;   // pe_probe_ray turns it on by itself; exposed for inspection
     else if (k == "adaptive") c->adapt = value != 0;
     else if (k == "canon_rays") c->opts.canon_rays = value != 0;
+    else if (k == "w_aware") c->opts.w_aware = value != 0;
     else if (k == "uniforms_in_smem") {
         if (value < 0 || value > 2) return c->fail("uniforms_in_smem must be 0 (constant bank), 1 (copy loop) or 2 (TMA bulk copy)");
         c->opts.uniforms_in_smem = value;

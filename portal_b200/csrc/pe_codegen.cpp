@@ -542,6 +542,7 @@ GenResult generate_program(const SceneDesc& scene, const ConstLayout& L, const G
     hd << "#define PE_WITH_PROBE " << (opts.with_probe ? 1 : 0) << "\n";
     hd << "#define PE_TILE_W " << opts.tile_w << "\n";
     hd << "#define PE_CANON_RAYS " << (opts.canon_rays ? 1 : 0) << "\n";
+    hd << "#define PE_W_AWARE " << ((opts.w_aware && opts.canon_rays) ? 1 : 0) << "\n";
     std::string swz_err;
     hd << "#define PE_SWZ_VEC2" << swizzle_macro(body.swz, 2) << lvalue_swizzle_macro(body.swz_w, 2, swz_err) << "\n";
     hd << "#define PE_SWZ_VEC3" << swizzle_macro(body.swz, 3) << lvalue_swizzle_macro(body.swz_w, 3, swz_err) << "\n";

@@ -106,6 +106,7 @@ struct GenOptions {
     // rays are checked for origin.w == 1 / direction.w == 0 once per bounce and then carry those as constants; matrices get a
     // "all entries finite" flag next to their 0 / 1 structure (pe_glsl.cuh smat4<Z, O, F>, pe_kernel.cuh bounce_once)
     bool canon_rays = true;
+    bool w_aware = true;   // `finite affine matrix * vec4` tests w for exactly 0 / 1 (folded where the compiler knows it): pe_glsl.cuh
     bool unroll_loops = true;  // false: `#pragma unroll 1` on every loop of the user snippets (smaller code)
     // per slot of i[] / per scene matrix: 1 = read it from the constant block even when specialisation is on (slots whose
     // value kept changing between renders, pe_api.cpp select_variant)

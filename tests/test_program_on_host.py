@@ -65,6 +65,7 @@ def test_generator_options_do_not_change_pixels(scene, tmp_path):
                           ("nomat", {"specialize_matrices": 0}, {}), ("noints", {}, {"specialize_ints": False}),
                           ("rolled", {"unroll_loops": 0}, {}), ("blk128", {"block_threads": 128, "min_blocks": 4}, {}),
                           ("smem", {"uniforms_in_smem": 1}, {}), ("tile16", {"tile_w": 16}, {}),
+                          ("nocanon", {"canon_rays": 0}, {}), ("nowaware", {"w_aware": 0}, {}),
                           ("tile32", {"tile_w": 32, "block_threads": 256, "min_blocks": 4}, {})]:
         got, s2 = _run_on_host(tmp_path, tag, scene, options=opts, **kw)
         assert s2 != src or tag == "rolled"          # a scene without loops has nothing to keep rolled
