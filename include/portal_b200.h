@@ -179,7 +179,7 @@ PE_API int pe_host_free(pe_ctx* ctx, void* p);
 PE_API int pe_probe_ray(pe_ctx* ctx, const float a[3], const float b[3], float pos_out[3], int32_t* have_result,
                         int32_t* encounter_object, int32_t* change_subspace);
 /* Per-scene autotuning: render `target` with each of the launch / specialisation alternatives that keep the pixels (512- or
- * 1024-thread blocks, canonical rays on or off), `reps` times each into context-owned scratch, timed with CUDA events, and
+ * 1024-thread blocks, canonical rays and w-aware products on or off), `reps` times each into context-owned scratch, timed with CUDA events, and
  * keep the fastest as the context's setting.  Synchronous; the programs are compiled (or taken from the cache) as needed.
  * `report` (optional) receives one text line per candidate and the choice. */
 PE_API int pe_autotune(pe_ctx* ctx, const pe_target* target, int reps, char* report, size_t report_len);

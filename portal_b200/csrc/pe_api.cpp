@@ -1239,15 +1239,16 @@ int pe_scratch_buffer(pe_ctx* c, int slot, size_t bytes, void** out) {
 
 // Launch / specialisation alternatives that keep the pixels, tried on the scene and target at hand.  Which is fastest depends on
 // the scene's own code: the Moebius portal's Newton solver wants 1024-thread blocks (-11 %) and loses 3 % to the canonical-ray
-// split, the plane-heavy scenes want 512-thread blocks and gain 6-14 % from it (profiles/r02f_sweep_*.txt).
+// split, the plane-heavy scenes want 512-thread blocks and gain 6-14 % from it; w-aware products give the portal-chain loop of
+// portal_in_portal another 10 % and cost triple_portal 4 % (profiles/r02f_sweep_*.txt, r02h_sweep_w_aware.txt).
 int pe_autotune(pe_ctx* c, const pe_target* t, int reps, char* report, size_t report_len) {
     if (!c) return 1;
     if (report && report_len) report[0] = 0;
     if (!check_target(c, t) || !bind_device(c)) return 1;
     if (c->opts.persistent) return 0;                       // the persistent scheduler has its own geometry: nothing to try
     if (reps < 1) reps = 3;
-    struct Cand { int block_threads, min_blocks; bool canon; };
-    const Cand cands[] = {{512, 2, true}, {512, 2, false}, {1024, 1, true}, {1024, 1, false}};
+    struct Cand { int block_threads, min_blocks; bool canon, w_aware; };
+    const Cand cands[] = {{512, 2, true, true}, {512, 2, true, false}, {512, 2, false, false}, {1024, 1, true, true}, {1024, 1, false, false}};
     const GenOptions saved = c->opts;
     void* scratch = nullptr;
     const size_t bytes = (pe_target_pixels(t) ? pe_target_pixels(t) : 1) * 16;
@@ -1262,6 +1263,7 @@ int pe_autotune(pe_ctx* c, const pe_target* t, int reps, char* report, size_t re
         c->opts.block_threads = cands[k].block_threads;
         c->opts.min_blocks = cands[k].min_blocks;
         c->opts.canon_rays = cands[k].canon;
+        c->opts.w_aware = cands[k].w_aware;
         c->current = nullptr;
         if (render_impl(c, t, scratch, nullptr, nullptr, false)) { rc = 1; break; }            // compile / load + warm-up
         cudaEventRecord(e0, c->stream);
@@ -1272,8 +1274,8 @@ int pe_autotune(pe_ctx* c, const pe_target* t, int reps, char* report, size_t re
         cudaEventElapsedTime(&ms, e0, e1);
         ms /= float(reps);
         char line[160];
-        std::snprintf(line, sizeof line, "block_threads %d min_blocks %d canon_rays %d: %.4f ms\n", cands[k].block_threads, cands[k].min_blocks,
-                      cands[k].canon ? 1 : 0, ms);
+        std::snprintf(line, sizeof line, "block_threads %d min_blocks %d canon_rays %d w_aware %d: %.4f ms\n", cands[k].block_threads,
+                      cands[k].min_blocks, cands[k].canon ? 1 : 0, cands[k].w_aware ? 1 : 0, ms);
         rep += line;
         if (best < 0 || ms < best_ms * 0.99f) { best = k; best_ms = ms; }          // a later candidate must win by more than the noise
     }
@@ -1285,9 +1287,10 @@ int pe_autotune(pe_ctx* c, const pe_target* t, int reps, char* report, size_t re
     c->opts.block_threads = cands[best].block_threads;
     c->opts.min_blocks = cands[best].min_blocks;
     c->opts.canon_rays = cands[best].canon;
+    c->opts.w_aware = cands[best].w_aware;
     char line[160];
-    std::snprintf(line, sizeof line, "chosen: block_threads %d min_blocks %d canon_rays %d\n", cands[best].block_threads, cands[best].min_blocks,
-                  cands[best].canon ? 1 : 0);
+    std::snprintf(line, sizeof line, "chosen: block_threads %d min_blocks %d canon_rays %d w_aware %d\n", cands[best].block_threads,
+                  cands[best].min_blocks, cands[best].canon ? 1 : 0, cands[best].w_aware ? 1 : 0);
     rep += line;
     if (report && report_len) std::snprintf(report, report_len, "%s", rep.c_str());
     return 0;
