@@ -15,6 +15,7 @@
 // The reference has no counterpart (one GL context); the caller-side loop this serves is render_frame / the video loop,
 // /root/reference/src/main.rs:2876-2968.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sched.h>
 #include <sys/mman.h>
@@ -27,6 +28,7 @@
 #include <atomic>
 #include <cctype>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -74,10 +76,33 @@ bool spin_until(F cond) {
     return true;
 }
 
-// CPUs next to a GPU, from sysfs (no NVML): /sys/bus/pci/devices/<domain:bus:dev.fn>/local_cpulist
+// CPUs next to a GPU.  First NVML's own answer (nvmlDeviceGetCpuAffinity; the library is dlopen'ed, nothing is linked), then
+// sysfs: /sys/bus/pci/devices/<domain:bus:dev.fn>/local_cpulist (often hidden inside containers).
+bool gpu_local_cpus_nvml(const char* bdf, cpu_set_t* set) {
+    void* h = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return false;
+    using InitFn = int (*)();
+    using HandleFn = int (*)(const char*, void**);
+    using AffFn = int (*)(void*, unsigned, unsigned long*);
+    auto init = reinterpret_cast<InitFn>(dlsym(h, "nvmlInit_v2"));
+    auto byid = reinterpret_cast<HandleFn>(dlsym(h, "nvmlDeviceGetHandleByPciBusId_v2"));
+    auto aff = reinterpret_cast<AffFn>(dlsym(h, "nvmlDeviceGetCpuAffinity"));
+    void* dev = nullptr;
+    unsigned long mask[CPU_SETSIZE / (8 * sizeof(unsigned long))] = {0};
+    const unsigned words = unsigned(sizeof mask / sizeof mask[0]);
+    if (!init || !byid || !aff || init() != 0 || byid(bdf, &dev) != 0 || aff(dev, words, mask) != 0) return false;
+    CPU_ZERO(set);
+    int count = 0;
+    for (unsigned w = 0; w < words; w++)
+        for (unsigned b = 0; b < 8 * sizeof(unsigned long); b++)
+            if (mask[w] >> b & 1ul) { CPU_SET(int(w * 8 * sizeof(unsigned long) + b), set); count++; }
+    return count > 0;
+}
+
 bool gpu_local_cpus(int device, cpu_set_t* set) {
     char bdf[32] = {0};
     if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, device) != cudaSuccess) return false;
+    if (gpu_local_cpus_nvml(bdf, set)) return true;
     for (char* p = bdf; *p; p++) *p = char(std::tolower((unsigned char)*p));
     const std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/local_cpulist";
     FILE* f = std::fopen(path.c_str(), "r");
@@ -308,6 +333,9 @@ int pe_sharder_create(pe_ctx* ctx, const char* name, int width, int height, int 
             }
         }
         if (moved) sched_setaffinity(0, sizeof old, &old);
+        if (std::getenv("PORTAL_B200_DEBUG"))
+            std::fprintf(stderr, "[pe_sharder] rank %d: host ring pages first touched %s\n", rank,
+                         moved ? "from the CPUs next to its GPU" : "from wherever the process runs (no GPU-local CPU list found)");
         if (!barrier(s, 0)) return bail("pe_sharder_create: a rank failed or timed out during set-up");
         if (pe_host_register(ctx, s->map, s->map_bytes)) return bail(std::string("page-locking the frame ring: ") + pe_last_error(ctx));
         s->registered = true;
