@@ -506,21 +506,32 @@ def run_ours(args):
 
         LAG = D.NativeSharder.PIPELINE_DEPTH - 1     # a rank keeps this many frames in flight behind the one it submits
 
+        prof = {"uniforms": 0.0, "submit": 0.0, "complete": 0.0, "wait_frame": 0.0}
+        debug = bool(os.environ.get("PORTAL_B200_DEBUG"))
+
         def pipelined_n(n):
             k, fr, done = None, None, 0
 
             def finish(f, last):
+                t_ = time.perf_counter()
                 hs.complete(f)
+                prof["complete"] += time.perf_counter() - t_
                 if rank == 0:
+                    t_ = time.perf_counter()
                     v = hs.wait_frame(f, view=last)          # the whole frame f is in host memory: the consumer may read it
+                    prof["wait_frame"] += time.perf_counter() - t_
                     out = v.copy() if last else None
                     hs.release_frame(f)
                     return out
                 return None
             first = None
             for i in range(n):
+                t_ = time.perf_counter()
                 k = e2e_uniforms()
+                t1_ = time.perf_counter()
                 f = hs.submit()
+                prof["uniforms"] += t1_ - t_
+                prof["submit"] += time.perf_counter() - t1_
                 if first is None:
                     first = f
                 if i >= LAG:
@@ -539,6 +550,9 @@ def run_ours(args):
         e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         e2e_rate = w * h * e2e_steps / float(e2e_s.item()) / 1e6
+        if debug:
+            print(f"[bench] rank {rank}: e2e host time per frame (us): " + ", ".join(f"{k} {v / (e2e_steps + 2 * LAG + 2) * 1e6:.0f}" for k, v in prof.items()) +
+                  f"; period {float(e2e_s.item()) / e2e_steps * 1e6:.0f}", file=sys.stderr, flush=True)
         barrier()
         hs.close()
     if rank == 0:

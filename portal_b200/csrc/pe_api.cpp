@@ -139,6 +139,15 @@ struct pe_ctx {
     size_t scratch8_bytes = 0;
     uint64_t launches = 0;
     const DriverApi* drv = nullptr;
+    // Uniform uploads go through a ring of PINNED staging images: cuMemcpyHtoDAsync from pageable memory first synchronises the
+    // stream (CUDA's documented behaviour), which made every frame's upload wait for the previous frame's kernel -- the host
+    // could never run ahead, and the frame pipelines (pe_submit_host_*, two frames in flight) were serialised by it.
+    static constexpr int kStage = 16;
+    uint8_t* ustage = nullptr;
+    size_t ustage_stride = 0;
+    cudaEvent_t ustage_done[kStage] = {nullptr};
+    bool ustage_used[kStage] = {false};
+    int ustage_next = 0;
     struct Scratch { void* dev = nullptr; size_t bytes = 0; };
     std::map<int, Scratch> user_scratch;   // pe_scratch_buffer
 
@@ -620,6 +629,8 @@ void pe_destroy(pe_ctx* c) {
         }
         for (auto& kv : c->user_scratch)
             if (kv.second.dev) cudaFree(kv.second.dev);
+        if (c->ustage) cudaFreeHost(c->ustage);
+        for (auto& e : c->ustage_done) if (e) cudaEventDestroy(e);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         if (c->queue_dev) cudaFree(c->queue_dev);
         if (c->stream) cudaStreamDestroy(c->stream);
@@ -927,6 +938,31 @@ size_t pe_target_pixels(const pe_target* t) {
     return size_t(t->n_strips) * size_t(t->strip_rows) * size_t(t->width);
 }
 
+// Enqueue the upload of the host image of the uniform block to `dst` on stream `s`, from pinned staging memory.
+static bool upload_uniform_block(pe_ctx* c, CUdeviceptr_t dst, CUstream_t s) {
+    const size_t n = c->cblock.size();
+    const size_t stride = (n + 255) & ~size_t(255);
+    if (!c->ustage || c->ustage_stride < stride) {
+        if (c->ustage) { cudaDeviceSynchronize(); cudaFreeHost(c->ustage); c->ustage = nullptr; }
+        if (!cuda_ok(c, cudaHostAlloc(reinterpret_cast<void**>(&c->ustage), stride * pe_ctx::kStage, cudaHostAllocDefault), "cudaHostAlloc(uniform staging)")) return false;
+        c->ustage_stride = stride;
+        for (int k = 0; k < pe_ctx::kStage; k++) {
+            c->ustage_used[k] = false;
+            if (!c->ustage_done[k] && !cuda_ok(c, cudaEventCreateWithFlags(&c->ustage_done[k], cudaEventDisableTiming), "event")) return false;
+        }
+    }
+    const int k = c->ustage_next;
+    c->ustage_next = (k + 1) % pe_ctx::kStage;
+    if (c->ustage_used[k] && !cuda_ok(c, cudaEventSynchronize(c->ustage_done[k]), "uniform staging")) return false;   // 16 uploads ago: long done
+    uint8_t* src = c->ustage + size_t(k) * c->ustage_stride;
+    std::memcpy(src, c->cblock.data(), n);
+    CUresult_t r = c->drv->cuMemcpyHtoDAsync(dst, src, n, s);
+    if (r != 0) { c->err = "uniform block upload: " + driver_error(c->drv, r); return false; }
+    if (!cuda_ok(c, cudaEventRecord(c->ustage_done[k], (cudaStream_t)s), "event record")) return false;
+    c->ustage_used[k] = true;
+    return true;
+}
+
 static int render_impl(pe_ctx* c, const pe_target* t, void* out_device, void* bounces_device, void* stream, bool rgba8, int instance = 0) {
     if (!c) return 1;
     if (!out_device) return c->fail("pe_render: out_device is null");
@@ -955,8 +991,7 @@ static int render_impl(pe_ctx* c, const pe_target* t, void* out_device, void* bo
         kernel = v->kernel2;
         const_ptr = v->const_ptr2;
     }
-    r = d->cuMemcpyHtoDAsync(const_ptr, c->cblock.data(), c->cblock.size(), s);
-    if (r != 0) return c->fail("uniform block upload: " + driver_error(d, r));
+    if (!upload_uniform_block(c, const_ptr, s)) return 1;
 
     PeLaunchHost L;
     std::memset(&L, 0, sizeof L);
@@ -1041,7 +1076,7 @@ int pe_probe_ray(pe_ctx* c, const float a[3], const float b[3], float pos_out[3]
         CUstream_t s = (CUstream_t)c->stream;
         P = {a[0], a[1], a[2], b[0], b[1], b[2], c->scratch8_dev};
         void* args[] = {&P};
-        CUresult_t r = d->cuMemcpyHtoDAsync(v->const_ptr, c->cblock.data(), c->cblock.size(), s);
+        CUresult_t r = upload_uniform_block(c, v->const_ptr, s) ? 0 : 999;
         if (r == 0) r = d->cuLaunchKernel(v->probe, 1, 1, 1, 32, 1, 1, 0, s, args, nullptr);
         if (r != 0) { c->err = "pe_probe_kernel: " + driver_error(d, r); ok = false; }
         else {
