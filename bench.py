@@ -571,7 +571,7 @@ def run_ours(args):
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp) and world == 1:
+        if os.path.exists(tp) and world == 1 and not args.orbit:
             with open(tp) as f:
                 traffic = json.load(f).get(f"{args.scene}_{w}x{h}_d{depth}") if fmt == "f32" else None
         cpu = None
