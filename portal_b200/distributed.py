@@ -231,7 +231,7 @@ class NativeSharder:
         self._lib = renderer._lib
         self._s = C.c_void_p()
         if name is None:
-            name = shm_name(f"{mode}_{fmt}")
+            name = shm_name(f"{mode}_{fmt}", rank, world)
         rc = self._lib.pe_sharder_create(renderer._ctx, name.encode(), width, height, rank, world, strip_rows, self.MODES[mode],
                                          self.FORMATS[fmt], C.byref(self._s))
         if rc:
@@ -308,11 +308,20 @@ class NativeSharder:
 _shm_counter = [0]
 
 
-def shm_name(tag: str) -> str:
+def shm_name(tag: str, rank: int | None = None, world: int | None = None) -> str:
     """A segment name every rank of one launch derives alike: the launcher's rendezvous port + a per-process counter
     (ranks create their sharders in the same order)."""
     _shm_counter[0] += 1
-    solo = f"_pid{os.getpid()}" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else ""     # a lone process needs no agreement
+    import torch.distributed as dist
+    if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            and world == dist.get_world_size() and rank == dist.get_rank()):
+        # the sharder spans the process group: a launch that has torch.distributed up agrees on a fresh random name: a file a crashed earlier run left behind
+        # under a derived name can then never be opened by mistake.  Collective: every rank creates its sharders in the same order.
+        import uuid
+        box = [uuid.uuid4().hex[:16] if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return f"portal_b200_{box[0]}_{tag}"
+    solo = f"_pid{os.getpid()}" if int(os.environ.get("WORLD_SIZE", "1")) == 1 or world == 1 else ""     # a lone process needs no agreement
     return f"portal_b200_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}_{_shm_counter[0]}_{tag}{solo}"
 
 

@@ -21,6 +21,12 @@ struct float4 { float x, y, z, w; };
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline int __float2int_rz(float v) {          // cvt.rzi.s32.f32: truncating, saturating, NaN -> 0
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return 2147483647;
+    if (v <= -2147483648.0f) return -2147483647 - 1;
+    return int(v);
+}
 namespace pe { struct mat4; inline mat4 operator*(const mat4& a, const mat4& b); }
 static float _offset_after_material = 0.005f;
 static int _angle_color_disable = 0, _grid_disable = 0, _black_border_disable = 0;
