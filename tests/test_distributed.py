@@ -68,6 +68,12 @@ WORKER = textwrap.dedent("""
     t = torch.tensor([float(rank + 1)], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     assert t.item() == world
+    # the sharder's shared-memory segment name: every rank gets the SAME fresh name per sharder, a new one each time
+    names = [D.shm_name("owner_f32", rank, world), D.shm_name("owner_f32", rank, world)]
+    every = [None] * world
+    dist.all_gather_object(every, names)
+    assert all(n == every[0] for n in every) and names[0] != names[1], every
+    assert D.shm_name("solo", 0, 1).endswith(f"_pid{{os.getpid()}}")          # a one-rank sharder inside a larger group needs no agreement
     dist.barrier()
     dist.destroy_process_group()
     print("RANK_OK", rank)
