@@ -582,7 +582,7 @@ def run_ours(args):
                 traffic = json.load(f).get(f"{args.scene}_{w}x{h}_d{depth}") if fmt == "f32" else None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            res = cpu_oracle(args, budget_s=20.0)
+            res = cpu_oracle(args, budget_s=15.0, steps=0)       # about 15 s of wall on all host threads: whole passes over the frame when one is shorter
             res1 = cpu_oracle(args, budget_s=4.0, threads=1)
             cpu = {"value": round(res["value"], 4), "unit": "Mpixels/s", "cores": res["threads_used"], "kind": "port", "sample": res["sample"],
                    "single_thread_value": round(res1["value"], 4)}

@@ -52,7 +52,7 @@ def main():
     ap.add_argument("--depth", type=int, required=True)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--budget", type=float, default=20.0, help="seconds of CPU rendering to spend on the sample (all steps together)")
-    ap.add_argument("--steps", type=int, default=1, help="split the sample into this many timed steps (the reference arm's --steps)")
+    ap.add_argument("--steps", type=int, default=1, help="split the sample into this many timed steps (the reference arm's --steps); 0 = as many passes over the frame as fit --budget")
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--scene-dir", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "scenes"))
     args = ap.parse_args()
@@ -83,7 +83,7 @@ def main():
     t0 = time.perf_counter()
     orc.render(w, h, depth, rows=mid, threads=threads)                       # calibrate
     per_band = max(time.perf_counter() - t0, 1e-4)
-    steps = max(1, args.steps)
+    steps = args.steps if args.steps > 0 else max(1, int(args.budget / (per_band * max(1, h // B))))    # 0: as many whole frames as fit the budget
     per_step = int(max(1, min(h // B, args.budget / per_band / steps)))      # bands of one step: a bounded sample of the frame
     rates, px, dt = [], 0, 0.0
     for k in range(steps):
