@@ -180,8 +180,9 @@ PE_API int pe_probe_ray(pe_ctx* ctx, const float a[3], const float b[3], float p
                         int32_t* encounter_object, int32_t* change_subspace);
 /* Per-scene autotuning: render `target` with each of the launch / specialisation alternatives that keep the pixels (512- or
  * 1024-thread blocks, canonical rays and w-aware products on or off), `reps` times each into context-owned scratch, timed with CUDA events, and
- * keep the fastest as the context's setting.  Synchronous; the programs are compiled (or taken from the cache) as needed.
- * `report` (optional) receives one text line per candidate and the choice. */
+ * keep the fastest as the context's setting.  A candidate whose frame is not bit-identical to the first candidate's (the
+ * default variant's) is reported as REJECTED and never chosen.  Synchronous; the programs are compiled (or taken from the
+ * cache) as needed.  `report` (optional) receives one text line per candidate and the choice. */
 PE_API int pe_autotune(pe_ctx* ctx, const pe_target* target, int reps, char* report, size_t report_len);
 PE_API int pe_sync(pe_ctx* ctx);
 /* Number of kernel launches this context has issued (render + helper kernels). */
@@ -262,6 +263,11 @@ PE_API int pe_average_frames_rgba8(pe_ctx* ctx, const void* const* frames_device
                             size_t n_pixels, void* stream);
 /* float RGBA -> RGBA8, the render target's quantisation. Device pointers. */
 PE_API int pe_quantize_rgba8(pe_ctx* ctx, const void* rgba_f32_device, void* rgba8_device, size_t n_pixels, void* stream);
+/* Bit comparison of two device buffers (16-byte aligned, `bytes` a multiple of 16): *words_out = how many 16-byte words
+ * (= float RGBA pixels) differ.  Synchronous.  pe_autotune's guard uses it -- a candidate variant is only eligible when its
+ * frame is the first candidate's frame bit for bit -- and a caller can use it to compare frames without a read-back (the
+ * reference has no counterpart: its frames are compared by eye). */
+PE_API int pe_frames_differ(pe_ctx* ctx, const void* a_device, const void* b_device, size_t bytes, void* stream, uint32_t* words_out);
 
 #ifdef __cplusplus
 }

@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
         "pe_ipc_close": (i32, [vp, vp]),
         "pe_average_frames_rgba8": (i32, [vp, C.POINTER(vp), i32, vp, C.c_size_t, vp]),
         "pe_quantize_rgba8": (i32, [vp, vp, vp, C.c_size_t, vp]),
+        "pe_frames_differ": (i32, [vp, vp, vp, C.c_size_t, vp, C.POINTER(C.c_uint32)]),
         "pe_shard_target": (i32, [i32, i32, i32, i32, i32, i32, C.POINTER(PeTarget)]),
         "pe_sharder_create": (i32, [vp, cp, i32, i32, i32, i32, i32, i32, i32, C.POINTER(vp)]),
         "pe_sharder_destroy": (None, [vp]),

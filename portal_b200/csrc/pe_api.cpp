@@ -569,7 +569,7 @@ int pe_internal_render(pe_ctx* c, const pe_target* t, void* out_device, void* st
 
 extern "C" {
 
-int pe_abi_version(void) { return 101; }
+int pe_abi_version(void) { return 102; }
 
 pe_ctx* pe_create(int device) {
     std::lock_guard<std::mutex> lk(g_create_mutex);
@@ -1285,9 +1285,10 @@ int pe_autotune(pe_ctx* c, const pe_target* t, int reps, char* report, size_t re
     struct Cand { int block_threads, min_blocks; bool canon, w_aware; };
     const Cand cands[] = {{512, 2, true, true}, {512, 2, true, false}, {512, 2, false, false}, {1024, 1, true, true}, {1024, 1, false, false}};
     const GenOptions saved = c->opts;
-    void* scratch = nullptr;
+    void *scratch = nullptr, *first = nullptr;
     const size_t bytes = (pe_target_pixels(t) ? pe_target_pixels(t) : 1) * 16;
-    if (pe_scratch_buffer(c, 127, bytes, &scratch)) return 1;
+    // the guard: a candidate is only eligible if its frame is, bit for bit, the frame the first candidate (the default variant) gave
+    if (pe_scratch_buffer(c, 127, bytes, &scratch) || pe_scratch_buffer(c, 126, bytes, &first)) return 1;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (!cuda_ok(c, cudaEventCreate(&e0), "event") || !cuda_ok(c, cudaEventCreate(&e1), "event")) return 1;
     int best = -1;
@@ -1308,14 +1309,34 @@ int pe_autotune(pe_ctx* c, const pe_target* t, int reps, char* report, size_t re
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, e0, e1);
         ms /= float(reps);
-        char line[160];
-        std::snprintf(line, sizeof line, "block_threads %d min_blocks %d canon_rays %d w_aware %d: %.4f ms\n", cands[k].block_threads,
+        unsigned differing = 0;
+        if (k == 0) {
+            if (!cuda_ok(c, cudaMemcpyAsync(first, scratch, bytes, cudaMemcpyDeviceToDevice, c->stream), "autotune copy")) { rc = 1; break; }
+        } else if (pe_target_pixels(t)) {
+            if (pe_frames_differ(c, first, scratch, bytes, nullptr, &differing)) { rc = 1; break; }
+        }
+        char line[200];
+        std::snprintf(line, sizeof line, "block_threads %d min_blocks %d canon_rays %d w_aware %d: %.4f ms", cands[k].block_threads,
                       cands[k].min_blocks, cands[k].canon ? 1 : 0, cands[k].w_aware ? 1 : 0, ms);
         rep += line;
+        if (differing) {
+            std::snprintf(line, sizeof line, " REJECTED: %u pixels differ from the first candidate's frame", differing);
+            rep += line;
+        }
+        rep += "\n";
+        if (differing) continue;
         if (best < 0 || ms < best_ms * 0.99f) { best = k; best_ms = ms; }          // a later candidate must win by more than the noise
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    cudaDeviceSynchronize();
+    for (int slot : {126}) {                                  // the guard's copy of the first frame is not kept around
+        auto it = c->user_scratch.find(slot);
+        if (it != c->user_scratch.end()) {
+            if (it->second.dev) cudaFree(it->second.dev);
+            c->user_scratch.erase(it);
+        }
+    }
     c->opts = saved;
     c->current = nullptr;
     if (rc) return 1;
@@ -1328,6 +1349,23 @@ int pe_autotune(pe_ctx* c, const pe_target* t, int reps, char* report, size_t re
                   cands[best].min_blocks, cands[best].canon ? 1 : 0, cands[best].w_aware ? 1 : 0);
     rep += line;
     if (report && report_len) std::snprintf(report, report_len, "%s", rep.c_str());
+    return 0;
+}
+
+int pe_frames_differ(pe_ctx* c, const void* a, const void* b, size_t bytes, void* stream, uint32_t* words_out) {
+    if (!c || !a || !b || !words_out) return c ? c->fail("pe_frames_differ: null argument") : 1;
+    if ((bytes & 15) || (uintptr_t(a) & 15) || (uintptr_t(b) & 15)) return c->fail("pe_frames_differ: buffers must be 16-byte aligned and a multiple of 16 bytes long");
+    if (!bind_device(c)) return 1;
+    *words_out = 0;
+    if (bytes == 0) return 0;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    void* diff = nullptr;
+    if (pe_scratch_buffer(c, 125, 16, &diff)) return 1;
+    if (!cuda_ok(c, cudaMemsetAsync(diff, 0, 16, s), "pe_frames_differ") ||
+        !cuda_ok(c, (cudaError_t)launch_count_diff(a, b, bytes / 16, (unsigned*)diff, c->sm_count, s), "pe_frames_differ") ||
+        !cuda_ok(c, cudaMemcpyAsync(words_out, diff, 4, cudaMemcpyDeviceToHost, s), "pe_frames_differ") ||
+        !cuda_ok(c, cudaStreamSynchronize(s), "pe_frames_differ")) return 1;
+    c->launches++;
     return 0;
 }
 

@@ -188,6 +188,20 @@ int grid_for(size_t n, int sms) {
     return int(blocks);
 }
 
+// How many 16-byte words of two frames differ (bit comparison; pe_autotune's guard: a candidate variant must give the frame
+// the first candidate gave).  One atomicAdd per warp that saw a difference.
+__global__ void __launch_bounds__(256) pe_k_count_diff(const uint4* __restrict__ a, const uint4* __restrict__ b, size_t n16,
+                                                       unsigned* __restrict__ count) {
+    unsigned mine = 0;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += size_t(gridDim.x) * blockDim.x) {
+        const uint4 x = a[i], y = b[i];
+        mine += ((x.x ^ y.x) | (x.y ^ y.y) | (x.z ^ y.z) | (x.w ^ y.w)) != 0u;
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(count, mine);
+}
+
+
 }  // namespace
 
 namespace pe_host {
@@ -227,6 +241,11 @@ int launch_average_rgba8(const void* const* frames, int n_frames, void* out, siz
     const unsigned magic = n_frames > 1 ? unsigned(((1ull << 32) + unsigned(n_frames) - 1) / unsigned(n_frames)) : 0u;
     if (vec) pe_k_average_rgba8<<<grid_for((n + 3) / 4, sms), 256, 0, s>>>(fp, n_frames, magic, (uchar4*)out, n);
     else pe_k_average_rgba8_px<<<grid_for(n, sms), 256, 0, s>>>(fp, n_frames, (unsigned*)out, n);
+    return (int)cudaGetLastError();
+}
+
+int launch_count_diff(const void* a, const void* b, size_t n16, unsigned* count, int sms, cudaStream_t s) {
+    pe_k_count_diff<<<grid_for(n16, sms), 256, 0, s>>>((const uint4*)a, (const uint4*)b, n16, count);
     return (int)cudaGetLastError();
 }
 

@@ -10,5 +10,7 @@ int launch_deinterleave(const void* gathered, void* frame, int width, int height
                         int strips_per_rank, int sms, cudaStream_t s);
 int launch_signal(void* const* ptrs, int n, unsigned int value, cudaStream_t s);
 int launch_average_rgba8(const void* const* frames, int n_frames, void* out, size_t n_pixels, int sms, cudaStream_t s);
+// *count += number of 16-byte words in which a and b differ (bitwise); both 16-byte aligned
+int launch_count_diff(const void* a, const void* b, size_t n_words16, unsigned* count, int sms, cudaStream_t s);
 
 }  // namespace pe_host

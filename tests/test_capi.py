@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert exported <= set(declared), f"exported but undeclared: {sorted(exported - set(declared))}"
     for name in declared:
         assert getattr(lib, name)
-    assert lib.pe_abi_version() == 101      # 1.01: pe_sharder_*, anaglyph uniforms, tile_w
+    assert lib.pe_abi_version() == 102      # 1.02: + pe_frames_differ, pe_autotune's bit guard (1.01: pe_sharder_*, anaglyph uniforms, tile_w)
 
 
 def test_library_is_built_for_sm_100a():

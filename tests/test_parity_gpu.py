@@ -411,6 +411,50 @@ def test_streaming_kernels_ragged_and_unaligned(torch_cuda):
             assert (got[:off] == 7).all() and (got[off + n:] == 7).all(), (n, off, nf)
 
 
+def test_frames_differ_counts_words_exactly(torch_cuda):
+    """pe_frames_differ (the detector behind pe_autotune's guard): identical buffers -> 0; k scattered single-bit flips in
+    k distinct 16-byte words -> k, whichever of the four lanes of the word they are in; NaN bit patterns compare as bits."""
+    torch = torch_cuda
+    import ctypes as C
+    r = _renderer("basics")
+    rng = np.random.default_rng(5)
+    for n_words in (1, 31, 4096, 250_001):
+        a = rng.integers(0, 2**32, size=(n_words, 4), dtype=np.uint32)
+        a[0, 0] = 0x7FC00001                                    # a NaN with a payload: equal to itself here
+        b = a.copy()
+        k = min(n_words, 37)
+        where = rng.choice(n_words, size=k, replace=False)
+        for j, wd in enumerate(where):
+            b[wd, j % 4] ^= np.uint32(1 << (j % 32))
+        da, db = torch.from_numpy(a.view(np.int32)).cuda(), torch.from_numpy(b.view(np.int32)).cuda()
+        out = C.c_uint32(12345)
+        assert r._lib.pe_frames_differ(r._ctx, da.data_ptr(), da.data_ptr(), a.nbytes, None, C.byref(out)) == 0 and out.value == 0
+        assert r._lib.pe_frames_differ(r._ctx, da.data_ptr(), db.data_ptr(), a.nbytes, None, C.byref(out)) == 0 and out.value == k, (n_words, out.value, k)
+    assert r._lib.pe_frames_differ(r._ctx, da.data_ptr() + 4, db.data_ptr(), 16, None, C.byref(out)) != 0      # misaligned: refused
+    assert b"16-byte" in r._lib.pe_last_error(r._ctx)
+    r.close()
+
+
+def test_autotune_keeps_the_pixels(torch_cuda):
+    """pe_autotune times five variants of the scene program and keeps the fastest; every candidate's frame is compared with
+    the first candidate's on the device, so none is REJECTED here, and the frame rendered with the chosen variant is the
+    frame rendered before tuning, bit for bit (both schedulers' tests above pin that frame to the oracle)."""
+    import ctypes as C
+    for scene, (w, h) in (("portal_in_portal", (640, 360)), ("mobius_monoportal", (320, 180))):
+        r = _renderer(scene)
+        before = r.render_host(w, h).copy()
+        t = r.full_target(w, h)
+        buf = C.create_string_buffer(2048)
+        r._check(r._lib.pe_autotune(r._ctx, C.byref(t), 2, buf, len(buf)))
+        lines = buf.value.decode().strip().splitlines()
+        assert len(lines) == 6 and lines[-1].startswith("chosen: block_threads"), lines
+        assert not any("REJECTED" in ln for ln in lines), lines
+        assert lines[-1][len("chosen: "):] in [ln.split(":")[0] for ln in lines[:-1]]
+        after = r.render_host(w, h)
+        assert np.array_equal(_bits(before), _bits(after)), scene
+        r.close()
+
+
 def test_full_size_properties(torch_cuda):
     """BASELINE headline size (3840x2160, depth 40): size-independent checks + a band against the oracle."""
     scene, w, h = "portal_in_portal", 3840, 2160
