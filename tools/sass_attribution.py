@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--options", default="{}")
     ap.add_argument("--persistent", type=int, default=0)
     ap.add_argument("--top", type=int, default=40)
+    ap.add_argument("--ops", default="", help="comma-separated opcodes: add a table of source lines by executed instructions of these opcodes only (e.g. BSSY,BSYNC,BRA)")
     args = ap.parse_args()
     from portal_b200.renderer import SceneRenderer, load_scene_ir
     ir = load_scene_ir(os.path.join(ROOT, "tests", "golden", "scenes", f"{args.scene}.scene.json"))
@@ -127,6 +128,16 @@ def main():
     print("\n## share per innermost source line")
     for (f_, l_), c in by_line.most_common(args.top):
         print(f"{100 * c / total:6.2f}%  {f_[:30]:30s}:{l_:<5d} {text.get(f_, {}).get(l_, '')[:120]}")
+    if args.ops:
+        want = set(args.ops.split(","))
+        sel = collections.Counter()
+        for a, ins, st in seq:
+            if opcode(ins) in want:
+                sel[st[0] if st else ("?", 0)] += counts[a][1]
+        tot_s = sum(sel.values())
+        print(f"\n## source lines by {args.ops} only ({100 * tot_s / total:.2f}% of all executed instructions)")
+        for (f_, l_), c in sel.most_common(args.top):
+            print(f"{100 * c / total:6.2f}%  {f_[:30]:30s}:{l_:<5d} {text.get(f_, {}).get(l_, '')[:120]}")
     hot = by_sec.most_common(1)[0][0]
     print(f"\n## opcodes of `{hot}`")
     tot_h = sum(ops[hot].values())
