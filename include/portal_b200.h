@@ -218,7 +218,10 @@ PE_API int pe_ipc_close(pe_ctx* ctx, void* device_ptr);
 /* ---- sharded frames behind the C ABI --------------------------------------
  * One process per GPU, all on one box; the ranks rendezvous through the POSIX shared-memory segment /dev/shm/<name>
  * (no collective library).  Every rank calls pe_sharder_create with the same name / geometry / mode / format and its
- * own rank; rank 0 creates the segment.  Uniforms are set on the context as usual before each render / submit.
+ * own rank; rank 0 creates the segment (and unlinks it in pe_sharder_destroy).  `name` must be FRESH for every sharder: a
+ * file of the same name left behind by a run that died could be opened by a late rank before rank 0 has replaced it, so
+ * derive it from something the launch agrees on anew each time (a launcher-supplied random token; the Python wrapper has
+ * rank 0 broadcast one).  Uniforms are set on the context as usual before each render / submit.
  *   PE_SHARD_OWNER  each rank keeps the strips it renders in its own HBM (compact rows: pe_sharder_target); nothing moves.
  *   PE_SHARD_P2P    every rank's render kernel stores its pixels straight into rank 0's whole frame over NVLink (CUDA
  *                   IPC mapping); frame completion / buffer reuse are stream-ordered flag words.  After
