@@ -62,8 +62,16 @@ PE_API int ph_scene_camera(ph_scene* s, double look_at[3], double* alpha, double
                            double* offset_after_material);
 /* Texture k: name and file path as stored in the scene; returns 0 while k is in range. */
 PE_API int ph_scene_texture(ph_scene* s, int k, const char** name, const char** path);
-/* Counts: 0 objects, 1 materials, 2 intersection materials, 3 library entries, 4 textures. */
+/* Counts: 0 objects, 1 materials, 2 intersection materials, 3 library entries, 4 textures, 5 videos. */
 PE_API int ph_scene_count(ph_scene* s, int what);
+/* Video k (src/gui/video.rs:14-20): a sampler named like a texture (`<name>_tex` in the scene's GLSL, scene.rs:405-409,
+ * 709-711) whose image is one frame of a clip; `uniform_name` ("" = none) is the uniform in [0, 1] that selects it.
+ * Decoding the clip is the caller's (the reference shells out to ffmpeg, video.rs:65-110): upload frames with pe_set_texture. */
+PE_API int ph_scene_video(ph_scene* s, int k, const char** name, const char** path, const char** uniform_name);
+/* Which of `frame_count` frames video k shows in the scene's current state: VideoRuntime::update (src/main.rs:862-895),
+ * round((frame_count - 1) * clamp(uniform, 0, 1)).  Returns non-zero when there is nothing to show (no uniform, no value, no
+ * frames): the reference leaves the texture as it is then. */
+PE_API int ph_scene_video_frame(ph_scene* s, int k, uint64_t frame_count, uint64_t* index);
 
 /* Describe the scene program to a renderer context (pe_scene_begin ... pe_scene_declare_*),
  * i.e. what Scene::get_new_material hands to load_material.  Does not compile. */

@@ -389,6 +389,12 @@ class Scene:
             (it["name"], it["data"][0][0][0]) for it in ser.get("intersection_materials", [[]])[0]
         ]
         self.library = [(it["name"], it["data"][0][0]) for it in ser["library"][0]]
+        # videos (video.rs:14-20; scene_serialized.rs:1200-1210, after the library and before the stages): a video is one more
+        # sampler2D named like a texture (scene.rs:405-409, 709-711) whose image the host replaces per frame, chosen by a uniform
+        self.videos = []
+        for it in ser.get("videos", [[]])[0]:
+            d = it["data"]
+            self.videos.append((it["name"], d.get("path", ""), self._uniform_ref(d.get("uniform"))))
 
         # animation stages + dev stage (scene_serialized.rs:1286-1371): inline elements are inserted at load time
         self.stages = {}
@@ -434,6 +440,25 @@ class Scene:
                     self.matrices[mid] = self.matrices[a[1]]
             elif mname in self.dev_matrices:
                 self.matrices[mid] = self.dev_matrices[mname]
+
+    def video_frame_index(self, k: int, frame_count: int):
+        """VideoRuntime::update (main.rs:862-895): which of `frame_count` frames video k shows in the scene's current state --
+        round((count - 1) * clamp(uniform, 0, 1)), Rust's round (half away from zero); None when the video has no uniform,
+        the uniform has no value, or there are no frames (the texture is then left as it is)."""
+        uid = self.videos[k][2]
+        if uid is None or frame_count <= 0:
+            return None
+        v = self.get_uniform(uid)
+        if v is None:
+            return None
+        kind, val = v
+        f = (1.0 if val else 0.0) if kind == "bool" else float(val)      # From<AnyUniformResult> for f64 (uniform.rs:298-311)
+        f = min(max(f, 0.0), 1.0) if f == f else f
+        x = (frame_count - 1) * f
+        if x != x:                                                        # NaN: `NaN as usize` is 0
+            return 0
+        r = math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
+        return int(min(max(r, 0.0), float(frame_count - 1)))
 
     # ---------------------------------------------------------------- loading
     def _add_uniform(self, data, name=None) -> int:
@@ -898,7 +923,11 @@ def scene_ir(scene: Scene, scene_name: str, time: float = 0.0, stage: str | None
         "camera_scale": camera_scale(cm),
         "renderer": d,
         "skybox": scene.skybox,
-        "textures": [{"name": n, "path": p} for n, p in scene.textures],
+        # samplers = textures and videos, each name once (the BTreeSet of scene.rs:703-716); a video has no image file:
+        # its frames come from the caller (`video_frame_index` says which)
+        "textures": [{"name": n, "path": p} for n, p in scene.textures] +
+                    [{"name": n, "path": None, "video": True} for n, _, _ in scene.videos if n not in {t for t, _ in scene.textures}],
+        "videos": [{"name": n, "path": p, "uniform": (scene.uniform_names[u] if u is not None else None)} for n, p, u in scene.videos],
         "materials": [_material_ir(n, m) for n, m in scene.materials],
         "material_ids": scene.material_ids(),
         "objects": objects,

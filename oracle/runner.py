@@ -134,6 +134,8 @@ class Oracle:
                 arr = np.ascontiguousarray(textures[t["name"]], dtype=np.uint8)
                 self._keep.append(arr)
                 self.lib.pe_oracle_set_texture(slot, arr.ctypes.data, arr.shape[1], arr.shape[0])
+            else:       # the library is loaded once per process: without this a sampler bound by an earlier Oracle stays bound
+                self.lib.pe_oracle_set_texture(slot, None, 0, 0)
 
     def set_uniforms(self, overrides: dict | None = None):
         m, f, i = uniform_arrays(self.ir, overrides)

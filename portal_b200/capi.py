@@ -136,6 +136,8 @@ def lib() -> C.CDLL:
         "ph_scene_camera": (i32, [vp, f64p, f64p, f64p, f64p, f64p]),
         "ph_scene_texture": (i32, [vp, i32, C.POINTER(cp), C.POINTER(cp)]),
         "ph_scene_count": (i32, [vp, i32]),
+        "ph_scene_video": (i32, [vp, i32, C.POINTER(cp), C.POINTER(cp), C.POINTER(cp)]),
+        "ph_scene_video_frame": (i32, [vp, i32, C.c_uint64, C.POINTER(C.c_uint64)]),
         "ph_scene_build_program": (i32, [vp, vp]),
         "ph_scene_upload_uniforms": (i32, [vp, vp]),
         "ph_orbit_camera_matrix": (None, [f64p, C.c_double, C.c_double, C.c_double, f64p]),

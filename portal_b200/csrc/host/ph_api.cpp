@@ -206,6 +206,23 @@ int ph_scene_texture(ph_scene* s, int k, const char** name, const char** path) {
     return 0;
 }
 
+int ph_scene_video(ph_scene* s, int k, const char** name, const char** path, const char** uniform_name) {
+    if (!s || k < 0 || k >= int(s->scene.videos.size())) return 1;
+    const auto& v = s->scene.videos[size_t(k)];
+    if (name) *name = v.name.c_str();
+    if (path) *path = v.path.c_str();
+    if (uniform_name) *uniform_name = v.uniform >= 0 && v.uniform < int(s->scene.uniform_names.size()) ? s->scene.uniform_names[size_t(v.uniform)].c_str() : "";
+    return 0;
+}
+
+int ph_scene_video_frame(ph_scene* s, int k, uint64_t frame_count, uint64_t* index) {
+    if (!s || !index) return 1;
+    size_t i = 0;
+    if (!s->scene.video_frame(k, size_t(frame_count), i)) return 1;
+    *index = uint64_t(i);
+    return 0;
+}
+
 int ph_scene_count(ph_scene* s, int what) {
     if (!s) return -1;
     switch (what) {
@@ -214,6 +231,7 @@ int ph_scene_count(ph_scene* s, int what) {
         case 2: return int(s->scene.intersection_materials.size());
         case 3: return int(s->scene.library.size());
         case 4: return int(s->scene.textures.size());
+        case 5: return int(s->scene.videos.size());
     }
     return -1;
 }
@@ -248,6 +266,11 @@ int ph_scene_build_program(ph_scene* s, pe_ctx* ctx) {
     for (auto& im : sc.intersection_materials) rc |= pe_scene_add_intersection_material(ctx, im.first.c_str(), im.second.c_str());
     for (auto& e : s->table) rc |= pe_scene_declare_uniform(ctx, e.name.c_str(), e.type);
     for (auto& t : sc.textures) rc |= pe_scene_declare_texture(ctx, t.first.c_str());
+    for (auto& v : sc.videos) {                               // a video is a sampler too; a name both lists hold is declared once
+        bool dup = false;
+        for (auto& t : sc.textures) dup = dup || t.first == v.name;
+        if (!dup) rc |= pe_scene_declare_texture(ctx, v.name.c_str());
+    }
     if (!sc.skybox.empty()) rc |= pe_scene_set_skybox(ctx, sc.skybox.c_str());
     if (rc) return fail(s, std::string("scene description rejected: ") + pe_last_error(ctx));
     return 0;

@@ -486,6 +486,18 @@ struct Loader {
         if (const RonValue* libs = storage(root, "library", true))
             for (auto& it : libs->items)
                 if (it->get("name")) sc.library.emplace_back(it->get("name")->s, code_of(it->get("data")));
+        // videos (scene_serialized.rs:1200-1210: after the library, before the stages; an inline uniform gets its id here)
+        if (const RonValue* vs = storage(root, "videos", false))   // #[serde(default)], scene_serialized.rs:625-626
+            for (auto& it : vs->items) {
+                const RonValue* n = it->get("name");
+                const RonValue* d = it->get("data");
+                if (!n || !d) continue;
+                Scene::Video v;
+                v.name = n->s;
+                if (const RonValue* pth = d->get("path")) v.path = pth->s;
+                v.uniform = uniform_ref(d->get("uniform"));
+                sc.videos.push_back(v);
+            }
 
         // animation stages (scene_serialized.rs:1286-1360): inline elements are inserted now
         auto stage_anim = [&](const RonValue* v, bool is_matrix) {
@@ -733,6 +745,21 @@ bool Scene::init_stage(const std::string& name) {
 
 std::string Scene::matrix_uniform_stem(int id) const {
     return matrix_names[id].empty() ? "id" + std::to_string(id) : matrix_names[id];
+}
+
+bool Scene::video_frame(int k, size_t frame_count, size_t& index) {
+    if (k < 0 || k >= int(videos.size()) || videos[size_t(k)].uniform < 0 || frame_count == 0) return false;
+    int kind = 0;
+    double v = 0.0;
+    std::vector<int> visited;
+    if (!get_uniform(videos[size_t(k)].uniform, kind, v, visited)) return false;
+    if (v == v) v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);          // f64::clamp keeps NaN
+    const double last = double(frame_count - 1);
+    double x = std::round(last * v);                              // Rust's round: half away from zero, like std::round
+    if (!(x == x)) x = 0.0;                                        // `NaN as usize` is 0
+    x = x < 0.0 ? 0.0 : (x > last ? last : x);
+    index = size_t(x);
+    return true;
 }
 
 bool Scene::get_uniform(int id, int& kind, double& value, std::vector<int>& visited) {

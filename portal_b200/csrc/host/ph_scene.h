@@ -146,6 +146,12 @@ struct Scene {
     std::vector<SceneMaterial> materials;
     std::vector<std::pair<std::string, std::string>> intersection_materials, library, textures;  // (name, code|path)
     std::string skybox;  // texture name, empty = none
+    // Videos (video.rs:14-20): one more sampler2D each, named like a texture (scene.rs:405-409, 709-711); the host replaces its
+    // image per frame with the frame the uniform selects (main.rs:862-914).
+    struct Video { std::string name, path; int uniform = -1; };
+    std::vector<Video> videos;
+    // VideoRuntime::update (main.rs:862-895): round((count - 1) * clamp(uniform, 0, 1)); false = no uniform / no value / no frames
+    bool video_frame(int k, size_t frame_count, size_t& index);
     std::string error;
     std::map<std::string, Stage> stages;                 // animation stages by name
     std::map<int, Uniform> dev_uniforms;                 // dev stage: target id -> value

@@ -97,8 +97,23 @@ class HostScene:
             k += 1
         return out
 
+    def videos(self):
+        """(name, path, uniform name or None) per video: samplers whose image the caller replaces per frame (video.rs:14-20)."""
+        out = []
+        name, path, uni = C.c_char_p(), C.c_char_p(), C.c_char_p()
+        k = 0
+        while self._lib.ph_scene_video(self._s, k, C.byref(name), C.byref(path), C.byref(uni)) == 0:
+            out.append((name.value.decode(), path.value.decode(), uni.value.decode() or None))
+            k += 1
+        return out
+
+    def video_frame_index(self, k: int, frame_count: int):
+        """VideoRuntime::update (main.rs:862-895): the frame video k shows in the scene's current state, or None."""
+        idx = C.c_uint64()
+        return int(idx.value) if self._lib.ph_scene_video_frame(self._s, k, frame_count, C.byref(idx)) == 0 else None
+
     def counts(self) -> dict:
-        names = ["objects", "materials", "intersection_materials", "library", "textures"]
+        names = ["objects", "materials", "intersection_materials", "library", "textures", "videos"]
         return {n: self._lib.ph_scene_count(self._s, i) for i, n in enumerate(names)}
 
 

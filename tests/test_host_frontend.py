@@ -34,7 +34,7 @@ def test_fixture_scene_table_matches_oracle_frontend():
     ir = _oracle_ir(FIXTURE, "two_spheres")
     _assert_same_table(hs.uniform_table(), ir)
     assert hs.camera() == ir["cam"]
-    assert hs.counts() == {"objects": 10, "materials": 7, "intersection_materials": 1, "library": 2, "textures": 0}
+    assert hs.counts() == {"objects": 10, "materials": 7, "intersection_materials": 1, "library": 2, "textures": 0, "videos": 0}
     t = hs.uniform_table()
     assert t["steps_u"] == ("int", 7) and t["open_u"] == ("int", 1)
     assert t["lift_u"][1] == 0.5 + 0.25 * 2 + -(math.sin(0.6) * (1 / 4))

@@ -35,6 +35,9 @@ def _run_on_host(tmp_path, tag, scene, options=None, uniforms=None, specialize_i
     args = [str(d / "run"), str(d / "block.bin"), str(W), str(H), str(d / "out.f32")]
     tex = (load_tex(scene) or {}) if tex is None else tex
     for t in ir["textures"]:                                   # declaration order = slot order in the block
+        if t["name"] not in tex:                               # trailing samplers nobody bound (a video without frames): left
+            assert all(u["name"] not in tex for u in ir["textures"][ir["textures"].index(t):])   # unbound -> texture() is black
+            break
         arr = np.ascontiguousarray(tex[t["name"]], dtype=np.uint8)
         path = d / f"{t['name']}.rgba"
         path.write_bytes(arr.tobytes())
