@@ -136,6 +136,12 @@ PE_API int ph_player_select_camera(ph_player* p, const char* camera_name);
 /* SceneRenderer::update(memory, time): `time_seconds` is wall time; inside a real animation the formula
  * variable `time` becomes (time % duration) / duration and `total_time` adds the earlier animations. */
 PE_API int ph_player_update(ph_player* p, double time_seconds);
+/* Called after every update the player performs -- ph_player_update and each motion-blur sub-frame of
+ * ph_player_render_motion_blur_frame -- before the frame's uniforms are uploaded: the place of SceneRenderer::update's tail
+ * (src/main.rs:1536-1542), where the reference swaps in the current frame of every video (ph_scene_video_frame + pe_set_texture).
+ * Non-zero return aborts the call.  NULL removes the hook. */
+typedef int (*ph_update_hook)(void* user);
+PE_API int ph_player_set_update_hook(ph_player* p, ph_update_hook fn, void* user);
 /* Camera after the last update, float64: `_camera`, `_camera_mul_inv` (column-major), `_camera_in_subspace`,
  * `_camera_scale`; orbit[6] = look_at xyz, alpha, beta, r; times[2] = formula time, total_time. */
 PE_API int ph_player_camera(ph_player* p, double camera16[16], double camera_mul_inv16[16], int32_t* in_subspace,
@@ -172,6 +178,20 @@ PE_API int ph_player_render_frame(ph_player* pl, pe_ctx* ctx, const ph_frame_par
 PE_API int ph_player_render_motion_blur_frame(ph_player* pl, pe_ctx* ctx, const ph_frame_params* p, int frame_index,
                                               int frame_count, int motion_blur_frames, double duration_seconds,
                                               uint8_t* out_host_rgba8);
+
+/* ---- image files either side of the path ------------------------------------------------------------------------
+ * Textures reach the reference as PNG files (Texture2D::from_file_with_format, src/main.rs:1066-1085) and frames leave it as
+ * PNG (Image::export_png, src/main.rs:2939-2943).  No libpng / zlib in the image: the codec is written out in
+ * portal_b200/csrc/host/ph_png.cpp (RFC 2083 / 1950 / 1951).  Host-side only.
+ * ph_png_decode: PNG bytes -> malloc'ed RGBA8 (top row first, w * h * 4 bytes; free with ph_png_free).  Colour types 0/2/3/4/6 at
+ * <= 8 bits per sample, tRNS honoured, non-interlaced; anything else fails with a message in `err`.
+ * ph_png_encode_rgba8: RGBA8 -> malloc'ed PNG file image (colour type 6, adaptive filters, LZ77 + fixed Huffman). */
+PE_API int ph_png_decode(const uint8_t* png, size_t len, uint8_t** rgba_out, int32_t* width, int32_t* height, char* err, size_t err_len);
+PE_API int ph_png_encode_rgba8(const uint8_t* rgba, int32_t width, int32_t height, uint8_t** png_out, size_t* len_out);
+PE_API void ph_png_free(uint8_t* p);
+/* Where the frames of a video live: "video_png/<file stem of path>" (video_frames_dir, src/main.rs:787-792); returns the length
+ * written (0 = the path has no file name). */
+PE_API int ph_video_frames_dir(const char* video_path, char* out, size_t out_len);
 
 #ifdef __cplusplus
 }

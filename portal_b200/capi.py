@@ -136,6 +136,11 @@ def lib() -> C.CDLL:
         "ph_scene_camera": (i32, [vp, f64p, f64p, f64p, f64p, f64p]),
         "ph_scene_texture": (i32, [vp, i32, C.POINTER(cp), C.POINTER(cp)]),
         "ph_scene_count": (i32, [vp, i32]),
+        "ph_player_set_update_hook": (i32, [vp, vp, vp]),
+        "ph_png_decode": (i32, [vp, C.c_size_t, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), cp, C.c_size_t]),
+        "ph_png_encode_rgba8": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+        "ph_png_free": (None, [vp]),
+        "ph_video_frames_dir": (i32, [cp, cp, C.c_size_t]),
         "ph_scene_video": (i32, [vp, i32, C.POINTER(cp), C.POINTER(cp), C.POINTER(cp)]),
         "ph_scene_video_frame": (i32, [vp, i32, C.c_uint64, C.POINTER(C.c_uint64)]),
         "ph_scene_build_program": (i32, [vp, vp]),

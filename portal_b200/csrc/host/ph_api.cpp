@@ -1,5 +1,8 @@
 // C API of the host front-end (include/portal_b200_host.h).
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iterator>
 #include <string>
@@ -7,6 +10,7 @@
 
 #include "../../../include/portal_b200_host.h"
 #include "ph_anim.h"
+#include "ph_png.h"
 #include "ph_scene.h"
 
 struct ph_scene {
@@ -22,6 +26,8 @@ struct ph_player {
     ph::Player player;
     pe_ctx* ctx = nullptr;
     std::string err;
+    ph_update_hook hook = nullptr;      // the caller's per-update work (video frames): SceneRenderer::update's tail, main.rs:1536-1542
+    void* hook_user = nullptr;
     explicit ph_player(ph_scene* sc) : s(sc), player(sc->scene) {}
 };
 
@@ -443,7 +449,16 @@ int ph_player_select_camera(ph_player* p, const char* name) {
 int ph_player_update(ph_player* p, double t) {
     if (!p) return 1;
     p->player.error.clear();
-    return p->player.update(t) ? 0 : pfail(p, p->player.error);
+    if (!p->player.update(t)) return pfail(p, p->player.error);
+    if (p->hook && p->hook(p->hook_user)) return pfail(p, "the update hook failed");
+    return 0;
+}
+
+int ph_player_set_update_hook(ph_player* p, ph_update_hook fn, void* user) {
+    if (!p) return 1;
+    p->hook = fn;
+    p->hook_user = user;
+    return 0;
 }
 
 int ph_player_camera(ph_player* p, double camera16[16], double inv16[16], int32_t* in_subspace, double* scale, double orbit[6],
@@ -573,6 +588,7 @@ int ph_player_render_motion_blur_frame(ph_player* pl, pe_ctx* ctx, const ph_fram
         ph_frame_params q = *p;
         q.aa_start = j;  // main.rs:1797
         if (!pl->player.update(tt * duration_seconds)) { pl->err = pl->player.error; rc = 1; break; }   // self.update(memory, t * duration)
+        if (pl->hook && pl->hook(pl->hook_user)) { pl->err = "the update hook failed"; rc = 1; break; }   // ... whose tail swaps video frames
         const ph::OrbitCam& c = pl->player.cam;
         if (ph_scene_upload_uniforms(pl->s, ctx) || upload_renderer_uniforms_cam(pl->s, ctx, &q, c.get_matrix(), c.teleport_matrix, c.in_subspace)) {
             pl->err = pl->s->err;
@@ -589,6 +605,55 @@ int ph_player_render_motion_blur_frame(ph_player* pl, pe_ctx* ctx, const ph_fram
         rc = 1;
     }
     return rc ? 1 : 0;
+}
+
+// ---- image files (ph_png.cpp)
+int ph_png_decode(const uint8_t* png, size_t len, uint8_t** rgba_out, int32_t* width, int32_t* height, char* err, size_t err_len) {
+    if (err && err_len) err[0] = 0;
+    if (!png || !rgba_out || !width || !height) return 1;
+    *rgba_out = nullptr;
+    std::vector<uint8_t> px;
+    std::string e;
+    int w = 0, h = 0;
+    if (!ph::png_decode(png, len, px, w, h, e)) {
+        if (err && err_len) std::snprintf(err, err_len, "%s", e.c_str());
+        return 1;
+    }
+    uint8_t* p = static_cast<uint8_t*>(std::malloc(px.size() ? px.size() : 1));
+    if (!p) return 1;
+    std::memcpy(p, px.data(), px.size());
+    *rgba_out = p;
+    *width = w;
+    *height = h;
+    return 0;
+}
+
+int ph_png_encode_rgba8(const uint8_t* rgba, int32_t width, int32_t height, uint8_t** png_out, size_t* len_out) {
+    if (!rgba || !png_out || !len_out || width <= 0 || height <= 0) return 1;
+    std::vector<uint8_t> out;
+    ph::png_encode_rgba8(rgba, width, height, out);
+    uint8_t* p = static_cast<uint8_t*>(std::malloc(out.size()));
+    if (!p) return 1;
+    std::memcpy(p, out.data(), out.size());
+    *png_out = p;
+    *len_out = out.size();
+    return 0;
+}
+
+void ph_png_free(uint8_t* p) { std::free(p); }
+
+int ph_video_frames_dir(const char* video_path, char* out, size_t out_len) {
+    if (!video_path || !out || !out_len) return 0;
+    std::string p = video_path;
+    while (!p.empty() && p.back() == '/') p.pop_back();             // Path::file_stem ignores trailing separators
+    const size_t slash = p.rfind('/');
+    std::string name = slash == std::string::npos ? p : p.substr(slash + 1);
+    if (name.empty() || name == "." || name == "..") { out[0] = 0; return 0; }
+    const size_t dot = name.rfind('.');
+    if (dot != std::string::npos && dot != 0) name = name.substr(0, dot);    // ".hidden" keeps its whole name, like Path::file_stem
+    const std::string dir = "video_png/" + name;
+    std::snprintf(out, out_len, "%s", dir.c_str());
+    return int(std::min(dir.size(), out_len - 1));
 }
 
 }  // extern "C"

@@ -3,16 +3,20 @@
 //
 //   portal_b200_render render-frame <scene.ron> [--width W] [--height H] [--render-depth D] [--aa-count N]
 //                      [--time T] [--stage NAME] [--animation NAME] [--camera NAME] [--device K]
-//                      [--texture name=file.rgba:WxH ...] [--output out.ppm]
+//                      [--texture name=file.png | name=file.rgba:WxH ...] [--assets DIR] [--output out.png|.ppm|.rgba]
 //   portal_b200_render render <scene.ron> [--animations a,b,... | --starts-with PREFIX] [--fps N] [--motion-blur-frames M] [--width W]
 //                      [--height H] [--render-depth D] [--aa-count N] [--stereo-image] [--no-skip-existing] [--out-dir DIR] [--max-frames K]
 //                      (`portal render`, main.rs:2808-2873 -> render_named_animations :1876-1930 ->
 //                       render_animation :1757-1830; frames are written as DIR/<animation>/frame_<i>.ppm, the
 //                       ffmpeg step is out of scope)
 //
-// Output: binary PPM (P6) of the RGBA8 frame the reference would hand to export_png (alpha dropped), or
-// raw RGBA8 with a .rgba extension.  PNG encode/decode is out of scope: textures
-// are passed as raw RGBA8 files.
+// Output: the RGBA8 frame the reference hands to export_png (main.rs:2939-2943) as a PNG when the name ends in .png
+// (ph_png_encode_rgba8), as raw RGBA8 for .rgba, else as a binary PPM (P6, alpha dropped).  Textures: every texture of the
+// scene is loaded from its stored path (a PNG, relative to --assets, default the working directory) like reload_textures
+// (main.rs:1066-1085) -- a file that cannot be read is reported and the sampler stays unbound, as there; --texture overrides one
+// by name (PNG, or raw RGBA8 with :WxH).  Videos: the frames of video_png/<stem>/*.png, sorted, the one the video's uniform
+// selects swapped in after every update (VideoRuntime, main.rs:771-930).
+#include <dirent.h>
 #include <sys/stat.h>
 #include <sys/types.h>
 
@@ -20,7 +24,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <fstream>
+#include <map>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -35,16 +41,86 @@ static std::string slurp(const std::string& path, bool& ok) {
     return ss.str();
 }
 
+static bool ends_with(const std::string& s, const char* suffix) {
+    const size_t n = std::strlen(suffix);
+    return s.size() >= n && s.compare(s.size() - n, n, suffix) == 0;
+}
+
 static bool write_image(const std::string& output, const std::vector<uint8_t>& px, int width, int height) {
     std::ofstream out(output, std::ios::binary);
     if (!out) return false;
-    if (output.size() > 5 && output.substr(output.size() - 5) == ".rgba") {
+    if (ends_with(output, ".png")) {             // Image::export_png (main.rs:2939-2943)
+        uint8_t* png = nullptr;
+        size_t n = 0;
+        if (ph_png_encode_rgba8(px.data(), width, height, &png, &n)) return false;
+        out.write(reinterpret_cast<const char*>(png), std::streamsize(n));
+        ph_png_free(png);
+    } else if (ends_with(output, ".rgba")) {
         out.write(reinterpret_cast<const char*>(px.data()), std::streamsize(px.size()));
     } else {
         out << "P6\n" << width << " " << height << "\n255\n";
         for (size_t i = 0; i < size_t(width) * size_t(height); i++) out.write(reinterpret_cast<const char*>(&px[4 * i]), 3);
     }
     return bool(out);
+}
+
+// One PNG file -> the sampler `name` (Texture2D::from_file_with_format + material.set_texture, main.rs:1072-1078)
+static bool set_texture_from_png(pe_ctx* ctx, const std::string& name, const std::string& path, std::string& why) {
+    bool ok = false;
+    const std::string bytes = slurp(path, ok);
+    if (!ok) { why = "cannot read " + path; return false; }
+    uint8_t* px = nullptr;
+    int32_t w = 0, h = 0;
+    char err[256] = {0};
+    if (ph_png_decode(reinterpret_cast<const uint8_t*>(bytes.data()), bytes.size(), &px, &w, &h, err, sizeof err)) { why = path + ": " + err; return false; }
+    const int rc = pe_set_texture(ctx, name.c_str(), px, w, h);
+    ph_png_free(px);
+    if (rc) { why = pe_last_error(ctx); return false; }
+    return true;
+}
+
+// VideoRuntime (main.rs:771-930): the sorted PNG frames of one video and the frame last uploaded
+struct VideoRuntime {
+    int video = 0;
+    std::string name;
+    std::vector<std::string> frames;
+    long last = -1;
+};
+struct VideoState {
+    ph_scene* scene = nullptr;
+    pe_ctx* ctx = nullptr;
+    std::vector<VideoRuntime> videos;
+};
+
+// video_collect_frame_files (main.rs:795-817): every *.png of video_png/<stem>, sorted by path
+static std::vector<std::string> video_frame_files(const std::string& assets, const char* video_path) {
+    std::vector<std::string> files;
+    char rel[1024];
+    if (!ph_video_frames_dir(video_path, rel, sizeof rel)) return files;
+    const std::string dir = assets.empty() ? std::string(rel) : assets + "/" + rel;
+    if (DIR* d = ::opendir(dir.c_str())) {
+        while (const dirent* e = ::readdir(d)) {
+            const std::string f = e->d_name;
+            if (ends_with(f, ".png")) files.push_back(dir + "/" + f);
+        }
+        ::closedir(d);
+    }
+    std::sort(files.begin(), files.end());
+    return files;
+}
+
+// VideoRuntime::update for every video (main.rs:862-914); the player calls it after each update (ph_player_set_update_hook)
+static int update_videos(void* user) {
+    VideoState& st = *static_cast<VideoState*>(user);
+    for (VideoRuntime& v : st.videos) {
+        uint64_t idx = 0;
+        if (ph_scene_video_frame(st.scene, v.video, v.frames.size(), &idx)) continue;
+        if (long(idx) == v.last) continue;                     // avoid a reload when the frame did not change
+        std::string why;
+        if (!set_texture_from_png(st.ctx, v.name, v.frames[size_t(idx)], why)) continue;   // IO errors are ignored there too: the texture just does not update
+        v.last = long(idx);
+    }
+    return 0;
 }
 
 static bool file_exists(const std::string& path) {
@@ -68,7 +144,7 @@ int main(int argc, char** argv) {
     const bool anim_cmd = argc >= 3 && std::strcmp(argv[1], "render") == 0;
     if (!frame_cmd && !anim_cmd) {
         std::fprintf(stderr, "usage: %s render-frame <scene.ron> [--width W] [--height H] [--render-depth D] [--aa-count N] [--time T] "
-                             "[--stage NAME] [--animation NAME] [--camera NAME] [--device K] [--texture name=file.rgba:WxH] [--output out.ppm]\n"
+                             "[--stage NAME] [--animation NAME] [--camera NAME] [--device K] [--texture name=file.png|name=file.rgba:WxH] [--assets DIR] [--output out.png|.ppm|.rgba]\n"
                              "       %s render <scene.ron> [a,b | --animations a,b | --starts-with PREFIX] [--fps N] [--motion-blur-frames M] [--width W] [--height H] "
                              "[--render-depth D] [--aa-count N] [--stereo-image] [--no-skip-existing] [--out-dir DIR] [--max-frames K]\n", argv[0], argv[0]);
         return 2;
@@ -80,7 +156,7 @@ int main(int argc, char** argv) {
     bool stereo = false, skip_existing = true;
     double time = 0.0;
     std::vector<std::string> textures;
-    std::string stage, animation, camera, animations, starts_with;
+    std::string stage, animation, camera, animations, starts_with, assets;
     int first_option = 3;
     if (anim_cmd && argc > 3 && std::strncmp(argv[3], "--", 2) != 0) animations = argv[first_option++];   // `render <scene> [animations]`
     for (int i = first_option; i < argc; i++) {
@@ -105,6 +181,7 @@ int main(int argc, char** argv) {
         else if (a == "--no-skip-existing" || a == "--no_skip_existing") skip_existing = false;
         else if (a == "--output") output = next();
         else if (a == "--texture") textures.push_back(next());
+        else if (a == "--assets") assets = next();
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     bool ok = false;
@@ -134,17 +211,49 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "%s\n", ph_scene_last_error(scene));
         return 1;
     }
-    for (const std::string& t : textures) {  // name=file.rgba:WxH
+    std::map<std::string, bool> given;
+    for (const std::string& t : textures) {  // name=file.png | name=file.rgba:WxH
         size_t eq = t.find('='), colon = t.rfind(':'), x = t.rfind('x');
+        if (eq != std::string::npos && ends_with(t, ".png")) {
+            std::string why;
+            if (!set_texture_from_png(ctx, t.substr(0, eq), t.substr(eq + 1), why)) { std::fprintf(stderr, "texture %s: %s\n", t.c_str(), why.c_str()); return 1; }
+            given[t.substr(0, eq)] = true;
+            continue;
+        }
         if (eq == std::string::npos || colon == std::string::npos || x == std::string::npos || x < colon) { std::fprintf(stderr, "bad --texture %s\n", t.c_str()); return 2; }
+        given[t.substr(0, eq)] = true;
         int tw = std::atoi(t.substr(colon + 1, x - colon - 1).c_str()), th = std::atoi(t.substr(x + 1).c_str());
         bool tok = false;
         std::string bytes = slurp(t.substr(eq + 1, colon - eq - 1), tok);
         if (!tok || bytes.size() != size_t(tw) * size_t(th) * 4) { std::fprintf(stderr, "texture %s: cannot read / wrong size\n", t.c_str()); return 1; }
         if (pe_set_texture(ctx, t.substr(0, eq).c_str(), reinterpret_cast<const uint8_t*>(bytes.data()), tw, th)) { std::fprintf(stderr, "%s\n", pe_last_error(ctx)); return 1; }
     }
+    // reload_textures (main.rs:1066-1085): every texture of the scene from its stored path; a failure is reported, the render goes on
+    for (int k = 0;; k++) {
+        const char *name = nullptr, *path = nullptr;
+        if (ph_scene_texture(scene, k, &name, &path)) break;
+        if (given.count(name)) continue;
+        const std::string file = assets.empty() || (path[0] == '/') ? std::string(path) : assets + "/" + path;
+        std::string why;
+        if (!set_texture_from_png(ctx, name, file, why)) std::fprintf(stderr, "texture `%s`: %s (the sampler stays unbound)\n", name, why.c_str());
+    }
     if (pe_scene_compile(ctx)) { std::fprintf(stderr, "%s\n", pe_last_error(ctx)); return 1; }
     ph_player_attach(player, ctx);  // camera teleportation goes through pe_probe_ray
+    // VideoRuntime::from_scene (main.rs:820-858): videos that have a path, a uniform and frames on disk
+    VideoState video_state;
+    video_state.scene = scene;
+    video_state.ctx = ctx;
+    for (int k = 0;; k++) {
+        const char *name = nullptr, *path = nullptr, *uniform = nullptr;
+        if (ph_scene_video(scene, k, &name, &path, &uniform)) break;
+        if (!path[0] || !uniform[0]) continue;
+        VideoRuntime v;
+        v.video = k;
+        v.name = name;
+        v.frames = video_frame_files(assets, path);
+        if (!v.frames.empty()) video_state.videos.push_back(v);
+    }
+    if (!video_state.videos.empty()) ph_player_set_update_hook(player, update_videos, &video_state);
     if (stereo) {                   // `render --stereo-image`: side-by-side eyes, doubled width (main.rs:2809-2816, 2842)
         width *= 2;
         ph_player_set_stereo(player, 1, 0.07, 0);

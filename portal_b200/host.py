@@ -327,3 +327,33 @@ class HostRenderer:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------ image files either side of the path
+def png_decode(data: bytes) -> np.ndarray:
+    """PNG file image -> uint8 [h, w, 4] (Texture2D::from_file_with_format, main.rs:1066-1085): ph_png_decode."""
+    lib = capi.lib()
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data) if data else (C.c_uint8 * 1)()
+    out, w, h = C.c_void_p(), C.c_int32(), C.c_int32()
+    err = C.create_string_buffer(512)
+    if lib.ph_png_decode(buf, len(data), C.byref(out), C.byref(w), C.byref(h), err, len(err)):
+        raise PortalB200Error("png: " + err.value.decode(errors="replace"))
+    try:
+        return np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(h.value, w.value, 4)).copy()
+    finally:
+        lib.ph_png_free(out)
+
+
+def png_encode(rgba8: np.ndarray) -> bytes:
+    """uint8 [h, w, 4] -> PNG file image (Image::export_png, main.rs:2939-2943): ph_png_encode_rgba8."""
+    lib = capi.lib()
+    arr = np.ascontiguousarray(rgba8, dtype=np.uint8)
+    if arr.ndim != 3 or arr.shape[2] != 4:
+        raise ValueError("frame must be [h, w, 4] uint8")
+    out, n = C.c_void_p(), C.c_size_t()
+    if lib.ph_png_encode_rgba8(arr.ctypes.data, arr.shape[1], arr.shape[0], C.byref(out), C.byref(n)):
+        raise PortalB200Error("png: cannot encode")
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        lib.ph_png_free(out)
