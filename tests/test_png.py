@@ -160,3 +160,18 @@ def test_video_frames_dir_rule():
                        ("x/.hidden", "video_png/.hidden"), ("dir/", "video_png/dir"), ("", "")):
         n = lib.ph_video_frames_dir(path.encode(), buf, len(buf))
         assert buf.value.decode() == want and n == len(want), path
+
+
+def test_codec_survives_damage_under_sanitizers(tmp_path):
+    """tests/host_harness/sanitize_png.cpp built with AddressSanitizer + UndefinedBehaviorSanitizer: round trips, every prefix
+    and thousands of mutated files (chunk CRCs repaired, so the damage reaches inflate / filters / palettes) -- no report."""
+    import subprocess
+    from conftest import ROOT
+    host = os.path.join(ROOT, "portal_b200", "csrc", "host")
+    exe = str(tmp_path / "sanitize_png")
+    cc = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-I", host,
+                         os.path.join(ROOT, "tests", "host_harness", "sanitize_png.cpp"), os.path.join(host, "ph_png.cpp"), "-o", exe],
+                        capture_output=True, text=True, timeout=600)
+    assert cc.returncode == 0, cc.stderr[-3000:]
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0 and "no crash" in run.stdout and "runtime error" not in run.stderr and "AddressSanitizer" not in run.stderr, (run.stdout + run.stderr)[-3000:]
