@@ -6,8 +6,9 @@
 //                      [--texture name=file.png | name=file.rgba:WxH ...] [--assets DIR] [--output out.png|.ppm|.rgba]
 //   portal_b200_render render <scene.ron> [--animations a,b,... | --starts-with PREFIX] [--fps N] [--motion-blur-frames M] [--width W]
 //                      [--height H] [--render-depth D] [--aa-count N] [--stereo-image] [--no-skip-existing] [--out-dir DIR] [--max-frames K]
+//                      [--frame-format ppm|png|rgba] [--assets DIR]
 //                      (`portal render`, main.rs:2808-2873 -> render_named_animations :1876-1930 ->
-//                       render_animation :1757-1830; frames are written as DIR/<animation>/frame_<i>.ppm, the
+//                       render_animation :1757-1830; frames are written as DIR/<animation>/frame_<i>.<format>, the
 //                       ffmpeg step is out of scope)
 //
 // Output: the RGBA8 frame the reference hands to export_png (main.rs:2939-2943) as a PNG when the name ends in .png
@@ -156,7 +157,7 @@ int main(int argc, char** argv) {
     bool stereo = false, skip_existing = true;
     double time = 0.0;
     std::vector<std::string> textures;
-    std::string stage, animation, camera, animations, starts_with, assets;
+    std::string stage, animation, camera, animations, starts_with, assets, frame_ext = ".ppm";
     int first_option = 3;
     if (anim_cmd && argc > 3 && std::strncmp(argv[3], "--", 2) != 0) animations = argv[first_option++];   // `render <scene> [animations]`
     for (int i = first_option; i < argc; i++) {
@@ -182,6 +183,7 @@ int main(int argc, char** argv) {
         else if (a == "--output") output = next();
         else if (a == "--texture") textures.push_back(next());
         else if (a == "--assets") assets = next();
+        else if (a == "--frame-format") frame_ext = std::string(".") + next();          // render: ppm (default) | png | rgba
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     bool ok = false;
@@ -302,12 +304,12 @@ int main(int argc, char** argv) {
             if (count < 1) count = 1;
             const int todo = max_frames >= 0 && max_frames < count ? max_frames : count;
             for (int i = 0; i < todo; i++) {
-                if (skip_existing && file_exists(dir + "/frame_" + std::to_string(i) + ".ppm")) continue;   // resumes like main.rs:1789-1793
+                if (skip_existing && file_exists(dir + "/frame_" + std::to_string(i) + frame_ext)) continue;   // resumes like main.rs:1789-1793
                 if (ph_player_render_motion_blur_frame(player, ctx, &p, i, count, motion_blur, double(duration32), px.data())) {
                     std::fprintf(stderr, "%s\n", ph_player_last_error(player));
                     return 1;
                 }
-                const std::string name = dir + "/frame_" + std::to_string(i) + ".ppm";
+                const std::string name = dir + "/frame_" + std::to_string(i) + frame_ext;
                 if (!write_image(name, px, width, height)) { std::fprintf(stderr, "cannot write %s\n", name.c_str()); return 1; }
                 std::printf("\r%d/%d done      ", i + 1, count);
                 std::fflush(stdout);
